@@ -1,0 +1,107 @@
+"""Import the reference's library modules UNMODIFIED from /root/reference under the TF stub.
+
+TEST INFRASTRUCTURE ONLY.  Used by `oracle/make_golden.py` (run in the build container,
+where /root/reference exists) and by the `-m "not gpu"` tests that cross-check the oracle
+against the live reference when it is present (they skip otherwise).  Nothing in the
+product path, `-m gpu` tests, `smoke()` or `bench.py` may import this module: the
+reference tree does not exist on the GPU box.
+
+No reference source is copied: modules are executed from where they lie.
+"""
+import ast
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+REF_ROOT = os.environ.get("DENSEHEAD_REFERENCE", "/root/reference")
+_STUB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tfstub")
+_SIBLINGS = ("utils", "tf_bias_layer", "fcos", "data_preprocess")
+_STUB_PKGS = ("tensorflow", "matplotlib", "classification_models")
+_cache = {}
+_stub_mods = {}  # one shared instance of the stub packages, so Tensor classes match across loads
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "FCOS"))
+
+
+def _enter(folder):
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.pop(k) for k in list(sys.modules)
+                  if k.split(".")[0] in _SIBLINGS + _STUB_PKGS}
+    sys.modules.update(_stub_mods)
+    sys.path[:0] = [_STUB, os.path.join(REF_ROOT, folder)]
+    if not hasattr(np, "int"):
+        np.int = int  # RetinaNet/retinanet_module.py:303 uses the alias removed in NumPy 1.24
+    return saved_path, saved_mods
+
+
+def _leave(state):
+    saved_path, saved_mods = state
+    for k in list(sys.modules):
+        root = k.split(".")[0]
+        if root in _STUB_PKGS:
+            _stub_mods[k] = sys.modules.pop(k)
+        elif root in _SIBLINGS:
+            sys.modules.pop(k)
+    sys.modules.update(saved_mods)
+    sys.path[:] = saved_path
+
+
+def load(folder, module):
+    """Return reference module `<folder>/<module>.py` executed under the stub."""
+    key = (folder, module)
+    if key in _cache:
+        return _cache[key]
+    if not available():
+        raise FileNotFoundError("reference tree not found at %s" % REF_ROOT)
+    state = _enter(folder)
+    try:
+        path = os.path.join(REF_ROOT, folder, module + ".py")
+        spec = importlib.util.spec_from_file_location("_ref_%s_%s" % (folder, module), path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        _leave(state)
+    _cache[key] = mod
+    return mod
+
+
+def tf():
+    """The stub `tensorflow` module (for building Tensor inputs)."""
+    if "tf" not in _cache:
+        state = _enter("FCOS")
+        try:
+            import tensorflow  # noqa: the stub
+            _cache["tf"] = tensorflow
+        finally:
+            _leave(state)
+    return _cache["tf"]
+
+
+def retinanet(n_classes, **kwargs):
+    """Instantiate the reference RetinaNet class with its Keras graph builder patched out
+    (RetinaNet/retinanet_module.py:194-196 builds a backbone in __init__)."""
+    mod = load("RetinaNet", "retinanet_module")
+    mod.build_model = lambda *a, **k: None
+    return mod.RetinaNet(n_classes, {i: str(i) for i in range(n_classes)}, **kwargs)
+
+
+def functions_only(folder, module, names, extra_globals=None):
+    """Exec only the named top-level FunctionDefs (+ imports) of a script whose module-level
+    code cannot run here (e.g. FCOS/infer_fcos.py loads pickles from C:/ at import time)."""
+    path = os.path.join(REF_ROOT, folder, module + ".py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    keep = [n for n in tree.body
+            if isinstance(n, (ast.Import, ast.ImportFrom))
+            or (isinstance(n, ast.FunctionDef) and n.name in names)]
+    state = _enter(folder)
+    try:
+        ns = dict(extra_globals or {})
+        exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    finally:
+        _leave(state)
+    return ns
