@@ -1,0 +1,98 @@
+// Handle, options and error reporting for libdensehead.so (see include/densehead.h).
+#include <cstring>
+
+#include "dh_host.h"
+
+namespace dh {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void* scratch(dh_handle_s* h, size_t bytes) {
+    if (bytes <= h->scratch_bytes) return h->scratch;
+    if (h->scratch) {
+        cudaDeviceSynchronize();  // a kernel in flight may still use the old block
+        cudaFree(h->scratch);
+        h->scratch = nullptr;
+        h->scratch_bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 1) + (1u << 20);
+    cudaError_t e = cudaMalloc(&h->scratch, want);
+    if (e != cudaSuccess) {
+        set_error(DH_ERR_CUDA, "cudaMalloc(%zu) for scratch failed: %s", want, cudaGetErrorString(e));
+        return nullptr;
+    }
+    h->scratch_bytes = want;
+    return h->scratch;
+}
+
+}  // namespace dh
+
+extern "C" {
+
+const char* dh_version(void) { return "densehead-b200 0.1.0 (sm_100a)"; }
+
+const char* dh_last_error(void) { return dh::g_err; }
+
+int dh_create(dh_handle_t* out, int device) {
+    DH_CHECK_ARG(out != nullptr, "dh_create: out is NULL");
+    int n = 0;
+    DH_CUDA(cudaGetDeviceCount(&n));
+    DH_CHECK_ARG(device >= 0 && device < n, "dh_create: device %d out of range (%d visible)", device, n);
+    cudaDeviceProp prop;
+    DH_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return dh::set_error(DH_ERR_CUDA, "dh_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                             device, prop.major, prop.minor);
+    dh_handle_s* h = new dh_handle_s();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->use_tma_store = 1;
+    h->tile_bytes = 32768;
+    h->ctas_per_sm = 2;
+    h->launches = 0;
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+    *out = h;
+    return DH_OK;
+}
+
+int dh_destroy(dh_handle_t h) {
+    if (!h) return DH_OK;
+    if (h->scratch) {
+        dh::DeviceGuard g(h->device);
+        cudaFree(h->scratch);
+    }
+    delete h;
+    return DH_OK;
+}
+
+int dh_set_option(dh_handle_t h, int option, int value) {
+    DH_CHECK_ARG(h != nullptr, "dh_set_option: handle is NULL");
+    switch (option) {
+        case DH_OPT_TMA_STORE:
+            h->use_tma_store = value ? 1 : 0;
+            return DH_OK;
+        case DH_OPT_TILE_BYTES:
+            DH_CHECK_ARG(value >= 2048 && value <= 98304, "DH_OPT_TILE_BYTES must be in [2048, 98304]");
+            h->tile_bytes = value & ~127;
+            return DH_OK;
+        case DH_OPT_CTAS_PER_SM:
+            DH_CHECK_ARG(value >= 1 && value <= 8, "DH_OPT_CTAS_PER_SM must be in [1, 8]");
+            h->ctas_per_sm = value;
+            return DH_OK;
+        default:
+            return dh::set_error(DH_ERR_BAD_ARG, "dh_set_option: unknown option %d", option);
+    }
+}
+
+long long dh_launch_count(dh_handle_t h) { return h ? h->launches : 0; }
+
+}  // extern "C"

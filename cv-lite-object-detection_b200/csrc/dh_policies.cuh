@@ -1,0 +1,453 @@
+// Encoder policies: the per-detector target rules, written as an order-free per-row gather.
+//
+// The reference paints boxes sequentially into NumPy maps ("last painter wins channels 0..4,
+// class channels OR").  Each policy restates that as: (1) `make_record` -- per-GT quantities
+// computed once per image by one thread per box, in the reference's float32 operation order;
+// (2) `tile_hit` -- can this GT touch this tile at all; (3) `emit_row` -- for one output row, scan
+// the tile's candidates, OR the class channels, pick the winner (= the painter the reference would
+// have painted last) and write the row into the zero-initialised shared-memory tile.
+// All citations are relative to /root/reference.
+#pragma once
+#include "dh_tile.cuh"
+
+namespace dh {
+
+enum FcosMode { FCOS_FOOTPRINT = 0, FCOS_CENTER3X3 = 1, FCOS_CENTER_ONLY = 2, FCOS_CENTER_V1 = 3 };
+enum CenterNetMode { CN_ONEHOT_SCALES = 0, CN_HOURGLASS = 1, CN_POWER_FALLOFF = 2 };
+
+struct Corners {
+    float y0, x0, y1, x1;
+};
+// FCOS/fcos.py:211-215 (same expression in every encoder): (c -/+ 0.5*d) * img_dim
+__device__ __forceinline__ Corners pixel_corners(const float* g, float hi, float wi) {
+    Corners c;
+    const float hh = fmul(0.5f, g[2]), hw = fmul(0.5f, g[3]);
+    c.y0 = fmul(fsub(g[0], hh), hi);
+    c.x0 = fmul(fsub(g[1], hw), wi);
+    c.y1 = fmul(fadd(g[0], hh), hi);
+    c.x1 = fmul(fadd(g[1], hw), wi);
+    return c;
+}
+// the reference's paint order is ascending area (stable): the later painter is the larger
+// (area, index) pair.
+__device__ __forceinline__ bool paints_later(float area, int k, float best_area, int best_k) {
+    return best_k < 0 || area > best_area || (area == best_area && k > best_k);
+}
+// FCOS/fcos.py:262-271 in float64
+__device__ __forceinline__ double ratio64(float a, float b) {
+    const double lo = static_cast<double>(fminf(a, b)), hi = static_cast<double>(fmaxf(a, b));
+    return ddiv(dadd(lo, 1.0e-8), dadd(hi, 1.0e-8));
+}
+
+// =====================================================================================
+// FCOS family: FCOS/fcos.py:136-378, fcos_center.py:149-279, fcos_center_v1.py:149-258
+// =====================================================================================
+struct FcosPolicy {
+    struct Params {
+        int n_levels, num_classes, mode;
+        int stride[DH_MAX_LEVELS];
+        float stride_f[DH_MAX_LEVELS];
+        float b_dim[DH_MAX_LEVELS];  // n_levels-1 thresholds
+        int hl[DH_MAX_LEVELS], wl[DH_MAX_LEVELS];
+        int* num_targets;  // [B, n_levels] or null
+    };
+    struct Rec {
+        float y0s, x0s, y1s, x1s;  // corners / stride  (CENTER_V1: the four regression values)
+        float area;
+        int level;
+        int ry0, ry1, rx0, rx1;  // half-open footprint in cells
+        int ycen, xcen;
+        int cls;
+        int flags;  // bit0 live_y, bit1 live_x, bit2 valid
+    };
+    static constexpr int kRegCh = 5;  // t, b, l, r, centerness
+
+    __device__ static void make_record(const Params& p, const float* g, float hi, float wi, int k, Rec& r) {
+        const float gh = fmul(g[2], hi), gw = fmul(g[3], wi);  // fcos.py:152-153
+        const float d = fmaxf(gw, gh);
+        int l = p.n_levels - 1;  // fcos.py:168-179
+        for (int n = 0; n < p.n_levels - 1; ++n)
+            if (d < p.b_dim[n]) {
+                l = n;
+                break;
+            }
+        r.level = l;
+        r.area = fmul(gh, gw);  // fcos.py:202-204
+        r.cls = trunc_i(g[4]);
+        const float s = p.stride_f[l];
+        const int hl = p.hl[l], wl = p.wl[l];
+        const Corners c = pixel_corners(g, hi, wi);
+        int flags = 4;
+        if (p.mode == FCOS_CENTER_V1) {  // fcos_center_v1.py:229-246
+            const float box_sc = (l < p.n_levels - 1) ? p.b_dim[l] : fmaxf(hi, wi);
+            const float raw_y = fmul(g[0], hi), raw_x = fmul(g[1], wi);
+            const int i = trunc_i(fdiv(raw_y, s)), j = trunc_i(fdiv(raw_x, s));
+            r.y0s = fdiv(fsub(raw_y, static_cast<float>(i * p.stride[l])), s);
+            r.x0s = fdiv(fsub(raw_x, static_cast<float>(j * p.stride[l])), s);
+            r.y1s = fdiv(gh, box_sc);
+            r.x1s = fdiv(gw, box_sc);
+            r.ry0 = i, r.ry1 = i + 1, r.rx0 = j, r.rx1 = j + 1;
+            r.ycen = i, r.xcen = j;
+            if (i < 0 || j < 0 || i >= hl || j >= wl) flags = 0;
+            r.flags = flags;
+            return;
+        }
+        r.y0s = fdiv(c.y0, s), r.x0s = fdiv(c.x0, s), r.y1s = fdiv(c.y1, s), r.x1s = fdiv(c.x1, s);
+        const float h_ratio = fdiv(hi, s), w_ratio = fdiv(wi, s);  // fcos.py:162-163
+        if (p.mode == FCOS_FOOTPRINT) {
+            const float half_h = fdiv(g[2], 2.0f), half_w = fdiv(g[3], 2.0f);
+            const int y_low = max(0, trunc_i(fmul(fsub(g[0], half_h), h_ratio)) + 1);  // fcos.py:217-225
+            const int x_low = max(0, trunc_i(fmul(fsub(g[1], half_w), w_ratio)) + 1);
+            const int y_upp = min(trunc_i(fmul(fadd(g[0], half_h), h_ratio)) + 1, hl);
+            const int x_upp = min(trunc_i(fmul(fadd(g[1], half_w), w_ratio)) + 1, wl);
+            r.ycen = min((y_low + y_upp) / 2, hl - 1);  // fcos.py:227-230 (C division truncates like int())
+            r.xcen = min((x_low + x_upp) / 2, wl - 1);
+            if (y_upp > y_low) {
+                flags |= 1;
+                r.ry0 = y_low, r.ry1 = y_upp;
+            } else {
+                r.ry0 = r.ycen, r.ry1 = r.ycen + 1;
+            }
+            if (x_upp > x_low) {
+                flags |= 2;
+                r.rx0 = x_low, r.rx1 = x_upp;
+            } else {
+                r.rx0 = r.xcen, r.rx1 = r.xcen + 1;
+            }
+            if (r.ry0 < 0 || r.rx0 < 0) flags = 0;  // box outside the image: out of contract
+        } else {  // fcos_center.py:231-246
+            const int rad = (p.mode == FCOS_CENTER_ONLY) ? 0 : 1;
+            r.ycen = trunc_i(fadd(fmul(g[0], h_ratio), 0.5f));
+            r.xcen = trunc_i(fadd(fmul(g[1], w_ratio), 0.5f));
+            r.ry0 = r.ycen - rad, r.ry1 = r.ycen + rad + 1;
+            r.rx0 = r.xcen - rad, r.rx1 = r.xcen + rad + 1;
+        }
+        r.flags = flags;
+    }
+
+    __device__ static void image_prologue(const Params& p, const Rec* recs, int n, int b) {
+        // num_targets[b][l] = GT count per level (fcos.py:376); written once per image
+        if (p.num_targets && threadIdx.x < p.n_levels) {
+            int c = 0;
+            for (int k = 0; k < n; ++k) c += (recs[k].level == static_cast<int>(threadIdx.x));
+            p.num_targets[b * p.n_levels + threadIdx.x] = c;
+        }
+    }
+
+    __device__ static void tile_epilogue(const Params&, const TileInfo&, int) {}
+
+    __device__ static bool tile_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        if (!(r.flags & 4) || r.level != ti.level) return false;
+        const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
+        const int i1 = static_cast<int>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
+        return r.ry1 > i0 && r.ry0 <= i1;
+    }
+
+    // returns the number of painters that touched the row (0 = row stays zero)
+    __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
+                                   const Rec* recs, const unsigned short* cand, int ncand) {
+        const int i = static_cast<int>(fdiv_u32(row, md.div_width));
+        const int j = row - i * ti.width;
+        int best = -1, hits = 0;
+        float best_area = 0.f, best_score = 0.f;
+        for (int q = 0; q < ncand; ++q) {
+            const int k = cand[q];
+            const Rec& r = recs[k];
+            if (i < r.ry0 || i >= r.ry1 || j < r.rx0 || j >= r.rx1) continue;
+            ++hits;
+            dst[kRegCh + r.cls] = 1.0f;
+            if (p.mode == FCOS_CENTER3X3 || p.mode == FCOS_CENTER_ONLY) {  // fcos_center.py:253-265
+                const int dy = r.ycen - i, dx = r.xcen - j;
+                const float sc = (dy == 0 && dx == 0) ? 1.0f : ((dy != 0 && dx != 0) ? 0.25f : 0.5f);
+                best_score = fmaxf(best_score, sc);
+            }
+            if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
+        }
+        if (best < 0) return 0;
+        const Rec& r = recs[best];
+        if (p.mode == FCOS_CENTER_V1) {
+            dst[0] = r.y0s, dst[1] = r.x0s, dst[2] = r.y1s, dst[3] = r.x1s, dst[4] = 1.0f;
+            return hits;
+        }
+        const float fi = static_cast<float>(i) + 0.5f, fj = static_cast<float>(j) + 0.5f;
+        if (p.mode != FCOS_FOOTPRINT) {  // fcos_center.py:267-273 (unclipped)
+            dst[0] = fsub(fi, r.y0s);
+            dst[1] = fsub(fsub(r.y1s, static_cast<float>(i)), 0.5f);
+            dst[2] = fsub(fj, r.x0s);
+            dst[3] = fsub(fsub(r.x1s, static_cast<float>(j)), 0.5f);
+            dst[4] = best_score;
+            return hits;
+        }
+        const bool live_y = r.flags & 1, live_x = r.flags & 2;
+        // fcos.py:241-257 on a live axis; :289-301 / :325-337 / :357-369 on a collapsed axis (the
+        // reference subtracts the integer centre and 0.5 separately there)
+        const float t = fmaxf(0.f, fsub(fi, r.y0s));
+        const float bt = live_y ? fmaxf(0.f, fsub(r.y1s, fi)) : fmaxf(0.f, fsub(fsub(r.y1s, static_cast<float>(i)), 0.5f));
+        const float l = fmaxf(0.f, fsub(fj, r.x0s));
+        const float rt = live_x ? fmaxf(0.f, fsub(r.x1s, fj)) : fmaxf(0.f, fsub(fsub(r.x1s, static_cast<float>(j)), 0.5f));
+        dst[0] = t, dst[1] = bt, dst[2] = l, dst[3] = rt;
+        float cen = 1.0f;  // fcos.py:371-372 when both axes collapsed
+        if (i == r.ycen && j == r.xcen) {
+            cen = 1.0f;  // fcos.py:279-280
+        } else if (live_y || live_x) {
+            const double qy = live_y ? ratio64(t, bt) : 1.0, qx = live_x ? ratio64(l, rt) : 1.0;
+            cen = static_cast<float>(sqrt(dmul(qy, qx)));  // fcos.py:273-274
+        }
+        dst[4] = cen;
+        return hits;
+    }
+};
+
+// =====================================================================================
+// RetinaNet: RetinaNet/retinanet_module.py:251-365 + RetinaNet/utils.py:42-83
+// =====================================================================================
+struct RetinaPolicy {
+    struct Params {
+        int n_levels, n_anchors, num_classes;
+        int stride[DH_MAX_LEVELS];
+        float anchor_h[DH_MAX_LEVELS][12], anchor_w[DH_MAX_LEVELS][12];
+        float thr;
+        int* num_pairs;  // [B] (zeroed by the launcher) or null
+    };
+    struct Rec {
+        float gy, gx, gh, gw;
+        float lo_y, lo_x, hi_y, hi_x;
+        float area;
+        int cls;
+    };
+    static constexpr int kRegCh = 4;
+
+    __device__ static void make_record(const Params& p, const float* g, float hi, float wi, int k, Rec& r) {
+        r.gy = fmul(g[0], hi), r.gx = fmul(g[1], wi), r.gh = fmul(g[2], hi), r.gw = fmul(g[3], wi);  // :274-278
+        const float hh = fdiv(r.gh, 2.0f), hw = fdiv(r.gw, 2.0f);                                    // utils.py:61-63
+        r.lo_y = fsub(r.gy, hh), r.lo_x = fsub(r.gx, hw), r.hi_y = fadd(r.gy, hh), r.hi_x = fadd(r.gx, hw);
+        r.area = fmul(r.gh, r.gw);
+        r.cls = trunc_i(g[4]);
+    }
+    __device__ static void image_prologue(const Params&, const Rec*, int, int) {}
+    // positive (gt, anchor) pairs of the tile -> num_pairs[b] (integer atomics: order-independent)
+    __device__ static void tile_epilogue(const Params& p, const TileInfo& ti, int pairs) {
+        if (!p.num_pairs) return;
+        const int s = warp_sum_i(pairs);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(p.num_pairs + ti.b, s);
+    }
+
+    __device__ static bool tile_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        const float ah = p.anchor_h[ti.level][ti.anchor], aw = p.anchor_w[ti.level][ti.anchor];
+        if (p.thr > 0.f) {  // IoU <= min(area)/max(area): conservative reject (slack covers rounding)
+            const float aa = ah * aw;
+            if (fminf(aa, r.area) < 0.999f * p.thr * fmaxf(aa, r.area)) return false;
+        } else if (p.thr < 0.f) {
+            return true;
+        }
+        const float s = static_cast<float>(p.stride[ti.level]);
+        const float i0 = static_cast<float>(fdiv_u32(ti.r0, md.div_width));
+        const float i1 = static_cast<float>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
+        return r.hi_y > i0 * s - 0.5f * ah - 1.0f && r.lo_y < i1 * s + 0.5f * ah + 1.0f;
+    }
+
+    // returns the number of (gt, anchor) pairs above the threshold at this row (:302-317)
+    __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
+                                   const Rec* recs, const unsigned short* cand, int ncand) {
+        const int i = static_cast<int>(fdiv_u32(row, md.div_width));
+        const int j = row - i * ti.width;
+        const int s = p.stride[ti.level];
+        const float ah = p.anchor_h[ti.level][ti.anchor], aw = p.anchor_w[ti.level][ti.anchor];
+        const float ay = static_cast<float>(i * s), ax = static_cast<float>(j * s);  // no half-cell offset (:293-294)
+        const float hh = fdiv(ah, 2.0f), hw = fdiv(aw, 2.0f);
+        const float alo_y = fsub(ay, hh), ahi_y = fadd(ay, hh), alo_x = fsub(ax, hw), ahi_x = fadd(ax, hw);
+        const float a_area = fmul(ah, aw);
+        int best = -1, pairs = 0;
+        for (int q = 0; q < ncand; ++q) {  // candidates are in ascending GT order
+            const int k = cand[q];
+            const Rec& r = recs[k];
+            const float dy = fmaxf(0.f, fsub(fminf(r.hi_y, ahi_y), fmaxf(r.lo_y, alo_y)));  // utils.py:66-72
+            const float dx = fmaxf(0.f, fsub(fminf(r.hi_x, ahi_x), fmaxf(r.lo_x, alo_x)));
+            const float inter = fmul(dy, dx);
+            if (!(inter > 0.f) && !(p.thr < 0.f)) continue;  // IoU == 0 cannot exceed thr >= 0
+            const float uni = fmaxf(fsub(fadd(r.area, a_area), inter), 1e-8f);  // utils.py:77-80
+            const float iou = fminf(fmaxf(fdiv(inter, uni), 0.f), 1.f);
+            if (iou > p.thr) {  // :302 strict
+                ++pairs;
+                dst[kRegCh + r.cls] = 1.0f;
+                best = k;  // highest GT index wins the regression (:357)
+            }
+        }
+        if (best >= 0) {  // :337-353, float64 like the reference's containers
+            const Rec& r = recs[best];
+            const double dah = static_cast<double>(ah), daw = static_cast<double>(aw);
+            dst[0] = static_cast<float>(ddiv(dsub(static_cast<double>(i * s), static_cast<double>(r.gy)), dah));
+            dst[1] = static_cast<float>(ddiv(dsub(static_cast<double>(j * s), static_cast<double>(r.gx)), daw));
+            dst[2] = static_cast<float>(ddiv(static_cast<double>(r.gh), dah));
+            dst[3] = static_cast<float>(ddiv(static_cast<double>(r.gw), daw));
+        }
+        return pairs;
+    }
+};
+
+// =====================================================================================
+// CenterNet: tf_centernet_resnet_s8.py:243-330, tf_centernet_hourglass.py:379-456,
+//            tf_centernet.py:152-342
+// =====================================================================================
+struct CenterNetPolicy {
+    struct Params {
+        int mode, num_classes, stride, n_scales;
+        float stride_f, sigma;
+        float scales[8];
+        int pad0, pad1;  // img_pad[0], img_pad[1]
+        int* status;     // bit0: a box was not below the largest scale (reference raises ValueError)
+    };
+    struct Rec {
+        float r0, r1, r2, r3;  // ONEHOT/HOURGLASS: regression values; FALLOFF: y0s, x0s, y1s, x1s
+        float area;
+        int row;                 // ONEHOT/HOURGLASS: target row, -1 if invalid
+        int ry0, ry1, rx0, rx1;  // FALLOFF footprint
+        int muy, mux;
+        int cls;
+        int flags;  // bit0 live_y, bit1 live_x, bit2 valid
+    };
+    static constexpr int kRegChOnehot = 4;
+
+    __device__ static int reg_ch(const Params& p) { return p.mode == CN_POWER_FALLOFF ? 5 : 4; }
+
+    __device__ static void make_record(const Params& p, const float* g, float hi, float wi, int k, Rec& r) {
+        const Corners c = pixel_corners(g, hi, wi);
+        const float s = p.stride_f;
+        r.area = fmul(fmul(g[2], hi), fmul(g[3], wi));
+        r.cls = trunc_i(g[4]);
+        r.flags = 4;
+        r.row = -1;
+        if (p.mode == CN_POWER_FALLOFF) {  // tf_centernet.py:165-223
+            const float h_ratio = fdiv(hi, s), w_ratio = fdiv(wi, s);
+            const int hl = static_cast<int>(static_cast<double>(p.pad0) / p.stride);
+            const int wl = static_cast<int>(static_cast<double>(p.pad1) / p.stride);
+            const int clip_h = trunc_i(fdiv(hi, s)), clip_w = trunc_i(fdiv(wi, s));  // clip by img_dim (:222-223)
+            r.r0 = fdiv(c.y0, s), r.r1 = fdiv(c.x0, s), r.r2 = fdiv(c.y1, s), r.r3 = fdiv(c.x1, s);
+            const int y_cen = trunc_i(fmul(g[0], h_ratio)), x_cen = trunc_i(fmul(g[1], w_ratio));
+            const float sh = fdiv(fmul(p.sigma, g[2]), 2.0f), sw = fdiv(fmul(p.sigma, g[3]), 2.0f);
+            const int y_low = max(0, 1 + trunc_i(fmul(fsub(g[0], sh), h_ratio)));
+            const int x_low = max(0, 1 + trunc_i(fmul(fsub(g[1], sw), w_ratio)));
+            const int y_upp = min(1 + trunc_i(fmul(fadd(g[0], sh), h_ratio)), clip_h);
+            const int x_upp = min(1 + trunc_i(fmul(fadd(g[1], sw), w_ratio)), clip_w);
+            int flags = 4;
+            if (y_upp > y_low) {
+                flags |= 1;
+                r.ry0 = y_low, r.ry1 = y_upp, r.muy = (y_low + y_upp) / 2;
+            } else {
+                r.ry0 = y_cen, r.ry1 = y_cen + 1, r.muy = y_cen;
+            }
+            if (x_upp > x_low) {
+                flags |= 2;
+                r.rx0 = x_low, r.rx1 = x_upp, r.mux = (x_low + x_upp) / 2;
+            } else {
+                r.rx0 = x_cen, r.rx1 = x_cen + 1, r.mux = x_cen;
+            }
+            if (r.ry0 < 0 || r.rx0 < 0 || r.ry0 >= hl || r.rx0 >= wl) flags = 0;
+            r.flags = flags;
+            return;
+        }
+        // centre-cell encoders; note the reference's swapped pad indices (tf_centernet_resnet_s8.py:259-262)
+        const int h_max = static_cast<int>(static_cast<double>(p.pad1) / p.stride);
+        const int w_max = static_cast<int>(static_cast<double>(p.pad0) / p.stride);
+        const float pad_y = static_cast<float>(trunc_i(fdiv(fsub(static_cast<float>(p.pad1), wi), 2.0f)));
+        const float pad_x = static_cast<float>(trunc_i(fdiv(fsub(static_cast<float>(p.pad0), hi), 2.0f)));
+        const float yc = fdiv(fadd(c.y0, c.y1), 2.0f), xc = fdiv(fadd(c.x0, c.x1), 2.0f);
+        const float py = fadd(pad_y, yc), px = fadd(pad_x, xc);
+        const int i = trunc_i(fdiv(py, s)), j = trunc_i(fdiv(px, s));  // :310-313
+        if (i < 0 || j < 0 || i >= h_max || j >= w_max) {
+            r.flags = 0;
+            return;
+        }
+        if (p.mode == CN_ONEHOT_SCALES) {
+            const float bh = fsub(c.y1, c.y0), bw = fsub(c.x1, c.x0);
+            const float d = fmaxf(bh, bw);
+            int sc = -1;
+            for (int n = 0; n < p.n_scales; ++n)
+                if (d < p.scales[n]) {
+                    sc = n;
+                    break;
+                }
+            if (sc < 0) {  // reference: min([]) -> ValueError (:306-307); the host wrapper raises
+                if (p.status) atomicOr(p.status, 1);
+                r.flags = 0;
+                return;
+            }
+            r.r0 = fdiv(fsub(py, static_cast<float>(i * p.stride)), s);  // :316-322
+            r.r1 = fdiv(fsub(px, static_cast<float>(j * p.stride)), s);
+            r.r2 = fdiv(bh, p.scales[sc]);
+            r.r3 = fdiv(bw, p.scales[sc]);
+            r.row = (i * w_max + j) * p.n_scales + sc;
+        } else {  // tf_centernet_hourglass.py:445-449
+            r.r0 = fsub(static_cast<float>(i) + 0.5f, fdiv(fadd(pad_y, c.y0), s));
+            r.r1 = fsub(fsub(fdiv(fadd(pad_y, c.y1), s), static_cast<float>(i)), 0.5f);
+            r.r2 = fsub(static_cast<float>(j) + 0.5f, fdiv(fadd(pad_x, c.x0), s));
+            r.r3 = fsub(fsub(fdiv(fadd(pad_x, c.x1), s), static_cast<float>(j)), 0.5f);
+            r.row = i * w_max + j;
+        }
+    }
+    __device__ static void image_prologue(const Params&, const Rec*, int, int) {}
+    __device__ static void tile_epilogue(const Params&, const TileInfo&, int) {}
+
+    __device__ static bool tile_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        if (!(r.flags & 4)) return false;
+        if (p.mode != CN_POWER_FALLOFF) return r.row >= ti.r0 && r.row < ti.r0 + ti.nrows;
+        const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
+        const int i1 = static_cast<int>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
+        return r.ry1 > i0 && r.ry0 <= i1;
+    }
+
+    __device__ static double inv_pow8(double d) {  // 1/(d^8): tf_centernet.py:6-19 with spread forced to 8 (:207)
+        const double d2 = dmul(d, d), d4 = dmul(d2, d2);
+        return ddiv(1.0, dmul(d4, d4));
+    }
+
+    __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
+                                   const Rec* recs, const unsigned short* cand, int ncand) {
+        int best = -1, hits = 0;
+        float best_area = 0.f;
+        if (p.mode != CN_POWER_FALLOFF) {
+            for (int q = 0; q < ncand; ++q) {
+                const int k = cand[q];
+                const Rec& r = recs[k];
+                if (r.row != row) continue;
+                ++hits;
+                dst[4 + r.cls] = 1.0f;
+                if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
+            }
+            if (best < 0) return 0;
+            const Rec& r = recs[best];
+            dst[0] = r.r0, dst[1] = r.r1, dst[2] = r.r2, dst[3] = r.r3;
+            return hits;
+        }
+        const int i = static_cast<int>(fdiv_u32(row, md.div_width));
+        const int j = row - i * ti.width;
+        for (int q = 0; q < ncand; ++q) {
+            const int k = cand[q];
+            const Rec& r = recs[k];
+            if (i < r.ry0 || i >= r.ry1 || j < r.rx0 || j >= r.rx1) continue;
+            ++hits;
+            dst[5 + r.cls] = 1.0f;
+            if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
+        }
+        if (best < 0) return 0;
+        const Rec& r = recs[best];
+        const bool live_y = r.flags & 1, live_x = r.flags & 2;
+        const float fi = static_cast<float>(i) + 0.5f, fj = static_cast<float>(j) + 0.5f;
+        dst[0] = fmaxf(0.f, fsub(fi, r.r0));
+        dst[1] = live_y ? fmaxf(0.f, fsub(r.r2, fi)) : fmaxf(0.f, fsub(fsub(r.r2, static_cast<float>(i)), 0.5f));
+        dst[2] = fmaxf(0.f, fsub(fj, r.r1));
+        dst[3] = live_x ? fmaxf(0.f, fsub(r.r3, fj)) : fmaxf(0.f, fsub(fsub(r.r3, static_cast<float>(j)), 0.5f));
+        float heat = 1.0f;
+        if (!(i == r.muy && j == r.mux) && (live_y || live_x)) {
+            // max over the footprint is reached at the centre cell: 1/0.5^8 = 256 per live axis
+            double v = 1.0;
+            if (live_y) v = dmul(v, inv_pow8(static_cast<double>(fi) - static_cast<double>(r.muy)) * (1.0 / 256.0));
+            if (live_x) v = dmul(v, inv_pow8(static_cast<double>(fj) - static_cast<double>(r.mux)) * (1.0 / 256.0));
+            heat = static_cast<float>(v);
+        }
+        dst[4] = heat;
+        return hits;
+    }
+};
+
+}  // namespace dh

@@ -1,0 +1,106 @@
+"""ctypes binding of libdensehead.so (the C ABI in include/densehead.h).
+
+There is NO CPU fallback: if the shared library is missing or a call fails, this raises.
+PyTorch is used only as the device-memory / stream provider; tensors cross the boundary as raw
+device pointers (see `_dlpack.py` for foreign DLPack producers such as TensorFlow).
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("DENSEHEAD_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libdensehead.so"))
+
+DH_OK = 0
+DH_ERR_BAD_ARG, DH_ERR_SHAPE, DH_ERR_CUDA, DH_ERR_CAPACITY = -1, -2, -3, -4
+DH_OPT_TMA_STORE, DH_OPT_TILE_BYTES, DH_OPT_CTAS_PER_SM = 1, 2, 3
+DH_MAX_BOXES_PER_IMAGE = 256
+
+c_fp = ctypes.POINTER(ctypes.c_float)
+c_ip = ctypes.POINTER(ctypes.c_int32)
+c_vp = ctypes.c_void_p
+
+
+class DenseHeadError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+_handles = {}
+
+
+def lib():
+    """Load libdensehead.so once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise DenseHeadError(
+                "libdensehead.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                "there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.dh_version.restype = ctypes.c_char_p
+        L.dh_last_error.restype = ctypes.c_char_p
+        L.dh_create.argtypes = [ctypes.POINTER(c_vp), ctypes.c_int]
+        L.dh_destroy.argtypes = [c_vp]
+        L.dh_set_option.argtypes = [c_vp, ctypes.c_int, ctypes.c_int]
+        L.dh_launch_count.argtypes = [c_vp]
+        L.dh_launch_count.restype = ctypes.c_longlong
+        I, F, P = ctypes.c_int, ctypes.c_float, c_vp
+        L.dh_fcos_encode.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, c_fp, I, I, ctypes.POINTER(c_vp), P, P]
+        L.dh_retina_encode.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, I, c_fp, F, I, ctypes.POINTER(c_vp), P, P]
+        L.dh_centernet_encode.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, P, P]
+        for name, proto in _OPTIONAL.items():
+            if hasattr(L, name):
+                getattr(L, name).argtypes = proto
+        _lib = L
+    return _lib
+
+
+# entry points added after the first milestone; bound when present
+_OPTIONAL = {}
+
+
+def check(rc, what=""):
+    if rc == DH_OK:
+        return
+    msg = lib().dh_last_error().decode("utf-8", "replace")
+    exc = {DH_ERR_BAD_ARG: ValueError, DH_ERR_SHAPE: ValueError, DH_ERR_CAPACITY: ValueError}.get(rc, DenseHeadError)
+    raise exc("%s failed (%d): %s" % (what or "densehead call", rc, msg))
+
+
+def handle(device_index):
+    """One library handle per CUDA device per process."""
+    h = _handles.get(device_index)
+    if h is None:
+        with _lock:
+            h = _handles.get(device_index)
+            if h is None:
+                out = c_vp()
+                check(lib().dh_create(ctypes.byref(out), int(device_index)), "dh_create")
+                h = _handles[device_index] = out
+    return h
+
+
+def set_option(device_index, option, value):
+    check(lib().dh_set_option(handle(device_index), option, int(value)), "dh_set_option")
+
+
+def launch_count(device_index=0):
+    return int(lib().dh_launch_count(handle(device_index)))
+
+
+def int_array(values):
+    return (ctypes.c_int32 * len(values))(*[int(v) for v in values])
+
+
+def float_array(values):
+    return (ctypes.c_float * len(values))(*[float(v) for v in values])
+
+
+def ptr_array(ptrs):
+    return (c_vp * len(ptrs))(*[c_vp(int(p)) for p in ptrs])

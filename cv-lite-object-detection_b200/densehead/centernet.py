@@ -1,0 +1,82 @@
+"""CenterNet dense-head routines: drop-in for CenterNet/tf_centernet_resnet_s8.py,
+CenterNet/tf_centernet_hourglass.py and CenterNet/tf_centernet.py of the reference."""
+import numpy as np
+import torch
+
+from . import _capi
+from ._batch import image_dims, pack_labels
+from ._tensors import as_host, current_device, stream_ptr, to_device
+
+MODES = {"s8": 0, "hourglass": 1, "falloff": 2}
+
+
+def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, stride=8, mode="s8", box_scales=None, sigma=0.25,
+                      out=None, status=None, stream=None):
+    """Encode a padded batch.  Output shape: s8 [B, H, W, S, C+4]; hourglass [B, H, W, C+4];
+    falloff [B, H, W, C+5].  `img_pad` is passed through with the reference's own indexing."""
+    dev = current_device()
+    boxes_d = to_device(boxes, torch.float32, dev)
+    if boxes_d.dim() != 3 or boxes_d.shape[2] != 5:
+        raise ValueError("boxes must be [B, Nmax, 5]")
+    batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
+    nbox_d = to_device(nbox, torch.int32, dev)
+    dims_d = to_device(image_dims(img_dim, batch) if not isinstance(img_dim, torch.Tensor) or not img_dim.is_cuda
+                       else img_dim, torch.float32, dev)
+    pad0, pad1 = int(img_pad[0]), int(img_pad[1])
+    m = MODES[mode]
+    scales = [float(v) for v in (box_scales if box_scales is not None else [])]
+    if m == 0:
+        if not scales:
+            raise ValueError("mode 's8' needs box_scales")
+        shape = (batch, int(pad1 / stride), int(pad0 / stride), len(scales), num_classes + 4)
+    elif m == 1:
+        shape = (batch, int(pad1 / stride), int(pad0 / stride), num_classes + 4)
+    else:
+        shape = (batch, int(pad0 / stride), int(pad1 / stride), num_classes + 5)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be contiguous float32 %r" % (shape,))
+    if status is None:
+        status = torch.empty((1,), dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().dh_centernet_encode(
+        _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax, pad0, pad1,
+        int(stride), len(scales), _capi.float_array(scales) if scales else None, float(sigma), int(num_classes), m,
+        out.data_ptr(), status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode")
+    return out, status
+
+
+def _prep(gt_labels, img_dim, img_pad):
+    g = as_host(gt_labels, np.float32).reshape(-1, 5)
+    dim = as_host(img_dim, np.float32).reshape(2)
+    pad = [int(v) for v in (as_host(img_pad, np.float64).reshape(2) if img_pad is not None else dim)]
+    boxes, nbox = pack_labels([g])
+    return g, dim, pad, boxes, nbox
+
+
+def format_data_s8(gt_labels, box_scales, img_dim, num_classes, img_pad=None, stride=8):
+    """CenterNet/tf_centernet_resnet_s8.py:243 `format_data` -> ([H, W, S, C+4] device tensor, n_targets).
+    Raises ValueError when a box is not below the largest scale, like the reference's `min([])`."""
+    g, dim, pad, boxes, nbox = _prep(gt_labels, img_dim, img_pad)
+    if len(g):
+        f = np.float32
+        bh = (g[:, 0] + f(.5) * g[:, 2]) * dim[0] - (g[:, 0] - f(.5) * g[:, 2]) * dim[0]
+        bw = (g[:, 1] + f(.5) * g[:, 3]) * dim[1] - (g[:, 1] - f(.5) * g[:, 3]) * dim[1]
+        if np.any(np.maximum(bh, bw) >= f(max(box_scales))):
+            raise ValueError("min() arg is an empty sequence")
+    out, _ = format_data_batch(boxes, nbox, dim[None], num_classes, pad, stride, "s8", box_scales)
+    return out[0], len(g)
+
+
+def format_data_hourglass(gt_labels, img_dim, num_classes, img_pad=None, stride=8):
+    """CenterNet/tf_centernet_hourglass.py:379 `format_data` -> ([H, W, C+4], n_targets)."""
+    g, dim, pad, boxes, nbox = _prep(gt_labels, img_dim, img_pad)
+    out, _ = format_data_batch(boxes, nbox, dim[None], num_classes, pad, stride, "hourglass")
+    return out[0], len(g)
+
+
+def format_data(gt_labels, img_dim, num_classes, img_pad=None, stride=8, sigma=0.25):
+    """CenterNet/tf_centernet.py:152 `format_data` -> [H, W, C+5] (inverse-power fall-off heat)."""
+    g, dim, pad, boxes, nbox = _prep(gt_labels, img_dim, img_pad)
+    out, _ = format_data_batch(boxes, nbox, dim[None], num_classes, pad, stride, "falloff", sigma=sigma)
+    return out[0]

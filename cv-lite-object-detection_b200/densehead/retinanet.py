@@ -1,0 +1,101 @@
+"""RetinaNet dense-head routines: drop-in for the non-Keras methods of
+RetinaNet/retinanet_module.py (`RetinaNet` class) and `compute_iou` of RetinaNet/utils.py.
+
+`RetinaNetHead` mirrors the reference class minus the backbone: same constructor arguments for the
+anchor configuration, same method names (`get_anchors`, `format_data`, `prediction_to_corners`,
+`cpu_nms`, `image_detections`, `train_loss` split into forward + `loss`).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._batch import image_dims, pack_labels
+from ._tensors import as_host, current_device, stream_ptr, to_device
+
+STRIDES = [8, 16, 32, 64, 128]
+
+
+def anchor_table(anchor_sizes=None, aspect_ratios=None, anchor_scales=None):
+    """float32 [5, A, 2] (h, w): RetinaNet/retinanet_module.py:201-219 in the reference's float32
+    operation order (`tf.math.sqrt(area / ratio)` on a float32 tensor, `area / h`, `scale * dims`)."""
+    sizes = [32.0, 64.0, 128.0, 256.0, 512.0] if anchor_sizes is None else list(anchor_sizes)
+    if len(sizes) != 5:
+        raise ValueError("anchor_sizes must be of dimension 5.")
+    ratios = [0.5, 1.0, 2.0] if aspect_ratios is None else list(aspect_ratios)
+    scales = [2 ** x for x in [0, 1 / 3, 2 / 3]] if anchor_scales is None else list(anchor_scales)
+    if len(scales) != 3:
+        raise ValueError("anchor_scales must be of dimension 3.")
+    f = np.float32
+    table = np.zeros((5, len(ratios) * len(scales), 2), dtype=np.float32)
+    for l, area in enumerate(sorted(x ** 2 for x in sizes)):
+        a = 0
+        for ratio in ratios:
+            h = np.sqrt(f(area / ratio))
+            w = f(area) / h
+            for sc in scales:
+                table[l, a] = (f(sc) * h, f(sc) * w)
+                a += 1
+    return table
+
+
+def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, anchor_hw=None, iou_thresh=0.5, strides=None,
+                      out=None, num_pairs=None, stream=None):
+    """Match + encode a padded batch.  Returns (list of 5 tensors [B, A, Hl, Wl, C+4], num_pairs int32 [B])."""
+    strides = list(STRIDES if strides is None else strides)
+    table = anchor_table() if anchor_hw is None else np.ascontiguousarray(anchor_hw, dtype=np.float32)
+    n_levels, n_anchors = table.shape[0], table.shape[1]
+    if n_levels != len(strides):
+        raise ValueError("anchor table has %d levels for %d strides" % (n_levels, len(strides)))
+    dev = current_device()
+    boxes_d = to_device(boxes, torch.float32, dev)
+    if boxes_d.dim() != 3 or boxes_d.shape[2] != 5:
+        raise ValueError("boxes must be [B, Nmax, 5]")
+    batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
+    nbox_d = to_device(nbox, torch.int32, dev)
+    dims_d = to_device(image_dims(img_dim, batch) if not isinstance(img_dim, torch.Tensor) or not img_dim.is_cuda
+                       else img_dim, torch.float32, dev)
+    pad_h, pad_w = int(img_pad[0]), int(img_pad[1])
+    ch = num_classes + 4
+    shapes = [(int(pad_h / s), int(pad_w / s)) for s in strides]
+    if out is None:
+        out = [torch.empty((batch, n_anchors, h, w, ch), dtype=torch.float32, device=dev) for h, w in shapes]
+    if num_pairs is None:
+        num_pairs = torch.empty((batch,), dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().dh_retina_encode(
+        _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax, pad_h, pad_w,
+        n_levels, _capi.int_array(strides), n_anchors, _capi.float_array(table.reshape(-1).tolist()),
+        float(iou_thresh), int(num_classes), _capi.ptr_array([o.data_ptr() for o in out]), num_pairs.data_ptr(),
+        stream_ptr(stream)), "dh_retina_encode")
+    return out, num_pairs
+
+
+class RetinaNetHead:
+    """The reference `RetinaNet` class (RetinaNet/retinanet_module.py:162-569) without its Keras model."""
+
+    def __init__(self, n_classes, id_2_label=None, aspect_ratios=None, anchor_scales=None, anchor_sizes=None):
+        self.n_class = n_classes
+        self.id_2_label = id_2_label
+        self.strides = list(STRIDES)
+        self.anchor_table = anchor_table(anchor_sizes, aspect_ratios, anchor_scales)
+        self.n_anchors = self.anchor_table.shape[1]
+        self.anchor_boxes = [[self.anchor_table[l, a].copy() for a in range(self.n_anchors)] for l in range(5)]
+
+    def get_anchors(self, cnn_shape, level):
+        """retinanet_module.py:221-246: per-anchor `[H, W, 4]` grids `(col, row, h, w)` (host, float64)."""
+        if level >= 5 or level < 0:
+            raise ValueError("level has to be between 0 and 4.")
+        gx, gy = np.meshgrid(np.arange(0, cnn_shape[1], dtype=np.float32), np.arange(0, cnn_shape[0], dtype=np.float32))
+        base = np.stack([gx, gy, np.ones_like(gx), np.ones_like(gx)], axis=-1).astype(np.float64)
+        return [base * np.array([1, 1, d[0], d[1]], dtype=np.float64).reshape(1, 1, 4) for d in self.anchor_boxes[level]]
+
+    def format_data(self, gt_labels, img_dim, iou_thresh=0.50, img_pad=None):
+        """retinanet_module.py:251-365.  Returns (`out[level][anchor]` device tensors [Hl, Wl, C+4], n_pairs)."""
+        g = as_host(gt_labels, np.float32).reshape(-1, 5)
+        dim = as_host(img_dim, np.float32).reshape(2)
+        pad = [int(v) for v in (as_host(img_pad, np.float64).reshape(2) if img_pad is not None else dim)]
+        boxes, nbox = pack_labels([g])
+        outs, pairs = format_data_batch(boxes, nbox, dim[None], self.n_class, pad, self.anchor_table, iou_thresh,
+                                        self.strides)
+        return [[o[0, a] for a in range(self.n_anchors)] for o in outs], int(pairs[0].item())

@@ -1,0 +1,111 @@
+/* densehead.h -- C ABI of libdensehead.so: the B200 (sm_100a) dense-head path of
+ * WD-Leong/CV-Lite-Object-Detection (target encoding, losses, decode + NMS).
+ *
+ * This is the drop-in boundary.  The reference is pure Python with no FFI of its own, so each
+ * entry point below names the reference routine it replaces (file:line relative to the reference
+ * repository) and `INTEGRATION.md` shows the ctypes binding a maintainer adds on the reference
+ * side.  Conventions:
+ *
+ *   - Plain C: pointers, sizes, scalars.  No framework types.  Pointers marked [dev] are CUDA device
+ *     pointers (obtained zero-copy from the framework tensor, e.g. via DLPack); pointers marked
+ *     [host] are small host arrays read synchronously during the call.
+ *   - The caller owns every buffer.  The library keeps only an opaque handle with its scratch.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and the call returns without synchronising, unless stated otherwise.
+ *   - Every function returns DH_OK (0) or a negative DH_ERR_* code; dh_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - GT rows are float32 (cy, cx, h, w, class) normalised by the image's unpadded size
+ *     `img_dim[b] = (H, W)`, padded to [B, max_boxes, 5] with a per-image count `nbox[b]`
+ *     (max_boxes <= DH_MAX_BOXES_PER_IMAGE).  Target maps are float32, channel-last, batch-major.
+ */
+#ifndef DENSEHEAD_H_
+#define DENSEHEAD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DH_OK 0
+#define DH_ERR_BAD_ARG (-1)
+#define DH_ERR_SHAPE (-2)
+#define DH_ERR_CUDA (-3)
+#define DH_ERR_CAPACITY (-4)
+
+#define DH_MAX_BOXES_PER_IMAGE 256
+#define DH_MAX_PYRAMID_LEVELS 8
+
+typedef struct dh_handle_s* dh_handle_t;
+
+/* ---- library / handle ------------------------------------------------------------------- */
+const char* dh_version(void);
+const char* dh_last_error(void);
+/* Binds the handle to CUDA device `device` (its SM count sizes the persistent grids). */
+int dh_create(dh_handle_t* out, int device);
+int dh_destroy(dh_handle_t h);
+/* Options: see DH_OPT_*.  Returns DH_ERR_BAD_ARG for an unknown option. */
+#define DH_OPT_TMA_STORE 1   /* 1 (default): tiles leave shared memory as TMA bulk stores; 0: st.global.v4 */
+#define DH_OPT_TILE_BYTES 2  /* shared-memory tile size in bytes (default 32768) */
+#define DH_OPT_CTAS_PER_SM 3 /* persistent CTAs per SM (default 2) */
+int dh_set_option(dh_handle_t h, int option, int value);
+/* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
+long long dh_launch_count(dh_handle_t h);
+
+/* ---- target encoders ---------------------------------------------------------------------- */
+
+/* FCOS family.  Replaces format_data in FCOS/fcos.py:136-378 (mode 0), FCOS/fcos_center.py:149-279
+ * (mode 1: 3x3 window, mode 2: center_only=True) and FCOS/fcos_center_v1.py:149-258 (mode 3).
+ * out_levels[l] is [B, Hl, Wl, C+5] with Hl = int(pad_h / strides[l]); fully overwritten.
+ * num_targets (optional) is [B, n_levels]: GT boxes assigned to each level.               */
+#define DH_FCOS_FOOTPRINT 0
+#define DH_FCOS_CENTER3X3 1
+#define DH_FCOS_CENTER_ONLY 2
+#define DH_FCOS_CENTER_V1 3
+int dh_fcos_encode(dh_handle_t h,
+                   const float* boxes /*[dev] [B,max_boxes,5]*/, const int32_t* nbox /*[dev] [B]*/,
+                   const float* img_dim /*[dev] [B,2]*/,
+                   int batch, int max_boxes, int pad_h, int pad_w,
+                   int n_levels, const int32_t* strides /*[host] [n_levels]*/,
+                   const float* b_dim /*[host] [n_levels-1]*/,
+                   int num_classes, int mode,
+                   float* const* out_levels /*[host] n_levels [dev] pointers*/,
+                   int32_t* num_targets /*[dev] [B,n_levels] or NULL*/,
+                   void* stream);
+
+/* RetinaNet matcher + box encoder.  Replaces RetinaNet.format_data (RetinaNet/retinanet_module.py:
+ * 251-365) together with get_anchors (:221-246) and compute_iou (RetinaNet/utils.py:42-83); anchors
+ * are generated analytically from anchor_hw.  out_levels[l] is [B, A, Hl, Wl, C+4] (slice [:, a] is
+ * the reference's all_outputs[l][a]).  num_pairs (optional) is [B]: positive (gt, anchor) pairs. */
+int dh_retina_encode(dh_handle_t h,
+                     const float* boxes, const int32_t* nbox, const float* img_dim,
+                     int batch, int max_boxes, int pad_h, int pad_w,
+                     int n_levels, const int32_t* strides /*[host]*/,
+                     int n_anchors, const float* anchor_hw /*[host] [n_levels,n_anchors,2] (h,w)*/,
+                     float iou_thresh, int num_classes,
+                     float* const* out_levels /*[host] n_levels [dev] pointers*/,
+                     int32_t* num_pairs /*[dev] [B] or NULL*/,
+                     void* stream);
+
+/* CenterNet encoders.  mode 0: tf_centernet_resnet_s8.format_data (CenterNet/tf_centernet_resnet_s8.py:
+ * 243-330), out [B,H,W,S,C+4]; mode 1: tf_centernet_hourglass.format_data (CenterNet/
+ * tf_centernet_hourglass.py:379-456), out [B,H,W,C+4]; mode 2: tf_centernet.format_data
+ * (CenterNet/tf_centernet.py:152-342, inverse-power fall-off heat), out [B,H,W,C+5].
+ * pad0/pad1 are img_pad[0]/img_pad[1] exactly as the reference indexes them (modes 0 and 1 swap
+ * them, tf_centernet_resnet_s8.py:259-262).  status (optional, [dev] int32, zeroed by the call)
+ * gets bit 0 set when a box is not below the largest box scale (the reference raises ValueError). */
+#define DH_CENTERNET_ONEHOT_SCALES 0
+#define DH_CENTERNET_HOURGLASS 1
+#define DH_CENTERNET_POWER_FALLOFF 2
+int dh_centernet_encode(dh_handle_t h,
+                        const float* boxes, const int32_t* nbox, const float* img_dim,
+                        int batch, int max_boxes, int pad0, int pad1, int stride,
+                        int n_scales, const float* box_scales /*[host] [n_scales], mode 0 only*/,
+                        float sigma, int num_classes, int mode,
+                        float* out /*[dev]*/, int32_t* status /*[dev] or NULL*/,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENSEHEAD_H_ */

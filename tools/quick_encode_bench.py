@@ -1,0 +1,55 @@
+"""Quick device-side timing of the encoders (development aid; bench.py is the contract)."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "cv-lite-object-detection_b200")]
+import numpy as np, torch
+import densehead as dh
+from oracle import synth
+
+def timeit(fn, iters=50, warm=5):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+def run(tag, fn, nbytes):
+    t = timeit(fn)
+    print(json.dumps({"case": tag, "us": round(t * 1e6, 2), "GBps": round(nbytes / t / 1e9, 1)}), flush=True)
+
+SC = [32, 64, 128, 256, 512]
+for tma in (1, 0):
+    dh.set_option(0, 1, tma)
+    for B in (8, 256):
+        boxes, nbox = synth.config_boxes("fcos_voc", B, 1)
+        bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+        dims = torch.tensor([[512., 512.]] * B, device="cuda")
+        outs, cnt = dh.fcos.format_data_batch(bd, nd, dims, 20, [512, 512])
+        run("fcos_voc B=%d tma=%d" % (B, tma), lambda: dh.fcos.format_data_batch(bd, nd, dims, 20, [512, 512], out=outs, num_targets=cnt), sum(o.numel() for o in outs) * 4)
+    for B in (32, 256):
+        boxes, nbox = synth.config_boxes("centernet_crowdhuman", B, 2)
+        bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+        dims = torch.tensor([[512., 512.]] * B, device="cuda")
+        out, st = dh.centernet.format_data_batch(bd, nd, dims, 1, [512, 512], stride=4, mode="s8", box_scales=SC)
+        run("centernet_s8 B=%d tma=%d" % (B, tma), lambda: dh.centernet.format_data_batch(bd, nd, dims, 1, [512, 512], stride=4, mode="s8", box_scales=SC, out=out, status=st), out.numel() * 4)
+    for B in (8, 64):
+        boxes, nbox = synth.config_boxes("retina_coco", B, 3)
+        bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+        dims = torch.tensor([[640., 640.]] * B, device="cuda")
+        outs, pr = dh.retinanet.format_data_batch(bd, nd, dims, 80, [640, 640])
+        run("retina_coco B=%d tma=%d" % (B, tma), lambda: dh.retinanet.format_data_batch(bd, nd, dims, 80, [640, 640], out=outs, num_pairs=pr), sum(o.numel() for o in outs) * 4)
+        if B == 64:
+            big = torch.empty(sum(o.numel() for o in outs), device="cuda")
+            run("cudaMemset same bytes", lambda: big.zero_(), big.numel() * 4)
+            src = torch.empty_like(big)
+            run("copy same bytes (r+w)", lambda: big.copy_(src), big.numel() * 8)
+dh.set_option(0, 1, 1)
+for tb in (8192, 16384, 32768, 49152):
+    for cps in (1, 2, 3, 4):
+        dh.set_option(0, 2, tb); dh.set_option(0, 3, cps)
+        try:
+            run("retina B=64 tile=%d ctas=%d" % (tb, cps), lambda: dh.retinanet.format_data_batch(bd, nd, dims, 80, [640, 640], out=outs, num_pairs=pr), sum(o.numel() for o in outs) * 4)
+        except Exception as e:
+            print("skip", tb, cps, e)
