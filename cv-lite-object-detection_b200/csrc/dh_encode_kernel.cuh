@@ -29,7 +29,7 @@ struct EncodeArgs {
 };
 
 struct EncodeSmemLayout {
-    int stage_off, rec_off, raw_off, cand_off, misc_off, total;
+    int stage_off, rec_off, raw_off, cand_off, misc_off, args_off, total;
 };
 template <class P>
 __host__ __device__ inline EncodeSmemLayout encode_smem_layout(int tile_buf_bytes) {
@@ -39,14 +39,19 @@ __host__ __device__ inline EncodeSmemLayout encode_smem_layout(int tile_buf_byte
     l.raw_off = l.rec_off + ((static_cast<int>(sizeof(typename P::Rec)) * DH_MAX_BOXES + 127) & ~127);
     l.cand_off = l.raw_off + DH_MAX_BOXES * 5 * 4;  // 5120, multiple of 128
     l.misc_off = l.cand_off + DH_MAX_BOXES * 2;     // 512
-    l.total = l.misc_off + 128;
+    l.args_off = l.misc_off + 128;
+    l.total = l.args_off + ((static_cast<int>(sizeof(EncodeArgs<P>)) + 127) & ~127);
     return l;
 }
 
 template <class P>
-__global__ void __launch_bounds__(DH_THREADS) encode_kernel(const __grid_constant__ EncodeArgs<P> a) {
+__global__ void __launch_bounds__(DH_THREADS) encode_kernel(const __grid_constant__ EncodeArgs<P> ga) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const EncodeSmemLayout lay = encode_smem_layout<P>(a.tile_buf_bytes);
+    const EncodeSmemLayout lay = encode_smem_layout<P>(ga.tile_buf_bytes);
+    // work from a shared-memory copy of the arguments: the tile table and the policy tables are
+    // indexed dynamically, which is slow from kernel-parameter constant memory
+    const EncodeArgs<P>& a = *reinterpret_cast<const EncodeArgs<P>*>(smem + lay.args_off);
+    copy_args_to_smem(ga, reinterpret_cast<EncodeArgs<P>*>(smem + lay.args_off));
     typename P::Rec* recs = reinterpret_cast<typename P::Rec*>(smem + lay.rec_off);
     float* raw = reinterpret_cast<float*>(smem + lay.raw_off);
     unsigned short* cand = reinterpret_cast<unsigned short*>(smem + lay.cand_off);
@@ -54,8 +59,8 @@ __global__ void __launch_bounds__(DH_THREADS) encode_kernel(const __grid_constan
     int* wcount = reinterpret_cast<int*>(smem + lay.misc_off + 16);  // [8] per-warp candidate counts
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ch = a.tt.ch;
-    const long long total_tiles = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
+    const int ch = ga.tt.ch;
+    const long long total_tiles = static_cast<long long>(ga.tt.batch) * ga.tt.tiles_per_image;
     const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
     const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
     if (t_begin >= t_end) return;
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(DH_THREADS) encode_kernel(const __grid_constan
     // zero the stage buffers once; afterwards only dirtied rows are re-zeroed
     {
         float4* z = reinterpret_cast<float4*>(smem + lay.stage_off);
-        const int n4 = kStages * a.tile_buf_bytes / 16;
+        const int n4 = kStages * ga.tile_buf_bytes / 16;
         for (int e = tid; e < n4; e += DH_THREADS) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (tid == 0) {
@@ -78,9 +83,11 @@ __global__ void __launch_bounds__(DH_THREADS) encode_kernel(const __grid_constan
     int mis0 = 0, mis1 = 0;             // float offset of the tile inside its stage buffer (global 16-B phase)
     int cur_img = -1, n_boxes = 0;
     int it = 0;
-    for (long long tile = t_begin; tile < t_end; ++tile, ++it) {
+    TileCursor cur;
+    cursor_init(a.tt, t_begin, cur);
+    for (long long tile = t_begin; tile < t_end; ++tile, ++it, cursor_next(a.tt, cur)) {
         TileInfo ti;
-        locate_tile(a.tt, tile, ti);
+        cursor_info(a.tt, cur, ti);
         const MapDesc& md = a.tt.maps[ti.m];
 
         if (ti.b != cur_img) {  // crossed an image boundary: stage its GT rows, build records

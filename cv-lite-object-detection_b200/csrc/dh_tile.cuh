@@ -40,27 +40,51 @@ struct TileInfo {
     int height, width, sub;
 };
 
-__device__ __forceinline__ void locate_tile(const TileTable& tt, long long tile, TileInfo& ti) {
-    int b = static_cast<int>(tile / tt.tiles_per_image);
-    int t = static_cast<int>(tile - static_cast<long long>(b) * tt.tiles_per_image);
+// A CTA walks a contiguous range of tile ids: locate the first one with a binary search, then
+// advance incrementally.  `tt` must be the CTA's shared-memory copy of the table (indexed loads
+// from kernel-parameter constant memory cost hundreds of cycles each when they miss).
+struct TileCursor {
+    int b, m, t;  // image, map, tile within the map
+};
+__device__ __forceinline__ void cursor_init(const TileTable& tt, long long tile, TileCursor& c) {
+    c.b = static_cast<int>(tile / tt.tiles_per_image);
+    const int t = static_cast<int>(tile - static_cast<long long>(c.b) * tt.tiles_per_image);
     int lo = 0, hi = tt.n_maps - 1;  // last map with tile_begin <= t
     while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
+        const int mid = (lo + hi + 1) >> 1;
         if (tt.maps[mid].tile_begin <= t)
             lo = mid;
         else
             hi = mid - 1;
     }
-    const MapDesc& md = tt.maps[lo];
-    ti.b = b;
-    ti.m = lo;
-    ti.r0 = (t - md.tile_begin) * tt.rows_per_tile;
+    c.m = lo;
+    c.t = t - tt.maps[lo].tile_begin;
+}
+__device__ __forceinline__ void cursor_next(const TileTable& tt, TileCursor& c) {
+    if (++c.t == tt.maps[c.m].n_tiles) {
+        c.t = 0;
+        if (++c.m == tt.n_maps) c.m = 0, ++c.b;
+    }
+}
+__device__ __forceinline__ void cursor_info(const TileTable& tt, const TileCursor& c, TileInfo& ti) {
+    const MapDesc& md = tt.maps[c.m];
+    ti.b = c.b;
+    ti.m = c.m;
+    ti.r0 = c.t * tt.rows_per_tile;
     ti.nrows = min(tt.rows_per_tile, md.rows - ti.r0);
     ti.level = md.level;
     ti.anchor = md.anchor;
     ti.height = md.height;
     ti.width = md.width;
     ti.sub = md.sub;
+}
+// Copy a kernel-parameter struct into shared memory (all threads; caller syncs).
+template <class T>
+__device__ __forceinline__ void copy_args_to_smem(const T& src, T* dst) {
+    static_assert(sizeof(T) % 4 == 0, "argument structs are 4-byte granular");
+    const int* s = reinterpret_cast<const int*>(&src);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(T) / 4); i += blockDim.x) d[i] = s[i];
 }
 
 // Stage the raw GT rows of image `b` ([max_boxes, 5] float32) into shared memory.  Uses one TMA

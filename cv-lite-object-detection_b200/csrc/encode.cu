@@ -51,6 +51,109 @@ static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, cons
 
 }  // namespace dh
 
+namespace dh {
+
+#define DH_FILL_CHECK(cond, ...)                              \
+    do {                                                      \
+        if (!(cond)) return set_error(DH_ERR_BAD_ARG, __VA_ARGS__); \
+    } while (0)
+
+int fill_fcos(FcosPolicy::Params& p, TileTable& tt, int pad_h, int pad_w, int n_levels, const int32_t* strides,
+              const float* b_dim, int num_classes, int mode, float* const* out_levels,
+              const float* const* pred_levels, int32_t* num_targets, const char* who) {
+    DH_FILL_CHECK(n_levels >= 1 && n_levels <= DH_MAX_LEVELS, "%s: n_levels %d not in [1,%d]", who, n_levels, DH_MAX_LEVELS);
+    DH_FILL_CHECK(n_levels == 1 || b_dim, "%s: b_dim is NULL", who);
+    DH_FILL_CHECK(pad_h > 0 && pad_w > 0, "%s: bad padded size", who);
+    DH_FILL_CHECK(num_classes >= 1 && num_classes <= 4096, "%s: num_classes %d", who, num_classes);
+    DH_FILL_CHECK(mode >= 0 && mode <= 3, "%s: mode %d", who, mode);
+    p.n_levels = n_levels, p.num_classes = num_classes, p.mode = mode, p.num_targets = num_targets;
+    tt.n_maps = n_levels;
+    for (int l = 0; l < n_levels; ++l) {
+        DH_FILL_CHECK(strides[l] > 0, "%s: stride of level %d", who, l);
+        DH_FILL_CHECK((!out_levels || out_levels[l]) && (!pred_levels || pred_levels[l]), "%s: level %d pointer is NULL", who, l);
+        p.stride[l] = strides[l];
+        p.stride_f[l] = static_cast<float>(strides[l]);
+        if (l < n_levels - 1) p.b_dim[l] = b_dim[l];
+        p.hl[l] = static_cast<int>(static_cast<double>(pad_h) / strides[l]);  // int(img_pad[0] / stride)
+        p.wl[l] = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
+        MapDesc& md = tt.maps[l];
+        md.out = out_levels ? out_levels[l] : nullptr;
+        md.pred = pred_levels ? pred_levels[l] : nullptr;
+        md.rows = p.hl[l] * p.wl[l];
+        md.height = p.hl[l], md.width = p.wl[l], md.sub = 1, md.level = l, md.anchor = 0;
+        md.image_stride = static_cast<long long>(md.rows) * (num_classes + 5);
+    }
+    return DH_OK;
+}
+
+int fill_retina(RetinaPolicy::Params& p, TileTable& tt, int pad_h, int pad_w, int n_levels, const int32_t* strides,
+                int n_anchors, const float* anchor_hw, float iou_thresh, int num_classes, float* const* out_levels,
+                const float* const* pred_levels, int32_t* num_pairs, const char* who) {
+    DH_FILL_CHECK(n_levels >= 1 && n_levels <= DH_MAX_LEVELS, "%s: n_levels %d", who, n_levels);
+    DH_FILL_CHECK(n_anchors >= 1 && n_anchors <= 12, "%s: n_anchors %d not in [1,12]", who, n_anchors);
+    if (n_levels * n_anchors > DH_MAX_MAPS)
+        return set_error(DH_ERR_CAPACITY, "%s: %d maps > %d", who, n_levels * n_anchors, DH_MAX_MAPS);
+    DH_FILL_CHECK(pad_h > 0 && pad_w > 0, "%s: bad padded size", who);
+    DH_FILL_CHECK(num_classes >= 1 && num_classes <= 4096, "%s: num_classes %d", who, num_classes);
+    p.n_levels = n_levels, p.n_anchors = n_anchors, p.num_classes = num_classes, p.thr = iou_thresh;
+    p.num_pairs = num_pairs;
+    const int ch = num_classes + 4;
+    int m = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        DH_FILL_CHECK(strides[l] > 0, "%s: stride of level %d", who, l);
+        DH_FILL_CHECK((!out_levels || out_levels[l]) && (!pred_levels || pred_levels[l]), "%s: level %d pointer is NULL", who, l);
+        p.stride[l] = strides[l];
+        const int hl = static_cast<int>(static_cast<double>(pad_h) / strides[l]);
+        const int wl = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
+        for (int an = 0; an < n_anchors; ++an, ++m) {
+            p.anchor_h[l][an] = anchor_hw[(l * n_anchors + an) * 2];
+            p.anchor_w[l][an] = anchor_hw[(l * n_anchors + an) * 2 + 1];
+            MapDesc& md = tt.maps[m];
+            md.rows = hl * wl;
+            md.height = hl, md.width = wl, md.sub = 1, md.level = l, md.anchor = an;
+            const long long map_off = static_cast<long long>(an) * md.rows * ch;
+            md.out = out_levels ? out_levels[l] + map_off : nullptr;
+            md.pred = pred_levels ? pred_levels[l] + map_off : nullptr;
+            md.image_stride = static_cast<long long>(n_anchors) * md.rows * ch;
+        }
+    }
+    tt.n_maps = m;
+    return DH_OK;
+}
+
+int fill_centernet(CenterNetPolicy::Params& p, TileTable& tt, int pad0, int pad1, int stride, int n_scales,
+                   const float* box_scales, float sigma, int num_classes, int mode, float* out, const float* pred,
+                   int32_t* status, const char* who) {
+    DH_FILL_CHECK(mode >= 0 && mode <= 2, "%s: mode %d", who, mode);
+    DH_FILL_CHECK(mode != DH_CENTERNET_ONEHOT_SCALES || (box_scales && n_scales >= 1 && n_scales <= 8),
+                  "%s: mode 0 needs 1..8 box_scales", who);
+    DH_FILL_CHECK(pad0 > 0 && pad1 > 0 && stride > 0, "%s: bad sizes", who);
+    DH_FILL_CHECK(num_classes >= 1 && num_classes <= 4096, "%s: num_classes %d", who, num_classes);
+    p.mode = mode, p.num_classes = num_classes, p.stride = stride, p.stride_f = static_cast<float>(stride);
+    p.sigma = sigma, p.pad0 = pad0, p.pad1 = pad1, p.status = status;
+    p.n_scales = (mode == DH_CENTERNET_ONEHOT_SCALES) ? n_scales : 1;
+    for (int n = 0; n < p.n_scales && mode == DH_CENTERNET_ONEHOT_SCALES; ++n) p.scales[n] = box_scales[n];
+    MapDesc& md = tt.maps[0];
+    tt.n_maps = 1;
+    int hh, ww;
+    if (mode == DH_CENTERNET_POWER_FALLOFF) {
+        hh = static_cast<int>(static_cast<double>(pad0) / stride);
+        ww = static_cast<int>(static_cast<double>(pad1) / stride);
+    } else {  // the reference swaps the indices (tf_centernet_resnet_s8.py:259-260)
+        hh = static_cast<int>(static_cast<double>(pad1) / stride);
+        ww = static_cast<int>(static_cast<double>(pad0) / stride);
+    }
+    const int ch = num_classes + (mode == DH_CENTERNET_POWER_FALLOFF ? 5 : 4);
+    md.out = out;
+    md.pred = pred;
+    md.height = hh, md.width = ww, md.sub = p.n_scales, md.level = 0, md.anchor = 0;
+    md.rows = hh * ww * p.n_scales;
+    md.image_stride = static_cast<long long>(md.rows) * ch;
+    return DH_OK;
+}
+
+}  // namespace dh
+
 using namespace dh;
 
 extern "C" {
@@ -59,32 +162,14 @@ int dh_fcos_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, const
                    int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, const float* b_dim,
                    int num_classes, int mode, float* const* out_levels, int32_t* num_targets, void* stream) {
     DH_CHECK_ARG(h && boxes && img_dim && strides && out_levels, "dh_fcos_encode: NULL argument");
-    DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_LEVELS, "dh_fcos_encode: n_levels %d not in [1,%d]", n_levels,
-                 DH_MAX_LEVELS);
-    DH_CHECK_ARG(n_levels == 1 || b_dim, "dh_fcos_encode: b_dim is NULL");
-    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0 && pad_h > 0 && pad_w > 0, "dh_fcos_encode: bad sizes");
+    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_fcos_encode: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_fcos_encode: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DH_CHECK_ARG(num_classes >= 1 && num_classes <= 4096, "dh_fcos_encode: num_classes %d", num_classes);
-    DH_CHECK_ARG(mode >= 0 && mode <= 3, "dh_fcos_encode: mode %d", mode);
     DeviceGuard guard(h->device);
     EncodeArgs<FcosPolicy> a;
     memset(&a, 0, sizeof(a));
-    FcosPolicy::Params& p = a.pp;
-    p.n_levels = n_levels, p.num_classes = num_classes, p.mode = mode, p.num_targets = num_targets;
-    a.tt.n_maps = n_levels;
-    for (int l = 0; l < n_levels; ++l) {
-        DH_CHECK_ARG(strides[l] > 0 && out_levels[l], "dh_fcos_encode: level %d stride/pointer", l);
-        p.stride[l] = strides[l];
-        p.stride_f[l] = static_cast<float>(strides[l]);
-        if (l < n_levels - 1) p.b_dim[l] = b_dim[l];
-        p.hl[l] = static_cast<int>(static_cast<double>(pad_h) / strides[l]);  // int(img_pad[0] / stride)
-        p.wl[l] = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
-        MapDesc& md = a.tt.maps[l];
-        md.out = out_levels[l];
-        md.rows = p.hl[l] * p.wl[l];
-        md.height = p.hl[l], md.width = p.wl[l], md.sub = 1, md.level = l, md.anchor = 0;
-        md.image_stride = static_cast<long long>(md.rows) * (num_classes + 5);
-    }
+    int rc = fill_fcos(a.pp, a.tt, pad_h, pad_w, n_levels, strides, b_dim, num_classes, mode, out_levels, nullptr,
+                       num_targets, "dh_fcos_encode");
+    if (rc) return rc;
     a.tile_buf_bytes = finish_table(a.tt, num_classes + 5, batch, h->tile_bytes);
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     return launch_encode<FcosPolicy>(h, a, static_cast<cudaStream_t>(stream), "dh_fcos_encode");
@@ -95,39 +180,16 @@ int dh_retina_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, con
                      const float* anchor_hw, float iou_thresh, int num_classes, float* const* out_levels,
                      int32_t* num_pairs, void* stream) {
     DH_CHECK_ARG(h && boxes && img_dim && strides && anchor_hw && out_levels, "dh_retina_encode: NULL argument");
-    DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_LEVELS, "dh_retina_encode: n_levels %d", n_levels);
-    DH_CHECK_ARG(n_anchors >= 1 && n_anchors <= 12, "dh_retina_encode: n_anchors %d not in [1,12]", n_anchors);
-    if (n_levels * n_anchors > DH_MAX_MAPS)
-        return set_error(DH_ERR_CAPACITY, "dh_retina_encode: %d maps > %d", n_levels * n_anchors, DH_MAX_MAPS);
-    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0 && pad_h > 0 && pad_w > 0, "dh_retina_encode: bad sizes");
+    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_retina_encode: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_retina_encode: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DH_CHECK_ARG(num_classes >= 1 && num_classes <= 4096, "dh_retina_encode: num_classes %d", num_classes);
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EncodeArgs<RetinaPolicy> a;
     memset(&a, 0, sizeof(a));
-    RetinaPolicy::Params& p = a.pp;
-    p.n_levels = n_levels, p.n_anchors = n_anchors, p.num_classes = num_classes, p.thr = iou_thresh;
-    p.num_pairs = num_pairs;
-    const int ch = num_classes + 4;
-    int m = 0;
-    for (int l = 0; l < n_levels; ++l) {
-        DH_CHECK_ARG(strides[l] > 0 && out_levels[l], "dh_retina_encode: level %d stride/pointer", l);
-        p.stride[l] = strides[l];
-        const int hl = static_cast<int>(static_cast<double>(pad_h) / strides[l]);
-        const int wl = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
-        for (int an = 0; an < n_anchors; ++an, ++m) {
-            p.anchor_h[l][an] = anchor_hw[(l * n_anchors + an) * 2];
-            p.anchor_w[l][an] = anchor_hw[(l * n_anchors + an) * 2 + 1];
-            MapDesc& md = a.tt.maps[m];
-            md.rows = hl * wl;
-            md.height = hl, md.width = wl, md.sub = 1, md.level = l, md.anchor = an;
-            md.out = out_levels[l] + static_cast<long long>(an) * md.rows * ch;
-            md.image_stride = static_cast<long long>(n_anchors) * md.rows * ch;
-        }
-    }
-    a.tt.n_maps = m;
-    a.tile_buf_bytes = finish_table(a.tt, ch, batch, h->tile_bytes);
+    int rc = fill_retina(a.pp, a.tt, pad_h, pad_w, n_levels, strides, n_anchors, anchor_hw, iou_thresh, num_classes,
+                         out_levels, nullptr, num_pairs, "dh_retina_encode");
+    if (rc) return rc;
+    a.tile_buf_bytes = finish_table(a.tt, num_classes + 4, batch, h->tile_bytes);
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (num_pairs && batch > 0) DH_CUDA(cudaMemsetAsync(num_pairs, 0, sizeof(int32_t) * batch, st));
     return launch_encode<RetinaPolicy>(h, a, st, "dh_retina_encode");
@@ -137,36 +199,16 @@ int dh_centernet_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, 
                         int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
                         float sigma, int num_classes, int mode, float* out, int32_t* status, void* stream) {
     DH_CHECK_ARG(h && boxes && img_dim && out, "dh_centernet_encode: NULL argument");
-    DH_CHECK_ARG(mode >= 0 && mode <= 2, "dh_centernet_encode: mode %d", mode);
-    DH_CHECK_ARG(mode != DH_CENTERNET_ONEHOT_SCALES || (box_scales && n_scales >= 1 && n_scales <= 8),
-                 "dh_centernet_encode: mode 0 needs 1..8 box_scales");
-    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0 && pad0 > 0 && pad1 > 0 && stride > 0, "dh_centernet_encode: bad sizes");
+    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_centernet_encode: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_centernet_encode: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DH_CHECK_ARG(num_classes >= 1 && num_classes <= 4096, "dh_centernet_encode: num_classes %d", num_classes);
     DeviceGuard guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EncodeArgs<CenterNetPolicy> a;
     memset(&a, 0, sizeof(a));
-    CenterNetPolicy::Params& p = a.pp;
-    p.mode = mode, p.num_classes = num_classes, p.stride = stride, p.stride_f = static_cast<float>(stride);
-    p.sigma = sigma, p.pad0 = pad0, p.pad1 = pad1, p.status = status;
-    p.n_scales = (mode == DH_CENTERNET_ONEHOT_SCALES) ? n_scales : 1;
-    for (int n = 0; n < p.n_scales && mode == DH_CENTERNET_ONEHOT_SCALES; ++n) p.scales[n] = box_scales[n];
-    MapDesc& md = a.tt.maps[0];
-    a.tt.n_maps = 1;
-    int hh, ww;
-    if (mode == DH_CENTERNET_POWER_FALLOFF) {
-        hh = static_cast<int>(static_cast<double>(pad0) / stride);
-        ww = static_cast<int>(static_cast<double>(pad1) / stride);
-    } else {  // reference swaps the indices (tf_centernet_resnet_s8.py:259-260)
-        hh = static_cast<int>(static_cast<double>(pad1) / stride);
-        ww = static_cast<int>(static_cast<double>(pad0) / stride);
-    }
+    int rc = fill_centernet(a.pp, a.tt, pad0, pad1, stride, n_scales, box_scales, sigma, num_classes, mode, out, nullptr,
+                            status, "dh_centernet_encode");
+    if (rc) return rc;
     const int ch = num_classes + (mode == DH_CENTERNET_POWER_FALLOFF ? 5 : 4);
-    md.out = out;
-    md.height = hh, md.width = ww, md.sub = p.n_scales, md.level = 0, md.anchor = 0;
-    md.rows = hh * ww * p.n_scales;
-    md.image_stride = static_cast<long long>(md.rows) * ch;
     a.tile_buf_bytes = finish_table(a.tt, ch, batch, h->tile_bytes);
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));

@@ -1,0 +1,182 @@
+// C-ABI launchers for the dense-head losses, unfused (targets in HBM) and fused encode+loss.
+#include <cstring>
+
+#include "dh_host.h"
+#include "dh_launch.h"
+#include "dh_loss_kernel.cuh"
+
+namespace dh {
+
+static int check_spec(const LossSpec& s, const char* who) {
+    if (!(s.reg_ch == 0 || s.reg_ch == 4)) return set_error(DH_ERR_BAD_ARG, "%s: reg_ch must be 0 or 4", who);
+    if (s.cen_mode < 0 || s.cen_mode > 3) return set_error(DH_ERR_BAD_ARG, "%s: cen_mode %d", who, s.cen_mode);
+    if (s.reg_mode < 0 || s.reg_mode > 1) return set_error(DH_ERR_BAD_ARG, "%s: reg_mode %d", who, s.reg_mode);
+    if (s.pos_rule < 0 || s.pos_rule > 2) return set_error(DH_ERR_BAD_ARG, "%s: pos_rule %d", who, s.pos_rule);
+    return DH_OK;
+}
+
+template <class P, bool kFused>
+static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, float* out_total, cudaStream_t st,
+                       const char* who) {
+    const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
+    if (a.tt.batch == 0) return DH_OK;
+    // scratch: tile partials + (optional) per-image sums when the caller only wants the total
+    const size_t part_bytes = static_cast<size_t>(total) * 16;
+    const size_t img_bytes = static_cast<size_t>(a.tt.batch) * 16;
+    char* sc = static_cast<char*>(scratch(h, part_bytes + img_bytes + 256));
+    if (!sc) return DH_ERR_CUDA;
+    a.partials = reinterpret_cast<float*>(sc);
+    float* per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
+    const LossSmemLayout lay = loss_smem_layout<P, kFused>(a.tile_buf_bytes, a.tt.rows_per_tile);
+    if (lay.total > 227 * 1024)
+        return set_error(DH_ERR_CAPACITY, "%s: needs %d bytes of shared memory", who, lay.total);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DH_CUDA(cudaFuncSetAttribute(loss_kernel<P, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    int per_sm = (227 * 1024) / (lay.total + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    long long grid = static_cast<long long>(h->sm_count) * per_sm;
+    if (grid > total) grid = total;
+    if (total > 0) {
+        loss_kernel<P, kFused><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+        DH_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    loss_finalize_images<<<a.tt.batch, 128, 0, st>>>(a.partials, a.tt.tiles_per_image, per_image);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    if (out_total) {
+        loss_finalize_total<<<1, 256, 0, st>>>(per_image, a.tt.batch, out_total);
+        DH_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    return DH_OK;
+}
+
+static int loss_tile_bytes(const dh_handle_s* h) {
+    int b = h->tile_bytes / 2;
+    return b < 4096 ? 4096 : b;
+}
+
+}  // namespace dh
+
+using namespace dh;
+
+extern "C" {
+
+int dh_dense_loss(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
+                  const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
+                  const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                  float alpha, float gamma, float delta, float* out_per_image, float* out_total, void* stream) {
+    DH_CHECK_ARG(h && target_maps && pred_maps && map_height && map_width, "dh_dense_loss: NULL argument");
+    DH_CHECK_ARG(n_maps >= 1 && n_maps <= DH_MAX_MAPS, "dh_dense_loss: n_maps %d not in [1,%d]", n_maps, DH_MAX_MAPS);
+    DH_CHECK_ARG(batch >= 0 && ch >= 1, "dh_dense_loss: bad sizes");
+    DH_CHECK_ARG(out_per_image || out_total, "dh_dense_loss: no output requested");
+    LossArgs<NoPolicy> a;
+    memset(&a, 0, sizeof(a));
+    a.spec.reg_ch = reg_ch, a.spec.cen_mode = cen_mode, a.spec.reg_mode = reg_mode, a.spec.pos_rule = pos_rule;
+    a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
+    int rc = check_spec(a.spec, "dh_dense_loss");
+    if (rc) return rc;
+    DH_CHECK_ARG(ch >= reg_ch + (cen_mode != 0 ? 1 : 0), "dh_dense_loss: ch %d too small for the channel layout", ch);
+    DH_CHECK_ARG(pos_rule != 2 || mask_maps, "dh_dense_loss: pos_rule 2 needs mask_maps");
+    DeviceGuard guard(h->device);
+    a.tt.n_maps = n_maps;
+    for (int m = 0; m < n_maps; ++m) {
+        DH_CHECK_ARG(target_maps[m] && pred_maps[m], "dh_dense_loss: map %d pointer is NULL", m);
+        DH_CHECK_ARG(pos_rule != 2 || mask_maps[m], "dh_dense_loss: mask %d pointer is NULL", m);
+        MapDesc& md = a.tt.maps[m];
+        md.out = const_cast<float*>(target_maps[m]);
+        md.pred = pred_maps[m];
+        md.height = map_height[m], md.width = map_width[m], md.sub = map_sub ? map_sub[m] : 1;
+        DH_CHECK_ARG(md.height >= 0 && md.width >= 0 && md.sub >= 1, "dh_dense_loss: map %d shape", m);
+        md.rows = md.height * md.width * md.sub;
+        md.image_stride = static_cast<long long>(md.rows) * ch;
+        md.level = m, md.anchor = 0;
+        a.mask_maps[m] = mask_maps ? mask_maps[m] : nullptr;
+    }
+    a.tile_buf_bytes = finish_table(a.tt, ch, batch, loss_tile_bytes(h));
+    return launch_loss<NoPolicy, false>(h, a, out_per_image, out_total, static_cast<cudaStream_t>(stream), "dh_dense_loss");
+}
+
+int dh_fcos_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                        int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, const float* b_dim,
+                        int num_classes, int mode, const float* const* pred_levels, int reg_mode, int cen_mode,
+                        float alpha, float gamma, float delta, float* out_per_image, float* out_total,
+                        int32_t* num_targets, void* stream) {
+    DH_CHECK_ARG(h && boxes && img_dim && strides && pred_levels, "dh_fcos_encode_loss: NULL argument");
+    DH_CHECK_ARG(out_per_image || out_total, "dh_fcos_encode_loss: no output requested");
+    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_fcos_encode_loss: bad sizes");
+    if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_fcos_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
+    DeviceGuard guard(h->device);
+    LossArgs<FcosPolicy> a;
+    memset(&a, 0, sizeof(a));
+    int rc = fill_fcos(a.pp, a.tt, pad_h, pad_w, n_levels, strides, b_dim, num_classes, mode, nullptr, pred_levels,
+                          num_targets, "dh_fcos_encode_loss");
+    if (rc) return rc;
+    a.spec.reg_ch = 4, a.spec.cen_mode = cen_mode, a.spec.reg_mode = reg_mode, a.spec.pos_rule = 0;
+    a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
+    DH_CHECK_ARG(cen_mode >= 1 && cen_mode <= 3, "dh_fcos_encode_loss: cen_mode must be 1, 2 or 3");
+    rc = check_spec(a.spec, "dh_fcos_encode_loss");
+    if (rc) return rc;
+    a.tile_buf_bytes = finish_table(a.tt, num_classes + 5, batch, loss_tile_bytes(h));
+    a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    return launch_loss<FcosPolicy, true>(h, a, out_per_image, out_total, static_cast<cudaStream_t>(stream), "dh_fcos_encode_loss");
+}
+
+int dh_retina_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                          int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, int n_anchors,
+                          const float* anchor_hw, float iou_thresh, int num_classes, const float* const* pred_levels,
+                          float alpha, float gamma, float delta, float* out_per_image, float* out_total,
+                          int32_t* num_pairs, void* stream) {
+    DH_CHECK_ARG(h && boxes && img_dim && strides && anchor_hw && pred_levels, "dh_retina_encode_loss: NULL argument");
+    DH_CHECK_ARG(out_per_image || out_total, "dh_retina_encode_loss: no output requested");
+    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_retina_encode_loss: bad sizes");
+    if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_retina_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LossArgs<RetinaPolicy> a;
+    memset(&a, 0, sizeof(a));
+    int rc = fill_retina(a.pp, a.tt, pad_h, pad_w, n_levels, strides, n_anchors, anchor_hw, iou_thresh, num_classes,
+                            nullptr, pred_levels, num_pairs, "dh_retina_encode_loss");
+    if (rc) return rc;
+    a.spec.reg_ch = 4, a.spec.cen_mode = 0, a.spec.reg_mode = 0, a.spec.pos_rule = 1;
+    a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
+    a.tile_buf_bytes = finish_table(a.tt, num_classes + 4, batch, loss_tile_bytes(h));
+    a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    if (num_pairs && batch > 0) DH_CUDA(cudaMemsetAsync(num_pairs, 0, sizeof(int32_t) * batch, st));
+    return launch_loss<RetinaPolicy, true>(h, a, out_per_image, out_total, st, "dh_retina_encode_loss");
+}
+
+int dh_centernet_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                             int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
+                             float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                             float gamma, float delta, float* out_per_image, float* out_total, int32_t* status,
+                             void* stream) {
+    DH_CHECK_ARG(h && boxes && img_dim && pred, "dh_centernet_encode_loss: NULL argument");
+    DH_CHECK_ARG(out_per_image || out_total, "dh_centernet_encode_loss: no output requested");
+    DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_centernet_encode_loss: bad sizes");
+    if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_centernet_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LossArgs<CenterNetPolicy> a;
+    memset(&a, 0, sizeof(a));
+    int rc = fill_centernet(a.pp, a.tt, pad0, pad1, stride, n_scales, box_scales, sigma, num_classes, mode, nullptr,
+                               pred, status, "dh_centernet_encode_loss");
+    if (rc) return rc;
+    const bool falloff = mode == DH_CENTERNET_POWER_FALLOFF;
+    a.spec.reg_ch = 4, a.spec.cen_mode = falloff ? 1 : 0, a.spec.reg_mode = falloff ? reg_mode : 0;
+    a.spec.pos_rule = falloff ? 0 : 1;  // tf_centernet.py:435 (>= 1) vs tf_centernet_resnet_s8.py:376 (> 0)
+    a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
+    rc = check_spec(a.spec, "dh_centernet_encode_loss");
+    if (rc) return rc;
+    a.tile_buf_bytes = finish_table(a.tt, num_classes + (falloff ? 5 : 4), batch, loss_tile_bytes(h));
+    a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    return launch_loss<CenterNetPolicy, true>(h, a, out_per_image, out_total, st, "dh_centernet_encode_loss");
+}
+
+}  // extern "C"

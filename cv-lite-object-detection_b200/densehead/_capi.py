@@ -54,6 +54,11 @@ def lib():
         L.dh_fcos_encode.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, c_fp, I, I, ctypes.POINTER(c_vp), P, P]
         L.dh_retina_encode.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, I, c_fp, F, I, ctypes.POINTER(c_vp), P, P]
         L.dh_centernet_encode.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, P, P]
+        PP = ctypes.POINTER(c_vp)
+        L.dh_dense_loss.argtypes = [P, I, PP, PP, PP, c_ip, c_ip, c_ip, I, I, I, I, I, I, F, F, F, P, P, P]
+        L.dh_fcos_encode_loss.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, c_fp, I, I, PP, I, I, F, F, F, P, P, P, P]
+        L.dh_retina_encode_loss.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, I, c_fp, F, I, PP, F, F, F, P, P, P, P]
+        L.dh_centernet_encode_loss.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, I, F, F, F, P, P, P, P]
         for name, proto in _OPTIONAL.items():
             if hasattr(L, name):
                 getattr(L, name).argtypes = proto

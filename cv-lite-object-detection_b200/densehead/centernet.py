@@ -3,7 +3,7 @@ CenterNet/tf_centernet_hourglass.py and CenterNet/tf_centernet.py of the referen
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, losses
 from ._batch import image_dims, pack_labels
 from ._tensors import as_host, current_device, stream_ptr, to_device
 
@@ -80,3 +80,63 @@ def format_data(gt_labels, img_dim, num_classes, img_pad=None, stride=8, sigma=0
     g, dim, pad, boxes, nbox = _prep(gt_labels, img_dim, img_pad)
     out, _ = format_data_batch(boxes, nbox, dim[None], num_classes, pad, stride, "falloff", sigma=sigma)
     return out[0]
+
+
+# ---- losses -------------------------------------------------------------------------------------
+def model_loss_s8(y_true, y_pred):
+    """CenterNet/tf_centernet_resnet_s8.py:368 `model_loss` on [B, H, W, S, C+4] -> (cls_loss, reg_loss)."""
+    dev = current_device()
+    yt = to_device(y_true, torch.float32, dev).contiguous()
+    yp = to_device(y_pred, torch.float32, dev).contiguous()
+    b, h, w, s, ch = (int(v) for v in yp.shape)
+    _, tot = losses.dense_loss([yt], [yp], [(h, w, s)], b, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_GT0)
+    return tot[0], tot[1]
+
+
+def model_loss_hourglass(y_true, y_pred):
+    """CenterNet/tf_centernet_hourglass.py:492 `model_loss` on [B, H, W, C+4] -> (cls_loss, reg_loss)."""
+    dev = current_device()
+    yt = to_device(y_true, torch.float32, dev).contiguous()
+    yp = to_device(y_pred, torch.float32, dev).contiguous()
+    b, h, w, ch = (int(v) for v in yp.shape)
+    _, tot = losses.dense_loss([yt], [yp], [(h, w, 1)], b, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_GT0)
+    return tot[0], tot[1]
+
+
+def model_loss(y_true, y_pred, reg_type="l1", cen_type="l1"):
+    """CenterNet/tf_centernet.py:428 `model_loss`: y_true [H, W, C+5], y_pred [1, H, W, C+5] (or batched)."""
+    dev = current_device()
+    yt = to_device(y_true, torch.float32, dev)
+    yp = to_device(y_pred, torch.float32, dev)
+    if yt.dim() == 3:
+        yt = yt.unsqueeze(0)
+    if yp.dim() == 3:
+        yp = yp.unsqueeze(0)
+    b, h, w, ch = (int(v) for v in yp.shape)
+    cen = losses.CEN_SMOOTH_L1 if cen_type.lower() == "l1" else losses.CEN_IGNORE
+    reg = losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1
+    _, tot = losses.dense_loss([yt.contiguous()], [yp.contiguous()], [(h, w, 1)], b, ch, 4, cen, reg, losses.POS_GE1)
+    return tot[0], tot[1], tot[2]
+
+
+def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride=8, mode="s8", box_scales=None,
+                      sigma=0.25, reg_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+    """Fused CenterNet encode + loss.  Returns (per_image [B,4], total [4], status [1])."""
+    dev = current_device()
+    boxes_d = to_device(boxes, torch.float32, dev)
+    batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
+    nbox_d = to_device(nbox, torch.int32, dev)
+    dims_d = to_device(image_dims(img_dim, batch) if not isinstance(img_dim, torch.Tensor) or not img_dim.is_cuda
+                       else img_dim, torch.float32, dev)
+    yp = to_device(y_pred, torch.float32, dev).contiguous()
+    scales = [float(v) for v in (box_scales if box_scales is not None else [])]
+    out_pi = torch.empty((batch, 4), dtype=torch.float32, device=dev)
+    out_tot = torch.empty((4,), dtype=torch.float32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().dh_centernet_encode_loss(
+        _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
+        int(img_pad[0]), int(img_pad[1]), int(stride), len(scales), _capi.float_array(scales) if scales else None,
+        float(sigma), int(num_classes), MODES[mode], yp.data_ptr(),
+        losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1, float(alpha), float(gamma), float(delta),
+        out_pi.data_ptr(), out_tot.data_ptr(), status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode_loss")
+    return out_pi, out_tot, status

@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, losses
 from ._batch import image_dims, pack_labels
 from ._tensors import as_host, current_device, stream_ptr, to_device
 
@@ -88,3 +88,84 @@ def format_data_center(gt_labels, img_dim, num_classes, img_pad=None, b_dim=None
 def format_data_center_v1(gt_labels, img_dim, num_classes, img_pad=None, b_dim=None, strides=None, center_only=False):
     """FCOS/fcos_center_v1.py:149 `format_data` (centre cell, YOLO-style offsets; `center_only` unused)."""
     return _single(gt_labels, img_dim, num_classes, img_pad, strides, b_dim, "center_v1")
+
+
+# ---- losses -------------------------------------------------------------------------------------
+def _as_batched(maps, dev):
+    """Accept per-level [Hl, Wl, ch], [1, Hl, Wl, ch] (the reference's `y_pred[l]`) or [B, Hl, Wl, ch]."""
+    out = []
+    for m in maps:
+        t = to_device(m, torch.float32, dev)
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        if t.dim() != 4:
+            raise ValueError("expected [Hl, Wl, ch] or [B, Hl, Wl, ch] maps")
+        out.append(t.contiguous())
+    return out
+
+
+def model_loss_batch(y_true, y_pred, reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+    """Loss over materialised FCOS targets for a batch -> (per_image [B,4], total [4]) = {cls, reg, cen, n_pos}."""
+    dev = current_device()
+    yt, yp = _as_batched(y_true, dev), _as_batched(y_pred, dev)
+    batch, ch = int(yp[0].shape[0]), int(yp[0].shape[-1])
+    shapes = [(int(p.shape[1]), int(p.shape[2]), 1) for p in yp]
+    cen = {"l1": losses.CEN_SMOOTH_L1, "focal": losses.CEN_FOCAL}.get(cen_type.lower(), losses.CEN_IGNORE)
+    reg = losses.REG_IOU if reg_type == "iou" else losses.REG_SMOOTH_L1
+    return losses.dense_loss(yt, yp, shapes, batch, ch, 4, cen, reg, losses.POS_GE1, alpha, gamma, delta, stream=stream)
+
+
+def model_loss(y_true, y_pred, strides=None, reg_type="l1", cen_type="l1", cls_lambda=2.5, reg_lambda=1.0):
+    """FCOS/fcos.py:464 `model_loss` -> (cls_loss, reg_loss, cen_loss) device scalars.  `strides`,
+    `cls_lambda`, `reg_lambda` are accepted and unused, as in the reference.  With cen_type other than
+    "l1" the centerness loss is 0 (fcos.py:483-486); use `model_loss_center` for the focal variant."""
+    _, tot = model_loss_batch(y_true, y_pred, reg_type, cen_type if cen_type.lower() == "l1" else "none")
+    return tot[0], tot[1], tot[2]
+
+
+def model_loss_center(y_true, y_pred, reg_type="l1", cen_type="l1"):
+    """FCOS/fcos_center.py:365 `model_loss` (centerness smooth-L1 or focal)."""
+    _, tot = model_loss_batch(y_true, y_pred, reg_type, "l1" if cen_type.lower() == "l1" else "focal")
+    return tot[0], tot[1], tot[2]
+
+
+def model_loss_center_v1(y_true, y_pred):
+    """FCOS/fcos_center_v1.py:294 `model_loss` (focal centerness, smooth-L1 boxes)."""
+    _, tot = model_loss_batch(y_true, y_pred, "l1", "focal")
+    return tot[0], tot[1], tot[2]
+
+
+def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, strides=None, b_dim=None, mode="fcos",
+                      reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+    """Fused target encoding + loss: targets never reach HBM.  y_pred: per-level [B, Hl, Wl, C+5].
+    Returns (per_image [B,4], total [4], num_targets [B, n_levels])."""
+    strides = list(DEFAULT_STRIDES if strides is None else strides)
+    b_dim = list(DEFAULT_B_DIM if b_dim is None else b_dim)
+    dev = current_device()
+    boxes_d = to_device(boxes, torch.float32, dev)
+    batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
+    nbox_d = to_device(nbox, torch.int32, dev)
+    dims_d = to_device(image_dims(img_dim, batch) if not isinstance(img_dim, torch.Tensor) or not img_dim.is_cuda
+                       else img_dim, torch.float32, dev)
+    yp = _as_batched(y_pred, dev)
+    shapes = level_shapes((int(img_pad[0]), int(img_pad[1])), strides)
+    for p, (h, w) in zip(yp, shapes):
+        if tuple(p.shape) != (batch, h, w, num_classes + 5):
+            raise ValueError("prediction level has shape %r, expected %r" % (tuple(p.shape), (batch, h, w, num_classes + 5)))
+    out_pi = torch.empty((batch, 4), dtype=torch.float32, device=dev)
+    out_tot = torch.empty((4,), dtype=torch.float32, device=dev)
+    cnt = torch.empty((batch, len(strides)), dtype=torch.int32, device=dev)
+    cen = {"l1": losses.CEN_SMOOTH_L1, "focal": losses.CEN_FOCAL}.get(cen_type.lower(), losses.CEN_IGNORE)
+    reg = losses.REG_IOU if reg_type == "iou" else losses.REG_SMOOTH_L1
+    _capi.check(_capi.lib().dh_fcos_encode_loss(
+        _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
+        int(img_pad[0]), int(img_pad[1]), len(strides), _capi.int_array(strides), _capi.float_array(b_dim),
+        int(num_classes), MODES[mode], _capi.ptr_array([p.data_ptr() for p in yp]), reg, cen, float(alpha),
+        float(gamma), float(delta), out_pi.data_ptr(), out_tot.data_ptr(), cnt.data_ptr(), stream_ptr(stream)),
+        "dh_fcos_encode_loss")
+    return out_pi, out_tot, cnt
+
+
+focal_loss = losses.focal_loss
+smooth_l1_loss = losses.smooth_l1_loss
+iou_loss = losses.iou_loss

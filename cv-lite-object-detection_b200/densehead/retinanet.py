@@ -10,7 +10,7 @@ import math
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, losses
 from ._batch import image_dims, pack_labels
 from ._tensors import as_host, current_device, stream_ptr, to_device
 
@@ -71,6 +71,69 @@ def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, anchor_hw=None
     return out, num_pairs
 
 
+def _pack_levels(x, n_anchors, dev):
+    """`x[level][anchor]` maps ([Hl, Wl, ch] or [1, Hl, Wl, ch]) or packed [B, A, Hl, Wl, ch] per level."""
+    out = []
+    for lv in x:
+        if isinstance(lv, (list, tuple)):
+            maps = [to_device(m, torch.float32, dev) for m in lv]
+            maps = [m[0] if m.dim() == 4 else m for m in maps]
+            lv = torch.stack(maps).unsqueeze(0)
+        else:
+            lv = to_device(lv, torch.float32, dev)
+        if lv.dim() != 5 or lv.shape[1] != n_anchors:
+            raise ValueError("expected [B, A, Hl, Wl, ch] per level")
+        out.append(lv.contiguous())
+    return out
+
+
+def loss_batch(x_label, x_pred, n_anchors=9, alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+    """Loss over materialised RetinaNet targets -> (per_image [B,4], total [4]) = {cls, reg, 0, n_pos}."""
+    dev = current_device()
+    yt, yp = _pack_levels(x_label, n_anchors, dev), _pack_levels(x_pred, n_anchors, dev)
+    batch, ch = int(yp[0].shape[0]), int(yp[0].shape[-1])
+    shapes = [(int(p.shape[2]), int(p.shape[3]), 1) for p in yp]
+    if batch == 1:  # [1, A, Hl, Wl, ch]: the anchor axis folds into rows
+        shapes = [(int(p.shape[1]) * int(p.shape[2]), int(p.shape[3]), 1) for p in yp]
+        return losses.dense_loss(yt, yp, shapes, 1, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_GT0,
+                                 alpha, gamma, delta, stream=stream)
+    # batch-major packed layout: image stride covers all anchors, so fold anchors into rows as well
+    shapes = [(int(p.shape[1]) * int(p.shape[2]), int(p.shape[3]), 1) for p in yp]
+    return losses.dense_loss(yt, yp, shapes, batch, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_GT0,
+                             alpha, gamma, delta, stream=stream)
+
+
+def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, x_pred, anchor_hw=None, iou_thresh=0.5,
+                      strides=None, alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+    """Fused match + encode + loss (targets never reach HBM).  x_pred: per-level [B, A, Hl, Wl, C+4].
+    Returns (per_image [B,4], total [4], num_pairs [B])."""
+    strides = list(STRIDES if strides is None else strides)
+    table = anchor_table() if anchor_hw is None else np.ascontiguousarray(anchor_hw, dtype=np.float32)
+    n_levels, n_anchors = table.shape[0], table.shape[1]
+    dev = current_device()
+    boxes_d = to_device(boxes, torch.float32, dev)
+    batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
+    nbox_d = to_device(nbox, torch.int32, dev)
+    dims_d = to_device(image_dims(img_dim, batch) if not isinstance(img_dim, torch.Tensor) or not img_dim.is_cuda
+                       else img_dim, torch.float32, dev)
+    yp = _pack_levels(x_pred, n_anchors, dev)
+    pad_h, pad_w = int(img_pad[0]), int(img_pad[1])
+    for p, s in zip(yp, strides):
+        want = (batch, n_anchors, int(pad_h / s), int(pad_w / s), num_classes + 4)
+        if tuple(p.shape) != want:
+            raise ValueError("prediction level has shape %r, expected %r" % (tuple(p.shape), want))
+    out_pi = torch.empty((batch, 4), dtype=torch.float32, device=dev)
+    out_tot = torch.empty((4,), dtype=torch.float32, device=dev)
+    pairs = torch.empty((batch,), dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().dh_retina_encode_loss(
+        _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax, pad_h, pad_w,
+        n_levels, _capi.int_array(strides), n_anchors, _capi.float_array(table.reshape(-1).tolist()),
+        float(iou_thresh), int(num_classes), _capi.ptr_array([p.data_ptr() for p in yp]), float(alpha), float(gamma),
+        float(delta), out_pi.data_ptr(), out_tot.data_ptr(), pairs.data_ptr(), stream_ptr(stream)),
+        "dh_retina_encode_loss")
+    return out_pi, out_tot, pairs
+
+
 class RetinaNetHead:
     """The reference `RetinaNet` class (RetinaNet/retinanet_module.py:162-569) without its Keras model."""
 
@@ -99,3 +162,12 @@ class RetinaNetHead:
         outs, pairs = format_data_batch(boxes, nbox, dim[None], self.n_class, pad, self.anchor_table, iou_thresh,
                                         self.strides)
         return [[o[0, a] for a in range(self.n_anchors)] for o in outs], int(pairs[0].item())
+
+    focal_loss = staticmethod(losses.focal_loss)
+    smooth_l1_loss = staticmethod(losses.smooth_l1_loss)
+
+    def loss(self, x_pred, x_label):
+        """retinanet_module.py:403 `train_loss` without the model forward: `x_pred[level][anchor]` are the
+        head outputs ([1, Hl, Wl, C+4]), `x_label` what `format_data` returned.  -> (cls_loss, reg_loss)."""
+        _, tot = loss_batch(x_label, x_pred, self.n_anchors)
+        return tot[0], tot[1]

@@ -105,6 +105,71 @@ int dh_centernet_encode(dh_handle_t h,
                         float* out /*[dev]*/, int32_t* status /*[dev] or NULL*/,
                         void* stream);
 
+/* ---- losses --------------------------------------------------------------------------------- */
+
+/* Channel layout of a row: [0, reg_ch) box regression, then one centerness channel if cen_mode != 0,
+ * then the class channels.  All sums are over every element (the reference never normalises).
+ *   cen_mode  DH_CEN_NONE      no centerness channel (RetinaNet, CenterNet s8 / hourglass)
+ *             DH_CEN_SMOOTH_L1 smooth-L1(target, sigmoid(pred)) over ALL rows (FCOS/fcos.py:483-486)
+ *             DH_CEN_FOCAL     focal(target, pred) (FCOS/fcos_center.py:387-389, fcos_center_v1.py:308-310)
+ *             DH_CEN_IGNORE    channel present, contributes 0 (fcos.py model_loss with cen_type != "l1")
+ *   reg_mode  DH_REG_SMOOTH_L1 where(|d| < delta, d^2/2, |d|) over positive rows (FCOS/fcos.py:380-391)
+ *             DH_REG_IOU       -log(IoU + 1e-12) on the integer grid over positive rows (FCOS/fcos.py:393-441)
+ *   pos_rule  DH_POS_GE1 max(class) >= 1 (fcos.py:475-477), DH_POS_GT0 max(class) > 0
+ *             (retinanet_module.py:416-418), DH_POS_MASK caller-supplied per-row float mask.
+ * Outputs are float32 {cls, reg, cen, n_pos}: out_per_image [B,4] and/or out_total [4] (either may be
+ * NULL, not both).  Summation order is fixed, so results are run-to-run deterministic.            */
+#define DH_CEN_NONE 0
+#define DH_CEN_SMOOTH_L1 1
+#define DH_CEN_FOCAL 2
+#define DH_CEN_IGNORE 3
+#define DH_REG_SMOOTH_L1 0
+#define DH_REG_IOU 1
+#define DH_POS_GE1 0
+#define DH_POS_GT0 1
+#define DH_POS_MASK 2
+
+/* Loss over materialised targets: replaces focal_loss / smooth_l1_loss / iou_loss / model_loss
+ * (FCOS/fcos.py:380-496 and the identical copies in fcos_center*.py, retinanet_module.py:367-426,
+ * tf_centernet*.py).  Map m holds [B, H_m*W_m*sub_m, ch] rows, targets and predictions alike.     */
+int dh_dense_loss(dh_handle_t h, int n_maps,
+                  const float* const* target_maps /*[host] n_maps [dev] ptrs*/,
+                  const float* const* pred_maps /*[host] n_maps [dev] ptrs*/,
+                  const float* const* mask_maps /*[host] n_maps [dev] ptrs [B,rows], DH_POS_MASK only, else NULL*/,
+                  const int32_t* map_height /*[host]*/, const int32_t* map_width /*[host]*/,
+                  const int32_t* map_sub /*[host] rows per cell, or NULL (=1)*/,
+                  int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                  float alpha, float gamma, float delta,
+                  float* out_per_image /*[dev] [B,4] or NULL*/, float* out_total /*[dev] [4] or NULL*/,
+                  void* stream);
+
+/* Fused encode + loss: targets are generated in shared memory and consumed there; HBM traffic is one
+ * read of the predictions.  Same target semantics as the matching dh_*_encode call, same loss
+ * semantics as dh_dense_loss.  pred_levels[l] has the layout of the corresponding out_levels[l].   */
+int dh_fcos_encode_loss(dh_handle_t h,
+                        const float* boxes, const int32_t* nbox, const float* img_dim,
+                        int batch, int max_boxes, int pad_h, int pad_w,
+                        int n_levels, const int32_t* strides, const float* b_dim,
+                        int num_classes, int mode,
+                        const float* const* pred_levels /*[host] n_levels [dev] ptrs [B,Hl,Wl,C+5]*/,
+                        int reg_mode, int cen_mode, float alpha, float gamma, float delta,
+                        float* out_per_image, float* out_total, int32_t* num_targets, void* stream);
+int dh_retina_encode_loss(dh_handle_t h,
+                          const float* boxes, const int32_t* nbox, const float* img_dim,
+                          int batch, int max_boxes, int pad_h, int pad_w,
+                          int n_levels, const int32_t* strides, int n_anchors, const float* anchor_hw,
+                          float iou_thresh, int num_classes,
+                          const float* const* pred_levels /*[host] n_levels [dev] ptrs [B,A,Hl,Wl,C+4]*/,
+                          float alpha, float gamma, float delta,
+                          float* out_per_image, float* out_total, int32_t* num_pairs, void* stream);
+int dh_centernet_encode_loss(dh_handle_t h,
+                             const float* boxes, const int32_t* nbox, const float* img_dim,
+                             int batch, int max_boxes, int pad0, int pad1, int stride,
+                             int n_scales, const float* box_scales, float sigma, int num_classes, int mode,
+                             const float* pred /*[dev] same layout as dh_centernet_encode's out*/,
+                             int reg_mode /*mode 2 only*/, float alpha, float gamma, float delta,
+                             float* out_per_image, float* out_total, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

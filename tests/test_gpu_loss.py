@@ -1,0 +1,147 @@
+"""CUDA losses (unfused over materialised targets, and fused encode+loss) vs the golden values frozen
+from the reference and vs the CPU oracle.  Tolerance: 1e-5 relative (north_star) on every loss scalar;
+positive counts exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import dense_head_ref as O  # noqa: E402
+from oracle import synth  # noqa: E402
+from conftest import assert_close  # noqa: E402
+
+SCALES = [32, 64, 128, 256, 512]
+RTOL = 1e-5
+
+
+def _dh():
+    import densehead
+    return densehead
+
+
+def _f(*vals):
+    return np.array([float(v) for v in vals])
+
+
+def test_kat_losses(golden):
+    dh = _dh()
+    k = golden("kat")
+    assert_close(float(dh.fcos.focal_loss([0, 1, 0, 1, 1.], [-3, -.5, 0, .5, 3.])), k["focal"], RTOL, what="focal KAT")
+    assert_close(float(dh.fcos.smooth_l1_loss([[0, 1, 2, 3.]], [[.5, 1, 4, 2.2]], mask=1.0)), 2.445, RTOL, what="sl1 KAT")
+    yt = np.zeros((2, 2, 4), np.float32); yt[1, 1] = (1, 2, 1.5, .5)
+    m = np.zeros((2, 2), np.float32); m[1, 1] = 1
+    assert_close(float(dh.fcos.iou_loss(yt, np.ones((2, 2, 4), np.float32), m)), k["iou_loss"], RTOL, what="iou KAT")
+
+
+def test_flat_losses_golden(golden):
+    dh = _dh()
+    z = golden("losses")
+    assert_close(float(dh.fcos.focal_loss(z["flat_y"], z["flat_x"])), z["flat_focal"], RTOL, what="flat focal")
+    assert_close(float(dh.fcos.focal_loss(z["flat_y"], z["flat_x"], alpha=0.4, gamma=1.5)), z["flat_focal_a4g15"], RTOL, what="focal a/g")
+    assert_close(float(dh.fcos.smooth_l1_loss(z["sl1_a"], z["sl1_b"], z["sl1_m"])), z["sl1"], RTOL, what="sl1")
+    assert_close(float(dh.fcos.smooth_l1_loss(z["sl1_a"], z["sl1_b"], z["sl1_m"], delta=2.0)), z["sl1_d2"], RTOL, what="sl1 d2")
+    assert_close(float(dh.fcos.iou_loss(np.abs(z["sl1_a"]), np.abs(z["sl1_b"]), z["sl1_m"])), z["iou_l"], RTOL, what="iou")
+    # scalar mask on a non-multiple-of-4 array (the centerness call pattern, fcos.py:484-486)
+    a = np.linspace(-2, 2, 37, dtype=np.float32); b = np.zeros(37, np.float32)
+    assert_close(float(dh.fcos.smooth_l1_loss(a, b, mask=1.0)), O.smooth_l1_loss(a, b), RTOL, what="sl1 scalar mask")
+
+
+@pytest.mark.parametrize("t", [0, 1, 2])
+def test_fcos_model_loss_golden(golden, t):
+    dh = _dh()
+    z = golden("losses")
+    g, seed = z["fcos%d_g" % t], int(z["fcos%d_seed" % t])
+    pred = synth.fcos_predictions(1, 512, 20, seed)
+    tg, _ = dh.fcos.format_data(g, [512, 512], 20)
+    assert_close(_f(*dh.fcos.model_loss(tg, pred, None)), z["fcos%d_l1" % t], RTOL, what="fcos l1")
+    assert_close(_f(*dh.fcos.model_loss(tg, pred, None, reg_type="iou")), z["fcos%d_iou" % t], RTOL, what="fcos iou")
+    assert float(dh.fcos.model_loss(tg, pred, None, cen_type="focal")[2]) == 0.0   # reference quirk Q27
+    tg, _ = dh.fcos.format_data_center(g, [512, 512], 20)
+    assert_close(_f(*dh.fcos.model_loss_center(tg, pred, cen_type="focal")), z["fcos%d_center_focal" % t], RTOL, what="center focal")
+    assert_close(_f(*dh.fcos.model_loss_center(tg, pred)), z["fcos%d_center_l1" % t], RTOL, what="center l1")
+    tg, _ = dh.fcos.format_data_center_v1(g, [512, 512], 20)
+    assert_close(_f(*dh.fcos.model_loss_center_v1(tg, pred)), z["fcos%d_v1" % t], RTOL, what="v1")
+    # fused: same numbers without materialising targets
+    boxes = np.zeros((1, 20, 5), np.float32); boxes[0, :len(g)] = g
+    for mode, reg, cen, key in (("fcos", "l1", "l1", "fcos%d_l1"), ("fcos", "iou", "l1", "fcos%d_iou"),
+                                ("center", "l1", "focal", "fcos%d_center_focal"), ("center_v1", "l1", "focal", "fcos%d_v1")):
+        pi, tot, cnt = dh.fcos.encode_loss_batch(boxes, [len(g)], [512, 512], 20, [512, 512], pred, mode=mode,
+                                                 reg_type=reg, cen_type=cen)
+        assert_close(tot[:3].cpu().numpy(), z[key % t], RTOL, what="fused " + key % t)
+        assert torch.equal(pi[0], tot)
+
+
+@pytest.mark.parametrize("t", [0, 1])
+def test_retina_loss_golden(golden, t):
+    dh = _dh()
+    z = golden("losses")
+    g, seed = z["retina%d_g" % t], int(z["retina%d_seed" % t])
+    head = dh.retinanet.RetinaNetHead(80)
+    lab, pairs = head.format_data(g, [256, 256])
+    pred = synth.retina_predictions(1, 256, 80, seed)
+    x_pred = [[torch.from_numpy(p[:, a]).cuda() for a in range(9)] for p in pred]   # reference layout [1,Hl,Wl,84]
+    assert_close(_f(*head.loss(x_pred, lab)), z["retina%d_loss" % t], RTOL, what="retina loss")
+    boxes = np.zeros((1, 12, 5), np.float32); boxes[0, :len(g)] = g
+    pi, tot, pr = dh.retinanet.encode_loss_batch(boxes, [len(g)], [256, 256], 80, [256, 256], pred)
+    assert_close(tot[:2].cpu().numpy(), z["retina%d_loss" % t], RTOL, what="retina fused")
+    assert int(pr[0]) == pairs
+
+
+def test_centernet_loss_golden(golden):
+    dh = _dh()
+    z = golden("losses")
+    boxes, nbox, seed = z["cn_boxes"], z["cn_nbox"], int(z["cn_seed"])
+    yp = synth.centernet_s8_predictions(2, 512, 8, 5, 3, seed)
+    yt, _ = dh.centernet.format_data_batch(boxes, nbox, [512, 512], 3, [512, 512], stride=8, mode="s8", box_scales=SCALES)
+    assert_close(_f(*dh.centernet.model_loss_s8(yt, yp)), z["cn_s8_loss"], RTOL, what="s8 loss")
+    pi, tot, st = dh.centernet.encode_loss_batch(boxes, nbox, [512, 512], 3, [512, 512], yp, stride=8, mode="s8", box_scales=SCALES)
+    assert_close(tot[:2].cpu().numpy(), z["cn_s8_loss"], RTOL, what="s8 fused")
+    yp2 = np.ascontiguousarray(yp[:, :, :, 0, :])
+    yt, _ = dh.centernet.format_data_batch(boxes, nbox, [512, 512], 3, [512, 512], stride=8, mode="hourglass")
+    assert_close(_f(*dh.centernet.model_loss_hourglass(yt, yp2)), z["cn_hg_loss"], RTOL, what="hg loss")
+    pi, tot, st = dh.centernet.encode_loss_batch(boxes, nbox, [512, 512], 3, [512, 512], yp2, stride=8, mode="hourglass")
+    assert_close(tot[:2].cpu().numpy(), z["cn_hg_loss"], RTOL, what="hg fused")
+
+
+def test_batched_losses_vs_oracle_and_determinism():
+    """C1-shaped FCOS batch and a RetinaNet batch: per-image sums equal the oracle's, the batch total is
+    the sum of the per-image rows, fused == unfused, and two runs are bit-identical."""
+    dh = _dh()
+    boxes, nbox = synth.config_boxes("fcos_voc", 8, synth.seed_for(5, 70))
+    pred = synth.fcos_predictions(8, 512, 20, 123)
+    tg, _ = dh.fcos.format_data_batch(boxes, nbox, [512, 512], 20, [512, 512])
+    pi, tot = dh.fcos.model_loss_batch(tg, pred)
+    pi2, tot2 = dh.fcos.model_loss_batch(tg, pred)
+    assert torch.equal(pi, pi2) and torch.equal(tot, tot2)
+    fpi, ftot, _ = dh.fcos.encode_loss_batch(boxes, nbox, [512, 512], 20, [512, 512], pred)
+    assert_close(fpi.cpu().numpy(), pi.cpu().numpy(), 2e-6, what="fused vs unfused per image")
+    assert_close(tot.cpu().numpy(), pi.double().sum(0).cpu().numpy(), 1e-6, what="total = sum(per image)")
+    for b in (0, 5):
+        want_t, _ = O.fcos_format_data(boxes[b, :nbox[b]], [512, 512], 20)
+        want = O.fcos_model_loss(want_t, [p[b] for p in pred])
+        assert_close(pi[b, :3].cpu().numpy(), _f(*want), RTOL, what="fcos b%d" % b)
+        npos = sum(int((x[..., 5:].max(-1) >= 1).sum()) for x in want_t)
+        assert int(pi[b, 3]) == npos == int(fpi[b, 3])
+    boxes, nbox = synth.make_boxes(3, 320, 40, 80, 8.0, 250.0, synth.seed_for(5, 71))
+    pred = synth.retina_predictions(3, 320, 80, 321)
+    lab, _ = dh.retinanet.format_data_batch(boxes, nbox, [320, 320], 80, [320, 320])
+    pi, tot = dh.retinanet.loss_batch(lab, pred)
+    fpi, ftot, _ = dh.retinanet.encode_loss_batch(boxes, nbox, [320, 320], 80, [320, 320], pred)
+    assert_close(fpi.cpu().numpy(), pi.cpu().numpy(), 2e-6, what="retina fused vs unfused")
+    want_l, _ = O.retina_format_data(boxes[1, :nbox[1]], [320, 320], 80)
+    want = O.retina_train_loss(want_l, [[p[1, a] for a in range(9)] for p in pred])
+    assert_close(pi[1, :2].cpu().numpy(), _f(*want), RTOL, what="retina b1")
+
+
+def test_loss_linearity_property():
+    """Size-independent property at C5's full batch: loss(batch) rows are independent of batch
+    composition -- any sub-batch reproduces the same per-image rows bit-for-bit."""
+    dh = _dh()
+    boxes, nbox = synth.config_boxes("fcos_voc", 256, synth.seed_for(5, 72))
+    pred = [torch.from_numpy(p).cuda() for p in synth.fcos_predictions(256, 512, 20, 77)]
+    pi, tot, _ = dh.fcos.encode_loss_batch(boxes, nbox, [512, 512], 20, [512, 512], pred)
+    sub = slice(64, 96)
+    spi, _, _ = dh.fcos.encode_loss_batch(boxes[sub], nbox[sub], [512, 512], 20, [512, 512], [p[sub].contiguous() for p in pred])
+    assert torch.equal(spi, pi[sub])
+    assert torch.isfinite(tot).all() and float(tot[3]) == float(pi[:, 3].sum())

@@ -53,3 +53,27 @@ for tb in (8192, 16384, 32768, 49152):
             run("retina B=64 tile=%d ctas=%d" % (tb, cps), lambda: dh.retinanet.format_data_batch(bd, nd, dims, 80, [640, 640], out=outs, num_pairs=pr), sum(o.numel() for o in outs) * 4)
         except Exception as e:
             print("skip", tb, cps, e)
+
+# ---- losses
+dh.set_option(0, 2, 32768); dh.set_option(0, 3, 2)
+B = 64
+boxes, nbox = synth.config_boxes("retina_coco", B, 3)
+bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+dims = torch.tensor([[640., 640.]] * B, device="cuda")
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+pred = [torch.randn((B, 9, h, h, 84), device="cuda", generator=g) - 4.0 for h in (80, 40, 20, 10, 5)]
+nb = sum(p.numel() for p in pred) * 4
+run("retina fused encode+loss B=64", lambda: dh.retinanet.encode_loss_batch(bd, nd, dims, 80, [640, 640], pred), nb)
+lab, _ = dh.retinanet.format_data_batch(bd, nd, dims, 80, [640, 640])
+run("retina unfused loss B=64 (2x bytes)", lambda: dh.retinanet.loss_batch(lab, pred), 2 * nb)
+for tb in (8192, 16384, 32768, 65536):
+    dh.set_option(0, 2, tb)
+    run("retina fused tile=%d" % (tb // 2), lambda: dh.retinanet.encode_loss_batch(bd, nd, dims, 80, [640, 640], pred), nb)
+dh.set_option(0, 2, 32768)
+B = 256
+boxes, nbox = synth.config_boxes("fcos_voc", B, 1)
+bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+dims = torch.tensor([[512., 512.]] * B, device="cuda")
+pred = [torch.randn((B, h, h, 25), device="cuda", generator=g) - 4.0 for h in (64, 32, 16, 8, 4)]
+nb = sum(p.numel() for p in pred) * 4
+run("fcos fused encode+loss B=256", lambda: dh.fcos.encode_loss_batch(bd, nd, dims, 20, [512, 512], pred), nb)
