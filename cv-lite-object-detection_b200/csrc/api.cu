@@ -33,6 +33,25 @@ void* scratch(dh_handle_s* h, size_t bytes) {
     return h->scratch;
 }
 
+constexpr int kSchedRing = 64;
+
+unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st) {
+    if (!h->sched) {
+        cudaError_t e = cudaMalloc(&h->sched, kSchedRing * 32 * sizeof(unsigned int));  // one 128-B line each
+        if (e != cudaSuccess) {
+            set_error(DH_ERR_CUDA, "cudaMalloc for the scheduler counters failed: %s", cudaGetErrorString(e));
+            return nullptr;
+        }
+    }
+    unsigned int* c = h->sched + (h->sched_next++ % kSchedRing) * 32;
+    cudaError_t e = cudaMemsetAsync(c, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) {
+        set_error(DH_ERR_CUDA, "cudaMemsetAsync on a scheduler counter failed: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    return c;
+}
+
 }  // namespace dh
 
 extern "C" {
@@ -55,20 +74,25 @@ int dh_create(dh_handle_t* out, int device) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->use_tma_store = 1;
-    h->tile_bytes = 32768;
-    h->ctas_per_sm = 2;
+    h->tile_bytes = 49152;
+    h->ctas_per_sm = 4;
     h->launches = 0;
     h->scratch = nullptr;
     h->scratch_bytes = 0;
+    h->phase_cycles = nullptr;
+    h->sched = nullptr;
+    h->sched_next = 0;
     *out = h;
     return DH_OK;
 }
 
 int dh_destroy(dh_handle_t h) {
     if (!h) return DH_OK;
-    if (h->scratch) {
+    {
         dh::DeviceGuard g(h->device);
-        cudaFree(h->scratch);
+        if (h->scratch) cudaFree(h->scratch);
+        if (h->sched) cudaFree(h->sched);
+        if (h->phase_cycles) cudaFree(h->phase_cycles);
     }
     delete h;
     return DH_OK;
@@ -88,11 +112,31 @@ int dh_set_option(dh_handle_t h, int option, int value) {
             DH_CHECK_ARG(value >= 1 && value <= 8, "DH_OPT_CTAS_PER_SM must be in [1, 8]");
             h->ctas_per_sm = value;
             return DH_OK;
+        case DH_OPT_PHASE_TIMING: {
+            dh::DeviceGuard g(h->device);
+            if (value && !h->phase_cycles) {
+                DH_CUDA(cudaMalloc(&h->phase_cycles, 8 * sizeof(long long)));
+            }
+            if (h->phase_cycles) DH_CUDA(cudaMemset(h->phase_cycles, 0, 8 * sizeof(long long)));
+            if (!value && h->phase_cycles) {
+                cudaFree(h->phase_cycles);
+                h->phase_cycles = nullptr;
+            }
+            return DH_OK;
+        }
         default:
             return dh::set_error(DH_ERR_BAD_ARG, "dh_set_option: unknown option %d", option);
     }
 }
 
 long long dh_launch_count(dh_handle_t h) { return h ? h->launches : 0; }
+
+int dh_read_phase_timing(dh_handle_t h, long long* out8) {
+    DH_CHECK_ARG(h && out8, "dh_read_phase_timing: NULL argument");
+    DH_CHECK_ARG(h->phase_cycles, "dh_read_phase_timing: DH_OPT_PHASE_TIMING is off");
+    dh::DeviceGuard g(h->device);
+    DH_CUDA(cudaMemcpy(out8, h->phase_cycles, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return DH_OK;
+}
 
 }  // extern "C"

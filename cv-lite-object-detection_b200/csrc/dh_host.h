@@ -16,6 +16,9 @@ struct dh_handle_s {
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
     size_t scratch_bytes;
+    long long* phase_cycles;  // DH_OPT_PHASE_TIMING: device [8] counters (profiling aid)
+    unsigned int* sched;      // ring of tile-scheduler counters (one per launch in flight)
+    int sched_next;
 };
 
 namespace dh {
@@ -23,6 +26,8 @@ namespace dh {
 int set_error(int code, const char* fmt, ...);
 // Ensure the handle's scratch holds at least `bytes`; returns device pointer or null (error set).
 void* scratch(dh_handle_s* h, size_t bytes);
+// A zeroed (stream-ordered) device counter for one kernel's dynamic tile scheduler; null on error.
+unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st);
 
 #define DH_CHECK_ARG(cond, ...)                                      \
     do {                                                             \

@@ -6,6 +6,8 @@ namespace dh {
 // Fill tile_begin / n_tiles / fast divisors for tt.maps[0..n_maps) and pick rows_per_tile so that one
 // tile is about `tile_bytes`.  Returns the shared-memory bytes one stage buffer needs.
 int finish_table(TileTable& tt, int ch, int batch, int tile_bytes);
+// Tile size for a problem: `max_tile_bytes` for large outputs, smaller when the output would not fill the SMs.
+int auto_tile_bytes(const TileTable& tt, int ch, int batch, int max_tile_bytes, int sm_count);
 
 // Validate the detector configuration and fill the policy parameters + map geometry.  `out_*` are the
 // target tensors (encode), `pred_*` the prediction tensors (fused loss); either may be null.

@@ -42,6 +42,7 @@ struct LossArgs {
     const int* nbox;
     const float* img_dim;
     int max_boxes;
+    int box_cap;  // shared-memory capacity in boxes (fused): max_boxes rounded up to 32
     int tile_buf_bytes;
     float* partials;  // [batch * tiles_per_image, 4]
     const float* mask_maps[DH_MAX_MAPS];
@@ -51,15 +52,15 @@ struct LossSmemLayout {
     int pred_off, tgt_off, rowpos_off, rec_off, raw_off, cand_off, misc_off, args_off, total;
 };
 template <class P, bool kFused>
-__host__ __device__ inline LossSmemLayout loss_smem_layout(int tile_buf_bytes, int rows_per_tile) {
+__host__ __device__ inline LossSmemLayout loss_smem_layout(int tile_buf_bytes, int rows_per_tile, int box_cap) {
     LossSmemLayout l;
     l.pred_off = 0;
     l.tgt_off = 2 * tile_buf_bytes;
     l.rowpos_off = l.tgt_off + (kFused ? 1 : 2) * tile_buf_bytes;
     l.rec_off = l.rowpos_off + ((rows_per_tile * 4 + 127) & ~127);
-    l.raw_off = l.rec_off + (kFused ? ((static_cast<int>(sizeof(typename P::Rec)) * DH_MAX_BOXES + 127) & ~127) : 0);
-    l.cand_off = l.raw_off + (kFused ? DH_MAX_BOXES * 5 * 4 : 0);
-    l.misc_off = l.cand_off + (kFused ? DH_MAX_BOXES * 2 : 0);
+    l.raw_off = l.rec_off + (kFused ? ((static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127) : 0);
+    l.cand_off = l.raw_off + (kFused ? ((box_cap * 20 + 127) & ~127) : 0);
+    l.misc_off = l.cand_off + (kFused ? ((box_cap * 2 + 127) & ~127) : 0);
     l.args_off = l.misc_off + 256;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
     return l;
@@ -118,7 +119,7 @@ __device__ __forceinline__ uint32_t bulk_body(const float* g, int nfl, int& head
 template <class P, bool kFused>
 __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant__ LossArgs<P> ga) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const LossSmemLayout lay = loss_smem_layout<P, kFused>(ga.tile_buf_bytes, ga.tt.rows_per_tile);
+    const LossSmemLayout lay = loss_smem_layout<P, kFused>(ga.tile_buf_bytes, ga.tt.rows_per_tile, ga.box_cap);
     const LossArgs<P>& a = *reinterpret_cast<const LossArgs<P>*>(smem + lay.args_off);  // see encode_kernel
     copy_args_to_smem(ga, reinterpret_cast<LossArgs<P>*>(smem + lay.args_off));
     int* rowpos = reinterpret_cast<int*>(smem + lay.rowpos_off);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
         if constexpr (kFused) {
             if (ti.b != cur_img) {
                 __syncthreads();
-                n_boxes = stage_boxes(a.boxes, a.nbox, ti.b, a.max_boxes, raw, boxbar, box_parity);
+                n_boxes = stage_boxes(a.boxes, a.nbox, ti.b, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
                 const float hi = a.img_dim[2 * ti.b], wi = a.img_dim[2 * ti.b + 1];
                 if (tid < n_boxes) P::make_record(a.pp, raw + 5 * tid, hi, wi, tid, recs[tid]);
                 __syncthreads();

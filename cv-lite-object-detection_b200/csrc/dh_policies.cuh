@@ -61,6 +61,7 @@ struct FcosPolicy {
         int flags;  // bit0 live_y, bit1 live_x, bit2 valid
     };
     static constexpr int kRegCh = 5;  // t, b, l, r, centerness
+    static constexpr bool kScatter = false;
 
     __device__ static void make_record(const Params& p, const float* g, float hi, float wi, int k, Rec& r) {
         const float gh = fmul(g[2], hi), gw = fmul(g[3], wi);  // fcos.py:152-153
@@ -216,6 +217,7 @@ struct RetinaPolicy {
         int cls;
     };
     static constexpr int kRegCh = 4;
+    static constexpr bool kScatter = false;
 
     __device__ static void make_record(const Params& p, const float* g, float hi, float wi, int k, Rec& r) {
         r.gy = fmul(g[0], hi), r.gx = fmul(g[1], wi), r.gh = fmul(g[2], hi), r.gw = fmul(g[3], wi);  // :274-278
@@ -232,18 +234,24 @@ struct RetinaPolicy {
         if ((threadIdx.x & 31) == 0 && s) atomicAdd(p.num_pairs + ti.b, s);
     }
 
+    // Necessary conditions for IoU > thr (thr > 0), used as cheap rejects before any division:
+    //   IoU <= min(area)/max(area),  IoU <= overlap_y / max(ah, gh),  IoU <= overlap_x / max(aw, gw)
+    // (inter <= oy * min(aw, gw) and union >= max(ah, gh) * min(aw, gw)).  0.999 covers float rounding.
     __device__ static bool tile_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        if (p.thr < 0.f) return true;
         const float ah = p.anchor_h[ti.level][ti.anchor], aw = p.anchor_w[ti.level][ti.anchor];
-        if (p.thr > 0.f) {  // IoU <= min(area)/max(area): conservative reject (slack covers rounding)
-            const float aa = ah * aw;
-            if (fminf(aa, r.area) < 0.999f * p.thr * fmaxf(aa, r.area)) return false;
-        } else if (p.thr < 0.f) {
-            return true;
-        }
         const float s = static_cast<float>(p.stride[ti.level]);
         const float i0 = static_cast<float>(fdiv_u32(ti.r0, md.div_width));
         const float i1 = static_cast<float>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
-        return r.hi_y > i0 * s - 0.5f * ah - 1.0f && r.lo_y < i1 * s + 0.5f * ah + 1.0f;
+        float need = 0.f;
+        if (p.thr > 0.f) {
+            const float aa = ah * aw;
+            if (fminf(aa, r.area) < 0.999f * p.thr * fmaxf(aa, r.area)) return false;
+            if (fminf(aw, r.gw) < 0.999f * p.thr * fmaxf(aw, r.gw)) return false;
+            need = 0.999f * p.thr * fmaxf(ah, r.gh);
+        }
+        // some anchor row i in [i0, i1] must overlap the GT by more than `need` in y
+        return i1 * s + 0.5f * ah > r.lo_y + need - 0.01f && i0 * s - 0.5f * ah < r.hi_y - need + 0.01f;
     }
 
     // returns the number of (gt, anchor) pairs above the threshold at this row (:302-317)
@@ -257,12 +265,14 @@ struct RetinaPolicy {
         const float hh = fdiv(ah, 2.0f), hw = fdiv(aw, 2.0f);
         const float alo_y = fsub(ay, hh), ahi_y = fadd(ay, hh), alo_x = fsub(ax, hw), ahi_x = fadd(ax, hw);
         const float a_area = fmul(ah, aw);
+        const float pre = 0.999f * p.thr;
         int best = -1, pairs = 0;
         for (int q = 0; q < ncand; ++q) {  // candidates are in ascending GT order
             const int k = cand[q];
             const Rec& r = recs[k];
             const float dy = fmaxf(0.f, fsub(fminf(r.hi_y, ahi_y), fmaxf(r.lo_y, alo_y)));  // utils.py:66-72
             const float dx = fmaxf(0.f, fsub(fminf(r.hi_x, ahi_x), fmaxf(r.lo_x, alo_x)));
+            if (p.thr > 0.f && (dy < pre * fmaxf(ah, r.gh) || dx < pre * fmaxf(aw, r.gw))) continue;  // see tile_hit
             const float inter = fmul(dy, dx);
             if (!(inter > 0.f) && !(p.thr < 0.f)) continue;  // IoU == 0 cannot exceed thr >= 0
             const float uni = fmaxf(fsub(fadd(r.area, a_area), inter), 1e-8f);  // utils.py:77-80
@@ -307,6 +317,8 @@ struct CenterNetPolicy {
         int flags;  // bit0 live_y, bit1 live_x, bit2 valid
     };
     static constexpr int kRegChOnehot = 4;
+    static constexpr bool kScatter = true;  // centre-cell modes: one thread per box writes its single row
+    __device__ static bool use_scatter(const Params& p) { return p.mode != CN_POWER_FALLOFF; }
 
     __device__ static int reg_ch(const Params& p) { return p.mode == CN_POWER_FALLOFF ? 5 : 4; }
 
@@ -394,6 +406,27 @@ struct CenterNetPolicy {
         const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
         const int i1 = static_cast<int>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
         return r.ry1 > i0 && r.ry0 <= i1;
+    }
+
+    // Scatter emission for the centre-cell modes: thread q owns candidate q, whose target is a single
+    // row.  Class bits are idempotent stores; the regression values are written only by the box no
+    // other candidate of the same row paints after (pairwise check instead of atomics).
+    __device__ static void emit_tile(const Params& p, const TileInfo& ti, const MapDesc& md, float* tile, int ch,
+                                     const Rec* recs, const unsigned short* cand, int ncand, unsigned short* dirty_rows) {
+        for (int q = threadIdx.x; q < ncand; q += blockDim.x) {
+            const int k = cand[q];
+            const Rec& r = recs[k];
+            const int local = r.row - ti.r0;
+            float* dst = tile + local * ch;
+            dst[4 + r.cls] = 1.0f;
+            bool wins = true;
+            for (int q2 = 0; q2 < ncand; ++q2) {
+                const int k2 = cand[q2];
+                if (k2 != k && recs[k2].row == r.row && paints_later(recs[k2].area, k2, r.area, k)) wins = false;
+            }
+            if (wins) dst[0] = r.r0, dst[1] = r.r1, dst[2] = r.r2, dst[3] = r.r3;
+            dirty_rows[q] = static_cast<unsigned short>(local);
+        }
     }
 
     __device__ static double inv_pow8(double d) {  // 1/(d^8): tf_centernet.py:6-19 with spread forced to 8 (:207)

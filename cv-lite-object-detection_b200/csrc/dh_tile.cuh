@@ -91,15 +91,15 @@ __device__ __forceinline__ void copy_args_to_smem(const T& src, T* dst) {
 // bulk copy when the source is 16-byte aligned and sized, otherwise cooperative loads.
 // Must be called by all threads of the CTA; ends with a __syncthreads().
 __device__ __forceinline__ int stage_boxes(const float* __restrict__ boxes, const int* __restrict__ nbox, int b,
-                                           int max_boxes, float* raw /*[DH_MAX_BOXES*5]*/, uint64_t* bar,
+                                           int max_boxes, int box_cap, float* raw /*[box_cap*5]*/, uint64_t* bar,
                                            uint32_t& bar_parity) {
     const float* src = boxes + static_cast<long long>(b) * max_boxes * 5;
     int n = nbox ? nbox[b] : max_boxes;
-    n = max(0, min(n, min(max_boxes, DH_MAX_BOXES)));
+    n = max(0, min(n, min(max_boxes, box_cap)));
     const uint32_t bytes = static_cast<uint32_t>(n) * 20u;
     const uint32_t bytes16 = (bytes + 15u) & ~15u;
     const bool tma_ok = n > 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0 &&
-                        bytes16 <= static_cast<uint32_t>(min(max_boxes, DH_MAX_BOXES)) * 20u;
+                        bytes16 <= static_cast<uint32_t>(min(max_boxes, box_cap)) * 20u;
     if (tma_ok) {
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, bytes16);

@@ -7,6 +7,18 @@
 
 namespace dh {
 
+int auto_tile_bytes(const TileTable& tt, int ch, int batch, int max_tile_bytes, int sm_count) {
+    // big tiles amortise the per-tile bookkeeping (6.3 TB/s at 48 KB vs 3.5 TB/s at 16 KB on B200), but a small
+    // problem still has to spread over all SMs: aim at >= 4 tiles per SM, never below 8 KB
+    long long bytes = 0;
+    for (int m = 0; m < tt.n_maps; ++m) bytes += static_cast<long long>(tt.maps[m].rows) * ch * 4;
+    bytes *= batch;
+    long long t = bytes / (static_cast<long long>(sm_count) * 4);
+    if (t > max_tile_bytes) t = max_tile_bytes;
+    if (t < 8192) t = 8192;
+    return static_cast<int>(t) & ~1023;
+}
+
 int finish_table(TileTable& tt, int ch, int batch, int tile_bytes) {
     int rpt = (tile_bytes / (ch * 4)) & ~3;
     if (rpt < 4) rpt = 4;
@@ -31,7 +43,8 @@ template <class P>
 static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, const char* who) {
     const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
     if (total == 0) return DH_OK;
-    const EncodeSmemLayout lay = encode_smem_layout<P>(a.tile_buf_bytes);
+    a.box_cap = ((a.max_boxes > 0 ? a.max_boxes : 1) + 31) & ~31;
+    const EncodeSmemLayout lay = encode_smem_layout<P>(a.tile_buf_bytes, a.box_cap);
     if (lay.total > 227 * 1024)
         return set_error(DH_ERR_CAPACITY, "%s: tile of %d bytes needs %d bytes of shared memory", who, a.tile_buf_bytes,
                          lay.total);
@@ -40,9 +53,35 @@ static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, cons
         DH_CUDA(cudaFuncSetAttribute(encode_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    long long grid = static_cast<long long>(h->sm_count) * h->ctas_per_sm;
+    int per_sm = (227 * 1024) / (lay.total + 1024);  // 1 KB per-CTA reservation
+    if (per_sm > h->ctas_per_sm) per_sm = h->ctas_per_sm;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = static_cast<long long>(h->sm_count) * per_sm;
     if (grid > total) grid = total;
+    // image-aligned chunks for the dynamic scheduler: aim at >= ~8 chunks per CTA, 8..64 tiles each
+    {
+        const int tpi = a.tt.tiles_per_image;
+        long long want = total / (grid * 8);
+        want = want < 8 ? 8 : (want > 64 ? 64 : want);
+        if (tpi <= want) {
+            a.chunks_per_image = 1;
+            a.images_per_chunk = static_cast<int>(want / tpi);
+            if (a.images_per_chunk < 1) a.images_per_chunk = 1;
+            a.chunk_tiles = a.images_per_chunk * tpi;
+            a.n_chunks = (a.tt.batch + a.images_per_chunk - 1) / a.images_per_chunk;
+        } else {
+            const int n_sub = static_cast<int>((tpi + want - 1) / want);
+            a.chunk_tiles = (tpi + n_sub - 1) / n_sub;
+            a.chunks_per_image = (tpi + a.chunk_tiles - 1) / a.chunk_tiles;
+            a.images_per_chunk = 1;
+            a.n_chunks = static_cast<long long>(a.tt.batch) * a.chunks_per_image;
+        }
+        if (grid > a.n_chunks) grid = a.n_chunks;
+    }
+    a.sched = next_sched_counter(h, st);
+    if (!a.sched) return DH_ERR_CUDA;
     a.use_tma_store = h->use_tma_store;
+    a.phase_cycles = h->phase_cycles;
     encode_kernel<P><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -170,7 +209,7 @@ int dh_fcos_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, const
     int rc = fill_fcos(a.pp, a.tt, pad_h, pad_w, n_levels, strides, b_dim, num_classes, mode, out_levels, nullptr,
                        num_targets, "dh_fcos_encode");
     if (rc) return rc;
-    a.tile_buf_bytes = finish_table(a.tt, num_classes + 5, batch, h->tile_bytes);
+    a.tile_buf_bytes = finish_table(a.tt, num_classes + 5, batch, auto_tile_bytes(a.tt, num_classes + 5, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     return launch_encode<FcosPolicy>(h, a, static_cast<cudaStream_t>(stream), "dh_fcos_encode");
 }
@@ -189,7 +228,7 @@ int dh_retina_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, con
     int rc = fill_retina(a.pp, a.tt, pad_h, pad_w, n_levels, strides, n_anchors, anchor_hw, iou_thresh, num_classes,
                          out_levels, nullptr, num_pairs, "dh_retina_encode");
     if (rc) return rc;
-    a.tile_buf_bytes = finish_table(a.tt, num_classes + 4, batch, h->tile_bytes);
+    a.tile_buf_bytes = finish_table(a.tt, num_classes + 4, batch, auto_tile_bytes(a.tt, num_classes + 4, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (num_pairs && batch > 0) DH_CUDA(cudaMemsetAsync(num_pairs, 0, sizeof(int32_t) * batch, st));
     return launch_encode<RetinaPolicy>(h, a, st, "dh_retina_encode");
@@ -209,7 +248,7 @@ int dh_centernet_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, 
                             status, "dh_centernet_encode");
     if (rc) return rc;
     const int ch = num_classes + (mode == DH_CENTERNET_POWER_FALLOFF ? 5 : 4);
-    a.tile_buf_bytes = finish_table(a.tt, ch, batch, h->tile_bytes);
+    a.tile_buf_bytes = finish_table(a.tt, ch, batch, auto_tile_bytes(a.tt, ch, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
     return launch_encode<CenterNetPolicy>(h, a, st, "dh_centernet_encode");

@@ -27,7 +27,8 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
     if (!sc) return DH_ERR_CUDA;
     a.partials = reinterpret_cast<float*>(sc);
     float* per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
-    const LossSmemLayout lay = loss_smem_layout<P, kFused>(a.tile_buf_bytes, a.tt.rows_per_tile);
+    a.box_cap = ((a.max_boxes > 0 ? a.max_boxes : 1) + 31) & ~31;
+    const LossSmemLayout lay = loss_smem_layout<P, kFused>(a.tile_buf_bytes, a.tt.rows_per_tile, a.box_cap);
     if (lay.total > 227 * 1024)
         return set_error(DH_ERR_CAPACITY, "%s: needs %d bytes of shared memory", who, lay.total);
     static bool attr_done = false;

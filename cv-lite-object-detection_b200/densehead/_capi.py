@@ -50,6 +50,7 @@ def lib():
         L.dh_set_option.argtypes = [c_vp, ctypes.c_int, ctypes.c_int]
         L.dh_launch_count.argtypes = [c_vp]
         L.dh_launch_count.restype = ctypes.c_longlong
+        L.dh_read_phase_timing.argtypes = [c_vp, ctypes.POINTER(ctypes.c_longlong)]
         I, F, P = ctypes.c_int, ctypes.c_float, c_vp
         L.dh_fcos_encode.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, c_fp, I, I, ctypes.POINTER(c_vp), P, P]
         L.dh_retina_encode.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, I, c_fp, F, I, ctypes.POINTER(c_vp), P, P]
@@ -97,6 +98,12 @@ def set_option(device_index, option, value):
 
 def launch_count(device_index=0):
     return int(lib().dh_launch_count(handle(device_index)))
+
+
+def phase_timing(device_index=0):
+    out = (ctypes.c_longlong * 8)()
+    check(lib().dh_read_phase_timing(handle(device_index), out), "dh_read_phase_timing")
+    return list(out)
 
 
 def int_array(values):

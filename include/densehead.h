@@ -46,9 +46,13 @@ int dh_create(dh_handle_t* out, int device);
 int dh_destroy(dh_handle_t h);
 /* Options: see DH_OPT_*.  Returns DH_ERR_BAD_ARG for an unknown option. */
 #define DH_OPT_TMA_STORE 1   /* 1 (default): tiles leave shared memory as TMA bulk stores; 0: st.global.v4 */
-#define DH_OPT_TILE_BYTES 2  /* shared-memory tile size in bytes (default 32768) */
-#define DH_OPT_CTAS_PER_SM 3 /* persistent CTAs per SM (default 2) */
+#define DH_OPT_TILE_BYTES 2  /* upper bound on the shared-memory tile size in bytes (default 49152; small problems use smaller tiles) */
+#define DH_OPT_CTAS_PER_SM 3 /* upper bound on persistent CTAs per SM (default 4; shared memory may allow fewer) */
+#define DH_OPT_PHASE_TIMING 4 /* profiling aid: 1 = CTA 0 of each encode kernel accumulates per-phase clock64 totals; (re)sets them */
 int dh_set_option(dh_handle_t h, int option, int value);
+/* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in
+ * {stage GT + records, candidates + buffer recycle, emit rows, hand-off to TMA, drain}, out8[5] = tiles. */
+int dh_read_phase_timing(dh_handle_t h, long long* out8 /*[host] [8]*/);
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 long long dh_launch_count(dh_handle_t h);
 

@@ -91,7 +91,7 @@ def test_fcos_per_image_dims_and_options():
         dh.set_option(0, 3, 1)
         outs4, _ = dh.fcos.format_data_batch(boxes, nbox, dims, 7, [384, 384])
     finally:
-        dh.set_option(0, 1, 1), dh.set_option(0, 2, 32768), dh.set_option(0, 3, 2)
+        dh.set_option(0, 1, 1), dh.set_option(0, 2, 49152), dh.set_option(0, 3, 4)
     for a, b2, c, d in zip(ref, outs2, outs3, outs4):
         assert torch.equal(a, b2) and torch.equal(a, c) and torch.equal(a, d)
 

@@ -46,8 +46,8 @@ for tma in (1, 0):
             src = torch.empty_like(big)
             run("copy same bytes (r+w)", lambda: big.copy_(src), big.numel() * 8)
 dh.set_option(0, 1, 1)
-for tb in (8192, 16384, 32768, 49152):
-    for cps in (1, 2, 3, 4):
+for tb in (16384, 24576, 28672, 32768, 40960, 49152):
+    for cps in (2, 3, 4):
         dh.set_option(0, 2, tb); dh.set_option(0, 3, cps)
         try:
             run("retina B=64 tile=%d ctas=%d" % (tb, cps), lambda: dh.retinanet.format_data_batch(bd, nd, dims, 80, [640, 640], out=outs, num_pairs=pr), sum(o.numel() for o in outs) * 4)
@@ -55,7 +55,7 @@ for tb in (8192, 16384, 32768, 49152):
             print("skip", tb, cps, e)
 
 # ---- losses
-dh.set_option(0, 2, 32768); dh.set_option(0, 3, 2)
+dh.set_option(0, 2, 28672); dh.set_option(0, 3, 4)
 B = 64
 boxes, nbox = synth.config_boxes("retina_coco", B, 3)
 bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
@@ -69,7 +69,7 @@ run("retina unfused loss B=64 (2x bytes)", lambda: dh.retinanet.loss_batch(lab, 
 for tb in (8192, 16384, 32768, 65536):
     dh.set_option(0, 2, tb)
     run("retina fused tile=%d" % (tb // 2), lambda: dh.retinanet.encode_loss_batch(bd, nd, dims, 80, [640, 640], pred), nb)
-dh.set_option(0, 2, 32768)
+dh.set_option(0, 2, 28672)
 B = 256
 boxes, nbox = synth.config_boxes("fcos_voc", B, 1)
 bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
