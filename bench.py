@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- the dense-head hot path on B200: images/s and % of the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[4], "full dense-head target+loss step"): RetinaNet COCO-shaped
+batches -- 640x640, 5 levels x 9 anchors, 80 classes, <= 100 GT boxes per image, 256 images per GPU.
+One step = anchor matching + box encoding + focal / smooth-L1 loss for every image of the batch
+(fused: targets are produced in shared memory and consumed there), followed at N > 1 by one NCCL
+all-reduce of the 4 loss scalars.  Images are sharded across ranks; per-GPU work is fixed, so scaling
+is "weak" and `value` counts the images all ranks processed.
+
+  value   images/s with boxes and predictions already resident in HBM (CUDA-event timed graph replays).
+  e2e     images/s through the public Python API (`densehead.retinanet.encode_loss_batch`) with HOST
+          inputs: every step copies the GT boxes AND the head predictions from pinned host memory and
+          reads the loss scalars back.  (`e2e_resident_pred` keeps the predictions on the device, which
+          is where the backbone leaves them in the reference's own training loop.)
+  roofline  fused encode+loss kernel: algorithmic bytes = one read of the predictions (+ boxes), over the
+          kernel's CUDA-event time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  extra   per-config numbers (C1 FCOS encode, C2 CenterNet encode, C3 RetinaNet encode, unfused loss).
+  cpu_baseline  the oracle port (NumPy restatement of the reference) on one host core, bounded sample.
+
+`--impl reference` times the reference algorithm's CPU port on all host cores (the reference is pure
+Python/NumPy and cannot travel to the GPU box) and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "cv-lite-object-detection_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+SIDE, CLASSES, NMAX, ANCHORS = 640, 80, 100, 9
+STRIDES = (8, 16, 32, 64, 128)
+LEVELS = [SIDE // s for s in STRIDES]
+PER_GPU_BATCH = 256
+ROWS_PER_IMAGE = sum(ANCHORS * h * h for h in LEVELS)            # 76 725 anchors
+PRED_BYTES_PER_IMAGE = ROWS_PER_IMAGE * (CLASSES + 4) * 4        # 25 779 600 B
+WORKLOAD = ("c5: full dense-head target+loss step, RetinaNet COCO-shaped (640x640, 9 anchors x 5 levels, 80 classes, "
+            "<=100 boxes/img), %d images per GPU" % PER_GPU_BATCH)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the per-config extra measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _worker_init(seed):
+    from oracle import dense_head_ref as O
+    from oracle import synth
+    _W["O"] = O
+    _W["pred"] = [[p[0, a] for a in range(ANCHORS)] for p in synth.retina_predictions(1, SIDE, CLASSES, seed)]
+    _W["boxes"], _W["nbox"] = synth.config_boxes("retina_coco", 64, seed)
+
+
+def _worker_step(i):
+    O = _W["O"]
+    b = i % len(_W["nbox"])
+    labels, _ = O.retina_format_data(_W["boxes"][b, :_W["nbox"][b]], [SIDE, SIDE], CLASSES)
+    cls, reg = O.retina_train_loss(labels, _W["pred"])
+    return float(cls), float(reg)
+
+
+def cpu_port_single_core(n_images=6):
+    """One core, bounded sample: encode + loss of `n_images` images with the oracle port."""
+    _worker_init(12345)
+    _worker_step(0)  # warm-up (imports, allocator)
+    t0 = time.perf_counter()
+    for i in range(n_images):
+        _worker_step(i)
+    dt = time.perf_counter() - t0
+    return {"value": n_images / dt, "unit": "images/s", "cores": 1, "kind": "port",
+            "sample": "%d images of the bench workload (oracle retina_format_data + retina_train_loss, %.1f s)" % (n_images, dt)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm's CPU port on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = max(1, min(os.cpu_count() or 1, 64))
+    per_step = workers  # one image per worker per step: a bounded sample of the 256-image batch
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers, initializer=_worker_init, initargs=(777,)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_worker_step, range(per_step))
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_worker_step, range(k * per_step, (k + 1) * per_step))
+        dt = time.perf_counter() - t0
+    ips = args.steps * per_step / dt
+    sample = "%d images per step (1 per worker) of the 256-image batch" % per_step
+    line = {"impl": "reference", "metric": "dense-head target+loss images/sec", "value": ips, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": workers, "kind": "port", "sample": sample,
+                             "note": "NumPy restatement of the reference (oracle/dense_head_ref.py); the reference itself is "
+                                     "Python+TF and /root/reference does not exist on the GPU box"},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import densehead as dh
+    from densehead import _capi, retinanet, fcos, centernet
+    from oracle import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    boxes_h, nbox_h = synth.config_boxes("retina_coco", B, synth.seed_for(5, 100 + rank))
+    dims_h = np.tile(np.array([[SIDE, SIDE]], dtype=np.float32), (B, 1))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    pred = []
+    for h in LEVELS:  # random-init head outputs: regs ~ U(-1,2), class logits ~ N(-4.595, 1) (focal prior)
+        p = torch.empty((B, ANCHORS, h, h, CLASSES + 4), device=dev)
+        p[..., :4].uniform_(-1, 2, generator=gen)
+        p[..., 4:].normal_(-4.595, 1.0, generator=gen)
+        pred.append(p)
+    boxes_d = torch.from_numpy(boxes_h).to(dev)
+    nbox_d = torch.from_numpy(nbox_h).to(dev)
+    dims_d = torch.from_numpy(dims_h).to(dev)
+    pred_bytes = sum(p.numel() for p in pred) * 4
+    box_bytes = boxes_h.nbytes + nbox_h.nbytes + dims_h.nbytes
+    assert pred_bytes == B * PRED_BYTES_PER_IMAGE
+
+    def step_device():
+        return retinanet.encode_loss_batch(boxes_d, nbox_d, dims_d, CLASSES, [SIDE, SIDE], pred)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also grows the library's scratch so nothing allocates inside the graph) ------------
+    for _ in range(max(args.warmup, 3)):
+        per_image, total, pairs = step_device()
+        if dist is not None:
+            dist.all_reduce(total)
+    torch.cuda.synchronize()
+
+    # ---- capture one step's kernels in a CUDA graph: the device-resident measurement must not time the
+    #      Python/ctypes launch path (that is what `e2e` is for)
+    l0 = dh.launch_count(local_rank)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        per_image, total, pairs = step_device()
+    launches_per_step = dh.launch_count(local_rank) - l0
+    graph.replay()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        graph.replay()
+        if dist is not None:
+            dist.all_reduce(total)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused encode+loss), timed alone on this rank ---------------
+    peak, peak_src = measured_peak()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(5, min(args.steps, 20))
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(reps):
+        graph.replay()
+    k1.record()
+    torch.cuda.synchronize()
+    kern_s = k0.elapsed_time(k1) / reps * 1e-3
+    alg_bytes = pred_bytes + box_bytes
+    achieved = alg_bytes / kern_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "loss_kernel<RetinaPolicy, fused> (+2 finalize kernels, <1% of the time)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_s * 1e3, "peak_source": peak_src}
+    ncu = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(ncu):
+        try:
+            with open(ncu) as f:
+                roofline["traffic"] = json.load(f).get("fused_loss_bytes_per_image", 0) * B or None
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through the public API ------------------------------------------------------
+    e2e = e2e_res = None
+    try:
+        pin_boxes = torch.from_numpy(boxes_h).pin_memory()
+        pin_nbox = torch.from_numpy(nbox_h).pin_memory()
+        pin_dims = torch.from_numpy(dims_h).pin_memory()
+        pin_pred = [torch.empty(p.shape, dtype=torch.float32, pin_memory=True).copy_(p) for p in pred]
+        stage = [torch.empty_like(p) for p in pred]  # device landing buffers for the per-step prediction copy
+        out_host = torch.empty(4, dtype=torch.float32, pin_memory=True)
+
+        def step_e2e(copy_pred):
+            b = pin_boxes.to(dev, non_blocking=True)
+            n = pin_nbox.to(dev, non_blocking=True)
+            d = pin_dims.to(dev, non_blocking=True)
+            if copy_pred:
+                for s_, p_ in zip(stage, pin_pred):
+                    s_.copy_(p_, non_blocking=True)
+                x = stage
+            else:
+                x = pred
+            _, tot, _ = retinanet.encode_loss_batch(b, n, d, CLASSES, [SIDE, SIDE], x)
+            if dist is not None:
+                dist.all_reduce(tot)
+            out_host.copy_(tot, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the loss
+            return out_host
+
+        def time_e2e(copy_pred, steps):
+            for _ in range(2):
+                step_e2e(copy_pred)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step_e2e(copy_pred)
+            barrier()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t[0])
+            return world * B * steps / dt
+
+        e2e_steps = max(3, min(args.steps, 10))
+        v = time_e2e(True, e2e_steps)
+        e2e = {"value": v, "unit": "images/s", "h2d_bytes_per_step": int(pred_bytes + box_bytes), "d2h_bytes_per_step": 16,
+               "steps": e2e_steps, "api": "densehead.retinanet.encode_loss_batch (ctypes -> dh_retina_encode_loss)",
+               "note": "GT boxes and head predictions copied from pinned host memory every step; PCIe-bound"}
+        v2 = time_e2e(False, max(args.steps, 10))
+        e2e_res = {"value": v2, "unit": "images/s", "h2d_bytes_per_step": int(box_bytes), "d2h_bytes_per_step": 16,
+                   "note": "predictions stay on the device (where the backbone writes them); boxes from pinned host memory"}
+        del pin_pred, stage
+    except Exception as exc:  # e.g. not enough pinned host memory
+        e2e = {"value": None, "unit": "images/s", "error": repr(exc)}
+
+    # ---- extra: the other BASELINE configs, device-resident, graph-timed ------------------------------
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        del pred
+        torch.cuda.empty_cache()
+        extra = extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_port_single_core()
+
+    if rank == 0:
+        line = {"metric": "dense-head target+loss images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "images sharded, dp%d" % world,
+                           "l2": "inputs (%.1f GB of predictions per GPU) are far larger than the 126 MB L2" % (pred_bytes / 1e9),
+                           "collective": "NCCL all-reduce of 4 float32 loss scalars per step" if world > 1 else "none"},
+                "clocks": clocks, "e2e": e2e, "e2e_resident_pred": e2e_res, "gpu_launches": int(launches_per_step * args.steps),
+                "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
+    """Device-resident, CUDA-graph-timed numbers for the other BASELINE configs (one launch each)."""
+    out = {}
+
+    def graph_time(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+
+    def entry(name, batch, nbytes, secs, note=""):
+        out[name] = {"images_per_s": batch / secs, "us": secs * 1e6, "GBps": nbytes / secs / 1e9,
+                     "frac_of_hbm_peak": nbytes / secs / 1e9 / peak, "algorithmic_bytes": int(nbytes), "note": note}
+
+    def dev_boxes(cfg, batch, seed, side):
+        b, n = synth.config_boxes(cfg, batch, seed)
+        return (torch.from_numpy(b).to(dev), torch.from_numpy(n).to(dev),
+                torch.tensor([[float(side), float(side)]] * batch, device=dev))
+
+    # C1: FCOS VOC-shaped, 8 images (launch-latency-bound: 4.4 MB) and the same shape at 256 images
+    for batch in (8, 256):
+        b, n, d = dev_boxes("fcos_voc", batch, synth.seed_for(1, 200), 512)
+        outs, cnt = fcos.format_data_batch(b, n, d, 20, [512, 512])
+        secs = graph_time(lambda: fcos.format_data_batch(b, n, d, 20, [512, 512], out=outs, num_targets=cnt))
+        entry("c1_fcos_encode_b%d" % batch, batch, sum(o.numel() for o in outs) * 4, secs,
+              "5 levels, 20 classes, <=20 boxes; batch 8 writes 4.4 MB and is launch-latency-bound")
+        del outs
+    # C2: CenterNet CrowdHuman-shaped, stride 4, batch 32 (+256)
+    sc = [32, 64, 128, 256, 512]
+    for batch in (32, 256):
+        b, n, d = dev_boxes("centernet_crowdhuman", batch, synth.seed_for(2, 200), 512)
+        o, st = centernet.format_data_batch(b, n, d, 1, [512, 512], stride=4, mode="s8", box_scales=sc)
+        secs = graph_time(lambda: centernet.format_data_batch(b, n, d, 1, [512, 512], stride=4, mode="s8", box_scales=sc, out=o, status=st))
+        entry("c2_centernet_s8_encode_b%d" % batch, batch, o.numel() * 4, secs, "[B,128,128,5,5] one-hot-centre targets, <=150 boxes")
+        del o
+    # C3: RetinaNet COCO-shaped encode (targets materialised), batch 64
+    batch = 64
+    b, n, d = dev_boxes("retina_coco", batch, synth.seed_for(3, 200), 640)
+    outs, pr = retinanet.format_data_batch(b, n, d, 80, [640, 640])
+    nbytes = sum(o.numel() for o in outs) * 4
+    secs = graph_time(lambda: retinanet.format_data_batch(b, n, d, 80, [640, 640], out=outs, num_pairs=pr))
+    entry("c3_retina_encode_b64", batch, nbytes, secs, "match + encode, targets written once (25.8 MB/image)")
+    big = torch.empty(nbytes // 4, device=dev)
+    secs = graph_time(lambda: big.zero_())
+    entry("memset_same_bytes_as_c3", batch, nbytes, secs, "cudaMemset of the same byte count: the write-only ceiling")
+    del big
+    # unfused loss over the materialised C3 targets (reads targets + predictions = 2x the map bytes)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    pred = [torch.randn(o.shape, device=dev, generator=gen) - 4.0 for o in outs]
+    secs = graph_time(lambda: retinanet.loss_batch(outs, pred))
+    entry("c3_retina_unfused_loss_b64", batch, 2 * nbytes, secs, "focal + smooth-L1 over materialised targets")
+    secs = graph_time(lambda: retinanet.encode_loss_batch(b, n, d, 80, [640, 640], pred))
+    entry("c3_retina_fused_encode_loss_b64", batch, nbytes, secs, "targets never reach HBM")
+    return out
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import __graft_entry__ as entry
+    if rank == 0 or not os.path.exists(entry.LIB):
+        entry.build()
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

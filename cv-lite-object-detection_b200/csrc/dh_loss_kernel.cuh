@@ -1,18 +1,22 @@
-// Dense-head losses as a tile streamer: focal (classes / centerness), smooth-L1 or -log(IoU) (boxes),
-// smooth-L1 of sigmoid (centerness) over (prediction, target) tiles.
+// Dense-head losses as a streaming kernel: focal (classes / centerness), smooth-L1 or -log(IoU)
+// (boxes), smooth-L1 of sigmoid (centerness) over (prediction, target) maps.
 //
-// Predictions always arrive through the TMA: one elected thread issues a 1-D bulk load per tile
-// into a two-stage shared-memory ring (mbarrier complete_tx), so the next tile is in flight while
-// the CTA does the transcendental work on the current one.  Targets come either from HBM the same
-// way (unfused: `format_data` output -> `model_loss`) or are produced on the fly by the encoder
-// policy into a zeroed shared-memory tile (fused encode+loss: targets never touch HBM, algorithmic
-// bytes drop from 3x to 1x the map size).
-// Per tile the CTA reduces {cls, reg, cen, n_pos} and writes one partial; a second tiny kernel sums
-// the partials per image in a fixed order (deterministic, float64 accumulation).
+// The kernel is bound by one read of the predictions (and, unfused, one of the targets), with about
+// 3 MUFU + 15 ALU instructions of transcendental work per element, so the structure is:
+//   * predictions are read straight from HBM with 128-bit loads, four independent loads in flight per
+//     thread (no shared-memory staging: every element is used exactly once);
+//   * targets come either from HBM the same way (unfused: `format_data` output -> `model_loss`) or are
+//     produced on the fly by the encoder policy into a small zeroed shared-memory tile (fused
+//     encode+loss: targets never touch HBM).  A tile that no GT box can touch -- the common case --
+//     takes a label-free fast path and never looks at shared memory;
+//   * tiles are handed out in image-aligned chunks by a device-side counter; a CTA keeps its partial
+//     sums in registers for a whole chunk and reduces once per chunk, so a tile costs one block barrier;
+//   * per-chunk partials {cls, reg, cen, n_pos} are summed per image by a second tiny kernel in a fixed
+//     order with float64 accumulation: results are deterministic run to run.
 //
 // Reference formulas: FCOS/fcos.py:380-496 (identical copies in the other modules).
 #pragma once
-#include "dh_policies.cuh"
+#include "dh_encode_kernel.cuh"  // build_candidates / total_candidates
 
 namespace dh {
 
@@ -35,55 +39,74 @@ struct NoPolicy {
 
 template <class P>
 struct LossArgs {
-    TileTable tt;  // maps[m].pred = predictions, maps[m].out = targets (unfused), maps[m].mask optional
+    TileTable tt;  // maps[m].pred = predictions, maps[m].out = targets (unfused)
     typename P::Params pp;
     LossSpec spec;
     const float* boxes;
     const int* nbox;
     const float* img_dim;
     int max_boxes;
-    int box_cap;  // shared-memory capacity in boxes (fused): max_boxes rounded up to 32
-    int tile_buf_bytes;
-    float* partials;  // [batch * tiles_per_image, 4]
+    int box_cap;         // shared-memory capacity in boxes (fused): max_boxes rounded up to 32
+    int tile_buf_bytes;  // fused: bytes of the shared-memory target tile
+    int chunk_tiles;     // tiles per scheduler chunk; an image is cut into chunks_per_image chunks
+    int chunks_per_image;
+    int allow_vec;  // every map pointer is 16-byte aligned
+    unsigned int* sched;
+    float* partials;  // [batch * chunks_per_image, 4]
     const float* mask_maps[DH_MAX_MAPS];
 };
 
 struct LossSmemLayout {
-    int pred_off, tgt_off, rowpos_off, rec_off, raw_off, cand_off, misc_off, args_off, total;
+    int tgt_off, rowpos_off, rec_off, raw_off, cand_off, cand2_off, misc_off, args_off, total;
 };
 template <class P, bool kFused>
 __host__ __device__ inline LossSmemLayout loss_smem_layout(int tile_buf_bytes, int rows_per_tile, int box_cap) {
     LossSmemLayout l;
-    l.pred_off = 0;
-    l.tgt_off = 2 * tile_buf_bytes;
-    l.rowpos_off = l.tgt_off + (kFused ? 1 : 2) * tile_buf_bytes;
+    l.tgt_off = 0;
+    l.rowpos_off = kFused ? tile_buf_bytes : 0;
     l.rec_off = l.rowpos_off + ((rows_per_tile * 4 + 127) & ~127);
     l.raw_off = l.rec_off + (kFused ? ((static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127) : 0);
     l.cand_off = l.raw_off + (kFused ? ((box_cap * 20 + 127) & ~127) : 0);
-    l.misc_off = l.cand_off + (kFused ? ((box_cap * 2 + 127) & ~127) : 0);
+    l.cand2_off = l.cand_off + (kFused ? 2 * DH_THREADS * 2 : 0);  // per-warp segments, double-buffered by tile parity
+    l.misc_off = l.cand2_off + (kFused ? ((box_cap * 2 + 127) & ~127) : 0);
     l.args_off = l.misc_off + 256;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
     return l;
 }
 
 // ---- element formulas (float32) ---------------------------------------------------------------
+struct ExpParts {
+    float e, inv, soft;  // exp(-|x|), 1/(1+e), log(1+e)
+};
+__device__ __forceinline__ ExpParts exp_parts(float x) {
+    ExpParts p;
+    p.e = __expf(-fabsf(x));
+    const float w = 1.0f + p.e;
+    p.inv = __fdividef(1.0f, w);
+    p.soft = __logf(w);  // log(1 + exp(-|x|)), as the reference writes it
+    return p;
+}
 // focal: y*a*(1-s)^g*softplus(-x) + (1-y)*(1-a)*s^g*softplus(x)   (FCOS/fcos.py:443-462, stable form)
 __device__ __forceinline__ float focal_term(float y, float x, float alpha, float gamma) {
-    const float ax = fabsf(x);
-    const float e = __expf(-ax);                 // exp(-|x|)
-    const float soft = __logf(1.0f + e);         // log(1 + exp(-|x|)), as the reference writes it
-    const float inv = __fdividef(1.0f, 1.0f + e);
-    const float s = x >= 0.f ? inv : e * inv;    // sigmoid(x)
-    const float om = x >= 0.f ? e * inv : inv;   // 1 - sigmoid(x)
+    const ExpParts p = exp_parts(x);
+    const float s = x >= 0.f ? p.inv : p.e * p.inv;   // sigmoid(x)
+    const float om = x >= 0.f ? p.e * p.inv : p.inv;  // 1 - sigmoid(x)
     float p_pos, p_neg;
     if (gamma == 2.0f) {
         p_pos = om * om, p_neg = s * s;
     } else {
         p_pos = __powf(om, gamma), p_neg = __powf(s, gamma);
     }
-    const float sp_pos = soft + fmaxf(x, 0.f);   // softplus(x)
-    const float sp_neg = soft - fminf(x, 0.f);   // softplus(-x)
+    const float sp_pos = p.soft + fmaxf(x, 0.f);  // softplus(x)
+    const float sp_neg = p.soft - fminf(x, 0.f);  // softplus(-x)
     return y * alpha * p_pos * sp_neg + (1.0f - y) * (1.0f - alpha) * p_neg * sp_pos;
+}
+// the same with y == 0: (1-a) * s^g * softplus(x)
+__device__ __forceinline__ float focal_neg(float x, float one_minus_alpha, float gamma) {
+    const ExpParts p = exp_parts(x);
+    const float s = x >= 0.f ? p.inv : p.e * p.inv;
+    const float pw = gamma == 2.0f ? s * s : __powf(s, gamma);
+    return one_minus_alpha * pw * (p.soft + fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float sigmoid_f(float x) {
     const float e = __expf(-fabsf(x));
@@ -106,14 +129,23 @@ __device__ __forceinline__ float iou_loss_term(const float* t, const float* p, f
     return -logf(iou + 1.0e-12f);
 }
 
-// Bring `nfl` floats starting at `g` into shared memory at `s` (same 16-byte phase as `g`):
-// the 16-byte aligned body goes through the TMA (returns its byte count for expect_tx), the ragged
-// edges (<= 3 floats each) are copied by the caller's threads with `edge_copy`.
-__device__ __forceinline__ uint32_t bulk_body(const float* g, int nfl, int& head, int& body) {
-    const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 2) & 3u);
-    head = min((4 - mis) & 3, nfl);
-    body = (nfl - head) & ~3;
-    return static_cast<uint32_t>(body) * 4u;
+struct LossAcc {
+    float cls, reg, cen;
+    int npos;
+};
+
+// One element of a row whose targets are known (`y`), `m` = positive-row weight (0, 1 or the caller's mask).
+__device__ __forceinline__ void accumulate_element(const LossSpec& sp, int cls0, int c, float x, float y, float m,
+                                                   LossAcc& acc) {
+    if (c >= cls0) {
+        acc.cls += focal_term(y, x, sp.alpha, sp.gamma);
+    } else if (c < sp.reg_ch) {
+        if (sp.reg_mode == 0 && m != 0.f) acc.reg += m * smooth_l1_term(y, x, sp.delta);
+    } else if (sp.cen_mode == 1) {
+        acc.cen += smooth_l1_term(y, sigmoid_f(x), sp.delta);
+    } else if (sp.cen_mode == 2) {
+        acc.cen += focal_term(y, x, sp.alpha, sp.gamma);
+    }
 }
 
 template <class P, bool kFused>
@@ -122,231 +154,255 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
     const LossSmemLayout lay = loss_smem_layout<P, kFused>(ga.tile_buf_bytes, ga.tt.rows_per_tile, ga.box_cap);
     const LossArgs<P>& a = *reinterpret_cast<const LossArgs<P>*>(smem + lay.args_off);  // see encode_kernel
     copy_args_to_smem(ga, reinterpret_cast<LossArgs<P>*>(smem + lay.args_off));
+    float* st = reinterpret_cast<float*>(smem + lay.tgt_off);  // fused: the on-the-fly target tile
     int* rowpos = reinterpret_cast<int*>(smem + lay.rowpos_off);
     typename P::Rec* recs = reinterpret_cast<typename P::Rec*>(smem + lay.rec_off);
     float* raw = reinterpret_cast<float*>(smem + lay.raw_off);
     unsigned short* cand = reinterpret_cast<unsigned short*>(smem + lay.cand_off);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + lay.misc_off);     // [2] tile-landed barriers
-    uint64_t* boxbar = reinterpret_cast<uint64_t*>(smem + lay.misc_off + 16);
-    int* wcount = reinterpret_cast<int*>(smem + lay.misc_off + 32);        // [8]
-    float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 64);      // [8][4]
+    unsigned short* cand_dense = reinterpret_cast<unsigned short*>(smem + lay.cand2_off);
+    uint64_t* boxbar = reinterpret_cast<uint64_t*>(smem + lay.misc_off);
+    long long* next_chunk = reinterpret_cast<long long*>(smem + lay.misc_off + 8);
+    int* wcnt = reinterpret_cast<int*>(smem + lay.misc_off + 32);      // [2][8]
+    float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 96);  // [8][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ch = ga.tt.ch;
+    const LossSpec sp = ga.spec;
+    const int cls0 = sp.reg_ch + (sp.cen_mode != 0 ? 1 : 0);
+    const bool vec = ga.allow_vec && (ch & 3) == 0 && sp.cen_mode == 0;  // rows are whole float4s: [regs][classes...]
+    const int vpr = ch >> 2;                            // float4s per row (vector path)
     const FastDiv div_ch = make_fastdiv(static_cast<uint32_t>(ch));
-    const long long total_tiles = static_cast<long long>(ga.tt.batch) * ga.tt.tiles_per_image;
-    const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
-    if (t_begin >= t_end) return;
+    const FastDiv div_vpr = make_fastdiv(static_cast<uint32_t>(vpr > 0 ? vpr : 1));
+    const float oma = 1.0f - sp.alpha;
+    const int tpi = ga.tt.tiles_per_image;
+    const long long n_chunks = static_cast<long long>(ga.tt.batch) * ga.chunks_per_image;
+    long long chunk = blockIdx.x;
+    if (chunk >= n_chunks) return;
 
-    if (kFused) {  // the on-the-fly target tile starts zeroed; owners re-zero what they dirty
+    {  // shared-memory state that must start at zero
         float4* z = reinterpret_cast<float4*>(smem + lay.tgt_off);
-        for (int e = tid; e < ga.tile_buf_bytes / 16; e += DH_THREADS) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n4 = (kFused ? ga.tile_buf_bytes : 0) / 16;
+        for (int e = tid; e < n4; e += DH_THREADS) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = tid; r < ga.tt.rows_per_tile; r += DH_THREADS) rowpos[r] = 0;
     }
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
         mbar_init(boxbar, 1);
         mbar_init_fence();
     }
     __syncthreads();
 
-    // producer: one thread issues the bulk loads of a tile into stage s
-    auto issue = [&](const TileCursor& c, int s) {
-        TileInfo ti;
-        cursor_info(a.tt, c, ti);
-        const MapDesc& md = a.tt.maps[ti.m];
-        const long long off = static_cast<long long>(ti.b) * md.image_stride + static_cast<long long>(ti.r0) * ch;
-        const int nfl = ti.nrows * ch;
-        int head, body;
-        const float* gp = md.pred + off;
-        uint32_t bytes = bulk_body(gp, nfl, head, body);
-        const int misp = static_cast<int>((reinterpret_cast<uintptr_t>(gp) >> 2) & 3u);
-        float* sp = reinterpret_cast<float*>(smem + lay.pred_off + s * a.tile_buf_bytes) + misp;
-        uint32_t tot = bytes;
-        const float* gt = nullptr;
-        float* st = nullptr;
-        int head_t = 0, body_t = 0;
-        if (!kFused) {
-            gt = md.out + off;
-            tot += bulk_body(gt, nfl, head_t, body_t);
-            const int mist = static_cast<int>((reinterpret_cast<uintptr_t>(gt) >> 2) & 3u);
-            st = reinterpret_cast<float*>(smem + lay.tgt_off + s * a.tile_buf_bytes) + mist;
-        }
-        mbar_expect_tx(&full[s], tot);  // tot may be 0: the arrival alone completes the phase
-        if (body > 0) bulk_g2s(sp + head, gp + head, static_cast<uint32_t>(body) * 4u, &full[s]);
-        if (!kFused && body_t > 0) bulk_g2s(st + head_t, gt + head_t, static_cast<uint32_t>(body_t) * 4u, &full[s]);
-    };
-
-    TileCursor cur, nxt;
-    cursor_init(a.tt, t_begin, cur);
-    nxt = cur;
-    if (tid == 0) issue(cur, 0);
-    uint32_t parity0 = 0, parity1 = 0, box_parity = 0;
+    uint32_t box_parity = 0;
     int cur_img = -1, n_boxes = 0;
     int it = 0;
-    for (long long tile = t_begin; tile < t_end; ++tile, ++it, cur = nxt) {
-        const int s = it & 1;
-        TileInfo ti;
-        cursor_info(a.tt, cur, ti);
-        const MapDesc& md = a.tt.maps[ti.m];
-        cursor_next(a.tt, nxt);
-        const long long off = static_cast<long long>(ti.b) * md.image_stride + static_cast<long long>(ti.r0) * ch;
-        const int nfl = ti.nrows * ch;
-        // stage s^1 was fully consumed before the __syncthreads that ended the previous iteration
-        if (tid == 0 && tile + 1 < t_end) issue(nxt, s ^ 1);
+    for (; chunk < n_chunks;) {
+        const long long img = chunk / ga.chunks_per_image;
+        const int sub = static_cast<int>(chunk - img * ga.chunks_per_image);
+        const long long t_begin = img * tpi + static_cast<long long>(sub) * ga.chunk_tiles;
+        const long long t_end = min(t_begin + ga.chunk_tiles, (img + 1) * tpi);
+        if (tid == 0) *next_chunk = static_cast<long long>(atomicAdd(ga.sched, 1u)) + gridDim.x;
+        LossAcc acc = {0.f, 0.f, 0.f, 0};
+        TileCursor cur;
+        cursor_init(a.tt, t_begin, cur);
+        for (long long tile = t_begin; tile < t_end; ++tile, ++it, cursor_next(a.tt, cur)) {
+            TileInfo ti;
+            cursor_info(a.tt, cur, ti);
+            const MapDesc& md = a.tt.maps[ti.m];
+            const long long off = static_cast<long long>(ti.b) * md.image_stride + static_cast<long long>(ti.r0) * ch;
+            const float* __restrict__ gp = md.pred + off;
+            const float* __restrict__ gt = kFused ? nullptr : md.out + off;
+            const int nfl = ti.nrows * ch;
+            int ncand = 0;
+            uint32_t dmask = 0u;
 
-        const float* gp = md.pred + off;
-        const int misp = static_cast<int>((reinterpret_cast<uintptr_t>(gp) >> 2) & 3u);
-        float* sp = reinterpret_cast<float*>(smem + lay.pred_off + s * a.tile_buf_bytes) + misp;
-        float* st;
-        {   // ragged edges of the prediction (and target) tile: plain loads into the same buffers
-            int head, body;
-            bulk_body(gp, nfl, head, body);
-            if (tid < head) sp[tid] = gp[tid];
-            const int tail0 = head + body;
-            if (tid >= 32 && tid - 32 < nfl - tail0) sp[tail0 + tid - 32] = gp[tail0 + tid - 32];
-        }
-        if (!kFused) {
-            const float* gt = md.out + off;
-            const int mist = static_cast<int>((reinterpret_cast<uintptr_t>(gt) >> 2) & 3u);
-            st = reinterpret_cast<float*>(smem + lay.tgt_off + s * a.tile_buf_bytes) + mist;
-            int head, body;
-            bulk_body(gt, nfl, head, body);
-            if (tid >= 64 && tid - 64 < head) st[tid - 64] = gt[tid - 64];
-            const int tail0 = head + body;
-            if (tid >= 96 && tid - 96 < nfl - tail0) st[tail0 + tid - 96] = gt[tail0 + tid - 96];
-        } else {
-            st = reinterpret_cast<float*>(smem + lay.tgt_off);
-        }
-
-        // ---- targets ------------------------------------------------------------------------
-        for (int r = tid; r < ti.nrows; r += DH_THREADS) rowpos[r] = 0;
-        uint32_t dmask = 0u;
-        if constexpr (kFused) {
-            if (ti.b != cur_img) {
-                __syncthreads();
-                n_boxes = stage_boxes(a.boxes, a.nbox, ti.b, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
-                const float hi = a.img_dim[2 * ti.b], wi = a.img_dim[2 * ti.b + 1];
-                if (tid < n_boxes) P::make_record(a.pp, raw + 5 * tid, hi, wi, tid, recs[tid]);
-                __syncthreads();
-                if (tile == static_cast<long long>(ti.b) * a.tt.tiles_per_image) P::image_prologue(a.pp, recs, n_boxes, ti.b);
-                cur_img = ti.b;
+            if constexpr (kFused) {
+                if (ti.b != cur_img) {
+                    __syncthreads();
+                    n_boxes = stage_boxes(a.boxes, a.nbox, ti.b, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
+                    const float hi = a.img_dim[2 * ti.b], wi = a.img_dim[2 * ti.b + 1];
+                    if (tid < n_boxes) P::make_record(a.pp, raw + 5 * tid, hi, wi, tid, recs[tid]);
+                    __syncthreads();
+                    if (tile == static_cast<long long>(ti.b) * tpi) P::image_prologue(a.pp, recs, n_boxes, ti.b);
+                    cur_img = ti.b;
+                }
+                unsigned short* cseg = cand + (it & 1) * DH_THREADS;  // parity double-buffer: one barrier per tile
+                int* wc = wcnt + (it & 1) * 8;
+                build_candidates<P>(a.pp, recs, n_boxes, ti, md, cseg, wc, warp, lane);
+                __syncthreads();  // barrier A
+                ncand = total_candidates(wc);
+                if (ncand > 0) {  // uniform: materialise this tile's targets in shared memory
+                    int base = 0;
+                    for (int w = 0; w < warp; ++w) base += wc[w];
+                    if (lane < wc[warp]) cand_dense[base + lane] = cseg[warp * 32 + lane];
+                    __syncthreads();
+                    int painted = 0;
+                    for (int k = 0, r = tid; r < ti.nrows; r += DH_THREADS, ++k) {
+                        const int n = P::emit_row(a.pp, ti, md, ti.r0 + r, st + r * ch, recs, cand_dense, ncand);
+                        if (n > 0) dmask |= (1u << k), rowpos[r] = 1, ++acc.npos;
+                        painted += n;
+                    }
+                    P::tile_epilogue(a.pp, ti, painted);
+                    __syncthreads();
+                }
+            } else {
+                // unfused: positive rows come from the materialised targets (or the caller's mask)
+                if (sp.reg_ch > 0) {
+                    if (sp.pos_rule == 2) {
+                        const float* gm = a.mask_maps[ti.m] + static_cast<long long>(ti.b) * md.rows + ti.r0;
+                        for (int r = tid; r < ti.nrows; r += DH_THREADS) rowpos[r] = __float_as_int(gm[r]);
+                    } else if (vec) {
+                        const float4* __restrict__ gt4 = reinterpret_cast<const float4*>(gt);
+                        for (int q = tid; q < ti.nrows * vpr; q += DH_THREADS) {
+                            const int r = static_cast<int>(fdiv_u32(q, div_vpr));
+                            if ((q - r * vpr) * 4 >= cls0) {
+                                const float4 y = __ldg(gt4 + q);
+                                const float mx = fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w));
+                                if (sp.pos_rule == 0 ? (mx >= 1.0f) : (mx > 0.0f)) rowpos[r] = 1;
+                            }
+                        }
+                    } else {
+                        for (int e = tid; e < nfl; e += DH_THREADS) {
+                            const int r = static_cast<int>(fdiv_u32(e, div_ch));
+                            if (e - r * ch >= cls0) {
+                                const float y = __ldg(gt + e);
+                                if (sp.pos_rule == 0 ? (y >= 1.0f) : (y > 0.0f)) rowpos[r] = 1;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                ncand = 1;  // targets always have to be looked at
             }
-            const bool hit = tid < n_boxes && P::tile_hit(a.pp, recs[tid], ti, md);
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) wcount[warp] = __popc(bal);
-            __syncthreads();
-            int base = 0, ncand = 0;
+
+            // ---- element pass --------------------------------------------------------------------
+            if (vec) {
+                const int nvec = ti.nrows * vpr;
+                const float4* __restrict__ gp4 = reinterpret_cast<const float4*>(gp);
+                const float4* __restrict__ gt4 = reinterpret_cast<const float4*>(gt);
+                const float4* st4 = reinterpret_cast<const float4*>(st);
+                for (int q0 = tid; q0 < nvec; q0 += 4 * DH_THREADS) {
+                    float4 x[4];
 #pragma unroll
-            for (int w = 0; w < DH_THREADS / 32; ++w) {
-                const int c = wcount[w];
-                base += (w < warp) ? c : 0;
-                ncand += c;
-            }
-            if (hit) cand[base + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(tid);
-            __syncthreads();
-            if (ncand > 0) {
-                int painted = 0;
-                for (int k = 0, r = tid; r < ti.nrows; r += DH_THREADS, ++k) {
-                    const int n = P::emit_row(a.pp, ti, md, ti.r0 + r, st + r * ch, recs, cand, ncand);
-                    if (n > 0) dmask |= (1u << k), rowpos[r] = 1;
-                    painted += n;
+                    for (int u = 0; u < 4; ++u) {
+                        const int q = q0 + u * DH_THREADS;
+                        x[u] = q < nvec ? __ldcs(gp4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int q = q0 + u * DH_THREADS;
+                        if (q >= nvec) break;
+                        const int r = static_cast<int>(fdiv_u32(q, div_vpr));
+                        const int c4 = q - r * vpr;
+                        const bool is_reg = sp.reg_ch > 0 && c4 == 0;
+                        if (kFused && (ncand == 0 || !rowpos[r])) {  // label-free fast path
+                            if (!is_reg) {
+                                acc.cls += focal_neg(x[u].x, oma, sp.gamma) + focal_neg(x[u].y, oma, sp.gamma) +
+                                           focal_neg(x[u].z, oma, sp.gamma) + focal_neg(x[u].w, oma, sp.gamma);
+                            }
+                            continue;
+                        }
+                        const float4 y = kFused ? st4[q] : __ldcs(gt4 + q);
+                        if (is_reg) {
+                            const float m = sp.pos_rule == 2 ? __int_as_float(rowpos[r]) : (rowpos[r] ? 1.0f : 0.0f);
+                            if (m != 0.f) {
+                                if (!kFused) ++acc.npos;
+                                if (sp.reg_mode == 0) {
+                                    acc.reg += m * (smooth_l1_term(y.x, x[u].x, sp.delta) + smooth_l1_term(y.y, x[u].y, sp.delta) +
+                                                    smooth_l1_term(y.z, x[u].z, sp.delta) + smooth_l1_term(y.w, x[u].w, sp.delta));
+                                } else {
+                                    const int row = ti.r0 + r;
+                                    const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
+                                    const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
+                                    const float tv[4] = {y.x, y.y, y.z, y.w}, pv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                                    acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                                }
+                            }
+                        } else {
+                            acc.cls += focal_term(y.x, x[u].x, sp.alpha, sp.gamma) + focal_term(y.y, x[u].y, sp.alpha, sp.gamma) +
+                                       focal_term(y.z, x[u].z, sp.alpha, sp.gamma) + focal_term(y.w, x[u].w, sp.alpha, sp.gamma);
+                        }
+                    }
                 }
-                P::tile_epilogue(a.pp, ti, painted);
-            }
-        }
-        // wait for the TMA bytes of this stage
-        mbar_wait(&full[s], s ? parity1 : parity0);
-        if (s) parity1 ^= 1u; else parity0 ^= 1u;
-        __syncthreads();  // edge loads + emitted rows + rowpos zeroing visible
-
-        const int cls0 = a.spec.reg_ch + (a.spec.cen_mode != 0 ? 1 : 0);
-        if (!kFused) {  // positive rows from the materialised targets (or the caller's mask)
-            if (a.spec.pos_rule == 2) {
-                const float* gm = a.mask_maps[ti.m] + static_cast<long long>(ti.b) * md.rows + ti.r0;
-                for (int r = tid; r < ti.nrows; r += DH_THREADS) rowpos[r] = __float_as_int(gm[r]);
-            } else if (a.spec.reg_ch > 0) {
-                for (int e = tid; e < nfl; e += DH_THREADS) {
-                    const int r = static_cast<int>(fdiv_u32(e, div_ch));
-                    const int c = e - r * ch;
-                    if (c >= cls0) {
-                        const float y = st[e];
-                        if (a.spec.pos_rule == 0 ? (y >= 1.0f) : (y > 0.0f)) rowpos[r] = 1;
+            } else {
+                for (int e0 = tid; e0 < nfl; e0 += 4 * DH_THREADS) {
+                    float x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * DH_THREADS;
+                        x[u] = e < nfl ? __ldcs(gp + e) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * DH_THREADS;
+                        if (e >= nfl) break;
+                        const int r = static_cast<int>(fdiv_u32(e, div_ch));
+                        const int c = e - r * ch;
+                        const bool pos_row = rowpos[r] != 0;
+                        float y = 0.f;
+                        if (!kFused) y = __ldcs(gt + e);
+                        else if (ncand > 0 && pos_row) y = st[e];
+                        const float m = sp.pos_rule == 2 ? __int_as_float(rowpos[r]) : (pos_row ? 1.0f : 0.0f);
+                        if (c == 0 && sp.reg_ch > 0 && m != 0.f) {
+                            if (!kFused) ++acc.npos;
+                            if (sp.reg_mode == 1) {
+                                const int row = ti.r0 + r;
+                                const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
+                                const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
+                                float tv[4], pv[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    pv[k] = gp[e + k];
+                                    tv[k] = kFused ? st[e + k] : gt[e + k];
+                                }
+                                acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                            }
+                        }
+                        accumulate_element(sp, cls0, c, x[u], y, m, acc);
                     }
                 }
             }
-            __syncthreads();
-        }
 
-        // ---- element pass -------------------------------------------------------------------
-        float acc_cls = 0.f, acc_reg = 0.f, acc_cen = 0.f;
-        int npos = 0;
-        const float alpha = a.spec.alpha, gamma = a.spec.gamma, delta = a.spec.delta;
-        for (int e = tid; e < nfl; e += DH_THREADS) {
-            const int r = static_cast<int>(fdiv_u32(e, div_ch));
-            const int c = e - r * ch;
-            const float x = sp[e], y = st[e];
-            if (c >= cls0) {
-                acc_cls += focal_term(y, x, alpha, gamma);
-            } else if (c < a.spec.reg_ch) {
-                float m;
-                if (a.spec.pos_rule == 2) {
-                    m = __int_as_float(rowpos[r]);
-                } else {
-                    m = rowpos[r] ? 1.0f : 0.0f;
+            if constexpr (kFused) {
+                if (ncand > 0) {  // uniform: re-zero the rows this thread emitted once everybody has read them
+                    __syncthreads();
+                    for (int k = 0; dmask; ++k, dmask >>= 1)
+                        if (dmask & 1u) {
+                            const int r = tid + k * DH_THREADS;
+                            float* row = st + r * ch;
+                            for (int c = 0; c < ch; ++c) row[c] = 0.f;
+                            rowpos[r] = 0;
+                        }
                 }
-                if (c == 0 && m != 0.f) ++npos;
-                if (m != 0.f) {
-                    if (a.spec.reg_mode == 0) {
-                        acc_reg += m * smooth_l1_term(y, x, delta);
-                    } else if (c == 0) {
-                        const int row = ti.r0 + r;
-                        const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
-                        const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
-                        const int j = cell - i * md.width;
-                        acc_reg += m * iou_loss_term(st + e, sp + e, static_cast<float>(i), static_cast<float>(j));
-                    }
-                }
-            } else {  // the centerness channel
-                if (a.spec.cen_mode == 1)
-                    acc_cen += smooth_l1_term(y, sigmoid_f(x), delta);
-                else if (a.spec.cen_mode == 2)
-                    acc_cen += focal_term(y, x, alpha, gamma);
+            } else if (sp.reg_ch > 0) {
+                __syncthreads();  // everybody has consumed rowpos
+                for (int r = tid; r < ti.nrows; r += DH_THREADS) rowpos[r] = 0;
             }
         }
-        // ---- per-tile reduction -> partials[tile] -------------------------------------------
-        acc_cls = warp_sum(acc_cls), acc_reg = warp_sum(acc_reg), acc_cen = warp_sum(acc_cen);
-        npos = warp_sum_i(npos);
+        // ---- per-chunk reduction -> partials[chunk] ----------------------------------------------------
+        acc.cls = warp_sum(acc.cls), acc.reg = warp_sum(acc.reg), acc.cen = warp_sum(acc.cen);
+        acc.npos = warp_sum_i(acc.npos);
         if (lane == 0) {
-            wred[warp * 4 + 0] = acc_cls, wred[warp * 4 + 1] = acc_reg, wred[warp * 4 + 2] = acc_cen;
-            wred[warp * 4 + 3] = static_cast<float>(npos);
+            wred[warp * 4 + 0] = acc.cls, wred[warp * 4 + 1] = acc.reg, wred[warp * 4 + 2] = acc.cen;
+            wred[warp * 4 + 3] = static_cast<float>(acc.npos);
         }
-        __syncthreads();
+        __syncthreads();  // also: the prefetched chunk id is visible
         if (tid < 4) {
             float v = 0.f;
 #pragma unroll
             for (int w = 0; w < DH_THREADS / 32; ++w) v += wred[w * 4 + tid];
-            a.partials[tile * 4 + tid] = v;
+            a.partials[chunk * 4 + tid] = v;
         }
-        if constexpr (kFused) {  // re-zero the rows this thread emitted
-            for (int k = 0; dmask; ++k, dmask >>= 1)
-                if (dmask & 1u) {
-                    float* row = st + (tid + k * DH_THREADS) * ch;
-                    for (int c = 0; c < ch; ++c) row[c] = 0.f;
-                }
-        }
-        __syncthreads();  // stage s, wred and the target tile are free again
+        chunk = *next_chunk;
+        __syncthreads();  // wred / next_chunk are free again
     }
 }
 
-// partials [B * tiles_per_image, 4] -> per_image [B, 4]; one CTA per image, fixed summation order
-__global__ void loss_finalize_images(const float* __restrict__ partials, int tiles_per_image, float* __restrict__ per_image) {
+// partials [B * chunks_per_image, 4] -> per_image [B, 4]; one CTA per image, fixed summation order
+__global__ void loss_finalize_images(const float* __restrict__ partials, int chunks_per_image, float* __restrict__ per_image) {
     __shared__ double red[128][4];
     const int b = blockIdx.x, tid = threadIdx.x;
     double acc[4] = {0, 0, 0, 0};
-    const float4* p = reinterpret_cast<const float4*>(partials) + static_cast<long long>(b) * tiles_per_image;
-    for (int t = tid; t < tiles_per_image; t += 128) {
+    const float4* p = reinterpret_cast<const float4*>(partials) + static_cast<long long>(b) * chunks_per_image;
+    for (int t = tid; t < chunks_per_image; t += 128) {
         const float4 v = p[t];
         acc[0] += v.x, acc[1] += v.y, acc[2] += v.z, acc[3] += v.w;
     }

@@ -20,13 +20,6 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
                        const char* who) {
     const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
     if (a.tt.batch == 0) return DH_OK;
-    // scratch: tile partials + (optional) per-image sums when the caller only wants the total
-    const size_t part_bytes = static_cast<size_t>(total) * 16;
-    const size_t img_bytes = static_cast<size_t>(a.tt.batch) * 16;
-    char* sc = static_cast<char*>(scratch(h, part_bytes + img_bytes + 256));
-    if (!sc) return DH_ERR_CUDA;
-    a.partials = reinterpret_cast<float*>(sc);
-    float* per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
     a.box_cap = ((a.max_boxes > 0 ? a.max_boxes : 1) + 31) & ~31;
     const LossSmemLayout lay = loss_smem_layout<P, kFused>(a.tile_buf_bytes, a.tt.rows_per_tile, a.box_cap);
     if (lay.total > 227 * 1024)
@@ -40,13 +33,37 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
-    if (grid > total) grid = total;
+    // image-aligned chunks (a chunk never mixes images, so per-image sums stay separable): aim at >= 8 chunks
+    // per CTA, 4..64 tiles each
+    const int tpi = a.tt.tiles_per_image;
+    long long want = total / (grid * 8);
+    want = want < 4 ? 4 : (want > 64 ? 64 : want);
+    const int n_sub = tpi > 0 ? static_cast<int>((tpi + want - 1) / want) : 1;
+    a.chunk_tiles = tpi > 0 ? (tpi + n_sub - 1) / n_sub : 1;
+    a.chunks_per_image = tpi > 0 ? (tpi + a.chunk_tiles - 1) / a.chunk_tiles : 1;
+    const long long n_chunks = static_cast<long long>(a.tt.batch) * a.chunks_per_image;
+    if (grid > n_chunks) grid = n_chunks;
+    a.allow_vec = 1;
+    for (int m = 0; m < a.tt.n_maps; ++m) {
+        if ((reinterpret_cast<uintptr_t>(a.tt.maps[m].pred) & 15u) || (!kFused && (reinterpret_cast<uintptr_t>(a.tt.maps[m].out) & 15u)))
+            a.allow_vec = 0;
+        if ((a.tt.maps[m].image_stride & 3) != 0) a.allow_vec = 0;
+    }
+    // scratch: chunk partials + (optional) per-image sums when the caller only wants the total
+    const size_t part_bytes = static_cast<size_t>(n_chunks) * 16;
+    const size_t img_bytes = static_cast<size_t>(a.tt.batch) * 16;
+    char* sc = static_cast<char*>(scratch(h, part_bytes + img_bytes + 512));
+    if (!sc) return DH_ERR_CUDA;
+    a.partials = reinterpret_cast<float*>(sc);
+    float* per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
     if (total > 0) {
+        a.sched = next_sched_counter(h, st);
+        if (!a.sched) return DH_ERR_CUDA;
         loss_kernel<P, kFused><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
         DH_CUDA(cudaGetLastError());
         h->launches += 1;
     }
-    loss_finalize_images<<<a.tt.batch, 128, 0, st>>>(a.partials, a.tt.tiles_per_image, per_image);
+    loss_finalize_images<<<a.tt.batch, 128, 0, st>>>(a.partials, total > 0 ? a.chunks_per_image : 0, per_image);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
     if (out_total) {
@@ -58,8 +75,8 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
 }
 
 static int loss_tile_bytes(const dh_handle_s* h) {
-    int b = h->tile_bytes / 2;
-    return b < 4096 ? 4096 : b;
+    (void)h;
+    return 32768;  // work granule of the loss kernels (and the fused path's shared-memory target tile)
 }
 
 }  // namespace dh
