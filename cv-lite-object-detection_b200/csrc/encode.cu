@@ -53,7 +53,8 @@ static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, cons
         DH_CUDA(cudaFuncSetAttribute(encode_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    int per_sm = (227 * 1024) / (lay.total + 1024);  // 1 KB per-CTA reservation
+    int per_sm = 1;  // resident CTAs per SM (registers and shared memory both count)
+    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<P>, DH_THREADS, lay.total));
     if (per_sm > h->ctas_per_sm) per_sm = h->ctas_per_sm;
     if (per_sm < 1) per_sm = 1;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;

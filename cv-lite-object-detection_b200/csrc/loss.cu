@@ -29,9 +29,9 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
         DH_CUDA(cudaFuncSetAttribute(loss_kernel<P, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    int per_sm = (227 * 1024) / (lay.total + 1024);
+    int per_sm = 1;  // resident CTAs per SM (registers and shared memory both count)
+    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_kernel<P, kFused>, DH_THREADS, lay.total));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
     // image-aligned chunks (a chunk never mixes images, so per-image sums stay separable): aim at >= 8 chunks
     // per CTA, 4..64 tiles each
