@@ -1,0 +1,260 @@
+// Greedy NMS on the device: sort by score, 64x64-blocked IoU bit matrix, single-warp sweep.
+//
+// Replaces RetinaNet.cpu_nms (RetinaNet/retinanet_module.py:453-481, class-agnostic, keeps `ovr <= thr`)
+// and the per-class / capped NMS that FCOS inference delegates to TensorFlow's
+// combined_non_max_suppression (FCOS/infer_fcos.py:58-61).  Both are one sweep in global score order:
+// a per-class NMS is the same sweep with "same class" folded into the suppression predicate, and the
+// per-class / total caps are counters inside the sweep.
+//
+//   kernel 1  nms_sort_kernel   one CTA per image: (score, index) keys -> bitonic sort in shared memory
+//                               (descending score, ascending index on ties = a stable sort), threshold,
+//                               gather boxes into score order.
+//   kernel 2  nms_mask_kernel   grid (col blocks, row blocks, images): bit j of mask[i][w] says box
+//                               64*w+j (later in order) is suppressed by box i; warp-ballot builds words.
+//   kernel 3  nms_sweep_kernel  one warp per image walks the order, OR-ing mask rows of kept boxes into a
+//                               register-resident `removed` bit vector (lanes own words).
+//
+// Float arithmetic follows the reference operation order with contraction disabled, so kept indices
+// are bit-identical to the NumPy loop.
+#include <cstring>
+
+#include "dh_common.cuh"
+#include "dh_host.h"
+
+namespace dh {
+
+constexpr int kNmsMaxN = 16384;  // candidates per image (shared-memory sort)
+constexpr int kSortThreads = 1024;
+
+struct NmsParams {
+    int n_max;        // row stride of dets in boxes: dets is [B, n_max, row_floats]
+    int row_floats;   // >= 5 (mode 0) or >= 6 (per-class)
+    int per_class;    // 0: class-agnostic cpu_nms rule; 1: same-class IoU > thr rule
+    int inclusive;    // 1: keep score >= min_score; 0: keep score > min_score
+    float iou_thr, min_score;
+    int max_per_class, max_total, num_classes;
+    int max_out;  // capacity of keep[b]
+};
+
+// ---- kernel 1 -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __restrict__ dets, const int* __restrict__ n_valid,
+                                                                NmsParams p, int n_pow2, float4* __restrict__ sorted_boxes,
+                                                                int* __restrict__ sorted_cls, int* __restrict__ order,
+                                                                int* __restrict__ n_cand) {
+    extern __shared__ unsigned long long keys[];  // [n_pow2]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = n_valid ? min(n_valid[b], p.n_max) : p.n_max;
+    const float* d = dets + static_cast<long long>(b) * p.n_max * p.row_floats;
+    for (int i = tid; i < n_pow2; i += kSortThreads) {
+        unsigned long long k = 0ull;  // sorts to the end
+        if (i < n) {
+            const float s = d[static_cast<long long>(i) * p.row_floats + 4];
+            const bool ok = p.inclusive ? (s >= p.min_score) : (s > p.min_score);
+            if (ok) {
+                // monotone map float -> uint (handles negatives too), then descending sort of the 64-bit key
+                unsigned u = __float_as_uint(s);
+                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                k = (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned>(i));
+                if (k == 0ull) k = 1ull;
+            }
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n_pow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (n_pow2 >> 1); t += kSortThreads) {
+                const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = keys[lo], c = keys[hi];
+                if (desc ? (a < c) : (a > c)) keys[lo] = c, keys[hi] = a;
+            }
+            __syncthreads();
+        }
+    }
+    // valid keys are a prefix; count them and gather boxes in score order
+    int cnt = 0;
+    for (int i = tid; i < n_pow2; i += kSortThreads) cnt += (keys[i] != 0ull);
+    __shared__ int total;
+    if (tid == 0) total = 0;
+    __syncthreads();
+    cnt = warp_sum_i(cnt);
+    if ((tid & 31) == 0 && cnt) atomicAdd(&total, cnt);
+    __syncthreads();
+    const int m = total;
+    if (tid == 0) n_cand[b] = m;
+    for (int i = tid; i < m; i += kSortThreads) {
+        const int src = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(keys[i] & 0xFFFFFFFFull));
+        const float* r = d + static_cast<long long>(src) * p.row_floats;
+        sorted_boxes[static_cast<long long>(b) * p.n_max + i] = make_float4(r[0], r[1], r[2], r[3]);
+        sorted_cls[static_cast<long long>(b) * p.n_max + i] = p.per_class ? __float2int_rz(r[5]) : 0;
+        order[static_cast<long long>(b) * p.n_max + i] = src;
+    }
+}
+
+// ---- suppression predicates ---------------------------------------------------------------------------
+// RetinaNet/retinanet_module.py:461-479: areas from raw corners, ovr = inter / (a_i + a_j - inter + 1e-8),
+// the later box survives only if ovr <= thr (a NaN does not survive).
+__device__ __forceinline__ bool suppress_agnostic(const float4& a, const float4& c, float thr) {
+    const float area_a = fmul(fsub(a.z, a.x), fsub(a.w, a.y));
+    const float area_c = fmul(fsub(c.z, c.x), fsub(c.w, c.y));
+    const float w = fmaxf(0.0f, fsub(fminf(a.z, c.z), fmaxf(a.x, c.x)));
+    const float h = fmaxf(0.0f, fsub(fminf(a.w, c.w), fmaxf(a.y, c.y)));
+    const float inter = fmul(w, h);
+    const float ovr = fdiv(inter, fadd(fsub(fadd(area_a, area_c), inter), 1e-8f));
+    return !(ovr <= thr);
+}
+// combined-NMS rule (TensorFlow's op, restated; parity unpinned): corner order normalised, degenerate
+// boxes never suppress, IoU > thr suppresses.
+__device__ __forceinline__ bool suppress_iou(const float4& a0, const float4& c0, float thr) {
+    const float ay1 = fminf(a0.x, a0.z), ax1 = fminf(a0.y, a0.w), ay2 = fmaxf(a0.x, a0.z), ax2 = fmaxf(a0.y, a0.w);
+    const float cy1 = fminf(c0.x, c0.z), cx1 = fminf(c0.y, c0.w), cy2 = fmaxf(c0.x, c0.z), cx2 = fmaxf(c0.y, c0.w);
+    const float area_a = fmul(fsub(ay2, ay1), fsub(ax2, ax1)), area_c = fmul(fsub(cy2, cy1), fsub(cx2, cx1));
+    if (!(area_a > 0.f) || !(area_c > 0.f)) return false;
+    const float ih = fmaxf(0.f, fsub(fminf(ay2, cy2), fmaxf(ay1, cy1)));
+    const float iw = fmaxf(0.f, fsub(fminf(ax2, cx2), fmaxf(ax1, cx1)));
+    const float inter = fmul(ih, iw);
+    const float uni = fsub(fadd(area_a, area_c), inter);
+    return uni > 0.f && fdiv(inter, uni) > thr;
+}
+
+// ---- kernel 2 -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sorted_boxes, const int* __restrict__ sorted_cls,
+                                                      const int* __restrict__ n_cand, NmsParams p, int words,
+                                                      unsigned long long* __restrict__ mask) {
+    const int b = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+    const int m = n_cand[b];
+    if (rb * 64 >= m || cb * 64 >= m || cb < rb) return;  // only later boxes (j > i) can be suppressed
+    __shared__ float4 cbox[64];
+    __shared__ int ccls[64];
+    const int tid = threadIdx.x;
+    const long long base = static_cast<long long>(b) * p.n_max;
+    const int j = cb * 64 + tid;
+    if (j < m) cbox[tid] = sorted_boxes[base + j], ccls[tid] = sorted_cls[base + j];
+    __syncthreads();
+    const int i = rb * 64 + tid;
+    if (i >= m) return;
+    const float4 a = sorted_boxes[base + i];
+    const int ac = sorted_cls[base + i];
+    unsigned long long bits = 0ull;
+    const int jn = min(64, m - cb * 64);
+    for (int t = (rb == cb) ? tid + 1 : 0; t < jn; ++t) {
+        bool sup;
+        if (p.per_class)
+            sup = (ccls[t] == ac) && suppress_iou(a, cbox[t], p.iou_thr);
+        else
+            sup = suppress_agnostic(a, cbox[t], p.iou_thr);
+        if (sup) bits |= (1ull << t);
+    }
+    mask[(base + i) * words + cb] = bits;
+}
+
+// ---- kernel 3 -----------------------------------------------------------------------------------------
+// One warp per image.  Lane l owns words l, l+32, ... of the `removed` vector (<= 8 words per lane).
+__global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ sorted_cls,
+                                                       const int* __restrict__ order, const int* __restrict__ n_cand, NmsParams p,
+                                                       int words, int* __restrict__ keep, int* __restrict__ n_keep) {
+    extern __shared__ int class_count[];  // [num_classes] when per-class caps are on
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int m = n_cand[b];
+    const long long base = static_cast<long long>(b) * p.n_max;
+    const bool caps = p.per_class && p.max_per_class > 0;
+    if (caps)
+        for (int c = lane; c < p.num_classes; c += 32) class_count[c] = 0;
+    __syncwarp();
+    unsigned long long removed[kNmsMaxN / 64 / 32];
+#pragma unroll
+    for (int k = 0; k < kNmsMaxN / 64 / 32; ++k) removed[k] = 0ull;
+    int kept = 0;
+    const int max_total = p.max_total > 0 ? min(p.max_total, p.max_out) : p.max_out;
+    for (int i = 0; i < m && kept < max_total; ++i) {
+        const int w = i >> 6;
+        // the owner lane of word w broadcasts the bit
+        unsigned long long word = 0ull;
+#pragma unroll
+        for (int k = 0; k < kNmsMaxN / 64 / 32; ++k)
+            if ((w >> 5) == k) word = removed[k];
+        word = __shfl_sync(0xffffffffu, word, w & 31);
+        if ((word >> (i & 63)) & 1ull) continue;
+        if (caps) {
+            const int c = sorted_cls[base + i];
+            const bool full = c >= 0 && c < p.num_classes && class_count[c] >= p.max_per_class;
+            if (full) continue;  // over the per-class cap: dropped, and it suppresses nobody (it was never selected)
+            __syncwarp();
+            if (lane == 0 && c >= 0 && c < p.num_classes) class_count[c] += 1;
+            __syncwarp();
+        }
+        if (lane == 0) keep[static_cast<long long>(b) * p.max_out + kept] = order[base + i];
+        ++kept;
+        const unsigned long long* row = mask + (base + i) * words;
+#pragma unroll
+        for (int k = 0; k < kNmsMaxN / 64 / 32; ++k) {
+            const int ww = lane + 32 * k;
+            if (ww < words && ww >= w) removed[k] |= row[ww];
+        }
+    }
+    if (lane == 0) n_keep[b] = kept;
+}
+
+}  // namespace dh
+
+using namespace dh;
+
+extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, int batch, int n_max, int row_floats,
+                      int mode, float iou_thr, float min_score, int score_inclusive, int num_classes, int max_per_class,
+                      int max_total, int32_t* keep, int max_out, int32_t* n_keep, void* stream) {
+    DH_CHECK_ARG(h && dets && keep && n_keep, "dh_nms: NULL argument");
+    DH_CHECK_ARG(batch >= 0 && n_max >= 0 && max_out >= 1, "dh_nms: bad sizes");
+    DH_CHECK_ARG(mode == DH_NMS_AGNOSTIC || mode == DH_NMS_PER_CLASS, "dh_nms: mode %d", mode);
+    DH_CHECK_ARG(row_floats >= (mode == DH_NMS_PER_CLASS ? 6 : 5), "dh_nms: row_floats %d too small", row_floats);
+    if (n_max > kNmsMaxN)
+        return set_error(DH_ERR_CAPACITY, "dh_nms: %d candidates per image > %d; apply a pre-NMS top-k first", n_max, kNmsMaxN);
+    DH_CHECK_ARG(mode != DH_NMS_PER_CLASS || max_per_class <= 0 || (num_classes >= 1 && num_classes <= 8192),
+                 "dh_nms: per-class caps need 1..8192 classes");
+    if (batch == 0) return DH_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_max == 0) {
+        DH_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * batch, st));
+        return DH_OK;
+    }
+    NmsParams p;
+    p.n_max = n_max, p.row_floats = row_floats, p.per_class = (mode == DH_NMS_PER_CLASS), p.inclusive = score_inclusive;
+    p.iou_thr = iou_thr, p.min_score = min_score, p.max_per_class = max_per_class, p.max_total = max_total;
+    p.num_classes = num_classes, p.max_out = max_out;
+    int n_pow2 = 64;
+    while (n_pow2 < n_max) n_pow2 <<= 1;
+    const int words = (n_max + 63) / 64;
+    // scratch: sorted boxes (16 B), classes, order, counts, mask
+    const size_t per_img = static_cast<size_t>(n_max);
+    size_t off_cls = static_cast<size_t>(batch) * per_img * 16;
+    size_t off_ord = off_cls + static_cast<size_t>(batch) * per_img * 4;
+    size_t off_cnt = off_ord + static_cast<size_t>(batch) * per_img * 4;
+    size_t off_mask = (off_cnt + static_cast<size_t>(batch) * 4 + 255) & ~size_t(255);
+    size_t total = off_mask + static_cast<size_t>(batch) * per_img * words * 8;
+    char* sc = static_cast<char*>(scratch(h, total));
+    if (!sc) return DH_ERR_CUDA;
+    float4* sboxes = reinterpret_cast<float4*>(sc);
+    int* scls = reinterpret_cast<int*>(sc + off_cls);
+    int* order = reinterpret_cast<int*>(sc + off_ord);
+    int* ncand = reinterpret_cast<int*>(sc + off_cnt);
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(sc + off_mask);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DH_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsMaxN * 8));
+        attr_done = true;
+    }
+    nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, sboxes, scls, order, ncand);
+    DH_CUDA(cudaGetLastError());
+    // rows whose column blocks are skipped (cb < rb) must read as zero
+    DH_CUDA(cudaMemsetAsync(mask, 0, static_cast<size_t>(batch) * per_img * words * 8, st));
+    dim3 grid(words, words, batch);
+    nms_mask_kernel<<<grid, 64, 0, st>>>(sboxes, scls, ncand, p, words, mask);
+    DH_CUDA(cudaGetLastError());
+    const size_t sweep_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
+    nms_sweep_kernel<<<batch, 32, sweep_smem, st>>>(mask, scls, order, ncand, p, words, keep, n_keep);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 3;
+    return DH_OK;
+}

@@ -3,7 +3,7 @@ CenterNet/tf_centernet_hourglass.py and CenterNet/tf_centernet.py of the referen
 import numpy as np
 import torch
 
-from . import _capi, losses
+from . import _capi, infer, losses
 from ._batch import image_dims, pack_labels
 from ._tensors import as_host, current_device, stream_ptr, to_device
 
@@ -140,3 +140,14 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
         losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1, float(alpha), float(gamma), float(delta),
         out_pi.data_ptr(), out_tot.data_ptr(), status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode_loss")
     return out_pi, out_tot, status
+
+
+# ---- inference ------------------------------------------------------------------------------------
+def prediction_to_corners(xy_pred, stride):
+    """CenterNet/tf_centernet.py:128 / tf_centernet_hourglass.py:355 (same as FCOS): tblr -> corners."""
+    return infer.prediction_to_corners(xy_pred, 0, stride)
+
+
+def prediction_to_corners_s8(xy_pred, box_scales, stride=8):
+    """CenterNet/tf_centernet_resnet_s8.py:210 -- [H, W, S, >=4] -> [H, W, S, 4]."""
+    return infer.prediction_to_corners(xy_pred, 3, stride, scales=box_scales)

@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _capi, losses
+from . import _capi, infer, losses
 from ._batch import image_dims, pack_labels
 from ._tensors import as_host, current_device, stream_ptr, to_device
 
@@ -169,3 +169,72 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
 focal_loss = losses.focal_loss
 smooth_l1_loss = losses.smooth_l1_loss
 iou_loss = losses.iou_loss
+
+
+# ---- inference ------------------------------------------------------------------------------------
+def prediction_to_corners(xy_pred, stride):
+    """FCOS/fcos.py:112 -- tblr map [H, W, >=4] -> pixel corners [H, W, 4] (y1, x1, y2, x2)."""
+    return infer.prediction_to_corners(xy_pred, 0, stride)
+
+
+def prediction_to_corners_center_v1(xy_pred, box_sc, stride):
+    """FCOS/fcos_center_v1.py:125."""
+    return infer.prediction_to_corners(xy_pred, 2, stride, d0=box_sc)
+
+
+def decode_batch(head_outputs, num_classes, img_pad, strides=None, center=False, stream=None):
+    """FCOS/infer_fcos.py:35-57 for a batch: per-level heads [B, Hl, Wl, C+5] -> (boxes [B, N, 4], scores [B, N, C])."""
+    strides = list(DEFAULT_STRIDES if strides is None else strides)
+    dev = current_device()
+    heads = _as_batched(head_outputs, dev)
+    batch = int(heads[0].shape[0])
+    n = sum(h * w for h, w in level_shapes(img_pad, strides))
+    boxes = torch.empty((batch, n, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((batch, n, num_classes), dtype=torch.float32, device=dev)
+    _capi.check(_capi.lib().dh_fcos_decode(
+        _capi.handle(dev.index), _capi.ptr_array([h.data_ptr() for h in heads]), batch, int(img_pad[0]), int(img_pad[1]),
+        len(strides), _capi.int_array(strides), int(num_classes), 1 if center else 0, boxes.data_ptr(), scores.data_ptr(),
+        stream_ptr(stream)), "dh_fcos_decode")
+    return boxes, scores
+
+
+def detect_batch(head_outputs, num_classes, img_pad, center=False, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,
+                 max_total_size=100, pre_nms_topk=1000, strides=None):
+    """Decode -> per-level top-k of (location, class) scores above cls_thresh -> per-class greedy NMS with the
+    combined-NMS caps.  Returns zero-padded (boxes [B, T, 4], scores [B, T], classes [B, T], valid [B]) with
+    T = max_total_size, like tf.image.combined_non_max_suppression.  `pre_nms_topk` bounds the candidates per
+    level (the reference has none; a value >= the number of scores above the threshold reproduces it)."""
+    strides = list(DEFAULT_STRIDES if strides is None else strides)
+    boxes, scores = decode_batch(head_outputs, num_classes, img_pad, strides, center)
+    batch, n, c = (int(v) for v in scores.shape)
+    shapes = level_shapes(img_pad, strides)
+    seg = np.concatenate([[0], np.cumsum([h * w * c for h, w in shapes])])
+    k = int(min(pre_nms_topk, max(int(np.diff(seg).max()), 1)))
+    if k * len(strides) > infer.NMS_MAX_CANDIDATES:
+        raise ValueError("pre_nms_topk * levels exceeds the NMS capacity (%d)" % infer.NMS_MAX_CANDIDATES)
+    flat = scores.reshape(batch, n * c, 1)
+    sel, src = infer.select_topk(flat, seg, k, cls_thresh, score_inclusive=False, score_col=0, with_source=True)
+    src64 = src.clamp(min=0).to(torch.int64)
+    cand = torch.empty((batch, src.shape[1], 6), dtype=torch.float32, device=scores.device)
+    cand[..., :4] = torch.gather(boxes, 1, (src64 // c).unsqueeze(-1).expand(-1, -1, 4))
+    cand[..., 4] = sel[..., 0]
+    cand[..., 5] = (src64 % c).to(torch.float32)
+    keep, n_keep = infer.nms(cand, iou_thresh, mode=infer.NMS_PER_CLASS, min_score=cls_thresh, score_inclusive=False,
+                             num_classes=num_classes, max_per_class=max_detections, max_total=max_total_size,
+                             max_out=max_total_size)
+    t = int(max_total_size)
+    valid = (torch.arange(t, device=keep.device).unsqueeze(0) < n_keep.unsqueeze(1))
+    rows = torch.gather(cand, 1, keep.clamp(min=0).to(torch.int64).unsqueeze(-1).expand(-1, -1, 6))
+    rows = torch.where(valid.unsqueeze(-1), rows, torch.zeros_like(rows))
+    return rows[..., :4].contiguous(), rows[..., 4].contiguous(), rows[..., 5].contiguous(), n_keep
+
+
+def image_detections(image, model, num_classes, center=False, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,
+                     max_total_size=100, head_outputs=None, pre_nms_topk=1000):
+    """FCOS/infer_fcos.py:27 `image_detections`.  `model(image, training=False)` must return the per-level head
+    outputs [1, Hl, Wl, C+5] (or pass them as `head_outputs`)."""
+    heads = head_outputs if head_outputs is not None else model(image, training=False)
+    dev = current_device()
+    hb = _as_batched(heads, dev)
+    pad = (int(hb[0].shape[1]) * DEFAULT_STRIDES[0], int(hb[0].shape[2]) * DEFAULT_STRIDES[0])
+    return detect_batch(hb, num_classes, pad, center, iou_thresh, cls_thresh, max_detections, max_total_size, pre_nms_topk)

@@ -10,7 +10,7 @@ import math
 import numpy as np
 import torch
 
-from . import _capi, losses
+from . import _capi, infer, losses
 from ._batch import image_dims, pack_labels
 from ._tensors import as_host, current_device, stream_ptr, to_device
 
@@ -134,6 +134,54 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, x_pred, anchor
     return out_pi, out_tot, pairs
 
 
+def decode_batch(head_outputs, num_classes, img_pad, anchor_hw=None, strides=None, stream=None):
+    """retinanet_module.py:487-520 for a batch: per-level heads [B, A, Hl, Wl, C+4] -> dets [B, N, 6]
+    (y1, x1, y2, x2, max score, first-argmax label), order level > anchor > row-major cell."""
+    strides = list(STRIDES if strides is None else strides)
+    table = anchor_table() if anchor_hw is None else np.ascontiguousarray(anchor_hw, dtype=np.float32)
+    n_anchors = table.shape[1]
+    dev = current_device()
+    heads = _pack_levels(head_outputs, n_anchors, dev)
+    batch = int(heads[0].shape[0])
+    pad_h, pad_w = int(img_pad[0]), int(img_pad[1])
+    n = sum(n_anchors * int(pad_h / s) * int(pad_w / s) for s in strides)
+    dets = torch.empty((batch, n, 6), dtype=torch.float32, device=dev)
+    table_d = torch.from_numpy(table).to(dev)
+    _capi.check(_capi.lib().dh_retina_decode(
+        _capi.handle(dev.index), _capi.ptr_array([h.data_ptr() for h in heads]), batch, pad_h, pad_w, len(strides),
+        _capi.int_array(strides), n_anchors, table_d.data_ptr(), int(num_classes), dets.data_ptr(), stream_ptr(stream)),
+        "dh_retina_decode")
+    return dets
+
+
+def detect_batch(head_outputs, num_classes, img_pad, iou_thresh=0.5, cls_thresh=0.05, anchor_hw=None, strides=None,
+                 pre_nms_topk=None):
+    """Decode -> `score >= cls_thresh` (-> optional per-level top-k) -> class-agnostic greedy NMS.
+    Returns (dets [B, n, 6] candidate rows, keep int32 [B, n] candidate indices in kept order, n_keep [B])."""
+    strides = list(STRIDES if strides is None else strides)
+    table = anchor_table() if anchor_hw is None else np.ascontiguousarray(anchor_hw, dtype=np.float32)
+    dets = decode_batch(head_outputs, num_classes, img_pad, table, strides)
+    n_anchors = table.shape[1]
+    lens = [n_anchors * int(int(img_pad[0]) / s) * int(int(img_pad[1]) / s) for s in strides]
+    seg = np.concatenate([[0], np.cumsum(lens)])
+    if pre_nms_topk is None:
+        if dets.shape[1] > infer.NMS_MAX_CANDIDATES:  # compact the rows above the threshold, keeping their order
+            k = int(max(lens))
+            cand = infer.select_topk(dets, seg, k, cls_thresh, score_inclusive=True)
+            passing = int((cand[..., 4] >= cls_thresh).sum(dim=1).max().item())
+            if passing > infer.NMS_MAX_CANDIDATES:
+                raise ValueError("%d candidates above the score threshold exceed the NMS capacity of %d; pass pre_nms_topk"
+                                 % (passing, infer.NMS_MAX_CANDIDATES))
+            order = torch.argsort((cand[..., 4] < cls_thresh).to(torch.int8), dim=1, stable=True)[:, :max(passing, 1)]
+            cand = torch.gather(cand, 1, order.unsqueeze(-1).expand(-1, -1, 6)).contiguous()
+        else:
+            cand = dets
+    else:
+        cand = infer.select_topk(dets, seg, int(pre_nms_topk), cls_thresh, score_inclusive=True)
+    keep, n_keep = infer.nms(cand, iou_thresh, mode=infer.NMS_AGNOSTIC, min_score=cls_thresh, score_inclusive=True)
+    return cand, keep, n_keep
+
+
 class RetinaNetHead:
     """The reference `RetinaNet` class (RetinaNet/retinanet_module.py:162-569) without its Keras model."""
 
@@ -171,3 +219,32 @@ class RetinaNetHead:
         head outputs ([1, Hl, Wl, C+4]), `x_label` what `format_data` returned.  -> (cls_loss, reg_loss)."""
         _, tot = loss_batch(x_label, x_pred, self.n_anchors)
         return tot[0], tot[1]
+
+    def prediction_to_corners(self, xy_pred, anchor_dim, stride):
+        """retinanet_module.py:428 -- [H, W, >=4] regressions -> pixel corners for one anchor shape."""
+        return infer.prediction_to_corners(xy_pred, 1, stride, d0=float(anchor_dim[0]), d1=float(anchor_dim[1]))
+
+    def cpu_nms(self, dets, base_thr):
+        """retinanet_module.py:453 -- class-agnostic greedy NMS of `[n, >=5]` rows (c0, c1, c2, c3, score, ...).
+        Returns the kept row indices (host int64 array, score-descending) like the reference."""
+        d = to_device(dets, torch.float32, current_device())
+        if d.shape[0] == 0:
+            return np.zeros((0,), dtype=np.int64)
+        keep, n_keep = infer.nms(d.unsqueeze(0), base_thr)
+        return keep[0, :int(n_keep[0])].to(torch.int64).cpu().numpy()
+
+    def image_detections(self, image=None, iou_thresh=0.5, cls_thresh=0.05, head_outputs=None, pre_nms_topk=None):
+        """retinanet_module.py:483 -- `[k, 6]` rows (y1, x1, y2, x2, score, label) in kept order for ONE image.
+        `self.model(image, training=False)` must yield `out[level][anchor]` heads [1, Hl, Wl, C+4] (or pass
+        `head_outputs`).  Returns None when there are no anchors at all, as the reference does."""
+        heads = head_outputs if head_outputs is not None else self.model(image, training=False)
+        packed = _pack_levels(heads, self.n_anchors, current_device())
+        pad = (int(packed[0].shape[2]) * self.strides[0], int(packed[0].shape[3]) * self.strides[0])
+        cand, keep, n_keep = detect_batch(packed, self.n_class, pad, iou_thresh, cls_thresh, self.anchor_table, self.strides,
+                                          pre_nms_topk)
+        if cand.shape[1] == 0:
+            return None
+        k = int(n_keep[0])
+        if k == 0:  # nothing above the threshold: the reference returns the (empty) thresholded array
+            return cand[0, :0]
+        return cand[0].index_select(0, keep[0, :k].to(torch.int64))

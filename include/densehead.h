@@ -174,6 +174,59 @@ int dh_centernet_encode_loss(dh_handle_t h,
                              int reg_mode /*mode 2 only*/, float alpha, float gamma, float delta,
                              float* out_per_image, float* out_total, int32_t* status, void* stream);
 
+/* ---- inference: decode, candidate selection, NMS ------------------------------------------------- */
+
+/* prediction_to_corners: head regression values -> pixel corner boxes (y1, x1, y2, x2), float32.
+ * pred holds rows of ch_in floats (the first 4 are used) laid out [B, H, W, sub]; out is [B, H, W, sub, 4].
+ *   mode 0  FCOS tblr, cell centres at i+.5, times stride         (FCOS/fcos.py:112-134; same in
+ *           fcos_center.py:125-147, tf_centernet.py:128-150, tf_centernet_hourglass.py:355-377)
+ *   mode 1  RetinaNet: centre = i*stride - p*anchor, size = p*anchor; d0, d1 = anchor (h, w)
+ *           (RetinaNet/retinanet_module.py:428-451)
+ *   mode 2  fcos_center_v1: centre = (i + p)*stride, size = p*box_sc; d0 = box_sc (FCOS/fcos_center_v1.py:125-147)
+ *   mode 3  CenterNet s8: like mode 2 with one scale per `sub` index (CenterNet/tf_centernet_resnet_s8.py:210-241) */
+int dh_prediction_to_corners(dh_handle_t h, const float* pred /*[dev]*/, int batch, int height, int width, int sub,
+                             int ch_in, int mode, float stride, float d0, float d1,
+                             const float* scales /*[host] [sub], mode 3*/, float* out /*[dev]*/, void* stream);
+
+/* FCOS decode front end (FCOS/infer_fcos.py:35-57): per-level heads [B,Hl,Wl,C+5] -> boxes [B,N,4] and
+ * scores [B,N,C] = sigmoid(class) (times sigmoid(centerness) when center != 0), levels concatenated. */
+int dh_fcos_decode(dh_handle_t h, const float* const* pred_levels /*[host] n_levels [dev] ptrs*/, int batch,
+                   int pad_h, int pad_w, int n_levels, const int32_t* strides /*[host]*/, int num_classes, int center,
+                   float* boxes /*[dev] [B,N,4]*/, float* scores /*[dev] [B,N,C]*/, void* stream);
+
+/* RetinaNet decode front end (RetinaNet/retinanet_module.py:487-520): per-level heads [B,A,Hl,Wl,C+4] ->
+ * dets [B,N,6] = (y1, x1, y2, x2, max_c sigmoid, first argmax), order level > anchor > row-major cell. */
+int dh_retina_decode(dh_handle_t h, const float* const* pred_levels /*[host] n_levels [dev] ptrs*/, int batch,
+                     int pad_h, int pad_w, int n_levels, const int32_t* strides /*[host]*/, int n_anchors,
+                     const float* anchor_hw /*[dev] [n_levels,n_anchors,2]*/, int num_classes,
+                     float* dets /*[dev] [B,N,6]*/, void* stream);
+
+/* Pre-NMS candidate selection: for every image and every segment [seg_off[s], seg_off[s+1]) of its
+ * n_total rows (a segment = a pyramid level), keep the rows whose score (column score_col) passes min_score and is
+ * among the k highest of the segment (exact; ties go to the lower index), in index order.
+ * out is [B, n_seg*k, row_floats]; unused slots get score = -inf.  out_src (optional) [B, n_seg*k]: source row.
+ * The reference has no top-k; with k >= segment length this is its plain threshold. */
+int dh_select_topk(dh_handle_t h, const float* dets /*[dev] [B,n_total,row_floats]*/, int batch, long long n_total,
+                   int row_floats, int score_col, const int32_t* seg_off /*[dev] [n_seg+1]*/, int n_seg, int k, float min_score,
+                   int score_inclusive, float* out /*[dev]*/, int32_t* out_src /*[dev] or NULL*/, void* stream);
+
+/* Greedy NMS.  dets is [B, n_max, row_floats] float32 rows (c0, c1, c2, c3, score[, class]); n_valid (optional)
+ * [B] limits the rows per image; rows failing the score test (>= min_score when score_inclusive, else >) are dropped.
+ *   DH_NMS_AGNOSTIC   RetinaNet.cpu_nms (RetinaNet/retinanet_module.py:453-481): class-agnostic,
+ *                     ovr = inter / (area_i + area_j - inter + 1e-8), a box survives while ovr <= iou_thr.
+ *   DH_NMS_PER_CLASS  the per-class greedy NMS with caps that FCOS/infer_fcos.py:58-61 gets from TensorFlow's
+ *                     combined_non_max_suppression: same-class boxes with IoU > iou_thr are suppressed, at most
+ *                     max_per_class kept per class and max_total overall (0 = no cap).  Parity unpinned (the op's
+ *                     source is not part of the reference); restated in oracle/dense_head_ref.py.
+ * keep is [B, max_out] original row indices in descending score order (ties: lower index first, where the
+ * reference's unstable argsort leaves the order unspecified); n_keep is [B].  n_max <= 16384. */
+#define DH_NMS_AGNOSTIC 0
+#define DH_NMS_PER_CLASS 1
+int dh_nms(dh_handle_t h, const float* dets /*[dev]*/, const int32_t* n_valid /*[dev] [B] or NULL*/, int batch,
+           int n_max, int row_floats, int mode, float iou_thr, float min_score, int score_inclusive,
+           int num_classes, int max_per_class, int max_total,
+           int32_t* keep /*[dev] [B,max_out]*/, int max_out, int32_t* n_keep /*[dev] [B]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -754,3 +754,47 @@ def fcos_image_detections(head_outputs, num_classes, center=False, iou_thresh=0.
     """FCOS/infer_fcos.py:27-62 with the third-party NMS replaced by `combined_nms`."""
     boxes, scores = fcos_decode_scores(head_outputs, num_classes, strides, center)
     return combined_nms(boxes, scores, max_detections, max_total_size, iou_thresh, cls_thresh)
+
+
+# --------------------------------------------------------------------------------------
+# pre-NMS top-k per pyramid level (an extension: the reference has none, SURVEY.md section 0)
+# --------------------------------------------------------------------------------------
+def select_topk(scores, seg_offsets, k, min_score, inclusive=True):
+    """Indices (ascending, per segment, concatenated) of the rows whose score passes `min_score` and is among
+    the k highest of its segment; ties go to the lower index.  With k >= segment length this is the
+    reference's plain threshold."""
+    s = np.asarray(scores, dtype=np.float32)
+    out = []
+    for a, b in zip(seg_offsets[:-1], seg_offsets[1:]):
+        seg = s[a:b]
+        ok = np.nonzero(seg >= F(min_score) if inclusive else seg > F(min_score))[0]
+        if len(ok) > k:
+            order = ok[np.argsort(-seg[ok], kind="stable")][:k]
+            ok = np.sort(order)
+        out.append(ok + a)
+    return out
+
+
+def retina_detect_from_dets(dets, seg_offsets, iou_thresh=0.5, cls_thresh=0.05, pre_nms_topk=None):
+    """`dets` [N, 6] as produced by the decode front end -> (candidate rows, kept candidate indices)."""
+    d = _f32(dets)
+    k = pre_nms_topk if pre_nms_topk is not None else len(d)
+    sel = np.concatenate(select_topk(d[:, 4], seg_offsets, k, cls_thresh, True)) if len(d) else np.zeros(0, np.int64)
+    cand = d[sel]
+    keep = cpu_nms(cand, iou_thresh) if len(cand) else np.zeros(0, np.int64)
+    return cand, keep, sel
+
+
+def fcos_detect_from_scores(boxes, scores, seg_offsets, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,
+                            max_total_size=100, pre_nms_topk=None):
+    """boxes [N, 4], scores [N, C] (decode front end); per-level top-k over the (location, class) scores,
+    then `combined_nms`.  seg_offsets are in units of flattened (location*C + class) entries."""
+    b, s = _f32(boxes), _f32(scores)
+    n, c = s.shape
+    flat = s.reshape(-1)
+    if pre_nms_topk is not None:
+        sel = np.concatenate(select_topk(flat, seg_offsets, pre_nms_topk, cls_thresh, False))
+        masked = np.zeros_like(flat)
+        masked[sel] = flat[sel]
+        s = masked.reshape(n, c)
+    return combined_nms(b, s, max_detections, max_total_size, iou_thresh, cls_thresh)
