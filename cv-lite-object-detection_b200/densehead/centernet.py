@@ -151,3 +151,39 @@ def prediction_to_corners(xy_pred, stride):
 def prediction_to_corners_s8(xy_pred, box_scales, stride=8):
     """CenterNet/tf_centernet_resnet_s8.py:210 -- [H, W, S, >=4] -> [H, W, S, 4]."""
     return infer.prediction_to_corners(xy_pred, 3, stride, scales=box_scales)
+
+
+def bboxes_iou(boxes1, boxes2):
+    """CenterNet/tf_centernet_resnet_s8.py:22 -- float64 IoU of corner boxes ([..., 4]), floored at float32 eps.
+    Shapes must match or one side must be a single box."""
+    dev = current_device()
+    b1 = to_device(np.asarray(as_host(boxes1, np.float64)), torch.float64, dev).reshape(-1, 4).contiguous()
+    b2 = to_device(np.asarray(as_host(boxes2, np.float64)), torch.float64, dev).reshape(-1, 4).contiguous()
+    n = max(int(b1.shape[0]), int(b2.shape[0])) if min(int(b1.shape[0]), int(b2.shape[0])) else 0
+    out = torch.empty((n,), dtype=torch.float64, device=dev)
+    _capi.check(_capi.lib().dh_bboxes_iou(_capi.handle(dev.index), b1.data_ptr(), int(b1.shape[0]), b2.data_ptr(),
+                                          int(b2.shape[0]), out.data_ptr(), stream_ptr(None)), "dh_bboxes_iou")
+    return out
+
+
+def nms(bboxes, iou_threshold, sigma=0.3, method="nms"):
+    """CenterNet/tf_centernet_resnet_s8.py:44 `nms`: rows (xmin, ymin, w, h, score, class) -> list of kept rows
+    (x1, y1, x2, y2, score, class) as host float64 arrays, classes visited in ascending order.  Unlike the
+    reference the input array is left untouched."""
+    assert method in ["nms", "soft-nms"]
+    dev = current_device()
+    host = as_host(bboxes, np.float64).reshape(-1, 6)
+    n = int(host.shape[0])
+    if n == 0:
+        return []
+    classes = np.unique(host[:, 5])
+    rows_d = to_device(host, torch.float64, dev)
+    cls_d = to_device(classes, torch.float64, dev)
+    out = torch.empty((n, 6), dtype=torch.float64, device=dev)
+    src = torch.empty((n,), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _capi.check(_capi.lib().dh_centernet_nms(
+        _capi.handle(dev.index), rows_d.data_ptr(), n, cls_d.data_ptr(), int(len(classes)), float(iou_threshold), float(sigma),
+        1 if method == "soft-nms" else 0, out.data_ptr(), src.data_ptr(), cnt.data_ptr(), stream_ptr(None)), "dh_centernet_nms")
+    k = int(cnt[0])
+    return list(out[:k].cpu().numpy())

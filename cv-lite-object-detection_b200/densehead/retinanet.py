@@ -134,6 +134,17 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, x_pred, anchor
     return out_pi, out_tot, pairs
 
 
+def compute_iou(boxes1, boxes2):
+    """RetinaNet/utils.py:42 -- pairwise float32 IoU matrix [N, M] of centre-size boxes (on the device)."""
+    dev = current_device()
+    b1 = to_device(boxes1, torch.float32, dev).reshape(-1, 4).contiguous()
+    b2 = to_device(boxes2, torch.float32, dev).reshape(-1, 4).contiguous()
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=dev)
+    _capi.check(_capi.lib().dh_compute_iou(_capi.handle(dev.index), b1.data_ptr(), int(b1.shape[0]), b2.data_ptr(),
+                                           int(b2.shape[0]), out.data_ptr(), stream_ptr(None)), "dh_compute_iou")
+    return out
+
+
 def decode_batch(head_outputs, num_classes, img_pad, anchor_hw=None, strides=None, stream=None):
     """retinanet_module.py:487-520 for a batch: per-level heads [B, A, Hl, Wl, C+4] -> dets [B, N, 6]
     (y1, x1, y2, x2, max score, first-argmax label), order level > anchor > row-major cell."""

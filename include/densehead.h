@@ -227,6 +227,25 @@ int dh_nms(dh_handle_t h, const float* dets /*[dev]*/, const int32_t* n_valid /*
            int num_classes, int max_per_class, int max_total,
            int32_t* keep /*[dev] [B,max_out]*/, int max_out, int32_t* n_keep /*[dev] [B]*/, void* stream);
 
+/* Pairwise IoU of centre-size boxes (c0, c1, size0, size1), float32: compute_iou of RetinaNet/utils.py:42-83
+ * (union floored at 1e-8, result clipped to [0, 1]).  out is [n, m]. */
+int dh_compute_iou(dh_handle_t h, const float* boxes1 /*[dev] [n,4]*/, int n, const float* boxes2 /*[dev] [m,4]*/, int m,
+                   float* out /*[dev] [n,m]*/, void* stream);
+
+/* float64 IoU of corner boxes floored at float32 eps: bboxes_iou of CenterNet/tf_centernet_resnet_s8.py:22-42
+ * (also tf_centernet_hourglass.py).  n1 and n2 must be equal, or one of them 1 (broadcast); out is [max(n1,n2)]. */
+int dh_bboxes_iou(dh_handle_t h, const double* boxes1 /*[dev] [n1,4]*/, int n1, const double* boxes2 /*[dev] [n2,4]*/,
+                  int n2, double* out /*[dev]*/, void* stream);
+
+/* CenterNet per-class (soft-)NMS: nms of CenterNet/tf_centernet_resnet_s8.py:44-85.  rows [n,6] float64
+ * (xmin, ymin, w, h, score, class); classes [n_classes] float64 = the distinct class values in the order to
+ * visit them (the reference iterates a Python set; ascending order is the canonical choice).  Kept rows come
+ * back as (x1, y1, x2, y2, score, class) in out_rows [n,6] with their source row in out_src [n]; n_out [1].
+ * soft != 0 selects method='soft-nms' with `sigma`.  The input is not modified (the reference mutates it). */
+int dh_centernet_nms(dh_handle_t h, const double* rows /*[dev]*/, int n, const double* classes /*[dev]*/, int n_classes,
+                     double iou_threshold, double sigma, int soft, double* out_rows /*[dev] [n,6]*/,
+                     int32_t* out_src /*[dev] [n]*/, int32_t* n_out /*[dev] [1]*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

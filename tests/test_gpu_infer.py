@@ -160,3 +160,37 @@ def test_c4_shaped_detection_pipelines():
         assert int(nv[b]) == wv
         assert np.array_equal(ob[b].cpu().numpy(), wb) and np.array_equal(os_[b].cpu().numpy(), ws)
         assert np.array_equal(oc[b].cpu().numpy(), wc)
+
+
+def test_compute_iou_and_bboxes_iou(golden):
+    dh = _dh()
+    k = golden("kat")
+    assert np.array_equal(dh.retinanet.compute_iou(k["iou_b1"], k["iou_b2"]).cpu().numpy(), k["iou"])
+    rng = np.random.default_rng(2)
+    b1 = rng.uniform(0, 300, size=(37, 4)).astype(np.float32); b2 = rng.uniform(0, 300, size=(211, 4)).astype(np.float32)
+    assert np.array_equal(dh.retinanet.compute_iou(b1, b2).cpu().numpy(), O.compute_iou(b1, b2))
+    c1 = np.sort(rng.uniform(0, 100, size=(50, 2, 2)), axis=1).reshape(50, 4)[:, [0, 1, 2, 3]]
+    c2 = np.sort(rng.uniform(0, 100, size=(50, 2, 2)), axis=1).reshape(50, 4)
+    assert np.allclose(dh.centernet.bboxes_iou(c1, c2).cpu().numpy(), O.bboxes_iou(c1, c2), rtol=1e-14, atol=0)
+    assert np.allclose(dh.centernet.bboxes_iou(c1[:1], c2).cpu().numpy(), O.bboxes_iou(c1[:1], c2), rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("n", [64, 700, 3000])
+def test_centernet_nms_golden(golden, n):
+    dh = _dh()
+    z = golden("decode_nms")
+    k = golden("kat")
+    rows = dh.centernet.nms(k["cnms_in"].copy(), .5)
+    assert np.array_equal(np.array(rows), k["cnms_hard"][np.argsort(k["cnms_hard"][:, 5], kind="stable")])
+    dets = synth.nms_candidates(n, 640, synth.seed_for(4, 60) + n)
+    bb = dets.astype(np.float64)
+    bb = np.stack([bb[:, 1], bb[:, 0], bb[:, 3] - bb[:, 1], bb[:, 2] - bb[:, 0], np.floor(bb[:, 4] * 100), bb[:, 5]], axis=1)
+    keep_in = bb.copy()
+    for method in ("nms", "soft-nms"):
+        got = np.array(dh.centernet.nms(bb, 0.5, method=method)).reshape(-1, 6)
+        want = z["cnms_%d_%s" % (n, method)]
+        assert got.shape == want.shape, method
+        assert np.allclose(got, want, rtol=1e-11, atol=0), method
+        assert np.array_equal(got[:, :4], want[:, :4]) and np.array_equal(got[:, 5], want[:, 5])
+    assert np.array_equal(bb, keep_in)   # input untouched
+    assert dh.centernet.nms(np.zeros((0, 6)), 0.5) == []
