@@ -1,0 +1,90 @@
+"""Live cross-check of the CPU oracle against the reference's own source executed under the TF stub.
+Needs /root/reference (the build container); skipped on the GPU box.  The frozen outputs of the same
+reference run are what tests/test_oracle_golden.py checks everywhere."""
+import numpy as np
+import pytest
+
+from oracle import dense_head_ref as O
+from oracle import ref_loader as R
+from oracle import synth
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="reference tree not present")
+SCALES = [32, 64, 128, 256, 512]
+
+
+def _eq(a, b):
+    return np.array_equal(np.asarray(a, np.float32), np.asarray(b, np.float64).astype(np.float32))
+
+
+@pytest.mark.parametrize("trial", range(8))
+def test_fcos_family_random(trial):
+    tf = R.tf()
+    fcos, fc, fv1 = R.load("FCOS", "fcos"), R.load("FCOS", "fcos_center"), R.load("FCOS", "fcos_center_v1")
+    side = [512, 384, 640][trial % 3]
+    boxes, nbox = synth.make_boxes(1, side, 20, 20, 4.0, 0.9 * side, 7000 + trial)
+    g = boxes[0, :nbox[0]]
+    dim = [side - 64.0 * (trial % 2), float(side)]
+    pad = [side, side + 128 * (trial % 2)]
+    lab, img = tf.constant(g), tf.cast(dim, tf.float32)
+    for ref_fn, ora_fn, kw in ((fcos.format_data, O.fcos_format_data, {}), (fc.format_data, O.fcos_center_format_data, {}),
+                               (fc.format_data, O.fcos_center_format_data, {"center_only": True}),
+                               (fv1.format_data, O.fcos_center_v1_format_data, {})):
+        ro, rn = ref_fn(lab, img, 20, img_pad=pad, **kw)
+        oo, on = ora_fn(g, dim, 20, img_pad=pad, **kw)
+        assert rn == on and all(_eq(a, b) for a, b in zip(oo, ro))
+
+
+@pytest.mark.parametrize("trial", range(3))
+def test_retina_random(trial):
+    tf = R.tf()
+    rn_ = R.retinanet(80)
+    side = [256, 384, 320][trial]
+    boxes, nbox = synth.make_boxes(1, side, 15, 80, 8.0, 0.6 * side, 7100 + trial)
+    g = boxes[0, :nbox[0]]
+    ro, rn = rn_.format_data(tf.constant(g), tf.cast([side, side], tf.float32), iou_thresh=[0.5, 0.4, 0.6][trial])
+    oo, on = O.retina_format_data(g, [side, side], 80, iou_thresh=[0.5, 0.4, 0.6][trial])
+    assert rn == on
+    for l in range(5):
+        for a in range(9):
+            assert _eq(oo[l][a], ro[l][a])
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_centernet_random(trial):
+    tf = R.tf()
+    s8, hg, cn = (R.load("CenterNet", m) for m in ("tf_centernet_resnet_s8", "tf_centernet_hourglass", "tf_centernet"))
+    stride = [8, 4, 16][trial % 3]
+    boxes, nbox = synth.make_boxes(1, 512, 60, 3, 8.0, 400, 7200 + trial)
+    g = boxes[0, :nbox[0]]
+    dim, pad = ([512, 512], [512, 512]) if trial < 3 else ([448, 448], [512, 512])
+    assert _eq(O.centernet_s8_format_data(g, SCALES, dim, 3, img_pad=pad, stride=stride)[0],
+               s8.format_data(tf.constant(g), SCALES, dim, 3, img_pad=pad, stride=stride)[0])
+    assert _eq(O.centernet_hourglass_format_data(g, dim, 3, img_pad=pad, stride=stride)[0],
+               hg.format_data(tf.constant(g), dim, 3, img_pad=pad, stride=stride)[0])
+    assert _eq(O.centernet_format_data(g, dim, 3, img_pad=pad, stride=stride),
+               cn.format_data(tf.constant(g), dim, 3, img_pad=pad, stride=stride))
+
+
+def test_losses_and_nms_random():
+    tf = R.tf()
+    fcos = R.load("FCOS", "fcos")
+    rn_ = R.retinanet(80)
+    s8 = R.load("CenterNet", "tf_centernet_resnet_s8")
+    boxes, nbox = synth.make_boxes(1, 512, 20, 20, 6.0, 400, 7300)
+    g = boxes[0, :nbox[0]]
+    tg, _ = fcos.format_data(tf.constant(g), tf.cast([512, 512], tf.float32), 20)
+    pred = synth.fcos_predictions(1, 512, 20, 7300)
+    for reg_type in ("l1", "iou"):
+        r = fcos.model_loss(tg, [tf.constant(p) for p in pred], None, reg_type=reg_type)
+        o = O.fcos_model_loss([x.astype(np.float32) for x in tg], [p[0] for p in pred], reg_type=reg_type)
+        for a, b in zip(o, r):
+            b = float(np.asarray(b.numpy() if hasattr(b, "numpy") else b))
+            assert abs(float(a) - b) <= 1e-5 * max(1.0, abs(b))
+    d = synth.nms_candidates(800, 640, 7301)
+    assert np.array_equal(rn_.cpu_nms(d, 0.5), O.cpu_nms(d, 0.5))
+    bb = d.astype(np.float64)
+    bb = np.stack([bb[:, 1], bb[:, 0], bb[:, 3] - bb[:, 1], bb[:, 2] - bb[:, 0], np.floor(bb[:, 4] * 100), bb[:, 5]], axis=1)
+    for method in ("nms", "soft-nms"):
+        rr = np.array(s8.nms(bb.copy(), 0.5, method=method)).reshape(-1, 6)
+        oo, _ = O.centernet_nms(bb, 0.5, method=method)
+        assert np.allclose(rr[np.argsort(rr[:, 5], kind="stable")], oo, rtol=1e-12)
