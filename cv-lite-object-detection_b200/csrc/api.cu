@@ -76,6 +76,7 @@ int dh_create(dh_handle_t* out, int device) {
     h->use_tma_store = 1;
     h->tile_bytes = 49152;
     h->ctas_per_sm = 4;
+    h->fused_loss_kernel = 0;
     h->launches = 0;
     h->scratch = nullptr;
     h->scratch_bytes = 0;
@@ -111,6 +112,10 @@ int dh_set_option(dh_handle_t h, int option, int value) {
         case DH_OPT_CTAS_PER_SM:
             DH_CHECK_ARG(value >= 1 && value <= 8, "DH_OPT_CTAS_PER_SM must be in [1, 8]");
             h->ctas_per_sm = value;
+            return DH_OK;
+        case DH_OPT_FUSED_LOSS_KERNEL:
+            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_FUSED_LOSS_KERNEL must be 0 or 1");
+            h->fused_loss_kernel = value;
             return DH_OK;
         case DH_OPT_PHASE_TIMING: {
             dh::DeviceGuard g(h->device);

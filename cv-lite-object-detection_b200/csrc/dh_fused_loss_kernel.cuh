@@ -1,0 +1,362 @@
+// Fused encode + loss, "stream + correct" formulation (the C5 step: format_data -> model_loss of one
+// training step, FCOS/train_fcos.py:142-154, RetinaNet/train_retinanet_coco.py:198-208, with the targets
+// never written anywhere).
+//
+// More than 99 % of the rows of a dense-head target map are all-zero, and for an all-zero row the loss needs
+// no label at all: sum_c (1-a) * sigmoid(x_c)^g * softplus(x_c) over the class logits.  So the kernel splits
+// the work of a 32-row warp tile in two:
+//   stream   every element of the tile is read once from HBM (128-bit loads, U independent loads in flight
+//            per lane) and accumulated as if its label were zero -- a tight loop with no shared-memory
+//            traffic, no row bookkeeping and no block barrier; two of every four reciprocals run as a
+//            quadratic seed + 2 Newton steps on the FMA pipe so that the MUFU pipe (ex2, lg2, rcp) is not
+//            the limiter (tools/focal_stream_probe.cu: 5.65 TB/s against 5.15 TB/s with 3 MUFU per element);
+//   correct  the encoder policy matches the tile's rows against the GT boxes that can touch it (per-warp
+//            candidate list, ballot-compacted, no block barrier).  A matched row is kept in registers as
+//            <= 5 regression values + a class bitmask (CompactSink); its owner lane re-reads that one row
+//            (L2-resident) and adds  term(y, x) - term(0, x)  for the channels whose label is not zero, plus
+//            the box-regression loss.  Rows are matched by the same policy code as the encoders, so the
+//            target semantics cannot drift from dh_*_encode.
+// Warps of a CTA never synchronise inside a chunk; partial sums stay in registers for the whole chunk and the
+// per-chunk partials are reduced in a fixed order by loss_finalize_images (deterministic results).
+#pragma once
+#include "dh_loss_kernel.cuh"
+
+namespace dh {
+
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 1/w for w in [1, 2] on the FMA pipe: minimax quadratic seed (rel. error 1.0e-2) + two Newton steps (-> 1e-8)
+__device__ __forceinline__ float rcp_unit_newton(float w) {
+    float r = fmaf(fmaf(0.32323232f, w, -1.45454545f), w, 2.12121212f);
+    float t = fmaf(-w, r, 1.0f);
+    r = fmaf(r, t, r);
+    t = fmaf(-w, r, 1.0f);
+    return fmaf(r, t, r);
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// label == 0 element: acc += sigmoid(x)^gamma * softplus(x) / ln 2   (the caller scales by (1 - alpha) * ln 2)
+template <bool kGamma2, bool kNewton>
+__device__ __forceinline__ void stream_term(float x, float gamma, float& acc) {
+    const float u = x * kLog2e;
+    const float e = ex2_fast(-fabsf(u));  // exp(-|x|)
+    const float w = 1.0f + e;
+    const float inv = kNewton ? rcp_unit_newton(w) : rcp_fast(w);
+    const float lg = lg2_fast(w);                    // log2(1 + exp(-|x|))
+    const float s = (x < 0.f ? e : 1.0f) * inv;      // sigmoid(x)
+    const float pw = kGamma2 ? s * s : ex2_fast(gamma * lg2_fast(s));
+    acc = fmaf(pw, lg + fmaxf(u, 0.f), acc);         // softplus(x) / ln 2 = lg + max(x, 0) * log2(e)
+}
+// smooth-L1(0, sigmoid(x)): the centerness term of an all-zero row (FCOS/fcos.py:483-486)
+__device__ __forceinline__ float cen_l1_zero(float x, float delta) {
+    const float s = sigmoid_f(x);
+    return s < delta ? 0.5f * s * s : s;
+}
+
+struct FusedSmemLayout {
+    int rec_off, raw_off, cand_off, misc_off, args_off, total;
+};
+template <class P>
+__host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
+    FusedSmemLayout l;
+    l.rec_off = 0;
+    l.raw_off = (static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127;
+    l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
+    l.misc_off = l.cand_off + (DH_THREADS / 32) * box_cap * 2;  // one candidate list per warp
+    l.args_off = l.misc_off + 256;
+    l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
+    return l;
+}
+
+struct StreamAcc {
+    float c0, c1, c2, c3;  // class focal, log2 units (4 chains for ILP)
+    float cen;             // centerness of all-zero rows, natural units
+};
+
+// ---- the label-free pass over one warp tile: rows [0, nrows) x ch floats starting at `p` --------------------
+// Lane l takes items l, l + 32, l + 64, ... (an item = one 128-bit load in the vector pass, one float in the
+// scalar pass); `c` tracks the item's position inside its row incrementally (no division in the loop).
+template <bool kGamma2>
+__device__ __forceinline__ void stream_vec_item(const float4& x, int c4, float gamma, StreamAcc& a) {
+    if (c4 != 0) {  // float4 0 of a row = the 4 regression channels
+        stream_term<kGamma2, false>(x.x, gamma, a.c0);
+        stream_term<kGamma2, true>(x.y, gamma, a.c1);
+        stream_term<kGamma2, false>(x.z, gamma, a.c2);
+        stream_term<kGamma2, true>(x.w, gamma, a.c3);
+    }
+}
+template <bool kGamma2, int U>
+__device__ __forceinline__ void stream_vec(const float* __restrict__ p, int nrows, int vpr, int c4, int step, int lane,
+                                           float gamma, StreamAcc& a) {
+    const float4* __restrict__ base = reinterpret_cast<const float4*>(p) + lane;
+    const int n_mine = (nrows * vpr - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
+    int k = 0;
+#pragma unroll 1
+    for (; k + U <= n_mine; k += U) {  // U independent loads in flight, no predicates
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = __ldcs(base + 32 * (k + u));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            stream_vec_item<kGamma2>(x[u], c4, gamma, a);
+            c4 += step;
+            if (c4 >= vpr) c4 -= vpr;
+        }
+    }
+#pragma unroll 1
+    for (; k < n_mine; ++k) {
+        const float4 x = __ldcs(base + 32 * k);
+        stream_vec_item<kGamma2>(x, c4, gamma, a);
+        c4 += step;
+        if (c4 >= vpr) c4 -= vpr;
+    }
+}
+
+template <bool kGamma2, bool kNewton>
+__device__ __forceinline__ void stream_scalar_item(float x, int c, const LossSpec& sp, float& cls_acc, StreamAcc& a) {
+    if (c < sp.reg_ch) return;
+    if (c == sp.reg_ch && sp.cen_mode != 0) {
+        if (sp.cen_mode == 1) a.cen += cen_l1_zero(x, sp.delta);
+        else if (sp.cen_mode == 2) a.cen += focal_term(0.f, x, sp.alpha, sp.gamma);
+    } else {
+        stream_term<kGamma2, kNewton>(x, sp.gamma, cls_acc);
+    }
+}
+template <bool kGamma2, int U>
+__device__ __forceinline__ void stream_scalar(const float* __restrict__ p, int nrows, int ch, int c, int step, int lane,
+                                              const LossSpec& sp, StreamAcc& a) {
+    const float* __restrict__ base = p + lane;
+    const int n_mine = (nrows * ch - lane + 31) >> 5;
+    int k = 0;
+#pragma unroll 1
+    for (; k + U <= n_mine; k += U) {
+        float x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = __ldcs(base + 32 * (k + u));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u & 1) stream_scalar_item<kGamma2, true>(x[u], c, sp, a.c1, a);
+            else stream_scalar_item<kGamma2, false>(x[u], c, sp, a.c0, a);
+            c += step;
+            if (c >= ch) c -= ch;
+        }
+    }
+#pragma unroll 1
+    for (; k < n_mine; ++k) {
+        stream_scalar_item<kGamma2, false>(__ldcs(base + 32 * k), c, sp, a.c2, a);
+        c += step;
+        if (c >= ch) c -= ch;
+    }
+}
+
+// The owner lane of a matched row: box-regression loss + (term(y, x) - term(0, x)) for the labelled channels.
+// Rare (well under 1 % of the rows), so it is kept out of line: its registers do not weigh on the streaming loop.
+__device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __restrict__ prow, CompactSink sink, float gy,
+                                            float gx) {
+    const int cls0 = sp.reg_ch + (sp.cen_mode != 0 ? 1 : 0);
+    LossAcc acc = {0.f, 0.f, 0.f, 1};
+    float x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = prow[k];
+    if (sp.reg_mode == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc.reg += smooth_l1_term(sink.r[k], x[k], sp.delta);
+    } else {
+        acc.reg += iou_loss_term(sink.r, x, gy, gx);
+    }
+    if (sp.cen_mode == 1) {
+        const float s = sigmoid_f(prow[4]);
+        acc.cen += smooth_l1_term(sink.r[4], s, sp.delta) - smooth_l1_term(0.f, s, sp.delta);
+    } else if (sp.cen_mode == 2) {
+        const float xc = prow[4];
+        acc.cen += focal_term(sink.r[4], xc, sp.alpha, sp.gamma) - focal_term(0.f, xc, sp.alpha, sp.gamma);
+    }
+#pragma unroll 1
+    for (int wd = 0; wd < kCompactClassWords; ++wd) {
+        uint32_t m = sink.m[wd];
+#pragma unroll 1
+        while (m) {
+            const int c = __ffs(m) - 1 + 32 * wd;
+            m &= m - 1;
+            const float xc = prow[cls0 + c];
+            acc.cls += focal_term(1.0f, xc, sp.alpha, sp.gamma) - focal_term(0.f, xc, sp.alpha, sp.gamma);
+        }
+    }
+    return acc;
+}
+
+// This warp's slice of tile `cur`: rows [r0, r0 + nrows) of map ti.m, or nrows <= 0 when the tile has fewer rows.
+template <class P>
+__device__ __forceinline__ const float* warp_tile(const LossArgs<P>& a, const TileCursor& cur, int img, int warp, TileInfo& ti) {
+    cursor_info(a.tt, cur, ti);
+    ti.nrows = min(32, ti.nrows - 32 * warp);
+    ti.r0 += 32 * warp;
+    const MapDesc& md = a.tt.maps[ti.m];
+    return md.pred + static_cast<long long>(img) * md.image_stride + static_cast<long long>(ti.r0) * a.tt.ch;
+}
+
+// ---- correct: the rows of this warp's tiles that receive targets ------------------------------------------------
+template <class P>
+__device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typename P::Rec* recs, int n_boxes,
+                                             unsigned short* cand, int img, int t_begin, int t_end) {
+    LossAcc acc = {0.f, 0.f, 0.f, 0};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TileCursor cur;
+    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
+        TileInfo ti;
+        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti);
+        if (ti.nrows <= 0) continue;
+        const MapDesc& md = a.tt.maps[ti.m];
+        int ncand = 0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < n_boxes; k0 += 32) {
+            const int k = k0 + lane;
+            const bool hit = k < n_boxes && P::tile_hit(a.pp, recs[k], ti, md);
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (hit) cand[ncand + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
+            ncand += __popc(bal);
+        }
+        if (ncand == 0) continue;  // warp-uniform
+        __syncwarp();
+        int pairs = 0;
+        if (lane < ti.nrows) {
+            CompactSink sink;
+            sink.clear();
+            const int row = ti.r0 + lane;
+            pairs = P::match_row(a.pp, ti, md, row, sink, recs, cand, ncand);
+            if (pairs > 0) {
+                const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
+                const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
+                const LossAcc d = correct_row(a.spec, gp + lane * a.tt.ch, sink, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                acc.cls += d.cls, acc.reg += d.reg, acc.cen += d.cen, acc.npos += d.npos;
+            }
+        }
+        P::tile_epilogue(a.pp, ti, pairs);
+        __syncwarp();  // the candidate list is rebuilt for the next tile
+    }
+    return acc;
+}
+
+// ---- stream: every element of this warp's tiles as if its label were zero -----------------------------------------
+template <class P, bool kGamma2>
+__device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img, int t_begin, int t_end) {
+    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int vpr = a.tt.ch >> 2;
+    const int step = 32 % vpr, c_lane = lane % vpr;
+    const float gamma = a.spec.gamma;
+    TileCursor cur;
+    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
+        TileInfo ti;
+        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti);
+        if (ti.nrows > 0) stream_vec<kGamma2, 7>(gp, ti.nrows, vpr, c_lane, step, lane, gamma, sa);
+    }
+    return sa;
+}
+template <class P, bool kGamma2>
+__device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int img, int t_begin, int t_end) {
+    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = a.tt.ch;
+    const int step = 32 % ch, c_lane = lane % ch;
+    const LossSpec sp = a.spec;
+    TileCursor cur;
+    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
+        TileInfo ti;
+        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti);
+        if (ti.nrows > 0) stream_scalar<kGamma2, 4>(gp, ti.nrows, ch, c_lane, step, lane, sp, sa);
+    }
+    return sa;
+}
+
+template <class P, bool kGamma2>
+__global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_constant__ LossArgs<P> ga) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const FusedSmemLayout lay = fused_smem_layout<P>(ga.box_cap);
+    const LossArgs<P>& a = *reinterpret_cast<const LossArgs<P>*>(smem + lay.args_off);  // see encode_kernel
+    copy_args_to_smem(ga, reinterpret_cast<LossArgs<P>*>(smem + lay.args_off));
+    typename P::Rec* recs = reinterpret_cast<typename P::Rec*>(smem + lay.rec_off);
+    float* raw = reinterpret_cast<float*>(smem + lay.raw_off);
+    uint64_t* boxbar = reinterpret_cast<uint64_t*>(smem + lay.misc_off);
+    long long* next_chunk = reinterpret_cast<long long*>(smem + lay.misc_off + 8);
+    float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 64);  // [8][4]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned short* cand = reinterpret_cast<unsigned short*>(smem + lay.cand_off) + warp * ga.box_cap;
+    const bool vec = ga.allow_vec && (ga.tt.ch & 3) == 0 && ga.spec.cen_mode == 0 && ga.spec.reg_ch == 4;
+    const int tpi = ga.tt.tiles_per_image;
+    const long long n_chunks = static_cast<long long>(ga.tt.batch) * ga.chunks_per_image;
+    long long chunk = blockIdx.x;
+    if (chunk >= n_chunks) return;
+    if (tid == 0) {
+        mbar_init(boxbar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    uint32_t box_parity = 0;
+    int cur_img = -1, n_boxes = 0;
+#pragma unroll 1
+    for (; chunk < n_chunks;) {
+        const int img = static_cast<int>(chunk / ga.chunks_per_image);
+        const int sub = static_cast<int>(chunk - static_cast<long long>(img) * ga.chunks_per_image);
+        const int t_begin = sub * ga.chunk_tiles;  // tile ids within the image
+        const int t_end = min(t_begin + ga.chunk_tiles, tpi);
+        if (tid == 0) *next_chunk = static_cast<long long>(atomicAdd(ga.sched, 1u)) + gridDim.x;
+        if (img != cur_img) {  // block-uniform; the barrier at the end of the previous chunk protects recs/raw
+            n_boxes = stage_boxes(a.boxes, a.nbox, img, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
+            const float hi = a.img_dim[2 * img], wi = a.img_dim[2 * img + 1];
+            if (tid < n_boxes) P::make_record(a.pp, raw + 5 * tid, hi, wi, tid, recs[tid]);
+            __syncthreads();
+            cur_img = img;
+        }
+        if (sub == 0) P::image_prologue(a.pp, recs, n_boxes, img);
+
+        const StreamAcc sa = vec ? stream_pass_vec<P, kGamma2>(a, img, t_begin, t_end) : stream_pass_scalar<P, kGamma2>(a, img, t_begin, t_end);
+        LossAcc acc = {0.f, 0.f, 0.f, 0};  // corrections + regression, natural units
+        if (n_boxes > 0) acc = correct_pass<P>(a, recs, n_boxes, cand, img, t_begin, t_end);
+
+        // ---- per-chunk reduction -> partials[chunk] -----------------------------------------------------------
+        float cls = ((sa.c0 + sa.c1) + (sa.c2 + sa.c3)) * ((1.0f - ga.spec.alpha) * kLn2) + acc.cls;
+        float cen = sa.cen + acc.cen;
+        cls = warp_sum(cls), cen = warp_sum(cen);
+        const float reg = warp_sum(acc.reg);
+        const int npos = warp_sum_i(acc.npos);
+        if (lane == 0) {
+            wred[warp * 4 + 0] = cls, wred[warp * 4 + 1] = reg, wred[warp * 4 + 2] = cen;
+            wred[warp * 4 + 3] = static_cast<float>(npos);
+        }
+        __syncthreads();  // also: every warp is done with recs; the prefetched chunk id is visible
+        if (tid < 4) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < DH_THREADS / 32; ++w) v += wred[w * 4 + tid];
+            a.partials[chunk * 4 + tid] = v;
+        }
+        chunk = *next_chunk;
+        __syncthreads();  // wred / next_chunk are free again
+    }
+}
+
+}  // namespace dh

@@ -13,6 +13,7 @@ struct dh_handle_s {
     int use_tma_store;
     int tile_bytes;
     int ctas_per_sm;
+    int fused_loss_kernel;  // DH_OPT_FUSED_LOSS_KERNEL
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
     size_t scratch_bytes;

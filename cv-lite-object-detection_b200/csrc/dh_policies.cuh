@@ -39,6 +39,37 @@ __device__ __forceinline__ double ratio64(float a, float b) {
     return ddiv(dadd(lo, 1.0e-8), dadd(hi, 1.0e-8));
 }
 
+// Where a policy writes the row it matched.  DenseSink is a zero-initialised row of the float32 target map
+// (encoders, and the shared-memory tile of the unfused-compatible loss kernel); CompactSink keeps the row in
+// registers as <= 5 regression values + a class bitmask (fused loss: targets never exist in memory at all).
+struct DenseSink {
+    float* dst;
+    __device__ __forceinline__ void cls(int first_class_ch, int c) { dst[first_class_ch + c] = 1.0f; }
+    __device__ __forceinline__ void reg(int k, float v) { dst[k] = v; }
+};
+constexpr int kCompactClassWords = 4;  // fused loss fast path: up to 128 classes
+struct CompactSink {
+    float r[5];
+    uint32_t m[kCompactClassWords];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[k] = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCompactClassWords; ++w) m[w] = 0u;
+    }
+    __device__ __forceinline__ void cls(int, int c) {
+        const uint32_t bit = 1u << (c & 31);
+        const int word = c >> 5;
+#pragma unroll
+        for (int w = 0; w < kCompactClassWords; ++w) m[w] |= (w == word) ? bit : 0u;
+    }
+    __device__ __forceinline__ void reg(int k, float v) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (q == k) r[q] = v;
+    }
+};
+
 // =====================================================================================
 // FCOS family: FCOS/fcos.py:136-378, fcos_center.py:149-279, fcos_center_v1.py:149-258
 // =====================================================================================
@@ -147,6 +178,12 @@ struct FcosPolicy {
     // returns the number of painters that touched the row (0 = row stays zero)
     __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
                                    const Rec* recs, const unsigned short* cand, int ncand) {
+        DenseSink sink{dst};
+        return match_row(p, ti, md, row, sink, recs, cand, ncand);
+    }
+    template <class Sink>
+    __device__ static int match_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, Sink& dst,
+                                    const Rec* recs, const unsigned short* cand, int ncand) {
         const int i = static_cast<int>(fdiv_u32(row, md.div_width));
         const int j = row - i * ti.width;
         int best = -1, hits = 0;
@@ -156,7 +193,7 @@ struct FcosPolicy {
             const Rec& r = recs[k];
             if (i < r.ry0 || i >= r.ry1 || j < r.rx0 || j >= r.rx1) continue;
             ++hits;
-            dst[kRegCh + r.cls] = 1.0f;
+            dst.cls(kRegCh, r.cls);
             if (p.mode == FCOS_CENTER3X3 || p.mode == FCOS_CENTER_ONLY) {  // fcos_center.py:253-265
                 const int dy = r.ycen - i, dx = r.xcen - j;
                 const float sc = (dy == 0 && dx == 0) ? 1.0f : ((dy != 0 && dx != 0) ? 0.25f : 0.5f);
@@ -167,16 +204,16 @@ struct FcosPolicy {
         if (best < 0) return 0;
         const Rec& r = recs[best];
         if (p.mode == FCOS_CENTER_V1) {
-            dst[0] = r.y0s, dst[1] = r.x0s, dst[2] = r.y1s, dst[3] = r.x1s, dst[4] = 1.0f;
+            dst.reg(0, r.y0s), dst.reg(1, r.x0s), dst.reg(2, r.y1s), dst.reg(3, r.x1s), dst.reg(4, 1.0f);
             return hits;
         }
         const float fi = static_cast<float>(i) + 0.5f, fj = static_cast<float>(j) + 0.5f;
         if (p.mode != FCOS_FOOTPRINT) {  // fcos_center.py:267-273 (unclipped)
-            dst[0] = fsub(fi, r.y0s);
-            dst[1] = fsub(fsub(r.y1s, static_cast<float>(i)), 0.5f);
-            dst[2] = fsub(fj, r.x0s);
-            dst[3] = fsub(fsub(r.x1s, static_cast<float>(j)), 0.5f);
-            dst[4] = best_score;
+            dst.reg(0, fsub(fi, r.y0s));
+            dst.reg(1, fsub(fsub(r.y1s, static_cast<float>(i)), 0.5f));
+            dst.reg(2, fsub(fj, r.x0s));
+            dst.reg(3, fsub(fsub(r.x1s, static_cast<float>(j)), 0.5f));
+            dst.reg(4, best_score);
             return hits;
         }
         const bool live_y = r.flags & 1, live_x = r.flags & 2;
@@ -186,7 +223,7 @@ struct FcosPolicy {
         const float bt = live_y ? fmaxf(0.f, fsub(r.y1s, fi)) : fmaxf(0.f, fsub(fsub(r.y1s, static_cast<float>(i)), 0.5f));
         const float l = fmaxf(0.f, fsub(fj, r.x0s));
         const float rt = live_x ? fmaxf(0.f, fsub(r.x1s, fj)) : fmaxf(0.f, fsub(fsub(r.x1s, static_cast<float>(j)), 0.5f));
-        dst[0] = t, dst[1] = bt, dst[2] = l, dst[3] = rt;
+        dst.reg(0, t), dst.reg(1, bt), dst.reg(2, l), dst.reg(3, rt);
         float cen = 1.0f;  // fcos.py:371-372 when both axes collapsed
         if (i == r.ycen && j == r.xcen) {
             cen = 1.0f;  // fcos.py:279-280
@@ -194,7 +231,7 @@ struct FcosPolicy {
             const double qy = live_y ? ratio64(t, bt) : 1.0, qx = live_x ? ratio64(l, rt) : 1.0;
             cen = static_cast<float>(sqrt(dmul(qy, qx)));  // fcos.py:273-274
         }
-        dst[4] = cen;
+        dst.reg(4, cen);
         return hits;
     }
 };
@@ -257,6 +294,12 @@ struct RetinaPolicy {
     // returns the number of (gt, anchor) pairs above the threshold at this row (:302-317)
     __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
                                    const Rec* recs, const unsigned short* cand, int ncand) {
+        DenseSink sink{dst};
+        return match_row(p, ti, md, row, sink, recs, cand, ncand);
+    }
+    template <class Sink>
+    __device__ static int match_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, Sink& dst,
+                                    const Rec* recs, const unsigned short* cand, int ncand) {
         const int i = static_cast<int>(fdiv_u32(row, md.div_width));
         const int j = row - i * ti.width;
         const int s = p.stride[ti.level];
@@ -279,17 +322,17 @@ struct RetinaPolicy {
             const float iou = fminf(fmaxf(fdiv(inter, uni), 0.f), 1.f);
             if (iou > p.thr) {  // :302 strict
                 ++pairs;
-                dst[kRegCh + r.cls] = 1.0f;
+                dst.cls(kRegCh, r.cls);
                 best = k;  // highest GT index wins the regression (:357)
             }
         }
         if (best >= 0) {  // :337-353, float64 like the reference's containers
             const Rec& r = recs[best];
             const double dah = static_cast<double>(ah), daw = static_cast<double>(aw);
-            dst[0] = static_cast<float>(ddiv(dsub(static_cast<double>(i * s), static_cast<double>(r.gy)), dah));
-            dst[1] = static_cast<float>(ddiv(dsub(static_cast<double>(j * s), static_cast<double>(r.gx)), daw));
-            dst[2] = static_cast<float>(ddiv(static_cast<double>(r.gh), dah));
-            dst[3] = static_cast<float>(ddiv(static_cast<double>(r.gw), daw));
+            dst.reg(0, static_cast<float>(ddiv(dsub(static_cast<double>(i * s), static_cast<double>(r.gy)), dah)));
+            dst.reg(1, static_cast<float>(ddiv(dsub(static_cast<double>(j * s), static_cast<double>(r.gx)), daw)));
+            dst.reg(2, static_cast<float>(ddiv(static_cast<double>(r.gh), dah)));
+            dst.reg(3, static_cast<float>(ddiv(static_cast<double>(r.gw), daw)));
         }
         return pairs;
     }
@@ -436,6 +479,12 @@ struct CenterNetPolicy {
 
     __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
                                    const Rec* recs, const unsigned short* cand, int ncand) {
+        DenseSink sink{dst};
+        return match_row(p, ti, md, row, sink, recs, cand, ncand);
+    }
+    template <class Sink>
+    __device__ static int match_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, Sink& dst,
+                                    const Rec* recs, const unsigned short* cand, int ncand) {
         int best = -1, hits = 0;
         float best_area = 0.f;
         if (p.mode != CN_POWER_FALLOFF) {
@@ -444,12 +493,12 @@ struct CenterNetPolicy {
                 const Rec& r = recs[k];
                 if (r.row != row) continue;
                 ++hits;
-                dst[4 + r.cls] = 1.0f;
+                dst.cls(4, r.cls);
                 if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
             }
             if (best < 0) return 0;
             const Rec& r = recs[best];
-            dst[0] = r.r0, dst[1] = r.r1, dst[2] = r.r2, dst[3] = r.r3;
+            dst.reg(0, r.r0), dst.reg(1, r.r1), dst.reg(2, r.r2), dst.reg(3, r.r3);
             return hits;
         }
         const int i = static_cast<int>(fdiv_u32(row, md.div_width));
@@ -459,17 +508,17 @@ struct CenterNetPolicy {
             const Rec& r = recs[k];
             if (i < r.ry0 || i >= r.ry1 || j < r.rx0 || j >= r.rx1) continue;
             ++hits;
-            dst[5 + r.cls] = 1.0f;
+            dst.cls(5, r.cls);
             if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
         }
         if (best < 0) return 0;
         const Rec& r = recs[best];
         const bool live_y = r.flags & 1, live_x = r.flags & 2;
         const float fi = static_cast<float>(i) + 0.5f, fj = static_cast<float>(j) + 0.5f;
-        dst[0] = fmaxf(0.f, fsub(fi, r.r0));
-        dst[1] = live_y ? fmaxf(0.f, fsub(r.r2, fi)) : fmaxf(0.f, fsub(fsub(r.r2, static_cast<float>(i)), 0.5f));
-        dst[2] = fmaxf(0.f, fsub(fj, r.r1));
-        dst[3] = live_x ? fmaxf(0.f, fsub(r.r3, fj)) : fmaxf(0.f, fsub(fsub(r.r3, static_cast<float>(j)), 0.5f));
+        dst.reg(0, fmaxf(0.f, fsub(fi, r.r0)));
+        dst.reg(1, live_y ? fmaxf(0.f, fsub(r.r2, fi)) : fmaxf(0.f, fsub(fsub(r.r2, static_cast<float>(i)), 0.5f)));
+        dst.reg(2, fmaxf(0.f, fsub(fj, r.r1)));
+        dst.reg(3, live_x ? fmaxf(0.f, fsub(r.r3, fj)) : fmaxf(0.f, fsub(fsub(r.r3, static_cast<float>(j)), 0.5f)));
         float heat = 1.0f;
         if (!(i == r.muy && j == r.mux) && (live_y || live_x)) {
             // max over the footprint is reached at the centre cell: 1/0.5^8 = 256 per live axis
@@ -478,7 +527,7 @@ struct CenterNetPolicy {
             if (live_x) v = dmul(v, inv_pow8(static_cast<double>(fj) - static_cast<double>(r.mux)) * (1.0 / 256.0));
             heat = static_cast<float>(v);
         }
-        dst[4] = heat;
+        dst.reg(4, heat);
         return hits;
     }
 };

@@ -3,7 +3,7 @@
 
 #include "dh_host.h"
 #include "dh_launch.h"
-#include "dh_loss_kernel.cuh"
+#include "dh_fused_loss_kernel.cuh"
 
 namespace dh {
 
@@ -74,9 +74,85 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
     return DH_OK;
 }
 
+
 static int loss_tile_bytes(const dh_handle_s* h) {
     (void)h;
     return 32768;  // work granule of the loss kernels (and the fused path's shared-memory target tile)
+}
+
+// Finalize kernels shared by both loss paths: chunk partials -> per-image sums -> total.
+static int finalize_loss(dh_handle_s* h, const float* partials, int batch, int chunks_per_image, float* per_image,
+                         float* out_total, cudaStream_t st) {
+    loss_finalize_images<<<batch, 128, 0, st>>>(partials, chunks_per_image, per_image);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    if (out_total) {
+        loss_finalize_total<<<1, 256, 0, st>>>(per_image, batch, out_total);
+        DH_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    return DH_OK;
+}
+
+// Fused encode+loss, stream + correct formulation (dh_fused_loss_kernel.cuh): 256-row tiles, 32 rows per warp.
+template <class P, bool kGamma2>
+static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, float* out_total, cudaStream_t st,
+                          const char* who) {
+    const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
+    const FusedSmemLayout lay = fused_smem_layout<P>(a.box_cap);
+    static bool attr_done = false;
+    if (!attr_done) {
+        DH_CUDA(cudaFuncSetAttribute(fused_loss_kernel<P, kGamma2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    int per_sm = 1;
+    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kGamma2>, DH_THREADS, lay.total));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = static_cast<long long>(h->sm_count) * per_sm;
+    // image-aligned chunks: aim at >= 8 chunks per CTA, 2..32 tiles (512..8192 rows) each
+    const int tpi = a.tt.tiles_per_image;
+    long long want = total / (grid * 8);
+    want = want < 2 ? 2 : (want > 32 ? 32 : want);
+    const int n_sub = tpi > 0 ? static_cast<int>((tpi + want - 1) / want) : 1;
+    a.chunk_tiles = tpi > 0 ? (tpi + n_sub - 1) / n_sub : 1;
+    a.chunks_per_image = tpi > 0 ? (tpi + a.chunk_tiles - 1) / a.chunk_tiles : 1;
+    const long long n_chunks = static_cast<long long>(a.tt.batch) * a.chunks_per_image;
+    if (grid > n_chunks) grid = n_chunks;
+    const size_t part_bytes = static_cast<size_t>(n_chunks) * 16;
+    const size_t img_bytes = static_cast<size_t>(a.tt.batch) * 16;
+    char* sc = static_cast<char*>(scratch(h, part_bytes + img_bytes + 512));
+    if (!sc) return DH_ERR_CUDA;
+    a.partials = reinterpret_cast<float*>(sc);
+    float* per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
+    if (total > 0) {
+        a.sched = next_sched_counter(h, st);
+        if (!a.sched) return DH_ERR_CUDA;
+        fused_loss_kernel<P, kGamma2><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+        DH_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    (void)who;
+    return finalize_loss(h, a.partials, a.tt.batch, total > 0 ? a.chunks_per_image : 0, per_image, out_total, st);
+}
+
+// Picks the fused kernel: stream + correct when the class bitmask fits (<= 128 classes), else the shared-memory
+// target-tile kernel (also selectable with DH_OPT_FUSED_LOSS_KERNEL = 1 for A/B checks).
+template <class P>
+static int launch_fused(dh_handle_s* h, LossArgs<P>& a, int num_classes, float* out_per_image, float* out_total,
+                        cudaStream_t st, const char* who) {
+    if (a.tt.batch == 0) return DH_OK;
+    const int ch = a.tt.ch;
+    if (h->fused_loss_kernel == 1 || num_classes > 32 * kCompactClassWords) {
+        a.tile_buf_bytes = finish_table(a.tt, ch, a.tt.batch, loss_tile_bytes(h));
+        return launch_loss<P, true>(h, a, out_per_image, out_total, st, who);
+    }
+    finish_table(a.tt, ch, a.tt.batch, DH_THREADS * ch * 4);  // one row per thread
+    a.box_cap = ((a.max_boxes > 0 ? a.max_boxes : 1) + 31) & ~31;
+    a.allow_vec = 1;
+    for (int m = 0; m < a.tt.n_maps; ++m)
+        if ((reinterpret_cast<uintptr_t>(a.tt.maps[m].pred) & 15u) || (a.tt.maps[m].image_stride & 3)) a.allow_vec = 0;
+    if (a.spec.gamma == 2.0f) return launch_fused_g<P, true>(h, a, out_per_image, out_total, st, who);
+    return launch_fused_g<P, false>(h, a, out_per_image, out_total, st, who);
 }
 
 }  // namespace dh
@@ -140,9 +216,9 @@ int dh_fcos_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, 
     DH_CHECK_ARG(cen_mode >= 1 && cen_mode <= 3, "dh_fcos_encode_loss: cen_mode must be 1, 2 or 3");
     rc = check_spec(a.spec, "dh_fcos_encode_loss");
     if (rc) return rc;
-    a.tile_buf_bytes = finish_table(a.tt, num_classes + 5, batch, loss_tile_bytes(h));
+    a.tt.ch = num_classes + 5, a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
-    return launch_loss<FcosPolicy, true>(h, a, out_per_image, out_total, static_cast<cudaStream_t>(stream), "dh_fcos_encode_loss");
+    return launch_fused<FcosPolicy>(h, a, num_classes, out_per_image, out_total, static_cast<cudaStream_t>(stream), "dh_fcos_encode_loss");
 }
 
 int dh_retina_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
@@ -163,10 +239,10 @@ int dh_retina_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox
     if (rc) return rc;
     a.spec.reg_ch = 4, a.spec.cen_mode = 0, a.spec.reg_mode = 0, a.spec.pos_rule = 1;
     a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
-    a.tile_buf_bytes = finish_table(a.tt, num_classes + 4, batch, loss_tile_bytes(h));
+    a.tt.ch = num_classes + 4, a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (num_pairs && batch > 0) DH_CUDA(cudaMemsetAsync(num_pairs, 0, sizeof(int32_t) * batch, st));
-    return launch_loss<RetinaPolicy, true>(h, a, out_per_image, out_total, st, "dh_retina_encode_loss");
+    return launch_fused<RetinaPolicy>(h, a, num_classes, out_per_image, out_total, st, "dh_retina_encode_loss");
 }
 
 int dh_centernet_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
@@ -191,10 +267,10 @@ int dh_centernet_encode_loss(dh_handle_t h, const float* boxes, const int32_t* n
     a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
     rc = check_spec(a.spec, "dh_centernet_encode_loss");
     if (rc) return rc;
-    a.tile_buf_bytes = finish_table(a.tt, num_classes + (falloff ? 5 : 4), batch, loss_tile_bytes(h));
+    a.tt.ch = num_classes + (falloff ? 5 : 4), a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
-    return launch_loss<CenterNetPolicy, true>(h, a, out_per_image, out_total, st, "dh_centernet_encode_loss");
+    return launch_fused<CenterNetPolicy>(h, a, num_classes, out_per_image, out_total, st, "dh_centernet_encode_loss");
 }
 
 }  // extern "C"

@@ -49,6 +49,7 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_TILE_BYTES 2  /* upper bound on the shared-memory tile size in bytes (default 49152; small problems use smaller tiles) */
 #define DH_OPT_CTAS_PER_SM 3 /* upper bound on persistent CTAs per SM (default 4; shared memory may allow fewer) */
 #define DH_OPT_PHASE_TIMING 4 /* profiling aid: 1 = CTA 0 of each encode kernel accumulates per-phase clock64 totals; (re)sets them */
+#define DH_OPT_FUSED_LOSS_KERNEL 5 /* 0 (default): stream + correct kernel when num_classes <= 128; 1: always the shared-memory target-tile kernel */
 int dh_set_option(dh_handle_t h, int option, int value);
 /* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in
  * {stage GT + records, candidates + buffer recycle, emit rows, hand-off to TMA, drain}, out8[5] = tiles. */

@@ -1,0 +1,190 @@
+// Microbenchmark for the label-free streaming pass of the fused loss kernel: how fast can a B200 read a
+// [rows, 84] float32 prediction map once and accumulate the focal term of the 80 class logits per row?
+// Variants differ in the element math (MUFU count) and in the load batching.  Build + run:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/focal_stream_probe tools/focal_stream_probe.cu
+//   tools/focal_stream_probe [GB]
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x)                                                                          \
+    do {                                                                               \
+        cudaError_t e_ = (x);                                                          \
+        if (e_ != cudaSuccess) {                                                       \
+            printf("%s failed: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); \
+            exit(1);                                                                   \
+        }                                                                              \
+    } while (0)
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcpf(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// sigma(x)^2 * softplus(x) / ln2, 3 MUFU
+__device__ __forceinline__ void term3(float x, float& acc) {
+    const float u = x * kLog2e;
+    const float e = ex2f(-fabsf(u));
+    const float w = 1.0f + e;
+    const float inv = rcpf(w);
+    const float lg = lg2f(w);
+    const float s = (x < 0.f ? e : 1.0f) * inv;
+    acc = fmaf(s * s, lg + fmaxf(u, 0.f), acc);
+}
+// 2 MUFU: reciprocal of w in (1, 2] by a quadratic seed + 2 Newton steps on the FMA pipe
+__device__ __forceinline__ float rcp_newton(float w) {
+    // minimax quadratic for 1/w on [1,2]: max rel err 1.01e-2 -> 1e-4 -> 1e-8 after two Newton steps
+    float r = fmaf(fmaf(0.32323232f, w, -1.45454545f), w, 2.12121212f);
+    float t = fmaf(-w, r, 1.0f);
+    r = fmaf(r, t, r);
+    t = fmaf(-w, r, 1.0f);
+    r = fmaf(r, t, r);
+    return r;
+}
+__device__ __forceinline__ void term2(float x, float& acc) {
+    const float u = x * kLog2e;
+    const float e = ex2f(-fabsf(u));
+    const float w = 1.0f + e;
+    const float inv = rcp_newton(w);
+    const float lg = lg2f(w);
+    const float s = (x < 0.f ? e : 1.0f) * inv;
+    acc = fmaf(s * s, lg + fmaxf(u, 0.f), acc);
+}
+// the current library formula (for comparison)
+__device__ __forceinline__ void term_old(float x, float& acc) {
+    const float e = __expf(-fabsf(x));
+    const float w = 1.0f + e;
+    const float inv = __fdividef(1.0f, w);
+    const float soft = __logf(w);
+    const float s = x >= 0.f ? inv : e * inv;
+    acc += 0.75f * (s * s) * (soft + fmaxf(x, 0.f));
+}
+__device__ __forceinline__ void term_none(float x, float& acc) { acc += x; }
+
+template <int V, int E = 0>
+__device__ __forceinline__ void term(float x, float& acc) {
+    if (V == 0) term_none(x, acc);
+    if (V == 1) term3(x, acc);
+    if (V == 2) term2(x, acc);
+    if (V == 3) term_old(x, acc);
+    if (V == 4) { if (E & 1) term2(x, acc); else term3(x, acc); }   // half the reciprocals on the FMA pipe
+    if (V == 5) { if (E == 3) term2(x, acc); else term3(x, acc); }  // a quarter
+}
+
+constexpr int VPR = 21;  // float4 per row (84 channels)
+
+// each warp owns 32-row sub-tiles (672 float4, contiguous); lane takes q = lane + 32 k and skips the one k whose
+// float4 holds the 4 regression channels
+template <int V, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) stream_kernel(const float4* __restrict__ p, long long n_sub, float* out) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (long long s = gw; s < n_sub; s += nw) {
+        const float4* base = p + s * (32 * VPR) + lane;
+        int c4 = lane % VPR;
+#pragma unroll 1
+        for (int k0 = 0; k0 < VPR; k0 += U) {
+            float4 x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < VPR) x[u] = __ldcs(base + (k0 + u) * 32);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k0 + u < VPR) {
+                    if (c4 != 0) {
+                        term<V, 0>(x[u].x, a0), term<V, 1>(x[u].y, a1), term<V, 2>(x[u].z, a2), term<V, 3>(x[u].w, a3);
+                    }
+                    c4 += 32 - VPR;
+                    if (c4 >= VPR) c4 -= VPR;
+                }
+            }
+        }
+    }
+    float a = (a0 + a1) + (a2 + a3);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) atomicAdd(out, a);
+}
+
+template <int V, int U, int MINB>
+static void run(const char* name, const float4* d, long long n_sub, float* d_out, int ctas_per_sm, double bytes) {
+    int dev, sms;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_kernel<V, U, MINB>, 256, 0));
+    const int per = ctas_per_sm < occ ? ctas_per_sm : occ;
+    const int grid = sms * per;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) stream_kernel<V, U, MINB><<<grid, 256>>>(d, n_sub, d_out);
+    CK(cudaDeviceSynchronize());
+    const int reps = 10;
+    CK(cudaMemset(d_out, 0, 4));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) stream_kernel<V, U, MINB><<<grid, 256>>>(d, n_sub, d_out);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    float h;
+    CK(cudaMemcpy(&h, d_out, 4, cudaMemcpyDeviceToHost));
+    printf("%-28s U=%d minb=%d ctas/sm=%d (occ %d)  %8.3f ms  %8.1f GB/s   sum/rep=%.6e\n", name, U, MINB, per, occ, ms / reps,
+           bytes / (ms / reps * 1e-3) / 1e9, h / reps);
+}
+
+int main(int argc, char** argv) {
+    const double gb = argc > 1 ? atof(argv[1]) : 3.3;
+    const long long n_sub = static_cast<long long>(gb * 1e9 / (32.0 * VPR * 16));
+    const long long n4 = n_sub * 32 * VPR;
+    const double bytes = static_cast<double>(n4) * 16;
+    float4* d;
+    float* d_out;
+    CK(cudaMalloc(&d, n4 * 16));
+    CK(cudaMalloc(&d_out, 4));
+    {  // logits ~ N(-4.595, 1) via a cheap host LCG + Box-Muller on a 64 MB pattern, tiled
+        const long long pat = 16ll << 20;
+        std::vector<float> h(pat);
+        unsigned long long s = 88172645463325252ull;
+        auto rnd = [&]() {
+            s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+            return (s >> 11) * (1.0 / 9007199254740992.0);
+        };
+        for (long long i = 0; i < pat; i += 2) {
+            const double r = sqrt(-2.0 * log(rnd() + 1e-300)), t = 6.283185307179586 * rnd();
+            h[i] = static_cast<float>(-4.595 + r * cos(t));
+            h[i + 1] = static_cast<float>(-4.595 + r * sin(t));
+        }
+        for (long long off = 0; off < n4 * 4; off += pat) {
+            const long long n = (n4 * 4 - off) < pat ? (n4 * 4 - off) : pat;
+            CK(cudaMemcpy(reinterpret_cast<float*>(d) + off, h.data(), n * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    printf("buffer %.2f GB, %lld warp sub-tiles\n", bytes / 1e9, n_sub);
+    run<0, 7, 1>("read+add", d, n_sub, d_out, 8, bytes);
+#define ROW(U, M)                                                        \
+    run<1, U, M>("3 MUFU", d, n_sub, d_out, 8, bytes);                   \
+    run<5, U, M>("2.75 MUFU", d, n_sub, d_out, 8, bytes);                \
+    run<4, U, M>("2.5 MUFU", d, n_sub, d_out, 8, bytes);                 \
+    run<2, U, M>("2 MUFU", d, n_sub, d_out, 8, bytes);
+    ROW(7, 1) ROW(7, 5) ROW(7, 6) ROW(3, 1) ROW(3, 6) ROW(3, 8) ROW(21, 1) ROW(11, 1)
+    return 0;
+}
