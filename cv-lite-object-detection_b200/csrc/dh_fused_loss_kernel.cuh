@@ -77,7 +77,7 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     l.rec_off = 0;
     l.raw_off = (static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127;
     l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
-    l.misc_off = l.cand_off + (DH_THREADS / 32) * box_cap * 2;  // one candidate list per warp
+    l.misc_off = l.cand_off + (DH_THREADS / 32) * box_cap * 4;  // per warp: tile candidates + map candidates
     l.args_off = l.misc_off + 256;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
     return l;
@@ -216,6 +216,8 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
                                              unsigned short* cand, int img, int t_begin, int t_end) {
     LossAcc acc = {0.f, 0.f, 0.f, 0};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned short* maplist = cand + a.box_cap;
+    int cur_m = -1, nmap = 0;
     TileCursor cur;
     cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
 #pragma unroll 1
@@ -224,11 +226,25 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
         const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti);
         if (ti.nrows <= 0) continue;
         const MapDesc& md = a.tt.maps[ti.m];
+        if (ti.m != cur_m) {  // entering another map: the boxes that can match it at all (tile-independent tests)
+            __syncwarp();
+            cur_m = ti.m, nmap = 0;
+#pragma unroll 1
+            for (int k0 = 0; k0 < n_boxes; k0 += 32) {
+                const int k = k0 + lane;
+                const bool hit = k < n_boxes && P::map_hit(a.pp, recs[k], ti.level, ti.anchor);
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) maplist[nmap + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
+                nmap += __popc(bal);
+            }
+            __syncwarp();
+        }
         int ncand = 0;
 #pragma unroll 1
-        for (int k0 = 0; k0 < n_boxes; k0 += 32) {
-            const int k = k0 + lane;
-            const bool hit = k < n_boxes && P::tile_hit(a.pp, recs[k], ti, md);
+        for (int q0 = 0; q0 < nmap; q0 += 32) {  // ... narrowed to this tile's rows (and columns)
+            const int q = q0 + lane;
+            const int k = q < nmap ? maplist[q] : 0;
+            const bool hit = q < nmap && P::range_hit(a.pp, recs[k], ti, md);
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
             if (hit) cand[ncand + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
             ncand += __popc(bal);
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 64);  // [8][4]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned short* cand = reinterpret_cast<unsigned short*>(smem + lay.cand_off) + warp * ga.box_cap;
+    unsigned short* cand = reinterpret_cast<unsigned short*>(smem + lay.cand_off) + warp * 2 * ga.box_cap;
     const bool vec = ga.allow_vec && (ga.tt.ch & 3) == 0 && ga.spec.cen_mode == 0 && ga.spec.reg_ch == 4;
     const int tpi = ga.tt.tiles_per_image;
     const long long n_chunks = static_cast<long long>(ga.tt.batch) * ga.chunks_per_image;

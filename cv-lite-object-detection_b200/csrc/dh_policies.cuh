@@ -174,6 +174,18 @@ struct FcosPolicy {
         const int i1 = static_cast<int>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
         return r.ry1 > i0 && r.ry0 <= i1;
     }
+    // two-level variant for small tiles (fused loss): map_hit is the tile-independent part, range_hit adds the
+    // row range and, when the tile lies inside one map row, the column range
+    __device__ static bool map_hit(const Params&, const Rec& r, int level, int) { return (r.flags & 4) && r.level == level; }
+    __device__ static bool range_hit(const Params&, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
+        const int last = ti.r0 + ti.nrows - 1;
+        const int i1 = static_cast<int>(fdiv_u32(last, md.div_width));
+        if (!(r.ry1 > i0 && r.ry0 <= i1)) return false;
+        if (i0 != i1) return true;
+        const int j0 = ti.r0 - i0 * md.width, j1 = last - i0 * md.width;
+        return r.rx1 > j0 && r.rx0 <= j1;
+    }
 
     // returns the number of painters that touched the row (0 = row stays zero)
     __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
@@ -289,6 +301,31 @@ struct RetinaPolicy {
         }
         // some anchor row i in [i0, i1] must overlap the GT by more than `need` in y
         return i1 * s + 0.5f * ah > r.lo_y + need - 0.01f && i0 * s - 0.5f * ah < r.hi_y - need + 0.01f;
+    }
+
+    __device__ static bool map_hit(const Params& p, const Rec& r, int level, int anchor) {
+        if (!(p.thr > 0.f)) return true;
+        const float ah = p.anchor_h[level][anchor], aw = p.anchor_w[level][anchor];
+        const float aa = ah * aw, k = 0.999f * p.thr;
+        return !(fminf(aa, r.area) < k * fmaxf(aa, r.area)) && !(fminf(aw, r.gw) < k * fmaxf(aw, r.gw)) &&
+               !(fminf(ah, r.gh) < k * fmaxf(ah, r.gh));
+    }
+    __device__ static bool range_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        if (p.thr < 0.f) return true;
+        const float ah = p.anchor_h[ti.level][ti.anchor], aw = p.anchor_w[ti.level][ti.anchor];
+        const float s = static_cast<float>(p.stride[ti.level]);
+        const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
+        const int last = ti.r0 + ti.nrows - 1;
+        const int i1 = static_cast<int>(fdiv_u32(last, md.div_width));
+        const float k = p.thr > 0.f ? 0.999f * p.thr : 0.f;
+        const float need_y = k * fmaxf(ah, r.gh);
+        if (!(static_cast<float>(i1) * s + 0.5f * ah > r.lo_y + need_y - 0.01f &&
+              static_cast<float>(i0) * s - 0.5f * ah < r.hi_y - need_y + 0.01f))
+            return false;
+        if (i0 != i1) return true;
+        const float j0 = static_cast<float>(ti.r0 - i0 * md.width), j1 = static_cast<float>(last - i0 * md.width);
+        const float need_x = k * fmaxf(aw, r.gw);
+        return j1 * s + 0.5f * aw > r.lo_x + need_x - 0.01f && j0 * s - 0.5f * aw < r.hi_x - need_x + 0.01f;
     }
 
     // returns the number of (gt, anchor) pairs above the threshold at this row (:302-317)
@@ -449,6 +486,17 @@ struct CenterNetPolicy {
         const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
         const int i1 = static_cast<int>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
         return r.ry1 > i0 && r.ry0 <= i1;
+    }
+    __device__ static bool map_hit(const Params&, const Rec& r, int, int) { return (r.flags & 4) != 0; }
+    __device__ static bool range_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        if (p.mode != CN_POWER_FALLOFF) return r.row >= ti.r0 && r.row < ti.r0 + ti.nrows;
+        const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
+        const int last = ti.r0 + ti.nrows - 1;
+        const int i1 = static_cast<int>(fdiv_u32(last, md.div_width));
+        if (!(r.ry1 > i0 && r.ry0 <= i1)) return false;
+        if (i0 != i1) return true;
+        const int j0 = ti.r0 - i0 * md.width, j1 = last - i0 * md.width;
+        return r.rx1 > j0 && r.rx0 <= j1;
     }
 
     // Scatter emission for the centre-cell modes: thread q owns candidate q, whose target is a single
