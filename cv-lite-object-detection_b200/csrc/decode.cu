@@ -134,124 +134,230 @@ __global__ void retina_decode_kernel(const float* __restrict__ pred, int batch, 
     }
 }
 
-// ---- exact per-segment top-k (radix select), stable in index order ------------------------------------
+// ---- exact per-segment top-k, stable in index order ------------------------------------------------------
+// One CTA per (segment, image).  The k-th best passing score is located with three reads of the segment:
+//   1. a 4096-bin histogram over a monotone *linear* map of the score (sigmoid scores spread over thousands of
+//      bins; a radix histogram of the float bits would pile them onto ~40 exponent bins and serialise the atomics);
+//   2. the entries of the boundary bin are collected into shared memory and ranked exactly by (score desc, index
+//      asc); the entry of rank need-1 gives the cut (T_key, T_idx).  (A boundary bin too large for shared memory
+//      is first narrowed by radix rounds on the float bits, and a run of identical scores by an ordered count.)
+//   3. an ordered compaction: `take = key > T_key || (key == T_key && index <= T_idx)` is a pure per-element
+//      predicate, so each thread handles 8 consecutive rows and a chunk of 8192 rows costs one block barrier.
 __device__ __forceinline__ unsigned score_key(float s) {
     const unsigned u = __float_as_uint(s);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone float -> uint
 }
+__device__ __forceinline__ int linear_bin(float s) {  // monotone non-decreasing in s
+    return s <= 0.f ? 0 : (s >= 1.f ? 4095 : static_cast<int>(s * 4096.0f));
+}
 
 constexpr int kSelThreads = 1024;
+constexpr int kSelItems = 8;     // consecutive rows per thread in the compaction pass
+constexpr int kSelListCap = 2048;  // boundary-bin entries ranked in shared memory
+
+struct SelShared {
+    unsigned hist[4096];
+    unsigned list_key[kSelListCap];
+    int list_idx[kSelListCap];
+    unsigned wtot[2][kSelThreads / 32];
+    unsigned n_list, bin, need, above, t_key;
+    int t_idx;
+};
+
+// largest bin b with sum(hist[b..nbins)) >= need; returns the bin and the count strictly above it (block-wide)
+__device__ __forceinline__ void find_boundary(SelShared& sh, int nbins, unsigned need, int tid) {
+    // thread t owns bins [t*per, t*per+per) counted from the top
+    const int per = (nbins + kSelThreads - 1) / kSelThreads;
+    unsigned mine = 0;
+    for (int q = 0; q < per; ++q) {
+        const int b = nbins - 1 - (tid * per + q);
+        if (b >= 0) mine += sh.hist[b];
+    }
+    // inclusive scan over threads (descending bins)
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) sh.wtot[0][warp] = incl;
+    __syncthreads();
+    unsigned before = 0;
+    for (int w = 0; w < warp; ++w) before += sh.wtot[0][w];
+    const unsigned excl = before + incl - mine;
+    if (excl < need && excl + mine >= need) {  // the boundary lies in this thread's bins (exactly one thread)
+        unsigned cum = excl;
+        for (int q = 0; q < per; ++q) {
+            const int b = nbins - 1 - (tid * per + q);
+            if (b < 0) break;
+            if (cum + sh.hist[b] >= need) {
+                sh.bin = static_cast<unsigned>(b), sh.above = cum;
+                break;
+            }
+            cum += sh.hist[b];
+        }
+    }
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ dets, long long n_total, int row_floats, int score_col,
                                                                   const int* __restrict__ seg_off /*[n_seg+1] device*/, int k_slots,
                                                                   float min_score, int inclusive, float* __restrict__ out,
                                                                   int* __restrict__ out_src, int out_rows) {
-    __shared__ unsigned hist[4096];
-    __shared__ unsigned s_prefix, s_need, s_scan[kSelThreads / 32], s_carry_gt, s_carry_eq;
+    __shared__ SelShared sh;
     const int b = blockIdx.y, seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lo = seg_off[seg], hi = seg_off[seg + 1];
-    const float* d = dets + static_cast<long long>(b) * n_total * row_floats;
+    const float* d = dets + static_cast<long long>(b) * n_total * row_floats + score_col;
     float* o = out + (static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots) * row_floats;
     int* osrc = out_src ? out_src + static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots : nullptr;
-    int k = k_slots;
-    if (k > hi - lo) k = max(hi - lo, 0);  // a segment shorter than k: the slots beyond its length stay padded
+    const int k = min(k_slots, max(hi - lo, 0));  // a segment shorter than k: the slots beyond its length stay padded
     auto passes = [&](float s) { return inclusive ? (s >= min_score) : (s > min_score); };
+    auto score_at = [&](int i) { return __ldg(d + static_cast<long long>(i) * row_floats); };
 
-    // three histogram rounds narrow the k-th largest key: bits [31:20], [19:8], [7:0]
-    unsigned prefix = 0, need = static_cast<unsigned>(k);  // keys matching `prefix` on the bits decided so far
-    bool take_all = false;
-    for (int round = 0; round < 3 && !take_all; ++round) {
-        const int shift = round == 0 ? 20 : (round == 1 ? 8 : 0);
-        const int bits = round == 2 ? 8 : 12;
-        const unsigned decided_mask = round == 0 ? 0u : (round == 1 ? 0xFFF00000u : 0xFFFFFF00u);
-        for (int i = tid; i < (1 << bits); i += kSelThreads) hist[i] = 0;
-        __syncthreads();
-        for (int i = lo + tid; i < hi; i += kSelThreads) {
-            const float s = d[static_cast<long long>(i) * row_floats + score_col];
-            if (!passes(s)) continue;
-            const unsigned key = score_key(s);
-            if ((key & decided_mask) == (prefix & decided_mask)) atomicAdd(&hist[(key >> shift) & ((1u << bits) - 1u)], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned cum = 0;
-            int bin = (1 << bits) - 1;
-            for (; bin >= 0; --bin) {
-                if (cum + hist[bin] >= need) break;
-                cum += hist[bin];
-            }
-            if (bin < 0) {
-                s_prefix = 0xFFFFFFFFu;  // fewer than `need` candidates: take everything that passes
-                s_need = 0;
-            } else {
-                s_prefix = prefix | (static_cast<unsigned>(bin) << shift);
-                s_need = need - cum;  // still to take among keys equal to the new prefix
-            }
-        }
-        __syncthreads();
-        if (s_prefix == 0xFFFFFFFFu && s_need == 0 && round == 0) take_all = true;
-        if (!take_all) prefix = s_prefix, need = s_need;
-        __syncthreads();
-    }
-    // stable compaction: key > T always, key == T for the first `need` in index order
-    const unsigned T = prefix;
-    if (tid == 0) s_carry_gt = 0, s_carry_eq = 0;
+    // ---- 1. linear histogram -------------------------------------------------------------------------------
+    for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
+    if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0;
     __syncthreads();
-    for (int base = lo; base < hi; base += kSelThreads) {
-        const int i = base + tid;
-        bool gt = false, eq = false;
-        if (i < hi) {
-            const float s = d[static_cast<long long>(i) * row_floats + score_col];
-            if (passes(s)) {
+    unsigned n_pass_local = 0;
+    for (int i = lo + tid; i < hi; i += kSelThreads) {
+        const float s = score_at(i);
+        if (passes(s)) atomicAdd(&sh.hist[linear_bin(s)], 1u), ++n_pass_local;
+    }
+    __syncthreads();
+    unsigned T_key = 0u;  // default: fewer than k rows pass -> take everything that passes
+    int T_idx = 0x7fffffff;
+    if (k > 0) find_boundary(sh, 4096, static_cast<unsigned>(k), tid);
+    if (k > 0 && sh.bin != 0xFFFFFFFFu) {
+        const int Bk = static_cast<int>(sh.bin);
+        unsigned need = static_cast<unsigned>(k) - sh.above;  // still to take inside the boundary bin (>= 1)
+        unsigned cnt = sh.hist[Bk];
+        // ---- 2a. (rare) boundary bin larger than the shared-memory list: narrow it by radix rounds on the key bits
+        unsigned prefix = 0u, decided = 0u;
+        bool all_equal = false;
+        for (int round = 0; cnt > kSelListCap && round < 3; ++round) {
+            const int shift = round == 0 ? 20 : (round == 1 ? 8 : 0);
+            const int bits = round == 2 ? 8 : 12;
+            __syncthreads();
+            for (int i = tid; i < (1 << bits); i += kSelThreads) sh.hist[i] = 0;
+            if (tid == 0) sh.bin = 0xFFFFFFFFu;
+            __syncthreads();
+            for (int i = lo + tid; i < hi; i += kSelThreads) {
+                const float s = score_at(i);
+                if (!passes(s) || linear_bin(s) != Bk) continue;
                 const unsigned key = score_key(s);
-                if (take_all) gt = true;
-                else gt = key > T, eq = key == T;
+                if ((key & decided) == prefix) atomicAdd(&sh.hist[(key >> shift) & ((1u << bits) - 1u)], 1u);
+            }
+            __syncthreads();
+            find_boundary(sh, 1 << bits, need, tid);
+            prefix |= sh.bin << shift;
+            decided |= ((1u << bits) - 1u) << shift;
+            need -= sh.above;
+            cnt = sh.hist[sh.bin];
+            if (round == 2) all_equal = true;  // every key bit decided: the remaining rows share one score
+        }
+        if (cnt > kSelListCap && all_equal) {
+            // ---- 2b. (rarer) more identical scores than the list holds: the cut is the need-th of them in index order
+            T_key = prefix;
+            unsigned carry = 0;
+            for (int base = lo; base < hi; base += kSelThreads) {
+                const int i = base + tid;
+                bool eq = false;
+                if (i < hi) {
+                    const float s = score_at(i);
+                    eq = passes(s) && score_key(s) == prefix;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, eq);
+                if (lane == 0) sh.wtot[0][warp] = __popc(bal);
+                __syncthreads();
+                unsigned before = carry;
+                for (int w = 0; w < warp; ++w) before += sh.wtot[0][w];
+                const unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
+                if (eq && rank == need - 1) sh.t_idx = i;
+                unsigned tot = 0;
+                for (int w = 0; w < kSelThreads / 32; ++w) tot += sh.wtot[0][w];
+                carry += tot;
+                __syncthreads();
+            }
+            T_idx = sh.t_idx;
+        } else {
+            // ---- 2. collect the boundary entries, rank them exactly ------------------------------------------------
+            __syncthreads();
+            for (int i = lo + tid; i < hi; i += kSelThreads) {
+                const float s = score_at(i);
+                if (!passes(s) || linear_bin(s) != Bk) continue;
+                const unsigned key = score_key(s);
+                if ((key & decided) != prefix) continue;
+                const unsigned slot = atomicAdd(&sh.n_list, 1u);
+                sh.list_key[slot] = key, sh.list_idx[slot] = i;
+            }
+            __syncthreads();
+            const int n_list = static_cast<int>(sh.n_list);
+            for (int e = tid; e < n_list; e += kSelThreads) {
+                const unsigned ke = sh.list_key[e];
+                const int ie = sh.list_idx[e];
+                unsigned rank = 0;
+                for (int f = 0; f < n_list; ++f) {
+                    const unsigned kf = sh.list_key[f];
+                    rank += (kf > ke || (kf == ke && sh.list_idx[f] < ie)) ? 1u : 0u;
+                }
+                if (rank == need - 1) sh.t_key = ke, sh.t_idx = ie;
+            }
+            __syncthreads();
+            T_key = sh.t_key, T_idx = sh.t_idx;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. ordered compaction ---------------------------------------------------------------------------------
+    unsigned carry = 0;
+    int it = 0;
+    for (int base = lo; base < hi; base += kSelThreads * kSelItems, ++it) {
+        const int i0 = base + tid * kSelItems;
+        unsigned flags = 0;
+#pragma unroll
+        for (int u = 0; u < kSelItems; ++u) {
+            const int i = i0 + u;
+            if (i < hi) {
+                const float s = score_at(i);
+                if (passes(s)) {
+                    const unsigned key = score_key(s);
+                    if (key > T_key || (key == T_key && i <= T_idx)) flags |= 1u << u;
+                }
             }
         }
-        // block-wide exclusive scans of gt and eq (packed: eq in the high 16 bits; chunk <= 1024 elements)
-        const unsigned v = (gt ? 1u : 0u) | (eq ? (1u << 16) : 0u);
-        unsigned incl = v;
+        const unsigned mine = __popc(flags);
+        unsigned incl = mine;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
             if (lane >= off) incl += t;
         }
-        if (lane == 31) s_scan[warp] = incl;
+        unsigned* wt = sh.wtot[it & 1];  // parity double buffer: one barrier per chunk
+        if (lane == 31) wt[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            unsigned w = s_scan[lane];
-            unsigned wi = w;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, wi, off);
-                if (lane >= off) wi += t;
+        unsigned before = carry, tot = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) {
+            const unsigned v = wt[w];
+            if (w < warp) before += v;
+            tot += v;
+        }
+        unsigned rank = before + incl - mine;
+        for (int u = 0; u < kSelItems && flags; ++u) {
+            if (!((flags >> u) & 1u)) continue;
+            if (rank < static_cast<unsigned>(k)) {
+                const int i = i0 + u;
+                const float* src = dets + (static_cast<long long>(b) * n_total + i) * row_floats;
+                float* dst = o + static_cast<long long>(rank) * row_floats;
+                for (int c = 0; c < row_floats; ++c) dst[c] = src[c];
+                if (osrc) osrc[rank] = i;
             }
-            s_scan[lane] = wi - w;  // exclusive prefix of warp totals
+            ++rank;
         }
-        __syncthreads();
-        const unsigned excl = incl - v + s_scan[warp];
-        const unsigned gt_before = (excl & 0xFFFFu) + s_carry_gt, eq_before = (excl >> 16) + s_carry_eq;
-        bool take = gt;
-        if (eq && eq_before < need) take = true;
-        // rank among taken elements, in index order
-        const unsigned eq_taken_before = eq_before < need ? eq_before : need;
-        const unsigned rank = gt_before + eq_taken_before;
-        if (take && rank < static_cast<unsigned>(k)) {
-            const float* src = d + static_cast<long long>(i) * row_floats;
-            float* dst = o + static_cast<long long>(rank) * row_floats;
-            for (int c = 0; c < row_floats; ++c) dst[c] = src[c];
-            if (osrc) osrc[rank] = i;
-        }
-        __syncthreads();
-        if (tid == kSelThreads - 1) {
-            s_carry_gt += (excl & 0xFFFFu) + (gt ? 1u : 0u);
-            s_carry_eq += (excl >> 16) + (eq ? 1u : 0u);
-        }
-        __syncthreads();
+        carry += tot;
     }
     // pad the unused slots with score = -inf so that any threshold drops them
-    const unsigned taken_eq = s_carry_eq < need ? s_carry_eq : need;
-    const unsigned filled = min(static_cast<unsigned>(k), s_carry_gt + (take_all ? 0u : taken_eq));
+    const unsigned filled = min(static_cast<unsigned>(k), carry);
     for (int r = filled + tid; r < k_slots; r += kSelThreads) {
         float* dst = o + static_cast<long long>(r) * row_floats;
         for (int c = 0; c < row_floats; ++c) dst[c] = 0.f;

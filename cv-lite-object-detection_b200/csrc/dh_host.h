@@ -14,6 +14,7 @@ struct dh_handle_s {
     int tile_bytes;
     int ctas_per_sm;
     int fused_loss_kernel;  // DH_OPT_FUSED_LOSS_KERNEL
+    int nms_kernel;         // DH_OPT_NMS_KERNEL
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
     size_t scratch_bytes;

@@ -11,8 +11,9 @@
 //                               gather boxes into score order.
 //   kernel 2  nms_mask_kernel   grid (col blocks, row blocks, images): bit j of mask[i][w] says box
 //                               64*w+j (later in order) is suppressed by box i; warp-ballot builds words.
-//   kernel 3  nms_sweep_kernel  one warp per image walks the order, OR-ing mask rows of kept boxes into a
-//                               register-resident `removed` bit vector (lanes own words).
+//   kernel 3  nms_sweep_kernel  one CTA per image walks the order 64 boxes at a time: one thread resolves the
+//                               block's greedy chain from its diagonal mask words, all threads OR the kept rows
+//                               into the shared-memory `removed` bit vector.
 //
 // Float arithmetic follows the reference operation order with contraction disabled, so kept indices
 // are bit-identical to the NumPy loop.
@@ -102,7 +103,13 @@ __device__ __forceinline__ bool suppress_agnostic(const float4& a, const float4&
     const float w = fmaxf(0.0f, fsub(fminf(a.z, c.z), fmaxf(a.x, c.x)));
     const float h = fmaxf(0.0f, fsub(fminf(a.w, c.w), fmaxf(a.y, c.y)));
     const float inter = fmul(w, h);
-    const float ovr = fdiv(inter, fadd(fsub(fadd(area_a, area_c), inter), 1e-8f));
+    const float den = fadd(fsub(fadd(area_a, area_c), inter), 1e-8f);
+    // ovr = inter / den decides; away from the threshold the division-free comparison gives the same answer
+    // (|inter - thr*den| far above the rounding error of either side), so the IEEE division runs only near it
+    const float rhs = fmul(thr, den);
+    const float gap = fabsf(fsub(inter, rhs)), tol = fmul(1.0e-6f, fadd(fabsf(inter), fabsf(rhs)));
+    if (den > 0.f && gap > tol) return inter > rhs;
+    const float ovr = fdiv(inter, den);
     return !(ovr <= thr);
 }
 // combined-NMS rule (TensorFlow's op, restated; parity unpinned): corner order normalised, degenerate
@@ -151,50 +158,181 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
 }
 
 // ---- kernel 3 -----------------------------------------------------------------------------------------
-// One warp per image.  Lane l owns words l, l+32, ... of the `removed` vector (<= 8 words per lane).
-__global__ void __launch_bounds__(32) nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ sorted_cls,
-                                                       const int* __restrict__ order, const int* __restrict__ n_cand, NmsParams p,
-                                                       int words, int* __restrict__ keep, int* __restrict__ n_keep) {
+// One CTA per image walks the score order 64 boxes at a time.  Inside a 64-block the greedy dependency needs only
+// the block's diagonal mask words, so one thread resolves it from shared memory (64 short steps); the rows of the
+// boxes it kept are then OR-ed into the `removed` bit vector by all threads in parallel (coalesced along the row).
+// Only mask words at or right of the diagonal are ever read, so nms_mask_kernel never has to clear the rest.
+constexpr int kSweepThreads = 256;
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ sorted_cls,
+                                                                  const int* __restrict__ order, const int* __restrict__ n_cand, NmsParams p,
+                                                                  int words, int* __restrict__ keep, int* __restrict__ n_keep) {
     extern __shared__ int class_count[];  // [num_classes] when per-class caps are on
-    const int b = blockIdx.x, lane = threadIdx.x;
+    __shared__ unsigned long long removed[kNmsMaxN / 64];
+    __shared__ unsigned long long diag[64];
+    __shared__ int bcls[64];
+    __shared__ unsigned long long s_km;
+    __shared__ int s_kept, s_stop;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int m = n_cand[b];
+    const int nblk = (m + 63) >> 6;
     const long long base = static_cast<long long>(b) * p.n_max;
     const bool caps = p.per_class && p.max_per_class > 0;
-    if (caps)
-        for (int c = lane; c < p.num_classes; c += 32) class_count[c] = 0;
-    __syncwarp();
-    unsigned long long removed[kNmsMaxN / 64 / 32];
-#pragma unroll
-    for (int k = 0; k < kNmsMaxN / 64 / 32; ++k) removed[k] = 0ull;
-    int kept = 0;
     const int max_total = p.max_total > 0 ? min(p.max_total, p.max_out) : p.max_out;
-    for (int i = 0; i < m && kept < max_total; ++i) {
-        const int w = i >> 6;
-        // the owner lane of word w broadcasts the bit
-        unsigned long long word = 0ull;
-#pragma unroll
-        for (int k = 0; k < kNmsMaxN / 64 / 32; ++k)
-            if ((w >> 5) == k) word = removed[k];
-        word = __shfl_sync(0xffffffffu, word, w & 31);
-        if ((word >> (i & 63)) & 1ull) continue;
-        if (caps) {
-            const int c = sorted_cls[base + i];
-            const bool full = c >= 0 && c < p.num_classes && class_count[c] >= p.max_per_class;
-            if (full) continue;  // over the per-class cap: dropped, and it suppresses nobody (it was never selected)
-            __syncwarp();
-            if (lane == 0 && c >= 0 && c < p.num_classes) class_count[c] += 1;
-            __syncwarp();
+    if (caps)
+        for (int c = tid; c < p.num_classes; c += kSweepThreads) class_count[c] = 0;
+    for (int w = tid; w < nblk; w += kSweepThreads) removed[w] = 0ull;
+    if (tid == 0) s_kept = 0, s_stop = (max_total <= 0);
+    __syncthreads();
+    for (int w = 0; w < nblk && !s_stop; ++w) {
+        const int first = w << 6, nb = min(64, m - first);
+        const int kept_before = s_kept;  // written by thread 0 before the barriers that end the previous block
+        if (tid < nb) {
+            diag[tid] = mask[(base + first + tid) * words + w];
+            if (caps) bcls[tid] = sorted_cls[base + first + tid];
         }
-        if (lane == 0) keep[static_cast<long long>(b) * p.max_out + kept] = order[base + i];
-        ++kept;
-        const unsigned long long* row = mask + (base + i) * words;
-#pragma unroll
-        for (int k = 0; k < kNmsMaxN / 64 / 32; ++k) {
-            const int ww = lane + 32 * k;
-            if (ww < words && ww >= w) removed[k] |= row[ww];
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long rem = removed[w], km = 0ull;
+            int kept = kept_before;
+            for (int r = 0; r < nb; ++r) {
+                if ((rem >> r) & 1ull) continue;
+                if (caps) {
+                    const int c = bcls[r];
+                    if (c >= 0 && c < p.num_classes) {
+                        if (class_count[c] >= p.max_per_class) continue;  // over the per-class cap: never selected, suppresses nobody
+                        class_count[c] += 1;
+                    }
+                }
+                km |= 1ull << r;
+                rem |= diag[r];
+                if (++kept >= max_total) {
+                    s_stop = 1;
+                    break;
+                }
+            }
+            s_km = km, s_kept = kept;
         }
+        __syncthreads();
+        const unsigned long long km = s_km;
+        if (tid < nb && ((km >> tid) & 1ull))
+            keep[static_cast<long long>(b) * p.max_out + kept_before + __popcll(km & ((1ull << tid) - 1ull))] = order[base + first + tid];
+        if (!s_stop && km) {
+            // thread <-> mask column; the 64 row loads are independent (16 in flight per thread), coalesced across threads
+            for (int ww = w + 1 + tid; ww < nblk; ww += kSweepThreads) {
+                const unsigned long long* col = mask + (base + first) * words + ww;
+                unsigned long long acc = removed[ww];
+#pragma unroll 1
+                for (int r0 = 0; r0 < 64; r0 += 16) {
+                    if (!((km >> r0) & 0xFFFFull)) continue;
+                    unsigned long long v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) v[u] = ((km >> (r0 + u)) & 1ull) ? __ldg(col + static_cast<long long>(r0 + u) * words) : 0ull;
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc |= v[u];
+                }
+                removed[ww] = acc;
+            }
+        }
+        __syncthreads();
     }
-    if (lane == 0) n_keep[b] = kept;
+    if (tid == 0) n_keep[b] = s_kept;
+}
+
+// ---- lazy variant: kernels 2 + 3 fused, one CTA per image -------------------------------------------------
+// Suppression bits are computed only for the boxes that are actually kept: per 64-block the diagonal tile is
+// evaluated in parallel, one thread resolves the block's greedy chain, and the boxes it kept are tested against
+// every later, still-alive candidate.  With a small output cap (FCOS: 100 per class / 100 total) the sweep ends
+// after two or three blocks and the 12.5 M-pair mask matrix is never formed.
+constexpr int kLazyThreads = 256;
+__device__ __forceinline__ bool suppresses(const NmsParams& p, const float4& a, int ac, const float4& c, int cc) {
+    if (p.per_class) return cc == ac && suppress_iou(a, c, p.iou_thr);
+    return suppress_agnostic(a, c, p.iou_thr);
+}
+__global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4* __restrict__ sorted_boxes, const int* __restrict__ sorted_cls,
+                                                                const int* __restrict__ order, const int* __restrict__ n_cand, NmsParams p,
+                                                                int* __restrict__ keep, int* __restrict__ n_keep) {
+    extern __shared__ int class_count[];  // [num_classes] when per-class caps are on
+    __shared__ unsigned removed[kNmsMaxN / 32];
+    __shared__ unsigned long long diag[64];
+    __shared__ float4 bbox[64], kbox[64];
+    __shared__ int bcls[64], kcls[64];
+    __shared__ unsigned long long s_km;
+    __shared__ int s_kept, s_stop;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int m = n_cand[b];
+    const int nblk = (m + 63) >> 6;
+    const long long base = static_cast<long long>(b) * p.n_max;
+    const bool caps = p.per_class && p.max_per_class > 0;
+    const int max_total = p.max_total > 0 ? min(p.max_total, p.max_out) : p.max_out;
+    if (caps)
+        for (int c = tid; c < p.num_classes; c += kLazyThreads) class_count[c] = 0;
+    for (int w = tid; w < 2 * nblk; w += kLazyThreads) removed[w] = 0u;
+    if (tid == 0) s_kept = 0, s_stop = (max_total <= 0);
+    __syncthreads();
+    for (int w = 0; w < nblk && !s_stop; ++w) {
+        const int first = w << 6, nb = min(64, m - first);
+        const int kept_before = s_kept;
+        if (tid < 64) {
+            diag[tid] = 0ull;
+            if (tid < nb) bbox[tid] = sorted_boxes[base + first + tid], bcls[tid] = sorted_cls[base + first + tid];
+        }
+        __syncthreads();
+        const unsigned long long alive = ~((static_cast<unsigned long long>(removed[2 * w + 1]) << 32) | removed[2 * w]);
+        {  // diagonal tile: thread (r, q) tests row r against columns 16 q .. 16 q + 15 that come after it
+            const int r = tid >> 2, q = tid & 3;
+            if (r < nb && ((alive >> r) & 1ull)) {
+                const float4 a = bbox[r];
+                const int ac = bcls[r];
+                unsigned long long bits = 0ull;
+                for (int c = max(16 * q, r + 1); c < min(16 * q + 16, nb); ++c)
+                    if (((alive >> c) & 1ull) && suppresses(p, a, ac, bbox[c], bcls[c])) bits |= 1ull << c;
+                if (bits) atomicOr(&diag[r], bits);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long rem = ~alive, km = 0ull;
+            int kept = kept_before;
+            for (int r = 0; r < nb; ++r) {
+                if ((rem >> r) & 1ull) continue;
+                if (caps) {
+                    const int c = bcls[r];
+                    if (c >= 0 && c < p.num_classes) {
+                        if (class_count[c] >= p.max_per_class) continue;  // never selected, suppresses nobody
+                        class_count[c] += 1;
+                    }
+                }
+                kbox[kept - kept_before] = bbox[r], kcls[kept - kept_before] = bcls[r];
+                km |= 1ull << r;
+                rem |= diag[r];
+                if (++kept >= max_total) {
+                    s_stop = 1;
+                    break;
+                }
+            }
+            s_km = km, s_kept = kept;
+        }
+        __syncthreads();
+        const unsigned long long km = s_km;
+        const int nk = __popcll(km);
+        if (tid < nb && ((km >> tid) & 1ull))
+            keep[static_cast<long long>(b) * p.max_out + kept_before + __popcll(km & ((1ull << tid) - 1ull))] = order[base + first + tid];
+        if (!s_stop && nk > 0) {  // the kept boxes of this block against every later candidate that is still alive
+            for (int j0 = first + 64; j0 < m; j0 += kLazyThreads) {
+                const int j = j0 + tid;  // j0 is a multiple of 32: a warp covers exactly one `removed` word
+                bool sup = false;
+                if (j < m && !((removed[j >> 5] >> (j & 31)) & 1u)) {
+                    const float4 c = __ldg(sorted_boxes + base + j);
+                    const int cc = p.per_class ? __ldg(sorted_cls + base + j) : 0;
+                    for (int q = 0; q < nk && !sup; ++q) sup = suppresses(p, kbox[q], kcls[q], c, cc);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                if ((tid & 31) == 0 && bal) removed[j >> 5] |= bal;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_keep[b] = s_kept;
 }
 
 }  // namespace dh
@@ -247,13 +385,21 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     }
     nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, sboxes, scls, order, ncand);
     DH_CUDA(cudaGetLastError());
-    // rows whose column blocks are skipped (cb < rb) must read as zero
-    DH_CUDA(cudaMemsetAsync(mask, 0, static_cast<size_t>(batch) * per_img * words * 8, st));
+    const size_t cap_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
+    // a small output cap ends the sweep after a few blocks, and a batch that fills the GPU gains nothing from the
+    // all-SM mask kernel: evaluate suppression lazily, one CTA per image
+    const int eff_total = max_total > 0 ? (max_total < max_out ? max_total : max_out) : max_out;
+    if (h->nms_kernel == 1 || (h->nms_kernel == 0 && (eff_total <= 512 || batch >= h->sm_count))) {
+        nms_lazy_kernel<<<batch, kLazyThreads, cap_smem, st>>>(sboxes, scls, order, ncand, p, keep, n_keep);
+        DH_CUDA(cudaGetLastError());
+        h->launches += 2;
+        return DH_OK;
+    }
     dim3 grid(words, words, batch);
     nms_mask_kernel<<<grid, 64, 0, st>>>(sboxes, scls, ncand, p, words, mask);
     DH_CUDA(cudaGetLastError());
     const size_t sweep_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
-    nms_sweep_kernel<<<batch, 32, sweep_smem, st>>>(mask, scls, order, ncand, p, words, keep, n_keep);
+    nms_sweep_kernel<<<batch, kSweepThreads, sweep_smem, st>>>(mask, scls, order, ncand, p, words, keep, n_keep);
     DH_CUDA(cudaGetLastError());
     h->launches += 3;
     return DH_OK;

@@ -19,6 +19,16 @@ def _dh():
     return densehead
 
 
+@pytest.fixture(autouse=True, params=["lazy", "mask+sweep"])
+def nms_kernel(request):
+    """Every test runs against both NMS implementations (DH_OPT_NMS_KERNEL): the lazy one-CTA-per-image sweep and
+    the all-SM mask matrix + block sweep; they must agree bit for bit with the oracle."""
+    dh = _dh()
+    dh.set_option(0, 6, 1 if request.param == "lazy" else 2)
+    yield request.param
+    dh.set_option(0, 6, 0)
+
+
 def test_prediction_to_corners_golden(golden):
     dh = _dh()
     z = golden("decode_nms")
