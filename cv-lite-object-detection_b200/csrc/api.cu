@@ -22,6 +22,8 @@ void* scratch(dh_handle_s* h, size_t bytes) {
         cudaFree(h->scratch);
         h->scratch = nullptr;
         h->scratch_bytes = 0;
+    h->scratch_b = nullptr;
+    h->scratch_b_bytes = 0;
     }
     size_t want = bytes + (bytes >> 1) + (1u << 20);
     cudaError_t e = cudaMalloc(&h->scratch, want);
@@ -31,6 +33,24 @@ void* scratch(dh_handle_s* h, size_t bytes) {
     }
     h->scratch_bytes = want;
     return h->scratch;
+}
+
+void* scratch_b(dh_handle_s* h, size_t bytes) {
+    if (bytes <= h->scratch_b_bytes) return h->scratch_b;
+    if (h->scratch_b) {
+        cudaDeviceSynchronize();
+        cudaFree(h->scratch_b);
+        h->scratch_b = nullptr;
+        h->scratch_b_bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 2) + (1u << 20);
+    cudaError_t e = cudaMalloc(&h->scratch_b, want);
+    if (e != cudaSuccess) {
+        set_error(DH_ERR_CUDA, "cudaMalloc(%zu) for pipeline scratch failed: %s", want, cudaGetErrorString(e));
+        return nullptr;
+    }
+    h->scratch_b_bytes = want;
+    return h->scratch_b;
 }
 
 constexpr int kSchedRing = 64;
@@ -81,6 +101,8 @@ int dh_create(dh_handle_t* out, int device) {
     h->launches = 0;
     h->scratch = nullptr;
     h->scratch_bytes = 0;
+    h->scratch_b = nullptr;
+    h->scratch_b_bytes = 0;
     h->phase_cycles = nullptr;
     h->sched = nullptr;
     h->sched_next = 0;
@@ -93,6 +115,7 @@ int dh_destroy(dh_handle_t h) {
     {
         dh::DeviceGuard g(h->device);
         if (h->scratch) cudaFree(h->scratch);
+        if (h->scratch_b) cudaFree(h->scratch_b);
         if (h->sched) cudaFree(h->sched);
         if (h->phase_cycles) cudaFree(h->phase_cycles);
     }

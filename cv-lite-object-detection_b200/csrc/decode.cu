@@ -15,6 +15,7 @@
 
 #include "dh_common.cuh"
 #include "dh_host.h"
+#include "dh_infer.h"
 
 namespace dh {
 
@@ -134,6 +135,164 @@ __global__ void retina_decode_kernel(const float* __restrict__ pred, int batch, 
     }
 }
 
+// ---- RetinaNet decode, streaming version ---------------------------------------------------------------------
+// HBM-bound on one read of the head (25.8 MB per COCO image).  Each warp owns 32-row tiles: one elected lane
+// pulls the tile (32 x ch floats, contiguous) into the warp's shared-memory stage with a single TMA bulk copy,
+// two stages deep, and every lane then scans ITS row out of shared memory.  max_c sigmoid(x_c) is monotone in the
+// logit, so the scan is a plain max over the logits; sigmoid is evaluated only for the winner and for the few
+// logits close enough to it that their float32 sigmoid could collide with the winner's (the reference's
+// np.argmax returns the FIRST index of the maximal score, so such a collision at a lower index must win).
+constexpr int kDecWarps = 8;
+struct RetinaDecodeArgs {
+    const float* head[DH_MAX_LEVELS];   // [B, A, Hl, Wl, ch]
+    long long rows[DH_MAX_LEVELS];      // B * A * Hl * Wl
+    long long tile_begin[DH_MAX_LEVELS + 1];
+    long long level_off[DH_MAX_LEVELS]; // first output row of the level inside an image
+    int per_img[DH_MAX_LEVELS];         // A * Hl * Wl
+    int cells[DH_MAX_LEVELS], wl[DH_MAX_LEVELS];
+    FastDiv div_per_img[DH_MAX_LEVELS], div_cells[DH_MAX_LEVELS], div_wl[DH_MAX_LEVELS];
+    float stride[DH_MAX_LEVELS];
+    const float* anchor_hw;             // device [n_levels, A, 2]
+    int n_levels, n_anchors, num_classes, ch, use_tma;
+    long long n_total;
+};
+
+// lower bound t such that x < t implies sigmoid_acc(x) < sigmoid_acc(m) strictly (conservative; see above)
+__device__ __forceinline__ float sigmoid_collision_floor(float m) {
+    const float e = expf(-m);
+    if (!(e > 0.f)) return fminf(16.0f, m);  // exp underflowed: every logit >= ~16.7 gives exactly 1
+    const float delta = 2.0f * log1pf(9.5367431640625e-07f * (1.0f + 1.0f / e)) + 1.0e-6f * fabsf(m);
+    const float t = m - delta;
+    return m > 16.0f ? fminf(16.0f, t) : t;
+}
+
+__global__ void __launch_bounds__(kDecWarps * 32) retina_decode_stream_kernel(const __grid_constant__ RetinaDecodeArgs a, float* __restrict__ dets) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = a.ch, C = a.num_classes;
+    const int stage_floats = 32 * ch;
+    float* stage0 = reinterpret_cast<float*>(smem) + static_cast<long long>(warp) * 2 * stage_floats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(kDecWarps) * 2 * stage_floats * 4) + warp * 2;
+    if (lane == 0) {
+        mbar_init(bars, 1), mbar_init(bars + 1, 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    const long long total_tiles = a.tile_begin[a.n_levels];
+    const long long gw = static_cast<long long>(blockIdx.x) * kDecWarps + warp;
+    const long long nw = static_cast<long long>(gridDim.x) * kDecWarps;
+    auto locate = [&](long long tile, int& l, long long& r0, int& nrows) {
+        l = 0;
+        while (l + 1 < a.n_levels && tile >= a.tile_begin[l + 1]) ++l;
+        r0 = (tile - a.tile_begin[l]) * 32;
+        const long long left = a.rows[l] - r0;
+        nrows = left < 32 ? static_cast<int>(left) : 32;
+    };
+    auto fetch = [&](long long tile, int st) {  // all lanes call
+        int l, nrows;
+        long long r0;
+        locate(tile, l, r0, nrows);
+        const float* src = a.head[l] + r0 * ch;
+        float* dst = stage0 + st * stage_floats;
+        if (a.use_tma) {
+            if (lane == 0) {
+                const uint32_t bytes = static_cast<uint32_t>(nrows) * ch * 4u;
+                mbar_expect_tx(bars + st, bytes);
+                bulk_g2s(dst, src, bytes, bars + st);
+            }
+        } else {
+            for (int e = lane; e < nrows * ch; e += 32) dst[e] = __ldg(src + e);
+        }
+    };
+    uint32_t parity[2] = {0u, 0u};
+    long long tile = gw;
+    if (tile < total_tiles) fetch(tile, 0);
+    for (int it = 0; tile < total_tiles; ++it, tile += nw) {
+        const int st = it & 1;
+        if (tile + nw < total_tiles) fetch(tile + nw, st ^ 1);  // the other stage was drained before the __syncwarp below
+        if (a.use_tma) {
+            mbar_wait(bars + st, parity[st]);
+            parity[st] ^= 1u;
+        } else {
+            __syncwarp();
+        }
+        int l, nrows;
+        long long r0;
+        locate(tile, l, r0, nrows);
+        float* tile_smem = stage0 + st * stage_floats;
+        float o6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        long long orow = 0;
+        if (lane < nrows) {
+            const float* q = tile_smem + lane * ch;
+            // max logit, its first index, and the largest logit before that index
+            float m = q[4], prev = -INFINITY;
+            int cm = 0;
+            if ((ch & 3) == 0) {
+                const float4* q4 = reinterpret_cast<const float4*>(q);
+                for (int v = 1; v < (ch >> 2); ++v) {
+                    const float4 x = q4[v];
+                    const int c0 = 4 * v - 4;
+                    if (x.x > m) prev = m, m = x.x, cm = c0;
+                    if (x.y > m) prev = m, m = x.y, cm = c0 + 1;
+                    if (x.z > m) prev = m, m = x.z, cm = c0 + 2;
+                    if (x.w > m) prev = m, m = x.w, cm = c0 + 3;
+                }
+            } else {
+                for (int c = 1; c < C; ++c)
+                    if (q[4 + c] > m) prev = m, m = q[4 + c], cm = c;
+            }
+            const float best = sigmoid_acc(m);
+            int label = cm;
+            if (best == 0.f) {
+                label = 0;  // every score is 0: the first index wins
+            } else if (cm > 0) {
+                // below 8 the collision window is < 6e-3 wide; the general bound is only evaluated for large logits
+                const float floor_x = m < 8.0f ? m - 0.01f : sigmoid_collision_floor(m);
+                if (prev >= floor_x) {  // rare: an earlier logit is close enough to tie after the sigmoid
+                    for (int c = 0; c < cm; ++c) {
+                        const float x = q[4 + c];
+                        if (x >= floor_x && sigmoid_acc(x) == best) {
+                            label = c;
+                            break;
+                        }
+                    }
+                }
+            }
+            const uint32_t r = static_cast<uint32_t>(r0) + lane;
+            const uint32_t b = fdiv_u32(r, a.div_per_img[l]);
+            const uint32_t local = r - b * a.per_img[l];
+            const uint32_t an = fdiv_u32(local, a.div_cells[l]);
+            const uint32_t loc = local - an * a.cells[l];
+            const uint32_t i = fdiv_u32(loc, a.div_wl[l]);
+            CornerParams cp;
+            cp.mode = 1, cp.stride = a.stride[l];
+            cp.d0 = __ldg(a.anchor_hw + (l * a.n_anchors + an) * 2), cp.d1 = __ldg(a.anchor_hw + (l * a.n_anchors + an) * 2 + 1);
+            const float4 o = corners_of(cp, static_cast<int>(i), static_cast<int>(loc - i * a.wl[l]), 0, q[0], q[1], q[2], q[3]);
+            o6[0] = o.x, o6[1] = o.y, o6[2] = o.z, o6[3] = o.w, o6[4] = best, o6[5] = static_cast<float>(label);
+            orow = static_cast<long long>(b) * a.n_total + a.level_off[l] + local;
+        }
+        // hand the 6-float rows to the stage buffer and write them out coalesced (the tile's output rows are
+        // contiguous unless it straddles an image boundary)
+        __syncwarp();
+        const long long orow0 = __shfl_sync(0xffffffffu, orow, 0);
+        const bool contiguous = __all_sync(0xffffffffu, lane >= nrows || orow == orow0 + lane);
+        if (contiguous) {
+            if (lane < nrows) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) tile_smem[lane * 6 + c] = o6[c];
+            }
+            __syncwarp();
+            float* dst = dets + orow0 * 6;
+            for (int e = lane; e < nrows * 6; e += 32) dst[e] = tile_smem[e];
+        } else if (lane < nrows) {
+            float* d = dets + orow * 6;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) d[c] = o6[c];
+        }
+        __syncwarp();  // every lane is done with this stage before it is refilled
+    }
+}
+
 // ---- exact per-segment top-k, stable in index order ------------------------------------------------------
 // One CTA per (segment, image).  The k-th best passing score is located with three reads of the segment:
 //   1. a 4096-bin histogram over a monotone *linear* map of the score (sigmoid scores spread over thousands of
@@ -160,7 +319,7 @@ struct SelShared {
     unsigned list_key[kSelListCap];
     int list_idx[kSelListCap];
     unsigned wtot[2][kSelThreads / 32];
-    unsigned n_list, bin, need, above, t_key;
+    unsigned n_list, bin, need, above, t_key, n_pass;
     int t_idx;
 };
 
@@ -201,29 +360,39 @@ __device__ __forceinline__ void find_boundary(SelShared& sh, int nbins, unsigned
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ dets, long long n_total, int row_floats, int score_col,
-                                                                  const int* __restrict__ seg_off /*[n_seg+1] device*/, int k_slots,
-                                                                  float min_score, int inclusive, float* __restrict__ out,
-                                                                  int* __restrict__ out_src, int out_rows) {
-    __shared__ SelShared sh;
-    const int b = blockIdx.y, seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lo = seg_off[seg], hi = seg_off[seg + 1];
-    const float* d = dets + static_cast<long long>(b) * n_total * row_floats + score_col;
-    float* o = out + (static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots) * row_floats;
-    int* osrc = out_src ? out_src + static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots : nullptr;
-    const int k = min(k_slots, max(hi - lo, 0));  // a segment shorter than k: the slots beyond its length stay padded
+// The selector proper, shared by the generic kernel (scores = one column of a row array) and the fused FCOS
+// kernel (scores computed on the fly from the head logits).  `Src` provides
+//   int n                               elements in the segment (indices 0 .. n-1)
+//   float score(int i)                  the element's score (deterministic: it is evaluated up to three times)
+//   void emit(int i, float s, int rank) write output slot `rank` from element i
+//   void pad(int rank)                  mark output slot `rank` unused
+// Selected elements are emitted in index order; exactly min(k, #passing) slots are filled.
+template <class Src>
+__device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k_slots, float min_score, int inclusive) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = src.n;
+    const int k = min(k_slots, max(n, 0));  // a segment shorter than k: the slots beyond its length stay padded
     auto passes = [&](float s) { return inclusive ? (s >= min_score) : (s > min_score); };
-    auto score_at = [&](int i) { return __ldg(d + static_cast<long long>(i) * row_floats); };
+    constexpr int U = 8;  // independent loads in flight per thread in the unordered passes
 
     // ---- 1. linear histogram -------------------------------------------------------------------------------
     for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
-    if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0;
+    if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0, sh.n_pass = 0;
     __syncthreads();
-    unsigned n_pass_local = 0;
-    for (int i = lo + tid; i < hi; i += kSelThreads) {
-        const float s = score_at(i);
-        if (passes(s)) atomicAdd(&sh.hist[linear_bin(s)], 1u), ++n_pass_local;
+    unsigned my_pass = 0;
+    for (int base = 0; base < n; base += kSelThreads * U) {
+        float s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * kSelThreads + tid;
+            s[u] = i < n ? src.score(i) : __int_as_float(0x7fc00000);  // NaN never passes
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (passes(s[u])) atomicAdd(&sh.hist[linear_bin(s[u])], 1u), ++my_pass;
     }
+    my_pass = static_cast<unsigned>(warp_sum_i(static_cast<int>(my_pass)));
+    if (lane == 0 && my_pass) atomicAdd(&sh.n_pass, my_pass);
     __syncthreads();
     unsigned T_key = 0u;  // default: fewer than k rows pass -> take everything that passes
     int T_idx = 0x7fffffff;
@@ -242,8 +411,8 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
             for (int i = tid; i < (1 << bits); i += kSelThreads) sh.hist[i] = 0;
             if (tid == 0) sh.bin = 0xFFFFFFFFu;
             __syncthreads();
-            for (int i = lo + tid; i < hi; i += kSelThreads) {
-                const float s = score_at(i);
+            for (int i = tid; i < n; i += kSelThreads) {
+                const float s = src.score(i);
                 if (!passes(s) || linear_bin(s) != Bk) continue;
                 const unsigned key = score_key(s);
                 if ((key & decided) == prefix) atomicAdd(&sh.hist[(key >> shift) & ((1u << bits) - 1u)], 1u);
@@ -260,22 +429,24 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
             // ---- 2b. (rarer) more identical scores than the list holds: the cut is the need-th of them in index order
             T_key = prefix;
             unsigned carry = 0;
-            for (int base = lo; base < hi; base += kSelThreads) {
+            for (int base = 0; base < n; base += kSelThreads) {
                 const int i = base + tid;
                 bool eq = false;
-                if (i < hi) {
-                    const float s = score_at(i);
+                if (i < n) {
+                    const float s = src.score(i);
                     eq = passes(s) && score_key(s) == prefix;
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, eq);
                 if (lane == 0) sh.wtot[0][warp] = __popc(bal);
                 __syncthreads();
-                unsigned before = carry;
-                for (int w = 0; w < warp; ++w) before += sh.wtot[0][w];
+                unsigned before = carry, tot = 0;
+                for (int w = 0; w < kSelThreads / 32; ++w) {
+                    const unsigned v = sh.wtot[0][w];
+                    if (w < warp) before += v;
+                    tot += v;
+                }
                 const unsigned rank = before + __popc(bal & ((1u << lane) - 1u));
                 if (eq && rank == need - 1) sh.t_idx = i;
-                unsigned tot = 0;
-                for (int w = 0; w < kSelThreads / 32; ++w) tot += sh.wtot[0][w];
                 carry += tot;
                 __syncthreads();
             }
@@ -283,13 +454,21 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
         } else {
             // ---- 2. collect the boundary entries, rank them exactly ------------------------------------------------
             __syncthreads();
-            for (int i = lo + tid; i < hi; i += kSelThreads) {
-                const float s = score_at(i);
-                if (!passes(s) || linear_bin(s) != Bk) continue;
-                const unsigned key = score_key(s);
-                if ((key & decided) != prefix) continue;
-                const unsigned slot = atomicAdd(&sh.n_list, 1u);
-                sh.list_key[slot] = key, sh.list_idx[slot] = i;
+            for (int base = 0; base < n; base += kSelThreads * U) {
+                float s[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * kSelThreads + tid;
+                    s[u] = i < n ? src.score(i) : __int_as_float(0x7fc00000);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (!passes(s[u]) || linear_bin(s[u]) != Bk) continue;
+                    const unsigned key = score_key(s[u]);
+                    if ((key & decided) != prefix) continue;
+                    const unsigned slot = atomicAdd(&sh.n_list, 1u);
+                    sh.list_key[slot] = key, sh.list_idx[slot] = base + u * kSelThreads + tid;
+                }
             }
             __syncthreads();
             const int n_list = static_cast<int>(sh.n_list);
@@ -312,18 +491,17 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
     // ---- 3. ordered compaction ---------------------------------------------------------------------------------
     unsigned carry = 0;
     int it = 0;
-    for (int base = lo; base < hi; base += kSelThreads * kSelItems, ++it) {
+    for (int base = 0; base < n; base += kSelThreads * kSelItems, ++it) {
         const int i0 = base + tid * kSelItems;
+        float s[kSelItems];
+#pragma unroll
+        for (int u = 0; u < kSelItems; ++u) s[u] = (i0 + u < n) ? src.score(i0 + u) : __int_as_float(0x7fc00000);
         unsigned flags = 0;
 #pragma unroll
         for (int u = 0; u < kSelItems; ++u) {
-            const int i = i0 + u;
-            if (i < hi) {
-                const float s = score_at(i);
-                if (passes(s)) {
-                    const unsigned key = score_key(s);
-                    if (key > T_key || (key == T_key && i <= T_idx)) flags |= 1u << u;
-                }
+            if (passes(s[u])) {
+                const unsigned key = score_key(s[u]);
+                if (key > T_key || (key == T_key && i0 + u <= T_idx)) flags |= 1u << u;
             }
         }
         const unsigned mine = __popc(flags);
@@ -343,27 +521,125 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
             tot += v;
         }
         unsigned rank = before + incl - mine;
-        for (int u = 0; u < kSelItems && flags; ++u) {
+#pragma unroll
+        for (int u = 0; u < kSelItems; ++u) {
             if (!((flags >> u) & 1u)) continue;
-            if (rank < static_cast<unsigned>(k)) {
-                const int i = i0 + u;
-                const float* src = dets + (static_cast<long long>(b) * n_total + i) * row_floats;
-                float* dst = o + static_cast<long long>(rank) * row_floats;
-                for (int c = 0; c < row_floats; ++c) dst[c] = src[c];
-                if (osrc) osrc[rank] = i;
-            }
+            if (rank < static_cast<unsigned>(k)) src.emit(i0 + u, s[u], static_cast<int>(rank));
             ++rank;
         }
         carry += tot;
     }
-    // pad the unused slots with score = -inf so that any threshold drops them
+    // pad the unused slots so that any threshold drops them
     const unsigned filled = min(static_cast<unsigned>(k), carry);
-    for (int r = filled + tid; r < k_slots; r += kSelThreads) {
-        float* dst = o + static_cast<long long>(r) * row_floats;
+    for (int r = filled + tid; r < k_slots; r += kSelThreads) src.pad(r);
+}
+
+// generic source: rows of `row_floats` floats, the score in column `score_col`; selected rows are copied whole
+struct RowSource {
+    const float* rows;  // first row of the segment
+    float* out;         // first output slot of the segment
+    int* out_src;       // or null
+    int row_floats, score_col, n, first_index;
+    __device__ __forceinline__ float score(int i) const { return __ldg(rows + static_cast<long long>(i) * row_floats + score_col); }
+    __device__ __forceinline__ void emit(int i, float, int rank) const {
+        const float* src = rows + static_cast<long long>(i) * row_floats;
+        float* dst = out + static_cast<long long>(rank) * row_floats;
+        for (int c = 0; c < row_floats; ++c) dst[c] = src[c];
+        if (out_src) out_src[rank] = first_index + i;
+    }
+    __device__ __forceinline__ void pad(int rank) const {
+        float* dst = out + static_cast<long long>(rank) * row_floats;
         for (int c = 0; c < row_floats; ++c) dst[c] = 0.f;
         dst[score_col] = -INFINITY;
-        if (osrc) osrc[r] = -1;
+        if (out_src) out_src[rank] = -1;
     }
+};
+
+struct SelSegs {
+    int off[DH_MAX_LEVELS + 1];
+};
+__global__ void __launch_bounds__(kSelThreads) select_topk_segs_kernel(const float* __restrict__ dets, long long n_total, int row_floats,
+                                                                       int score_col, SelSegs segs, int k_slots, float min_score, int inclusive,
+                                                                       float* __restrict__ out, int out_rows, int* __restrict__ overflow) {
+    __shared__ SelShared sh;
+    const int b = blockIdx.y, seg = blockIdx.x;
+    const int lo = segs.off[seg], hi = segs.off[seg + 1];
+    RowSource src;
+    src.rows = dets + (static_cast<long long>(b) * n_total + lo) * row_floats;
+    src.out = out + (static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots) * row_floats;
+    src.out_src = nullptr;
+    src.row_floats = row_floats, src.score_col = score_col, src.n = hi - lo, src.first_index = lo;
+    select_core(sh, src, k_slots, min_score, inclusive);
+    if (overflow && threadIdx.x == 0 && sh.n_pass > static_cast<unsigned>(k_slots)) atomicOr(overflow + b, 1);
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ dets, long long n_total, int row_floats, int score_col,
+                                                                  const int* __restrict__ seg_off /*[n_seg+1] device*/, int k_slots,
+                                                                  float min_score, int inclusive, float* __restrict__ out,
+                                                                  int* __restrict__ out_src, int out_rows) {
+    __shared__ SelShared sh;
+    const int b = blockIdx.y, seg = blockIdx.x;
+    const int lo = seg_off[seg], hi = seg_off[seg + 1];
+    RowSource src;
+    src.rows = dets + (static_cast<long long>(b) * n_total + lo) * row_floats;
+    src.out = out + (static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots) * row_floats;
+    src.out_src = out_src ? out_src + static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots : nullptr;
+    src.row_floats = row_floats, src.score_col = score_col, src.n = hi - lo, src.first_index = lo;
+    select_core(sh, src, k_slots, min_score, inclusive);
+}
+
+// Fused FCOS front end (FCOS/infer_fcos.py:35-57 + the pre-NMS selection): one CTA per (level, image) reads the
+// head rows [Hl*Wl, C+5], scores every (location, class) pair on the fly -- sigmoid(class) [* sigmoid(centerness)],
+// the same float32 expression as fcos_decode_kernel -- and emits the selected pairs as candidate rows
+// (y1, x1, y2, x2, score, class) in (location, class) order.  Neither the [B, N, C] score tensor nor the decoded
+// boxes of unselected locations are ever written.
+struct FcosSource {
+    const float* head;  // [rows, C+5] of this (image, level)
+    float* out;         // [k, 6]
+    int n, num_classes, ch, wl, center;
+    float stride;
+    FastDiv div_c;
+    __device__ __forceinline__ float score(int i) const {
+        const int loc = static_cast<int>(fdiv_u32(static_cast<uint32_t>(i), div_c));
+        const int c = i - loc * num_classes;
+        const float* q = head + static_cast<long long>(loc) * ch;
+        const float s = sigmoid_acc(__ldg(q + 5 + c));
+        return center ? fmul(sigmoid_acc(__ldg(q + 4)), s) : s;
+    }
+    __device__ __forceinline__ void emit(int i, float s, int rank) const {
+        const int loc = static_cast<int>(fdiv_u32(static_cast<uint32_t>(i), div_c));
+        const int c = i - loc * num_classes;
+        const float* q = head + static_cast<long long>(loc) * ch;
+        CornerParams cp;
+        cp.mode = 0, cp.stride = stride;
+        const float4 o = corners_of(cp, loc / wl, loc % wl, 0, q[0], q[1], q[2], q[3]);
+        float* dst = out + static_cast<long long>(rank) * 6;
+        dst[0] = o.x, dst[1] = o.y, dst[2] = o.z, dst[3] = o.w, dst[4] = s, dst[5] = static_cast<float>(c);
+    }
+    __device__ __forceinline__ void pad(int rank) const {
+        float* dst = out + static_cast<long long>(rank) * 6;
+        dst[0] = dst[1] = dst[2] = dst[3] = 0.f, dst[4] = -INFINITY, dst[5] = 0.f;
+    }
+};
+
+struct FcosSelectArgs {
+    const float* head[DH_MAX_LEVELS];
+    int hl[DH_MAX_LEVELS], wl[DH_MAX_LEVELS];
+    float stride[DH_MAX_LEVELS];
+    int num_classes, center, k_slots, n_levels, inclusive;
+    float min_score;
+};
+__global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs a, float* __restrict__ cand /*[B, L*k, 6]*/) {
+    __shared__ SelShared sh;
+    const int b = blockIdx.y, l = blockIdx.x;
+    FcosSource src;
+    const int rows = a.hl[l] * a.wl[l];
+    src.ch = a.num_classes + 5, src.num_classes = a.num_classes, src.wl = a.wl[l], src.center = a.center, src.stride = a.stride[l];
+    src.head = a.head[l] + static_cast<long long>(b) * rows * src.ch;
+    src.out = cand + (static_cast<long long>(b) * a.n_levels + l) * a.k_slots * 6;
+    src.n = rows * a.num_classes;
+    src.div_c = make_fastdiv(static_cast<uint32_t>(a.num_classes));
+    select_core(sh, src, a.k_slots, a.min_score, a.inclusive);
 }
 
 static int grid_for(long long threads_needed, int block, int sm_count) {
@@ -371,6 +647,39 @@ static int grid_for(long long threads_needed, int block, int sm_count) {
     const long long cap = static_cast<long long>(sm_count) * 16;
     if (g > cap) g = cap;
     return static_cast<int>(g < 1 ? 1 : g);
+}
+
+int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batch, int pad_h, int pad_w, int n_levels,
+                       const int32_t* strides, int num_classes, int center, int k, float min_score, int inclusive, float* cand,
+                       cudaStream_t st) {
+    FcosSelectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.num_classes = num_classes, a.center = center, a.k_slots = k, a.n_levels = n_levels, a.inclusive = inclusive, a.min_score = min_score;
+    for (int l = 0; l < n_levels; ++l) {
+        a.head[l] = pred_levels[l];
+        a.hl[l] = static_cast<int>(static_cast<double>(pad_h) / strides[l]);
+        a.wl[l] = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
+        if (a.wl[l] < 1) a.wl[l] = 1, a.hl[l] = 0;
+        a.stride[l] = static_cast<float>(strides[l]);
+    }
+    dim3 grid(n_levels, batch);
+    fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return DH_OK;
+}
+
+int launch_select_segs(dh_handle_s* h, const float* dets, int batch, long long n_total, int row_floats, int score_col, const int* seg_off_host,
+                       int n_seg, int k, float min_score, int inclusive, float* out, int* overflow, cudaStream_t st) {
+    SelSegs segs;
+    memset(&segs, 0, sizeof(segs));
+    for (int s = 0; s <= n_seg; ++s) segs.off[s] = seg_off_host[s];
+    dim3 grid(n_seg, batch);
+    select_topk_segs_kernel<<<grid, kSelThreads, 0, st>>>(dets, n_total, row_floats, score_col, segs, k, min_score, inclusive, out, n_seg * k,
+                                                          overflow);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return DH_OK;
 }
 
 }  // namespace dh
@@ -435,13 +744,58 @@ int dh_retina_decode(dh_handle_t h, const float* const* pred_levels, int batch, 
     for (int l = 0; l < n_levels; ++l)
         n_total += static_cast<long long>(n_anchors) * static_cast<int>(static_cast<double>(pad_h) / strides[l]) *
                    static_cast<int>(static_cast<double>(pad_w) / strides[l]);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ch = num_classes + 4;
+    const size_t stream_smem = static_cast<size_t>(kDecWarps) * 2 * 32 * ch * 4 + kDecWarps * 2 * 8;
+    if (stream_smem <= 200 * 1024 && batch > 0) {  // streaming kernel: TMA-staged 32-row tiles, one lane per row
+        RetinaDecodeArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_levels = n_levels, a.n_anchors = n_anchors, a.num_classes = num_classes, a.ch = ch, a.n_total = n_total;
+        a.anchor_hw = anchor_hw_dev;
+        a.use_tma = (ch * 4) % 16 == 0 ? 1 : 0;
+        long long off = 0, tiles = 0;
+        for (int l = 0; l < n_levels; ++l) {
+            DH_CHECK_ARG(pred_levels[l] && strides[l] > 0, "dh_retina_decode: level %d", l);
+            const int hl = static_cast<int>(static_cast<double>(pad_h) / strides[l]), wl = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
+            a.head[l] = pred_levels[l];
+            a.cells[l] = hl * wl > 0 ? hl * wl : 1, a.wl[l] = wl > 0 ? wl : 1, a.stride[l] = static_cast<float>(strides[l]);
+            a.per_img[l] = n_anchors * hl * wl > 0 ? n_anchors * hl * wl : 1;
+            a.div_per_img[l] = make_fastdiv(static_cast<uint32_t>(a.per_img[l]));
+            a.div_cells[l] = make_fastdiv(static_cast<uint32_t>(a.cells[l]));
+            a.div_wl[l] = make_fastdiv(static_cast<uint32_t>(a.wl[l]));
+            DH_CHECK_ARG(static_cast<long long>(batch) * n_anchors * hl * wl < (1ll << 31), "dh_retina_decode: level %d has too many rows", l);
+            a.rows[l] = static_cast<long long>(batch) * n_anchors * hl * wl;
+            a.level_off[l] = off;
+            a.tile_begin[l] = tiles;
+            tiles += (a.rows[l] + 31) / 32;
+            off += static_cast<long long>(n_anchors) * hl * wl;
+            if (reinterpret_cast<uintptr_t>(pred_levels[l]) & 15u) a.use_tma = 0;
+        }
+        a.tile_begin[n_levels] = tiles;
+        if (tiles == 0) return DH_OK;
+        static bool attr_done = false;
+        if (!attr_done) {
+            DH_CUDA(cudaFuncSetAttribute(retina_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done = true;
+        }
+        int per_sm = 1;
+        DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, retina_decode_stream_kernel, kDecWarps * 32, stream_smem));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = static_cast<long long>(h->sm_count) * per_sm;
+        const long long need = (tiles + kDecWarps - 1) / kDecWarps;
+        if (grid > need) grid = need;
+        retina_decode_stream_kernel<<<static_cast<unsigned>(grid), kDecWarps * 32, stream_smem, st>>>(a, dets);
+        DH_CUDA(cudaGetLastError());
+        h->launches += 1;
+        return DH_OK;
+    }
     long long off = 0;
     for (int l = 0; l < n_levels; ++l) {
         DH_CHECK_ARG(pred_levels[l] && strides[l] > 0, "dh_retina_decode: level %d", l);
         const int hl = static_cast<int>(static_cast<double>(pad_h) / strides[l]), wl = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
         const long long rows = static_cast<long long>(batch) * n_anchors * hl * wl;
         if (rows > 0) {
-            retina_decode_kernel<<<grid_for(rows * 32, 256, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            retina_decode_kernel<<<grid_for(rows * 32, 256, h->sm_count), 256, 0, st>>>(
                 pred_levels[l], batch, n_anchors, hl, wl, num_classes, static_cast<float>(strides[l]),
                 anchor_hw_dev + static_cast<long long>(l) * n_anchors * 2, n_total, off, dets);
             DH_CUDA(cudaGetLastError());

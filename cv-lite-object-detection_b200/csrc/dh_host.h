@@ -18,6 +18,8 @@ struct dh_handle_s {
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
     size_t scratch_bytes;
+    void* scratch_b;      // second arena: intermediates of the multi-kernel pipelines (detect), which call into
+    size_t scratch_b_bytes;  // routines that use `scratch` themselves
     long long* phase_cycles;  // DH_OPT_PHASE_TIMING: device [8] counters (profiling aid)
     unsigned int* sched;      // ring of tile-scheduler counters (one per launch in flight)
     int sched_next;
@@ -28,6 +30,7 @@ namespace dh {
 int set_error(int code, const char* fmt, ...);
 // Ensure the handle's scratch holds at least `bytes`; returns device pointer or null (error set).
 void* scratch(dh_handle_s* h, size_t bytes);
+void* scratch_b(dh_handle_s* h, size_t bytes);
 // A zeroed (stream-ordered) device counter for one kernel's dynamic tile scheduler; null on error.
 unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st);
 

@@ -238,12 +238,13 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned
     if (tid == 0) n_keep[b] = s_kept;
 }
 
-// ---- lazy variant: kernels 2 + 3 fused, one CTA per image -------------------------------------------------
-// Suppression bits are computed only for the boxes that are actually kept: per 64-block the diagonal tile is
-// evaluated in parallel, one thread resolves the block's greedy chain, and the boxes it kept are tested against
-// every later, still-alive candidate.  With a small output cap (FCOS: 100 per class / 100 total) the sweep ends
-// after two or three blocks and the 12.5 M-pair mask matrix is never formed.
+// ---- lazy variant for capped outputs: kernels 2 + 3 fused, one CTA per image --------------------------------
+// With an output cap (FCOS: 100 per class / 100 total) the sweep ends after a few 64-blocks, so suppression is
+// evaluated only where the sweep actually goes: a block's candidates are first tested against the boxes kept so
+// far (held in shared memory, at most kLazyMaxKept), then the block's own 64x64 tile is evaluated and one thread
+// resolves its greedy chain.  The 12.5 M-pair mask matrix of a 5 000-candidate image is never formed.
 constexpr int kLazyThreads = 256;
+constexpr int kLazyMaxKept = 1024;
 __device__ __forceinline__ bool suppresses(const NmsParams& p, const float4& a, int ac, const float4& c, int cc) {
     if (p.per_class) return cc == ac && suppress_iou(a, c, p.iou_thr);
     return suppress_agnostic(a, c, p.iou_thr);
@@ -252,21 +253,21 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4* __
                                                                 const int* __restrict__ order, const int* __restrict__ n_cand, NmsParams p,
                                                                 int* __restrict__ keep, int* __restrict__ n_keep) {
     extern __shared__ int class_count[];  // [num_classes] when per-class caps are on
-    __shared__ unsigned removed[kNmsMaxN / 32];
+    __shared__ float4 kbox[kLazyMaxKept];
+    __shared__ int kcls[kLazyMaxKept];
     __shared__ unsigned long long diag[64];
-    __shared__ float4 bbox[64], kbox[64];
-    __shared__ int bcls[64], kcls[64];
-    __shared__ unsigned long long s_km;
+    __shared__ float4 bbox[64];
+    __shared__ int bcls[64];
+    __shared__ unsigned long long s_dead, s_km;
     __shared__ int s_kept, s_stop;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int m = n_cand[b];
     const int nblk = (m + 63) >> 6;
     const long long base = static_cast<long long>(b) * p.n_max;
     const bool caps = p.per_class && p.max_per_class > 0;
-    const int max_total = p.max_total > 0 ? min(p.max_total, p.max_out) : p.max_out;
+    const int max_total = min(p.max_total > 0 ? min(p.max_total, p.max_out) : p.max_out, kLazyMaxKept);
     if (caps)
         for (int c = tid; c < p.num_classes; c += kLazyThreads) class_count[c] = 0;
-    for (int w = tid; w < 2 * nblk; w += kLazyThreads) removed[w] = 0u;
     if (tid == 0) s_kept = 0, s_stop = (max_total <= 0);
     __syncthreads();
     for (int w = 0; w < nblk && !s_stop; ++w) {
@@ -276,9 +277,21 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4* __
             diag[tid] = 0ull;
             if (tid < nb) bbox[tid] = sorted_boxes[base + first + tid], bcls[tid] = sorted_cls[base + first + tid];
         }
+        if (tid == 0) s_dead = 0ull;
         __syncthreads();
-        const unsigned long long alive = ~((static_cast<unsigned long long>(removed[2 * w + 1]) << 32) | removed[2 * w]);
-        {  // diagonal tile: thread (r, q) tests row r against columns 16 q .. 16 q + 15 that come after it
+        {  // candidates of this block against everything kept so far: thread (c, part) walks a quarter of the kept list
+            const int c = tid >> 2, part = tid & 3;
+            if (c < nb) {
+                const float4 cb = bbox[c];
+                const int cc = bcls[c];
+                bool dead = false;
+                for (int q = part; q < kept_before && !dead; q += 4) dead = suppresses(p, kbox[q], kcls[q], cb, cc);
+                if (dead) atomicOr(&s_dead, 1ull << c);
+            }
+        }
+        __syncthreads();
+        const unsigned long long alive = ~s_dead;
+        {  // the block's own tile: thread (r, q) tests row r against columns 16 q .. 16 q + 15 that come after it
             const int r = tid >> 2, q = tid & 3;
             if (r < nb && ((alive >> r) & 1ull)) {
                 const float4 a = bbox[r];
@@ -302,7 +315,7 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4* __
                         class_count[c] += 1;
                     }
                 }
-                kbox[kept - kept_before] = bbox[r], kcls[kept - kept_before] = bcls[r];
+                kbox[kept] = bbox[r], kcls[kept] = bcls[r];
                 km |= 1ull << r;
                 rem |= diag[r];
                 if (++kept >= max_total) {
@@ -314,22 +327,8 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4* __
         }
         __syncthreads();
         const unsigned long long km = s_km;
-        const int nk = __popcll(km);
         if (tid < nb && ((km >> tid) & 1ull))
             keep[static_cast<long long>(b) * p.max_out + kept_before + __popcll(km & ((1ull << tid) - 1ull))] = order[base + first + tid];
-        if (!s_stop && nk > 0) {  // the kept boxes of this block against every later candidate that is still alive
-            for (int j0 = first + 64; j0 < m; j0 += kLazyThreads) {
-                const int j = j0 + tid;  // j0 is a multiple of 32: a warp covers exactly one `removed` word
-                bool sup = false;
-                if (j < m && !((removed[j >> 5] >> (j & 31)) & 1u)) {
-                    const float4 c = __ldg(sorted_boxes + base + j);
-                    const int cc = p.per_class ? __ldg(sorted_cls + base + j) : 0;
-                    for (int q = 0; q < nk && !sup; ++q) sup = suppresses(p, kbox[q], kcls[q], c, cc);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, sup);
-                if ((tid & 31) == 0 && bal) removed[j >> 5] |= bal;
-            }
-        }
         __syncthreads();
     }
     if (tid == 0) n_keep[b] = s_kept;
@@ -386,10 +385,9 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, sboxes, scls, order, ncand);
     DH_CUDA(cudaGetLastError());
     const size_t cap_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
-    // a small output cap ends the sweep after a few blocks, and a batch that fills the GPU gains nothing from the
-    // all-SM mask kernel: evaluate suppression lazily, one CTA per image
+    // a small output cap ends the sweep after a few blocks: evaluate suppression lazily, one CTA per image
     const int eff_total = max_total > 0 ? (max_total < max_out ? max_total : max_out) : max_out;
-    if (h->nms_kernel == 1 || (h->nms_kernel == 0 && (eff_total <= 512 || batch >= h->sm_count))) {
+    if (eff_total <= kLazyMaxKept && (h->nms_kernel == 1 || (h->nms_kernel == 0 && eff_total <= 512))) {
         nms_lazy_kernel<<<batch, kLazyThreads, cap_smem, st>>>(sboxes, scls, order, ncand, p, keep, n_keep);
         DH_CUDA(cudaGetLastError());
         h->launches += 2;

@@ -66,6 +66,8 @@ def lib():
         L.dh_select_topk.argtypes = [P, P, I, ctypes.c_longlong, I, I, P, I, I, F, I, P, P, P]
         L.dh_nms.argtypes = [P, P, P, I, I, I, I, F, F, I, I, I, I, P, I, P, P]
         D = ctypes.c_double
+        L.dh_fcos_detect.argtypes = [P, PP, I, I, I, I, c_ip, I, I, F, F, I, I, I, P, P, P, P, P, P]
+        L.dh_retina_detect.argtypes = [P, PP, I, I, I, I, c_ip, I, P, I, F, F, I, P, I, P, P, P, P, P]
         L.dh_compute_iou.argtypes = [P, P, I, P, I, P, P]
         L.dh_bboxes_iou.argtypes = [P, P, I, P, I, P, P]
         L.dh_centernet_nms.argtypes = [P, P, I, P, I, D, D, I, P, P, P, P]

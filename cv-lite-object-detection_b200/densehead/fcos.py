@@ -199,34 +199,29 @@ def decode_batch(head_outputs, num_classes, img_pad, strides=None, center=False,
 
 
 def detect_batch(head_outputs, num_classes, img_pad, center=False, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,
-                 max_total_size=100, pre_nms_topk=1000, strides=None):
-    """Decode -> per-level top-k of (location, class) scores above cls_thresh -> per-class greedy NMS with the
-    combined-NMS caps.  Returns zero-padded (boxes [B, T, 4], scores [B, T], classes [B, T], valid [B]) with
-    T = max_total_size, like tf.image.combined_non_max_suppression.  `pre_nms_topk` bounds the candidates per
-    level (the reference has none; a value >= the number of scores above the threshold reproduces it)."""
+                 max_total_size=100, pre_nms_topk=1000, strides=None, with_candidates=False, stream=None):
+    """FCOS/infer_fcos.py:27-62 for a batch, one library call (dh_fcos_detect): decode -> per-level top-k of the
+    (location, class) scores above cls_thresh -> per-class greedy NMS with the combined-NMS caps.  Returns zero-padded
+    (boxes [B, T, 4], scores [B, T], classes [B, T], valid [B]) with T = max_total_size, like
+    tf.image.combined_non_max_suppression.  `pre_nms_topk` bounds the candidates per level (the reference has none;
+    a value >= the number of scores above the threshold reproduces it)."""
     strides = list(DEFAULT_STRIDES if strides is None else strides)
-    boxes, scores = decode_batch(head_outputs, num_classes, img_pad, strides, center)
-    batch, n, c = (int(v) for v in scores.shape)
-    shapes = level_shapes(img_pad, strides)
-    seg = np.concatenate([[0], np.cumsum([h * w * c for h, w in shapes])])
-    k = int(min(pre_nms_topk, max(int(np.diff(seg).max()), 1)))
-    if k * len(strides) > infer.NMS_MAX_CANDIDATES:
-        raise ValueError("pre_nms_topk * levels exceeds the NMS capacity (%d)" % infer.NMS_MAX_CANDIDATES)
-    flat = scores.reshape(batch, n * c, 1)
-    sel, src = infer.select_topk(flat, seg, k, cls_thresh, score_inclusive=False, score_col=0, with_source=True)
-    src64 = src.clamp(min=0).to(torch.int64)
-    cand = torch.empty((batch, src.shape[1], 6), dtype=torch.float32, device=scores.device)
-    cand[..., :4] = torch.gather(boxes, 1, (src64 // c).unsqueeze(-1).expand(-1, -1, 4))
-    cand[..., 4] = sel[..., 0]
-    cand[..., 5] = (src64 % c).to(torch.float32)
-    keep, n_keep = infer.nms(cand, iou_thresh, mode=infer.NMS_PER_CLASS, min_score=cls_thresh, score_inclusive=False,
-                             num_classes=num_classes, max_per_class=max_detections, max_total=max_total_size,
-                             max_out=max_total_size)
-    t = int(max_total_size)
-    valid = (torch.arange(t, device=keep.device).unsqueeze(0) < n_keep.unsqueeze(1))
-    rows = torch.gather(cand, 1, keep.clamp(min=0).to(torch.int64).unsqueeze(-1).expand(-1, -1, 6))
-    rows = torch.where(valid.unsqueeze(-1), rows, torch.zeros_like(rows))
-    return rows[..., :4].contiguous(), rows[..., 4].contiguous(), rows[..., 5].contiguous(), n_keep
+    dev = current_device()
+    heads = _as_batched(head_outputs, dev)
+    batch, t = int(heads[0].shape[0]), int(max_total_size)
+    longest = max([h * w * int(num_classes) for h, w in level_shapes(img_pad, strides)] + [1])
+    k = int(min(pre_nms_topk, longest))
+    boxes = torch.empty((batch, t, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((batch, t), dtype=torch.float32, device=dev)
+    classes = torch.empty((batch, t), dtype=torch.float32, device=dev)
+    valid = torch.zeros((batch,), dtype=torch.int32, device=dev)
+    cand = torch.empty((batch, len(strides) * k, 6), dtype=torch.float32, device=dev) if with_candidates else None
+    _capi.check(_capi.lib().dh_fcos_detect(
+        _capi.handle(dev.index), _capi.ptr_array([h.data_ptr() for h in heads]), batch, int(img_pad[0]), int(img_pad[1]),
+        len(strides), _capi.int_array(strides), int(num_classes), 1 if center else 0, float(iou_thresh), float(cls_thresh),
+        int(max_detections), t, int(pre_nms_topk), boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(), valid.data_ptr(),
+        cand.data_ptr() if cand is not None else None, stream_ptr(stream)), "dh_fcos_detect")
+    return (boxes, scores, classes, valid, cand) if with_candidates else (boxes, scores, classes, valid)
 
 
 def image_detections(image, model, num_classes, center=False, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,

@@ -166,31 +166,40 @@ def decode_batch(head_outputs, num_classes, img_pad, anchor_hw=None, strides=Non
 
 
 def detect_batch(head_outputs, num_classes, img_pad, iou_thresh=0.5, cls_thresh=0.05, anchor_hw=None, strides=None,
-                 pre_nms_topk=None):
-    """Decode -> `score >= cls_thresh` (-> optional per-level top-k) -> class-agnostic greedy NMS.
-    Returns (dets [B, n, 6] candidate rows, keep int32 [B, n] candidate indices in kept order, n_keep [B])."""
+                 pre_nms_topk=None, with_rows=False, stream=None):
+    """retinanet_module.py:483-530 for a batch, one library call (dh_retina_detect): decode -> `score >= cls_thresh`
+    (-> optional per-level top-k) -> class-agnostic greedy NMS.  Returns (cand [B, n, 6] candidate rows, keep int32
+    [B, n] candidate indices in kept order, n_keep [B]); with_rows=True appends the kept rows [B, n, 6] themselves.
+    Without `pre_nms_topk` (the reference has none) at most 16384 / levels candidates per level reach the NMS; an
+    image with more raises ValueError."""
     strides = list(STRIDES if strides is None else strides)
     table = anchor_table() if anchor_hw is None else np.ascontiguousarray(anchor_hw, dtype=np.float32)
-    dets = decode_batch(head_outputs, num_classes, img_pad, table, strides)
     n_anchors = table.shape[1]
-    lens = [n_anchors * int(int(img_pad[0]) / s) * int(int(img_pad[1]) / s) for s in strides]
-    seg = np.concatenate([[0], np.cumsum(lens)])
-    if pre_nms_topk is None:
-        if dets.shape[1] > infer.NMS_MAX_CANDIDATES:  # compact the rows above the threshold, keeping their order
-            k = int(max(lens))
-            cand = infer.select_topk(dets, seg, k, cls_thresh, score_inclusive=True)
-            passing = int((cand[..., 4] >= cls_thresh).sum(dim=1).max().item())
-            if passing > infer.NMS_MAX_CANDIDATES:
-                raise ValueError("%d candidates above the score threshold exceed the NMS capacity of %d; pass pre_nms_topk"
-                                 % (passing, infer.NMS_MAX_CANDIDATES))
-            order = torch.argsort((cand[..., 4] < cls_thresh).to(torch.int8), dim=1, stable=True)[:, :max(passing, 1)]
-            cand = torch.gather(cand, 1, order.unsqueeze(-1).expand(-1, -1, 6)).contiguous()
-        else:
-            cand = dets
-    else:
-        cand = infer.select_topk(dets, seg, int(pre_nms_topk), cls_thresh, score_inclusive=True)
-    keep, n_keep = infer.nms(cand, iou_thresh, mode=infer.NMS_AGNOSTIC, min_score=cls_thresh, score_inclusive=True)
-    return cand, keep, n_keep
+    dev = current_device()
+    heads = _pack_levels(head_outputs, n_anchors, dev)
+    batch = int(heads[0].shape[0])
+    pad_h, pad_w = int(img_pad[0]), int(img_pad[1])
+    lens = [n_anchors * int(pad_h / s) * int(pad_w / s) for s in strides]
+    k = int(pre_nms_topk) if pre_nms_topk else infer.NMS_MAX_CANDIDATES // len(strides)
+    k = max(min(k, max(lens + [1])), 1)
+    n = len(strides) * k
+    if n > infer.NMS_MAX_CANDIDATES:
+        raise ValueError("pre_nms_topk * levels exceeds the NMS capacity (%d)" % infer.NMS_MAX_CANDIDATES)
+    rows = torch.empty((batch, n, 6), dtype=torch.float32, device=dev)
+    cand = torch.empty((batch, n, 6), dtype=torch.float32, device=dev)
+    keep = torch.empty((batch, n), dtype=torch.int32, device=dev)
+    n_keep = torch.zeros((batch,), dtype=torch.int32, device=dev)
+    overflow = torch.zeros((batch,), dtype=torch.int32, device=dev) if not pre_nms_topk else None
+    table_d = torch.from_numpy(table).to(dev)
+    _capi.check(_capi.lib().dh_retina_detect(
+        _capi.handle(dev.index), _capi.ptr_array([h.data_ptr() for h in heads]), batch, pad_h, pad_w, len(strides),
+        _capi.int_array(strides), n_anchors, table_d.data_ptr(), int(num_classes), float(iou_thresh), float(cls_thresh),
+        int(pre_nms_topk or 0), rows.data_ptr(), n, n_keep.data_ptr(), overflow.data_ptr() if overflow is not None else None,
+        cand.data_ptr(), keep.data_ptr(), stream_ptr(stream)), "dh_retina_detect")
+    if overflow is not None and bool(overflow.any().item()):
+        raise ValueError("more than %d candidates above the score threshold on one level exceed the NMS capacity; "
+                         "pass pre_nms_topk" % k)
+    return (cand, keep, n_keep, rows) if with_rows else (cand, keep, n_keep)
 
 
 class RetinaNetHead:

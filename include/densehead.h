@@ -50,7 +50,7 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_CTAS_PER_SM 3 /* upper bound on persistent CTAs per SM (default 4; shared memory may allow fewer) */
 #define DH_OPT_PHASE_TIMING 4 /* profiling aid: 1 = CTA 0 of each encode kernel accumulates per-phase clock64 totals; (re)sets them */
 #define DH_OPT_FUSED_LOSS_KERNEL 5 /* 0 (default): stream + correct kernel when num_classes <= 128; 1: always the shared-memory target-tile kernel */
-#define DH_OPT_NMS_KERNEL 6 /* 0 (default): pick per call; 1: lazy one-CTA-per-image NMS; 2: mask matrix on all SMs + block sweep */
+#define DH_OPT_NMS_KERNEL 6 /* 0 (default): pick per call; 1: lazy one-CTA-per-image NMS whenever the output cap is <= 1024; 2: always mask matrix on all SMs + block sweep */
 int dh_set_option(dh_handle_t h, int option, int value);
 /* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in
  * {stage GT + records, candidates + buffer recycle, emit rows, hand-off to TMA, drain}, out8[5] = tiles. */
@@ -228,6 +228,33 @@ int dh_nms(dh_handle_t h, const float* dets /*[dev]*/, const int32_t* n_valid /*
            int n_max, int row_floats, int mode, float iou_thr, float min_score, int score_inclusive,
            int num_classes, int max_per_class, int max_total,
            int32_t* keep /*[dev] [B,max_out]*/, int max_out, int32_t* n_keep /*[dev] [B]*/, void* stream);
+
+/* Whole-image pipelines: head outputs in, final detections out, in one call (all intermediates live in the handle's
+ * scratch; nothing synchronises with the host).
+ *
+ * dh_fcos_detect = image_detections of FCOS/infer_fcos.py:27-62.  Scores are sigmoid(class) (times
+ * sigmoid(centerness) when center != 0); per level the pre_nms_topk best (location, class) pairs with score > cls_thr
+ * go to the per-class NMS with caps (see DH_NMS_PER_CLASS).  Outputs have the layout of
+ * tf.image.combined_non_max_suppression: boxes [B,T,4], scores [B,T], classes [B,T] zero padded, valid [B], with
+ * T = max_total.  pre_nms_topk >= the number of passing pairs reproduces the reference (which has no top-k).
+ * out_cand (optional) receives the candidate rows [B, n_levels*k, 6], k = min(pre_nms_topk, longest level). */
+int dh_fcos_detect(dh_handle_t h, const float* const* pred_levels /*[host] n_levels [dev] ptrs [B,Hl,Wl,C+5]*/, int batch,
+                   int pad_h, int pad_w, int n_levels, const int32_t* strides /*[host]*/, int num_classes, int center,
+                   float iou_thr, float cls_thr, int max_per_class, int max_total, int pre_nms_topk,
+                   float* out_boxes /*[dev] [B,T,4]*/, float* out_scores /*[dev] [B,T]*/, float* out_classes /*[dev] [B,T]*/,
+                   int32_t* out_valid /*[dev] [B]*/, float* out_cand /*[dev] or NULL*/, void* stream);
+
+/* dh_retina_detect = RetinaNet.image_detections of RetinaNet/retinanet_module.py:483-530 for a batch: rows
+ * (y1, x1, y2, x2, score, label) in kept (score-descending) order, out_rows [B, max_out, 6] zero padded, out_n [B].
+ * pre_nms_topk > 0 keeps that many candidates per level; 0 = threshold only like the reference, limited to
+ * 16384 / n_levels candidates per level -- out_overflow [B] (optional) gets 1 where an image had more.
+ * out_cand [B, n_levels*k, 6] / out_keep [B, max_out] (optional) receive the candidates and the kept indices. */
+int dh_retina_detect(dh_handle_t h, const float* const* pred_levels /*[host] n_levels [dev] ptrs [B,A,Hl,Wl,C+4]*/, int batch,
+                     int pad_h, int pad_w, int n_levels, const int32_t* strides /*[host]*/, int n_anchors,
+                     const float* anchor_hw /*[dev] [n_levels,n_anchors,2]*/, int num_classes, float iou_thr, float cls_thr,
+                     int pre_nms_topk, float* out_rows /*[dev]*/, int max_out, int32_t* out_n /*[dev] [B]*/,
+                     int32_t* out_overflow /*[dev] [B] or NULL*/, float* out_cand /*[dev] or NULL*/, int32_t* out_keep /*[dev] or NULL*/,
+                     void* stream);
 
 /* Pairwise IoU of centre-size boxes (c0, c1, size0, size1), float32: compute_iou of RetinaNet/utils.py:42-83
  * (union floored at 1e-8, result clipped to [0, 1]).  out is [n, m]. */
