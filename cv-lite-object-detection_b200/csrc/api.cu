@@ -98,6 +98,7 @@ int dh_create(dh_handle_t* out, int device) {
     h->ctas_per_sm = 4;
     h->fused_loss_kernel = 0;
     h->nms_kernel = 0;
+    h->fcos_select_exact_only = 0;
     h->launches = 0;
     h->scratch = nullptr;
     h->scratch_bytes = 0;
@@ -144,6 +145,10 @@ int dh_set_option(dh_handle_t h, int option, int value) {
         case DH_OPT_NMS_KERNEL:
             DH_CHECK_ARG(value >= 0 && value <= 2, "DH_OPT_NMS_KERNEL must be 0, 1 or 2");
             h->nms_kernel = value;
+            return DH_OK;
+        case DH_OPT_FCOS_SELECT:
+            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_FCOS_SELECT must be 0 or 1");
+            h->fcos_select_exact_only = value;
             return DH_OK;
         case DH_OPT_PHASE_TIMING: {
             dh::DeviceGuard g(h->device);

@@ -606,6 +606,10 @@ struct FcosSource {
         const float s = sigmoid_acc(__ldg(q + 5 + c));
         return center ? fmul(sigmoid_acc(__ldg(q + 4)), s) : s;
     }
+    __device__ __forceinline__ float logit(int i) const {
+        const int loc = static_cast<int>(fdiv_u32(static_cast<uint32_t>(i), div_c));
+        return __ldg(head + static_cast<long long>(loc) * ch + 5 + (i - loc * num_classes));
+    }
     __device__ __forceinline__ void emit(int i, float s, int rank) const {
         const int loc = static_cast<int>(fdiv_u32(static_cast<uint32_t>(i), div_c));
         const int c = i - loc * num_classes;
@@ -622,11 +626,163 @@ struct FcosSource {
     }
 };
 
+// Without centerness the score is a non-decreasing function of the class logit, so the three passes of the
+// selector can run on raw logits (no transcendental per element).  Exactness needs care in two places where distinct
+// logits collide after the float32 sigmoid: (1) the score threshold -- logits within 1e-3 of logit(thr) are decided
+// with the real sigmoid; (2) ties at the k-th score must be cut by index -- the entries ranked exactly in shared
+// memory are those of the boundary bin AND of enough neighbouring bins that no score tie can reach outside them
+// (sigmoid_collision_floor bounds how far below a logit a colliding logit can lie).  Returns false (nothing
+// written) when the shortcut does not apply; the caller then runs the generic exact selector.
+__device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const FcosSource& src, int k_slots, float min_score, int inclusive) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = src.n;
+    const int k = min(k_slots, max(n, 0));
+    if (src.center || !(min_score > 1.0e-6f && min_score < 0.999f) || k <= 0) return false;
+    const float x_thr = logf(min_score / (1.0f - min_score));
+    const float thr_lo = x_thr - 1.0e-3f, thr_hi = x_thr + 1.0e-3f;
+    constexpr float kScale = 4096.0f / 24.0f;  // bins of 0.0059 logit units from the threshold upwards
+    auto score_passes = [&](float sc) { return inclusive ? (sc >= min_score) : (sc > min_score); };
+    auto passes_x = [&](float x) { return x > thr_hi ? true : (x >= thr_lo ? score_passes(sigmoid_acc(x)) : false); };
+    auto bin_x = [&](float x) {
+        const float t = (x - thr_lo) * kScale;
+        return t <= 0.f ? 0 : (t >= 4095.f ? 4095 : static_cast<int>(t));
+    };
+    constexpr int U = 8;
+    for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
+    if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0, sh.n_pass = 0, sh.t_key = 0u, sh.t_idx = 0x7fffffff;
+    __syncthreads();
+    for (int base = 0; base < n; base += kSelThreads * U) {
+        float x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * kSelThreads + tid;
+            x[u] = i < n ? src.logit(i) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (passes_x(x[u])) atomicAdd(&sh.hist[bin_x(x[u])], 1u);
+    }
+    __syncthreads();
+    find_boundary(sh, 4096, static_cast<unsigned>(k), tid);
+    const bool take_all = sh.bin == 0xFFFFFFFFu;  // fewer than k pass
+    int lo_bin = 0, hi_bin = 4095;
+    if (!take_all) {
+        if (tid == 0) {
+            const int Bk = static_cast<int>(sh.bin);
+            const float lo_edge = thr_lo + static_cast<float>(Bk) / kScale, hi_edge = thr_lo + static_cast<float>(Bk + 1) / kScale;
+            const int below = static_cast<int>(ceilf((lo_edge - sigmoid_collision_floor(lo_edge)) * kScale)) + 1;
+            int beyond = -1;
+            for (int t = 1; t <= 8 && beyond < 0; ++t)
+                if (sigmoid_collision_floor(hi_edge + static_cast<float>(t) / kScale) > hi_edge) beyond = t + 1;
+            const int lo = max(Bk - below, 0), hi = Bk + beyond;
+            bool ok = beyond > 0 && hi < 4095;
+            unsigned inside = 0, between = 0;
+            if (ok) {
+                for (int q = lo; q <= hi; ++q) inside += sh.hist[q];
+                for (int q = Bk + 1; q <= hi; ++q) between += sh.hist[q];
+                ok = inside <= kSelListCap;
+            }
+            sh.wtot[1][0] = ok ? 1u : 0u, sh.wtot[1][1] = static_cast<unsigned>(lo), sh.wtot[1][2] = static_cast<unsigned>(hi);
+            sh.need = static_cast<unsigned>(k) - (sh.above - between);
+        }
+        __syncthreads();
+        if (!sh.wtot[1][0]) {
+            __syncthreads();
+            return false;
+        }
+        lo_bin = static_cast<int>(sh.wtot[1][1]), hi_bin = static_cast<int>(sh.wtot[1][2]);
+        const unsigned need = sh.need;
+        // collect the entries that can tie with the k-th score, with their exact scores
+        for (int base = 0; base < n; base += kSelThreads * U) {
+            float x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kSelThreads + tid;
+                x[u] = i < n ? src.logit(i) : -INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!passes_x(x[u])) continue;
+                const int bn = bin_x(x[u]);
+                if (bn < lo_bin || bn > hi_bin) continue;
+                const unsigned slot = atomicAdd(&sh.n_list, 1u);
+                sh.list_key[slot] = score_key(sigmoid_acc(x[u])), sh.list_idx[slot] = base + u * kSelThreads + tid;
+            }
+        }
+        __syncthreads();
+        const int n_list = static_cast<int>(sh.n_list);
+        for (int e = tid; e < n_list; e += kSelThreads) {
+            const unsigned ke = sh.list_key[e];
+            const int ie = sh.list_idx[e];
+            unsigned rank = 0;
+            for (int f = 0; f < n_list; ++f) {
+                const unsigned kf = sh.list_key[f];
+                rank += (kf > ke || (kf == ke && sh.list_idx[f] < ie)) ? 1u : 0u;
+            }
+            if (rank == need - 1) sh.t_key = ke, sh.t_idx = ie;
+        }
+        __syncthreads();
+    }
+    const unsigned T_key = sh.t_key;
+    const int T_idx = sh.t_idx;
+    // ordered compaction
+    unsigned carry = 0;
+    int it = 0;
+    for (int base = 0; base < n; base += kSelThreads * kSelItems, ++it) {
+        const int i0 = base + tid * kSelItems;
+        float x[kSelItems];
+#pragma unroll
+        for (int u = 0; u < kSelItems; ++u) x[u] = (i0 + u < n) ? src.logit(i0 + u) : -INFINITY;
+        unsigned flags = 0;
+#pragma unroll
+        for (int u = 0; u < kSelItems; ++u) {
+            if (!passes_x(x[u])) continue;
+            bool take = take_all;
+            if (!take) {
+                const int bn = bin_x(x[u]);
+                if (bn > hi_bin) take = true;
+                else if (bn >= lo_bin) {
+                    const unsigned key = score_key(sigmoid_acc(x[u]));
+                    take = key > T_key || (key == T_key && i0 + u <= T_idx);
+                }
+            }
+            if (take) flags |= 1u << u;
+        }
+        const unsigned mine = __popc(flags);
+        unsigned incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        unsigned* wt = sh.wtot[it & 1];
+        if (lane == 31) wt[warp] = incl;
+        __syncthreads();
+        unsigned before = carry, tot = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) {
+            const unsigned v = wt[w];
+            if (w < warp) before += v;
+            tot += v;
+        }
+        unsigned rank = before + incl - mine;
+#pragma unroll
+        for (int u = 0; u < kSelItems; ++u) {
+            if (!((flags >> u) & 1u)) continue;
+            if (rank < static_cast<unsigned>(k)) src.emit(i0 + u, sigmoid_acc(x[u]), static_cast<int>(rank));
+            ++rank;
+        }
+        carry += tot;
+    }
+    const unsigned filled = min(static_cast<unsigned>(k), carry);
+    for (int r = filled + tid; r < k_slots; r += kSelThreads) src.pad(r);
+    return true;
+}
+
 struct FcosSelectArgs {
     const float* head[DH_MAX_LEVELS];
     int hl[DH_MAX_LEVELS], wl[DH_MAX_LEVELS];
     float stride[DH_MAX_LEVELS];
-    int num_classes, center, k_slots, n_levels, inclusive;
+    int num_classes, center, k_slots, n_levels, inclusive, allow_logit_space;
     float min_score;
 };
 __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs a, float* __restrict__ cand /*[B, L*k, 6]*/) {
@@ -639,6 +795,7 @@ __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs
     src.out = cand + (static_cast<long long>(b) * a.n_levels + l) * a.k_slots * 6;
     src.n = rows * a.num_classes;
     src.div_c = make_fastdiv(static_cast<uint32_t>(a.num_classes));
+    if (a.allow_logit_space && fcos_select_logit_space(sh, src, a.k_slots, a.min_score, a.inclusive)) return;
     select_core(sh, src, a.k_slots, a.min_score, a.inclusive);
 }
 
@@ -655,6 +812,7 @@ int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batc
     FcosSelectArgs a;
     memset(&a, 0, sizeof(a));
     a.num_classes = num_classes, a.center = center, a.k_slots = k, a.n_levels = n_levels, a.inclusive = inclusive, a.min_score = min_score;
+    a.allow_logit_space = h->fcos_select_exact_only ? 0 : 1;
     for (int l = 0; l < n_levels; ++l) {
         a.head[l] = pred_levels[l];
         a.hl[l] = static_cast<int>(static_cast<double>(pad_h) / strides[l]);

@@ -172,6 +172,37 @@ def test_c4_shaped_detection_pipelines():
         assert np.array_equal(oc[b].cpu().numpy(), wc)
 
 
+@pytest.mark.parametrize("case", ["plain", "quantised ties", "saturated", "few pass", "threshold edge"])
+def test_fcos_select_logit_space_equals_exact_scoring(case):
+    """dh_fcos_detect selects candidates on raw logits when it can (no sigmoid per element); the candidate rows and the
+    final detections must be bit-identical to the path that scores every (location, class) pair (DH_OPT_FCOS_SELECT=1),
+    including where distinct logits collide after the float32 sigmoid and ties are cut by index."""
+    dh = _dh()
+    B = 2
+    heads = synth.fcos_predictions(B, 256, 20, synth.seed_for(4, 90))
+    for h in heads:
+        x = h[..., 5:] * 2.5 + 6.9
+        if case == "quantised ties":
+            x = np.round(x * 8) / 8
+        elif case == "saturated":
+            x = x + 14.0                      # thousands of scores round to exactly 1.0 or within a few ulps of it
+        elif case == "few pass":
+            x = x - 6.0
+        elif case == "threshold edge":
+            x = np.where(np.abs(x + 2.9444) < 0.2, np.float32(-2.9444389) + np.round((x + 2.9444) * 1e7) * np.float32(2.4e-7), x)
+        h[..., 5:] = x.astype(np.float32)
+    out = []
+    for exact_only in (0, 1):
+        dh.set_option(0, 7, exact_only)
+        try:
+            out.append([t.cpu().numpy() for t in dh.fcos.detect_batch(heads, 20, [256, 256], pre_nms_topk=300, with_candidates=True)])
+        finally:
+            dh.set_option(0, 7, 0)
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+    assert np.isfinite(out[0][4][..., 4]).any() or case == "few pass"
+
+
 def test_compute_iou_and_bboxes_iou(golden):
     dh = _dh()
     k = golden("kat")
