@@ -429,7 +429,22 @@ def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
     entry("c3_retina_unfused_loss_b64", batch, 2 * nbytes, secs, "focal + smooth-L1 over materialised targets")
     secs = graph_time(lambda: retinanet.encode_loss_batch(b, n, d, 80, [640, 640], pred))
     entry("c3_retina_fused_encode_loss_b64", batch, nbytes, secs, "targets never reach HBM")
-    del outs, pred
+    grads = [torch.empty_like(p) for p in pred]
+    from densehead import _capi as capi
+    from densehead._tensors import stream_ptr
+    table = retinanet.anchor_table()
+    hnd, st_ = capi.handle(dev.index), [8, 16, 32, 64, 128]
+    opi, otot, opr = torch.empty((batch, 4), device=dev), torch.empty(4, device=dev), torch.empty(batch, dtype=torch.int32, device=dev)
+    def fwd_bwd():
+        capi.check(capi.lib().dh_retina_encode_loss_grad(
+            hnd, b.data_ptr(), n.data_ptr(), d.data_ptr(), batch, int(b.shape[1]), 640, 640, 5, capi.int_array(st_), 9,
+            capi.float_array(table.reshape(-1).tolist()), 0.5, 80, capi.ptr_array([p.data_ptr() for p in pred]), 0.25, 2.0, 1.0,
+            1.0, 1.0, capi.ptr_array([g.data_ptr() for g in grads]), opi.data_ptr(), otot.data_ptr(), opr.data_ptr(),
+            stream_ptr(None)), "dh_retina_encode_loss_grad")
+    secs = graph_time(fwd_bwd)
+    entry("c3_retina_fused_encode_loss_and_grad_b64", batch, 2 * nbytes, secs,
+          "forward + d loss / d pred in one pass: one read of the predictions, one write of the gradient")
+    del outs, pred, grads
     torch.cuda.empty_cache()
     # C4: inference decode + per-level top-k (1000) + NMS, batch 64, COCO-shaped heads (eager timing: the pipeline
     # sizes one intermediate from a device-side count)

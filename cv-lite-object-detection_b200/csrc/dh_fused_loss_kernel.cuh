@@ -50,9 +50,11 @@ __device__ __forceinline__ float rcp_unit_newton(float w) {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-// label == 0 element: acc += sigmoid(x)^gamma * softplus(x) / ln 2   (the caller scales by (1 - alpha) * ln 2)
-template <bool kGamma2, bool kNewton>
-__device__ __forceinline__ void stream_term(float x, float gamma, float& acc) {
+// label == 0 element: acc += sigmoid(x)^gamma * softplus(x) / ln 2   (the caller scales by (1 - alpha) * ln 2).
+// With kGrad the derivative of sigmoid^gamma * softplus is returned too (natural units; the caller scales by
+// (1 - alpha) * w_cls):  d/dx = s^g * (g * (1 - s) * softplus(x) + s).
+template <bool kGamma2, bool kNewton, bool kGrad>
+__device__ __forceinline__ float stream_term(float x, float gamma, float& acc) {
     const float u = x * kLog2e;
     const float e = ex2_fast(-fabsf(u));  // exp(-|x|)
     const float w = 1.0f + e;
@@ -60,7 +62,11 @@ __device__ __forceinline__ void stream_term(float x, float gamma, float& acc) {
     const float lg = lg2_fast(w);                    // log2(1 + exp(-|x|))
     const float s = (x < 0.f ? e : 1.0f) * inv;      // sigmoid(x)
     const float pw = kGamma2 ? s * s : ex2_fast(gamma * lg2_fast(s));
-    acc = fmaf(pw, lg + fmaxf(u, 0.f), acc);         // softplus(x) / ln 2 = lg + max(x, 0) * log2(e)
+    const float sp2 = lg + fmaxf(u, 0.f);            // softplus(x) / ln 2
+    acc = fmaf(pw, sp2, acc);
+    if (!kGrad) return 0.f;
+    const float om = (x < 0.f ? 1.0f : e) * inv;     // 1 - sigmoid(x)
+    return pw * fmaf((kGamma2 ? 2.0f : gamma) * kLn2 * om, sp2, s);
 }
 // smooth-L1(0, sigmoid(x)): the centerness term of an all-zero row (FCOS/fcos.py:483-486)
 __device__ __forceinline__ float cen_l1_zero(float x, float delta) {
@@ -91,19 +97,22 @@ struct StreamAcc {
 // ---- the label-free pass over one warp tile: rows [0, nrows) x ch floats starting at `p` --------------------
 // Lane l takes items l, l + 32, l + 64, ... (an item = one 128-bit load in the vector pass, one float in the
 // scalar pass); `c` tracks the item's position inside its row incrementally (no division in the loop).
-template <bool kGamma2>
-__device__ __forceinline__ void stream_vec_item(const float4& x, int c4, float gamma, StreamAcc& a) {
+template <bool kGamma2, bool kGrad>
+__device__ __forceinline__ void stream_vec_item(const float4& x, int c4, float gamma, float gscale, StreamAcc& a, float4* g) {
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c4 != 0) {  // float4 0 of a row = the 4 regression channels
-        stream_term<kGamma2, false>(x.x, gamma, a.c0);
-        stream_term<kGamma2, true>(x.y, gamma, a.c1);
-        stream_term<kGamma2, false>(x.z, gamma, a.c2);
-        stream_term<kGamma2, true>(x.w, gamma, a.c3);
+        d.x = stream_term<kGamma2, false, kGrad>(x.x, gamma, a.c0);
+        d.y = stream_term<kGamma2, true, kGrad>(x.y, gamma, a.c1);
+        d.z = stream_term<kGamma2, false, kGrad>(x.z, gamma, a.c2);
+        d.w = stream_term<kGamma2, true, kGrad>(x.w, gamma, a.c3);
     }
+    if (kGrad) __stcs(g, make_float4(d.x * gscale, d.y * gscale, d.z * gscale, d.w * gscale));
 }
-template <bool kGamma2, int U>
-__device__ __forceinline__ void stream_vec(const float* __restrict__ p, int nrows, int vpr, int c4, int step, int lane,
-                                           float gamma, StreamAcc& a) {
+template <bool kGamma2, bool kGrad, int U>
+__device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int c4, int step,
+                                           int lane, float gamma, float gscale, StreamAcc& a) {
     const float4* __restrict__ base = reinterpret_cast<const float4*>(p) + lane;
+    float4* __restrict__ gbase = reinterpret_cast<float4*>(gout) + lane;
     const int n_mine = (nrows * vpr - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
     int k = 0;
 #pragma unroll 1
@@ -113,7 +122,7 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, int nrow
         for (int u = 0; u < U; ++u) x[u] = __ldcs(base + 32 * (k + u));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            stream_vec_item<kGamma2>(x[u], c4, gamma, a);
+            stream_vec_item<kGamma2, kGrad>(x[u], c4, gamma, gscale, a, gbase + 32 * (k + u));
             c4 += step;
             if (c4 >= vpr) c4 -= vpr;
         }
@@ -121,26 +130,35 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, int nrow
 #pragma unroll 1
     for (; k < n_mine; ++k) {
         const float4 x = __ldcs(base + 32 * k);
-        stream_vec_item<kGamma2>(x, c4, gamma, a);
+        stream_vec_item<kGamma2, kGrad>(x, c4, gamma, gscale, a, gbase + 32 * k);
         c4 += step;
         if (c4 >= vpr) c4 -= vpr;
     }
 }
 
-template <bool kGamma2, bool kNewton>
-__device__ __forceinline__ void stream_scalar_item(float x, int c, const LossSpec& sp, float& cls_acc, StreamAcc& a) {
-    if (c < sp.reg_ch) return;
-    if (c == sp.reg_ch && sp.cen_mode != 0) {
-        if (sp.cen_mode == 1) a.cen += cen_l1_zero(x, sp.delta);
-        else if (sp.cen_mode == 2) a.cen += focal_term(0.f, x, sp.alpha, sp.gamma);
-    } else {
-        stream_term<kGamma2, kNewton>(x, sp.gamma, cls_acc);
+template <bool kGamma2, bool kNewton, bool kGrad>
+__device__ __forceinline__ void stream_scalar_item(float x, int c, const LossSpec& sp, float& cls_acc, StreamAcc& a, float* g) {
+    float d = 0.f;
+    if (c >= sp.reg_ch) {
+        if (c == sp.reg_ch && sp.cen_mode != 0) {
+            if (sp.cen_mode == 1) {
+                a.cen += cen_l1_zero(x, sp.delta);
+                if (kGrad) d = sp.w_cen * cen_l1_grad(0.f, x, sp.delta);
+            } else if (sp.cen_mode == 2) {
+                a.cen += focal_term(0.f, x, sp.alpha, sp.gamma);
+                if (kGrad) d = sp.w_cen * focal_grad(0.f, x, sp.alpha, sp.gamma);
+            }
+        } else {
+            d = stream_term<kGamma2, kNewton, kGrad>(x, sp.gamma, cls_acc) * ((1.0f - sp.alpha) * sp.w_cls);
+        }
     }
+    if (kGrad) __stcs(g, d);
 }
-template <bool kGamma2, int U>
-__device__ __forceinline__ void stream_scalar(const float* __restrict__ p, int nrows, int ch, int c, int step, int lane,
-                                              const LossSpec& sp, StreamAcc& a) {
+template <bool kGamma2, bool kGrad, int U>
+__device__ __forceinline__ void stream_scalar(const float* __restrict__ p, float* __restrict__ gout, int nrows, int ch, int c, int step,
+                                              int lane, const LossSpec& sp, StreamAcc& a) {
     const float* __restrict__ base = p + lane;
+    float* __restrict__ gbase = gout + lane;
     const int n_mine = (nrows * ch - lane + 31) >> 5;
     int k = 0;
 #pragma unroll 1
@@ -150,15 +168,15 @@ __device__ __forceinline__ void stream_scalar(const float* __restrict__ p, int n
         for (int u = 0; u < U; ++u) x[u] = __ldcs(base + 32 * (k + u));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (u & 1) stream_scalar_item<kGamma2, true>(x[u], c, sp, a.c1, a);
-            else stream_scalar_item<kGamma2, false>(x[u], c, sp, a.c0, a);
+            if (u & 1) stream_scalar_item<kGamma2, true, kGrad>(x[u], c, sp, a.c1, a, gbase + 32 * (k + u));
+            else stream_scalar_item<kGamma2, false, kGrad>(x[u], c, sp, a.c0, a, gbase + 32 * (k + u));
             c += step;
             if (c >= ch) c -= ch;
         }
     }
 #pragma unroll 1
     for (; k < n_mine; ++k) {
-        stream_scalar_item<kGamma2, false>(__ldcs(base + 32 * k), c, sp, a.c2, a);
+        stream_scalar_item<kGamma2, false, kGrad>(__ldcs(base + 32 * k), c, sp, a.c2, a, gbase + 32 * k);
         c += step;
         if (c >= ch) c -= ch;
     }
@@ -166,8 +184,8 @@ __device__ __forceinline__ void stream_scalar(const float* __restrict__ p, int n
 
 // The owner lane of a matched row: box-regression loss + (term(y, x) - term(0, x)) for the labelled channels.
 // Rare (well under 1 % of the rows), so it is kept out of line: its registers do not weigh on the streaming loop.
-__device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __restrict__ prow, CompactSink sink, float gy,
-                                            float gx) {
+__device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __restrict__ prow, float* __restrict__ grow, CompactSink sink,
+                                            float gy, float gx) {
     const int cls0 = sp.reg_ch + (sp.cen_mode != 0 ? 1 : 0);
     LossAcc acc = {0.f, 0.f, 0.f, 1};
     float x[4];
@@ -176,15 +194,27 @@ __device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __r
     if (sp.reg_mode == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc.reg += smooth_l1_term(sink.r[k], x[k], sp.delta);
+        if (grow) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) grow[k] = sp.w_reg * smooth_l1_grad(sink.r[k], x[k], sp.delta);
+        }
     } else {
         acc.reg += iou_loss_term(sink.r, x, gy, gx);
+        if (grow) {
+            float g[4];
+            iou_loss_grad(sink.r, x, gy, gx, g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) grow[k] = sp.w_reg * g[k];
+        }
     }
     if (sp.cen_mode == 1) {
         const float s = sigmoid_f(prow[4]);
         acc.cen += smooth_l1_term(sink.r[4], s, sp.delta) - smooth_l1_term(0.f, s, sp.delta);
+        if (grow) grow[4] = sp.w_cen * cen_l1_grad(sink.r[4], prow[4], sp.delta);
     } else if (sp.cen_mode == 2) {
         const float xc = prow[4];
         acc.cen += focal_term(sink.r[4], xc, sp.alpha, sp.gamma) - focal_term(0.f, xc, sp.alpha, sp.gamma);
+        if (grow) grow[4] = sp.w_cen * focal_grad(sink.r[4], xc, sp.alpha, sp.gamma);
     }
 #pragma unroll 1
     for (int wd = 0; wd < kCompactClassWords; ++wd) {
@@ -195,6 +225,7 @@ __device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __r
             m &= m - 1;
             const float xc = prow[cls0 + c];
             acc.cls += focal_term(1.0f, xc, sp.alpha, sp.gamma) - focal_term(0.f, xc, sp.alpha, sp.gamma);
+            if (grow) grow[cls0 + c] = sp.w_cls * focal_grad(1.0f, xc, sp.alpha, sp.gamma);
         }
     }
     return acc;
@@ -202,12 +233,15 @@ __device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __r
 
 // This warp's slice of tile `cur`: rows [r0, r0 + nrows) of map ti.m, or nrows <= 0 when the tile has fewer rows.
 template <class P>
-__device__ __forceinline__ const float* warp_tile(const LossArgs<P>& a, const TileCursor& cur, int img, int warp, TileInfo& ti) {
+__device__ __forceinline__ const float* warp_tile(const LossArgs<P>& a, const TileCursor& cur, int img, int warp, TileInfo& ti,
+                                                  float** grad = nullptr) {
     cursor_info(a.tt, cur, ti);
     ti.nrows = min(32, ti.nrows - 32 * warp);
     ti.r0 += 32 * warp;
     const MapDesc& md = a.tt.maps[ti.m];
-    return md.pred + static_cast<long long>(img) * md.image_stride + static_cast<long long>(ti.r0) * a.tt.ch;
+    const long long off = static_cast<long long>(img) * md.image_stride + static_cast<long long>(ti.r0) * a.tt.ch;
+    if (grad) *grad = a.grad_maps[ti.m] ? a.grad_maps[ti.m] + off : nullptr;
+    return md.pred + off;
 }
 
 // ---- correct: the rows of this warp's tiles that receive targets ------------------------------------------------
@@ -223,7 +257,8 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
 #pragma unroll 1
     for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
         TileInfo ti;
-        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti);
+        float* gg = nullptr;
+        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, &gg);
         if (ti.nrows <= 0) continue;
         const MapDesc& md = a.tt.maps[ti.m];
         if (ti.m != cur_m) {  // entering another map: the boxes that can match it at all (tile-independent tests)
@@ -260,7 +295,8 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
             if (pairs > 0) {
                 const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
                 const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
-                const LossAcc d = correct_row(a.spec, gp + lane * a.tt.ch, sink, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                const LossAcc d = correct_row(a.spec, gp + lane * a.tt.ch, gg ? gg + lane * a.tt.ch : nullptr, sink, static_cast<float>(i),
+                                              static_cast<float>(cell - i * md.width));
                 acc.cls += d.cls, acc.reg += d.reg, acc.cen += d.cen, acc.npos += d.npos;
             }
         }
@@ -271,24 +307,25 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
 }
 
 // ---- stream: every element of this warp's tiles as if its label were zero -----------------------------------------
-template <class P, bool kGamma2>
+template <class P, bool kGamma2, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img, int t_begin, int t_end) {
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = a.tt.ch >> 2;
     const int step = 32 % vpr, c_lane = lane % vpr;
-    const float gamma = a.spec.gamma;
+    const float gamma = a.spec.gamma, gscale = (1.0f - a.spec.alpha) * a.spec.w_cls;
     TileCursor cur;
     cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
 #pragma unroll 1
     for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
         TileInfo ti;
-        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti);
-        if (ti.nrows > 0) stream_vec<kGamma2, 7>(gp, ti.nrows, vpr, c_lane, step, lane, gamma, sa);
+        float* gg = nullptr;
+        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
+        if (ti.nrows > 0) stream_vec<kGamma2, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
     }
     return sa;
 }
-template <class P, bool kGamma2>
+template <class P, bool kGamma2, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int img, int t_begin, int t_end) {
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -300,13 +337,14 @@ __device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int i
 #pragma unroll 1
     for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
         TileInfo ti;
-        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti);
-        if (ti.nrows > 0) stream_scalar<kGamma2, 4>(gp, ti.nrows, ch, c_lane, step, lane, sp, sa);
+        float* gg = nullptr;
+        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
+        if (ti.nrows > 0) stream_scalar<kGamma2, kGrad, 4>(gp, gg, ti.nrows, ch, c_lane, step, lane, sp, sa);
     }
     return sa;
 }
 
-template <class P, bool kGamma2>
+template <class P, bool kGamma2, bool kGrad>
 __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_constant__ LossArgs<P> ga) {
     extern __shared__ __align__(128) unsigned char smem[];
     const FusedSmemLayout lay = fused_smem_layout<P>(ga.box_cap);
@@ -349,7 +387,9 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         }
         if (sub == 0) P::image_prologue(a.pp, recs, n_boxes, img);
 
-        const StreamAcc sa = vec ? stream_pass_vec<P, kGamma2>(a, img, t_begin, t_end) : stream_pass_scalar<P, kGamma2>(a, img, t_begin, t_end);
+        const StreamAcc sa = vec ? stream_pass_vec<P, kGamma2, kGrad>(a, img, t_begin, t_end)
+                                 : stream_pass_scalar<P, kGamma2, kGrad>(a, img, t_begin, t_end);
+        if (kGrad) __syncwarp();  // this warp's zero-label gradients are written before the matched rows overwrite theirs
         LossAcc acc = {0.f, 0.f, 0.f, 0};  // corrections + regression, natural units
         if (n_boxes > 0) acc = correct_pass<P>(a, recs, n_boxes, cand, img, t_begin, t_end);
 

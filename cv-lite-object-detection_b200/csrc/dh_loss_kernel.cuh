@@ -26,6 +26,7 @@ struct LossSpec {
     int reg_mode;  // 0 smooth-L1, 1 -log(IoU) on the integer grid
     int pos_rule;  // 0 max(class) >= 1, 1 max(class) > 0, 2 external per-row mask
     float alpha, gamma, delta;
+    float w_cls, w_reg, w_cen;  // gradient weights: grad = d(w_cls*cls + w_reg*reg + w_cen*cen) / d pred
 };
 
 struct NoPolicy {
@@ -54,6 +55,7 @@ struct LossArgs {
     unsigned int* sched;
     float* partials;  // [batch * chunks_per_image, 4]
     const float* mask_maps[DH_MAX_MAPS];
+    float* grad_maps[DH_MAX_MAPS];  // null: forward only; else d loss / d pred, same layout as the predictions
 };
 
 struct LossSmemLayout {
@@ -127,6 +129,60 @@ __device__ __forceinline__ float iou_loss_term(const float* t, const float* p, f
     const float uni = ((ty1 - ty0) * (tx1 - tx0) + (py1 - py0) * (px1 - px0)) - inter;
     const float iou = inter / (uni + 1.0e-12f);
     return -logf(iou + 1.0e-12f);
+}
+
+// ---- derivatives with respect to the prediction (what TF autodiff yields for the formulas above) -----------------
+// d/dx [ y*a*(1-s)^g*softplus(-x) + (1-y)*(1-a)*s^g*softplus(x) ]
+__device__ __forceinline__ float focal_grad(float y, float x, float alpha, float gamma) {
+    const ExpParts p = exp_parts(x);
+    const float s = x >= 0.f ? p.inv : p.e * p.inv;
+    const float om = x >= 0.f ? p.e * p.inv : p.inv;
+    float p_pos, p_neg;
+    if (gamma == 2.0f) {
+        p_pos = om * om, p_neg = s * s;
+    } else {
+        p_pos = __powf(om, gamma), p_neg = __powf(s, gamma);
+    }
+    const float sp_pos = p.soft + fmaxf(x, 0.f);  // softplus(x)
+    const float sp_neg = p.soft - fminf(x, 0.f);  // softplus(-x)
+    const float d_pos = -(gamma * s * p_pos * sp_neg + p_pos * om);
+    const float d_neg = gamma * p_neg * om * sp_pos + p_neg * s;
+    return y * alpha * d_pos + (1.0f - y) * (1.0f - alpha) * d_neg;
+}
+// d/dx where(|y-x| < delta, (y-x)^2/2, |y-x|)
+__device__ __forceinline__ float smooth_l1_grad(float y, float x, float delta) {
+    const float d = x - y, ad = fabsf(d);
+    return ad < delta ? d : (d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.f));
+}
+// d/dx smooth_l1(y, sigmoid(x))
+__device__ __forceinline__ float cen_l1_grad(float y, float x, float delta) {
+    const float s = sigmoid_f(x);
+    return smooth_l1_grad(y, s, delta) * s * (1.0f - s);
+}
+// gradient of iou_loss_term with respect to the four predicted distances (t, b, l, r)
+__device__ __forceinline__ void iou_loss_grad(const float* t, const float* p, float gy, float gx, float* g) {
+    const float ty0 = gy - t[0], ty1 = gy + t[1], tx0 = gx - t[2], tx1 = gx + t[3];
+    const float py0 = gy - p[0], py1 = gy + p[1], px0 = gx - p[2], px1 = gx + p[3];
+    const float ih_raw = fminf(ty1, py1) - fmaxf(ty0, py0), iw_raw = fminf(tx1, px1) - fmaxf(tx0, px0);
+    const float ih = fmaxf(0.f, ih_raw), iw = fmaxf(0.f, iw_raw);
+    const float inter = iw * ih;
+    const float ph = py1 - py0, pw = px1 - px0;
+    const float uni = ((ty1 - ty0) * (tx1 - tx0) + ph * pw) - inter;
+    const float den = uni + 1.0e-12f;
+    const float iou = inter / den;
+    const float live_h = ih_raw > 0.f ? 1.0f : 0.f, live_w = iw_raw > 0.f ? 1.0f : 0.f;
+    float di[4], da[4];  // d inter / d p_k, d area_pred / d p_k
+    di[0] = iw * live_h * (py0 > ty0 ? 1.0f : 0.f);  // the top edge of the intersection is the prediction's
+    di[1] = iw * live_h * (py1 < ty1 ? 1.0f : 0.f);
+    di[2] = ih * live_w * (px0 > tx0 ? 1.0f : 0.f);
+    di[3] = ih * live_w * (px1 < tx1 ? 1.0f : 0.f);
+    da[0] = da[1] = pw, da[2] = da[3] = ph;
+    const float k = -1.0f / (iou + 1.0e-12f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float d_uni = da[q] - di[q];
+        g[q] = k * (di[q] * den - inter * d_uni) / (den * den);
+    }
 }
 
 struct LossAcc {
@@ -210,6 +266,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
             const long long off = static_cast<long long>(ti.b) * md.image_stride + static_cast<long long>(ti.r0) * ch;
             const float* __restrict__ gp = md.pred + off;
             const float* __restrict__ gt = kFused ? nullptr : md.out + off;
+            float* __restrict__ gg = (!kFused && a.grad_maps[ti.m]) ? a.grad_maps[ti.m] + off : nullptr;
             const int nfl = ti.nrows * ch;
             int ncand = 0;
             uint32_t dmask = 0u;
@@ -301,6 +358,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                             continue;
                         }
                         const float4 y = kFused ? st4[q] : __ldcs(gt4 + q);
+                        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (is_reg) {
                             const float m = sp.pos_rule == 2 ? __int_as_float(rowpos[r]) : (rowpos[r] ? 1.0f : 0.0f);
                             if (m != 0.f) {
@@ -308,18 +366,33 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                                 if (sp.reg_mode == 0) {
                                     acc.reg += m * (smooth_l1_term(y.x, x[u].x, sp.delta) + smooth_l1_term(y.y, x[u].y, sp.delta) +
                                                     smooth_l1_term(y.z, x[u].z, sp.delta) + smooth_l1_term(y.w, x[u].w, sp.delta));
+                                    if (gg) {
+                                        const float k = m * sp.w_reg;
+                                        gv = make_float4(k * smooth_l1_grad(y.x, x[u].x, sp.delta), k * smooth_l1_grad(y.y, x[u].y, sp.delta),
+                                                         k * smooth_l1_grad(y.z, x[u].z, sp.delta), k * smooth_l1_grad(y.w, x[u].w, sp.delta));
+                                    }
                                 } else {
                                     const int row = ti.r0 + r;
                                     const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
                                     const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
                                     const float tv[4] = {y.x, y.y, y.z, y.w}, pv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
                                     acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                                    if (gg) {
+                                        float g4[4];
+                                        iou_loss_grad(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), g4);
+                                        const float k = m * sp.w_reg;
+                                        gv = make_float4(k * g4[0], k * g4[1], k * g4[2], k * g4[3]);
+                                    }
                                 }
                             }
                         } else {
                             acc.cls += focal_term(y.x, x[u].x, sp.alpha, sp.gamma) + focal_term(y.y, x[u].y, sp.alpha, sp.gamma) +
                                        focal_term(y.z, x[u].z, sp.alpha, sp.gamma) + focal_term(y.w, x[u].w, sp.alpha, sp.gamma);
+                            if (gg)
+                                gv = make_float4(sp.w_cls * focal_grad(y.x, x[u].x, sp.alpha, sp.gamma), sp.w_cls * focal_grad(y.y, x[u].y, sp.alpha, sp.gamma),
+                                                 sp.w_cls * focal_grad(y.z, x[u].z, sp.alpha, sp.gamma), sp.w_cls * focal_grad(y.w, x[u].w, sp.alpha, sp.gamma));
                         }
+                        if (gg) __stcs(reinterpret_cast<float4*>(gg) + q, gv);
                     }
                 }
             } else {
@@ -357,6 +430,32 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                             }
                         }
                         accumulate_element(sp, cls0, c, x[u], y, m, acc);
+                        if (gg) {
+                            float g = 0.f;
+                            if (c >= cls0) {
+                                g = sp.w_cls * focal_grad(y, x[u], sp.alpha, sp.gamma);
+                            } else if (c < sp.reg_ch) {
+                                if (m != 0.f) {
+                                    if (sp.reg_mode == 0) {
+                                        g = m * sp.w_reg * smooth_l1_grad(y, x[u], sp.delta);
+                                    } else {  // each of the row's four regression elements recomputes the row's IoU gradient
+                                        const int row = ti.r0 + r;
+                                        const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
+                                        const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
+                                        float tv[4], pv[4], g4[4];
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) pv[k] = gp[e - c + k], tv[k] = gt[e - c + k];
+                                        iou_loss_grad(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), g4);
+                                        g = m * sp.w_reg * (c == 0 ? g4[0] : (c == 1 ? g4[1] : (c == 2 ? g4[2] : g4[3])));
+                                    }
+                                }
+                            } else if (sp.cen_mode == 1) {
+                                g = sp.w_cen * cen_l1_grad(y, x[u], sp.delta);
+                            } else if (sp.cen_mode == 2) {
+                                g = sp.w_cen * focal_grad(y, x[u], sp.alpha, sp.gamma);
+                            }
+                            __stcs(gg + e, g);
+                        }
                     }
                 }
             }

@@ -48,6 +48,7 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
         if ((reinterpret_cast<uintptr_t>(a.tt.maps[m].pred) & 15u) || (!kFused && (reinterpret_cast<uintptr_t>(a.tt.maps[m].out) & 15u)))
             a.allow_vec = 0;
         if ((a.tt.maps[m].image_stride & 3) != 0) a.allow_vec = 0;
+        if (reinterpret_cast<uintptr_t>(a.grad_maps[m]) & 15u) a.allow_vec = 0;
     }
     // scratch: chunk partials + (optional) per-image sums when the caller only wants the total
     const size_t part_bytes = static_cast<size_t>(n_chunks) * 16;
@@ -95,18 +96,18 @@ static int finalize_loss(dh_handle_s* h, const float* partials, int batch, int c
 }
 
 // Fused encode+loss, stream + correct formulation (dh_fused_loss_kernel.cuh): 256-row tiles, 32 rows per warp.
-template <class P, bool kGamma2>
+template <class P, bool kGamma2, bool kGrad>
 static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, float* out_total, cudaStream_t st,
                           const char* who) {
     const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
     const FusedSmemLayout lay = fused_smem_layout<P>(a.box_cap);
     static bool attr_done = false;
     if (!attr_done) {
-        DH_CUDA(cudaFuncSetAttribute(fused_loss_kernel<P, kGamma2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DH_CUDA(cudaFuncSetAttribute(fused_loss_kernel<P, kGamma2, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     int per_sm = 1;
-    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kGamma2>, DH_THREADS, lay.total));
+    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kGamma2, kGrad>, DH_THREADS, lay.total));
     if (per_sm < 1) per_sm = 1;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
     // image-aligned chunks: aim at >= 8 chunks per CTA, 2..32 tiles (512..8192 rows) each
@@ -127,7 +128,7 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     if (total > 0) {
         a.sched = next_sched_counter(h, st);
         if (!a.sched) return DH_ERR_CUDA;
-        fused_loss_kernel<P, kGamma2><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+        fused_loss_kernel<P, kGamma2, kGrad><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
         DH_CUDA(cudaGetLastError());
         h->launches += 1;
     }
@@ -143,6 +144,10 @@ static int launch_fused(dh_handle_s* h, LossArgs<P>& a, int num_classes, float* 
     if (a.tt.batch == 0) return DH_OK;
     const int ch = a.tt.ch;
     if (h->fused_loss_kernel == 1 || num_classes > 32 * kCompactClassWords) {
+        for (int m = 0; m < a.tt.n_maps; ++m)
+            if (a.grad_maps[m])
+                return set_error(DH_ERR_CAPACITY, "%s: the gradient needs the stream+correct kernel (<= %d classes, DH_OPT_FUSED_LOSS_KERNEL 0)",
+                                 who, 32 * kCompactClassWords);
         a.tile_buf_bytes = finish_table(a.tt, ch, a.tt.batch, loss_tile_bytes(h));
         return launch_loss<P, true>(h, a, out_per_image, out_total, st, who);
     }
@@ -151,24 +156,37 @@ static int launch_fused(dh_handle_s* h, LossArgs<P>& a, int num_classes, float* 
     a.allow_vec = 1;
     for (int m = 0; m < a.tt.n_maps; ++m)
         if ((reinterpret_cast<uintptr_t>(a.tt.maps[m].pred) & 15u) || (a.tt.maps[m].image_stride & 3)) a.allow_vec = 0;
-    if (a.spec.gamma == 2.0f) return launch_fused_g<P, true>(h, a, out_per_image, out_total, st, who);
-    return launch_fused_g<P, false>(h, a, out_per_image, out_total, st, who);
+    bool grad = false;
+    for (int m = 0; m < a.tt.n_maps; ++m) {
+        if (a.grad_maps[m]) grad = true;
+        if (reinterpret_cast<uintptr_t>(a.grad_maps[m]) & 15u) a.allow_vec = 0;
+    }
+    if (grad) {
+        if (a.spec.gamma == 2.0f) return launch_fused_g<P, true, true>(h, a, out_per_image, out_total, st, who);
+        return launch_fused_g<P, false, true>(h, a, out_per_image, out_total, st, who);
+    }
+    if (a.spec.gamma == 2.0f) return launch_fused_g<P, true, false>(h, a, out_per_image, out_total, st, who);
+    return launch_fused_g<P, false, false>(h, a, out_per_image, out_total, st, who);
 }
 
 }  // namespace dh
 
 using namespace dh;
 
-extern "C" {
+struct GradOut {
+    float w_cls, w_reg, w_cen;
+    float* const* grad;  // per level (fused) / per map (dense)
+};
 
-int dh_dense_loss(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
+
+static int dense_loss_impl(const GradOut* go, dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
                   const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
                   const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
                   float alpha, float gamma, float delta, float* out_per_image, float* out_total, void* stream) {
     DH_CHECK_ARG(h && target_maps && pred_maps && map_height && map_width, "dh_dense_loss: NULL argument");
     DH_CHECK_ARG(n_maps >= 1 && n_maps <= DH_MAX_MAPS, "dh_dense_loss: n_maps %d not in [1,%d]", n_maps, DH_MAX_MAPS);
     DH_CHECK_ARG(batch >= 0 && ch >= 1, "dh_dense_loss: bad sizes");
-    DH_CHECK_ARG(out_per_image || out_total, "dh_dense_loss: no output requested");
+    DH_CHECK_ARG(go || out_per_image || out_total, "dh_dense_loss: no output requested");
     LossArgs<NoPolicy> a;
     memset(&a, 0, sizeof(a));
     a.spec.reg_ch = reg_ch, a.spec.cen_mode = cen_mode, a.spec.reg_mode = reg_mode, a.spec.pos_rule = pos_rule;
@@ -193,16 +211,23 @@ int dh_dense_loss(dh_handle_t h, int n_maps, const float* const* target_maps, co
         a.mask_maps[m] = mask_maps ? mask_maps[m] : nullptr;
     }
     a.tile_buf_bytes = finish_table(a.tt, ch, batch, loss_tile_bytes(h));
+    if (go) {
+        a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
+        for (int m = 0; m < n_maps; ++m) {
+            DH_CHECK_ARG(go->grad[m], "dh_dense_loss_grad: gradient map %d is NULL", m);
+            a.grad_maps[m] = go->grad[m];
+        }
+    }
     return launch_loss<NoPolicy, false>(h, a, out_per_image, out_total, static_cast<cudaStream_t>(stream), "dh_dense_loss");
 }
 
-int dh_fcos_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+static int fcos_encode_loss_impl(const GradOut* go, dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
                         int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, const float* b_dim,
                         int num_classes, int mode, const float* const* pred_levels, int reg_mode, int cen_mode,
                         float alpha, float gamma, float delta, float* out_per_image, float* out_total,
                         int32_t* num_targets, void* stream) {
     DH_CHECK_ARG(h && boxes && img_dim && strides && pred_levels, "dh_fcos_encode_loss: NULL argument");
-    DH_CHECK_ARG(out_per_image || out_total, "dh_fcos_encode_loss: no output requested");
+    DH_CHECK_ARG(go || out_per_image || out_total, "dh_fcos_encode_loss: no output requested");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_fcos_encode_loss: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_fcos_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
     DeviceGuard guard(h->device);
@@ -218,16 +243,24 @@ int dh_fcos_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, 
     if (rc) return rc;
     a.tt.ch = num_classes + 5, a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    if (go) {
+        a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
+        for (int m = 0; m < a.tt.n_maps; ++m) {
+            const int l = a.tt.maps[m].level;
+            DH_CHECK_ARG(go->grad[l], "gradient pointer of level %d is NULL", l);
+            a.grad_maps[m] = go->grad[l] + (a.tt.maps[m].pred - pred_levels[l]);
+        }
+    }
     return launch_fused<FcosPolicy>(h, a, num_classes, out_per_image, out_total, static_cast<cudaStream_t>(stream), "dh_fcos_encode_loss");
 }
 
-int dh_retina_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+static int retina_encode_loss_impl(const GradOut* go, dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
                           int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, int n_anchors,
                           const float* anchor_hw, float iou_thresh, int num_classes, const float* const* pred_levels,
                           float alpha, float gamma, float delta, float* out_per_image, float* out_total,
                           int32_t* num_pairs, void* stream) {
     DH_CHECK_ARG(h && boxes && img_dim && strides && anchor_hw && pred_levels, "dh_retina_encode_loss: NULL argument");
-    DH_CHECK_ARG(out_per_image || out_total, "dh_retina_encode_loss: no output requested");
+    DH_CHECK_ARG(go || out_per_image || out_total, "dh_retina_encode_loss: no output requested");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_retina_encode_loss: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_retina_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
     DeviceGuard guard(h->device);
@@ -242,16 +275,24 @@ int dh_retina_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox
     a.tt.ch = num_classes + 4, a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (num_pairs && batch > 0) DH_CUDA(cudaMemsetAsync(num_pairs, 0, sizeof(int32_t) * batch, st));
+    if (go) {
+        a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
+        for (int m = 0; m < a.tt.n_maps; ++m) {
+            const int l = a.tt.maps[m].level;
+            DH_CHECK_ARG(go->grad[l], "gradient pointer of level %d is NULL", l);
+            a.grad_maps[m] = go->grad[l] + (a.tt.maps[m].pred - pred_levels[l]);
+        }
+    }
     return launch_fused<RetinaPolicy>(h, a, num_classes, out_per_image, out_total, st, "dh_retina_encode_loss");
 }
 
-int dh_centernet_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+static int centernet_encode_loss_impl(const GradOut* go, dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
                              int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
                              float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
                              float gamma, float delta, float* out_per_image, float* out_total, int32_t* status,
                              void* stream) {
     DH_CHECK_ARG(h && boxes && img_dim && pred, "dh_centernet_encode_loss: NULL argument");
-    DH_CHECK_ARG(out_per_image || out_total, "dh_centernet_encode_loss: no output requested");
+    DH_CHECK_ARG(go || out_per_image || out_total, "dh_centernet_encode_loss: no output requested");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_centernet_encode_loss: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_centernet_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
     DeviceGuard guard(h->device);
@@ -270,7 +311,91 @@ int dh_centernet_encode_loss(dh_handle_t h, const float* boxes, const int32_t* n
     a.tt.ch = num_classes + (falloff ? 5 : 4), a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    if (go) {
+        a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
+        DH_CHECK_ARG(go->grad[0], "gradient pointer is NULL");
+        a.grad_maps[0] = go->grad[0];
+    }
     return launch_fused<CenterNetPolicy>(h, a, num_classes, out_per_image, out_total, st, "dh_centernet_encode_loss");
+}
+
+extern "C" {
+
+int dh_dense_loss(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
+                  const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
+                  const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                  float alpha, float gamma, float delta, float* out_per_image, float* out_total, void* stream) {
+    return dense_loss_impl(nullptr, h, n_maps, target_maps, pred_maps, mask_maps, map_height, map_width, map_sub, batch, ch, reg_ch,
+                           cen_mode, reg_mode, pos_rule, alpha, gamma, delta, out_per_image, out_total, stream);
+}
+int dh_dense_loss_grad(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
+                       const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
+                       const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                       float alpha, float gamma, float delta, float w_cls, float w_reg, float w_cen, float* const* grad_maps,
+                       float* out_per_image, float* out_total, void* stream) {
+    DH_CHECK_ARG(grad_maps, "dh_dense_loss_grad: grad_maps is NULL");
+    const GradOut go = {w_cls, w_reg, w_cen, grad_maps};
+    return dense_loss_impl(&go, h, n_maps, target_maps, pred_maps, mask_maps, map_height, map_width, map_sub, batch, ch, reg_ch,
+                           cen_mode, reg_mode, pos_rule, alpha, gamma, delta, out_per_image, out_total, stream);
+}
+
+int dh_fcos_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                        int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, const float* b_dim,
+                        int num_classes, int mode, const float* const* pred_levels, int reg_mode, int cen_mode,
+                        float alpha, float gamma, float delta, float* out_per_image, float* out_total,
+                        int32_t* num_targets, void* stream) {
+    return fcos_encode_loss_impl(nullptr, h, boxes, nbox, img_dim, batch, max_boxes, pad_h, pad_w, n_levels, strides, b_dim, num_classes,
+                                 mode, pred_levels, reg_mode, cen_mode, alpha, gamma, delta, out_per_image, out_total, num_targets, stream);
+}
+int dh_fcos_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                             int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, const float* b_dim,
+                             int num_classes, int mode, const float* const* pred_levels, int reg_mode, int cen_mode,
+                             float alpha, float gamma, float delta, float w_cls, float w_reg, float w_cen,
+                             float* const* grad_levels, float* out_per_image, float* out_total, int32_t* num_targets,
+                             void* stream) {
+    DH_CHECK_ARG(grad_levels, "dh_fcos_encode_loss_grad: grad_levels is NULL");
+    const GradOut go = {w_cls, w_reg, w_cen, grad_levels};
+    return fcos_encode_loss_impl(&go, h, boxes, nbox, img_dim, batch, max_boxes, pad_h, pad_w, n_levels, strides, b_dim, num_classes,
+                                 mode, pred_levels, reg_mode, cen_mode, alpha, gamma, delta, out_per_image, out_total, num_targets, stream);
+}
+
+int dh_retina_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                          int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, int n_anchors,
+                          const float* anchor_hw, float iou_thresh, int num_classes, const float* const* pred_levels,
+                          float alpha, float gamma, float delta, float* out_per_image, float* out_total,
+                          int32_t* num_pairs, void* stream) {
+    return retina_encode_loss_impl(nullptr, h, boxes, nbox, img_dim, batch, max_boxes, pad_h, pad_w, n_levels, strides, n_anchors, anchor_hw,
+                                   iou_thresh, num_classes, pred_levels, alpha, gamma, delta, out_per_image, out_total, num_pairs, stream);
+}
+int dh_retina_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                               int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, int n_anchors,
+                               const float* anchor_hw, float iou_thresh, int num_classes, const float* const* pred_levels,
+                               float alpha, float gamma, float delta, float w_cls, float w_reg, float* const* grad_levels,
+                               float* out_per_image, float* out_total, int32_t* num_pairs, void* stream) {
+    DH_CHECK_ARG(grad_levels, "dh_retina_encode_loss_grad: grad_levels is NULL");
+    const GradOut go = {w_cls, w_reg, 0.f, grad_levels};
+    return retina_encode_loss_impl(&go, h, boxes, nbox, img_dim, batch, max_boxes, pad_h, pad_w, n_levels, strides, n_anchors, anchor_hw,
+                                   iou_thresh, num_classes, pred_levels, alpha, gamma, delta, out_per_image, out_total, num_pairs, stream);
+}
+
+int dh_centernet_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                             int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
+                             float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                             float gamma, float delta, float* out_per_image, float* out_total, int32_t* status,
+                             void* stream) {
+    return centernet_encode_loss_impl(nullptr, h, boxes, nbox, img_dim, batch, max_boxes, pad0, pad1, stride, n_scales, box_scales, sigma,
+                                      num_classes, mode, pred, reg_mode, alpha, gamma, delta, out_per_image, out_total, status, stream);
+}
+int dh_centernet_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                                  int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
+                                  float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                                  float gamma, float delta, float w_cls, float w_reg, float w_cen, float* grad,
+                                  float* out_per_image, float* out_total, int32_t* status, void* stream) {
+    DH_CHECK_ARG(grad, "dh_centernet_encode_loss_grad: grad is NULL");
+    float* const levels[1] = {grad};
+    const GradOut go = {w_cls, w_reg, w_cen, levels};
+    return centernet_encode_loss_impl(&go, h, boxes, nbox, img_dim, batch, max_boxes, pad0, pad1, stride, n_scales, box_scales, sigma,
+                                      num_classes, mode, pred, reg_mode, alpha, gamma, delta, out_per_image, out_total, status, stream);
 }
 
 }  // extern "C"

@@ -120,8 +120,9 @@ def model_loss(y_true, y_pred, reg_type="l1", cen_type="l1"):
 
 
 def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride=8, mode="s8", box_scales=None,
-                      sigma=0.25, reg_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None):
-    """Fused CenterNet encode + loss.  Returns (per_image [B,4], total [4], status [1])."""
+                      sigma=0.25, reg_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
+    """Fused CenterNet encode + loss.  Returns (per_image [B,4], total [4], status [1]); with `weights` = (w_cls,
+    w_reg, w_cen) a fourth item, the gradient d(w . {cls, reg, cen}) / d y_pred (dh_centernet_encode_loss_grad)."""
     dev = current_device()
     boxes_d = to_device(boxes, torch.float32, dev)
     batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
@@ -133,6 +134,16 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
     out_pi = torch.empty((batch, 4), dtype=torch.float32, device=dev)
     out_tot = torch.empty((4,), dtype=torch.float32, device=dev)
     status = torch.empty((1,), dtype=torch.int32, device=dev)
+    if weights is not None:
+        grad = torch.empty_like(yp)
+        _capi.check(_capi.lib().dh_centernet_encode_loss_grad(
+            _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
+            int(img_pad[0]), int(img_pad[1]), int(stride), len(scales), _capi.float_array(scales) if scales else None,
+            float(sigma), int(num_classes), MODES[mode], yp.data_ptr(),
+            losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1, float(alpha), float(gamma), float(delta),
+            float(weights[0]), float(weights[1]), float(weights[2]), grad.data_ptr(), out_pi.data_ptr(), out_tot.data_ptr(),
+            status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode_loss_grad")
+        return out_pi, out_tot, status, grad
     _capi.check(_capi.lib().dh_centernet_encode_loss(
         _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
         int(img_pad[0]), int(img_pad[1]), int(stride), len(scales), _capi.float_array(scales) if scales else None,

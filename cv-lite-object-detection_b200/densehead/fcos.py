@@ -104,15 +104,16 @@ def _as_batched(maps, dev):
     return out
 
 
-def model_loss_batch(y_true, y_pred, reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None):
-    """Loss over materialised FCOS targets for a batch -> (per_image [B,4], total [4]) = {cls, reg, cen, n_pos}."""
+def model_loss_batch(y_true, y_pred, reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
+    """Loss over materialised FCOS targets for a batch -> (per_image [B,4], total [4]) = {cls, reg, cen, n_pos}
+    (+ per-level gradients when `weights` = (w_cls, w_reg, w_cen) is given)."""
     dev = current_device()
     yt, yp = _as_batched(y_true, dev), _as_batched(y_pred, dev)
     batch, ch = int(yp[0].shape[0]), int(yp[0].shape[-1])
     shapes = [(int(p.shape[1]), int(p.shape[2]), 1) for p in yp]
     cen = {"l1": losses.CEN_SMOOTH_L1, "focal": losses.CEN_FOCAL}.get(cen_type.lower(), losses.CEN_IGNORE)
     reg = losses.REG_IOU if reg_type == "iou" else losses.REG_SMOOTH_L1
-    return losses.dense_loss(yt, yp, shapes, batch, ch, 4, cen, reg, losses.POS_GE1, alpha, gamma, delta, stream=stream)
+    return losses.dense_loss(yt, yp, shapes, batch, ch, 4, cen, reg, losses.POS_GE1, alpha, gamma, delta, stream=stream, weights=weights)
 
 
 def model_loss(y_true, y_pred, strides=None, reg_type="l1", cen_type="l1", cls_lambda=2.5, reg_lambda=1.0):
@@ -136,9 +137,10 @@ def model_loss_center_v1(y_true, y_pred):
 
 
 def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, strides=None, b_dim=None, mode="fcos",
-                      reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+                      reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
     """Fused target encoding + loss: targets never reach HBM.  y_pred: per-level [B, Hl, Wl, C+5].
-    Returns (per_image [B,4], total [4], num_targets [B, n_levels])."""
+    Returns (per_image [B,4], total [4], num_targets [B, n_levels]); with `weights` = (w_cls, w_reg, w_cen) a fourth
+    item, the per-level gradients d(w . {cls, reg, cen}) / d y_pred (dh_fcos_encode_loss_grad, same pass)."""
     strides = list(DEFAULT_STRIDES if strides is None else strides)
     b_dim = list(DEFAULT_B_DIM if b_dim is None else b_dim)
     dev = current_device()
@@ -157,6 +159,16 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
     cnt = torch.empty((batch, len(strides)), dtype=torch.int32, device=dev)
     cen = {"l1": losses.CEN_SMOOTH_L1, "focal": losses.CEN_FOCAL}.get(cen_type.lower(), losses.CEN_IGNORE)
     reg = losses.REG_IOU if reg_type == "iou" else losses.REG_SMOOTH_L1
+    if weights is not None:
+        grads = [torch.empty_like(p) for p in yp]
+        _capi.check(_capi.lib().dh_fcos_encode_loss_grad(
+            _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
+            int(img_pad[0]), int(img_pad[1]), len(strides), _capi.int_array(strides), _capi.float_array(b_dim),
+            int(num_classes), MODES[mode], _capi.ptr_array([p.data_ptr() for p in yp]), reg, cen, float(alpha),
+            float(gamma), float(delta), float(weights[0]), float(weights[1]), float(weights[2]),
+            _capi.ptr_array([g.data_ptr() for g in grads]), out_pi.data_ptr(), out_tot.data_ptr(), cnt.data_ptr(),
+            stream_ptr(stream)), "dh_fcos_encode_loss_grad")
+        return out_pi, out_tot, cnt, grads
     _capi.check(_capi.lib().dh_fcos_encode_loss(
         _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
         int(img_pad[0]), int(img_pad[1]), len(strides), _capi.int_array(strides), _capi.float_array(b_dim),

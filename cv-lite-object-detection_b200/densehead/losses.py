@@ -17,9 +17,10 @@ POS_GE1, POS_GT0, POS_MASK = 0, 1, 2
 
 
 def dense_loss(targets, preds, shapes, batch, ch, reg_ch, cen_mode, reg_mode, pos_rule, alpha=0.25, gamma=2.0,
-               delta=1.0, masks=None, per_image=True, stream=None):
+               delta=1.0, masks=None, per_image=True, stream=None, weights=None):
     """targets/preds: lists of contiguous float32 device tensors, map m holding [B, H*W*sub, ch] rows.
-    shapes: list of (H, W, sub).  Returns (per_image [B,4] or None, total [4])."""
+    shapes: list of (H, W, sub).  Returns (per_image [B,4] or None, total [4]); with `weights` = (w_cls, w_reg,
+    w_cen) also the gradient maps d(w . {cls, reg, cen}) / d preds (dh_dense_loss_grad, same pass)."""
     dev = current_device()
     for t, p in zip(targets, preds):
         if t.numel() != p.numel():
@@ -27,15 +28,38 @@ def dense_loss(targets, preds, shapes, batch, ch, reg_ch, cen_mode, reg_mode, po
     out_pi = torch.empty((batch, 4), dtype=torch.float32, device=dev) if per_image else None
     out_tot = torch.empty((4,), dtype=torch.float32, device=dev)
     n = len(targets)
-    _capi.check(_capi.lib().dh_dense_loss(
-        _capi.handle(dev.index), n, _capi.ptr_array([t.data_ptr() for t in targets]),
-        _capi.ptr_array([p.data_ptr() for p in preds]),
-        _capi.ptr_array([m.data_ptr() for m in masks]) if masks is not None else None,
-        _capi.int_array([s[0] for s in shapes]), _capi.int_array([s[1] for s in shapes]),
-        _capi.int_array([s[2] for s in shapes]), int(batch), int(ch), int(reg_ch), int(cen_mode), int(reg_mode),
-        int(pos_rule), float(alpha), float(gamma), float(delta),
-        out_pi.data_ptr() if per_image else None, out_tot.data_ptr(), stream_ptr(stream)), "dh_dense_loss")
-    return out_pi, out_tot
+    common = [_capi.handle(dev.index), n, _capi.ptr_array([t.data_ptr() for t in targets]),
+              _capi.ptr_array([p.data_ptr() for p in preds]),
+              _capi.ptr_array([m.data_ptr() for m in masks]) if masks is not None else None,
+              _capi.int_array([s[0] for s in shapes]), _capi.int_array([s[1] for s in shapes]),
+              _capi.int_array([s[2] for s in shapes]), int(batch), int(ch), int(reg_ch), int(cen_mode), int(reg_mode),
+              int(pos_rule), float(alpha), float(gamma), float(delta)]
+    outs = [out_pi.data_ptr() if per_image else None, out_tot.data_ptr(), stream_ptr(stream)]
+    if weights is None:
+        _capi.check(_capi.lib().dh_dense_loss(*(common + outs)), "dh_dense_loss")
+        return out_pi, out_tot
+    grads = [torch.empty_like(p) for p in preds]
+    _capi.check(_capi.lib().dh_dense_loss_grad(*(common + [float(weights[0]), float(weights[1]), float(weights[2]),
+                                                            _capi.ptr_array([g.data_ptr() for g in grads])] + outs)),
+                "dh_dense_loss_grad")
+    return out_pi, out_tot, grads
+
+
+class WeightedLoss(torch.autograd.Function):
+    """Differentiable scalar `w_cls*cls + w_reg*reg + w_cen*cen` for torch callers (the reference differentiates its
+    model_loss with tf.GradientTape, FCOS/train_fcos.py:152-176).  `run(weights)` must return (total [4], grads list)
+    computed by one of the *_grad entry points for the prediction tensors passed as `preds`."""
+
+    @staticmethod
+    def forward(ctx, run, weights, *preds):
+        total, grads = run(weights)
+        ctx.grads = grads
+        w = torch.tensor([float(weights[0]), float(weights[1]), float(weights[2])], device=total.device)
+        return (total[:3] * w).sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None) + tuple(g * x for x in ctx.grads)
 
 
 def _flat(x, dev):

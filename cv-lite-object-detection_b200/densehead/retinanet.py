@@ -87,7 +87,7 @@ def _pack_levels(x, n_anchors, dev):
     return out
 
 
-def loss_batch(x_label, x_pred, n_anchors=9, alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+def loss_batch(x_label, x_pred, n_anchors=9, alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
     """Loss over materialised RetinaNet targets -> (per_image [B,4], total [4]) = {cls, reg, 0, n_pos}."""
     dev = current_device()
     yt, yp = _pack_levels(x_label, n_anchors, dev), _pack_levels(x_pred, n_anchors, dev)
@@ -100,13 +100,15 @@ def loss_batch(x_label, x_pred, n_anchors=9, alpha=0.25, gamma=2.0, delta=1.0, s
     # batch-major packed layout: image stride covers all anchors, so fold anchors into rows as well
     shapes = [(int(p.shape[1]) * int(p.shape[2]), int(p.shape[3]), 1) for p in yp]
     return losses.dense_loss(yt, yp, shapes, batch, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_GT0,
-                             alpha, gamma, delta, stream=stream)
+                             alpha, gamma, delta, stream=stream,
+                             weights=None if weights is None else (weights[0], weights[1], 0.0))
 
 
 def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, x_pred, anchor_hw=None, iou_thresh=0.5,
-                      strides=None, alpha=0.25, gamma=2.0, delta=1.0, stream=None):
+                      strides=None, alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
     """Fused match + encode + loss (targets never reach HBM).  x_pred: per-level [B, A, Hl, Wl, C+4].
-    Returns (per_image [B,4], total [4], num_pairs [B])."""
+    Returns (per_image [B,4], total [4], num_pairs [B]); with `weights` = (w_cls, w_reg) a fourth item, the
+    per-level gradients d(w_cls*cls + w_reg*reg) / d x_pred (dh_retina_encode_loss_grad, same pass)."""
     strides = list(STRIDES if strides is None else strides)
     table = anchor_table() if anchor_hw is None else np.ascontiguousarray(anchor_hw, dtype=np.float32)
     n_levels, n_anchors = table.shape[0], table.shape[1]
@@ -125,6 +127,15 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, x_pred, anchor
     out_pi = torch.empty((batch, 4), dtype=torch.float32, device=dev)
     out_tot = torch.empty((4,), dtype=torch.float32, device=dev)
     pairs = torch.empty((batch,), dtype=torch.int32, device=dev)
+    if weights is not None:
+        grads = [torch.empty_like(p) for p in yp]
+        _capi.check(_capi.lib().dh_retina_encode_loss_grad(
+            _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax, pad_h, pad_w,
+            n_levels, _capi.int_array(strides), n_anchors, _capi.float_array(table.reshape(-1).tolist()),
+            float(iou_thresh), int(num_classes), _capi.ptr_array([p.data_ptr() for p in yp]), float(alpha), float(gamma),
+            float(delta), float(weights[0]), float(weights[1]), _capi.ptr_array([g.data_ptr() for g in grads]),
+            out_pi.data_ptr(), out_tot.data_ptr(), pairs.data_ptr(), stream_ptr(stream)), "dh_retina_encode_loss_grad")
+        return out_pi, out_tot, pairs, grads
     _capi.check(_capi.lib().dh_retina_encode_loss(
         _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax, pad_h, pad_w,
         n_levels, _capi.int_array(strides), n_anchors, _capi.float_array(table.reshape(-1).tolist()),

@@ -177,6 +177,37 @@ int dh_centernet_encode_loss(dh_handle_t h,
                              int reg_mode /*mode 2 only*/, float alpha, float gamma, float delta,
                              float* out_per_image, float* out_total, int32_t* status, void* stream);
 
+/* ---- losses with gradients ------------------------------------------------------------
+ * The reference differentiates through model_loss with tf.GradientTape (FCOS/train_fcos.py:152-176,
+ * RetinaNet/train_retinanet_coco.py:207-218, CenterNet/tf_centernet_resnet_s8.py:417-432).  Each *_grad entry point
+ * computes the same loss sums as its forward twin AND, in the same pass over the predictions, writes
+ *     grad = d (w_cls * cls + w_reg * reg + w_cen * cen) / d pred
+ * into caller-owned maps with the layout of the predictions (every element is written; one read of the predictions,
+ * one write of the gradient).  out_per_image / out_total may both be NULL when only the gradient is wanted.     */
+int dh_dense_loss_grad(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
+                       const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
+                       const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                       float alpha, float gamma, float delta, float w_cls, float w_reg, float w_cen,
+                       float* const* grad_maps /*[host] n_maps [dev] ptrs*/, float* out_per_image, float* out_total,
+                       void* stream);
+int dh_fcos_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                             int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, const float* b_dim,
+                             int num_classes, int mode, const float* const* pred_levels, int reg_mode, int cen_mode,
+                             float alpha, float gamma, float delta, float w_cls, float w_reg, float w_cen,
+                             float* const* grad_levels /*[host] n_levels [dev] ptrs*/, float* out_per_image,
+                             float* out_total, int32_t* num_targets, void* stream);
+int dh_retina_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                               int max_boxes, int pad_h, int pad_w, int n_levels, const int32_t* strides, int n_anchors,
+                               const float* anchor_hw, float iou_thresh, int num_classes, const float* const* pred_levels,
+                               float alpha, float gamma, float delta, float w_cls, float w_reg,
+                               float* const* grad_levels /*[host] n_levels [dev] ptrs*/, float* out_per_image,
+                               float* out_total, int32_t* num_pairs, void* stream);
+int dh_centernet_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
+                                  int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
+                                  float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                                  float gamma, float delta, float w_cls, float w_reg, float w_cen, float* grad /*[dev]*/,
+                                  float* out_per_image, float* out_total, int32_t* status, void* stream);
+
 /* ---- inference: decode, candidate selection, NMS ------------------------------------------------- */
 
 /* prediction_to_corners: head regression values -> pixel corner boxes (y1, x1, y2, x2), float32.

@@ -546,6 +546,110 @@ def centernet_hourglass_model_loss(y_true, y_pred):
 
 
 # --------------------------------------------------------------------------------------
+# f-1  loss gradients (what tf.GradientTape yields for the formulas above; FCOS/train_fcos.py:152-176)
+# --------------------------------------------------------------------------------------
+# Parity unpinned: TensorFlow's autodiff is not available here.  These are the analytic derivatives of the
+# reference's loss expressions in float64; tests/test_oracle_grad.py checks them against central finite
+# differences of a float64 evaluation of the same expressions.
+def dense_loss_f64(target, pred, reg_ch=4, cen_mode=0, reg_mode=0, pos_rule="gt0", alpha=0.25, gamma=2.0, delta=1.0,
+                   mask=None):
+    """(cls, reg, cen) of one [H, W, ch] (or [..., ch]) map in float64: channels [0, reg_ch) boxes, then an optional
+    centerness channel (cen_mode 1 smooth-L1 of sigmoid, 2 focal, 3 ignored), then classes."""
+    t, p = np.asarray(target, np.float64), np.asarray(pred, np.float64)
+    cls0 = reg_ch + (1 if cen_mode else 0)
+    y, x = t[..., cls0:], p[..., cls0:]
+    sg = 1.0 / (1.0 + np.exp(-x))
+    sp_pos, sp_neg = np.logaddexp(0.0, x), np.logaddexp(0.0, -x)
+    cls = np.sum(y * alpha * (1 - sg) ** gamma * sp_neg + (1 - y) * (1 - alpha) * sg ** gamma * sp_pos)
+    if mask is None:
+        obj = t[..., cls0:].max(axis=-1)
+        mask = (obj >= 1) if pos_rule == "ge1" else (obj > 0)
+    m = np.asarray(mask, np.float64)
+    reg = 0.0
+    if reg_ch:
+        if reg_mode == 0:
+            d = t[..., :4] - p[..., :4]
+            reg = np.sum(np.where(np.abs(d) < delta, 0.5 * d * d, np.abs(d)) * m[..., None])
+        else:
+            hh, ww = p.shape[-3], p.shape[-2]
+            gx, gy = np.meshgrid(np.arange(ww, dtype=np.float64), np.arange(hh, dtype=np.float64))
+            tb = (gy - t[..., 0], gx - t[..., 2], gy + t[..., 1], gx + t[..., 3])
+            pb = (gy - p[..., 0], gx - p[..., 2], gy + p[..., 1], gx + p[..., 3])
+            ih = np.maximum(0, np.minimum(tb[2], pb[2]) - np.maximum(tb[0], pb[0]))
+            iw = np.maximum(0, np.minimum(tb[3], pb[3]) - np.maximum(tb[1], pb[1]))
+            inter = iw * ih
+            union = (tb[2] - tb[0]) * (tb[3] - tb[1]) + (pb[2] - pb[0]) * (pb[3] - pb[1]) - inter
+            with np.errstate(divide="ignore", invalid="ignore"):
+                per = -np.log(inter / (union + 1e-12) + 1e-12)
+            reg = np.sum(np.where(m > 0, per, 0.0) * m)
+    cen = 0.0
+    if cen_mode == 1:
+        d = t[..., reg_ch] - 1.0 / (1.0 + np.exp(-p[..., reg_ch]))
+        cen = np.sum(np.where(np.abs(d) < delta, 0.5 * d * d, np.abs(d)))
+    elif cen_mode == 2:
+        yc, xc = t[..., reg_ch], p[..., reg_ch]
+        sc = 1.0 / (1.0 + np.exp(-xc))
+        cen = np.sum(yc * alpha * (1 - sc) ** gamma * np.logaddexp(0.0, -xc) + (1 - yc) * (1 - alpha) * sc ** gamma * np.logaddexp(0.0, xc))
+    return float(cls), float(reg), float(cen)
+
+
+def _focal_grad64(y, x, alpha, gamma):
+    sg = 1.0 / (1.0 + np.exp(-x))
+    om = 1.0 - sg
+    sp_pos, sp_neg = np.logaddexp(0.0, x), np.logaddexp(0.0, -x)
+    d_pos = -(gamma * sg * om ** gamma * sp_neg + om ** (gamma + 1))
+    d_neg = gamma * sg ** gamma * om * sp_pos + sg ** (gamma + 1)
+    return y * alpha * d_pos + (1 - y) * (1 - alpha) * d_neg
+
+
+def _sl1_grad64(y, x, delta):
+    d = x - y
+    return np.where(np.abs(d) < delta, d, np.sign(d))
+
+
+def dense_loss_grad(target, pred, weights=(1.0, 1.0, 1.0), reg_ch=4, cen_mode=0, reg_mode=0, pos_rule="gt0", alpha=0.25,
+                    gamma=2.0, delta=1.0, mask=None):
+    """d(w_cls*cls + w_reg*reg + w_cen*cen) / d pred of `dense_loss_f64`, float64, same shape as `pred`."""
+    t, p = np.asarray(target, np.float64), np.asarray(pred, np.float64)
+    w_cls, w_reg, w_cen = (float(v) for v in weights)
+    cls0 = reg_ch + (1 if cen_mode else 0)
+    g = np.zeros_like(p)
+    g[..., cls0:] = w_cls * _focal_grad64(t[..., cls0:], p[..., cls0:], alpha, gamma)
+    if mask is None:
+        obj = t[..., cls0:].max(axis=-1)
+        mask = (obj >= 1) if pos_rule == "ge1" else (obj > 0)
+    m = np.asarray(mask, np.float64)
+    if reg_ch:
+        if reg_mode == 0:
+            g[..., :4] = w_reg * m[..., None] * _sl1_grad64(t[..., :4], p[..., :4], delta)
+        else:
+            hh, ww = p.shape[-3], p.shape[-2]
+            gx, gy = np.meshgrid(np.arange(ww, dtype=np.float64), np.arange(hh, dtype=np.float64))
+            ty0, tx0, ty1, tx1 = gy - t[..., 0], gx - t[..., 2], gy + t[..., 1], gx + t[..., 3]
+            py0, px0, py1, px1 = gy - p[..., 0], gx - p[..., 2], gy + p[..., 1], gx + p[..., 3]
+            ih_raw = np.minimum(ty1, py1) - np.maximum(ty0, py0)
+            iw_raw = np.minimum(tx1, px1) - np.maximum(tx0, px0)
+            ih, iw = np.maximum(0, ih_raw), np.maximum(0, iw_raw)
+            inter = iw * ih
+            ph, pw = py1 - py0, px1 - px0
+            den = (ty1 - ty0) * (tx1 - tx0) + ph * pw - inter + 1e-12
+            with np.errstate(divide="ignore", invalid="ignore"):
+                k = -1.0 / (inter / den + 1e-12)
+                di = [iw * (ih_raw > 0) * (py0 > ty0), iw * (ih_raw > 0) * (py1 < ty1),
+                      ih * (iw_raw > 0) * (px0 > tx0), ih * (iw_raw > 0) * (px1 < tx1)]
+                da = [pw, pw, ph, ph]
+                for q in range(4):
+                    gq = k * (di[q] * den - inter * (da[q] - di[q])) / (den * den)
+                    g[..., q] = w_reg * np.where(m > 0, gq, 0.0) * m
+    if cen_mode == 1:
+        sc = 1.0 / (1.0 + np.exp(-p[..., reg_ch]))
+        g[..., reg_ch] = w_cen * _sl1_grad64(t[..., reg_ch], sc, delta) * sc * (1 - sc)
+    elif cen_mode == 2:
+        g[..., reg_ch] = w_cen * _focal_grad64(t[..., reg_ch], p[..., reg_ch], alpha, gamma)
+    return g
+
+
+# --------------------------------------------------------------------------------------
 # a11  prediction_to_corners variants
 # --------------------------------------------------------------------------------------
 def _grid32(h, w, half):
