@@ -98,41 +98,37 @@ struct StreamAcc {
 // Lane l takes items l, l + 32, l + 64, ... (an item = one 128-bit load in the vector pass, one float in the
 // scalar pass); `c` tracks the item's position inside its row incrementally (no division in the loop).
 template <bool kGamma2, bool kGrad>
-__device__ __forceinline__ void stream_vec_item(const float4& x, int c4, float gamma, float gscale, StreamAcc& a, float4* g) {
+__device__ __forceinline__ void stream_vec_item(const float4& x, bool is_reg, float gamma, float gscale, StreamAcc& a, float4* g) {
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c4 != 0) {  // float4 0 of a row = the 4 regression channels
-        d.x = stream_term<kGamma2, false, kGrad>(x.x, gamma, a.c0);
+    if (!is_reg) {  // float4 0 of a row = the 4 regression channels
+        d.x = stream_term<kGamma2, true, kGrad>(x.x, gamma, a.c0);
         d.y = stream_term<kGamma2, true, kGrad>(x.y, gamma, a.c1);
-        d.z = stream_term<kGamma2, false, kGrad>(x.z, gamma, a.c2);
-        d.w = stream_term<kGamma2, true, kGrad>(x.w, gamma, a.c3);
+        d.z = stream_term<kGamma2, true, kGrad>(x.z, gamma, a.c2);
+        d.w = stream_term<kGamma2, false, kGrad>(x.w, gamma, a.c3);
     }
     if (kGrad) __stcs(g, make_float4(d.x * gscale, d.y * gscale, d.z * gscale, d.w * gscale));
 }
+// `kstar` = the one k in [0, vpr) at which this lane's item lane + 32 k is float4 0 of a row (tiles start on a row
+// boundary and a lane has at most vpr items per tile, so there is exactly one)
 template <bool kGamma2, bool kGrad, int U>
-__device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int c4, int step,
+__device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int kstar,
                                            int lane, float gamma, float gscale, StreamAcc& a) {
-    const float4* __restrict__ base = reinterpret_cast<const float4*>(p) + lane;
-    float4* __restrict__ gbase = reinterpret_cast<float4*>(gout) + lane;
+    const float4* __restrict__ ptr = reinterpret_cast<const float4*>(p) + lane;
+    float4* __restrict__ gptr = reinterpret_cast<float4*>(gout) + lane;
     const int n_mine = (nrows * vpr - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
     int k = 0;
 #pragma unroll 1
-    for (; k + U <= n_mine; k += U) {  // U independent loads in flight, no predicates
+    for (; k + U <= n_mine; k += U, ptr += 32 * U, gptr += 32 * U) {  // U independent loads in flight, no predicates
         float4 x[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) x[u] = __ldcs(base + 32 * (k + u));
+        for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            stream_vec_item<kGamma2, kGrad>(x[u], c4, gamma, gscale, a, gbase + 32 * (k + u));
-            c4 += step;
-            if (c4 >= vpr) c4 -= vpr;
-        }
+        for (int u = 0; u < U; ++u) stream_vec_item<kGamma2, kGrad>(x[u], k + u == kstar, gamma, gscale, a, gptr + 32 * u);
     }
 #pragma unroll 1
-    for (; k < n_mine; ++k) {
-        const float4 x = __ldcs(base + 32 * k);
-        stream_vec_item<kGamma2, kGrad>(x, c4, gamma, gscale, a, gbase + 32 * k);
-        c4 += step;
-        if (c4 >= vpr) c4 -= vpr;
+    for (; k < n_mine; ++k, ptr += 32, gptr += 32) {
+        const float4 x = __ldcs(ptr);
+        stream_vec_item<kGamma2, kGrad>(x, k == kstar, gamma, gscale, a, gptr);
     }
 }
 
@@ -312,7 +308,8 @@ __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img,
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = a.tt.ch >> 2;
-    const int step = 32 % vpr, c_lane = lane % vpr;
+    int kstar = 0;
+    while ((lane + 32 * kstar) % vpr != 0) ++kstar;
     const float gamma = a.spec.gamma, gscale = (1.0f - a.spec.alpha) * a.spec.w_cls;
     TileCursor cur;
     cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
@@ -321,7 +318,7 @@ __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img,
         TileInfo ti;
         float* gg = nullptr;
         const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
-        if (ti.nrows > 0) stream_vec<kGamma2, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
+        if (ti.nrows > 0) stream_vec<kGamma2, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, kstar, lane, gamma, gscale, sa);
     }
     return sa;
 }

@@ -72,6 +72,9 @@ def lib():
         D = ctypes.c_double
         L.dh_fcos_detect.argtypes = [P, PP, I, I, I, I, c_ip, I, I, F, F, I, I, I, P, P, P, P, P, P]
         L.dh_retina_detect.argtypes = [P, PP, I, I, I, I, c_ip, I, P, I, F, F, I, P, I, P, P, P, P, P]
+        L.dh_box_convert.argtypes = [P, P, ctypes.c_longlong, I, P, P]
+        L.dh_prepare_labels.argtypes = [P, P, P, P, P, P, I, I, I, P, P, P]
+        L.dh_format_detections.argtypes = [P, P, P, P, I, I, P, P, P, P]
         L.dh_compute_iou.argtypes = [P, P, I, P, I, P, P]
         L.dh_bboxes_iou.argtypes = [P, P, I, P, I, P, P]
         L.dh_centernet_nms.argtypes = [P, P, I, P, I, D, D, I, P, P, P, P]

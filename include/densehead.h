@@ -112,6 +112,35 @@ int dh_centernet_encode(dh_handle_t h,
                         float* out /*[dev]*/, int32_t* status /*[dev] or NULL*/,
                         void* stream);
 
+/* ---- label preparation / result formatting (the steps either side of the path) ------------------------------- */
+
+/* Element-wise box transforms on [n, 4] float32 rows: swap_xy, convert_to_xywh, convert_to_corners
+ * (FCOS/utils.py:6-40, identical in RetinaNet/ and CenterNet/) and the box half of random_flip_horizontal
+ * (FCOS/data_preprocess.py:36-39: (xmin, ymin, xmax, ymax) -> (1 - xmax, ymin, 1 - xmin, ymax)).  In place is allowed. */
+#define DH_BOX_SWAP_XY 0
+#define DH_BOX_TO_XYWH 1
+#define DH_BOX_TO_CORNERS 2
+#define DH_BOX_FLIP_HORIZONTAL 3
+int dh_box_convert(dh_handle_t h, const float* boxes /*[dev] [n,4]*/, long long n, int mode, float* out /*[dev] [n,4]*/, void* stream);
+
+/* Dataset boxes (xmin, ymin, xmax, ymax, normalised; FCOS/format_VOC_fcos.py:60-68) + class ids -> the padded
+ * [B, max_boxes, 5] (cy, cx, h, w, class) + nbox layout the encoders take: per-image optional horizontal flip,
+ * swap_xy, convert_to_xywh, concat with the class (FCOS/data_preprocess.py:121-131, FCOS/train_fcos.py:131-135).
+ * Input is ragged when box_offsets ([B+1], rows of image b are [off[b], off[b+1])) is given, else padded
+ * [B, in_max_boxes, 4] with optional nbox.  Images with more than max_boxes rows are truncated (out_nbox says so). */
+int dh_prepare_labels(dh_handle_t h, const float* raw_boxes /*[dev]*/, const float* classes /*[dev] float32, indexed like raw_boxes*/,
+                      const int32_t* box_offsets /*[dev] [B+1] or NULL*/, const int32_t* nbox /*[dev] [B] or NULL*/,
+                      const int32_t* flip /*[dev] [B] or NULL*/, int batch, int in_max_boxes, int max_boxes,
+                      float* out_labels /*[dev] [B,max_boxes,5]*/, int32_t* out_nbox /*[dev] [B] or NULL*/, void* stream);
+
+/* RetinaNet.detect_bboxes after the NMS (RetinaNet/retinanet_module.py:559-569): kept rows (y1, x1, y2, x2, score,
+ * label) -> boxes (x1, y1, x2, y2) rescaled by ratios[b] = (w_ratio, h_ratio) exactly as the reference multiplies
+ * them (columns 0 and 2 by w_ratio, 1 and 3 by h_ratio, in float64), scores, integer labels (the caller maps them to
+ * names).  Slots >= n_keep[b] are zero / label -1. */
+int dh_format_detections(dh_handle_t h, const float* rows /*[dev] [B,n,6]*/, const int32_t* n_keep /*[dev] [B]*/,
+                         const float* ratios /*[dev] [B,2]*/, int batch, int n, float* out_boxes /*[dev] [B,n,4]*/,
+                         float* out_scores /*[dev] [B,n]*/, int32_t* out_labels /*[dev] [B,n]*/, void* stream);
+
 /* ---- losses --------------------------------------------------------------------------------- */
 
 /* Channel layout of a row: [0, reg_ch) box regression, then one centerness channel if cen_mode != 0,

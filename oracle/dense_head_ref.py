@@ -546,6 +546,53 @@ def centernet_hourglass_model_loss(y_true, y_pred):
 
 
 # --------------------------------------------------------------------------------------
+# f-3 / f-4  label preparation before the path, result formatting after it
+# --------------------------------------------------------------------------------------
+def swap_xy(boxes):
+    """FCOS/utils.py:6-14 (same in RetinaNet/utils.py, CenterNet/utils.py)."""
+    b = _f32(boxes)
+    return np.stack([b[..., 1], b[..., 0], b[..., 3], b[..., 2]], axis=-1)
+
+
+def convert_to_xywh(boxes):
+    """FCOS/utils.py:16-27 -- [(lo + hi) / 2, hi - lo] in float32."""
+    b = _f32(boxes)
+    return np.concatenate([(b[..., :2] + b[..., 2:]) / F(2), b[..., 2:] - b[..., :2]], axis=-1)
+
+
+def convert_to_corners(boxes):
+    """FCOS/utils.py:29-40 -- [c - size / 2, c + size / 2] in float32."""
+    b = _f32(boxes)
+    return np.concatenate([b[..., :2] - b[..., 2:] / F(2), b[..., :2] + b[..., 2:] / F(2)], axis=-1)
+
+
+def flip_boxes_horizontal(boxes):
+    """The box half of random_flip_horizontal, FCOS/data_preprocess.py:36-39."""
+    b = _f32(boxes)
+    return np.stack([F(1) - b[..., 2], b[..., 1], F(1) - b[..., 0], b[..., 3]], axis=-1)
+
+
+def prepare_labels(bboxes, classes, flip=False):
+    """One image: dataset boxes (xmin, ymin, xmax, ymax) + class ids -> [n, 5] (cy, cx, h, w, class) --
+    random_flip_horizontal (when flipped), swap_xy, convert_to_xywh (FCOS/data_preprocess.py:121-131), then the
+    concat with the class column (FCOS/train_fcos.py:131-135)."""
+    b = _f32(bboxes).reshape(-1, 4)
+    if flip:
+        b = flip_boxes_horizontal(b)
+    b = convert_to_xywh(swap_xy(b))
+    return np.concatenate([b, _f32(classes).reshape(-1, 1)], axis=1).astype(np.float32)
+
+
+def format_detections(rows, w_ratio, h_ratio):
+    """RetinaNet/retinanet_module.py:559-569 after image_detections: `swap_xy(dets[:, :4] * [wr, hr, wr, hr])` (the
+    product is float64 because the ratio array is), scores, integer labels."""
+    r = _f32(rows).reshape(-1, 6)
+    scaled = r[:, :4].astype(np.float64) * np.array([w_ratio, h_ratio, w_ratio, h_ratio], dtype=np.float64)
+    boxes = np.stack([scaled[:, 1], scaled[:, 0], scaled[:, 3], scaled[:, 2]], axis=-1).astype(np.float32)
+    return boxes, r[:, 4].copy(), r[:, 5].astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------
 # f-1  loss gradients (what tf.GradientTape yields for the formulas above; FCOS/train_fcos.py:152-176)
 # --------------------------------------------------------------------------------------
 # Parity unpinned: TensorFlow's autodiff is not available here.  These are the analytic derivatives of the

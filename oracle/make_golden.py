@@ -275,12 +275,33 @@ def decode_nms(tf):
     np.savez_compressed(os.path.join(OUT, "decode_nms.npz"), **d)
 
 
+def prep(tf):
+    """Label preparation helpers (FCOS/utils.py, FCOS/data_preprocess.py) executed from the reference."""
+    utils = R.load("FCOS", "utils")
+    dp = R.load("FCOS", "data_preprocess")
+    rng = np.random.default_rng(synth.seed_for(6, 1))
+    lo = rng.uniform(0.0, 0.7, size=(40, 2)).astype(np.float32)
+    raw = np.concatenate([lo, lo + rng.uniform(0.02, 0.3, size=(40, 2)).astype(np.float32)], axis=1)   # xmin, ymin, xmax, ymax
+    d = {"raw": raw}
+    d["swap_xy"] = f32(utils.swap_xy(tf.constant(raw)))
+    d["to_xywh"] = f32(utils.convert_to_xywh(tf.constant(raw)))
+    d["to_corners"] = f32(utils.convert_to_corners(tf.constant(raw)))
+    img = tf.constant(np.zeros((4, 6, 3), np.float32))
+    _, flipped = dp.random_flip_horizontal(img, tf.constant(raw), p_flip=1.0)
+    _, kept = dp.random_flip_horizontal(img, tf.constant(raw), p_flip=-1.0)
+    d["flipped"] = f32(flipped)
+    assert np.array_equal(f32(kept), raw)
+    d["labels_flipped"] = f32(utils.convert_to_xywh(utils.swap_xy(flipped)))
+    d["labels_plain"] = f32(utils.convert_to_xywh(utils.swap_xy(tf.constant(raw))))
+    np.savez_compressed(os.path.join(OUT, "prep.npz"), **d)
+
+
 def main():
     if not R.available():
         raise SystemExit("reference tree not found at %s" % R.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
     tf = R.tf()
-    for fn in (kat, fcos_family, retina, centernet, losses, decode_nms):
+    for fn in (kat, fcos_family, retina, centernet, losses, decode_nms, prep):
         fn(tf)
         print("wrote", fn.__name__)
     for f in sorted(os.listdir(OUT)):

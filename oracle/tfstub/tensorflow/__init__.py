@@ -320,6 +320,23 @@ class _NN:
 nn = _NN()
 
 
+class _Random:
+    """tf.random.uniform(()) draws from np.random (seed it with np.random.seed for reproducible reference runs)."""
+    @staticmethod
+    def uniform(shape=(), minval=0.0, maxval=1.0, dtype=None):
+        return Tensor(np.random.uniform(minval, maxval, size=tuple(shape)).astype(np.float32))
+
+
+class _Image:
+    @staticmethod
+    def flip_left_right(image):
+        return Tensor(np.asarray(_t(image)._v)[..., :, ::-1, :])
+
+
+random = _Random()
+image = _Image()
+
+
 def constant_initializer(value=0):
     return ("constant_initializer", value)
 

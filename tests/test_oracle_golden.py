@@ -185,3 +185,23 @@ def test_combined_nms_against_torchvision():
     assert v2 == 12 and np.array_equal(os2[:12], np.sort(os2[:12])[::-1])
     for c in range(4):
         assert (oc2[:v2] == c).sum() <= 5
+
+
+def test_label_prep_golden(golden):
+    """f-3: swap_xy / convert_to_xywh / convert_to_corners / horizontal box flip / label assembly against the
+    reference's FCOS/utils.py and FCOS/data_preprocess.py outputs frozen in prep.npz."""
+    z = golden("prep")
+    raw = z["raw"]
+    assert np.array_equal(O.swap_xy(raw), z["swap_xy"])
+    assert np.array_equal(O.convert_to_xywh(raw), z["to_xywh"])
+    assert np.array_equal(O.convert_to_corners(raw), z["to_corners"])
+    assert np.array_equal(O.flip_boxes_horizontal(raw), z["flipped"])
+    cls = np.arange(len(raw), dtype=np.float32) % 7
+    assert np.array_equal(O.prepare_labels(raw, cls)[:, :4], z["labels_plain"])
+    assert np.array_equal(O.prepare_labels(raw, cls, flip=True)[:, :4], z["labels_flipped"])
+    assert np.array_equal(O.prepare_labels(raw, cls)[:, 4], cls)
+    # f-4: detect_bboxes post-processing (retinanet_module.py:559-569), restated: columns 0/2 scale with w_ratio
+    rows = np.array([[10, 20, 30, 40, .9, 3], [1, 2, 3, 4, .5, 0]], np.float32)
+    b, s, l = O.format_detections(rows, 2.0, 0.5)
+    assert np.array_equal(b, np.array([[10, 20, 20, 60], [1, 2, 2, 6]], np.float32))
+    assert s.tolist() == [np.float32(.9), .5] and l.tolist() == [3, 0]
