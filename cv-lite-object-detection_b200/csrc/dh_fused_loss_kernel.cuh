@@ -50,23 +50,34 @@ __device__ __forceinline__ float rcp_unit_newton(float w) {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-// label == 0 element: acc += sigmoid(x)^gamma * softplus(x) / ln 2   (the caller scales by (1 - alpha) * ln 2).
-// With kGrad the derivative of sigmoid^gamma * softplus is returned too (natural units; the caller scales by
-// (1 - alpha) * w_cls):  d/dx = s^g * (g * (1 - s) * softplus(x) + s).
-template <bool kGamma2, bool kNewton, bool kGrad>
+// label == 0 element of the classification loss, accumulated in log2 units.  kCls selects the loss:
+//   0 focal, any gamma   acc += sigmoid(x)^gamma * softplus(x) / ln 2      (the caller scales by (1 - alpha) * ln 2)
+//   1 focal, gamma == 2  the same with the power as one multiply
+//   2 sigmoid BCE        acc += softplus(x) / ln 2                          (the caller scales by ln 2)
+// With kGrad the derivative is returned too, in natural units before the caller's scale ((1 - alpha) * w_cls for
+// focal: d/dx = s^g * (g * (1 - s) * softplus(x) + s);  w_cls for BCE: d/dx = s).
+template <int kCls, bool kNewton, bool kGrad>
 __device__ __forceinline__ float stream_term(float x, float gamma, float& acc) {
     const float u = x * kLog2e;
     const float e = ex2_fast(-fabsf(u));  // exp(-|x|)
     const float w = 1.0f + e;
-    const float inv = kNewton ? rcp_unit_newton(w) : rcp_fast(w);
     const float lg = lg2_fast(w);                    // log2(1 + exp(-|x|))
-    const float s = (x < 0.f ? e : 1.0f) * inv;      // sigmoid(x)
-    const float pw = kGamma2 ? s * s : ex2_fast(gamma * lg2_fast(s));
     const float sp2 = lg + fmaxf(u, 0.f);            // softplus(x) / ln 2
+    if (kCls == 2 && !kGrad) {
+        acc += sp2;
+        return 0.f;
+    }
+    const float inv = kNewton ? rcp_unit_newton(w) : rcp_fast(w);
+    const float s = (x < 0.f ? e : 1.0f) * inv;      // sigmoid(x)
+    if (kCls == 2) {
+        acc += sp2;
+        return s;
+    }
+    const float pw = kCls == 1 ? s * s : ex2_fast(gamma * lg2_fast(s));
     acc = fmaf(pw, sp2, acc);
     if (!kGrad) return 0.f;
     const float om = (x < 0.f ? 1.0f : e) * inv;     // 1 - sigmoid(x)
-    return pw * fmaf((kGamma2 ? 2.0f : gamma) * kLn2 * om, sp2, s);
+    return pw * fmaf((kCls == 1 ? 2.0f : gamma) * kLn2 * om, sp2, s);
 }
 // smooth-L1(0, sigmoid(x)): the centerness term of an all-zero row (FCOS/fcos.py:483-486)
 __device__ __forceinline__ float cen_l1_zero(float x, float delta) {
@@ -97,20 +108,20 @@ struct StreamAcc {
 // ---- the label-free pass over one warp tile: rows [0, nrows) x ch floats starting at `p` --------------------
 // Lane l takes items l, l + 32, l + 64, ... (an item = one 128-bit load in the vector pass, one float in the
 // scalar pass); `c` tracks the item's position inside its row incrementally (no division in the loop).
-template <bool kGamma2, bool kGrad>
+template <int kCls, bool kGrad>
 __device__ __forceinline__ void stream_vec_item(const float4& x, bool is_reg, float gamma, float gscale, StreamAcc& a, float4* g) {
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!is_reg) {  // float4 0 of a row = the 4 regression channels
-        d.x = stream_term<kGamma2, true, kGrad>(x.x, gamma, a.c0);
-        d.y = stream_term<kGamma2, true, kGrad>(x.y, gamma, a.c1);
-        d.z = stream_term<kGamma2, true, kGrad>(x.z, gamma, a.c2);
-        d.w = stream_term<kGamma2, false, kGrad>(x.w, gamma, a.c3);
+        d.x = stream_term<kCls, true, kGrad>(x.x, gamma, a.c0);
+        d.y = stream_term<kCls, true, kGrad>(x.y, gamma, a.c1);
+        d.z = stream_term<kCls, true, kGrad>(x.z, gamma, a.c2);
+        d.w = stream_term<kCls, false, kGrad>(x.w, gamma, a.c3);
     }
     if (kGrad) __stcs(g, make_float4(d.x * gscale, d.y * gscale, d.z * gscale, d.w * gscale));
 }
 // `kstar` = the one k in [0, vpr) at which this lane's item lane + 32 k is float4 0 of a row (tiles start on a row
 // boundary and a lane has at most vpr items per tile, so there is exactly one)
-template <bool kGamma2, bool kGrad, int U>
+template <int kCls, bool kGrad, int U>
 __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int kstar,
                                            int lane, float gamma, float gscale, StreamAcc& a) {
     const float4* __restrict__ ptr = reinterpret_cast<const float4*>(p) + lane;
@@ -123,16 +134,16 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
 #pragma unroll
         for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; ++u) stream_vec_item<kGamma2, kGrad>(x[u], k + u == kstar, gamma, gscale, a, gptr + 32 * u);
+        for (int u = 0; u < U; ++u) stream_vec_item<kCls, kGrad>(x[u], k + u == kstar, gamma, gscale, a, gptr + 32 * u);
     }
 #pragma unroll 1
     for (; k < n_mine; ++k, ptr += 32, gptr += 32) {
         const float4 x = __ldcs(ptr);
-        stream_vec_item<kGamma2, kGrad>(x, k == kstar, gamma, gscale, a, gptr);
+        stream_vec_item<kCls, kGrad>(x, k == kstar, gamma, gscale, a, gptr);
     }
 }
 
-template <bool kGamma2, bool kNewton, bool kGrad>
+template <int kCls, bool kNewton, bool kGrad>
 __device__ __forceinline__ void stream_scalar_item(float x, int c, const LossSpec& sp, float& cls_acc, StreamAcc& a, float* g) {
     float d = 0.f;
     if (c >= sp.reg_ch) {
@@ -145,12 +156,12 @@ __device__ __forceinline__ void stream_scalar_item(float x, int c, const LossSpe
                 if (kGrad) d = sp.w_cen * focal_grad(0.f, x, sp.alpha, sp.gamma);
             }
         } else {
-            d = stream_term<kGamma2, kNewton, kGrad>(x, sp.gamma, cls_acc) * ((1.0f - sp.alpha) * sp.w_cls);
+            d = stream_term<kCls, kNewton, kGrad>(x, sp.gamma, cls_acc) * ((kCls == 2 ? 1.0f : 1.0f - sp.alpha) * sp.w_cls);
         }
     }
     if (kGrad) __stcs(g, d);
 }
-template <bool kGamma2, bool kGrad, int U>
+template <int kCls, bool kGrad, int U>
 __device__ __forceinline__ void stream_scalar(const float* __restrict__ p, float* __restrict__ gout, int nrows, int ch, int c, int step,
                                               int lane, const LossSpec& sp, StreamAcc& a) {
     const float* __restrict__ base = p + lane;
@@ -164,15 +175,15 @@ __device__ __forceinline__ void stream_scalar(const float* __restrict__ p, float
         for (int u = 0; u < U; ++u) x[u] = __ldcs(base + 32 * (k + u));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (u & 1) stream_scalar_item<kGamma2, true, kGrad>(x[u], c, sp, a.c1, a, gbase + 32 * (k + u));
-            else stream_scalar_item<kGamma2, false, kGrad>(x[u], c, sp, a.c0, a, gbase + 32 * (k + u));
+            if (u & 1) stream_scalar_item<kCls, true, kGrad>(x[u], c, sp, a.c1, a, gbase + 32 * (k + u));
+            else stream_scalar_item<kCls, false, kGrad>(x[u], c, sp, a.c0, a, gbase + 32 * (k + u));
             c += step;
             if (c >= ch) c -= ch;
         }
     }
 #pragma unroll 1
     for (; k < n_mine; ++k) {
-        stream_scalar_item<kGamma2, false, kGrad>(__ldcs(base + 32 * k), c, sp, a.c2, a, gbase + 32 * k);
+        stream_scalar_item<kCls, false, kGrad>(__ldcs(base + 32 * k), c, sp, a.c2, a, gbase + 32 * k);
         c += step;
         if (c >= ch) c -= ch;
     }
@@ -220,8 +231,8 @@ __device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __r
             const int c = __ffs(m) - 1 + 32 * wd;
             m &= m - 1;
             const float xc = prow[cls0 + c];
-            acc.cls += focal_term(1.0f, xc, sp.alpha, sp.gamma) - focal_term(0.f, xc, sp.alpha, sp.gamma);
-            if (grow) grow[cls0 + c] = sp.w_cls * focal_grad(1.0f, xc, sp.alpha, sp.gamma);
+            acc.cls += cls_term(sp, 1.0f, xc) - cls_term(sp, 0.f, xc);
+            if (grow) grow[cls0 + c] = sp.w_cls * cls_grad(sp, 1.0f, xc);
         }
     }
     return acc;
@@ -303,14 +314,14 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
 }
 
 // ---- stream: every element of this warp's tiles as if its label were zero -----------------------------------------
-template <class P, bool kGamma2, bool kGrad>
+template <class P, int kCls, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img, int t_begin, int t_end) {
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = a.tt.ch >> 2;
     int kstar = 0;
     while ((lane + 32 * kstar) % vpr != 0) ++kstar;
-    const float gamma = a.spec.gamma, gscale = (1.0f - a.spec.alpha) * a.spec.w_cls;
+    const float gamma = a.spec.gamma, gscale = (kCls == 2 ? 1.0f : 1.0f - a.spec.alpha) * a.spec.w_cls;
     TileCursor cur;
     cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
 #pragma unroll 1
@@ -318,11 +329,11 @@ __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img,
         TileInfo ti;
         float* gg = nullptr;
         const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
-        if (ti.nrows > 0) stream_vec<kGamma2, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, kstar, lane, gamma, gscale, sa);
+        if (ti.nrows > 0) stream_vec<kCls, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, kstar, lane, gamma, gscale, sa);
     }
     return sa;
 }
-template <class P, bool kGamma2, bool kGrad>
+template <class P, int kCls, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int img, int t_begin, int t_end) {
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -336,12 +347,12 @@ __device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int i
         TileInfo ti;
         float* gg = nullptr;
         const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
-        if (ti.nrows > 0) stream_scalar<kGamma2, kGrad, 4>(gp, gg, ti.nrows, ch, c_lane, step, lane, sp, sa);
+        if (ti.nrows > 0) stream_scalar<kCls, kGrad, 4>(gp, gg, ti.nrows, ch, c_lane, step, lane, sp, sa);
     }
     return sa;
 }
 
-template <class P, bool kGamma2, bool kGrad>
+template <class P, int kCls, bool kGrad>
 __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_constant__ LossArgs<P> ga) {
     extern __shared__ __align__(128) unsigned char smem[];
     const FusedSmemLayout lay = fused_smem_layout<P>(ga.box_cap);
@@ -384,14 +395,14 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         }
         if (sub == 0) P::image_prologue(a.pp, recs, n_boxes, img);
 
-        const StreamAcc sa = vec ? stream_pass_vec<P, kGamma2, kGrad>(a, img, t_begin, t_end)
-                                 : stream_pass_scalar<P, kGamma2, kGrad>(a, img, t_begin, t_end);
+        const StreamAcc sa = vec ? stream_pass_vec<P, kCls, kGrad>(a, img, t_begin, t_end)
+                                 : stream_pass_scalar<P, kCls, kGrad>(a, img, t_begin, t_end);
         if (kGrad) __syncwarp();  // this warp's zero-label gradients are written before the matched rows overwrite theirs
         LossAcc acc = {0.f, 0.f, 0.f, 0};  // corrections + regression, natural units
         if (n_boxes > 0) acc = correct_pass<P>(a, recs, n_boxes, cand, img, t_begin, t_end);
 
         // ---- per-chunk reduction -> partials[chunk] -----------------------------------------------------------
-        float cls = ((sa.c0 + sa.c1) + (sa.c2 + sa.c3)) * ((1.0f - ga.spec.alpha) * kLn2) + acc.cls;
+        float cls = ((sa.c0 + sa.c1) + (sa.c2 + sa.c3)) * ((kCls == 2 ? 1.0f : 1.0f - ga.spec.alpha) * kLn2) + acc.cls;
         float cen = sa.cen + acc.cen;
         cls = warp_sum(cls), cen = warp_sum(cen);
         const float reg = warp_sum(acc.reg);

@@ -25,6 +25,7 @@ struct LossSpec {
     int cen_mode;  // 0 no centerness channel, 1 smooth-L1(sigmoid(pred)) over all rows, 2 focal, 3 present but unused
     int reg_mode;  // 0 smooth-L1, 1 -log(IoU) on the integer grid
     int pos_rule;  // 0 max(class) >= 1, 1 max(class) > 0, 2 external per-row mask
+    int cls_mode;  // 0 focal, 1 sigmoid cross-entropy (alpha / gamma unused)
     float alpha, gamma, delta;
     float w_cls, w_reg, w_cen;  // gradient weights: grad = d(w_cls*cls + w_reg*reg + w_cen*cen) / d pred
 };
@@ -185,6 +186,16 @@ __device__ __forceinline__ void iou_loss_grad(const float* t, const float* p, fl
     }
 }
 
+// class-channel term / derivative for either classification loss
+__device__ __forceinline__ float cls_term(const LossSpec& sp, float y, float x) {
+    if (sp.cls_mode == 0) return focal_term(y, x, sp.alpha, sp.gamma);
+    return fmaxf(x, 0.f) - x * y + __logf(1.0f + __expf(-fabsf(x)));  // max(x, 0) - x z + log(1 + exp(-|x|))
+}
+__device__ __forceinline__ float cls_grad(const LossSpec& sp, float y, float x) {
+    if (sp.cls_mode == 0) return focal_grad(y, x, sp.alpha, sp.gamma);
+    return sigmoid_f(x) - y;
+}
+
 struct LossAcc {
     float cls, reg, cen;
     int npos;
@@ -194,7 +205,7 @@ struct LossAcc {
 __device__ __forceinline__ void accumulate_element(const LossSpec& sp, int cls0, int c, float x, float y, float m,
                                                    LossAcc& acc) {
     if (c >= cls0) {
-        acc.cls += focal_term(y, x, sp.alpha, sp.gamma);
+        acc.cls += cls_term(sp, y, x);
     } else if (c < sp.reg_ch) {
         if (sp.reg_mode == 0 && m != 0.f) acc.reg += m * smooth_l1_term(y, x, sp.delta);
     } else if (sp.cen_mode == 1) {
@@ -352,8 +363,11 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                         const bool is_reg = sp.reg_ch > 0 && c4 == 0;
                         if (kFused && (ncand == 0 || !rowpos[r])) {  // label-free fast path
                             if (!is_reg) {
-                                acc.cls += focal_neg(x[u].x, oma, sp.gamma) + focal_neg(x[u].y, oma, sp.gamma) +
-                                           focal_neg(x[u].z, oma, sp.gamma) + focal_neg(x[u].w, oma, sp.gamma);
+                                if (sp.cls_mode == 0)
+                                    acc.cls += focal_neg(x[u].x, oma, sp.gamma) + focal_neg(x[u].y, oma, sp.gamma) +
+                                               focal_neg(x[u].z, oma, sp.gamma) + focal_neg(x[u].w, oma, sp.gamma);
+                                else
+                                    acc.cls += cls_term(sp, 0.f, x[u].x) + cls_term(sp, 0.f, x[u].y) + cls_term(sp, 0.f, x[u].z) + cls_term(sp, 0.f, x[u].w);
                             }
                             continue;
                         }
@@ -386,11 +400,10 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                                 }
                             }
                         } else {
-                            acc.cls += focal_term(y.x, x[u].x, sp.alpha, sp.gamma) + focal_term(y.y, x[u].y, sp.alpha, sp.gamma) +
-                                       focal_term(y.z, x[u].z, sp.alpha, sp.gamma) + focal_term(y.w, x[u].w, sp.alpha, sp.gamma);
+                            acc.cls += cls_term(sp, y.x, x[u].x) + cls_term(sp, y.y, x[u].y) + cls_term(sp, y.z, x[u].z) + cls_term(sp, y.w, x[u].w);
                             if (gg)
-                                gv = make_float4(sp.w_cls * focal_grad(y.x, x[u].x, sp.alpha, sp.gamma), sp.w_cls * focal_grad(y.y, x[u].y, sp.alpha, sp.gamma),
-                                                 sp.w_cls * focal_grad(y.z, x[u].z, sp.alpha, sp.gamma), sp.w_cls * focal_grad(y.w, x[u].w, sp.alpha, sp.gamma));
+                                gv = make_float4(sp.w_cls * cls_grad(sp, y.x, x[u].x), sp.w_cls * cls_grad(sp, y.y, x[u].y),
+                                                 sp.w_cls * cls_grad(sp, y.z, x[u].z), sp.w_cls * cls_grad(sp, y.w, x[u].w));
                         }
                         if (gg) __stcs(reinterpret_cast<float4*>(gg) + q, gv);
                     }
@@ -433,7 +446,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                         if (gg) {
                             float g = 0.f;
                             if (c >= cls0) {
-                                g = sp.w_cls * focal_grad(y, x[u], sp.alpha, sp.gamma);
+                                g = sp.w_cls * cls_grad(sp, y, x[u]);
                             } else if (c < sp.reg_ch) {
                                 if (m != 0.f) {
                                     if (sp.reg_mode == 0) {

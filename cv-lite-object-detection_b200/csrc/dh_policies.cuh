@@ -13,7 +13,7 @@
 namespace dh {
 
 enum FcosMode { FCOS_FOOTPRINT = 0, FCOS_CENTER3X3 = 1, FCOS_CENTER_ONLY = 2, FCOS_CENTER_V1 = 3 };
-enum CenterNetMode { CN_ONEHOT_SCALES = 0, CN_HOURGLASS = 1, CN_POWER_FALLOFF = 2 };
+enum CenterNetMode { CN_ONEHOT_SCALES = 0, CN_HOURGLASS = 1, CN_POWER_FALLOFF = 2, CN_HOURGLASS4 = 3 };
 
 struct Corners {
     float y0, x0, y1, x1;
@@ -400,7 +400,7 @@ struct CenterNetPolicy {
     static constexpr bool kScatter = true;  // centre-cell modes: one thread per box writes its single row
     __device__ static bool use_scatter(const Params& p) { return p.mode != CN_POWER_FALLOFF; }
 
-    __device__ static int reg_ch(const Params& p) { return p.mode == CN_POWER_FALLOFF ? 5 : 4; }
+    __device__ static int reg_ch(const Params& p) { return (p.mode == CN_POWER_FALLOFF || p.mode == CN_HOURGLASS4) ? 5 : 4; }
 
     __device__ static void make_record(const Params& p, const float* g, float hi, float wi, int k, Rec& r) {
         const Corners c = pixel_corners(g, hi, wi);
@@ -436,6 +436,36 @@ struct CenterNetPolicy {
             }
             if (r.ry0 < 0 || r.rx0 < 0 || r.ry0 >= hl || r.rx0 >= wl) flags = 0;
             r.flags = flags;
+            return;
+        }
+        if (p.mode == CN_HOURGLASS4) {  // the inline encoder of CenterNet/train_hourglass_voc.py:99-153
+            const int n_map_y = static_cast<int>(static_cast<double>(p.pad0) / p.stride);
+            const int n_map_x = static_cast<int>(static_cast<double>(p.pad1) / p.stride);
+            const float pad_y = static_cast<float>(trunc_i(fdiv(fsub(static_cast<float>(p.pad0), hi), 2.0f)));  // :93
+            const float pad_x = static_cast<float>(trunc_i(fdiv(fsub(static_cast<float>(p.pad1), wi), 2.0f)));
+            const float y_cen = fadd(pad_y, fmul(g[0], hi)), x_cen = fadd(pad_x, fmul(g[1], wi));  // :118-119
+            const float bh = fmul(g[2], hi), bw = fmul(g[3], wi);                                   // :120-121
+            r.area = fmul(fmul(g[3], g[2]), 100.0f);                                                // :110-111
+            if (bw < 0.f || bh < 0.f) {  // :123-124
+                r.flags = 0;
+                return;
+            }
+            int sc = p.n_scales - 1;  // :125-138: the first scale that exceeds BOTH sides, else the last
+            for (int n = 0; n < p.n_scales - 1; ++n)
+                if (bw < p.scales[n] && bh < p.scales[n]) {
+                    sc = n;
+                    break;
+                }
+            const int i = trunc_i(fdiv(y_cen, s)), j = trunc_i(fdiv(x_cen, s));  // :142-143
+            if (i < 0 || j < 0 || i >= n_map_y || j >= n_map_x) {
+                r.flags = 0;
+                return;
+            }
+            r.r0 = fdiv(fsub(y_cen, static_cast<float>(i * p.stride)), s);  // :144-145
+            r.r1 = fdiv(fsub(x_cen, static_cast<float>(j * p.stride)), s);
+            r.r2 = fdiv(bh, p.scales[sc]);                                   // :140-141
+            r.r3 = fdiv(bw, p.scales[sc]);
+            r.row = (i * n_map_x + j) * p.n_scales + sc;
             return;
         }
         // centre-cell encoders; note the reference's swapped pad indices (tf_centernet_resnet_s8.py:259-262)
@@ -509,7 +539,8 @@ struct CenterNetPolicy {
             const Rec& r = recs[k];
             const int local = r.row - ti.r0;
             float* dst = tile + local * ch;
-            dst[4 + r.cls] = 1.0f;
+            if (p.mode == CN_HOURGLASS4) dst[4] = 1.0f, dst[5 + r.cls] = 1.0f;  // objectness + class (:148-150)
+            else dst[4 + r.cls] = 1.0f;
             bool wins = true;
             for (int q2 = 0; q2 < ncand; ++q2) {
                 const int k2 = cand[q2];
@@ -541,7 +572,8 @@ struct CenterNetPolicy {
                 const Rec& r = recs[k];
                 if (r.row != row) continue;
                 ++hits;
-                dst.cls(4, r.cls);
+                if (p.mode == CN_HOURGLASS4) dst.cls(4, 0), dst.cls(4, r.cls + 1);  // ch 4 = objectness, then the classes
+                else dst.cls(4, r.cls);
                 if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
             }
             if (best < 0) return 0;

@@ -164,26 +164,28 @@ int fill_retina(RetinaPolicy::Params& p, TileTable& tt, int pad_h, int pad_w, in
 int fill_centernet(CenterNetPolicy::Params& p, TileTable& tt, int pad0, int pad1, int stride, int n_scales,
                    const float* box_scales, float sigma, int num_classes, int mode, float* out, const float* pred,
                    int32_t* status, const char* who) {
-    DH_FILL_CHECK(mode >= 0 && mode <= 2, "%s: mode %d", who, mode);
+    DH_FILL_CHECK(mode >= 0 && mode <= 3, "%s: mode %d", who, mode);
     DH_FILL_CHECK(mode != DH_CENTERNET_ONEHOT_SCALES || (box_scales && n_scales >= 1 && n_scales <= 8),
                   "%s: mode 0 needs 1..8 box_scales", who);
     DH_FILL_CHECK(pad0 > 0 && pad1 > 0 && stride > 0, "%s: bad sizes", who);
     DH_FILL_CHECK(num_classes >= 1 && num_classes <= 4096, "%s: num_classes %d", who, num_classes);
     p.mode = mode, p.num_classes = num_classes, p.stride = stride, p.stride_f = static_cast<float>(stride);
     p.sigma = sigma, p.pad0 = pad0, p.pad1 = pad1, p.status = status;
-    p.n_scales = (mode == DH_CENTERNET_ONEHOT_SCALES) ? n_scales : 1;
+    p.n_scales = (mode == DH_CENTERNET_ONEHOT_SCALES) ? n_scales : (mode == DH_CENTERNET_HOURGLASS4 ? 4 : 1);
     for (int n = 0; n < p.n_scales && mode == DH_CENTERNET_ONEHOT_SCALES; ++n) p.scales[n] = box_scales[n];
+    if (mode == DH_CENTERNET_HOURGLASS4)  // img_dims / (8, 4, 2, 1), train_hourglass_voc.py:96-97 (square padded image)
+        for (int n = 0; n < 4; ++n) p.scales[n] = static_cast<float>(static_cast<double>(pad0) / (1 << (3 - n)));
     MapDesc& md = tt.maps[0];
     tt.n_maps = 1;
     int hh, ww;
-    if (mode == DH_CENTERNET_POWER_FALLOFF) {
+    if (mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_HOURGLASS4) {
         hh = static_cast<int>(static_cast<double>(pad0) / stride);
         ww = static_cast<int>(static_cast<double>(pad1) / stride);
     } else {  // the reference swaps the indices (tf_centernet_resnet_s8.py:259-260)
         hh = static_cast<int>(static_cast<double>(pad1) / stride);
         ww = static_cast<int>(static_cast<double>(pad0) / stride);
     }
-    const int ch = num_classes + (mode == DH_CENTERNET_POWER_FALLOFF ? 5 : 4);
+    const int ch = num_classes + ((mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4);
     md.out = out;
     md.pred = pred;
     md.height = hh, md.width = ww, md.sub = p.n_scales, md.level = 0, md.anchor = 0;
@@ -248,7 +250,7 @@ int dh_centernet_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, 
     int rc = fill_centernet(a.pp, a.tt, pad0, pad1, stride, n_scales, box_scales, sigma, num_classes, mode, out, nullptr,
                             status, "dh_centernet_encode");
     if (rc) return rc;
-    const int ch = num_classes + (mode == DH_CENTERNET_POWER_FALLOFF ? 5 : 4);
+    const int ch = num_classes + ((mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4);
     a.tile_buf_bytes = finish_table(a.tt, ch, batch, auto_tile_bytes(a.tt, ch, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));

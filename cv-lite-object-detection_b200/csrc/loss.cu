@@ -12,6 +12,7 @@ static int check_spec(const LossSpec& s, const char* who) {
     if (s.cen_mode < 0 || s.cen_mode > 3) return set_error(DH_ERR_BAD_ARG, "%s: cen_mode %d", who, s.cen_mode);
     if (s.reg_mode < 0 || s.reg_mode > 1) return set_error(DH_ERR_BAD_ARG, "%s: reg_mode %d", who, s.reg_mode);
     if (s.pos_rule < 0 || s.pos_rule > 2) return set_error(DH_ERR_BAD_ARG, "%s: pos_rule %d", who, s.pos_rule);
+    if (s.cls_mode < 0 || s.cls_mode > 1) return set_error(DH_ERR_BAD_ARG, "%s: cls_mode %d", who, s.cls_mode);
     return DH_OK;
 }
 
@@ -96,18 +97,18 @@ static int finalize_loss(dh_handle_s* h, const float* partials, int batch, int c
 }
 
 // Fused encode+loss, stream + correct formulation (dh_fused_loss_kernel.cuh): 256-row tiles, 32 rows per warp.
-template <class P, bool kGamma2, bool kGrad>
+template <class P, int kCls, bool kGrad>
 static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, float* out_total, cudaStream_t st,
                           const char* who) {
     const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
     const FusedSmemLayout lay = fused_smem_layout<P>(a.box_cap);
     static bool attr_done = false;
     if (!attr_done) {
-        DH_CUDA(cudaFuncSetAttribute(fused_loss_kernel<P, kGamma2, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DH_CUDA(cudaFuncSetAttribute(fused_loss_kernel<P, kCls, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     int per_sm = 1;
-    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kGamma2, kGrad>, DH_THREADS, lay.total));
+    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kCls, kGrad>, DH_THREADS, lay.total));
     if (per_sm < 1) per_sm = 1;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
     // image-aligned chunks: aim at >= 8 chunks per CTA, 2..32 tiles (512..8192 rows) each
@@ -128,7 +129,7 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     if (total > 0) {
         a.sched = next_sched_counter(h, st);
         if (!a.sched) return DH_ERR_CUDA;
-        fused_loss_kernel<P, kGamma2, kGrad><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+        fused_loss_kernel<P, kCls, kGrad><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
         DH_CUDA(cudaGetLastError());
         h->launches += 1;
     }
@@ -161,12 +162,15 @@ static int launch_fused(dh_handle_s* h, LossArgs<P>& a, int num_classes, float* 
         if (a.grad_maps[m]) grad = true;
         if (reinterpret_cast<uintptr_t>(a.grad_maps[m]) & 15u) a.allow_vec = 0;
     }
+    const int kind = a.spec.cls_mode == 1 ? 2 : (a.spec.gamma == 2.0f ? 1 : 0);
     if (grad) {
-        if (a.spec.gamma == 2.0f) return launch_fused_g<P, true, true>(h, a, out_per_image, out_total, st, who);
-        return launch_fused_g<P, false, true>(h, a, out_per_image, out_total, st, who);
+        if (kind == 2) return launch_fused_g<P, 2, true>(h, a, out_per_image, out_total, st, who);
+        if (kind == 1) return launch_fused_g<P, 1, true>(h, a, out_per_image, out_total, st, who);
+        return launch_fused_g<P, 0, true>(h, a, out_per_image, out_total, st, who);
     }
-    if (a.spec.gamma == 2.0f) return launch_fused_g<P, true, false>(h, a, out_per_image, out_total, st, who);
-    return launch_fused_g<P, false, false>(h, a, out_per_image, out_total, st, who);
+    if (kind == 2) return launch_fused_g<P, 2, false>(h, a, out_per_image, out_total, st, who);
+    if (kind == 1) return launch_fused_g<P, 1, false>(h, a, out_per_image, out_total, st, who);
+    return launch_fused_g<P, 0, false>(h, a, out_per_image, out_total, st, who);
 }
 
 }  // namespace dh
@@ -181,7 +185,7 @@ struct GradOut {
 
 static int dense_loss_impl(const GradOut* go, dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
                   const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
-                  const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                  const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule, int cls_mode,
                   float alpha, float gamma, float delta, float* out_per_image, float* out_total, void* stream) {
     DH_CHECK_ARG(h && target_maps && pred_maps && map_height && map_width, "dh_dense_loss: NULL argument");
     DH_CHECK_ARG(n_maps >= 1 && n_maps <= DH_MAX_MAPS, "dh_dense_loss: n_maps %d not in [1,%d]", n_maps, DH_MAX_MAPS);
@@ -190,6 +194,7 @@ static int dense_loss_impl(const GradOut* go, dh_handle_t h, int n_maps, const f
     LossArgs<NoPolicy> a;
     memset(&a, 0, sizeof(a));
     a.spec.reg_ch = reg_ch, a.spec.cen_mode = cen_mode, a.spec.reg_mode = reg_mode, a.spec.pos_rule = pos_rule;
+    a.spec.cls_mode = cls_mode;
     a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
     int rc = check_spec(a.spec, "dh_dense_loss");
     if (rc) return rc;
@@ -288,7 +293,7 @@ static int retina_encode_loss_impl(const GradOut* go, dh_handle_t h, const float
 
 static int centernet_encode_loss_impl(const GradOut* go, dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
                              int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
-                             float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                             float sigma, int num_classes, int mode, const float* pred, int reg_mode, int cls_mode, float alpha,
                              float gamma, float delta, float* out_per_image, float* out_total, int32_t* status,
                              void* stream) {
     DH_CHECK_ARG(h && boxes && img_dim && pred, "dh_centernet_encode_loss: NULL argument");
@@ -305,10 +310,11 @@ static int centernet_encode_loss_impl(const GradOut* go, dh_handle_t h, const fl
     const bool falloff = mode == DH_CENTERNET_POWER_FALLOFF;
     a.spec.reg_ch = 4, a.spec.cen_mode = falloff ? 1 : 0, a.spec.reg_mode = falloff ? reg_mode : 0;
     a.spec.pos_rule = falloff ? 0 : 1;  // tf_centernet.py:435 (>= 1) vs tf_centernet_resnet_s8.py:376 (> 0)
+    a.spec.cls_mode = cls_mode;
     a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
     rc = check_spec(a.spec, "dh_centernet_encode_loss");
     if (rc) return rc;
-    a.tt.ch = num_classes + (falloff ? 5 : 4), a.tt.batch = batch;
+    a.tt.ch = num_classes + ((falloff || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4), a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
     if (go) {
@@ -323,20 +329,20 @@ extern "C" {
 
 int dh_dense_loss(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
                   const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
-                  const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                  const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule, int cls_mode,
                   float alpha, float gamma, float delta, float* out_per_image, float* out_total, void* stream) {
     return dense_loss_impl(nullptr, h, n_maps, target_maps, pred_maps, mask_maps, map_height, map_width, map_sub, batch, ch, reg_ch,
-                           cen_mode, reg_mode, pos_rule, alpha, gamma, delta, out_per_image, out_total, stream);
+                           cen_mode, reg_mode, pos_rule, cls_mode, alpha, gamma, delta, out_per_image, out_total, stream);
 }
 int dh_dense_loss_grad(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
                        const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
-                       const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                       const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule, int cls_mode,
                        float alpha, float gamma, float delta, float w_cls, float w_reg, float w_cen, float* const* grad_maps,
                        float* out_per_image, float* out_total, void* stream) {
     DH_CHECK_ARG(grad_maps, "dh_dense_loss_grad: grad_maps is NULL");
     const GradOut go = {w_cls, w_reg, w_cen, grad_maps};
     return dense_loss_impl(&go, h, n_maps, target_maps, pred_maps, mask_maps, map_height, map_width, map_sub, batch, ch, reg_ch,
-                           cen_mode, reg_mode, pos_rule, alpha, gamma, delta, out_per_image, out_total, stream);
+                           cen_mode, reg_mode, pos_rule, cls_mode, alpha, gamma, delta, out_per_image, out_total, stream);
 }
 
 int dh_fcos_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
@@ -380,22 +386,22 @@ int dh_retina_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t*
 
 int dh_centernet_encode_loss(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
                              int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
-                             float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                             float sigma, int num_classes, int mode, const float* pred, int reg_mode, int cls_mode, float alpha,
                              float gamma, float delta, float* out_per_image, float* out_total, int32_t* status,
                              void* stream) {
     return centernet_encode_loss_impl(nullptr, h, boxes, nbox, img_dim, batch, max_boxes, pad0, pad1, stride, n_scales, box_scales, sigma,
-                                      num_classes, mode, pred, reg_mode, alpha, gamma, delta, out_per_image, out_total, status, stream);
+                                      num_classes, mode, pred, reg_mode, cls_mode, alpha, gamma, delta, out_per_image, out_total, status, stream);
 }
 int dh_centernet_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
                                   int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
-                                  float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                                  float sigma, int num_classes, int mode, const float* pred, int reg_mode, int cls_mode, float alpha,
                                   float gamma, float delta, float w_cls, float w_reg, float w_cen, float* grad,
                                   float* out_per_image, float* out_total, int32_t* status, void* stream) {
     DH_CHECK_ARG(grad, "dh_centernet_encode_loss_grad: grad is NULL");
     float* const levels[1] = {grad};
     const GradOut go = {w_cls, w_reg, w_cen, levels};
     return centernet_encode_loss_impl(&go, h, boxes, nbox, img_dim, batch, max_boxes, pad0, pad1, stride, n_scales, box_scales, sigma,
-                                      num_classes, mode, pred, reg_mode, alpha, gamma, delta, out_per_image, out_total, status, stream);
+                                      num_classes, mode, pred, reg_mode, cls_mode, alpha, gamma, delta, out_per_image, out_total, status, stream);
 }
 
 }  // extern "C"

@@ -56,14 +56,14 @@ def lib():
         L.dh_retina_encode.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, I, c_fp, F, I, ctypes.POINTER(c_vp), P, P]
         L.dh_centernet_encode.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, P, P]
         PP = ctypes.POINTER(c_vp)
-        L.dh_dense_loss.argtypes = [P, I, PP, PP, PP, c_ip, c_ip, c_ip, I, I, I, I, I, I, F, F, F, P, P, P]
+        L.dh_dense_loss.argtypes = [P, I, PP, PP, PP, c_ip, c_ip, c_ip, I, I, I, I, I, I, I, F, F, F, P, P, P]
         L.dh_fcos_encode_loss.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, c_fp, I, I, PP, I, I, F, F, F, P, P, P, P]
         L.dh_retina_encode_loss.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, I, c_fp, F, I, PP, F, F, F, P, P, P, P]
-        L.dh_centernet_encode_loss.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, I, F, F, F, P, P, P, P]
-        L.dh_dense_loss_grad.argtypes = [P, I, PP, PP, PP, c_ip, c_ip, c_ip, I, I, I, I, I, I, F, F, F, F, F, F, PP, P, P, P]
+        L.dh_centernet_encode_loss.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, I, I, F, F, F, P, P, P, P]
+        L.dh_dense_loss_grad.argtypes = [P, I, PP, PP, PP, c_ip, c_ip, c_ip, I, I, I, I, I, I, I, F, F, F, F, F, F, PP, P, P, P]
         L.dh_fcos_encode_loss_grad.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, c_fp, I, I, PP, I, I, F, F, F, F, F, F, PP, P, P, P, P]
         L.dh_retina_encode_loss_grad.argtypes = [P, P, P, P, I, I, I, I, I, c_ip, I, c_fp, F, I, PP, F, F, F, F, F, PP, P, P, P, P]
-        L.dh_centernet_encode_loss_grad.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, I, F, F, F, F, F, F, P, P, P, P, P]
+        L.dh_centernet_encode_loss_grad.argtypes = [P, P, P, P, I, I, I, I, I, I, c_fp, F, I, I, P, I, I, F, F, F, F, F, F, P, P, P, P, P]
         L.dh_prediction_to_corners.argtypes = [P, P, I, I, I, I, I, I, F, F, F, c_fp, P, P]
         L.dh_fcos_decode.argtypes = [P, PP, I, I, I, I, c_ip, I, I, P, P, P]
         L.dh_retina_decode.argtypes = [P, PP, I, I, I, I, c_ip, I, P, I, P, P]

@@ -7,13 +7,15 @@ from . import _capi, infer, losses
 from ._batch import image_dims, pack_labels
 from ._tensors import as_host, current_device, stream_ptr, to_device
 
-MODES = {"s8": 0, "hourglass": 1, "falloff": 2}
+MODES = {"s8": 0, "hourglass": 1, "falloff": 2, "hourglass4": 3}
 
 
 def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, stride=8, mode="s8", box_scales=None, sigma=0.25,
                       out=None, status=None, stream=None):
     """Encode a padded batch.  Output shape: s8 [B, H, W, S, C+4]; hourglass [B, H, W, C+4];
-    falloff [B, H, W, C+5].  `img_pad` is passed through with the reference's own indexing."""
+    falloff [B, H, W, C+5]; hourglass4 [B, H, W, 4, C+5] (the inline encoder of train_hourglass_voc.py:99-153: `img_dim` is
+    the unpadded square side per image, `img_pad` the padded one).  `img_pad` is passed through with the reference's own
+    indexing."""
     dev = current_device()
     boxes_d = to_device(boxes, torch.float32, dev)
     if boxes_d.dim() != 3 or boxes_d.shape[2] != 5:
@@ -31,6 +33,8 @@ def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, stride=8, mode
         shape = (batch, int(pad1 / stride), int(pad0 / stride), len(scales), num_classes + 4)
     elif m == 1:
         shape = (batch, int(pad1 / stride), int(pad0 / stride), num_classes + 4)
+    elif m == 3:
+        shape = (batch, int(pad0 / stride), int(pad1 / stride), 4, num_classes + 5)
     else:
         shape = (batch, int(pad0 / stride), int(pad1 / stride), num_classes + 5)
     if out is None:
@@ -103,6 +107,29 @@ def model_loss_hourglass(y_true, y_pred):
     return tot[0], tot[1]
 
 
+def format_data_hourglass4(gt_labels, raw_dims, img_dims, num_classes, stride=8):
+    """The 4-scale encoder CenterNet/train_hourglass_voc.py:99-153 keeps inline: one image's (cy, cx, h, w, class) rows
+    (normalised by the unpadded side `raw_dims`) -> device tensor [img_dims/8, img_dims/8, 4, C+5]."""
+    g = as_host(gt_labels, np.float32).reshape(-1, 5)
+    boxes, nbox = pack_labels([g])
+    out, _ = format_data_batch(boxes, nbox, [[raw_dims, raw_dims]], num_classes, [int(img_dims), int(img_dims)], stride, "hourglass4")
+    return out[0]
+
+
+def model_loss_hourglass4(bboxes, masks, outputs, loss_type="sigmoid"):
+    """CenterNet/tf_hourglass_net.py:372 `model_loss(bboxes, masks, outputs)` on [B, H, W, 4, C+5] maps and a [B, H, W, 4]
+    mask -> (total_cls_loss, total_reg_loss): sigmoid cross-entropy (or focal) over channels 4:, masked L1 over :4."""
+    dev = current_device()
+    yt = to_device(bboxes, torch.float32, dev).contiguous()
+    yp = to_device(outputs, torch.float32, dev).contiguous()
+    m = to_device(masks, torch.float32, dev).contiguous()
+    b, h, w, s, ch = (int(v) for v in yp.shape)
+    _, tot = losses.dense_loss([yt], [yp], [(h, w, s)], b, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_MASK,
+                               delta=0.0, masks=[m.reshape(b, -1)],
+                               cls_mode=losses.CLS_SIGMOID_BCE if loss_type == "sigmoid" else losses.CLS_FOCAL)
+    return tot[0], tot[1]
+
+
 def model_loss(y_true, y_pred, reg_type="l1", cen_type="l1"):
     """CenterNet/tf_centernet.py:428 `model_loss`: y_true [H, W, C+5], y_pred [1, H, W, C+5] (or batched)."""
     dev = current_device()
@@ -120,7 +147,7 @@ def model_loss(y_true, y_pred, reg_type="l1", cen_type="l1"):
 
 
 def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride=8, mode="s8", box_scales=None,
-                      sigma=0.25, reg_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
+                      sigma=0.25, reg_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None, cls_type="focal"):
     """Fused CenterNet encode + loss.  Returns (per_image [B,4], total [4], status [1]); with `weights` = (w_cls,
     w_reg, w_cen) a fourth item, the gradient d(w . {cls, reg, cen}) / d y_pred (dh_centernet_encode_loss_grad)."""
     dev = current_device()
@@ -140,7 +167,8 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
             _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
             int(img_pad[0]), int(img_pad[1]), int(stride), len(scales), _capi.float_array(scales) if scales else None,
             float(sigma), int(num_classes), MODES[mode], yp.data_ptr(),
-            losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1, float(alpha), float(gamma), float(delta),
+            losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1,
+            losses.CLS_SIGMOID_BCE if cls_type == "sigmoid" else losses.CLS_FOCAL, float(alpha), float(gamma), float(delta),
             float(weights[0]), float(weights[1]), float(weights[2]), grad.data_ptr(), out_pi.data_ptr(), out_tot.data_ptr(),
             status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode_loss_grad")
         return out_pi, out_tot, status, grad
@@ -148,7 +176,8 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
         _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
         int(img_pad[0]), int(img_pad[1]), int(stride), len(scales), _capi.float_array(scales) if scales else None,
         float(sigma), int(num_classes), MODES[mode], yp.data_ptr(),
-        losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1, float(alpha), float(gamma), float(delta),
+        losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1,
+        losses.CLS_SIGMOID_BCE if cls_type == "sigmoid" else losses.CLS_FOCAL, float(alpha), float(gamma), float(delta),
         out_pi.data_ptr(), out_tot.data_ptr(), status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode_loss")
     return out_pi, out_tot, status
 

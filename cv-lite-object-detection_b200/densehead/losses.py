@@ -14,10 +14,11 @@ from ._tensors import current_device, stream_ptr, to_device
 CEN_NONE, CEN_SMOOTH_L1, CEN_FOCAL, CEN_IGNORE = 0, 1, 2, 3
 REG_SMOOTH_L1, REG_IOU = 0, 1
 POS_GE1, POS_GT0, POS_MASK = 0, 1, 2
+CLS_FOCAL, CLS_SIGMOID_BCE = 0, 1
 
 
 def dense_loss(targets, preds, shapes, batch, ch, reg_ch, cen_mode, reg_mode, pos_rule, alpha=0.25, gamma=2.0,
-               delta=1.0, masks=None, per_image=True, stream=None, weights=None):
+               delta=1.0, masks=None, per_image=True, stream=None, weights=None, cls_mode=CLS_FOCAL):
     """targets/preds: lists of contiguous float32 device tensors, map m holding [B, H*W*sub, ch] rows.
     shapes: list of (H, W, sub).  Returns (per_image [B,4] or None, total [4]); with `weights` = (w_cls, w_reg,
     w_cen) also the gradient maps d(w . {cls, reg, cen}) / d preds (dh_dense_loss_grad, same pass)."""
@@ -33,7 +34,7 @@ def dense_loss(targets, preds, shapes, batch, ch, reg_ch, cen_mode, reg_mode, po
               _capi.ptr_array([m.data_ptr() for m in masks]) if masks is not None else None,
               _capi.int_array([s[0] for s in shapes]), _capi.int_array([s[1] for s in shapes]),
               _capi.int_array([s[2] for s in shapes]), int(batch), int(ch), int(reg_ch), int(cen_mode), int(reg_mode),
-              int(pos_rule), float(alpha), float(gamma), float(delta)]
+              int(pos_rule), int(cls_mode), float(alpha), float(gamma), float(delta)]
     outs = [out_pi.data_ptr() if per_image else None, out_tot.data_ptr(), stream_ptr(stream)]
     if weights is None:
         _capi.check(_capi.lib().dh_dense_loss(*(common + outs)), "dh_dense_loss")

@@ -97,13 +97,16 @@ int dh_retina_encode(dh_handle_t h,
 /* CenterNet encoders.  mode 0: tf_centernet_resnet_s8.format_data (CenterNet/tf_centernet_resnet_s8.py:
  * 243-330), out [B,H,W,S,C+4]; mode 1: tf_centernet_hourglass.format_data (CenterNet/
  * tf_centernet_hourglass.py:379-456), out [B,H,W,C+4]; mode 2: tf_centernet.format_data
- * (CenterNet/tf_centernet.py:152-342, inverse-power fall-off heat), out [B,H,W,C+5].
+ * (CenterNet/tf_centernet.py:152-342, inverse-power fall-off heat), out [B,H,W,C+5]; mode 3: the 4-scale encoder that
+ * CenterNet/train_hourglass_voc.py:99-153 keeps inline in train(): out [B,H,W,4,C+5] = (h_off, w_off, h_reg, w_reg,
+ * objectness, classes), scales = pad0 / (8, 4, 2, 1), image offset int((pad - img_dim) / 2) (box_scales is ignored).
  * pad0/pad1 are img_pad[0]/img_pad[1] exactly as the reference indexes them (modes 0 and 1 swap
  * them, tf_centernet_resnet_s8.py:259-262).  status (optional, [dev] int32, zeroed by the call)
  * gets bit 0 set when a box is not below the largest box scale (the reference raises ValueError). */
 #define DH_CENTERNET_ONEHOT_SCALES 0
 #define DH_CENTERNET_HOURGLASS 1
 #define DH_CENTERNET_POWER_FALLOFF 2
+#define DH_CENTERNET_HOURGLASS4 3
 int dh_centernet_encode(dh_handle_t h,
                         const float* boxes, const int32_t* nbox, const float* img_dim,
                         int batch, int max_boxes, int pad0, int pad1, int stride,
@@ -151,10 +154,13 @@ int dh_format_detections(dh_handle_t h, const float* rows /*[dev] [B,n,6]*/, con
  *             DH_CEN_IGNORE    channel present, contributes 0 (fcos.py model_loss with cen_type != "l1")
  *   reg_mode  DH_REG_SMOOTH_L1 where(|d| < delta, d^2/2, |d|) over positive rows (FCOS/fcos.py:380-391)
  *             DH_REG_IOU       -log(IoU + 1e-12) on the integer grid over positive rows (FCOS/fcos.py:393-441)
+ *   cls_mode  DH_CLS_FOCAL (alpha, gamma) or DH_CLS_SIGMOID_BCE (CenterNet/tf_hourglass_net.py:347-349, :381-382)
  *   pos_rule  DH_POS_GE1 max(class) >= 1 (fcos.py:475-477), DH_POS_GT0 max(class) > 0
  *             (retinanet_module.py:416-418), DH_POS_MASK caller-supplied per-row float mask.
  * Outputs are float32 {cls, reg, cen, n_pos}: out_per_image [B,4] and/or out_total [4] (either may be
  * NULL, not both).  Summation order is fixed, so results are run-to-run deterministic.            */
+#define DH_CLS_FOCAL 0
+#define DH_CLS_SIGMOID_BCE 1 /* tf.nn.sigmoid_cross_entropy_with_logits summed (CenterNet/tf_hourglass_net.py:347-349) */
 #define DH_CEN_NONE 0
 #define DH_CEN_SMOOTH_L1 1
 #define DH_CEN_FOCAL 2
@@ -174,7 +180,7 @@ int dh_dense_loss(dh_handle_t h, int n_maps,
                   const float* const* mask_maps /*[host] n_maps [dev] ptrs [B,rows], DH_POS_MASK only, else NULL*/,
                   const int32_t* map_height /*[host]*/, const int32_t* map_width /*[host]*/,
                   const int32_t* map_sub /*[host] rows per cell, or NULL (=1)*/,
-                  int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                  int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule, int cls_mode,
                   float alpha, float gamma, float delta,
                   float* out_per_image /*[dev] [B,4] or NULL*/, float* out_total /*[dev] [4] or NULL*/,
                   void* stream);
@@ -203,7 +209,8 @@ int dh_centernet_encode_loss(dh_handle_t h,
                              int batch, int max_boxes, int pad0, int pad1, int stride,
                              int n_scales, const float* box_scales, float sigma, int num_classes, int mode,
                              const float* pred /*[dev] same layout as dh_centernet_encode's out*/,
-                             int reg_mode /*mode 2 only*/, float alpha, float gamma, float delta,
+                             int reg_mode /*mode 2 only*/, int cls_mode /*DH_CLS_*; mode 3 counts objectness + classes as the class channels, boxes = smooth-L1 with delta (0 = plain L1, CenterNet/tf_hourglass_net.py:386-387)*/,
+                             float alpha, float gamma, float delta,
                              float* out_per_image, float* out_total, int32_t* status, void* stream);
 
 /* ---- losses with gradients ------------------------------------------------------------
@@ -215,7 +222,7 @@ int dh_centernet_encode_loss(dh_handle_t h,
  * one write of the gradient).  out_per_image / out_total may both be NULL when only the gradient is wanted.     */
 int dh_dense_loss_grad(dh_handle_t h, int n_maps, const float* const* target_maps, const float* const* pred_maps,
                        const float* const* mask_maps, const int32_t* map_height, const int32_t* map_width,
-                       const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule,
+                       const int32_t* map_sub, int batch, int ch, int reg_ch, int cen_mode, int reg_mode, int pos_rule, int cls_mode,
                        float alpha, float gamma, float delta, float w_cls, float w_reg, float w_cen,
                        float* const* grad_maps /*[host] n_maps [dev] ptrs*/, float* out_per_image, float* out_total,
                        void* stream);
@@ -233,7 +240,7 @@ int dh_retina_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t*
                                float* out_total, int32_t* num_pairs, void* stream);
 int dh_centernet_encode_loss_grad(dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
                                   int max_boxes, int pad0, int pad1, int stride, int n_scales, const float* box_scales,
-                                  float sigma, int num_classes, int mode, const float* pred, int reg_mode, float alpha,
+                                  float sigma, int num_classes, int mode, const float* pred, int reg_mode, int cls_mode, float alpha,
                                   float gamma, float delta, float w_cls, float w_reg, float w_cen, float* grad /*[dev]*/,
                                   float* out_per_image, float* out_total, int32_t* status, void* stream);
 

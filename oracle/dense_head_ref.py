@@ -546,6 +546,58 @@ def centernet_hourglass_model_loss(y_true, y_pred):
 
 
 # --------------------------------------------------------------------------------------
+# f-2  hourglass 4-scale encoder (inline in CenterNet/train_hourglass_voc.py:95-153) and its losses
+# --------------------------------------------------------------------------------------
+def hourglass4_format_data(gt_labels, raw_dims, img_dims, num_classes, stride=8):
+    """The inline encoder of CenterNet/train_hourglass_voc.py:99-153 -> float32 [img_dims/8, img_dims/8, 4, C+5]:
+    channels (h_off, w_off, h_reg, w_reg, objectness, classes...).  `gt_labels` rows are (cy, cx, h, w, class) normalised
+    by the unpadded square side `raw_dims`; the image sits at offset pad = int((img_dims - raw_dims) / 2) in the padded
+    `img_dims` square (:91-93).  Scales are img_dims / (8, 4, 2, 1) (:96-97); a box goes to the first scale that exceeds
+    BOTH its sides, else the last (:123-138); ascending-area paint order (:109-115), last painter wins the five
+    regression / objectness channels, classes OR (:148-150).  float32 arithmetic (NumPy >= 2 scalar rules)."""
+    g = _labels(gt_labels)
+    n_map = int(img_dims / stride)
+    out = np.zeros((n_map, n_map, 4, num_classes + 5), dtype=np.float32)
+    scales = [img_dims / (2 ** x) for x in range(4)][::-1]
+    pad = int((img_dims - raw_dims) / 2.0)
+    areas = g[:, 3] * g[:, 2] * F(100)                      # w * h * 100 (:110-111)
+    for k in np.argsort(areas, kind="stable"):
+        cy, cx, h, w, c = g[k]
+        x_cen, y_cen = F(pad + cx * F(raw_dims)), F(pad + cy * F(raw_dims))
+        bw, bh = F(w * F(raw_dims)), F(h * F(raw_dims))
+        if bw < 0 or bh < 0:
+            continue
+        sc = 3
+        for n in range(3):
+            if bw < scales[n] and bh < scales[n]:
+                sc = n
+                break
+        box_scale = F(scales[sc])
+        i, j = int(y_cen / F(stride)), int(x_cen / F(stride))
+        if not (0 <= i < n_map and 0 <= j < n_map):
+            continue                                        # the reference would raise / wrap; out of contract
+        out[i, j, sc, :5] = [(y_cen - F(i * stride)) / F(stride), (x_cen - F(j * stride)) / F(stride), bh / box_scale, bw / box_scale, 1.0]
+        out[i, j, sc, 5 + int(c)] = 1.0
+    return out
+
+
+def sigmoid_bce_sum(labels, logits):
+    """`reduce_sum(tf.nn.sigmoid_cross_entropy_with_logits)` -- CenterNet/tf_hourglass_net.py:347-349, :381-382:
+    max(x, 0) - x*z + log(1 + exp(-|x|)) in float32."""
+    z, x = _f32(labels), _f32(logits)
+    return F(np.sum(np.maximum(x, F(0)) - x * z + np.log(F(1) + np.exp(-np.abs(x))), dtype=np.float32))
+
+
+def hourglass4_model_loss(bboxes, masks, outputs, loss_type="sigmoid"):
+    """(cls, reg) -- CenterNet/tf_hourglass_net.py:372-388: sigmoid BCE (or focal) summed over channels 4: (objectness
+    + classes), L1 `sum(|bboxes[..., :4] - outputs[..., :4]| * masks[..., None])`."""
+    yt, yp, m = _f32(bboxes), _f32(outputs), _f32(masks)
+    cls = sigmoid_bce_sum(yt[..., 4:], yp[..., 4:]) if loss_type == "sigmoid" else focal_loss(yt[..., 4:], yp[..., 4:])
+    reg = F(np.sum(np.abs(yt[..., :4] - yp[..., :4]) * m[..., None], dtype=np.float32))
+    return cls, reg
+
+
+# --------------------------------------------------------------------------------------
 # f-3 / f-4  label preparation before the path, result formatting after it
 # --------------------------------------------------------------------------------------
 def swap_xy(boxes):

@@ -296,12 +296,31 @@ def prep(tf):
     np.savez_compressed(os.path.join(OUT, "prep.npz"), **d)
 
 
+def hourglass4(tf):
+    """The 4-scale encoder that CenterNet/train_hourglass_voc.py:95-153 keeps inline in train(), sliced out of the
+    reference file and executed unmodified (oracle/ref_loader.hourglass_inline_encoder)."""
+    from oracle import dense_head_ref as O
+    d = {}
+    for t, raw_dims in enumerate([320, 288]):
+        img_dims = raw_dims if raw_dims % 64 == 0 else (raw_dims // 64 + 1) * 64          # :87-92
+        pad = int((img_dims - raw_dims) / 2.0)
+        boxes, nbox = synth.make_boxes(1, raw_dims, 25, 5, 6.0, 0.95 * raw_dims, synth.seed_for(6, 20 + t))
+        g = boxes[0, :nbox[0]]
+        bb = np.stack([g[:, 1] - g[:, 3] / 2, g[:, 0] - g[:, 2] / 2, g[:, 1] + g[:, 3] / 2, g[:, 0] + g[:, 2] / 2], 1).astype(np.float32)
+        ref = R.hourglass_inline_encoder([{"objects": {"bbox": bb, "label": g[:, 4].astype(np.int64)}}], 5, raw_dims, img_dims, pad)[0]
+        xywh = O.convert_to_xywh(bb)            # what the reference derives from the dataset boxes (:104)
+        d["hg4_%d_labels" % t] = np.stack([xywh[:, 1], xywh[:, 0], xywh[:, 3], xywh[:, 2], g[:, 4]], 1).astype(np.float32)
+        d["hg4_%d_dims" % t] = np.array([raw_dims, img_dims])
+        d["hg4_%d_map" % t] = f32(ref)
+    np.savez_compressed(os.path.join(OUT, "hourglass4.npz"), **d)
+
+
 def main():
     if not R.available():
         raise SystemExit("reference tree not found at %s" % R.REF_ROOT)
     os.makedirs(OUT, exist_ok=True)
     tf = R.tf()
-    for fn in (kat, fcos_family, retina, centernet, losses, decode_nms, prep):
+    for fn in (kat, fcos_family, retina, centernet, losses, decode_nms, prep, hourglass4):
         fn(tf)
         print("wrote", fn.__name__)
     for f in sorted(os.listdir(OUT)):

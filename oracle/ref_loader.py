@@ -105,3 +105,25 @@ def functions_only(folder, module, names, extra_globals=None):
     finally:
         _leave(state)
     return ns
+
+
+def hourglass_inline_encoder(samples, n_classes, raw_dims, img_dims, pad_dims):
+    """Run the 4-scale target encoder that CenterNet/train_hourglass_voc.py keeps INLINE in train() (lines 95-153, not a
+    function) on `samples` = list of {"objects": {"bbox": [n,4] (xmin,ymin,xmax,ymax) normalised, "label": [n]}}.
+    The statements are sliced out of the reference file by their text markers, dedented and exec'd unmodified under the
+    stub with the loop variables the surrounding code would have set.  Returns the list of [H/8, W/8, 4, C+5] maps."""
+    path = os.path.join(REF_ROOT, "CenterNet", "train_hourglass_voc.py")
+    with open(path) as f:
+        lines = f.read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip() == "img_boxes = []")
+    end = next(i for i in range(start, len(lines)) if lines[i].strip() == "del img_bbox")
+    body = "\n".join(l[8:] if l.startswith(" " * 8) else l for l in lines[start:end + 1])
+    utils = load("CenterNet", "utils")
+    ns = {"np": np, "convert_to_xywh": utils.convert_to_xywh, "train_data": samples, "batch_sample": list(range(len(samples))),
+          "n_classes": n_classes, "raw_dims": raw_dims, "img_dims": img_dims, "pad_dims": pad_dims}
+    state = _enter("CenterNet")
+    try:
+        exec(compile(body, path, "exec"), ns)
+    finally:
+        _leave(state)
+    return ns["img_boxes"]

@@ -205,3 +205,17 @@ def test_label_prep_golden(golden):
     b, s, l = O.format_detections(rows, 2.0, 0.5)
     assert np.array_equal(b, np.array([[10, 20, 20, 60], [1, 2, 2, 6]], np.float32))
     assert s.tolist() == [np.float32(.9), .5] and l.tolist() == [3, 0]
+
+
+def test_hourglass4_encoder_golden(golden):
+    """f-2: the inline 4-scale encoder of CenterNet/train_hourglass_voc.py:99-153 (frozen reference output)."""
+    z = golden("hourglass4")
+    for t in range(2):
+        raw_dims, img_dims = (int(v) for v in z["hg4_%d_dims" % t])
+        got = O.hourglass4_format_data(z["hg4_%d_labels" % t], raw_dims, img_dims, 5)
+        assert np.array_equal(got, z["hg4_%d_map" % t])
+        assert got[..., 4].sum() > 0 and got.shape == (img_dims // 8, img_dims // 8, 4, 10)
+    # BCE against the closed form (float64)
+    x = np.linspace(-9, 9, 41).astype(np.float32); zl = (np.arange(41) % 3 == 0).astype(np.float32)
+    want = np.sum(np.logaddexp(0, x.astype(np.float64)) - x.astype(np.float64) * zl)
+    assert abs(float(O.sigmoid_bce_sum(zl, x)) - want) <= 1e-6 * want

@@ -88,3 +88,30 @@ def test_losses_and_nms_random():
         rr = np.array(s8.nms(bb.copy(), 0.5, method=method)).reshape(-1, 6)
         oo, _ = O.centernet_nms(bb, 0.5, method=method)
         assert np.allclose(rr[np.argsort(rr[:, 5], kind="stable")], oo, rtol=1e-12)
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_hourglass4_inline_encoder_random(trial):
+    raw_dims = [320, 288, 416, 224, 352, 256][trial]
+    img_dims = raw_dims if raw_dims % 64 == 0 else (raw_dims // 64 + 1) * 64
+    pad = int((img_dims - raw_dims) / 2.0)
+    boxes, nbox = synth.make_boxes(1, raw_dims, 25, 5, 6.0, 0.95 * raw_dims, 7400 + trial)
+    g = boxes[0, :nbox[0]]
+    bb = np.stack([g[:, 1] - g[:, 3] / 2, g[:, 0] - g[:, 2] / 2, g[:, 1] + g[:, 3] / 2, g[:, 0] + g[:, 2] / 2], 1).astype(np.float32)
+    ref = R.hourglass_inline_encoder([{"objects": {"bbox": bb, "label": g[:, 4].astype(np.int64)}}], 5, raw_dims, img_dims, pad)[0]
+    xywh = O.convert_to_xywh(bb)
+    gl = np.stack([xywh[:, 1], xywh[:, 0], xywh[:, 3], xywh[:, 2], g[:, 4]], 1).astype(np.float32)
+    assert _eq(O.hourglass4_format_data(gl, raw_dims, img_dims, 5), ref)
+
+
+def test_label_prep_against_reference_utils():
+    tf = R.tf()
+    utils, dp = R.load("FCOS", "utils"), R.load("FCOS", "data_preprocess")
+    rng = np.random.default_rng(3)
+    lo = rng.uniform(0, 0.7, size=(30, 2)).astype(np.float32)
+    raw = np.concatenate([lo, lo + rng.uniform(0.02, 0.3, size=(30, 2)).astype(np.float32)], axis=1)
+    assert _eq(O.swap_xy(raw), utils.swap_xy(tf.constant(raw)))
+    assert _eq(O.convert_to_xywh(raw), utils.convert_to_xywh(tf.constant(raw)))
+    assert _eq(O.convert_to_corners(raw), utils.convert_to_corners(tf.constant(raw)))
+    _, fl = dp.random_flip_horizontal(tf.constant(np.zeros((2, 2, 3), np.float32)), tf.constant(raw), p_flip=1.0)
+    assert _eq(O.flip_boxes_horizontal(raw), fl)
