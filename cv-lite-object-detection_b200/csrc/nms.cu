@@ -97,12 +97,16 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
 // ---- suppression predicates ---------------------------------------------------------------------------
 // RetinaNet/retinanet_module.py:461-479: areas from raw corners, ovr = inter / (a_i + a_j - inter + 1e-8),
 // the later box survives only if ovr <= thr (a NaN does not survive).
-__device__ __forceinline__ bool suppress_agnostic(const float4& a, const float4& c, float thr) {
-    const float area_a = fmul(fsub(a.z, a.x), fsub(a.w, a.y));
-    const float area_c = fmul(fsub(c.z, c.x), fsub(c.w, c.y));
-    const float w = fmaxf(0.0f, fsub(fminf(a.z, c.z), fmaxf(a.x, c.x)));
-    const float h = fmaxf(0.0f, fsub(fminf(a.w, c.w), fmaxf(a.y, c.y)));
-    const float inter = fmul(w, h);
+__device__ __forceinline__ float box_area(const float4& b) { return fmul(fsub(b.z, b.x), fsub(b.w, b.y)); }
+__device__ __forceinline__ bool suppress_agnostic(const float4& a, float area_a, const float4& c, float area_c, float thr) {
+    const float w_raw = fsub(fminf(a.z, c.z), fmaxf(a.x, c.x)), h_raw = fsub(fminf(a.w, c.w), fmaxf(a.y, c.y));
+    if (!(w_raw > 0.f && h_raw > 0.f)) {
+        // no overlap: inter = 0, so ovr = 0 / (area_a + area_c + 1e-8), which is <= thr unless thr < 0 or the
+        // denominator is 0 / NaN (degenerate boxes) -- the same answer as the full expression, without the division
+        const float den = fadd(fadd(area_a, area_c), 1e-8f);
+        return thr < 0.f || !(den < 0.f || den > 0.f);
+    }
+    const float inter = fmul(w_raw, h_raw);
     const float den = fadd(fsub(fadd(area_a, area_c), inter), 1e-8f);
     // ovr = inter / den decides; away from the threshold the division-free comparison gives the same answer
     // (|inter - thr*den| far above the rounding error of either side), so the IEEE division runs only near it
@@ -111,6 +115,9 @@ __device__ __forceinline__ bool suppress_agnostic(const float4& a, const float4&
     if (den > 0.f && gap > tol) return inter > rhs;
     const float ovr = fdiv(inter, den);
     return !(ovr <= thr);
+}
+__device__ __forceinline__ bool suppress_agnostic(const float4& a, const float4& c, float thr) {
+    return suppress_agnostic(a, box_area(a), c, box_area(c), thr);
 }
 // combined-NMS rule (TensorFlow's op, restated; parity unpinned): corner order normalised, degenerate
 // boxes never suppress, IoU > thr suppresses.
@@ -134,27 +141,38 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
     const int m = n_cand[b];
     if (rb * 64 >= m || cb * 64 >= m || cb < rb) return;  // only later boxes (j > i) can be suppressed
     __shared__ float4 cbox[64];
+    __shared__ float carea[64];
     __shared__ int ccls[64];
     const int tid = threadIdx.x;
     const long long base = static_cast<long long>(b) * p.n_max;
     const int j = cb * 64 + tid;
-    if (j < m) cbox[tid] = sorted_boxes[base + j], ccls[tid] = sorted_cls[base + j];
+    if (j < m) {
+        const float4 c = sorted_boxes[base + j];
+        cbox[tid] = c, carea[tid] = box_area(c), ccls[tid] = sorted_cls[base + j];
+    }
     __syncthreads();
     const int i = rb * 64 + tid;
     if (i >= m) return;
     const float4 a = sorted_boxes[base + i];
+    const float area_a = box_area(a);
     const int ac = sorted_cls[base + i];
     unsigned long long bits = 0ull;
     const int jn = min(64, m - cb * 64);
-    for (int t = (rb == cb) ? tid + 1 : 0; t < jn; ++t) {
-        bool sup;
-        if (p.per_class)
-            sup = (ccls[t] == ac) && suppress_iou(a, cbox[t], p.iou_thr);
-        else
-            sup = suppress_agnostic(a, cbox[t], p.iou_thr);
-        if (sup) bits |= (1ull << t);
+    if (p.per_class) {
+        for (int t = (rb == cb) ? tid + 1 : 0; t < jn; ++t)
+            if (ccls[t] == ac && suppress_iou(a, cbox[t], p.iou_thr)) bits |= (1ull << t);
+    } else {
+        unsigned lo = 0u, hi = 0u;  // two 32-bit halves: no 64-bit shifts in the loop
+        const int t0 = (rb == cb) ? tid + 1 : 0;
+        for (int t = t0; t < min(jn, 32); ++t)
+            if (suppress_agnostic(a, area_a, cbox[t], carea[t], p.iou_thr)) lo |= 1u << t;
+        for (int t = max(t0, 32); t < jn; ++t)
+            if (suppress_agnostic(a, area_a, cbox[t], carea[t], p.iou_thr)) hi |= 1u << (t - 32);
+        bits = (static_cast<unsigned long long>(hi) << 32) | lo;
     }
-    mask[(base + i) * words + cb] = bits;
+    // block-major layout [image][row block][column block][row in block]: a row block's words right of the diagonal are
+    // one contiguous range (a single bulk copy for the sweep) and this store is coalesced
+    mask[(((static_cast<long long>(b) * words + rb) * words + cb) << 6) + tid] = bits;
 }
 
 // ---- kernel 3 -----------------------------------------------------------------------------------------
@@ -163,79 +181,112 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
 // boxes it kept are then OR-ed into the `removed` bit vector by all threads in parallel (coalesced along the row).
 // Only mask words at or right of the diagonal are ever read, so nms_mask_kernel never has to clear the rest.
 constexpr int kSweepThreads = 256;
+constexpr int kSweepStageWords = 96;  // a row block's mask words are staged in shared memory when words <= this (n <= 6144)
+constexpr int kSweepDepth = 3;        // stage buffers: blocks w + 1 and w + 2 are in flight while block w is swept
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ sorted_cls,
                                                                   const int* __restrict__ order, const int* __restrict__ n_cand, NmsParams p,
-                                                                  int words, int* __restrict__ keep, int* __restrict__ n_keep) {
-    extern __shared__ int class_count[];  // [num_classes] when per-class caps are on
+                                                                  int words, int staged, int* __restrict__ keep, int* __restrict__ n_keep) {
+    // dynamic shared memory: [kSweepDepth][words][64] staged mask words (when `staged`), then class_count (caps)
+    extern __shared__ __align__(128) unsigned char sweep_smem[];
     __shared__ unsigned long long removed[kNmsMaxN / 64];
-    __shared__ unsigned long long diag[64];
-    __shared__ int bcls[64];
+    __shared__ int bcls[2][64];
     __shared__ unsigned long long s_km;
+    __shared__ uint64_t bars[kSweepDepth];
     __shared__ int s_kept, s_stop;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int m = n_cand[b];
     const int nblk = (m + 63) >> 6;
     const long long base = static_cast<long long>(b) * p.n_max;
     const bool caps = p.per_class && p.max_per_class > 0;
     const int max_total = p.max_total > 0 ? min(p.max_total, p.max_out) : p.max_out;
+    const size_t buf_words = staged ? static_cast<size_t>(words) * 64 : 0;
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(sweep_smem);
+    int* class_count = reinterpret_cast<int*>(sweep_smem + kSweepDepth * buf_words * 8);
+    // mask words of row block rb from its diagonal column on: [column block - rb][row in block]
+    auto block_words = [&](int rb) { return mask + (((static_cast<long long>(b) * words + rb) * words + rb) << 6); };
     if (caps)
         for (int c = tid; c < p.num_classes; c += kSweepThreads) class_count[c] = 0;
     for (int w = tid; w < nblk; w += kSweepThreads) removed[w] = 0ull;
-    if (tid == 0) s_kept = 0, s_stop = (max_total <= 0);
+    if (tid == 0) {
+        s_kept = 0, s_stop = (max_total <= 0);
+        for (int q = 0; q < kSweepDepth; ++q) mbar_init(&bars[q], 1);
+        mbar_init_fence();
+    }
+    if (caps && tid < min(64, m)) bcls[0][tid] = sorted_cls[base + tid];
     __syncthreads();
-    for (int w = 0; w < nblk && !s_stop; ++w) {
-        const int first = w << 6, nb = min(64, m - first);
-        const int kept_before = s_kept;  // written by thread 0 before the barriers that end the previous block
-        if (tid < nb) {
-            diag[tid] = mask[(base + first + tid) * words + w];
-            if (caps) bcls[tid] = sorted_cls[base + first + tid];
-        }
-        __syncthreads();
+    auto prefetch_block = [&](int blk) {  // thread 0: one TMA bulk copy per block into stage[blk % depth]
+        if (!staged || blk >= nblk) return;
+        const uint32_t bytes = static_cast<uint32_t>(nblk - blk) * 512u;
+        const int buf = blk % kSweepDepth;
+        mbar_expect_tx(&bars[buf], bytes);
+        bulk_g2s(stage + buf * buf_words, block_words(blk), bytes, &bars[buf]);
+    };
+    if (tid == 0) prefetch_block(0), prefetch_block(1);
+    int w = 0;
+    for (; w < nblk && !s_stop; ++w) {
+        const int first = w << 6, nb = min(64, m - first), cur = w & 1;
+        const int kept_before = s_kept;  // written before the barriers that end the previous block
+        const int buf = w % kSweepDepth;
+        const int my_order = tid < nb ? __ldg(order + base + first + tid) : 0;  // issued early: its latency hides behind the chain walk
+        if (staged) mbar_wait(&bars[buf], static_cast<uint32_t>((w / kSweepDepth) & 1));  // requested two blocks ago
+        const unsigned long long* src = staged ? stage + buf * buf_words : block_words(w);
         if (tid == 0) {
+            // one thread walks the greedy chain with the 64 diagonal words in registers: each step is a bit test and a
+            // predicated OR, no memory access on the dependent path
+            unsigned long long d[64];
+#pragma unroll
+            for (int r = 0; r < 64; ++r) d[r] = src[r];
             unsigned long long rem = removed[w], km = 0ull;
             int kept = kept_before;
-            for (int r = 0; r < nb; ++r) {
-                if ((rem >> r) & 1ull) continue;
-                if (caps) {
-                    const int c = bcls[r];
-                    if (c >= 0 && c < p.num_classes) {
-                        if (class_count[c] >= p.max_per_class) continue;  // over the per-class cap: never selected, suppresses nobody
-                        class_count[c] += 1;
+            bool live = true;
+#pragma unroll
+            for (int r = 0; r < 64; ++r) {
+                bool take = live && r < nb && !((rem >> r) & 1ull);
+                if (caps && take) {
+                    const int cc = bcls[cur][r];
+                    if (cc >= 0 && cc < p.num_classes) {
+                        if (class_count[cc] >= p.max_per_class) take = false;  // over the per-class cap: never selected, suppresses nobody
+                        else class_count[cc] += 1;
                     }
                 }
-                km |= 1ull << r;
-                rem |= diag[r];
-                if (++kept >= max_total) {
-                    s_stop = 1;
-                    break;
+                if (take) {
+                    km |= 1ull << r;
+                    rem |= d[r];
+                    if (++kept >= max_total) live = false;
                 }
             }
             s_km = km, s_kept = kept;
+            if (!live) s_stop = 1;
+        } else if (caps && tid >= 64 && tid < 128 && first + tid < m) {
+            bcls[cur ^ 1][tid - 64] = sorted_cls[base + first + tid];  // the next block's classes
         }
         __syncthreads();
         const unsigned long long km = s_km;
         if (tid < nb && ((km >> tid) & 1ull))
-            keep[static_cast<long long>(b) * p.max_out + kept_before + __popcll(km & ((1ull << tid) - 1ull))] = order[base + first + tid];
+            keep[static_cast<long long>(b) * p.max_out + kept_before + __popcll(km & ((1ull << tid) - 1ull))] = my_order;
         if (!s_stop && km) {
-            // thread <-> mask column; the 64 row loads are independent (16 in flight per thread), coalesced across threads
-            for (int ww = w + 1 + tid; ww < nblk; ww += kSweepThreads) {
-                const unsigned long long* col = mask + (base + first) * words + ww;
-                unsigned long long acc = removed[ww];
-#pragma unroll 1
-                for (int r0 = 0; r0 < 64; r0 += 16) {
-                    if (!((km >> r0) & 0xFFFFull)) continue;
-                    unsigned long long v[16];
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) v[u] = ((km >> (r0 + u)) & 1ull) ? __ldg(col + static_cast<long long>(r0 + u) * words) : 0ull;
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) acc |= v[u];
-                }
-                removed[ww] = acc;
+            // OR the kept rows into `removed`: one warp per mask column, lane l takes rows l and l + 32 (coalesced /
+            // conflict-free), two redux instructions combine the warp and lane 0 updates the word (no atomics needed)
+            const bool k0 = (km >> lane) & 1ull, k1 = (km >> (lane + 32)) & 1ull;
+            for (int col = 1 + (tid >> 5); col < nblk - w; col += kSweepThreads / 32) {
+                const unsigned long long* cw = src + (static_cast<size_t>(col) << 6);
+                const unsigned long long v = (k0 ? cw[lane] : 0ull) | (k1 ? cw[lane + 32] : 0ull);
+                const unsigned lo = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(v));
+                const unsigned hi = __reduce_or_sync(0xffffffffu, static_cast<unsigned>(v >> 32));
+                if (lane == 0 && (lo | hi)) removed[w + col] |= (static_cast<unsigned long long>(hi) << 32) | lo;
             }
         }
         __syncthreads();
+        if (tid == 0) prefetch_block(w + 2);  // buffer (w + 2) % depth was drained one block ago
     }
-    if (tid == 0) n_keep[b] = s_kept;
+    if (tid == 0) {
+        n_keep[b] = s_kept;
+        // blocks < w were waited for; an early stop leaves the prefetches of blocks w and w + 1 in flight: let them land
+        // before the CTA (and its shared memory) goes away
+        if (staged)
+            for (int blk = w; blk <= w + 1; ++blk)
+                if (blk < nblk) mbar_wait(&bars[blk % kSweepDepth], static_cast<uint32_t>((blk / kSweepDepth) & 1));
+    }
 }
 
 // ---- lazy variant for capped outputs: kernels 2 + 3 fused, one CTA per image --------------------------------
@@ -362,14 +413,14 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     p.num_classes = num_classes, p.max_out = max_out;
     int n_pow2 = 64;
     while (n_pow2 < n_max) n_pow2 <<= 1;
-    const int words = (n_max + 63) / 64;
+    const int words = (((n_max + 63) / 64) + 1) & ~1;  // even: every mask row is 16-byte aligned for the TMA bulk copies
     // scratch: sorted boxes (16 B), classes, order, counts, mask
     const size_t per_img = static_cast<size_t>(n_max);
     size_t off_cls = static_cast<size_t>(batch) * per_img * 16;
     size_t off_ord = off_cls + static_cast<size_t>(batch) * per_img * 4;
     size_t off_cnt = off_ord + static_cast<size_t>(batch) * per_img * 4;
     size_t off_mask = (off_cnt + static_cast<size_t>(batch) * 4 + 255) & ~size_t(255);
-    size_t total = off_mask + static_cast<size_t>(batch) * per_img * words * 8;
+    size_t total = off_mask + static_cast<size_t>(batch) * words * words * 64 * 8;
     char* sc = static_cast<char*>(scratch(h, total));
     if (!sc) return DH_ERR_CUDA;
     float4* sboxes = reinterpret_cast<float4*>(sc);
@@ -396,8 +447,15 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     dim3 grid(words, words, batch);
     nms_mask_kernel<<<grid, 64, 0, st>>>(sboxes, scls, ncand, p, words, mask);
     DH_CUDA(cudaGetLastError());
-    const size_t sweep_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
-    nms_sweep_kernel<<<batch, kSweepThreads, sweep_smem, st>>>(mask, scls, order, ncand, p, words, keep, n_keep);
+    const int staged = words <= kSweepStageWords ? 1 : 0;
+    const size_t stage_bytes = staged ? static_cast<size_t>(kSweepDepth) * 64 * words * 8 : 0;  // [depth][words][64] words
+    const size_t sweep_smem = stage_bytes + ((p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0);
+    static bool sweep_attr_done = false;
+    if (!sweep_attr_done) {
+        DH_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        sweep_attr_done = true;
+    }
+    nms_sweep_kernel<<<batch, kSweepThreads, sweep_smem, st>>>(mask, scls, order, ncand, p, words, staged, keep, n_keep);
     DH_CUDA(cudaGetLastError());
     h->launches += 3;
     return DH_OK;
