@@ -633,11 +633,39 @@ struct FcosSource {
 // memory are those of the boundary bin AND of enough neighbouring bins that no score tie can reach outside them
 // (sigmoid_collision_floor bounds how far below a logit a colliding logit can lie).  Returns false (nothing
 // written) when the shortcut does not apply; the caller then runs the generic exact selector.
+// kVec: the head rows of one (image, level) are walked as float4 items in memory order (4 logits per load; the five
+// regression / centerness channels of each row come along and are skipped); otherwise one (location, class) pair per
+// load.  Memory order IS (location, class) order, so the ordered compaction emits the same sequence either way.
+template <bool kVec>
 __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const FcosSource& src, int k_slots, float min_score, int inclusive) {
+    constexpr int W = kVec ? 4 : 1;  // logits per load item
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = src.n;
     const int k = min(k_slots, max(n, 0));
     if (src.center || !(min_score > 1.0e-6f && min_score < 0.999f) || k <= 0) return false;
+    const int rows = n / src.num_classes;
+    const int n_items = kVec ? (rows * src.ch) >> 2 : n;
+    const FastDiv div_ch = make_fastdiv(static_cast<uint32_t>(src.ch));
+    // item -> W logits (-inf where the slot is not a class channel / out of range) and their pair indices
+    auto load = [&](int item, float* x, int* idx) {
+        if (!kVec) {
+            x[0] = item < n_items ? src.logit(item) : -INFINITY;
+            idx[0] = item;
+            return;
+        }
+        float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (item < n_items) v = __ldg(reinterpret_cast<const float4*>(src.head) + item);
+        const int p0 = item << 2;
+        int r = static_cast<int>(fdiv_u32(static_cast<uint32_t>(p0), div_ch));
+        int c = p0 - r * src.ch;
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            x[e] = c >= 5 ? vv[e] : -INFINITY;
+            idx[e] = r * src.num_classes + (c - 5);
+            if (++c == src.ch) c = 0, ++r;
+        }
+    };
     const float x_thr = logf(min_score / (1.0f - min_score));
     const float thr_lo = x_thr - 1.0e-3f, thr_hi = x_thr + 1.0e-3f;
     constexpr float kScale = 4096.0f / 24.0f;  // bins of 0.0059 logit units from the threshold upwards
@@ -647,20 +675,20 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
         const float t = (x - thr_lo) * kScale;
         return t <= 0.f ? 0 : (t >= 4095.f ? 4095 : static_cast<int>(t));
     };
-    constexpr int U = 8;
+    constexpr int U = kVec ? 4 : 8;  // independent loads in flight per thread in the unordered passes
     for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
     if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0, sh.n_pass = 0, sh.t_key = 0u, sh.t_idx = 0x7fffffff;
     __syncthreads();
-    for (int base = 0; base < n; base += kSelThreads * U) {
-        float x[U];
+    for (int base = 0; base < n_items; base += kSelThreads * U) {
+        float x[U][W];
+        int idx[U][W];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = base + u * kSelThreads + tid;
-            x[u] = i < n ? src.logit(i) : -INFINITY;
-        }
+        for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], idx[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (passes_x(x[u])) atomicAdd(&sh.hist[bin_x(x[u])], 1u);
+#pragma unroll
+            for (int e = 0; e < W; ++e)
+                if (passes_x(x[u][e])) atomicAdd(&sh.hist[bin_x(x[u][e])], 1u);
     }
     __syncthreads();
     find_boundary(sh, 4096, static_cast<unsigned>(k), tid);
@@ -693,21 +721,21 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
         lo_bin = static_cast<int>(sh.wtot[1][1]), hi_bin = static_cast<int>(sh.wtot[1][2]);
         const unsigned need = sh.need;
         // collect the entries that can tie with the k-th score, with their exact scores
-        for (int base = 0; base < n; base += kSelThreads * U) {
-            float x[U];
+        for (int base = 0; base < n_items; base += kSelThreads * U) {
+            float x[U][W];
+            int idx[U][W];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = base + u * kSelThreads + tid;
-                x[u] = i < n ? src.logit(i) : -INFINITY;
-            }
+            for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], idx[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!passes_x(x[u])) continue;
-                const int bn = bin_x(x[u]);
-                if (bn < lo_bin || bn > hi_bin) continue;
-                const unsigned slot = atomicAdd(&sh.n_list, 1u);
-                sh.list_key[slot] = score_key(sigmoid_acc(x[u])), sh.list_idx[slot] = base + u * kSelThreads + tid;
-            }
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int e = 0; e < W; ++e) {
+                    if (!passes_x(x[u][e])) continue;
+                    const int bn = bin_x(x[u][e]);
+                    if (bn < lo_bin || bn > hi_bin) continue;
+                    const unsigned slot = atomicAdd(&sh.n_list, 1u);
+                    sh.list_key[slot] = score_key(sigmoid_acc(x[u][e])), sh.list_idx[slot] = idx[u][e];
+                }
         }
         __syncthreads();
         const int n_list = static_cast<int>(sh.n_list);
@@ -725,29 +753,33 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
     }
     const unsigned T_key = sh.t_key;
     const int T_idx = sh.t_idx;
-    // ordered compaction
+    // ordered compaction: each thread owns kSelItems consecutive logits (= kSelItems / W consecutive load items)
+    constexpr int IPT = kSelItems / W;
     unsigned carry = 0;
     int it = 0;
-    for (int base = 0; base < n; base += kSelThreads * kSelItems, ++it) {
-        const int i0 = base + tid * kSelItems;
-        float x[kSelItems];
+    for (int base = 0; base < n_items; base += kSelThreads * IPT, ++it) {
+        float x[IPT][W];
+        int idx[IPT][W];
 #pragma unroll
-        for (int u = 0; u < kSelItems; ++u) x[u] = (i0 + u < n) ? src.logit(i0 + u) : -INFINITY;
+        for (int u = 0; u < IPT; ++u) load(base + tid * IPT + u, x[u], idx[u]);
         unsigned flags = 0;
 #pragma unroll
-        for (int u = 0; u < kSelItems; ++u) {
-            if (!passes_x(x[u])) continue;
-            bool take = take_all;
-            if (!take) {
-                const int bn = bin_x(x[u]);
-                if (bn > hi_bin) take = true;
-                else if (bn >= lo_bin) {
-                    const unsigned key = score_key(sigmoid_acc(x[u]));
-                    take = key > T_key || (key == T_key && i0 + u <= T_idx);
+        for (int u = 0; u < IPT; ++u)
+#pragma unroll
+            for (int e = 0; e < W; ++e) {
+                const float xv = x[u][e];
+                if (!passes_x(xv)) continue;
+                bool take = take_all;
+                if (!take) {
+                    const int bn = bin_x(xv);
+                    if (bn > hi_bin) take = true;
+                    else if (bn >= lo_bin) {
+                        const unsigned key = score_key(sigmoid_acc(xv));
+                        take = key > T_key || (key == T_key && idx[u][e] <= T_idx);
+                    }
                 }
+                if (take) flags |= 1u << (u * W + e);
             }
-            if (take) flags |= 1u << u;
-        }
         const unsigned mine = __popc(flags);
         unsigned incl = mine;
 #pragma unroll
@@ -766,11 +798,13 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
         }
         unsigned rank = before + incl - mine;
 #pragma unroll
-        for (int u = 0; u < kSelItems; ++u) {
-            if (!((flags >> u) & 1u)) continue;
-            if (rank < static_cast<unsigned>(k)) src.emit(i0 + u, sigmoid_acc(x[u]), static_cast<int>(rank));
-            ++rank;
-        }
+        for (int u = 0; u < IPT; ++u)
+#pragma unroll
+            for (int e = 0; e < W; ++e) {
+                if (!((flags >> (u * W + e)) & 1u)) continue;
+                if (rank < static_cast<unsigned>(k)) src.emit(idx[u][e], sigmoid_acc(x[u][e]), static_cast<int>(rank));
+                ++rank;
+            }
         carry += tot;
     }
     const unsigned filled = min(static_cast<unsigned>(k), carry);
@@ -795,7 +829,12 @@ __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs
     src.out = cand + (static_cast<long long>(b) * a.n_levels + l) * a.k_slots * 6;
     src.n = rows * a.num_classes;
     src.div_c = make_fastdiv(static_cast<uint32_t>(a.num_classes));
-    if (a.allow_logit_space && fcos_select_logit_space(sh, src, a.k_slots, a.min_score, a.inclusive)) return;
+    if (a.allow_logit_space) {
+        const bool vec = (reinterpret_cast<uintptr_t>(src.head) & 15u) == 0 && ((rows * src.ch) & 3) == 0;  // block-uniform
+        if (vec ? fcos_select_logit_space<true>(sh, src, a.k_slots, a.min_score, a.inclusive)
+                : fcos_select_logit_space<false>(sh, src, a.k_slots, a.min_score, a.inclusive))
+            return;
+    }
     select_core(sh, src, a.k_slots, a.min_score, a.inclusive);
 }
 

@@ -215,7 +215,7 @@ __device__ __forceinline__ void accumulate_element(const LossSpec& sp, int cls0,
     }
 }
 
-template <class P, bool kFused>
+template <class P, bool kFused, bool kGrad = false>
 __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant__ LossArgs<P> ga) {
     extern __shared__ __align__(128) unsigned char smem[];
     const LossSmemLayout lay = loss_smem_layout<P, kFused>(ga.tile_buf_bytes, ga.tt.rows_per_tile, ga.box_cap);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
             const long long off = static_cast<long long>(ti.b) * md.image_stride + static_cast<long long>(ti.r0) * ch;
             const float* __restrict__ gp = md.pred + off;
             const float* __restrict__ gt = kFused ? nullptr : md.out + off;
-            float* __restrict__ gg = (!kFused && a.grad_maps[ti.m]) ? a.grad_maps[ti.m] + off : nullptr;
+            float* __restrict__ gg = (kGrad && !kFused && a.grad_maps[ti.m]) ? a.grad_maps[ti.m] + off : nullptr;
             const int nfl = ti.nrows * ch;
             int ncand = 0;
             uint32_t dmask = 0u;
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                                 if (sp.reg_mode == 0) {
                                     acc.reg += m * (smooth_l1_term(y.x, x[u].x, sp.delta) + smooth_l1_term(y.y, x[u].y, sp.delta) +
                                                     smooth_l1_term(y.z, x[u].z, sp.delta) + smooth_l1_term(y.w, x[u].w, sp.delta));
-                                    if (gg) {
+                                    if (kGrad && gg) {
                                         const float k = m * sp.w_reg;
                                         gv = make_float4(k * smooth_l1_grad(y.x, x[u].x, sp.delta), k * smooth_l1_grad(y.y, x[u].y, sp.delta),
                                                          k * smooth_l1_grad(y.z, x[u].z, sp.delta), k * smooth_l1_grad(y.w, x[u].w, sp.delta));
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                                     const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
                                     const float tv[4] = {y.x, y.y, y.z, y.w}, pv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
                                     acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width));
-                                    if (gg) {
+                                    if (kGrad && gg) {
                                         float g4[4];
                                         iou_loss_grad(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), g4);
                                         const float k = m * sp.w_reg;
@@ -401,11 +401,11 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                             }
                         } else {
                             acc.cls += cls_term(sp, y.x, x[u].x) + cls_term(sp, y.y, x[u].y) + cls_term(sp, y.z, x[u].z) + cls_term(sp, y.w, x[u].w);
-                            if (gg)
+                            if (kGrad && gg)
                                 gv = make_float4(sp.w_cls * cls_grad(sp, y.x, x[u].x), sp.w_cls * cls_grad(sp, y.y, x[u].y),
                                                  sp.w_cls * cls_grad(sp, y.z, x[u].z), sp.w_cls * cls_grad(sp, y.w, x[u].w));
                         }
-                        if (gg) __stcs(reinterpret_cast<float4*>(gg) + q, gv);
+                        if (kGrad && gg) __stcs(reinterpret_cast<float4*>(gg) + q, gv);
                     }
                 }
             } else {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                             }
                         }
                         accumulate_element(sp, cls0, c, x[u], y, m, acc);
-                        if (gg) {
+                        if (kGrad && gg) {
                             float g = 0.f;
                             if (c >= cls0) {
                                 g = sp.w_cls * cls_grad(sp, y, x[u]);

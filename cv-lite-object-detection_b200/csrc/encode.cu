@@ -55,14 +55,24 @@ static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, cons
     }
     int per_sm = 1;  // resident CTAs per SM (registers and shared memory both count)
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<P>, DH_THREADS, lay.total));
+    // one CTA per SM leaves the TMA stores of a tile uncovered by another CTA's bookkeeping (CenterNet with 150 boxes:
+    // 117 KB at 48 KB tiles, 3.5 TB/s): shrink the tile until two fit
+    EncodeSmemLayout lay2 = lay;
+    for (int tb = a.tile_buf_bytes; per_sm < 2 && h->ctas_per_sm >= 2 && tb > 20 * 1024;) {
+        tb -= 4096;
+        a.tile_buf_bytes = finish_table(a.tt, a.tt.ch, a.tt.batch, tb - 256);
+        lay2 = encode_smem_layout<P>(a.tile_buf_bytes, a.box_cap);
+        DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<P>, DH_THREADS, lay2.total));
+    }
     if (per_sm > h->ctas_per_sm) per_sm = h->ctas_per_sm;
     if (per_sm < 1) per_sm = 1;
+    const long long total2 = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;  // the table may have been re-cut
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
-    if (grid > total) grid = total;
+    if (grid > total2) grid = total2;
     // image-aligned chunks for the dynamic scheduler: aim at >= ~8 chunks per CTA, 8..64 tiles each
     {
         const int tpi = a.tt.tiles_per_image;
-        long long want = total / (grid * 8);
+        long long want = total2 / (grid * 8);
         want = want < 8 ? 8 : (want > 64 ? 64 : want);
         if (tpi <= want) {
             a.chunks_per_image = 1;
@@ -83,7 +93,7 @@ static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, cons
     if (!a.sched) return DH_ERR_CUDA;
     a.use_tma_store = h->use_tma_store;
     a.phase_cycles = h->phase_cycles;
-    encode_kernel<P><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+    encode_kernel<P><<<static_cast<unsigned>(grid), DH_THREADS, lay2.total, st>>>(a);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
     return DH_OK;

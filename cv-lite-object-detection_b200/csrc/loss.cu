@@ -28,6 +28,7 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
     static bool attr_done = false;
     if (!attr_done) {
         DH_CUDA(cudaFuncSetAttribute(loss_kernel<P, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DH_CUDA(cudaFuncSetAttribute(loss_kernel<P, kFused, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     int per_sm = 1;  // resident CTAs per SM (registers and shared memory both count)
@@ -61,7 +62,10 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
     if (total > 0) {
         a.sched = next_sched_counter(h, st);
         if (!a.sched) return DH_ERR_CUDA;
-        loss_kernel<P, kFused><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+        bool grad = false;
+        for (int m = 0; m < a.tt.n_maps; ++m) grad = grad || a.grad_maps[m] != nullptr;
+        if (grad && !kFused) loss_kernel<P, kFused, true><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+        else loss_kernel<P, kFused, false><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
         DH_CUDA(cudaGetLastError());
         h->launches += 1;
     }
