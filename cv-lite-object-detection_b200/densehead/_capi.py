@@ -26,7 +26,7 @@ class DenseHeadError(RuntimeError):
 
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()  # re-entrant: handle() creates the handle under the lock and lib() takes it too
 _handles = {}
 
 

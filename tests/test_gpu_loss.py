@@ -145,3 +145,55 @@ def test_loss_linearity_property():
     spi, _, _ = dh.fcos.encode_loss_batch(boxes[sub], nbox[sub], [512, 512], 20, [512, 512], [p[sub].contiguous() for p in pred])
     assert torch.equal(spi, pi[sub])
     assert torch.isfinite(tot).all() and float(tot[3]) == float(pi[:, 3].sum())
+
+
+def test_fused_loss_edge_cases():
+    """Images without boxes, 256 boxes per image (the capacity), > 128 classes (falls back to the
+    shared-memory target-tile kernel), predictions at a 4-byte-aligned (not 16-byte) address (scalar loads), and the
+    stream+correct kernel against the target-tile kernel (DH_OPT_FUSED_LOSS_KERNEL)."""
+    dh = _dh()
+    C = 20
+    # no boxes at all: pure zero-label loss, equal to the unfused loss over all-zero targets
+    pred = synth.fcos_predictions(2, 256, C, 5)
+    boxes, nbox = np.zeros((2, 4, 5), np.float32), np.zeros((2,), np.int32)
+    pi, tot, _ = dh.fcos.encode_loss_batch(boxes, nbox, [256, 256], C, [256, 256], pred)
+    zeros = [np.zeros_like(p) for p in pred]
+    upi, utot = dh.fcos.model_loss_batch(zeros, pred)
+    assert_close(pi.cpu().numpy(), upi.cpu().numpy(), 2e-6, what="no boxes") and float(tot[3]) == 0
+    # capacity: 256 boxes in one image
+    boxes, nbox = synth.make_boxes(1, 512, 256, C, 4.0, 200.0, synth.seed_for(5, 90), full=True)
+    assert int(nbox[0]) == 256
+    pred = synth.fcos_predictions(1, 512, C, 6)
+    tg, _ = dh.fcos.format_data_batch(boxes, nbox, [512, 512], C, [512, 512])
+    upi, _ = dh.fcos.model_loss_batch(tg, pred)
+    for opt in (0, 1):
+        dh.set_option(0, 5, opt)
+        try:
+            fpi, _, _ = dh.fcos.encode_loss_batch(boxes, nbox, [512, 512], C, [512, 512], pred)
+        finally:
+            dh.set_option(0, 5, 0)
+        assert_close(fpi.cpu().numpy(), upi.cpu().numpy(), 2e-6, what="256 boxes, kernel %d" % opt)
+        assert int(fpi[0, 3]) == int(upi[0, 3])
+    # > 128 classes: the bitmask of the stream+correct kernel does not fit, the tile kernel takes over
+    Cb = 150
+    boxes, nbox = synth.make_boxes(2, 256, 12, Cb, 8.0, 150.0, synth.seed_for(5, 91))
+    pred = synth.fcos_predictions(2, 256, Cb, 7)
+    tg, _ = dh.fcos.format_data_batch(boxes, nbox, [256, 256], Cb, [256, 256])
+    upi, _ = dh.fcos.model_loss_batch(tg, pred)
+    fpi, _, _ = dh.fcos.encode_loss_batch(boxes, nbox, [256, 256], Cb, [256, 256], pred)
+    assert_close(fpi.cpu().numpy(), upi.cpu().numpy(), 2e-6, what="150 classes")
+    with pytest.raises(ValueError):
+        dh.fcos.encode_loss_batch(boxes, nbox, [256, 256], Cb, [256, 256], pred, weights=(1, 1, 1))
+    # misaligned predictions (RetinaNet, C = 80: the vector path needs 16-byte alignment)
+    boxes, nbox = synth.make_boxes(2, 256, 12, 80, 8.0, 150.0, synth.seed_for(5, 92))
+    pred = synth.retina_predictions(2, 256, 80, 8)
+    aligned = [torch.from_numpy(p).cuda() for p in pred]
+    shifted = []
+    for p in aligned:
+        buf = torch.empty(p.numel() + 1, device="cuda")
+        buf[1:].copy_(p.reshape(-1))
+        shifted.append(buf[1:].view(p.shape))
+        assert shifted[-1].data_ptr() % 16 == 4
+    a = dh.retinanet.encode_loss_batch(boxes, nbox, [256, 256], 80, [256, 256], aligned)
+    b = dh.retinanet.encode_loss_batch(boxes, nbox, [256, 256], 80, [256, 256], shifted)
+    assert_close(b[0].cpu().numpy(), a[0].cpu().numpy(), 2e-6, what="misaligned") and torch.equal(a[2], b[2])
