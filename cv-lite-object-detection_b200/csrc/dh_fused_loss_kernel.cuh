@@ -119,10 +119,10 @@ __device__ __forceinline__ void stream_vec_item(const float4& x, bool is_reg, fl
     }
     if (kGrad) __stcs(g, make_float4(d.x * gscale, d.y * gscale, d.z * gscale, d.w * gscale));
 }
-// `kstar` = the one k in [0, vpr) at which this lane's item lane + 32 k is float4 0 of a row (tiles start on a row
-// boundary and a lane has at most vpr items per tile, so there is exactly one)
+// `c4` = position of this lane's next item inside its row (in float4s), advanced by 32 mod vpr per item: no division
+// in the loop, and correct for every row length (a lane may meet several regression float4s per tile, or none)
 template <int kCls, bool kGrad, int U>
-__device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int kstar,
+__device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int c4, int step,
                                            int lane, float gamma, float gscale, StreamAcc& a) {
     const float4* __restrict__ ptr = reinterpret_cast<const float4*>(p) + lane;
     float4* __restrict__ gptr = reinterpret_cast<float4*>(gout) + lane;
@@ -134,12 +134,18 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
 #pragma unroll
         for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; ++u) stream_vec_item<kCls, kGrad>(x[u], k + u == kstar, gamma, gscale, a, gptr + 32 * u);
+        for (int u = 0; u < U; ++u) {
+            stream_vec_item<kCls, kGrad>(x[u], c4 == 0, gamma, gscale, a, gptr + 32 * u);
+            c4 += step;
+            if (c4 >= vpr) c4 -= vpr;
+        }
     }
 #pragma unroll 1
     for (; k < n_mine; ++k, ptr += 32, gptr += 32) {
         const float4 x = __ldcs(ptr);
-        stream_vec_item<kCls, kGrad>(x, k == kstar, gamma, gscale, a, gptr);
+        stream_vec_item<kCls, kGrad>(x, c4 == 0, gamma, gscale, a, gptr);
+        c4 += step;
+        if (c4 >= vpr) c4 -= vpr;
     }
 }
 
@@ -319,8 +325,7 @@ __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img,
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = a.tt.ch >> 2;
-    int kstar = 0;
-    while ((lane + 32 * kstar) % vpr != 0) ++kstar;
+    const int step = 32 % vpr, c_lane = lane % vpr;
     const float gamma = a.spec.gamma, gscale = (kCls == 2 ? 1.0f : 1.0f - a.spec.alpha) * a.spec.w_cls;
     TileCursor cur;
     cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
@@ -329,7 +334,7 @@ __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img,
         TileInfo ti;
         float* gg = nullptr;
         const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
-        if (ti.nrows > 0) stream_vec<kCls, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, kstar, lane, gamma, gscale, sa);
+        if (ti.nrows > 0) stream_vec<kCls, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
     }
     return sa;
 }

@@ -197,3 +197,18 @@ def test_fused_loss_edge_cases():
     a = dh.retinanet.encode_loss_batch(boxes, nbox, [256, 256], 80, [256, 256], aligned)
     b = dh.retinanet.encode_loss_batch(boxes, nbox, [256, 256], 80, [256, 256], shifted)
     assert_close(b[0].cpu().numpy(), a[0].cpu().numpy(), 2e-6, what="misaligned") and torch.equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("classes", [20, 12, 28, 1])
+def test_retina_fused_loss_row_lengths(classes):
+    """Row lengths whose float4 count shares a factor with the warp size (C = 20 -> 6 float4 per row, 12 -> 4, 28 -> 8)
+    and a non-vector row (C = 1 -> 5 floats): fused == unfused, with gradients."""
+    dh = _dh()
+    boxes, nbox = synth.make_boxes(2, 256, 12, classes, 8.0, 150.0, synth.seed_for(5, 93))
+    pred = synth.retina_predictions(2, 256, classes, 9)
+    lab, _ = dh.retinanet.format_data_batch(boxes, nbox, [256, 256], classes, [256, 256])
+    upi, utot, ug = dh.retinanet.loss_batch(lab, pred, weights=(1.0, 1.0))
+    fpi, ftot, _, fg = dh.retinanet.encode_loss_batch(boxes, nbox, [256, 256], classes, [256, 256], pred, weights=(1.0, 1.0))
+    assert_close(fpi.cpu().numpy(), upi.cpu().numpy(), 2e-6, what="C=%d" % classes)
+    for a, b in zip(fg, ug):
+        assert torch.allclose(a, b, rtol=2e-5, atol=1e-6)
