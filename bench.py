@@ -178,7 +178,7 @@ def run_reference(args, rank, world):
                                      "Python+TF and /root/reference does not exist on the GPU box"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_json(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -361,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
                            "collective": "NCCL all-reduce of 4 float32 loss scalars per step" if world > 1 else "none"},
                 "clocks": clocks, "e2e": e2e, "e2e_resident_pred": e2e_res, "gpu_launches": int(launches_per_step * args.steps),
                 "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
-        print(json.dumps(line), flush=True)
+        emit_json(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -486,18 +486,53 @@ def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
     return out
 
 
+class QuietStdout:
+    """Route file descriptor 1 to stderr while the benchmark runs (NCCL and other native libraries print banners on
+    stdout) and give it back for the one JSON line the contract asks for."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
+def emit_json(line):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global OUT
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    import __graft_entry__ as entry
-    if rank == 0 or not os.path.exists(entry.LIB):
-        entry.build()
-    run_ours(args, rank, world, local_rank)
+    with QuietStdout() as OUT:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+            return
+        import __graft_entry__ as entry
+        if rank == 0 or not os.path.exists(entry.LIB):
+            entry.build()
+        run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
