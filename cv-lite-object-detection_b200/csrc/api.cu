@@ -98,6 +98,7 @@ int dh_create(dh_handle_t* out, int device) {
     h->ctas_per_sm = 4;
     h->fused_loss_kernel = 0;
     h->nms_kernel = 0;
+    h->fused_chunks_per_cta = 12;
     h->fcos_select_exact_only = 0;
     h->launches = 0;
     h->scratch = nullptr;
@@ -149,6 +150,10 @@ int dh_set_option(dh_handle_t h, int option, int value) {
         case DH_OPT_FCOS_SELECT:
             DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_FCOS_SELECT must be 0 or 1");
             h->fcos_select_exact_only = value;
+            return DH_OK;
+        case DH_OPT_FUSED_CHUNKS_PER_CTA:
+            DH_CHECK_ARG(value >= 1 && value <= 64, "DH_OPT_FUSED_CHUNKS_PER_CTA must be in [1, 64]");
+            h->fused_chunks_per_cta = value;
             return DH_OK;
         case DH_OPT_PHASE_TIMING: {
             dh::DeviceGuard g(h->device);

@@ -117,8 +117,10 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
     // image-aligned chunks: aim at >= 8 chunks per CTA, 2..32 tiles (512..8192 rows) each
     const int tpi = a.tt.tiles_per_image;
-    long long want = total / (grid * 8);
-    want = want < 2 ? 2 : (want > 32 ? 32 : want);
+    // measured on B200 (tools/fused_loss_probe.py): chunks of 4..8 tiles (1-2 K rows) balance best -- smaller chunks pay
+    // the chunk-end barrier too often, larger ones leave a tail
+    long long want = total / (grid * h->fused_chunks_per_cta);
+    want = want < 4 ? 4 : (want > 8 ? 8 : want);
     const int n_sub = tpi > 0 ? static_cast<int>((tpi + want - 1) / want) : 1;
     a.chunk_tiles = tpi > 0 ? (tpi + n_sub - 1) / n_sub : 1;
     a.chunks_per_image = tpi > 0 ? (tpi + a.chunk_tiles - 1) / a.chunk_tiles : 1;

@@ -49,5 +49,10 @@ for tag, n, opt in (("real boxes", nd, 0), ("no boxes (stream only)", zero, 0), 
     print(json.dumps({"case": tag, "B": B, "us": round(t * 1e6, 1), "GBps": round(nbytes / t / 1e9, 1),
                       "total": res[tag], "pairs": int(pairs.sum())}), flush=True)
 dh.set_option(0, 5, 0)
+for cpc in (2, 3, 4, 6, 8, 12, 16):
+    dh.set_option(0, 8, cpc)
+    t = timeit(lambda: dh.retinanet.encode_loss_batch(bd, nd, dims, 80, [640, 640], pred))
+    print(json.dumps({"chunks_per_cta": cpc, "B": B, "us": round(t * 1e6, 1), "GBps": round(nbytes / t / 1e9, 1)}), flush=True)
+dh.set_option(0, 8, 12)
 a, b = np.array(res["real boxes"]), np.array(res["smem-tile kernel"])
 print("stream+correct vs smem-tile kernel, relative difference:", (np.abs(a - b) / np.maximum(np.abs(b), 1e-30)).tolist())
