@@ -123,6 +123,77 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const float4* __restr
     if (lane == 0) atomicAdd(out, a);
 }
 
+// software-pipelined variant: the loads of batch n + 1 (possibly of the next sub-tile) are issued before batch n is
+// computed, so a warp always has U loads in flight
+template <int V, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) stream_kernel_pf(const float4* __restrict__ p, long long n_sub, float* out) {
+    static_assert(VPR % U == 0, "U must divide the row length");
+    const int lane = threadIdx.x & 31;
+    const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float4 cur[U], nxt[U];
+    long long s = gw;
+    if (s < n_sub) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = __ldcs(p + s * (32 * VPR) + lane + u * 32);
+    }
+    int c4 = lane % VPR;
+    for (; s < n_sub; s += nw) {
+        const float4* base = p + s * (32 * VPR) + lane;
+#pragma unroll 1
+        for (int k0 = 0; k0 < VPR; k0 += U) {
+            const bool last = k0 + U >= VPR;
+            const float4* nb = last ? p + (s + nw) * (32 * VPR) + lane : base + (k0 + U) * 32;
+            if (!last || s + nw < n_sub) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) nxt[u] = __ldcs(nb + u * 32);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (c4 != 0) {
+                    term<V, 0>(cur[u].x, a0), term<V, 1>(cur[u].y, a1), term<V, 2>(cur[u].z, a2), term<V, 3>(cur[u].w, a3);
+                }
+                c4 += 32 - VPR;
+                if (c4 >= VPR) c4 -= VPR;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        }
+    }
+    float a = (a0 + a1) + (a2 + a3);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) atomicAdd(out, a);
+}
+
+template <int V, int U, int MINB>
+static void run_pf(const char* name, const float4* d, long long n_sub, float* d_out, int ctas_per_sm, double bytes) {
+    int dev, sms;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_kernel_pf<V, U, MINB>, 256, 0));
+    const int per = ctas_per_sm < occ ? ctas_per_sm : occ;
+    const int grid = sms * per;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) stream_kernel_pf<V, U, MINB><<<grid, 256>>>(d, n_sub, d_out);
+    CK(cudaDeviceSynchronize());
+    const int reps = 10;
+    CK(cudaMemset(d_out, 0, 4));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) stream_kernel_pf<V, U, MINB><<<grid, 256>>>(d, n_sub, d_out);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    float h;
+    CK(cudaMemcpy(&h, d_out, 4, cudaMemcpyDeviceToHost));
+    printf("%-28s U=%d minb=%d ctas/sm=%d (occ %d)  %8.3f ms  %8.1f GB/s   sum/rep=%.6e  [prefetch]\n", name, U, MINB, per, occ, ms / reps,
+           bytes / (ms / reps * 1e-3) / 1e9, h / reps);
+}
+
 template <int V, int U, int MINB>
 static void run(const char* name, const float4* d, long long n_sub, float* d_out, int ctas_per_sm, double bytes) {
     int dev, sms;
@@ -180,11 +251,15 @@ int main(int argc, char** argv) {
     }
     printf("buffer %.2f GB, %lld warp sub-tiles\n", bytes / 1e9, n_sub);
     run<0, 7, 1>("read+add", d, n_sub, d_out, 8, bytes);
-#define ROW(U, M)                                                        \
-    run<1, U, M>("3 MUFU", d, n_sub, d_out, 8, bytes);                   \
-    run<5, U, M>("2.75 MUFU", d, n_sub, d_out, 8, bytes);                \
-    run<4, U, M>("2.5 MUFU", d, n_sub, d_out, 8, bytes);                 \
-    run<2, U, M>("2 MUFU", d, n_sub, d_out, 8, bytes);
-    ROW(7, 1) ROW(7, 5) ROW(7, 6) ROW(3, 1) ROW(3, 6) ROW(3, 8) ROW(21, 1) ROW(11, 1)
+    run<4, 7, 4>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
+    run<4, 7, 5>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<4, 3, 4>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<4, 3, 5>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<4, 3, 6>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<4, 7, 3>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<4, 7, 4>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<2, 3, 5>("2 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<2, 7, 4>("2 MUFU", d, n_sub, d_out, 8, bytes);
+    run_pf<1, 3, 5>("3 MUFU", d, n_sub, d_out, 8, bytes);
     return 0;
 }
