@@ -56,20 +56,18 @@ void* scratch_b(dh_handle_s* h, size_t bytes) {
 constexpr int kSchedRing = 64;
 
 unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st) {
+    (void)st;
     if (!h->sched) {
-        cudaError_t e = cudaMalloc(&h->sched, kSchedRing * 32 * sizeof(unsigned int));  // one 128-B line each
+        // one 128-byte line per launch in flight: word 0 = next chunk, word 1 = CTAs done.  Zeroed once; the last CTA of
+        // every launch puts its line back to zero (sched_release), so no per-launch memset node is needed.
+        cudaError_t e = cudaMalloc(&h->sched, kSchedRing * 32 * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMemset(h->sched, 0, kSchedRing * 32 * sizeof(unsigned int));
         if (e != cudaSuccess) {
-            set_error(DH_ERR_CUDA, "cudaMalloc for the scheduler counters failed: %s", cudaGetErrorString(e));
+            set_error(DH_ERR_CUDA, "allocating the scheduler counters failed: %s", cudaGetErrorString(e));
             return nullptr;
         }
     }
-    unsigned int* c = h->sched + (h->sched_next++ % kSchedRing) * 32;
-    cudaError_t e = cudaMemsetAsync(c, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) {
-        set_error(DH_ERR_CUDA, "cudaMemsetAsync on a scheduler counter failed: %s", cudaGetErrorString(e));
-        return nullptr;
-    }
-    return c;
+    return h->sched + (h->sched_next++ % kSchedRing) * 32;
 }
 
 }  // namespace dh

@@ -117,6 +117,20 @@ __device__ __forceinline__ uint32_t fdiv_u32(uint32_t n, const FastDiv& f) {
     return f.d <= 1 ? n : (__umulhi(n, f.mul) >> f.shr);
 }
 
+// ------------------------------------------------------------------ dynamic tile scheduler counter
+// sched[0] hands out chunk ids, sched[1] counts finished CTAs; the last CTA to finish zeroes both, so the line is
+// ready for the next launch that gets it (launches on one stream are ordered; the host rotates lines between launches).
+// Called by one thread per CTA after the CTA's last use of sched[0].
+__device__ __forceinline__ void sched_release(unsigned int* sched) {
+    __threadfence();
+    const unsigned done = atomicAdd(sched + 1, 1u);
+    if (done == gridDim.x - 1) {
+        sched[0] = 0u;
+        sched[1] = 0u;
+        __threadfence();
+    }
+}
+
 // ------------------------------------------------------------------ reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -108,7 +108,10 @@ __global__ void __launch_bounds__(DH_THREADS) encode_kernel(const __grid_constan
     const long long n_chunks = ga.n_chunks;
     const int tpi = ga.tt.tiles_per_image;
     long long chunk = blockIdx.x;
-    if (chunk >= n_chunks) return;
+    if (chunk >= n_chunks) {  // (the launchers clamp the grid to the chunk count; kept for safety)
+        if (threadIdx.x == 0) sched_release(ga.sched);
+        return;
+    }
 
     // zero the stage buffers once; afterwards only dirtied rows are re-zeroed
     {
@@ -262,7 +265,10 @@ __global__ void __launch_bounds__(DH_THREADS) encode_kernel(const __grid_constan
     chunk = *next_chunk;
     __syncthreads();  // ... and read by all before thread 0 overwrites it
     }
-    if (tid == 0) bulk_wait_read<0>();
+    if (tid == 0) {
+        bulk_wait_read<0>();
+        sched_release(ga.sched);
+    }
     if (prof) {
         DH_PHASE(4)
         for (int i = 0; i < 5; ++i)

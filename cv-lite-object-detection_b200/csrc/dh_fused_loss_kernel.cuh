@@ -375,7 +375,10 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     const int tpi = ga.tt.tiles_per_image;
     const long long n_chunks = static_cast<long long>(ga.tt.batch) * ga.chunks_per_image;
     long long chunk = blockIdx.x;
-    if (chunk >= n_chunks) return;
+    if (chunk >= n_chunks) {  // (the launchers clamp the grid to the chunk count; kept for safety)
+        if (threadIdx.x == 0) sched_release(ga.sched);
+        return;
+    }
     if (tid == 0) {
         mbar_init(boxbar, 1);
         mbar_init_fence();
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         chunk = *next_chunk;
         __syncthreads();  // wred / next_chunk are free again
     }
+    if (tid == 0) sched_release(ga.sched);
 }
 
 }  // namespace dh

@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
     const int tpi = ga.tt.tiles_per_image;
     const long long n_chunks = static_cast<long long>(ga.tt.batch) * ga.chunks_per_image;
     long long chunk = blockIdx.x;
-    if (chunk >= n_chunks) return;
+    if (chunk >= n_chunks) {  // (the launchers clamp the grid to the chunk count; kept for safety)
+        if (threadIdx.x == 0) sched_release(ga.sched);
+        return;
+    }
 
     {  // shared-memory state that must start at zero
         float4* z = reinterpret_cast<float4*>(smem + lay.tgt_off);
@@ -506,6 +509,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
         chunk = *next_chunk;
         __syncthreads();  // wred / next_chunk are free again
     }
+    if (tid == 0) sched_release(ga.sched);
 }
 
 // partials [B * chunks_per_image, 4] -> per_image [B, 4]; one CTA per image, fixed summation order
