@@ -97,6 +97,7 @@ int dh_create(dh_handle_t* out, int device) {
     h->fused_loss_kernel = 0;
     h->nms_kernel = 0;
     h->fused_chunks_per_cta = 12;
+    h->encode_min_chunk = 2;
     h->fcos_select_exact_only = 0;
     h->launches = 0;
     h->scratch = nullptr;
@@ -152,6 +153,10 @@ int dh_set_option(dh_handle_t h, int option, int value) {
         case DH_OPT_FUSED_CHUNKS_PER_CTA:
             DH_CHECK_ARG(value >= 1 && value <= 64, "DH_OPT_FUSED_CHUNKS_PER_CTA must be in [1, 64]");
             h->fused_chunks_per_cta = value;
+            return DH_OK;
+        case DH_OPT_ENCODE_MIN_CHUNK:
+            DH_CHECK_ARG(value >= 1 && value <= 64, "DH_OPT_ENCODE_MIN_CHUNK must be in [1, 64]");
+            h->encode_min_chunk = value;
             return DH_OK;
         case DH_OPT_PHASE_TIMING: {
             dh::DeviceGuard g(h->device);

@@ -69,11 +69,15 @@ static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, cons
     const long long total2 = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;  // the table may have been re-cut
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
     if (grid > total2) grid = total2;
-    // image-aligned chunks for the dynamic scheduler: aim at >= ~8 chunks per CTA, 8..64 tiles each
+    // image-aligned chunks for the dynamic scheduler: aim at ~8 chunks per CTA of up to 64 tiles each; a problem with
+    // fewer tiles than that is cut into about one chunk per CTA (2..8 tiles) so that it still spreads over every SM --
+    // per CTA the work is a chain of latencies, so a 4 MB output finishes sooner on 592 CTAs x 1-2 tiles than on 72 x 11
     {
         const int tpi = a.tt.tiles_per_image;
         long long want = total2 / (grid * 8);
-        want = want < 8 ? 8 : (want > 64 ? 64 : want);
+        long long lo = total2 / grid;  // measured (tools/quick_encode_bench.py): about one chunk per CTA, 2..8 tiles each
+        lo = lo < h->encode_min_chunk ? h->encode_min_chunk : (lo > 8 ? 8 : lo);
+        want = want < lo ? lo : (want > 64 ? 64 : want);
         if (tpi <= want) {
             a.chunks_per_image = 1;
             a.images_per_chunk = static_cast<int>(want / tpi);

@@ -53,6 +53,7 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_NMS_KERNEL 6 /* 0 (default): pick per call; 1: lazy one-CTA-per-image NMS whenever the output cap is <= 1024; 2: always mask matrix on all SMs + block sweep */
 #define DH_OPT_FCOS_SELECT 7 /* 0 (default): dh_fcos_detect selects in logit space when it can; 1: always score every pair (A/B checks) */
 #define DH_OPT_FUSED_CHUNKS_PER_CTA 8 /* fused loss scheduler: aim at this many image-aligned chunks per persistent CTA (default 12; a chunk is always 4..8 tiles of 256 rows) */
+#define DH_OPT_ENCODE_MIN_CHUNK 9 /* encoders: smallest scheduler chunk in tiles (default 2) */
 int dh_set_option(dh_handle_t h, int option, int value);
 /* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in
  * {stage GT + records, candidates + buffer recycle, emit rows, hand-off to TMA, drain}, out8[5] = tiles. */

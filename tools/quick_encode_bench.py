@@ -20,6 +20,29 @@ def run(tag, fn, nbytes):
     print(json.dumps({"case": tag, "us": round(t * 1e6, 2), "GBps": round(nbytes / t / 1e9, 1)}), flush=True)
 
 SC = [32, 64, 128, 256, 512]
+for mc in (2,):
+    dh.set_option(0, 9, mc)
+    for cfg, B, side, C in (("fcos_voc", 8, 512, 20), ("fcos_voc", 32, 512, 20), ("fcos_voc", 256, 512, 20)):
+        boxes, nbox = synth.config_boxes(cfg, B, 1)
+        bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+        dims = torch.tensor([[float(side)] * 2] * B, device="cuda")
+        outs, cnt = dh.fcos.format_data_batch(bd, nd, dims, C, [side, side])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            dh.fcos.format_data_batch(bd, nd, dims, C, [side, side], out=outs, num_targets=cnt)
+        run("min_chunk=%d fcos B=%d (graph)" % (mc, B), g.replay, sum(o.numel() for o in outs) * 4)
+    for B in (32, 256):
+        boxes, nbox = synth.config_boxes("centernet_crowdhuman", B, 2)
+        bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+        dims = torch.tensor([[512., 512.]] * B, device="cuda")
+        out, st = dh.centernet.format_data_batch(bd, nd, dims, 1, [512, 512], stride=4, mode="s8", box_scales=SC)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            dh.centernet.format_data_batch(bd, nd, dims, 1, [512, 512], stride=4, mode="s8", box_scales=SC, out=out, status=st)
+        run("min_chunk=%d centernet B=%d (graph)" % (mc, B), g.replay, out.numel() * 4)
+dh.set_option(0, 9, 2)
+sys.exit(0)
+SC = [32, 64, 128, 256, 512]
 for tma in (1, 0):
     dh.set_option(0, 1, tma)
     for B in (8, 256):
