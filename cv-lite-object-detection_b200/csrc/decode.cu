@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_segs_kernel(const flo
                                                                        int score_col, SelSegs segs, int k_slots, float min_score, int inclusive,
                                                                        float* __restrict__ out, int out_rows, int* __restrict__ overflow) {
     __shared__ SelShared sh;
-    const int b = blockIdx.y, seg = blockIdx.x;
+    const int b = blockIdx.x, seg = blockIdx.y;  // level-major dispatch: the long (fine-level) segments of every image start first
     const int lo = segs.off[seg], hi = segs.off[seg + 1];
     RowSource src;
     src.rows = dets + (static_cast<long long>(b) * n_total + lo) * row_floats;
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
                                                                   float min_score, int inclusive, float* __restrict__ out,
                                                                   int* __restrict__ out_src, int out_rows) {
     __shared__ SelShared sh;
-    const int b = blockIdx.y, seg = blockIdx.x;
+    const int b = blockIdx.x, seg = blockIdx.y;
     const int lo = seg_off[seg], hi = seg_off[seg + 1];
     RowSource src;
     src.rows = dets + (static_cast<long long>(b) * n_total + lo) * row_floats;
@@ -646,25 +646,37 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
     const int rows = n / src.num_classes;
     const int n_items = kVec ? (rows * src.ch) >> 2 : n;
     const FastDiv div_ch = make_fastdiv(static_cast<uint32_t>(src.ch));
-    // item -> W logits (-inf where the slot is not a class channel / out of range) and their pair indices
-    auto load = [&](int item, float* x, int* idx) {
+    // item -> W logits (-inf where the slot is not a class channel / out of range).  The pair index of slot e is only
+    // needed for the few entries near the cut, so it is derived on demand from the item's (row, first channel): most
+    // float4 items lie entirely inside the class channels and need no per-slot channel test at all.
+    struct ItemPos {
+        int r, c;  // row and channel of slot 0 (vector items); unused for scalar items
+    };
+    auto load = [&](int item, float* x, ItemPos& pos) {
         if (!kVec) {
             x[0] = item < n_items ? src.logit(item) : -INFINITY;
-            idx[0] = item;
             return;
         }
         float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         if (item < n_items) v = __ldg(reinterpret_cast<const float4*>(src.head) + item);
         const int p0 = item << 2;
-        int r = static_cast<int>(fdiv_u32(static_cast<uint32_t>(p0), div_ch));
-        int c = p0 - r * src.ch;
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        pos.r = static_cast<int>(fdiv_u32(static_cast<uint32_t>(p0), div_ch));
+        pos.c = p0 - pos.r * src.ch;
+        x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+        if (pos.c < 5 || pos.c > src.ch - 4) {  // the item touches the 5 regression / centerness channels of a row
+            int c = pos.c;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            x[e] = c >= 5 ? vv[e] : -INFINITY;
-            idx[e] = r * src.num_classes + (c - 5);
-            if (++c == src.ch) c = 0, ++r;
+            for (int e = 0; e < 4; ++e) {
+                if (c < 5) x[e] = -INFINITY;
+                if (++c == src.ch) c = 0;
+            }
         }
+    };
+    auto pair_index = [&](int item, const ItemPos& pos, int e) {
+        if (!kVec) return item;
+        int r = pos.r, c = pos.c + e;
+        if (c >= src.ch) c -= src.ch, ++r;
+        return r * src.num_classes + (c - 5);
     };
     const float x_thr = logf(min_score / (1.0f - min_score));
     const float thr_lo = x_thr - 1.0e-3f, thr_hi = x_thr + 1.0e-3f;
@@ -681,9 +693,9 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
     __syncthreads();
     for (int base = 0; base < n_items; base += kSelThreads * U) {
         float x[U][W];
-        int idx[U][W];
+        ItemPos pos[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], idx[u]);
+        for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], pos[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -723,9 +735,9 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
         // collect the entries that can tie with the k-th score, with their exact scores
         for (int base = 0; base < n_items; base += kSelThreads * U) {
             float x[U][W];
-            int idx[U][W];
+            ItemPos pos[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], idx[u]);
+            for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], pos[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -734,7 +746,8 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
                     const int bn = bin_x(x[u][e]);
                     if (bn < lo_bin || bn > hi_bin) continue;
                     const unsigned slot = atomicAdd(&sh.n_list, 1u);
-                    sh.list_key[slot] = score_key(sigmoid_acc(x[u][e])), sh.list_idx[slot] = idx[u][e];
+                    sh.list_key[slot] = score_key(sigmoid_acc(x[u][e]));
+                    sh.list_idx[slot] = pair_index(base + u * kSelThreads + tid, pos[u], e);
                 }
         }
         __syncthreads();
@@ -759,9 +772,9 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
     int it = 0;
     for (int base = 0; base < n_items; base += kSelThreads * IPT, ++it) {
         float x[IPT][W];
-        int idx[IPT][W];
+        ItemPos pos[IPT];
 #pragma unroll
-        for (int u = 0; u < IPT; ++u) load(base + tid * IPT + u, x[u], idx[u]);
+        for (int u = 0; u < IPT; ++u) load(base + tid * IPT + u, x[u], pos[u]);
         unsigned flags = 0;
 #pragma unroll
         for (int u = 0; u < IPT; ++u)
@@ -775,7 +788,7 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
                     if (bn > hi_bin) take = true;
                     else if (bn >= lo_bin) {
                         const unsigned key = score_key(sigmoid_acc(xv));
-                        take = key > T_key || (key == T_key && idx[u][e] <= T_idx);
+                        take = key > T_key || (key == T_key && pair_index(base + tid * IPT + u, pos[u], e) <= T_idx);
                     }
                 }
                 if (take) flags |= 1u << (u * W + e);
@@ -802,7 +815,8 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
 #pragma unroll
             for (int e = 0; e < W; ++e) {
                 if (!((flags >> (u * W + e)) & 1u)) continue;
-                if (rank < static_cast<unsigned>(k)) src.emit(idx[u][e], sigmoid_acc(x[u][e]), static_cast<int>(rank));
+                if (rank < static_cast<unsigned>(k))
+                    src.emit(pair_index(base + tid * IPT + u, pos[u], e), sigmoid_acc(x[u][e]), static_cast<int>(rank));
                 ++rank;
             }
         carry += tot;
@@ -821,7 +835,7 @@ struct FcosSelectArgs {
 };
 __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs a, float* __restrict__ cand /*[B, L*k, 6]*/) {
     __shared__ SelShared sh;
-    const int b = blockIdx.y, l = blockIdx.x;
+    const int b = blockIdx.x, l = blockIdx.y;  // level-major dispatch: the 64 x 512 K-logit level-0 CTAs start first, the rest fill in
     FcosSource src;
     const int rows = a.hl[l] * a.wl[l];
     src.ch = a.num_classes + 5, src.num_classes = a.num_classes, src.wl = a.wl[l], src.center = a.center, src.stride = a.stride[l];
@@ -859,7 +873,7 @@ int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batc
         if (a.wl[l] < 1) a.wl[l] = 1, a.hl[l] = 0;
         a.stride[l] = static_cast<float>(strides[l]);
     }
-    dim3 grid(n_levels, batch);
+    dim3 grid(batch, n_levels);
     fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -871,7 +885,7 @@ int launch_select_segs(dh_handle_s* h, const float* dets, int batch, long long n
     SelSegs segs;
     memset(&segs, 0, sizeof(segs));
     for (int s = 0; s <= n_seg; ++s) segs.off[s] = seg_off_host[s];
-    dim3 grid(n_seg, batch);
+    dim3 grid(batch, n_seg);
     select_topk_segs_kernel<<<grid, kSelThreads, 0, st>>>(dets, n_total, row_floats, score_col, segs, k, min_score, inclusive, out, n_seg * k,
                                                           overflow);
     DH_CUDA(cudaGetLastError());
@@ -1012,7 +1026,7 @@ int dh_select_topk(dh_handle_t h, const float* dets, int batch, long long n_tota
                  "dh_select_topk: bad sizes");
     if (batch == 0) return DH_OK;
     DeviceGuard guard(h->device);
-    dim3 grid(n_seg, batch);
+    dim3 grid(batch, n_seg);
     select_topk_kernel<<<grid, kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(dets, n_total, row_floats, score_col, seg_off_dev, k, min_score,
                                                                                    score_inclusive, out, out_src, n_seg * k);
     DH_CUDA(cudaGetLastError());
