@@ -2,7 +2,8 @@
 
 There is NO CPU fallback: if the shared library is missing or a call fails, this raises.
 PyTorch is used only as the device-memory / stream provider; tensors cross the boundary as raw
-device pointers (see `_dlpack.py` for foreign DLPack producers such as TensorFlow).
+device pointers (`_tensors.to_device` consumes DLPack capsules and `__dlpack__` objects zero-copy; `_dlpack.py` reads a
+capsule without any framework, which is what a TensorFlow-side binding uses).
 """
 import ctypes
 import os

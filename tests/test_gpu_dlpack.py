@@ -1,0 +1,42 @@
+"""Tensors cross the boundary zero-copy via DLPack: device-resident capsules / `__dlpack__` objects (what
+`tf.experimental.dlpack.to_dlpack` produces on the reference side) reach the kernels without a copy, and the raw-pointer
+reader of densehead/_dlpack.py agrees with the framework about where the data lives."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import synth  # noqa: E402
+
+
+class Foreign:
+    """A tensor from 'another framework': speaks only the DLPack protocol."""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __dlpack__(self, stream=None):
+        return self._t.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+def test_device_capsules_are_consumed_without_a_copy():
+    import densehead as dh
+    from densehead import _dlpack, _tensors
+    boxes, nbox = synth.config_boxes("fcos_voc", 4, synth.seed_for(8, 1))
+    pred = [torch.from_numpy(p).cuda() for p in synth.fcos_predictions(4, 512, 20, 3)]
+    bt, nt = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+    v = _dlpack.view(torch.utils.dlpack.to_dlpack(pred[0]))
+    assert v.ptr == pred[0].data_ptr() and v.device == ("cuda", 0) and v.dtype == "float32" and v.is_contiguous()
+    assert _tensors.to_device(torch.utils.dlpack.to_dlpack(pred[0]), torch.float32).data_ptr() == pred[0].data_ptr()
+    assert _tensors.to_device(Foreign(pred[0]), torch.float32).data_ptr() == pred[0].data_ptr()
+    want = dh.fcos.encode_loss_batch(bt, nt, [512, 512], 20, [512, 512], pred)
+    got = dh.fcos.encode_loss_batch(torch.utils.dlpack.to_dlpack(bt), Foreign(nt), [512, 512], 20, [512, 512],
+                                    [torch.utils.dlpack.to_dlpack(p) if i % 2 else Foreign(p) for i, p in enumerate(pred)])
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
+    outs, cnt = dh.fcos.format_data_batch(Foreign(bt), torch.utils.dlpack.to_dlpack(nt), [512, 512], 20, [512, 512])
+    outs2, cnt2 = dh.fcos.format_data_batch(boxes, nbox, [512, 512], 20, [512, 512])
+    assert torch.equal(cnt, cnt2) and all(torch.equal(a, b) for a, b in zip(outs, outs2))
