@@ -3,7 +3,7 @@
 
 #include "dh_host.h"
 #include "dh_launch.h"
-#include "dh_fused_loss_kernel.cuh"
+#include "dh_dense_stream_kernel.cuh"
 
 namespace dh {
 
@@ -179,6 +179,68 @@ static int launch_fused(dh_handle_s* h, LossArgs<P>& a, int num_classes, float* 
     return launch_fused_g<P, 0, false>(h, a, out_per_image, out_total, st, who);
 }
 
+// Loss over materialised targets, stream + row-pass kernel (dh_dense_stream_kernel.cuh): 256-row tiles, 32 rows per warp.
+template <int kCls, bool kGrad>
+static int launch_dense_g(dh_handle_s* h, LossArgs<NoPolicy>& a, float* out_per_image, float* out_total, cudaStream_t st) {
+    const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
+    const size_t smem = (sizeof(LossArgs<NoPolicy>) + 127) & ~size_t(127);
+    int per_sm = 1;
+    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_stream_kernel<kCls, kGrad>, DH_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = static_cast<long long>(h->sm_count) * per_sm;
+    const int tpi = a.tt.tiles_per_image;
+    long long want = total / (grid * h->fused_chunks_per_cta);
+    want = want < 4 ? 4 : (want > 8 ? 8 : want);
+    const int n_sub = tpi > 0 ? static_cast<int>((tpi + want - 1) / want) : 1;
+    a.chunk_tiles = tpi > 0 ? (tpi + n_sub - 1) / n_sub : 1;
+    a.chunks_per_image = tpi > 0 ? (tpi + a.chunk_tiles - 1) / a.chunk_tiles : 1;
+    const long long n_chunks = static_cast<long long>(a.tt.batch) * a.chunks_per_image;
+    if (grid > n_chunks) grid = n_chunks;
+    const size_t part_bytes = static_cast<size_t>(n_chunks) * 16;
+    const size_t img_bytes = static_cast<size_t>(a.tt.batch) * 16;
+    char* sc = static_cast<char*>(scratch(h, part_bytes + img_bytes + 512));
+    if (!sc) return DH_ERR_CUDA;
+    a.partials = reinterpret_cast<float*>(sc);
+    float* per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
+    if (total > 0) {
+        a.sched = next_sched_counter(h, st);
+        if (!a.sched) return DH_ERR_CUDA;
+        dense_stream_kernel<kCls, kGrad><<<static_cast<unsigned>(grid), DH_THREADS, smem, st>>>(a);
+        DH_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    if (!out_per_image && !out_total) return DH_OK;  // gradient only
+    return finalize_loss(h, a.partials, a.tt.batch, total > 0 ? a.chunks_per_image : 0, per_image, out_total, st);
+}
+
+static int launch_dense(dh_handle_s* h, LossArgs<NoPolicy>& a, float* out_per_image, float* out_total, cudaStream_t st) {
+    if (a.tt.batch == 0) return DH_OK;
+    const int ch = a.tt.ch;
+    if (h->fused_loss_kernel == 1) {  // A/B: the shared-memory tile kernel
+        a.tile_buf_bytes = finish_table(a.tt, ch, a.tt.batch, loss_tile_bytes(h));
+        return launch_loss<NoPolicy, false>(h, a, out_per_image, out_total, st, "dh_dense_loss");
+    }
+    finish_table(a.tt, ch, a.tt.batch, DH_THREADS * ch * 4);
+    a.allow_vec = 1;
+    bool grad = false;
+    for (int m = 0; m < a.tt.n_maps; ++m) {
+        const MapDesc& md = a.tt.maps[m];
+        if ((reinterpret_cast<uintptr_t>(md.pred) | reinterpret_cast<uintptr_t>(md.out) | reinterpret_cast<uintptr_t>(a.grad_maps[m])) & 15u)
+            a.allow_vec = 0;
+        if (md.image_stride & 3) a.allow_vec = 0;
+        grad = grad || a.grad_maps[m] != nullptr;
+    }
+    const int kind = a.spec.cls_mode == 1 ? 2 : (a.spec.gamma == 2.0f ? 1 : 0);
+    if (grad) {
+        if (kind == 2) return launch_dense_g<2, true>(h, a, out_per_image, out_total, st);
+        if (kind == 1) return launch_dense_g<1, true>(h, a, out_per_image, out_total, st);
+        return launch_dense_g<0, true>(h, a, out_per_image, out_total, st);
+    }
+    if (kind == 2) return launch_dense_g<2, false>(h, a, out_per_image, out_total, st);
+    if (kind == 1) return launch_dense_g<1, false>(h, a, out_per_image, out_total, st);
+    return launch_dense_g<0, false>(h, a, out_per_image, out_total, st);
+}
+
 }  // namespace dh
 
 using namespace dh;
@@ -221,7 +283,7 @@ static int dense_loss_impl(const GradOut* go, dh_handle_t h, int n_maps, const f
         md.level = m, md.anchor = 0;
         a.mask_maps[m] = mask_maps ? mask_maps[m] : nullptr;
     }
-    a.tile_buf_bytes = finish_table(a.tt, ch, batch, loss_tile_bytes(h));
+    a.tt.ch = ch, a.tt.batch = batch;
     if (go) {
         a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
         for (int m = 0; m < n_maps; ++m) {
@@ -229,7 +291,7 @@ static int dense_loss_impl(const GradOut* go, dh_handle_t h, int n_maps, const f
             a.grad_maps[m] = go->grad[m];
         }
     }
-    return launch_loss<NoPolicy, false>(h, a, out_per_image, out_total, static_cast<cudaStream_t>(stream), "dh_dense_loss");
+    return launch_dense(h, a, out_per_image, out_total, static_cast<cudaStream_t>(stream));
 }
 
 static int fcos_encode_loss_impl(const GradOut* go, dh_handle_t h, const float* boxes, const int32_t* nbox, const float* img_dim, int batch,
