@@ -34,10 +34,16 @@ __device__ __forceinline__ void dense_vec(const LossSpec& sp, const float* __res
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c4 != 0) {
             if (y.x == 0.f && y.y == 0.f && y.z == 0.f && y.w == 0.f) {
-                d.x = stream_term<kCls, false, kGrad>(x.x, sp.gamma, a.s.c0) * gscale;
-                d.y = stream_term<kCls, true, kGrad>(x.y, sp.gamma, a.s.c1) * gscale;
-                d.z = stream_term<kCls, true, kGrad>(x.z, sp.gamma, a.s.c2) * gscale;
-                d.w = stream_term<kCls, false, kGrad>(x.w, sp.gamma, a.s.c3) * gscale;
+                if (kCls == 1) {
+                    stream_pair_g2<kGrad>(x.x, x.y, a.s.p0, d.x, d.y);
+                    stream_pair_g2<kGrad>(x.z, x.w, a.s.p1, d.z, d.w);
+                } else {
+                    d.x = stream_term<kCls, false, kGrad>(x.x, sp.gamma, a.s.c0);
+                    d.y = stream_term<kCls, true, kGrad>(x.y, sp.gamma, a.s.c1);
+                    d.z = stream_term<kCls, true, kGrad>(x.z, sp.gamma, a.s.c2);
+                    d.w = stream_term<kCls, false, kGrad>(x.w, sp.gamma, a.s.c3);
+                }
+                d.x *= gscale, d.y *= gscale, d.z *= gscale, d.w *= gscale;
             } else {  // rare: a labelled class channel
                 d.x = labelled_term<kCls, false, kGrad>(sp, y.x, x.x, gscale, a.s.c0, a.cls_nat);
                 d.y = labelled_term<kCls, false, kGrad>(sp, y.y, x.y, gscale, a.s.c1, a.cls_nat);
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) dense_stream_kernel(const __gri
         const int sub = static_cast<int>(chunk - static_cast<long long>(img) * ga.chunks_per_image);
         const int t_begin = sub * ga.chunk_tiles, t_end = min(t_begin + ga.chunk_tiles, tpi);
         if (tid == 0) next_chunk = static_cast<long long>(atomicAdd(ga.sched, 1u)) + gridDim.x;
-        DenseAcc acc = {{0.f, 0.f, 0.f, 0.f, 0.f}, 0.f};
+        DenseAcc acc = {{0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull}, 0.f};
         float reg = 0.f;
         int npos = 0;
         TileCursor cur;
@@ -196,7 +202,10 @@ __global__ void __launch_bounds__(DH_THREADS, 4) dense_stream_kernel(const __gri
             }
             __syncwarp();
         }
-        float cls = ((acc.s.c0 + acc.s.c1) + (acc.s.c2 + acc.s.c3)) * ((kCls == 2 ? 1.0f : 1.0f - sp.alpha) * kLn2) + acc.cls_nat;
+        float q0, q1, q2, q3;
+        unpack2(acc.s.p0, q0, q1);
+        unpack2(acc.s.p1, q2, q3);
+        float cls = (((acc.s.c0 + acc.s.c1) + (acc.s.c2 + acc.s.c3)) + ((q0 + q1) + (q2 + q3))) * ((kCls == 2 ? 1.0f : 1.0f - sp.alpha) * kLn2) + acc.cls_nat;
         cls = warp_sum(cls);
         reg = warp_sum(reg);
         const float cen = warp_sum(acc.s.cen);

@@ -79,6 +79,59 @@ __device__ __forceinline__ float stream_term(float x, float gamma, float& acc) {
     const float om = (x < 0.f ? 1.0f : e) * inv;     // 1 - sigmoid(x)
     return pw * fmaf((kCls == 1 ? 2.0f : gamma) * kLn2 * om, sp2, s);
 }
+// ---- packed fp32 (sm_100a FFMA2 / FMUL2 / FADD2): two elements per FMA-pipe instruction --------------------------
+// The streaming pass is bound by instruction issue, not by HBM: with the reciprocal on the FMA pipe (2 MUFU per
+// element) and the FMA-pipe work packed two-wide, the loop of tools/focal_stream_probe.cu moves from 5.6 to 6.3 TB/s.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// two label == 0 focal elements with gamma == 2: acc += sigmoid(x)^2 * softplus(x) / ln 2 (both lanes of `acc`); with
+// kGrad the derivatives s^2 * (2 (1 - s) softplus(x) + s) come back in (d0, d1), before the caller's scale
+template <bool kGrad>
+__device__ __forceinline__ void stream_pair_g2(float x0, float x1, f32x2& acc, float& d0, float& d1) {
+    const f32x2 one = pack2(1.0f, 1.0f);
+    float u0, u1;
+    unpack2(mul2(pack2(x0, x1), pack2(kLog2e, kLog2e)), u0, u1);
+    const float e0 = ex2_fast(-fabsf(u0)), e1 = ex2_fast(-fabsf(u1));  // exp(-|x|)
+    const f32x2 w = add2(pack2(e0, e1), one);
+    float w0, w1;
+    unpack2(w, w0, w1);
+    // 1 / w for w in [1, 2]: quadratic seed + two Newton steps, all on the FMA pipe
+    const f32x2 nw = mul2(w, pack2(-1.0f, -1.0f));
+    f32x2 r = fma2(fma2(pack2(0.32323232f, 0.32323232f), w, pack2(-1.45454545f, -1.45454545f)), w, pack2(2.12121212f, 2.12121212f));
+    f32x2 t = fma2(nw, r, one);
+    r = fma2(r, t, r);
+    t = fma2(nw, r, one);
+    const f32x2 inv = fma2(r, t, r);
+    const f32x2 sp2 = add2(pack2(lg2_fast(w0), lg2_fast(w1)), pack2(fmaxf(u0, 0.f), fmaxf(u1, 0.f)));  // softplus(x) / ln 2
+    const f32x2 s = mul2(pack2(x0 < 0.f ? e0 : 1.0f, x1 < 0.f ? e1 : 1.0f), inv);                      // sigmoid(x)
+    const f32x2 pw = mul2(s, s);
+    acc = fma2(pw, sp2, acc);
+    if (kGrad) {
+        const f32x2 om = mul2(pack2(x0 < 0.f ? 1.0f : e0, x1 < 0.f ? 1.0f : e1), inv);  // 1 - sigmoid(x)
+        unpack2(mul2(pw, fma2(mul2(om, pack2(2.0f * kLn2, 2.0f * kLn2)), sp2, s)), d0, d1);
+    }
+}
+
 // smooth-L1(0, sigmoid(x)): the centerness term of an all-zero row (FCOS/fcos.py:483-486)
 __device__ __forceinline__ float cen_l1_zero(float x, float delta) {
     const float s = sigmoid_f(x);
@@ -103,6 +156,7 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
 struct StreamAcc {
     float c0, c1, c2, c3;  // class focal, log2 units (4 chains for ILP)
     float cen;             // centerness of all-zero rows, natural units
+    f32x2 p0, p1;          // packed-math chains of the gamma == 2 vector path (two lanes each), log2 units
 };
 
 // ---- the label-free pass over one warp tile: rows [0, nrows) x ch floats starting at `p` --------------------
@@ -112,10 +166,15 @@ template <int kCls, bool kGrad>
 __device__ __forceinline__ void stream_vec_item(const float4& x, bool is_reg, float gamma, float gscale, StreamAcc& a, float4* g) {
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!is_reg) {  // float4 0 of a row = the 4 regression channels
-        d.x = stream_term<kCls, true, kGrad>(x.x, gamma, a.c0);
-        d.y = stream_term<kCls, true, kGrad>(x.y, gamma, a.c1);
-        d.z = stream_term<kCls, true, kGrad>(x.z, gamma, a.c2);
-        d.w = stream_term<kCls, false, kGrad>(x.w, gamma, a.c3);
+        if (kCls == 1) {
+            stream_pair_g2<kGrad>(x.x, x.y, a.p0, d.x, d.y);
+            stream_pair_g2<kGrad>(x.z, x.w, a.p1, d.z, d.w);
+        } else {
+            d.x = stream_term<kCls, true, kGrad>(x.x, gamma, a.c0);
+            d.y = stream_term<kCls, true, kGrad>(x.y, gamma, a.c1);
+            d.z = stream_term<kCls, true, kGrad>(x.z, gamma, a.c2);
+            d.w = stream_term<kCls, false, kGrad>(x.w, gamma, a.c3);
+        }
     }
     if (kGrad) __stcs(g, make_float4(d.x * gscale, d.y * gscale, d.z * gscale, d.w * gscale));
 }
@@ -322,7 +381,7 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
 // ---- stream: every element of this warp's tiles as if its label were zero -----------------------------------------
 template <class P, int kCls, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img, int t_begin, int t_end) {
-    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
+    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vpr = a.tt.ch >> 2;
     const int step = 32 % vpr, c_lane = lane % vpr;
@@ -340,7 +399,7 @@ __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img,
 }
 template <class P, int kCls, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int img, int t_begin, int t_end) {
-    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f};
+    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ch = a.tt.ch;
     const int step = 32 % ch, c_lane = lane % ch;
@@ -410,7 +469,10 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         if (n_boxes > 0) acc = correct_pass<P>(a, recs, n_boxes, cand, img, t_begin, t_end);
 
         // ---- per-chunk reduction -> partials[chunk] -----------------------------------------------------------
-        float cls = ((sa.c0 + sa.c1) + (sa.c2 + sa.c3)) * ((kCls == 2 ? 1.0f : 1.0f - ga.spec.alpha) * kLn2) + acc.cls;
+        float q0, q1, q2, q3;
+        unpack2(sa.p0, q0, q1);
+        unpack2(sa.p1, q2, q3);
+        float cls = (((sa.c0 + sa.c1) + (sa.c2 + sa.c3)) + ((q0 + q1) + (q2 + q3))) * ((kCls == 2 ? 1.0f : 1.0f - ga.spec.alpha) * kLn2) + acc.cls;
         float cen = sa.cen + acc.cen;
         cls = warp_sum(cls), cen = warp_sum(cen);
         const float reg = warp_sum(acc.reg);

@@ -87,6 +87,59 @@ __device__ __forceinline__ void term(float x, float& acc) {
     if (V == 5) { if (E == 3) term2(x, acc); else term3(x, acc); }  // a quarter
 }
 
+// ---- packed-fp32 variant (sm_100a FFMA2 / FMUL2 / FADD2): two elements per FMA-pipe instruction -----------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// kNewton: both reciprocals on the FMA pipe (2 MUFU per element), else MUFU.RCP (3 MUFU per element)
+template <bool kNewton>
+__device__ __forceinline__ void term_pair(float x0, float x1, u64& acc) {
+    const u64 kL2E = pack2(kLog2e, kLog2e), kOne = pack2(1.0f, 1.0f);
+    const u64 u = mul2(pack2(x0, x1), kL2E);
+    float u0, u1;
+    unpack2(u, u0, u1);
+    const float e0 = ex2f(-fabsf(u0)), e1 = ex2f(-fabsf(u1));
+    const u64 w = add2(pack2(e0, e1), kOne);
+    float w0, w1;
+    unpack2(w, w0, w1);
+    u64 inv;
+    if (kNewton) {
+        const u64 c2 = pack2(0.32323232f, 0.32323232f), c1 = pack2(-1.45454545f, -1.45454545f), c0 = pack2(2.12121212f, 2.12121212f);
+        const u64 nw = mul2(w, pack2(-1.0f, -1.0f));
+        u64 r = fma2(fma2(c2, w, c1), w, c0);
+        u64 t = fma2(nw, r, kOne);
+        r = fma2(r, t, r);
+        t = fma2(nw, r, kOne);
+        inv = fma2(r, t, r);
+    } else {
+        inv = pack2(rcpf(w0), rcpf(w1));
+    }
+    const float lg0 = lg2f(w0), lg1 = lg2f(w1);
+    const u64 sel = pack2(x0 < 0.f ? e0 : 1.0f, x1 < 0.f ? e1 : 1.0f);
+    const u64 s = mul2(sel, inv);
+    const u64 sp = add2(pack2(lg0, lg1), pack2(fmaxf(u0, 0.f), fmaxf(u1, 0.f)));
+    acc = fma2(mul2(s, s), sp, acc);
+}
+
 constexpr int VPR = 21;  // float4 per row (84 channels)
 
 // each warp owns 32-row sub-tiles (672 float4, contiguous); lane takes q = lane + 32 k and skips the one k whose
@@ -194,6 +247,70 @@ static void run_pf(const char* name, const float4* d, long long n_sub, float* d_
            bytes / (ms / reps * 1e-3) / 1e9, h / reps);
 }
 
+template <bool kNewton, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) stream_kernel_packed(const float4* __restrict__ p, long long n_sub, float* out) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    u64 a0 = 0ull, a1 = 0ull;
+    for (long long s = gw; s < n_sub; s += nw) {
+        const float4* base = p + s * (32 * VPR) + lane;
+        int c4 = lane % VPR;
+#pragma unroll 1
+        for (int k0 = 0; k0 < VPR; k0 += U) {
+            float4 x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < VPR) x[u] = __ldcs(base + (k0 + u) * 32);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k0 + u < VPR) {
+                    if (c4 != 0) {
+                        term_pair<kNewton>(x[u].x, x[u].y, a0);
+                        term_pair<kNewton>(x[u].z, x[u].w, a1);
+                    }
+                    c4 += 32 - VPR;
+                    if (c4 >= VPR) c4 -= VPR;
+                }
+            }
+        }
+    }
+    float f0, f1, f2, f3;
+    unpack2(a0, f0, f1);
+    unpack2(a1, f2, f3);
+    float a = (f0 + f1) + (f2 + f3);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) atomicAdd(out, a);
+}
+
+template <bool kNewton, int U, int MINB>
+static void run_packed(const char* name, const float4* d, long long n_sub, float* d_out, int ctas_per_sm, double bytes) {
+    int dev, sms;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_kernel_packed<kNewton, U, MINB>, 256, 0));
+    const int per = ctas_per_sm < occ ? ctas_per_sm : occ;
+    const int grid = sms * per;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) stream_kernel_packed<kNewton, U, MINB><<<grid, 256>>>(d, n_sub, d_out);
+    CK(cudaDeviceSynchronize());
+    const int reps = 10;
+    CK(cudaMemset(d_out, 0, 4));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) stream_kernel_packed<kNewton, U, MINB><<<grid, 256>>>(d, n_sub, d_out);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    float h;
+    CK(cudaMemcpy(&h, d_out, 4, cudaMemcpyDeviceToHost));
+    printf("%-28s U=%d minb=%d ctas/sm=%d (occ %d)  %8.3f ms  %8.1f GB/s   sum/rep=%.6e  [packed f32x2]\n", name, U, MINB, per, occ, ms / reps,
+           bytes / (ms / reps * 1e-3) / 1e9, h / reps);
+}
+
 template <int V, int U, int MINB>
 static void run(const char* name, const float4* d, long long n_sub, float* d_out, int ctas_per_sm, double bytes) {
     int dev, sms;
@@ -252,14 +369,12 @@ int main(int argc, char** argv) {
     printf("buffer %.2f GB, %lld warp sub-tiles\n", bytes / 1e9, n_sub);
     run<0, 7, 1>("read+add", d, n_sub, d_out, 8, bytes);
     run<4, 7, 4>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
-    run<4, 7, 5>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<4, 3, 4>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<4, 3, 5>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<4, 3, 6>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<4, 7, 3>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<4, 7, 4>("2.5 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<2, 3, 5>("2 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<2, 7, 4>("2 MUFU", d, n_sub, d_out, 8, bytes);
-    run_pf<1, 3, 5>("3 MUFU", d, n_sub, d_out, 8, bytes);
+    run<1, 7, 4>("3 MUFU", d, n_sub, d_out, 8, bytes);
+    run_packed<false, 7, 4>("3 MUFU", d, n_sub, d_out, 8, bytes);
+    run_packed<false, 7, 5>("3 MUFU", d, n_sub, d_out, 8, bytes);
+    run_packed<true, 7, 4>("2 MUFU", d, n_sub, d_out, 8, bytes);
+    run_packed<true, 7, 5>("2 MUFU", d, n_sub, d_out, 8, bytes);
+    run_packed<true, 3, 6>("2 MUFU", d, n_sub, d_out, 8, bytes);
+    run_packed<false, 3, 6>("3 MUFU", d, n_sub, d_out, 8, bytes);
     return 0;
 }
