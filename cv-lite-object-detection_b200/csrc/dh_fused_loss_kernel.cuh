@@ -379,43 +379,65 @@ __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typenam
 }
 
 // ---- stream: every element of this warp's tiles as if its label were zero -----------------------------------------
+// The chunk's rows (its tiles laid end to end) are split into eight equal contiguous spans, one per warp: a warp
+// streams a few long contiguous runs (one per tile it touches) instead of one 32-row slice of every tile, which
+// amortises the per-run setup and balances ragged tiles.  `run(ptr, grad_ptr, nrows)` is called per run.
+template <class P, class Run>
+__device__ __forceinline__ void for_warp_span(const LossArgs<P>& a, int img, int t_begin, int t_end, bool want_grad, Run run) {
+    const int warp = threadIdx.x >> 5;
+    const int ch = a.tt.ch;
+    TileCursor cur;
+    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
+    int total = 0;
+    {
+        TileCursor c = cur;
+        for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, c)) {
+            TileInfo ti;
+            cursor_info(a.tt, c, ti);
+            total += ti.nrows;
+        }
+    }
+    const int lo = static_cast<int>(static_cast<long long>(total) * warp / (DH_THREADS / 32));
+    const int hi = static_cast<int>(static_cast<long long>(total) * (warp + 1) / (DH_THREADS / 32));
+    int off = 0;
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end && off < hi; ++tile, cursor_next(a.tt, cur)) {
+        TileInfo ti;
+        cursor_info(a.tt, cur, ti);
+        const int b0 = max(lo, off), b1 = min(hi, off + ti.nrows);
+        if (b1 > b0) {
+            const MapDesc& md = a.tt.maps[ti.m];
+            const long long e = static_cast<long long>(img) * md.image_stride + static_cast<long long>(ti.r0 + (b0 - off)) * ch;
+            run(md.pred + e, (want_grad && a.grad_maps[ti.m]) ? a.grad_maps[ti.m] + e : nullptr, b1 - b0);
+        }
+        off += ti.nrows;
+    }
+}
+
 template <class P, int kCls, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img, int t_begin, int t_end) {
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int vpr = a.tt.ch >> 2;
     const int step = 32 % vpr, c_lane = lane % vpr;
     const float gamma = a.spec.gamma, gscale = (kCls == 2 ? 1.0f : 1.0f - a.spec.alpha) * a.spec.w_cls;
-    TileCursor cur;
-    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
-#pragma unroll 1
-    for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
-        TileInfo ti;
-        float* gg = nullptr;
-        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
-        if (ti.nrows > 0) stream_vec<kCls, kGrad, kGrad ? 5 : 7>(gp, gg, ti.nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
-    }
+    for_warp_span(a, img, t_begin, t_end, kGrad, [&](const float* gp, float* gg, int nrows) {
+        stream_vec<kCls, kGrad, kGrad ? 5 : 7>(gp, gg, nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
+    });
     return sa;
 }
 template <class P, int kCls, bool kGrad>
 __device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int img, int t_begin, int t_end) {
     StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int ch = a.tt.ch;
     const int step = 32 % ch, c_lane = lane % ch;
     const LossSpec sp = a.spec;
-    TileCursor cur;
-    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
-#pragma unroll 1
-    for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
-        TileInfo ti;
-        float* gg = nullptr;
-        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, kGrad ? &gg : nullptr);
-        if (ti.nrows > 0) stream_scalar<kCls, kGrad, 4>(gp, gg, ti.nrows, ch, c_lane, step, lane, sp, sa);
-    }
+    for_warp_span(a, img, t_begin, t_end, kGrad, [&](const float* gp, float* gg, int nrows) {
+        stream_scalar<kCls, kGrad, 4>(gp, gg, nrows, ch, c_lane, step, lane, sp, sa);
+    });
     return sa;
 }
-
 template <class P, int kCls, bool kGrad>
 __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_constant__ LossArgs<P> ga) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -464,7 +486,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
 
         const StreamAcc sa = vec ? stream_pass_vec<P, kCls, kGrad>(a, img, t_begin, t_end)
                                  : stream_pass_scalar<P, kCls, kGrad>(a, img, t_begin, t_end);
-        if (kGrad) __syncwarp();  // this warp's zero-label gradients are written before the matched rows overwrite theirs
+        if (kGrad) __syncthreads();  // every zero-label gradient of the chunk is written before a matched row overwrites its own
         LossAcc acc = {0.f, 0.f, 0.f, 0};  // corrections + regression, natural units
         if (n_boxes > 0) acc = correct_pass<P>(a, recs, n_boxes, cand, img, t_begin, t_end);
 
