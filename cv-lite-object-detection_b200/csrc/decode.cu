@@ -11,6 +11,9 @@
 //
 // These kernels are HBM-bound on one read of the head output; thread mapping is one thread per output
 // row with the class loop vectorised where the row is 16-byte aligned.
+#include <cooperative_groups.h>
+
+#include <algorithm>
 #include <cstring>
 
 #include "dh_common.cuh"
@@ -324,9 +327,10 @@ struct SelShared {
 };
 
 // largest bin b with sum(hist[b..nbins)) >= need; returns the bin and the count strictly above it (block-wide)
+template <int T = kSelThreads>
 __device__ __forceinline__ void find_boundary(SelShared& sh, int nbins, unsigned need, int tid) {
     // thread t owns bins [t*per, t*per+per) counted from the top
-    const int per = (nbins + kSelThreads - 1) / kSelThreads;
+    const int per = (nbins + T - 1) / T;
     unsigned mine = 0;
     for (int q = 0; q < per; ++q) {
         const int b = nbins - 1 - (tid * per + q);
@@ -367,7 +371,7 @@ __device__ __forceinline__ void find_boundary(SelShared& sh, int nbins, unsigned
 //   void emit(int i, float s, int rank) write output slot `rank` from element i
 //   void pad(int rank)                  mark output slot `rank` unused
 // Selected elements are emitted in index order; exactly min(k, #passing) slots are filled.
-template <class Src>
+template <class Src, int T = kSelThreads>
 __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k_slots, float min_score, int inclusive) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = src.n;
@@ -376,15 +380,15 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
     constexpr int U = 8;  // independent loads in flight per thread in the unordered passes
 
     // ---- 1. linear histogram -------------------------------------------------------------------------------
-    for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
+    for (int i = tid; i < 4096; i += T) sh.hist[i] = 0;
     if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0, sh.n_pass = 0;
     __syncthreads();
     unsigned my_pass = 0;
-    for (int base = 0; base < n; base += kSelThreads * U) {
+    for (int base = 0; base < n; base += T * U) {
         float s[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = base + u * kSelThreads + tid;
+            const int i = base + u * T + tid;
             s[u] = i < n ? src.score(i) : __int_as_float(0x7fc00000);  // NaN never passes
         }
 #pragma unroll
@@ -396,7 +400,7 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
     __syncthreads();
     unsigned T_key = 0u;  // default: fewer than k rows pass -> take everything that passes
     int T_idx = 0x7fffffff;
-    if (k > 0) find_boundary(sh, 4096, static_cast<unsigned>(k), tid);
+    if (k > 0) find_boundary<T>(sh, 4096, static_cast<unsigned>(k), tid);
     if (k > 0 && sh.bin != 0xFFFFFFFFu) {
         const int Bk = static_cast<int>(sh.bin);
         unsigned need = static_cast<unsigned>(k) - sh.above;  // still to take inside the boundary bin (>= 1)
@@ -408,17 +412,17 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
             const int shift = round == 0 ? 20 : (round == 1 ? 8 : 0);
             const int bits = round == 2 ? 8 : 12;
             __syncthreads();
-            for (int i = tid; i < (1 << bits); i += kSelThreads) sh.hist[i] = 0;
+            for (int i = tid; i < (1 << bits); i += T) sh.hist[i] = 0;
             if (tid == 0) sh.bin = 0xFFFFFFFFu;
             __syncthreads();
-            for (int i = tid; i < n; i += kSelThreads) {
+            for (int i = tid; i < n; i += T) {
                 const float s = src.score(i);
                 if (!passes(s) || linear_bin(s) != Bk) continue;
                 const unsigned key = score_key(s);
                 if ((key & decided) == prefix) atomicAdd(&sh.hist[(key >> shift) & ((1u << bits) - 1u)], 1u);
             }
             __syncthreads();
-            find_boundary(sh, 1 << bits, need, tid);
+            find_boundary<T>(sh, 1 << bits, need, tid);
             prefix |= sh.bin << shift;
             decided |= ((1u << bits) - 1u) << shift;
             need -= sh.above;
@@ -429,7 +433,7 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
             // ---- 2b. (rarer) more identical scores than the list holds: the cut is the need-th of them in index order
             T_key = prefix;
             unsigned carry = 0;
-            for (int base = 0; base < n; base += kSelThreads) {
+            for (int base = 0; base < n; base += T) {
                 const int i = base + tid;
                 bool eq = false;
                 if (i < n) {
@@ -440,7 +444,7 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
                 if (lane == 0) sh.wtot[0][warp] = __popc(bal);
                 __syncthreads();
                 unsigned before = carry, tot = 0;
-                for (int w = 0; w < kSelThreads / 32; ++w) {
+                for (int w = 0; w < T / 32; ++w) {
                     const unsigned v = sh.wtot[0][w];
                     if (w < warp) before += v;
                     tot += v;
@@ -454,11 +458,11 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
         } else {
             // ---- 2. collect the boundary entries, rank them exactly ------------------------------------------------
             __syncthreads();
-            for (int base = 0; base < n; base += kSelThreads * U) {
+            for (int base = 0; base < n; base += T * U) {
                 float s[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int i = base + u * kSelThreads + tid;
+                    const int i = base + u * T + tid;
                     s[u] = i < n ? src.score(i) : __int_as_float(0x7fc00000);
                 }
 #pragma unroll
@@ -467,12 +471,12 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
                     const unsigned key = score_key(s[u]);
                     if ((key & decided) != prefix) continue;
                     const unsigned slot = atomicAdd(&sh.n_list, 1u);
-                    sh.list_key[slot] = key, sh.list_idx[slot] = base + u * kSelThreads + tid;
+                    sh.list_key[slot] = key, sh.list_idx[slot] = base + u * T + tid;
                 }
             }
             __syncthreads();
             const int n_list = static_cast<int>(sh.n_list);
-            for (int e = tid; e < n_list; e += kSelThreads) {
+            for (int e = tid; e < n_list; e += T) {
                 const unsigned ke = sh.list_key[e];
                 const int ie = sh.list_idx[e];
                 unsigned rank = 0;
@@ -491,7 +495,7 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
     // ---- 3. ordered compaction ---------------------------------------------------------------------------------
     unsigned carry = 0;
     int it = 0;
-    for (int base = 0; base < n; base += kSelThreads * kSelItems, ++it) {
+    for (int base = 0; base < n; base += T * kSelItems, ++it) {
         const int i0 = base + tid * kSelItems;
         float s[kSelItems];
 #pragma unroll
@@ -515,7 +519,7 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
         if (lane == 31) wt[warp] = incl;
         __syncthreads();
         unsigned before = carry, tot = 0;
-        for (int w = 0; w < kSelThreads / 32; ++w) {
+        for (int w = 0; w < T / 32; ++w) {
             const unsigned v = wt[w];
             if (w < warp) before += v;
             tot += v;
@@ -531,7 +535,7 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
     }
     // pad the unused slots so that any threshold drops them
     const unsigned filled = min(static_cast<unsigned>(k), carry);
-    for (int r = filled + tid; r < k_slots; r += kSelThreads) src.pad(r);
+    for (int r = filled + tid; r < k_slots; r += T) src.pad(r);
 }
 
 // generic source: rows of `row_floats` floats, the score in column `score_col`; selected rows are copied whole
@@ -631,99 +635,286 @@ struct FcosSource {
 // logits collide after the float32 sigmoid: (1) the score threshold -- logits within 1e-3 of logit(thr) are decided
 // with the real sigmoid; (2) ties at the k-th score must be cut by index -- the entries ranked exactly in shared
 // memory are those of the boundary bin AND of enough neighbouring bins that no score tie can reach outside them
-// (sigmoid_collision_floor bounds how far below a logit a colliding logit can lie).  Returns false (nothing
-// written) when the shortcut does not apply; the caller then runs the generic exact selector.
+// (sigmoid_collision_floor bounds how far below a logit a colliding logit can lie).
 // kVec: the head rows of one (image, level) are walked as float4 items in memory order (4 logits per load; the five
 // regression / centerness channels of each row come along and are skipped); otherwise one (location, class) pair per
 // load.  Memory order IS (location, class) order, so the ordered compaction emits the same sequence either way.
+constexpr float kLogitBinScale = 4096.0f / 24.0f;  // bins of 0.0059 logit units from the threshold upwards
+
+__device__ __forceinline__ bool logit_space_applies(const FcosSource& src, float min_score, int k) {
+    return !src.center && min_score > 1.0e-6f && min_score < 0.999f && k > 0;
+}
+
+// The (image, level) segment seen as load items, with the logit-space threshold test and bin map.
+__device__ __noinline__ bool logit_passes_exact(float x, float min_score, int inclusive) {
+    const float sc = sigmoid_acc(x);
+    return inclusive ? (sc >= min_score) : (sc > min_score);
+}
 template <bool kVec>
-__device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const FcosSource& src, int k_slots, float min_score, int inclusive) {
-    constexpr int W = kVec ? 4 : 1;  // logits per load item
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = src.n;
-    const int k = min(k_slots, max(n, 0));
-    if (src.center || !(min_score > 1.0e-6f && min_score < 0.999f) || k <= 0) return false;
-    const int rows = n / src.num_classes;
-    const int n_items = kVec ? (rows * src.ch) >> 2 : n;
-    const FastDiv div_ch = make_fastdiv(static_cast<uint32_t>(src.ch));
-    // item -> W logits (-inf where the slot is not a class channel / out of range).  The pair index of slot e is only
-    // needed for the few entries near the cut, so it is derived on demand from the item's (row, first channel): most
-    // float4 items lie entirely inside the class channels and need no per-slot channel test at all.
-    struct ItemPos {
-        int r, c;  // row and channel of slot 0 (vector items); unused for scalar items
+struct LogitItems {
+    static constexpr int W = kVec ? 4 : 1;  // logits per load item
+    struct Item {
+        float x[W];  // the item's values as loaded (-inf for an item outside the range)
+        int r, c5;   // row and (channel - 5) of slot 0 (vector items); unused for scalar items
     };
-    auto load = [&](int item, float* x, ItemPos& pos) {
+    const FcosSource* src;
+    int n_items, inclusive;
+    FastDiv div_ch;
+    float min_score, thr_lo, thr_hi, thr_pass;  // x >= thr_pass: passes for sure; x < thr_lo: fails for sure
+
+    __device__ __forceinline__ void init(const FcosSource& s, float min_score_, int inclusive_) {
+        src = &s, min_score = min_score_, inclusive = inclusive_;
+        const int rows = s.n / s.num_classes;
+        n_items = kVec ? (rows * s.ch) >> 2 : s.n;
+        div_ch = make_fastdiv(static_cast<uint32_t>(s.ch));
+        const float x_thr = logf(min_score_ / (1.0f - min_score_));
+        thr_lo = x_thr - 1.0e-3f, thr_hi = x_thr + 1.0e-3f;
+        thr_pass = nextafterf(thr_hi, INFINITY);
+    }
+    // nothing but the load: the loads of a batch of items issue back to back
+    __device__ __forceinline__ void fetch(int item, bool valid, Item& it) const {
         if (!kVec) {
-            x[0] = item < n_items ? src.logit(item) : -INFINITY;
+            it.x[0] = valid ? src->logit(item) : -INFINITY;
             return;
         }
         float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (item < n_items) v = __ldg(reinterpret_cast<const float4*>(src.head) + item);
+        if (valid) v = __ldg(reinterpret_cast<const float4*>(src->head) + item);
+        it.x[0] = v.x, it.x[kVec ? 1 : 0] = v.y, it.x[kVec ? 2 : 0] = v.z, it.x[kVec ? 3 : 0] = v.w;
+    }
+    __device__ __forceinline__ void locate(int item, Item& it) const {
+        if (!kVec) return;
         const int p0 = item << 2;
-        pos.r = static_cast<int>(fdiv_u32(static_cast<uint32_t>(p0), div_ch));
-        pos.c = p0 - pos.r * src.ch;
-        x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
-        if (pos.c < 5 || pos.c > src.ch - 4) {  // the item touches the 5 regression / centerness channels of a row
-            int c = pos.c;
+        it.r = static_cast<int>(fdiv_u32(static_cast<uint32_t>(p0), div_ch));
+        it.c5 = p0 - it.r * src->ch - 5;
+    }
+    // slot e of the item is a class logit: not one of the five regression / centerness channels of this row or, where
+    // the item runs over the end of its row, of the next one
+    __device__ __forceinline__ bool is_class(const Item& it, int e) const {
+        return !kVec || static_cast<unsigned>(it.c5 + e) < static_cast<unsigned>(src->num_classes);
+    }
+    // the threshold test of a class logit (the float32 sigmoid decides within 1e-3 of the threshold logit)
+    __device__ __forceinline__ bool passes(float x) const { return x >= thr_lo && (x >= thr_pass || logit_passes_exact(x, min_score, inclusive)); }
+    // (location, class) pair index of a class-logit slot; only needed for the few entries near the cut
+    __device__ __forceinline__ int pair_index(int item, const Item& it, int e) const {
+        return kVec ? it.r * src->num_classes + it.c5 + e : item;
+    }
+    // the load item that holds (location, class) pair p
+    __device__ __forceinline__ int item_of_pair(int p) const {
+        if (!kVec) return p;
+        const int r = static_cast<int>(fdiv_u32(static_cast<uint32_t>(p), src->div_c));
+        return (r * src->ch + 5 + (p - r * src->num_classes)) >> 2;
+    }
+    __device__ __forceinline__ int bin_x(float x) const {  // monotone; x >= thr_lo for every entry that passes
+        return min(max(__float2int_rz((x - thr_lo) * kLogitBinScale), 0), 4095);
+    }
+    // Logit bounds for the passes that follow the histogram: a class logit >= take_from passes the threshold and lies in
+    // a bin above hi_bin; one < look_from fails the threshold or lies in a bin below lo_bin (0.01 bins of slack cover
+    // the rounding of bin_x); the few in between are decided exactly.
+    __device__ __forceinline__ float take_from(bool take_all, int hi_bin) const {
+        return take_all ? thr_pass : fmaxf(thr_pass, thr_lo + (static_cast<float>(hi_bin) + 1.01f) / kLogitBinScale);
+    }
+    __device__ __forceinline__ float look_from(bool take_all, int lo_bin) const {
+        return take_all ? thr_lo : fmaxf(thr_lo, thr_lo + (static_cast<float>(lo_bin) - 0.01f) / kLogitBinScale);
+    }
+};
+
+// One batch of N load items: fetch them all, then every class-logit slot with x >= x_hot gets hot(u, e, x) -- the
+// cheap, branch-free common case -- and the slots with x_lo <= x < x_hot are remembered in a bit mask and handed to
+// slow(u, e, x) afterwards (rare: one branch per batch).  The passes are instruction-issue-bound before they are
+// memory-bound, so the per-slot code is a handful of instructions.
+template <bool kVec, int N, class Idx, class Hot, class Slow>
+__device__ __forceinline__ void logit_scan(const LogitItems<kVec>& it, typename LogitItems<kVec>::Item (&q)[N], int i_hi, float x_hot,
+                                           float x_lo, const Idx& idx, const Hot& hot, const Slow& slow) {
+    constexpr int W = LogitItems<kVec>::W;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (c < 5) x[e] = -INFINITY;
-                if (++c == src.ch) c = 0;
-            }
+    for (int u = 0; u < N; ++u) it.fetch(idx(u), idx(u) < i_hi, q[u]);
+    unsigned maybe = 0;
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        it.locate(idx(u), q[u]);
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+            const float x = q[u].x[e];
+            const bool cls = it.is_class(q[u], e);
+            const bool h = cls && x >= x_hot;
+            if (h) hot(u, e, x);
+            if (cls && x >= x_lo && !h) maybe |= 1u << (u * W + e);
         }
-    };
-    auto pair_index = [&](int item, const ItemPos& pos, int e) {
-        if (!kVec) return item;
-        int r = pos.r, c = pos.c + e;
-        if (c >= src.ch) c -= src.ch, ++r;
-        return r * src.num_classes + (c - 5);
-    };
-    const float x_thr = logf(min_score / (1.0f - min_score));
-    const float thr_lo = x_thr - 1.0e-3f, thr_hi = x_thr + 1.0e-3f;
-    constexpr float kScale = 4096.0f / 24.0f;  // bins of 0.0059 logit units from the threshold upwards
-    auto score_passes = [&](float sc) { return inclusive ? (sc >= min_score) : (sc > min_score); };
-    auto passes_x = [&](float x) { return x > thr_hi ? true : (x >= thr_lo ? score_passes(sigmoid_acc(x)) : false); };
-    auto bin_x = [&](float x) {
-        const float t = (x - thr_lo) * kScale;
-        return t <= 0.f ? 0 : (t >= 4095.f ? 4095 : static_cast<int>(t));
-    };
+    }
+    if (maybe) {
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+#pragma unroll
+            for (int e = 0; e < W; ++e)
+                if ((maybe >> (u * W + e)) & 1u) slow(u, e, q[u].x[e]);
+    }
+}
+
+// One thread, after find_boundary put the k-th best into bin Bk with `above` entries in the bins over it: the bins
+// [lo, hi] whose entries can tie with the k-th score after the sigmoid, and how many of them are to be taken.
+// False when the window cannot be bounded or holds more entries than the shared-memory list.
+__device__ inline bool logit_tie_window(const unsigned* hist, int Bk, float thr_lo, unsigned k, unsigned above, int& lo, int& hi, unsigned& need) {
+    const float lo_edge = thr_lo + static_cast<float>(Bk) / kLogitBinScale, hi_edge = thr_lo + static_cast<float>(Bk + 1) / kLogitBinScale;
+    const int below = static_cast<int>(ceilf((lo_edge - sigmoid_collision_floor(lo_edge)) * kLogitBinScale)) + 1;
+    int beyond = -1;
+    for (int t = 1; t <= 8 && beyond < 0; ++t)
+        if (sigmoid_collision_floor(hi_edge + static_cast<float>(t) / kLogitBinScale) > hi_edge) beyond = t + 1;
+    lo = max(Bk - below, 0), hi = Bk + beyond;
+    if (!(beyond > 0 && hi < 4095)) return false;
+    unsigned inside = 0, between = 0;
+    for (int q = lo; q <= hi; ++q) inside += hist[q];
+    for (int q = Bk + 1; q <= hi; ++q) between += hist[q];
+    need = k - (above - between);
+    return inside <= kSelListCap;
+}
+
+// Rank the collected window entries exactly by (score desc, index asc); the entry of rank need-1 is the cut.
+// `on_taken(index)` is called for every entry at or before the cut.
+template <int T, class OnTaken>
+__device__ __forceinline__ void rank_window(SelShared& sh, unsigned need, int tid, const OnTaken& on_taken) {
+    const int n_list = static_cast<int>(sh.n_list);
+    for (int e = tid; e < n_list; e += T) {
+        const unsigned ke = sh.list_key[e];
+        const int ie = sh.list_idx[e];
+        unsigned rank = 0;
+        for (int f = 0; f < n_list; ++f) {
+            const unsigned kf = sh.list_key[f];
+            rank += (kf > ke || (kf == ke && sh.list_idx[f] < ie)) ? 1u : 0u;
+        }
+        if (rank == need - 1) sh.t_key = ke, sh.t_idx = ie;
+        if (rank < need) on_taken(ie);
+    }
+}
+
+// ---- the three passes over the load items [i_lo, i_hi) of a segment ----------------------------------------------------
+// 1. histogram of the passing logits; returns this thread's number of passing entries
+template <bool kVec, int T>
+__device__ __forceinline__ unsigned logit_histogram(unsigned* hist, const LogitItems<kVec>& it, int i_lo, int i_hi) {
     constexpr int U = kVec ? 4 : 8;  // independent loads in flight per thread in the unordered passes
+    const int tid = threadIdx.x;
+    unsigned n_pass = 0;
+    for (int base = i_lo; base < i_hi; base += T * U) {
+        typename LogitItems<kVec>::Item q[U];
+        logit_scan<kVec, U>(
+            it, q, i_hi, it.thr_pass, it.thr_lo, [&](int u) { return base + u * T + tid; },
+            [&](int, int, float x) { atomicAdd(&hist[it.bin_x(x)], 1u), ++n_pass; },
+            [&](int, int, float x) {
+                if (it.passes(x)) atomicAdd(&hist[it.bin_x(x)], 1u), ++n_pass;
+            });
+    }
+    return n_pass;
+}
+// 2. the entries of the tie window [lo_bin, hi_bin] are appended (exact score key, pair index) to a list, which may
+//    live in another CTA of the cluster; returns this thread's number of entries above the window
+template <bool kVec, int T>
+__device__ __forceinline__ unsigned logit_collect(const LogitItems<kVec>& it, int i_lo, int i_hi, int lo_bin, int hi_bin, unsigned* n_list,
+                                                  unsigned* list_key, int* list_idx) {
+    constexpr int U = kVec ? 4 : 8;
+    const int tid = threadIdx.x;
+    const float x_take = it.take_from(false, hi_bin), x_look = it.look_from(false, lo_bin);
+    unsigned n_above = 0;
+    for (int base = i_lo; base < i_hi; base += T * U) {
+        typename LogitItems<kVec>::Item q[U];
+        logit_scan<kVec, U>(
+            it, q, i_hi, x_take, x_look, [&](int u) { return base + u * T + tid; }, [&](int, int, float) { ++n_above; },
+            [&](int u, int e, float x) {
+                if (!it.passes(x)) return;
+                const int bn = it.bin_x(x);
+                if (bn > hi_bin) ++n_above;
+                if (bn < lo_bin || bn > hi_bin) return;
+                const unsigned slot = atomicAdd(n_list, 1u);
+                list_key[slot] = score_key(sigmoid_acc(x));
+                list_idx[slot] = it.pair_index(base + u * T + tid, q[u], e);
+            });
+    }
+    return n_above;
+}
+// 3. ordered compaction: each thread owns kItems consecutive logits per chunk, the taken ones are emitted to slots
+//    first_rank, first_rank + 1, ... in item order.  Returns the number taken.
+template <bool kVec, int T, int kItems>
+__device__ __forceinline__ unsigned logit_compact(SelShared& sh, const LogitItems<kVec>& it, int i_lo, int i_hi, bool take_all, int lo_bin,
+                                                  int hi_bin, unsigned T_key, int T_idx, unsigned first_rank, int k) {
+    constexpr int W = LogitItems<kVec>::W;
+    constexpr int IPT = kItems / W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float x_take = it.take_from(take_all, hi_bin), x_look = it.look_from(take_all, lo_bin);
+    unsigned carry = first_rank;
+    int chunk = 0;
+    for (int base = i_lo; base < i_hi; base += T * IPT, ++chunk) {
+        typename LogitItems<kVec>::Item q[IPT];
+        unsigned flags = 0;
+        logit_scan<kVec, IPT>(
+            it, q, i_hi, x_take, x_look, [&](int u) { return base + tid * IPT + u; }, [&](int u, int e, float) { flags |= 1u << (u * W + e); },
+            [&](int u, int e, float x) {
+                if (!it.passes(x)) return;
+                bool take = take_all;
+                if (!take) {
+                    const int bn = it.bin_x(x);
+                    if (bn > hi_bin) take = true;
+                    else if (bn >= lo_bin) {
+                        const unsigned key = score_key(sigmoid_acc(x));
+                        take = key > T_key || (key == T_key && it.pair_index(base + tid * IPT + u, q[u], e) <= T_idx);
+                    }
+                }
+                if (take) flags |= 1u << (u * W + e);
+            });
+        const unsigned mine = __popc(flags);
+        unsigned incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        unsigned* wt = sh.wtot[chunk & 1];  // parity double buffer: one barrier per chunk
+        if (lane == 31) wt[warp] = incl;
+        __syncthreads();
+        unsigned before = carry, tot = 0;
+        for (int w = 0; w < T / 32; ++w) {
+            const unsigned v = wt[w];
+            if (w < warp) before += v;
+            tot += v;
+        }
+        unsigned rank = before + incl - mine;
+        if (flags) {  // emit the taken slots in order
+#pragma unroll
+            for (int u = 0; u < IPT; ++u)
+#pragma unroll
+                for (int e = 0; e < W; ++e) {
+                    if (!((flags >> (u * W + e)) & 1u)) continue;
+                    if (rank < static_cast<unsigned>(k))
+                        it.src->emit(it.pair_index(base + tid * IPT + u, q[u], e), sigmoid_acc(q[u].x[e]), static_cast<int>(rank));
+                    ++rank;
+                }
+        }
+        carry += tot;
+    }
+    return carry - first_rank;
+}
+
+// One CTA does the whole segment.  Returns false (nothing written) when the shortcut does not apply; the caller then
+// runs the generic exact selector.
+template <bool kVec>
+__device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const FcosSource& src, int k_slots, float min_score, int inclusive) {
+    const int tid = threadIdx.x;
+    const int k = min(k_slots, max(src.n, 0));
+    if (!logit_space_applies(src, min_score, k)) return false;
+    LogitItems<kVec> it;
+    it.init(src, min_score, inclusive);
     for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
     if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0, sh.n_pass = 0, sh.t_key = 0u, sh.t_idx = 0x7fffffff;
     __syncthreads();
-    for (int base = 0; base < n_items; base += kSelThreads * U) {
-        float x[U][W];
-        ItemPos pos[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], pos[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int e = 0; e < W; ++e)
-                if (passes_x(x[u][e])) atomicAdd(&sh.hist[bin_x(x[u][e])], 1u);
-    }
+    logit_histogram<kVec, kSelThreads>(sh.hist, it, 0, it.n_items);
     __syncthreads();
     find_boundary(sh, 4096, static_cast<unsigned>(k), tid);
     const bool take_all = sh.bin == 0xFFFFFFFFu;  // fewer than k pass
     int lo_bin = 0, hi_bin = 4095;
     if (!take_all) {
         if (tid == 0) {
-            const int Bk = static_cast<int>(sh.bin);
-            const float lo_edge = thr_lo + static_cast<float>(Bk) / kScale, hi_edge = thr_lo + static_cast<float>(Bk + 1) / kScale;
-            const int below = static_cast<int>(ceilf((lo_edge - sigmoid_collision_floor(lo_edge)) * kScale)) + 1;
-            int beyond = -1;
-            for (int t = 1; t <= 8 && beyond < 0; ++t)
-                if (sigmoid_collision_floor(hi_edge + static_cast<float>(t) / kScale) > hi_edge) beyond = t + 1;
-            const int lo = max(Bk - below, 0), hi = Bk + beyond;
-            bool ok = beyond > 0 && hi < 4095;
-            unsigned inside = 0, between = 0;
-            if (ok) {
-                for (int q = lo; q <= hi; ++q) inside += sh.hist[q];
-                for (int q = Bk + 1; q <= hi; ++q) between += sh.hist[q];
-                ok = inside <= kSelListCap;
-            }
+            int lo, hi;
+            unsigned need = 0;
+            const bool ok = logit_tie_window(sh.hist, static_cast<int>(sh.bin), it.thr_lo, static_cast<unsigned>(k), sh.above, lo, hi, need);
             sh.wtot[1][0] = ok ? 1u : 0u, sh.wtot[1][1] = static_cast<unsigned>(lo), sh.wtot[1][2] = static_cast<unsigned>(hi);
-            sh.need = static_cast<unsigned>(k) - (sh.above - between);
+            sh.need = need;
         }
         __syncthreads();
         if (!sh.wtot[1][0]) {
@@ -732,96 +923,13 @@ __device__ __forceinline__ bool fcos_select_logit_space(SelShared& sh, const Fco
         }
         lo_bin = static_cast<int>(sh.wtot[1][1]), hi_bin = static_cast<int>(sh.wtot[1][2]);
         const unsigned need = sh.need;
-        // collect the entries that can tie with the k-th score, with their exact scores
-        for (int base = 0; base < n_items; base += kSelThreads * U) {
-            float x[U][W];
-            ItemPos pos[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) load(base + u * kSelThreads + tid, x[u], pos[u]);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int e = 0; e < W; ++e) {
-                    if (!passes_x(x[u][e])) continue;
-                    const int bn = bin_x(x[u][e]);
-                    if (bn < lo_bin || bn > hi_bin) continue;
-                    const unsigned slot = atomicAdd(&sh.n_list, 1u);
-                    sh.list_key[slot] = score_key(sigmoid_acc(x[u][e]));
-                    sh.list_idx[slot] = pair_index(base + u * kSelThreads + tid, pos[u], e);
-                }
-        }
+        logit_collect<kVec, kSelThreads>(it, 0, it.n_items, lo_bin, hi_bin, &sh.n_list, sh.list_key, sh.list_idx);
         __syncthreads();
-        const int n_list = static_cast<int>(sh.n_list);
-        for (int e = tid; e < n_list; e += kSelThreads) {
-            const unsigned ke = sh.list_key[e];
-            const int ie = sh.list_idx[e];
-            unsigned rank = 0;
-            for (int f = 0; f < n_list; ++f) {
-                const unsigned kf = sh.list_key[f];
-                rank += (kf > ke || (kf == ke && sh.list_idx[f] < ie)) ? 1u : 0u;
-            }
-            if (rank == need - 1) sh.t_key = ke, sh.t_idx = ie;
-        }
+        rank_window<kSelThreads>(sh, need, tid, [](int) {});
         __syncthreads();
     }
-    const unsigned T_key = sh.t_key;
-    const int T_idx = sh.t_idx;
-    // ordered compaction: each thread owns kSelItems consecutive logits (= kSelItems / W consecutive load items)
-    constexpr int IPT = kSelItems / W;
-    unsigned carry = 0;
-    int it = 0;
-    for (int base = 0; base < n_items; base += kSelThreads * IPT, ++it) {
-        float x[IPT][W];
-        ItemPos pos[IPT];
-#pragma unroll
-        for (int u = 0; u < IPT; ++u) load(base + tid * IPT + u, x[u], pos[u]);
-        unsigned flags = 0;
-#pragma unroll
-        for (int u = 0; u < IPT; ++u)
-#pragma unroll
-            for (int e = 0; e < W; ++e) {
-                const float xv = x[u][e];
-                if (!passes_x(xv)) continue;
-                bool take = take_all;
-                if (!take) {
-                    const int bn = bin_x(xv);
-                    if (bn > hi_bin) take = true;
-                    else if (bn >= lo_bin) {
-                        const unsigned key = score_key(sigmoid_acc(xv));
-                        take = key > T_key || (key == T_key && pair_index(base + tid * IPT + u, pos[u], e) <= T_idx);
-                    }
-                }
-                if (take) flags |= 1u << (u * W + e);
-            }
-        const unsigned mine = __popc(flags);
-        unsigned incl = mine;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += t;
-        }
-        unsigned* wt = sh.wtot[it & 1];
-        if (lane == 31) wt[warp] = incl;
-        __syncthreads();
-        unsigned before = carry, tot = 0;
-        for (int w = 0; w < kSelThreads / 32; ++w) {
-            const unsigned v = wt[w];
-            if (w < warp) before += v;
-            tot += v;
-        }
-        unsigned rank = before + incl - mine;
-#pragma unroll
-        for (int u = 0; u < IPT; ++u)
-#pragma unroll
-            for (int e = 0; e < W; ++e) {
-                if (!((flags >> (u * W + e)) & 1u)) continue;
-                if (rank < static_cast<unsigned>(k))
-                    src.emit(pair_index(base + tid * IPT + u, pos[u], e), sigmoid_acc(x[u][e]), static_cast<int>(rank));
-                ++rank;
-            }
-        carry += tot;
-    }
-    const unsigned filled = min(static_cast<unsigned>(k), carry);
+    const unsigned taken = logit_compact<kVec, kSelThreads, kSelItems>(sh, it, 0, it.n_items, take_all, lo_bin, hi_bin, sh.t_key, sh.t_idx, 0u, k);
+    const unsigned filled = min(static_cast<unsigned>(k), taken);
     for (int r = filled + tid; r < k_slots; r += kSelThreads) src.pad(r);
     return true;
 }
@@ -833,9 +941,7 @@ struct FcosSelectArgs {
     int num_classes, center, k_slots, n_levels, inclusive, allow_logit_space;
     float min_score;
 };
-__global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs a, float* __restrict__ cand /*[B, L*k, 6]*/) {
-    __shared__ SelShared sh;
-    const int b = blockIdx.x, l = blockIdx.y;  // level-major dispatch: the 64 x 512 K-logit level-0 CTAs start first, the rest fill in
+__device__ __forceinline__ FcosSource fcos_source(const FcosSelectArgs& a, int b, int l, float* cand) {
     FcosSource src;
     const int rows = a.hl[l] * a.wl[l];
     src.ch = a.num_classes + 5, src.num_classes = a.num_classes, src.wl = a.wl[l], src.center = a.center, src.stride = a.stride[l];
@@ -843,13 +949,170 @@ __global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs
     src.out = cand + (static_cast<long long>(b) * a.n_levels + l) * a.k_slots * 6;
     src.n = rows * a.num_classes;
     src.div_c = make_fastdiv(static_cast<uint32_t>(a.num_classes));
+    return src;
+}
+__device__ __forceinline__ bool fcos_source_vec(const FcosSource& src) {  // uniform over everything that works on the segment
+    return (reinterpret_cast<uintptr_t>(src.head) & 15u) == 0 && (((src.n / src.num_classes) * src.ch) & 3) == 0;
+}
+// `only_flagged` (optional, [B*L]): segments whose entry is 0 are skipped (they were done by the pre-select path).
+__global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs a, float* __restrict__ cand /*[B, L*k, 6]*/,
+                                                                  const int* __restrict__ only_flagged) {
+    __shared__ SelShared sh;
+    const int b = blockIdx.x, l = blockIdx.y;  // level-major dispatch: the 64 x 512 K-logit level-0 CTAs start first, the rest fill in
+    if (only_flagged && !only_flagged[b * a.n_levels + l]) return;
+    const FcosSource src = fcos_source(a, b, l, cand);
     if (a.allow_logit_space) {
-        const bool vec = (reinterpret_cast<uintptr_t>(src.head) & 15u) == 0 && ((rows * src.ch) & 3) == 0;  // block-uniform
-        if (vec ? fcos_select_logit_space<true>(sh, src, a.k_slots, a.min_score, a.inclusive)
-                : fcos_select_logit_space<false>(sh, src, a.k_slots, a.min_score, a.inclusive))
+        if (fcos_source_vec(src) ? fcos_select_logit_space<true>(sh, src, a.k_slots, a.min_score, a.inclusive)
+                                 : fcos_select_logit_space<false>(sh, src, a.k_slots, a.min_score, a.inclusive))
             return;
     }
     select_core(sh, src, a.k_slots, a.min_score, a.inclusive);
+}
+
+// ---- the same selection with a thread-block cluster per segment --------------------------------------------------------
+// One CTA per (image, level) leaves most of the GPU idle: 64 images give 64 long level-0 segments (2.2 MB each, read three
+// times) for 148 SMs.  Here a *group* of up to 8 CTAs of one cluster shares a segment: every CTA histograms, collects
+// and compacts its contiguous slice of the load items, and the group meets in the shared memory of its leader CTA
+// (distributed shared memory): the slice histograms are summed into the leader's, the leader finds the boundary bin and
+// the tie window, every CTA appends its window entries to the leader's list, the leader ranks them and counts how many
+// each slice keeps, and each CTA then knows the output slot its slice starts at.  A cluster holds one long segment or
+// several short ones of the same image (host-side plan); the six cluster barriers are executed by every CTA.
+constexpr int kSelCluster = 8;
+#ifndef DH_CLUSTER_SEL_THREADS
+#define DH_CLUSTER_SEL_THREADS 512
+#endif
+constexpr int kClThreads = DH_CLUSTER_SEL_THREADS;  // several CTAs per SM: one cluster's barriers and leader-only steps overlap another's streaming
+constexpr int kClItems = 16;                         // consecutive logits per thread and chunk in the compaction pass (4 loads in flight)
+struct FcosClusterPlan {
+    int n_types;                                     // clusters per image
+    signed char level[DH_MAX_LEVELS][kSelCluster];   // level worked on by rank r of cluster type t; -1: idle
+    unsigned char lead[DH_MAX_LEVELS][kSelCluster];  // rank of the group's leader CTA
+    unsigned char members[DH_MAX_LEVELS][kSelCluster];
+};
+struct ClusterCtl {
+    unsigned mode, lo_bin, hi_bin, need, local_cnt;
+    unsigned cnt_above[kSelCluster];   // per slice: entries above the tie window (or all passing entries when everything is taken)
+    unsigned cnt_window[kSelCluster];  // per slice: window entries at or before the cut
+};
+enum : unsigned { kModeTakeAll = 1u, kModeRanked = 2u, kModeFallback = 3u };
+
+template <bool kVec>
+__device__ __forceinline__ void fcos_select_cluster_group(SelShared& sh, ClusterCtl& ctl, const FcosSource& src, int k_slots, float min_score,
+                                                          int inclusive, bool active, int g, int G, int lead) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31;
+    SelShared* lsh = cluster.map_shared_rank(&sh, lead);
+    ClusterCtl* lctl = cluster.map_shared_rank(&ctl, lead);
+    const bool leader = active && g == 0;
+    const int k = active ? min(k_slots, max(src.n, 0)) : 0;
+    LogitItems<kVec> it;
+    int per = 1, i_lo = 0, i_hi = 0;
+    if (active) {
+        it.init(src, min_score, inclusive);
+        per = max((it.n_items + G - 1) / G, 1);
+        i_lo = min(g * per, it.n_items), i_hi = min(i_lo + per, it.n_items);
+    }
+    for (int i = tid; i < 4096; i += kClThreads) sh.hist[i] = 0;
+    if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0, sh.n_pass = 0, sh.t_key = 0u, sh.t_idx = 0x7fffffff;
+    if (tid == 0) ctl.mode = 0u, ctl.local_cnt = 0u;
+    if (tid < kSelCluster) ctl.cnt_above[tid] = 0u, ctl.cnt_window[tid] = 0u;
+    __syncthreads();
+    // ---- 1. slice histogram
+    unsigned my_pass = logit_histogram<kVec, kClThreads>(sh.hist, it, i_lo, i_hi);
+    my_pass = static_cast<unsigned>(warp_sum_i(static_cast<int>(my_pass)));
+    if (lane == 0 && my_pass) atomicAdd(&sh.n_pass, my_pass);
+    cluster.sync();  // A: every slice histogram is complete
+    if (active && G > 1) {
+        // CTA g sums its share of the bins over the group's histograms and leaves the totals in the leader's
+        const int share = (4096 + G - 1) / G;
+        const unsigned* peer[kSelCluster];
+#pragma unroll
+        for (int r = 0; r < kSelCluster; ++r) peer[r] = cluster.map_shared_rank(sh.hist, lead + min(r, G - 1));
+        for (int i = g * share + tid; i < min((g + 1) * share, 4096); i += kClThreads) {
+            unsigned sum = 0;
+#pragma unroll
+            for (int r = 0; r < kSelCluster; ++r)
+                if (r < G) sum += peer[r][i];
+            lsh->hist[i] = sum;
+        }
+    }
+    cluster.sync();  // B: the leader holds the segment's histogram
+    if (leader) {
+        find_boundary<kClThreads>(sh, 4096, static_cast<unsigned>(k), tid);
+        if (tid == 0) {
+            if (k <= 0 || sh.bin == 0xFFFFFFFFu) {
+                ctl.mode = kModeTakeAll;  // fewer than k pass
+            } else {
+                int lo, hi;
+                unsigned need = 0;
+                const bool ok = logit_tie_window(sh.hist, static_cast<int>(sh.bin), it.thr_lo, static_cast<unsigned>(k), sh.above, lo, hi, need);
+                ctl.mode = ok ? kModeRanked : kModeFallback;
+                ctl.lo_bin = static_cast<unsigned>(lo), ctl.hi_bin = static_cast<unsigned>(hi), ctl.need = need;
+            }
+        }
+    }
+    cluster.sync();  // C: mode and tie window are published
+    const unsigned mode = active ? lctl->mode : 0u;
+    const int lo_bin = mode == kModeRanked ? static_cast<int>(lctl->lo_bin) : 0;
+    const int hi_bin = mode == kModeRanked ? static_cast<int>(lctl->hi_bin) : 4095;
+    const unsigned need = mode == kModeRanked ? lctl->need : 0u;
+    if (mode == kModeRanked) {
+        // ---- 2. window entries go to the leader's list with their exact scores; count what lies above the window
+        unsigned n_above = logit_collect<kVec, kClThreads>(it, i_lo, i_hi, lo_bin, hi_bin, &lsh->n_list, lsh->list_key, lsh->list_idx);
+        n_above = static_cast<unsigned>(warp_sum_i(static_cast<int>(n_above)));
+        if (lane == 0 && n_above) atomicAdd(&ctl.local_cnt, n_above);
+        __syncthreads();
+        if (tid == 0) lctl->cnt_above[g] = ctl.local_cnt;
+    } else if (mode == kModeTakeAll) {
+        if (tid == 0) lctl->cnt_above[g] = sh.n_pass;
+    }
+    cluster.sync();  // D: the leader's list and the per-slice counts are complete
+    if (leader && mode == kModeRanked) {
+        rank_window<kClThreads>(sh, need, tid, [&](int pair) { atomicAdd(&ctl.cnt_window[it.item_of_pair(pair) / per], 1u); });
+    }
+    cluster.sync();  // E: the cut and the per-slice window counts are published
+    unsigned T_key = 0u, first_rank = 0u, total = 0u;
+    int T_idx = 0x7fffffff;
+    if (mode == kModeRanked || mode == kModeTakeAll) {
+        T_key = lsh->t_key, T_idx = lsh->t_idx;
+        for (int r = 0; r < G; ++r) {
+            const unsigned c = lctl->cnt_above[r] + lctl->cnt_window[r];
+            if (r < g) first_rank += c;
+            total += c;
+        }
+    }
+    cluster.sync();  // F: nobody reads another CTA's shared memory from here on
+    if (mode == kModeRanked || mode == kModeTakeAll) {
+        // ---- 3. ordered compaction of the slice into its slots
+        logit_compact<kVec, kClThreads, kClItems>(sh, it, i_lo, i_hi, mode == kModeTakeAll, lo_bin, hi_bin, T_key, T_idx, first_rank, k);
+        if (leader) {
+            const unsigned filled = min(static_cast<unsigned>(k), total);
+            for (int r = filled + tid; r < k_slots; r += kClThreads) src.pad(r);
+        }
+    } else if (leader) {
+        // (rare) a tie window too large for the list: the leader redoes the whole segment with the generic exact selector
+        __syncthreads();
+        select_core<FcosSource, kClThreads>(sh, src, k_slots, min_score, inclusive);
+    }
+}
+
+__global__ void __launch_bounds__(kClThreads, 1024 / kClThreads) fcos_select_cluster_kernel(const __grid_constant__ FcosSelectArgs a,
+                                                                          const __grid_constant__ FcosClusterPlan plan, int batch,
+                                                                          float* __restrict__ cand /*[B, L*k, 6]*/) {
+    __shared__ SelShared sh;
+    __shared__ ClusterCtl ctl;
+    const int rank = static_cast<int>(cooperative_groups::this_cluster().block_rank());
+    const int cid = blockIdx.x / kSelCluster;  // type-major: the clusters with the long segments start first
+    const int type = cid / batch, b = cid - type * batch;
+    const int l = plan.level[type][rank];
+    const bool active = l >= 0;
+    const int lead = plan.lead[type][rank], G = plan.members[type][rank];
+    FcosSource src = fcos_source(a, b, active ? l : 0, cand);
+    if (active && fcos_source_vec(src))
+        fcos_select_cluster_group<true>(sh, ctl, src, a.k_slots, a.min_score, a.inclusive, active, rank - lead, G, lead);
+    else
+        fcos_select_cluster_group<false>(sh, ctl, src, a.k_slots, a.min_score, a.inclusive, active, rank - lead, G, lead);
 }
 
 static int grid_for(long long threads_needed, int block, int sm_count) {
@@ -859,24 +1122,381 @@ static int grid_for(long long threads_needed, int block, int sm_count) {
     return static_cast<int>(g < 1 ? 1 : g);
 }
 
+// ---- the same selection for many segments: estimate, one streaming pass, finish ----------------------------------------
+// With dozens of long segments the three passes above are issue- and latency-bound.  Here the head is read ONCE by the
+// whole GPU: (1) a sample of every 16th load item of a segment gives a logit bound x_est above which about 2.5 k logits
+// are expected (the lower edge of a histogram bin; the threshold itself when the sample holds few passing entries or the
+// segment is short) -- an estimate only, exactness never depends on it; (2) one streaming kernel over all (image,
+// level, chunk) triples appends the class logits >= x_est with their pair index to the segment's candidate list (staged
+// in shared memory, one global atomic per chunk); (3) one CTA per segment selects the exact top k among its candidates
+// with the same machinery as above -- histogram, boundary bin, tie window ranked exactly -- marks the winners in a
+// shared-memory bitmap over the pair indices and emits them in index order by a popcount scan.  A segment whose
+// candidates do not provably contain its top k (list overflow, fewer than k candidates above an estimate that is not the
+// threshold, a tie window reaching down to the estimate's bin or too large for the list) is flagged, and
+// fcos_select_kernel redoes the flagged segments exactly as before.
+constexpr int kPreChunkItems = 2048;    // load items per CTA of the streaming pass
+constexpr int kPreThreads = 256;
+constexpr int kPreStage = 1024;         // candidates a chunk can stage (more: the segment is flagged)
+constexpr int kPreSampleStride = 16;
+constexpr int kPreBitmapWords = 16384;  // 512 K (location, class) pairs per segment
+
+struct PreselWork {
+    float* x_est;    // [B*L] logit bound of the candidates
+    int* est_bin;    // [B*L] its histogram bin; -1: the bound is the threshold itself (every passing entry is a candidate)
+    unsigned* count; // [B*L] candidates appended
+    int* flag;       // [B*L] 1: the segment has to be redone by fcos_select_kernel
+    float* cand_x;   // [B*L, cap]
+    int* cand_pair;  // [B*L, cap]
+    int cap, bitmap_words;  // list capacity per segment; words of the finish kernel's shared-memory bitmap
+};
+
+// (1) grid (B, L)
+__global__ void __launch_bounds__(kSelThreads) fcos_presel_estimate_kernel(const __grid_constant__ FcosSelectArgs a, PreselWork w) {
+    __shared__ SelShared sh;
+    const int b = blockIdx.x, l = blockIdx.y, seg = b * a.n_levels + l, tid = threadIdx.x;
+    const FcosSource src = fcos_source(a, b, l, nullptr);
+    if (tid == 0) w.count[seg] = 0u, w.flag[seg] = 0;
+    const int k = min(a.k_slots, max(src.n, 0));
+    LogitItems<true> it;
+    it.init(src, a.min_score, a.inclusive);
+    if (src.n <= w.cap || !fcos_source_vec(src)) {  // short (or unaligned, hence short) segment: everything that passes
+        if (tid == 0) w.est_bin[seg] = -1, w.x_est[seg] = it.thr_lo;
+        return;
+    }
+    for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
+    if (tid == 0) sh.bin = 0xFFFFFFFFu, sh.above = 0;
+    __syncthreads();
+    const int n_sample = it.n_items / kPreSampleStride;
+    for (int base = 0; base < n_sample; base += kSelThreads * 4) {
+        LogitItems<true>::Item q[4];
+        logit_scan<true, 4>(
+            it, q, n_sample * kPreSampleStride, it.thr_pass, INFINITY, [&](int u) { return (base + u * kSelThreads + tid) * kPreSampleStride; },
+            [&](int, int, float x) { atomicAdd(&sh.hist[it.bin_x(x)], 1u); }, [](int, int, float) {});
+    }
+    __syncthreads();
+    // aim at 2.5 k candidates: the r-th largest of the sample with r = 2.5 k / stride
+    const unsigned r = static_cast<unsigned>(max((5 * k) / (2 * kPreSampleStride), 8));
+    find_boundary<kSelThreads>(sh, 4096, r, tid);
+    if (tid == 0) {
+        const bool all = sh.bin == 0xFFFFFFFFu || sh.bin == 0u;
+        w.est_bin[seg] = all ? -1 : static_cast<int>(sh.bin);
+        w.x_est[seg] = all ? it.thr_lo : it.thr_lo + static_cast<float>(sh.bin) / kLogitBinScale;
+    }
+}
+
+// (2) one CTA per (level, image, chunk); the chunk table is level-major so that the long segments start first
+struct PreselChunks {
+    int first[DH_MAX_LEVELS + 1];  // first chunk id of each level (ids run level > image > chunk)
+    int per_seg[DH_MAX_LEVELS];    // chunks per segment
+};
+template <bool kVec>
+__device__ __forceinline__ void presel_collect_chunk(const FcosSource& src, const FcosSelectArgs& a, const PreselWork& w, int seg, int chunk,
+                                                     float* st_x, int* st_pair, unsigned* st_n) {
+    LogitItems<kVec> it;
+    it.init(src, a.min_score, a.inclusive);
+    const int tid = threadIdx.x;
+    const int i_lo = chunk * kPreChunkItems, i_hi = min(i_lo + kPreChunkItems, it.n_items);
+    const float x_est = w.x_est[seg];
+    constexpr int U = kVec ? 4 : 8;
+    for (int base = i_lo; base < i_hi; base += kPreThreads * U) {
+        typename LogitItems<kVec>::Item q[U];
+        logit_scan<kVec, U>(
+            it, q, i_hi, x_est, INFINITY, [&](int u) { return base + u * kPreThreads + tid; },
+            [&](int u, int e, float x) {
+                const unsigned slot = atomicAdd(st_n, 1u);
+                if (slot < kPreStage) st_x[slot] = x, st_pair[slot] = it.pair_index(base + u * kPreThreads + tid, q[u], e);
+            },
+            [](int, int, float) {});
+    }
+}
+__global__ void __launch_bounds__(kPreThreads) fcos_presel_collect_kernel(const __grid_constant__ FcosSelectArgs a,
+                                                                        const __grid_constant__ PreselChunks ct, int batch, PreselWork w) {
+    __shared__ float st_x[kPreStage];
+    __shared__ int st_pair[kPreStage];
+    __shared__ unsigned st_n, st_base;
+    int l = 0;
+    while (l + 1 < a.n_levels && static_cast<int>(blockIdx.x) >= ct.first[l + 1]) ++l;
+    const int local = blockIdx.x - ct.first[l];
+    const int b = local / ct.per_seg[l], chunk = local - b * ct.per_seg[l];
+    const int seg = b * a.n_levels + l, tid = threadIdx.x;
+    if (tid == 0) st_n = 0u;
+    __syncthreads();
+    const FcosSource src = fcos_source(a, b, l, nullptr);
+    if (fcos_source_vec(src)) presel_collect_chunk<true>(src, a, w, seg, chunk, st_x, st_pair, &st_n);
+    else presel_collect_chunk<false>(src, a, w, seg, chunk, st_x, st_pair, &st_n);
+    __syncthreads();
+    const unsigned n = st_n;
+    if (n == 0u) return;
+    if (n > kPreStage) {  // more candidates in one chunk than the stage holds: the estimate was useless here
+        if (tid == 0) w.flag[seg] = 1;
+        return;
+    }
+    if (tid == 0) st_base = atomicAdd(&w.count[seg], n);
+    __syncthreads();
+    const unsigned base = st_base;
+    for (unsigned i = tid; i < n; i += kPreThreads)
+        if (base + i < static_cast<unsigned>(w.cap)) {
+            w.cand_x[static_cast<long long>(seg) * w.cap + base + i] = st_x[i];
+            w.cand_pair[static_cast<long long>(seg) * w.cap + base + i] = st_pair[i];
+        }
+}
+
+// (3) grid (B, L); dynamic shared memory: candidates (x, pair) [cap] + bitmap [kPreBitmapWords]
+__global__ void __launch_bounds__(kSelThreads) fcos_presel_finish_kernel(const __grid_constant__ FcosSelectArgs a, PreselWork w,
+                                                                       float* __restrict__ cand /*[B, L*k, 6]*/) {
+    __shared__ SelShared sh;
+    __shared__ unsigned s_pass;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    float* cx = reinterpret_cast<float*>(dyn);
+    int* cp = reinterpret_cast<int*>(dyn) + w.cap;
+    unsigned* ckey = reinterpret_cast<unsigned*>(dyn) + 2 * w.cap;
+    unsigned* bitmap = reinterpret_cast<unsigned*>(dyn) + 3 * w.cap;
+    const int b = blockIdx.x, l = blockIdx.y, seg = b * a.n_levels + l, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const FcosSource src = fcos_source(a, b, l, cand);
+    const int k = min(a.k_slots, max(src.n, 0));
+    const unsigned count = w.count[seg];
+    const int est_bin = w.est_bin[seg];
+    const int words = (src.n + 31) >> 5;
+    if (w.flag[seg] || count > static_cast<unsigned>(w.cap) || words > w.bitmap_words) {
+        if (tid == 0) w.flag[seg] = 1;
+        return;
+    }
+    LogitItems<false> it;  // only the threshold test and the bin map are used here
+    it.init(src, a.min_score, a.inclusive);
+    const int n = static_cast<int>(count);
+    for (int i = tid; i < 4096; i += kSelThreads) sh.hist[i] = 0;
+    for (int i = tid; i < words; i += kSelThreads) bitmap[i] = 0u;
+    if (tid == 0) sh.n_list = 0, sh.bin = 0xFFFFFFFFu, sh.above = 0, sh.t_key = 0u, sh.t_idx = 0x7fffffff, s_pass = 0u;
+    __syncthreads();
+    // candidates -> shared memory with their exact score keys (0: fails the threshold), histogram of the passing ones
+    unsigned my_pass = 0;
+    for (int i = tid; i < n; i += kSelThreads) {
+        const float x = w.cand_x[static_cast<long long>(seg) * w.cap + i];
+        cx[i] = x, cp[i] = w.cand_pair[static_cast<long long>(seg) * w.cap + i];
+        const bool ok = it.passes(x);
+        ckey[i] = ok ? score_key(sigmoid_acc(x)) : 0u;
+        if (ok) atomicAdd(&sh.hist[it.bin_x(x)], 1u), ++my_pass;
+    }
+    my_pass = static_cast<unsigned>(warp_sum_i(static_cast<int>(my_pass)));
+    if (lane == 0 && my_pass) atomicAdd(&s_pass, my_pass);
+    __syncthreads();
+    const unsigned n_pass = s_pass;
+    bool take_all = false;
+    int lo_bin = 0, hi_bin = 4095;
+    if (n_pass < static_cast<unsigned>(k)) {
+        if (est_bin >= 0) {  // fewer than k candidates, and they are not everything that passes
+            if (tid == 0) w.flag[seg] = 1;
+            return;
+        }
+        take_all = true;
+    } else if (k > 0) {
+        find_boundary<kSelThreads>(sh, 4096, static_cast<unsigned>(k), tid);
+        if (tid == 0) {
+            int lo, hi;
+            unsigned need = 0;
+            bool ok = logit_tie_window(sh.hist, static_cast<int>(sh.bin), it.thr_lo, static_cast<unsigned>(k), sh.above, lo, hi, need);
+            ok = ok && lo > est_bin;  // every entry of the segment in the window's bins is a candidate
+            sh.wtot[1][0] = ok ? 1u : 0u, sh.wtot[1][1] = static_cast<unsigned>(lo), sh.wtot[1][2] = static_cast<unsigned>(hi);
+            sh.need = need;
+        }
+        __syncthreads();
+        if (!sh.wtot[1][0]) {
+            if (tid == 0) w.flag[seg] = 1;
+            return;
+        }
+        lo_bin = static_cast<int>(sh.wtot[1][1]), hi_bin = static_cast<int>(sh.wtot[1][2]);
+        for (int i = tid; i < n; i += kSelThreads) {
+            if (!ckey[i]) continue;
+            const int bn = it.bin_x(cx[i]);
+            if (bn < lo_bin || bn > hi_bin) continue;
+            const unsigned slot = atomicAdd(&sh.n_list, 1u);
+            sh.list_key[slot] = ckey[i], sh.list_idx[slot] = cp[i];
+        }
+        __syncthreads();
+        rank_window<kSelThreads>(sh, sh.need, tid, [](int) {});
+        __syncthreads();
+    }
+    const unsigned T_key = sh.t_key;
+    const int T_idx = sh.t_idx;
+    // winners -> bitmap over the pair indices
+    for (int i = tid; i < n; i += kSelThreads) {
+        const unsigned key = ckey[i];
+        bool take = key != 0u;
+        if (take && !take_all) {
+            const int bn = it.bin_x(cx[i]);
+            take = bn > hi_bin || (bn >= lo_bin && (key > T_key || (key == T_key && cp[i] <= T_idx)));
+        }
+        if (take) atomicOr(&bitmap[cp[i] >> 5], 1u << (cp[i] & 31));
+        else ckey[i] = 0u;
+    }
+    __syncthreads();
+    // ranks in index order: popcount scan over the bitmap (thread t owns words [t*wpt, (t+1)*wpt))
+    const int wpt = (words + kSelThreads - 1) / kSelThreads;
+    unsigned mine = 0;
+    for (int q = 0; q < wpt; ++q) {
+        const int wi = tid * wpt + q;
+        if (wi < words) mine += __popc(bitmap[wi]);
+    }
+    unsigned incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) sh.wtot[0][warp] = incl;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+    for (int q = 0; q < kSelThreads / 32; ++q) {
+        const unsigned v = sh.wtot[0][q];
+        if (q < warp) before += v;
+        total += v;
+    }
+    unsigned* prefix = sh.list_key;  // [kSelThreads] exclusive prefix per thread (the list is no longer needed)
+    __syncthreads();
+    prefix[tid] = before + incl - mine;
+    __syncthreads();
+    for (int i = tid; i < n; i += kSelThreads) {
+        if (!ckey[i]) continue;
+        const int pair = cp[i], wi = pair >> 5, owner = wi / wpt;
+        unsigned rank = prefix[owner] + __popc(bitmap[wi] & ((1u << (pair & 31)) - 1u));
+        for (int q = owner * wpt; q < wi; ++q) rank += __popc(bitmap[q]);
+        if (rank < static_cast<unsigned>(k)) src.emit(pair, sigmoid_acc(cx[i]), static_cast<int>(rank));
+    }
+    const unsigned filled = min(static_cast<unsigned>(k), total);
+    for (int r = filled + tid; r < a.k_slots; r += kSelThreads) src.pad(r);
+}
+
+// Host-side plan: how many CTAs share each level's segment and which clusters they sit in.  A segment gets one CTA
+// per 64 K head values (at most a whole cluster); levels are packed into clusters first-fit by decreasing size and the
+// ranks left over go to the groups with the longest slices.
+static FcosClusterPlan plan_fcos_clusters(const long long* values, int n_levels) {
+    FcosClusterPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    memset(plan.level, -1, sizeof(plan.level));
+    int order[DH_MAX_LEVELS], want[DH_MAX_LEVELS];
+    for (int l = 0; l < n_levels; ++l) {
+        order[l] = l;
+        const long long w = (values[l] + 65535) / 65536;
+        want[l] = static_cast<int>(w < 1 ? 1 : (w > kSelCluster ? kSelCluster : w));
+    }
+    for (int i = 1; i < n_levels; ++i)  // insertion sort, longest first (stable)
+        for (int j = i; j > 0 && values[order[j]] > values[order[j - 1]]; --j) {
+            const int t = order[j];
+            order[j] = order[j - 1], order[j - 1] = t;
+        }
+    int used[DH_MAX_LEVELS] = {0}, n_groups[DH_MAX_LEVELS] = {0};
+    int group_level[DH_MAX_LEVELS][kSelCluster], group_members[DH_MAX_LEVELS][kSelCluster];
+    for (int i = 0; i < n_levels; ++i) {
+        const int l = order[i];
+        int t = 0;
+        while (t < plan.n_types && used[t] + want[l] > kSelCluster) ++t;
+        if (t == plan.n_types) ++plan.n_types;
+        group_level[t][n_groups[t]] = l, group_members[t][n_groups[t]] = want[l];
+        ++n_groups[t], used[t] += want[l];
+    }
+    for (int t = 0; t < plan.n_types; ++t) {
+        while (used[t] < kSelCluster) {
+            int best = -1;
+            long long best_slice = 16384;  // shorter slices are not worth another CTA
+            for (int q = 0; q < n_groups[t]; ++q) {
+                const long long slice = values[group_level[t][q]] / group_members[t][q];
+                if (slice > best_slice) best = q, best_slice = slice;
+            }
+            if (best < 0) break;
+            ++group_members[t][best], ++used[t];
+        }
+        int rank = 0;
+        for (int q = 0; q < n_groups[t]; ++q) {
+            const int lead = rank;
+            for (int m = 0; m < group_members[t][q]; ++m, ++rank) {
+                plan.level[t][rank] = static_cast<signed char>(group_level[t][q]);
+                plan.lead[t][rank] = static_cast<unsigned char>(lead);
+                plan.members[t][rank] = static_cast<unsigned char>(group_members[t][q]);
+            }
+        }
+    }
+    return plan;
+}
+
 int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batch, int pad_h, int pad_w, int n_levels,
                        const int32_t* strides, int num_classes, int center, int k, float min_score, int inclusive, float* cand,
                        cudaStream_t st) {
     FcosSelectArgs a;
     memset(&a, 0, sizeof(a));
     a.num_classes = num_classes, a.center = center, a.k_slots = k, a.n_levels = n_levels, a.inclusive = inclusive, a.min_score = min_score;
-    a.allow_logit_space = h->fcos_select_exact_only ? 0 : 1;
+    a.allow_logit_space = h->fcos_select_mode == 1 ? 0 : 1;
+    long long values[DH_MAX_LEVELS];
     for (int l = 0; l < n_levels; ++l) {
         a.head[l] = pred_levels[l];
         a.hl[l] = static_cast<int>(static_cast<double>(pad_h) / strides[l]);
         a.wl[l] = static_cast<int>(static_cast<double>(pad_w) / strides[l]);
         if (a.wl[l] < 1) a.wl[l] = 1, a.hl[l] = 0;
         a.stride[l] = static_cast<float>(strides[l]);
+        values[l] = static_cast<long long>(a.hl[l]) * a.wl[l] * (num_classes + 5);
     }
-    dim3 grid(batch, n_levels);
-    fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand);
-    DH_CUDA(cudaGetLastError());
-    h->launches += 1;
+    // same condition as logit_space_applies(): the cluster kernel has no scoring path of its own
+    const bool logit_space = !center && min_score > 1.0e-6f && min_score < 0.999f && k > 0;
+    // Which selector (all exact, all bit-identical):
+    //   pre-select  reads the head once with every SM; for k <= 1024 it is the fastest at every batch size (B200, C4
+    //               shape, whole dh_fcos_detect: 276 us for 64 images against 466 us with one CTA per segment);
+    //   clusters    pay barriers and leader-only steps per segment: they beat one CTA per segment while the long
+    //               segments alone cannot fill the GPU (2.1x faster at 1..8 images, break-even near 48);
+    //   one CTA per (image, level) otherwise.
+    const bool few_segments = static_cast<long long>(batch) * 3 <= h->sm_count;
+    long long longest_pairs = 1;
+    for (int l = 0; l < n_levels; ++l) longest_pairs = std::max(longest_pairs, static_cast<long long>(a.hl[l]) * a.wl[l] * num_classes);
+    const bool presel_fits = k <= 1024 && (longest_pairs + 31) / 32 <= kPreBitmapWords;
+    int launched = 1;
+    const bool use_presel = logit_space && presel_fits && (h->fcos_select_mode == 4 || h->fcos_select_mode == 0);
+    if (logit_space && !use_presel && (h->fcos_select_mode == 3 || (h->fcos_select_mode == 0 && few_segments))) {
+        const FcosClusterPlan plan = plan_fcos_clusters(values, n_levels);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(static_cast<unsigned>(kSelCluster) * plan.n_types * batch), cfg.blockDim = dim3(kClThreads), cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = kSelCluster, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr, cfg.numAttrs = 1;
+        DH_CUDA(cudaLaunchKernelEx(&cfg, fcos_select_cluster_kernel, a, plan, batch, cand));
+    } else if (use_presel) {
+        const int segs = batch * n_levels;
+        PreselWork w;
+        w.cap = 4096;
+        w.bitmap_words = static_cast<int>((longest_pairs + 31) / 32);
+        const size_t head_bytes = (static_cast<size_t>(segs) * 16 + 255) & ~size_t(255);
+        char* base = static_cast<char*>(scratch(h, head_bytes + static_cast<size_t>(segs) * w.cap * 8));
+        if (!base) return DH_ERR_CUDA;
+        w.x_est = reinterpret_cast<float*>(base), w.est_bin = reinterpret_cast<int*>(base) + segs;
+        w.count = reinterpret_cast<unsigned*>(base) + 2 * segs, w.flag = reinterpret_cast<int*>(base) + 3 * segs;
+        w.cand_x = reinterpret_cast<float*>(base + head_bytes);
+        w.cand_pair = reinterpret_cast<int*>(base + head_bytes) + static_cast<size_t>(segs) * w.cap;
+        PreselChunks ct;
+        memset(&ct, 0, sizeof(ct));
+        for (int l = 0; l < n_levels; ++l) {
+            const bool vec = (reinterpret_cast<uintptr_t>(a.head[l]) & 15u) == 0 && (values[l] & 3) == 0;  // fcos_source_vec()
+            const long long items = vec ? values[l] >> 2 : static_cast<long long>(a.hl[l]) * a.wl[l] * num_classes;
+            ct.per_seg[l] = static_cast<int>((items + kPreChunkItems - 1) / kPreChunkItems);
+            ct.first[l + 1] = ct.first[l] + ct.per_seg[l] * batch;
+        }
+        dim3 grid(batch, n_levels);
+        fcos_presel_estimate_kernel<<<grid, kSelThreads, 0, st>>>(a, w);
+        if (ct.first[n_levels] > 0) fcos_presel_collect_kernel<<<ct.first[n_levels], kPreThreads, 0, st>>>(a, ct, batch, w);
+        const size_t dyn = (static_cast<size_t>(3) * w.cap + w.bitmap_words) * 4;
+        static size_t configured_dyn = 0;  // grows only; a repeated call with the same value is skipped
+        if (dyn > configured_dyn) {
+            DH_CUDA(cudaFuncSetAttribute(fcos_presel_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+            configured_dyn = dyn;
+        }
+        fcos_presel_finish_kernel<<<grid, kSelThreads, dyn, st>>>(a, w, cand);
+        fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand, w.flag);
+        DH_CUDA(cudaGetLastError());
+        launched = 4;
+    } else {
+        dim3 grid(batch, n_levels);
+        fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand, nullptr);
+        DH_CUDA(cudaGetLastError());
+    }
+    h->launches += launched;
     return DH_OK;
 }
 

@@ -17,7 +17,7 @@ struct dh_handle_s {
     int nms_kernel;         // DH_OPT_NMS_KERNEL
     int fused_chunks_per_cta;  // DH_OPT_FUSED_CHUNKS_PER_CTA
     int encode_min_chunk;      // DH_OPT_ENCODE_MIN_CHUNK
-    int fcos_select_exact_only;  // DH_OPT_FCOS_SELECT
+    int fcos_select_mode;  // DH_OPT_FCOS_SELECT
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
     size_t scratch_bytes;

@@ -51,7 +51,7 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_PHASE_TIMING 4 /* profiling aid: 1 = CTA 0 of each encode kernel accumulates per-phase clock64 totals; (re)sets them */
 #define DH_OPT_FUSED_LOSS_KERNEL 5 /* 0 (default): stream + correct kernel when num_classes <= 128; 1: always the shared-memory target-tile kernel */
 #define DH_OPT_NMS_KERNEL 6 /* 0 (default): pick per call; 1: lazy one-CTA-per-image NMS whenever the output cap is <= 1024; 2: always mask matrix on all SMs + block sweep */
-#define DH_OPT_FCOS_SELECT 7 /* 0 (default): dh_fcos_detect selects in logit space when it can; 1: always score every pair (A/B checks) */
+#define DH_OPT_FCOS_SELECT 7 /* dh_fcos_detect candidate selection (every choice is exact and bit-identical). 0 (default): in logit space when it can -- estimate + one streaming pass + per-level finish for pre_nms_topk <= 1024, else a thread-block cluster per long level for small batches; 1: always score every pair, one CTA per (image, level); 2: logit space, one CTA per (image, level); 3: logit space, always clusters; 4: logit space, the streaming pre-select whenever it fits */
 #define DH_OPT_FUSED_CHUNKS_PER_CTA 8 /* fused loss scheduler: aim at this many image-aligned chunks per persistent CTA (default 12; a chunk is always 4..8 tiles of 256 rows) */
 #define DH_OPT_ENCODE_MIN_CHUNK 9 /* encoders: smallest scheduler chunk in tiles (default 2) */
 int dh_set_option(dh_handle_t h, int option, int value);

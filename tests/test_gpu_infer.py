@@ -172,14 +172,19 @@ def test_c4_shaped_detection_pipelines():
         assert np.array_equal(oc[b].cpu().numpy(), wc)
 
 
+@pytest.mark.parametrize("shape", [(256, 20, 300), (640, 80, 1000)], ids=["256px-20cls", "640px-80cls"])
 @pytest.mark.parametrize("case", ["plain", "quantised ties", "saturated", "few pass", "threshold edge"])
-def test_fcos_select_logit_space_equals_exact_scoring(case):
-    """dh_fcos_detect selects candidates on raw logits when it can (no sigmoid per element); the candidate rows and the
-    final detections must be bit-identical to the path that scores every (location, class) pair (DH_OPT_FCOS_SELECT=1),
-    including where distinct logits collide after the float32 sigmoid and ties are cut by index."""
+def test_fcos_select_logit_space_equals_exact_scoring(case, shape):
+    """dh_fcos_detect selects candidates on raw logits when it can (no sigmoid per element) -- by default with a
+    thread-block cluster per long level (DH_OPT_FCOS_SELECT=3), an estimate + one streaming pass + per-level finish (=4;
+    the default, 0, picks between these two by batch size) or one CTA per (image, level) (=2); the candidate rows and
+    the final detections must be bit-identical to the path that scores every (location, class) pair (=1), including
+    where distinct logits collide after the float32 sigmoid and ties are cut by index.  The 640-pixel shape spreads
+    level 0 over a whole cluster and has a level whose rows are not float4-aligned."""
     dh = _dh()
+    size, classes, topk = shape
     B = 2
-    heads = synth.fcos_predictions(B, 256, 20, synth.seed_for(4, 90))
+    heads = synth.fcos_predictions(B, size, classes, synth.seed_for(4, 90))
     for h in heads:
         x = h[..., 5:] * 2.5 + 6.9
         if case == "quantised ties":
@@ -187,20 +192,42 @@ def test_fcos_select_logit_space_equals_exact_scoring(case):
         elif case == "saturated":
             x = x + 14.0                      # thousands of scores round to exactly 1.0 or within a few ulps of it
         elif case == "few pass":
-            x = x - 6.0
+            x = x - (6.0 if size == 256 else 9.0)
         elif case == "threshold edge":
             x = np.where(np.abs(x + 2.9444) < 0.2, np.float32(-2.9444389) + np.round((x + 2.9444) * 1e7) * np.float32(2.4e-7), x)
         h[..., 5:] = x.astype(np.float32)
     out = []
-    for exact_only in (0, 1):
-        dh.set_option(0, 7, exact_only)
+    for mode in (3, 1, 2, 4, 0):
+        dh.set_option(0, 7, mode)
         try:
-            out.append([t.cpu().numpy() for t in dh.fcos.detect_batch(heads, 20, [256, 256], pre_nms_topk=300, with_candidates=True)])
+            out.append([t.cpu().numpy() for t in dh.fcos.detect_batch(heads, classes, [size, size], pre_nms_topk=topk, with_candidates=True)])
         finally:
             dh.set_option(0, 7, 0)
-    for a, b in zip(*out):
-        assert np.array_equal(a, b)
+    for other in (out[0], out[2], out[3], out[4]):
+        for a, b in zip(other, out[1]):
+            assert np.array_equal(a, b)
     assert np.isfinite(out[0][4][..., 4]).any() or case == "few pass"
+
+
+def test_fcos_select_cluster_small_batches_and_levels():
+    """The cluster selector's host-side plan and the streaming pre-select's chunk table: one level only, levels shorter
+    than a slice / a chunk, a single image."""
+    dh = _dh()
+    for size, classes, strides, B in ((640, 80, [8], 1), (128, 3, [8, 16, 32, 64, 128], 3), (512, 20, [16, 32], 2)):
+        heads = synth.fcos_predictions(B, size, classes, synth.seed_for(4, 91), strides=strides)
+        for h in heads:
+            h[..., 5:] = h[..., 5:] * 2.5 + 6.9
+        out = []
+        for mode in (1, 3, 4):
+            dh.set_option(0, 7, mode)
+            try:
+                out.append([t.cpu().numpy() for t in dh.fcos.detect_batch(heads, classes, [size, size], pre_nms_topk=200, with_candidates=True,
+                                                                           strides=strides)])
+            finally:
+                dh.set_option(0, 7, 0)
+        for other in out[1:]:
+            for a, b in zip(other, out[0]):
+                assert np.array_equal(a, b)
 
 
 def test_compute_iou_and_bboxes_iou(golden):
