@@ -99,6 +99,7 @@ int dh_create(dh_handle_t* out, int device) {
     h->fused_chunks_per_cta = 12;
     h->encode_min_chunk = 2;
     h->fcos_select_mode = 0;
+    h->nms_sort = 0;
     h->launches = 0;
     h->scratch = nullptr;
     h->scratch_bytes = 0;
@@ -149,6 +150,10 @@ int dh_set_option(dh_handle_t h, int option, int value) {
         case DH_OPT_FCOS_SELECT:
             DH_CHECK_ARG(value >= 0 && value <= 4, "DH_OPT_FCOS_SELECT must be in [0, 4]");
             h->fcos_select_mode = value;
+            return DH_OK;
+        case DH_OPT_NMS_SORT:
+            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_NMS_SORT must be 0 or 1");
+            h->nms_sort = value;
             return DH_OK;
         case DH_OPT_FUSED_CHUNKS_PER_CTA:
             DH_CHECK_ARG(value >= 1 && value <= 64, "DH_OPT_FUSED_CHUNKS_PER_CTA must be in [1, 64]");

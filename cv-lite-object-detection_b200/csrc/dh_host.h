@@ -18,6 +18,7 @@ struct dh_handle_s {
     int fused_chunks_per_cta;  // DH_OPT_FUSED_CHUNKS_PER_CTA
     int encode_min_chunk;      // DH_OPT_ENCODE_MIN_CHUNK
     int fcos_select_mode;  // DH_OPT_FCOS_SELECT
+    int nms_sort;          // DH_OPT_NMS_SORT
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
     size_t scratch_bytes;

@@ -38,60 +38,130 @@ struct NmsParams {
 };
 
 // ---- kernel 1 -----------------------------------------------------------------------------------------
+// Keys are distinct (the candidate index sits in the low word), so the sorted order is unique and any correct sort
+// gives the same result.  The fast path is a bucket sort in shared memory with six block barriers: 4096 buckets over
+// the span of the score keys (descending), a prefix over the bucket counts, a scatter into the bucket segments, and
+// each key's rank inside its bucket by counting the larger keys of the segment.  Scores piled onto few buckets (a
+// segment longer than kSortMaxBucket) fall back to the bitonic network, which does 91 barrier-separated stages for
+// 8192 keys.
+constexpr int kSortBuckets = 4096;
+constexpr int kSortMaxBucket = 384;
+
+__device__ __forceinline__ unsigned long long nms_sort_key(const float* d, int row_floats, int i, int inclusive, float min_score) {
+    const float s = d[static_cast<long long>(i) * row_floats + 4];
+    const bool ok = inclusive ? (s >= min_score) : (s > min_score);
+    if (!ok) return 0ull;  // sorts to the end
+    // monotone map float -> uint (handles negatives too), then descending sort of the 64-bit key
+    unsigned u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const unsigned long long k = (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned>(i));
+    return k == 0ull ? 1ull : k;
+}
+
 __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __restrict__ dets, const int* __restrict__ n_valid,
-                                                                NmsParams p, int n_pow2, float4* __restrict__ sorted_boxes,
+                                                                NmsParams p, int n_pow2, int force_bitonic, float4* __restrict__ sorted_boxes,
                                                                 int* __restrict__ sorted_cls, int* __restrict__ order,
                                                                 int* __restrict__ n_cand) {
     extern __shared__ unsigned long long keys[];  // [n_pow2]
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ unsigned bucket_start[kSortBuckets], bucket_fill[kSortBuckets];
+    __shared__ unsigned warp_tot[kSortThreads / 32];
+    __shared__ unsigned key_min, key_max, biggest;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = n_valid ? min(n_valid[b], p.n_max) : p.n_max;
     const float* d = dets + static_cast<long long>(b) * p.n_max * p.row_floats;
-    for (int i = tid; i < n_pow2; i += kSortThreads) {
-        unsigned long long k = 0ull;  // sorts to the end
-        if (i < n) {
-            const float s = d[static_cast<long long>(i) * p.row_floats + 4];
-            const bool ok = p.inclusive ? (s >= p.min_score) : (s > p.min_score);
-            if (ok) {
-                // monotone map float -> uint (handles negatives too), then descending sort of the 64-bit key
-                unsigned u = __float_as_uint(s);
-                u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-                k = (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned>(i));
-                if (k == 0ull) k = 1ull;
-            }
-        }
-        keys[i] = k;
+    auto emit = [&](int pos, unsigned long long key) {
+        const int src = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFull));
+        const float* r = d + static_cast<long long>(src) * p.row_floats;
+        sorted_boxes[static_cast<long long>(b) * p.n_max + pos] = make_float4(r[0], r[1], r[2], r[3]);
+        sorted_cls[static_cast<long long>(b) * p.n_max + pos] = p.per_class ? __float2int_rz(r[5]) : 0;
+        order[static_cast<long long>(b) * p.n_max + pos] = src;
+    };
+    // span of the score keys
+    if (tid == 0) key_min = 0xFFFFFFFFu, key_max = 0u, biggest = 0u;
+    for (int i = tid; i < kSortBuckets; i += kSortThreads) bucket_fill[i] = 0u;
+    __syncthreads();
+    unsigned lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < n; i += kSortThreads) {
+        const unsigned long long k = nms_sort_key(d, p.row_floats, i, p.inclusive, p.min_score);
+        if (k) lo = min(lo, static_cast<unsigned>(k >> 32)), hi = max(hi, static_cast<unsigned>(k >> 32));
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)), hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    if (lane == 0 && lo <= hi) atomicMin(&key_min, lo), atomicMax(&key_max, hi);
+    __syncthreads();
+    const unsigned kmin = key_min, span = key_max >= kmin ? key_max - kmin : 0u;
+    const int shift = max(0, (32 - __clz(span)) - 12);  // (u - kmin) >> shift < 4096
+    auto bucket_of = [&](unsigned long long k) { return kSortBuckets - 1 - static_cast<int>((static_cast<unsigned>(k >> 32) - kmin) >> shift); };
+    for (int i = tid; i < n; i += kSortThreads) {
+        const unsigned long long k = nms_sort_key(d, p.row_floats, i, p.inclusive, p.min_score);
+        if (k) atomicAdd(&bucket_fill[bucket_of(k)], 1u);
+    }
+    __syncthreads();
+    // exclusive prefix over the buckets (thread t owns 4 consecutive buckets)
+    unsigned c[kSortBuckets / kSortThreads], mine = 0, most = 0;
+#pragma unroll
+    for (int q = 0; q < kSortBuckets / kSortThreads; ++q) c[q] = bucket_fill[tid * (kSortBuckets / kSortThreads) + q], mine += c[q], most = max(most, c[q]);
+    unsigned incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, o));
+    if (lane == 31) warp_tot[warp] = incl;
+    if (lane == 0) atomicMax(&biggest, most);
+    __syncthreads();
+    unsigned before = 0, m_total = 0;
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+        const unsigned v = warp_tot[w];
+        if (w < warp) before += v;
+        m_total += v;
+    }
+    const int m = static_cast<int>(m_total);
+    if (biggest <= kSortMaxBucket && !force_bitonic) {
+        unsigned run = before + incl - mine;
+#pragma unroll
+        for (int q = 0; q < kSortBuckets / kSortThreads; ++q) {
+            bucket_start[tid * (kSortBuckets / kSortThreads) + q] = run, bucket_fill[tid * (kSortBuckets / kSortThreads) + q] = run;
+            run += c[q];
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += kSortThreads) {
+            const unsigned long long k = nms_sort_key(d, p.row_floats, i, p.inclusive, p.min_score);
+            if (k) keys[atomicAdd(&bucket_fill[bucket_of(k)], 1u)] = k;
+        }
+        __syncthreads();
+        if (tid == 0) n_cand[b] = m;
+        for (int q = tid; q < m; q += kSortThreads) {
+            const unsigned long long k = keys[q];
+            const int bk = bucket_of(k);
+            const unsigned s0 = bucket_start[bk], s1 = bucket_fill[bk];  // after the scatter the fill cursor is the segment's end
+            unsigned r = 0;
+            for (unsigned j = s0; j < s1; ++j) r += keys[j] > k ? 1u : 0u;
+            emit(static_cast<int>(s0 + r), k);
+        }
+        return;
+    }
+    // bitonic network over n_pow2 keys
+    __syncthreads();
+    for (int i = tid; i < n_pow2; i += kSortThreads) keys[i] = i < n ? nms_sort_key(d, p.row_floats, i, p.inclusive, p.min_score) : 0ull;
     __syncthreads();
     for (int size = 2; size <= n_pow2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = tid; t < (n_pow2 >> 1); t += kSortThreads) {
-                const int lo = ((t / stride) * (stride << 1)) + (t % stride);
-                const int hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const unsigned long long a = keys[lo], c = keys[hi];
-                if (desc ? (a < c) : (a > c)) keys[lo] = c, keys[hi] = a;
+                const int lo_i = ((t / stride) * (stride << 1)) + (t % stride);
+                const int hi_i = lo_i + stride;
+                const bool desc = ((lo_i & size) == 0);
+                const unsigned long long a = keys[lo_i], cc = keys[hi_i];
+                if (desc ? (a < cc) : (a > cc)) keys[lo_i] = cc, keys[hi_i] = a;
             }
             __syncthreads();
         }
     }
-    // valid keys are a prefix; count them and gather boxes in score order
-    int cnt = 0;
-    for (int i = tid; i < n_pow2; i += kSortThreads) cnt += (keys[i] != 0ull);
-    __shared__ int total;
-    if (tid == 0) total = 0;
-    __syncthreads();
-    cnt = warp_sum_i(cnt);
-    if ((tid & 31) == 0 && cnt) atomicAdd(&total, cnt);
-    __syncthreads();
-    const int m = total;
+    // valid keys are a prefix (m of them); gather boxes in score order
     if (tid == 0) n_cand[b] = m;
-    for (int i = tid; i < m; i += kSortThreads) {
-        const int src = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(keys[i] & 0xFFFFFFFFull));
-        const float* r = d + static_cast<long long>(src) * p.row_floats;
-        sorted_boxes[static_cast<long long>(b) * p.n_max + i] = make_float4(r[0], r[1], r[2], r[3]);
-        sorted_cls[static_cast<long long>(b) * p.n_max + i] = p.per_class ? __float2int_rz(r[5]) : 0;
-        order[static_cast<long long>(b) * p.n_max + i] = src;
-    }
+    for (int i = tid; i < m; i += kSortThreads) emit(i, keys[i]);
 }
 
 // ---- suppression predicates ---------------------------------------------------------------------------
@@ -433,7 +503,8 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
         DH_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsMaxN * 8));
         attr_done = true;
     }
-    nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, sboxes, scls, order, ncand);
+    nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, h->nms_sort == 1 ? 1 : 0, sboxes, scls, order,
+                                                                                    ncand);
     DH_CUDA(cudaGetLastError());
     const size_t cap_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
     // a small output cap ends the sweep after a few blocks: evaluate suppression lazily, one CTA per image

@@ -54,6 +54,7 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_FCOS_SELECT 7 /* dh_fcos_detect candidate selection (every choice is exact and bit-identical). 0 (default): in logit space when it can -- estimate + one streaming pass + per-level finish for pre_nms_topk <= 1024, else a thread-block cluster per long level for small batches; 1: always score every pair, one CTA per (image, level); 2: logit space, one CTA per (image, level); 3: logit space, always clusters; 4: logit space, the streaming pre-select whenever it fits */
 #define DH_OPT_FUSED_CHUNKS_PER_CTA 8 /* fused loss scheduler: aim at this many image-aligned chunks per persistent CTA (default 12; a chunk is always 4..8 tiles of 256 rows) */
 #define DH_OPT_ENCODE_MIN_CHUNK 9 /* encoders: smallest scheduler chunk in tiles (default 2) */
+#define DH_OPT_NMS_SORT 10 /* score sort ahead of the NMS. 0 (default): bucket sort in shared memory, bitonic network when the scores pile onto few buckets; 1: always the bitonic network (A/B checks) */
 int dh_set_option(dh_handle_t h, int option, int value);
 /* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in
  * {stage GT + records, candidates + buffer recycle, emit rows, hand-off to TMA, drain}, out8[5] = tiles. */

@@ -19,14 +19,17 @@ def _dh():
     return densehead
 
 
-@pytest.fixture(autouse=True, params=["lazy", "mask+sweep"])
+@pytest.fixture(autouse=True, params=["lazy", "mask+sweep", "mask+sweep, bitonic sort"])
 def nms_kernel(request):
     """Every test runs against both NMS implementations (DH_OPT_NMS_KERNEL): the lazy one-CTA-per-image sweep and
-    the all-SM mask matrix + block sweep; they must agree bit for bit with the oracle."""
+    the all-SM mask matrix + block sweep, and against both score sorts (DH_OPT_NMS_SORT: bucket sort, bitonic network);
+    they must agree bit for bit with the oracle."""
     dh = _dh()
     dh.set_option(0, 6, 1 if request.param == "lazy" else 2)
+    dh.set_option(0, 10, 1 if "bitonic" in request.param else 0)
     yield request.param
     dh.set_option(0, 6, 0)
+    dh.set_option(0, 10, 0)
 
 
 def test_prediction_to_corners_golden(golden):
