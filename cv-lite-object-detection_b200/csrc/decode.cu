@@ -954,12 +954,9 @@ __device__ __forceinline__ FcosSource fcos_source(const FcosSelectArgs& a, int b
 __device__ __forceinline__ bool fcos_source_vec(const FcosSource& src) {  // uniform over everything that works on the segment
     return (reinterpret_cast<uintptr_t>(src.head) & 15u) == 0 && (((src.n / src.num_classes) * src.ch) & 3) == 0;
 }
-// `only_flagged` (optional, [B*L]): segments whose entry is 0 are skipped (they were done by the pre-select path).
-__global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs a, float* __restrict__ cand /*[B, L*k, 6]*/,
-                                                                  const int* __restrict__ only_flagged) {
+__global__ void __launch_bounds__(kSelThreads) fcos_select_kernel(FcosSelectArgs a, float* __restrict__ cand /*[B, L*k, 6]*/) {
     __shared__ SelShared sh;
     const int b = blockIdx.x, l = blockIdx.y;  // level-major dispatch: the 64 x 512 K-logit level-0 CTAs start first, the rest fill in
-    if (only_flagged && !only_flagged[b * a.n_levels + l]) return;
     const FcosSource src = fcos_source(a, b, l, cand);
     if (a.allow_logit_space) {
         if (fcos_source_vec(src) ? fcos_select_logit_space<true>(sh, src, a.k_slots, a.min_score, a.inclusive)
@@ -1132,11 +1129,11 @@ static int grid_for(long long threads_needed, int block, int sm_count) {
 // with the same machinery as above -- histogram, boundary bin, tie window ranked exactly -- marks the winners in a
 // shared-memory bitmap over the pair indices and emits them in index order by a popcount scan.  A segment whose
 // candidates do not provably contain its top k (list overflow, fewer than k candidates above an estimate that is not the
-// threshold, a tie window reaching down to the estimate's bin or too large for the list) is flagged, and
-// fcos_select_kernel redoes the flagged segments exactly as before.
+// threshold, a tie window reaching down to the estimate's bin or too large for the list) is redone on the spot by the
+// same CTA with the one-CTA selector above.
 constexpr int kPreChunkItems = 2048;    // load items per CTA of the streaming pass
 constexpr int kPreThreads = 256;
-constexpr int kPreStage = 1024;         // candidates a chunk can stage (more: the segment is flagged)
+constexpr int kPreStage = 1024;         // candidates a chunk stages in shared memory (more go to the list one by one)
 constexpr int kPreSampleStride = 16;
 constexpr int kPreBitmapWords = 16384;  // 512 K (location, class) pairs per segment
 
@@ -1144,7 +1141,6 @@ struct PreselWork {
     float* x_est;    // [B*L] logit bound of the candidates
     int* est_bin;    // [B*L] its histogram bin; -1: the bound is the threshold itself (every passing entry is a candidate)
     unsigned* count; // [B*L] candidates appended
-    int* flag;       // [B*L] 1: the segment has to be redone by fcos_select_kernel
     float* cand_x;   // [B*L, cap]
     int* cand_pair;  // [B*L, cap]
     int cap, bitmap_words;  // list capacity per segment; words of the finish kernel's shared-memory bitmap
@@ -1155,7 +1151,7 @@ __global__ void __launch_bounds__(kSelThreads) fcos_presel_estimate_kernel(const
     __shared__ SelShared sh;
     const int b = blockIdx.x, l = blockIdx.y, seg = b * a.n_levels + l, tid = threadIdx.x;
     const FcosSource src = fcos_source(a, b, l, nullptr);
-    if (tid == 0) w.count[seg] = 0u, w.flag[seg] = 0;
+    if (tid == 0) w.count[seg] = 0u;
     const int k = min(a.k_slots, max(src.n, 0));
     LogitItems<true> it;
     it.init(src, a.min_score, a.inclusive);
@@ -1203,8 +1199,17 @@ __device__ __forceinline__ void presel_collect_chunk(const FcosSource& src, cons
         logit_scan<kVec, U>(
             it, q, i_hi, x_est, INFINITY, [&](int u) { return base + u * kPreThreads + tid; },
             [&](int u, int e, float x) {
+                const int pair = it.pair_index(base + u * kPreThreads + tid, q[u], e);
                 const unsigned slot = atomicAdd(st_n, 1u);
-                if (slot < kPreStage) st_x[slot] = x, st_pair[slot] = it.pair_index(base + u * kPreThreads + tid, q[u], e);
+                if (slot < kPreStage) {
+                    st_x[slot] = x, st_pair[slot] = pair;
+                } else {  // the stage is full (a dense chunk): append to the segment's list directly
+                    const unsigned g = atomicAdd(&w.count[seg], 1u);
+                    if (g < static_cast<unsigned>(w.cap)) {
+                        w.cand_x[static_cast<long long>(seg) * w.cap + g] = x;
+                        w.cand_pair[static_cast<long long>(seg) * w.cap + g] = pair;
+                    }
+                }
             },
             [](int, int, float) {});
     }
@@ -1225,12 +1230,8 @@ __global__ void __launch_bounds__(kPreThreads) fcos_presel_collect_kernel(const 
     if (fcos_source_vec(src)) presel_collect_chunk<true>(src, a, w, seg, chunk, st_x, st_pair, &st_n);
     else presel_collect_chunk<false>(src, a, w, seg, chunk, st_x, st_pair, &st_n);
     __syncthreads();
-    const unsigned n = st_n;
+    const unsigned n = min(st_n, static_cast<unsigned>(kPreStage));
     if (n == 0u) return;
-    if (n > kPreStage) {  // more candidates in one chunk than the stage holds: the estimate was useless here
-        if (tid == 0) w.flag[seg] = 1;
-        return;
-    }
     if (tid == 0) st_base = atomicAdd(&w.count[seg], n);
     __syncthreads();
     const unsigned base = st_base;
@@ -1257,10 +1258,8 @@ __global__ void __launch_bounds__(kSelThreads) fcos_presel_finish_kernel(const _
     const unsigned count = w.count[seg];
     const int est_bin = w.est_bin[seg];
     const int words = (src.n + 31) >> 5;
-    if (w.flag[seg] || count > static_cast<unsigned>(w.cap) || words > w.bitmap_words) {
-        if (tid == 0) w.flag[seg] = 1;
-        return;
-    }
+    const bool done = [&]() -> bool {  // false: the candidates do not provably hold the segment's top k
+    if (count > static_cast<unsigned>(w.cap) || words > w.bitmap_words) return false;
     LogitItems<false> it;  // only the threshold test and the bin map are used here
     it.init(src, a.min_score, a.inclusive);
     const int n = static_cast<int>(count);
@@ -1284,10 +1283,7 @@ __global__ void __launch_bounds__(kSelThreads) fcos_presel_finish_kernel(const _
     bool take_all = false;
     int lo_bin = 0, hi_bin = 4095;
     if (n_pass < static_cast<unsigned>(k)) {
-        if (est_bin >= 0) {  // fewer than k candidates, and they are not everything that passes
-            if (tid == 0) w.flag[seg] = 1;
-            return;
-        }
+        if (est_bin >= 0) return false;  // fewer than k candidates, and they are not everything that passes
         take_all = true;
     } else if (k > 0) {
         find_boundary<kSelThreads>(sh, 4096, static_cast<unsigned>(k), tid);
@@ -1300,10 +1296,7 @@ __global__ void __launch_bounds__(kSelThreads) fcos_presel_finish_kernel(const _
             sh.need = need;
         }
         __syncthreads();
-        if (!sh.wtot[1][0]) {
-            if (tid == 0) w.flag[seg] = 1;
-            return;
-        }
+        if (!sh.wtot[1][0]) return false;
         lo_bin = static_cast<int>(sh.wtot[1][1]), hi_bin = static_cast<int>(sh.wtot[1][2]);
         for (int i = tid; i < n; i += kSelThreads) {
             if (!ckey[i]) continue;
@@ -1364,6 +1357,15 @@ __global__ void __launch_bounds__(kSelThreads) fcos_presel_finish_kernel(const _
     }
     const unsigned filled = min(static_cast<unsigned>(k), total);
     for (int r = filled + tid; r < a.k_slots; r += kSelThreads) src.pad(r);
+    return true;
+    }();
+    if (done) return;
+    // redo the segment with the one-CTA selector
+    __syncthreads();
+    if (fcos_source_vec(src) ? fcos_select_logit_space<true>(sh, src, a.k_slots, a.min_score, a.inclusive)
+                             : fcos_select_logit_space<false>(sh, src, a.k_slots, a.min_score, a.inclusive))
+        return;
+    select_core(sh, src, a.k_slots, a.min_score, a.inclusive);
 }
 
 // Host-side plan: how many CTAs share each level's segment and which clusters they sit in.  A segment gets one CTA
@@ -1467,7 +1469,7 @@ int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batc
         char* base = static_cast<char*>(scratch(h, head_bytes + static_cast<size_t>(segs) * w.cap * 8));
         if (!base) return DH_ERR_CUDA;
         w.x_est = reinterpret_cast<float*>(base), w.est_bin = reinterpret_cast<int*>(base) + segs;
-        w.count = reinterpret_cast<unsigned*>(base) + 2 * segs, w.flag = reinterpret_cast<int*>(base) + 3 * segs;
+        w.count = reinterpret_cast<unsigned*>(base) + 2 * segs;
         w.cand_x = reinterpret_cast<float*>(base + head_bytes);
         w.cand_pair = reinterpret_cast<int*>(base + head_bytes) + static_cast<size_t>(segs) * w.cap;
         PreselChunks ct;
@@ -1488,12 +1490,11 @@ int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batc
             configured_dyn = dyn;
         }
         fcos_presel_finish_kernel<<<grid, kSelThreads, dyn, st>>>(a, w, cand);
-        fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand, w.flag);
         DH_CUDA(cudaGetLastError());
-        launched = 4;
+        launched = 3;
     } else {
         dim3 grid(batch, n_levels);
-        fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand, nullptr);
+        fcos_select_kernel<<<grid, kSelThreads, 0, st>>>(a, cand);
         DH_CUDA(cudaGetLastError());
     }
     h->launches += launched;
