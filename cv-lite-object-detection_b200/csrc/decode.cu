@@ -1131,8 +1131,14 @@ static int grid_for(long long threads_needed, int block, int sm_count) {
 // candidates do not provably contain its top k (list overflow, fewer than k candidates above an estimate that is not the
 // threshold, a tie window reaching down to the estimate's bin or too large for the list) is redone on the spot by the
 // same CTA with the one-CTA selector above.
-constexpr int kPreChunkItems = 2048;    // load items per CTA of the streaming pass
-constexpr int kPreThreads = 256;
+#ifndef DH_PRE_CHUNK_ITEMS
+#define DH_PRE_CHUNK_ITEMS 1024
+#endif
+#ifndef DH_PRE_THREADS
+#define DH_PRE_THREADS 128
+#endif
+constexpr int kPreChunkItems = DH_PRE_CHUNK_ITEMS;  // load items per CTA of the streaming pass
+constexpr int kPreThreads = DH_PRE_THREADS;
 constexpr int kPreStage = 1024;         // candidates a chunk stages in shared memory (more go to the list one by one)
 constexpr int kPreSampleStride = 16;
 constexpr int kPreBitmapWords = 16384;  // 512 K (location, class) pairs per segment
@@ -1484,10 +1490,9 @@ int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batc
         fcos_presel_estimate_kernel<<<grid, kSelThreads, 0, st>>>(a, w);
         if (ct.first[n_levels] > 0) fcos_presel_collect_kernel<<<ct.first[n_levels], kPreThreads, 0, st>>>(a, ct, batch, w);
         const size_t dyn = (static_cast<size_t>(3) * w.cap + w.bitmap_words) * 4;
-        static size_t configured_dyn = 0;  // grows only; a repeated call with the same value is skipped
-        if (dyn > configured_dyn) {
-            DH_CUDA(cudaFuncSetAttribute(fcos_presel_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-            configured_dyn = dyn;
+        DH_ONCE_PER_DEVICE(h) {  // the largest it can be: cap candidates x 3 words + the whole bitmap
+            DH_CUDA(cudaFuncSetAttribute(fcos_presel_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (3 * 4096 + kPreBitmapWords) * 4));
         }
         fcos_presel_finish_kernel<<<grid, kSelThreads, dyn, st>>>(a, w, cand);
         DH_CUDA(cudaGetLastError());
@@ -1605,10 +1610,8 @@ int dh_retina_decode(dh_handle_t h, const float* const* pred_levels, int batch, 
         }
         a.tile_begin[n_levels] = tiles;
         if (tiles == 0) return DH_OK;
-        static bool attr_done = false;
-        if (!attr_done) {
+        DH_ONCE_PER_DEVICE(h) {
             DH_CUDA(cudaFuncSetAttribute(retina_decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
         }
         int per_sm = 1;
         DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, retina_decode_stream_kernel, kDecWarps * 32, stream_smem));

@@ -51,6 +51,12 @@ unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st);
                                    __FILE__, __LINE__);                                            \
     } while (0)
 
+// Function attributes (the opt-in to more than 48 KB of dynamic shared memory) are per device: a block that sets them runs
+// once for every device a handle is created on, not once per process.
+//   DH_ONCE_PER_DEVICE(h) { DH_CUDA(cudaFuncSetAttribute(...)); }
+#define DH_ONCE_PER_DEVICE(h) \
+    for (static unsigned long long dh_once_mask_ = 0ull; !((dh_once_mask_ >> ((h)->device & 63)) & 1ull); dh_once_mask_ |= 1ull << ((h)->device & 63))
+
 struct DeviceGuard {
     int prev;
     bool ok;

@@ -48,10 +48,8 @@ static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, cons
     if (lay.total > 227 * 1024)
         return set_error(DH_ERR_CAPACITY, "%s: tile of %d bytes needs %d bytes of shared memory", who, a.tile_buf_bytes,
                          lay.total);
-    static bool attr_done = false;  // per template instantiation
-    if (!attr_done) {
+    DH_ONCE_PER_DEVICE(h) {  // (and per template instantiation)
         DH_CUDA(cudaFuncSetAttribute(encode_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     int per_sm = 1;  // resident CTAs per SM (registers and shared memory both count)
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel<P>, DH_THREADS, lay.total));

@@ -25,11 +25,9 @@ static int launch_loss(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, flo
     const LossSmemLayout lay = loss_smem_layout<P, kFused>(a.tile_buf_bytes, a.tt.rows_per_tile, a.box_cap);
     if (lay.total > 227 * 1024)
         return set_error(DH_ERR_CAPACITY, "%s: needs %d bytes of shared memory", who, lay.total);
-    static bool attr_done = false;
-    if (!attr_done) {
+    DH_ONCE_PER_DEVICE(h) {
         DH_CUDA(cudaFuncSetAttribute(loss_kernel<P, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DH_CUDA(cudaFuncSetAttribute(loss_kernel<P, kFused, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     int per_sm = 1;  // resident CTAs per SM (registers and shared memory both count)
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_kernel<P, kFused>, DH_THREADS, lay.total));
@@ -106,10 +104,8 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
                           const char* who) {
     const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
     const FusedSmemLayout lay = fused_smem_layout<P>(a.box_cap);
-    static bool attr_done = false;
-    if (!attr_done) {
+    DH_ONCE_PER_DEVICE(h) {
         DH_CUDA(cudaFuncSetAttribute(fused_loss_kernel<P, kCls, kGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     int per_sm = 1;
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kCls, kGrad>, DH_THREADS, lay.total));

@@ -498,10 +498,8 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     int* order = reinterpret_cast<int*>(sc + off_ord);
     int* ncand = reinterpret_cast<int*>(sc + off_cnt);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(sc + off_mask);
-    static bool attr_done = false;
-    if (!attr_done) {
+    DH_ONCE_PER_DEVICE(h) {
         DH_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsMaxN * 8));
-        attr_done = true;
     }
     nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, h->nms_sort == 1 ? 1 : 0, sboxes, scls, order,
                                                                                     ncand);
@@ -521,10 +519,8 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     const int staged = words <= kSweepStageWords ? 1 : 0;
     const size_t stage_bytes = staged ? static_cast<size_t>(kSweepDepth) * 64 * words * 8 : 0;  // [depth][words][64] words
     const size_t sweep_smem = stage_bytes + ((p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0);
-    static bool sweep_attr_done = false;
-    if (!sweep_attr_done) {
+    DH_ONCE_PER_DEVICE(h) {
         DH_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        sweep_attr_done = true;
     }
     nms_sweep_kernel<<<batch, kSweepThreads, sweep_smem, st>>>(mask, scls, order, ncand, p, words, staged, keep, n_keep);
     DH_CUDA(cudaGetLastError());

@@ -233,6 +233,25 @@ def test_fcos_select_cluster_small_batches_and_levels():
                 assert np.array_equal(a, b)
 
 
+def test_fcos_select_large_topk_uses_clusters_by_default():
+    """pre_nms_topk above 1024 does not fit the streaming pre-select: the default falls back to the cluster selector
+    (small batch) -- same candidates and detections as scoring every pair."""
+    dh = _dh()
+    heads = synth.fcos_predictions(2, 640, 80, synth.seed_for(4, 92))
+    for h in heads:
+        h[..., 5:] = h[..., 5:] * 2.5 + 6.9
+    out = []
+    for mode in (1, 0, 4):
+        dh.set_option(0, 7, mode)
+        try:
+            out.append([t.cpu().numpy() for t in dh.fcos.detect_batch(heads, 80, [640, 640], pre_nms_topk=3000, with_candidates=True)])
+        finally:
+            dh.set_option(0, 7, 0)
+    for other in out[1:]:
+        for a, b in zip(other, out[0]):
+            assert np.array_equal(a, b)
+
+
 def test_compute_iou_and_bboxes_iou(golden):
     dh = _dh()
     k = golden("kat")
