@@ -132,6 +132,30 @@ __device__ __forceinline__ void stream_pair_g2(float x0, float x1, f32x2& acc, f
     }
 }
 
+// The same two elements when both logits are <= -0.7, i.e. e = exp(x) <= 0.4966 -- all but a few of the label == 0
+// logits of a detector (prior -4.6): sigmoid(x)^2 softplus(x) / ln 2 = e^3 ln(1 + e) / (e (1 + e)^2 ln 2) = e^3 P(e) with a
+// degree-7 polynomial (least-squares fit of the relative error on Chebyshev nodes of [0, 0.5]; max relative error
+// 6.4e-7 in float32 Horner form).  1 MUFU + 5.5 packed FMA-pipe instructions per element instead of 2 MUFU + ~12.
+constexpr float kSmallLogit = -0.7f;
+__device__ __forceinline__ void stream_pair_g2_small(float x0, float x1, f32x2& acc) {
+    float u0, u1;
+    unpack2(mul2(pack2(x0, x1), pack2(kLog2e, kLog2e)), u0, u1);
+    const f32x2 e = pack2(ex2_fast(u0), ex2_fast(u1));  // exp(x)
+    f32x2 p = fma2(pack2(-3.1173593997955322f, -3.1173593997955322f), e, pack2(8.865461349487305f, 8.865461349487305f));
+    p = fma2(p, e, pack2(-12.291608810424805f, -12.291608810424805f));
+    p = fma2(p, e, pack2(11.74155330657959f, 11.74155330657959f));
+    p = fma2(p, e, pack2(-9.157456398010254f, -9.157456398010254f));
+    p = fma2(p, e, pack2(6.245364189147949f, 6.245364189147949f));
+    p = fma2(p, e, pack2(-3.606579303741455f, -3.606579303741455f));
+    p = fma2(p, e, pack2(1.4426943063735962f, 1.4426943063735962f));
+    acc = fma2(mul2(mul2(e, e), e), p, acc);
+}
+// smallest of the four values' bit patterns as unsigned integers: >= bits(kSmallLogit) exactly when every value is
+// <= kSmallLogit (negative floats order by magnitude as unsigned integers; anything with the sign bit clear is smaller)
+__device__ __forceinline__ unsigned min_bits4(const float4& x) {
+    return min(min(__float_as_uint(x.x), __float_as_uint(x.y)), min(__float_as_uint(x.z), __float_as_uint(x.w)));
+}
+
 // smooth-L1(0, sigmoid(x)): the centerness term of an all-zero row (FCOS/fcos.py:483-486)
 __device__ __forceinline__ float cen_l1_zero(float x, float delta) {
     const float s = sigmoid_f(x);
@@ -187,16 +211,49 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
     float4* __restrict__ gptr = reinterpret_cast<float4*>(gout) + lane;
     const int n_mine = (nrows * vpr - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
     int k = 0;
+    if constexpr (kCls == 1 && !kGrad) {
+        // gamma == 2 forward: when every class logit of the warp's batch is <= kSmallLogit (one vote per 128 U elements;
+        // 96 % of the batches at logits ~ N(-4.6, 1)) the batch takes the polynomial form of the term
+        const unsigned small_bits = __float_as_uint(kSmallLogit);
+        const int n_all = (nrows * vpr) >> 5;  // items EVERY lane has: the vote below needs a warp-uniform trip count
 #pragma unroll 1
-    for (; k + U <= n_mine; k += U, ptr += 32 * U, gptr += 32 * U) {  // U independent loads in flight, no predicates
-        float4 x[U];
+        for (; k + U <= n_all; k += U, ptr += 32 * U) {
+            float4 x[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
+            for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
+            unsigned reg_items = 0u, lowest = 0xFFFFFFFFu;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            stream_vec_item<kCls, kGrad>(x[u], c4 == 0, gamma, gscale, a, gptr + 32 * u);
-            c4 += step;
-            if (c4 >= vpr) c4 -= vpr;
+            for (int u = 0; u < U; ++u) {
+                if (c4 == 0) reg_items |= 1u << u;  // float4 0 of a row = the 4 regression channels
+                else lowest = min(lowest, min_bits4(x[u]));
+                c4 += step;
+                if (c4 >= vpr) c4 -= vpr;
+            }
+            if (__all_sync(0xffffffffu, lowest >= small_bits)) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (!((reg_items >> u) & 1u)) {
+                        stream_pair_g2_small(x[u].x, x[u].y, a.p0);
+                        stream_pair_g2_small(x[u].z, x[u].w, a.p1);
+                    }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) stream_vec_item<kCls, kGrad>(x[u], (reg_items >> u) & 1u, gamma, gscale, a, nullptr);
+            }
+        }
+        gptr += 32 * k;
+    } else {
+#pragma unroll 1
+        for (; k + U <= n_mine; k += U, ptr += 32 * U, gptr += 32 * U) {  // U independent loads in flight, no predicates
+            float4 x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                stream_vec_item<kCls, kGrad>(x[u], c4 == 0, gamma, gscale, a, gptr + 32 * u);
+                c4 += step;
+                if (c4 >= vpr) c4 -= vpr;
+            }
         }
     }
 #pragma unroll 1

@@ -57,7 +57,9 @@ def test_retina_gradients_fused_and_unfused():
     lab, _ = dh.retinanet.format_data_batch(boxes, nbox, [320, 320], C, [320, 320])
     pi, tot, pairs, grads = dh.retinanet.encode_loss_batch(boxes, nbox, [320, 320], C, [320, 320], pred, weights=(W[0], W[1]))
     pi0, tot0, _ = dh.retinanet.encode_loss_batch(boxes, nbox, [320, 320], C, [320, 320], pred)
-    assert torch.equal(pi, pi0) and torch.equal(tot, tot0)
+    # the forward-only gamma == 2 kernel evaluates the label-0 term of small logits as e^3 P(e) (6.4e-7 relative), the
+    # gradient kernel through sigmoid and softplus: the loss values agree to a few 1e-7, not bit for bit
+    assert torch.allclose(pi, pi0, rtol=2e-6, atol=0) and torch.allclose(tot, tot0, rtol=2e-6, atol=0)
     upi, utot, ugrads = dh.retinanet.loss_batch(lab, pred, weights=(W[0], W[1]))
     for l in range(5):
         want = O.dense_loss_grad(lab[l].cpu().numpy(), pred[l], weights=(W[0], W[1], 0.0), reg_ch=4, cen_mode=0, pos_rule="gt0")
