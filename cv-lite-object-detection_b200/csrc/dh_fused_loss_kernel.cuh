@@ -221,24 +221,25 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
             float4 x[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
-            unsigned reg_items = 0u, lowest = 0xFFFFFFFFu;
+            unsigned lowest = 0xFFFFFFFFu;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (c4 == 0) reg_items |= 1u << u;  // float4 0 of a row = the 4 regression channels
-                else lowest = min(lowest, min_bits4(x[u]));
+                // float4 0 of a row = the 4 regression channels: as -inf they add exactly 0 in either form (e = 0), which
+                // is cheaper than branching around them
+                if (c4 == 0) x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                lowest = min(lowest, min_bits4(x[u]));
                 c4 += step;
                 if (c4 >= vpr) c4 -= vpr;
             }
             if (__all_sync(0xffffffffu, lowest >= small_bits)) {
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (!((reg_items >> u) & 1u)) {
-                        stream_pair_g2_small(x[u].x, x[u].y, a.p0);
-                        stream_pair_g2_small(x[u].z, x[u].w, a.p1);
-                    }
+                for (int u = 0; u < U; ++u) {
+                    stream_pair_g2_small(x[u].x, x[u].y, a.p0);
+                    stream_pair_g2_small(x[u].z, x[u].w, a.p1);
+                }
             } else {
 #pragma unroll
-                for (int u = 0; u < U; ++u) stream_vec_item<kCls, kGrad>(x[u], (reg_items >> u) & 1u, gamma, gscale, a, nullptr);
+                for (int u = 0; u < U; ++u) stream_vec_item<kCls, kGrad>(x[u], false, gamma, gscale, a, nullptr);
             }
         }
         gptr += 32 * k;

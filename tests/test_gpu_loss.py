@@ -212,3 +212,39 @@ def test_retina_fused_loss_row_lengths(classes):
     assert_close(fpi.cpu().numpy(), upi.cpu().numpy(), 2e-6, what="C=%d" % classes)
     for a, b in zip(fg, ug):
         assert torch.allclose(a, b, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("classes", [80, 20, 12])
+@pytest.mark.parametrize("logits", ["prior N(-4.6, 1)", "wide N(-2, 3)", "all below -0.7", "one above -0.7 per image"])
+def test_retina_fused_forward_small_logit_form(logits, classes):
+    """The forward gamma == 2 kernel evaluates the label-0 focal term of a warp batch whose logits are all <= -0.7 as
+    e^3 P(e) and any other batch through sigmoid and softplus: every mix of the two must agree with the loss over
+    materialised targets (which never uses the polynomial) and with the float64 oracle to the 1e-5 bar."""
+    dh = _dh()
+    B = 3
+    boxes, nbox = synth.make_boxes(B, 320, 30, classes, 8.0, 250.0, synth.seed_for(5, 94))
+    pred = synth.retina_predictions(B, 320, classes, 10, logit_sigma=1.0)
+    rng = np.random.default_rng(12)
+    for p in pred:
+        if logits.startswith("wide"):
+            p[..., 4:] = rng.normal(-2.0, 3.0, size=p[..., 4:].shape).astype(np.float32)
+        elif logits.startswith("all below"):
+            p[..., 4:] = np.minimum(p[..., 4:], np.float32(-0.7))
+        elif logits.startswith("one above"):
+            p[..., 4:] = np.minimum(p[..., 4:], np.float32(-0.7))
+            p[:, 0, 0, 0, 4] = 3.0
+    pred[0][0, 1, 2, 3, 5] = np.float32(-0.7)          # exactly the switch point
+    pred[0][0, 1, 2, 3, 6] = np.nextafter(np.float32(-0.7), np.float32(0))
+    lab, _ = dh.retinanet.format_data_batch(boxes, nbox, [320, 320], classes, [320, 320])
+    upi, utot = dh.retinanet.loss_batch(lab, pred)[:2]
+    fpi, ftot = dh.retinanet.encode_loss_batch(boxes, nbox, [320, 320], classes, [320, 320], pred)[:2]
+    assert_close(fpi.cpu().numpy(), upi.cpu().numpy(), 2e-6, what=logits)
+    want = np.zeros(2)
+    for l in range(5):
+        y = lab[l].cpu().numpy().astype(np.float64)
+        x = pred[l].astype(np.float64)
+        s = 1.0 / (1.0 + np.exp(-x[..., 4:]))
+        sp_pos, sp_neg = np.logaddexp(0.0, -x[..., 4:]), np.logaddexp(0.0, x[..., 4:])
+        yl = y[..., 4:]
+        want[0] += float(np.sum(yl * 0.25 * (1 - s) ** 2 * sp_pos + (1 - yl) * 0.75 * s ** 2 * sp_neg))
+    assert_close(ftot[:1].cpu().numpy(), want[:1], RTOL, what=logits + " vs float64")
