@@ -150,6 +150,30 @@ __device__ __forceinline__ void stream_pair_g2_small(float x0, float x1, f32x2& 
     p = fma2(p, e, pack2(1.4426943063735962f, 1.4426943063735962f));
     acc = fma2(mul2(mul2(e, e), e), p, acc);
 }
+// ... and its derivative, in natural units before the caller's scale: d/dx [sigmoid^2 softplus] = e^3 Q(e), a second
+// degree-7 fit (max relative error 2.0e-6 in float32 Horner form over [0, 0.5])
+__device__ __forceinline__ void stream_pair_g2_small_grad(float x0, float x1, f32x2& acc, float& d0, float& d1) {
+    float u0, u1;
+    unpack2(mul2(pack2(x0, x1), pack2(kLog2e, kLog2e)), u0, u1);
+    const f32x2 e = pack2(ex2_fast(u0), ex2_fast(u1));  // exp(x)
+    f32x2 p = fma2(pack2(-3.1173593997955322f, -3.1173593997955322f), e, pack2(8.865461349487305f, 8.865461349487305f));
+    f32x2 q = fma2(pack2(-17.49591827392578f, -17.49591827392578f), e, pack2(48.32270050048828f, 48.32270050048828f));
+    p = fma2(p, e, pack2(-12.291608810424805f, -12.291608810424805f));
+    q = fma2(q, e, pack2(-63.491676330566406f, -63.491676330566406f));
+    p = fma2(p, e, pack2(11.74155330657959f, 11.74155330657959f));
+    q = fma2(q, e, pack2(55.418338775634766f, 55.418338775634766f));
+    p = fma2(p, e, pack2(-9.157456398010254f, -9.157456398010254f));
+    q = fma2(q, e, pack2(-37.818424224853516f, -37.818424224853516f));
+    p = fma2(p, e, pack2(6.245364189147949f, 6.245364189147949f));
+    q = fma2(q, e, pack2(21.622814178466797f, 21.622814178466797f));
+    p = fma2(p, e, pack2(-3.606579303741455f, -3.606579303741455f));
+    q = fma2(q, e, pack2(-9.998870849609375f, -9.998870849609375f));
+    p = fma2(p, e, pack2(1.4426943063735962f, 1.4426943063735962f));
+    q = fma2(q, e, pack2(2.999994993209839f, 2.999994993209839f));
+    const f32x2 e3 = mul2(mul2(e, e), e);
+    acc = fma2(e3, p, acc);
+    unpack2(mul2(e3, q), d0, d1);
+}
 // smallest of the four values' bit patterns as unsigned integers: >= bits(kSmallLogit) exactly when every value is
 // <= kSmallLogit (negative floats order by magnitude as unsigned integers; anything with the sign bit clear is smaller)
 __device__ __forceinline__ unsigned min_bits4(const float4& x) {
@@ -211,13 +235,13 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
     float4* __restrict__ gptr = reinterpret_cast<float4*>(gout) + lane;
     const int n_mine = (nrows * vpr - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
     int k = 0;
-    if constexpr (kCls == 1 && !kGrad) {
-        // gamma == 2 forward: when every class logit of the warp's batch is <= kSmallLogit (one vote per 128 U elements;
-        // 96 % of the batches at logits ~ N(-4.6, 1)) the batch takes the polynomial form of the term
+    if constexpr (kCls == 1) {
+        // gamma == 2: when every class logit of the warp's batch is <= kSmallLogit (one vote per 128 U elements; 96 % of the
+        // batches at logits ~ N(-4.6, 1)) the batch takes the polynomial form of the term (and of its derivative)
         const unsigned small_bits = __float_as_uint(kSmallLogit);
         const int n_all = (nrows * vpr) >> 5;  // items EVERY lane has: the vote below needs a warp-uniform trip count
 #pragma unroll 1
-        for (; k + U <= n_all; k += U, ptr += 32 * U) {
+        for (; k + U <= n_all; k += U, ptr += 32 * U, gptr += 32 * U) {
             float4 x[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
@@ -234,15 +258,21 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
             if (__all_sync(0xffffffffu, lowest >= small_bits)) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    stream_pair_g2_small(x[u].x, x[u].y, a.p0);
-                    stream_pair_g2_small(x[u].z, x[u].w, a.p1);
+                    if constexpr (kGrad) {
+                        float4 d;
+                        stream_pair_g2_small_grad(x[u].x, x[u].y, a.p0, d.x, d.y);
+                        stream_pair_g2_small_grad(x[u].z, x[u].w, a.p1, d.z, d.w);
+                        __stcs(gptr + 32 * u, make_float4(d.x * gscale, d.y * gscale, d.z * gscale, d.w * gscale));
+                    } else {
+                        stream_pair_g2_small(x[u].x, x[u].y, a.p0);
+                        stream_pair_g2_small(x[u].z, x[u].w, a.p1);
+                    }
                 }
             } else {
 #pragma unroll
-                for (int u = 0; u < U; ++u) stream_vec_item<kCls, kGrad>(x[u], false, gamma, gscale, a, nullptr);
+                for (int u = 0; u < U; ++u) stream_vec_item<kCls, kGrad>(x[u], false, gamma, gscale, a, gptr + 32 * u);
             }
         }
-        gptr += 32 * k;
     } else {
 #pragma unroll 1
         for (; k + U <= n_mine; k += U, ptr += 32 * U, gptr += 32 * U) {  // U independent loads in flight, no predicates
