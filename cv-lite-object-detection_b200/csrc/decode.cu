@@ -7,9 +7,12 @@
 //   dh_retina_decode           RetinaNet.image_detections up to the threshold (retinanet_module.py:487-520):
 //                              dets [B,N,6] = (y1, x1, y2, x2, max score, argmax label), level > anchor > row-major
 //   dh_select_topk             per-segment (= per pyramid level) score threshold + exact top-k, stable in index
-//                              order (radix select: 12+12+8 bit histograms in shared memory)
+//                              order (linear 4096-bin histogram, boundary bin ranked exactly, ordered compaction)
+//   launch_fcos_select         (dh_fcos_detect) the same selection fused with the FCOS decode, on raw logits: three
+//                              exact, bit-identical variants -- estimate + one all-SM streaming pass + per-segment
+//                              finish, a thread-block cluster per long segment, one CTA per segment
 //
-// These kernels are HBM-bound on one read of the head output; thread mapping is one thread per output
+// These kernels are HBM-bound on one read of the head output; the decode kernels map one thread to an output
 // row with the class loop vectorised where the row is 16-byte aligned.
 #include <cooperative_groups.h>
 
