@@ -1429,6 +1429,17 @@ static FcosClusterPlan plan_fcos_clusters(const long long* values, int n_levels)
     return plan;
 }
 
+// chunk table of the streaming pre-select: `items[l]` load items per segment of level l, one CTA per kPreChunkItems
+static PreselChunks plan_presel_chunks(const long long* items, int n_levels, int batch) {
+    PreselChunks ct;
+    memset(&ct, 0, sizeof(ct));
+    for (int l = 0; l < n_levels; ++l) {
+        ct.per_seg[l] = static_cast<int>((items[l] + kPreChunkItems - 1) / kPreChunkItems);
+        ct.first[l + 1] = ct.first[l] + ct.per_seg[l] * batch;
+    }
+    return ct;
+}
+
 int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batch, int pad_h, int pad_w, int n_levels,
                        const int32_t* strides, int num_classes, int center, int k, float min_score, int inclusive, float* cand,
                        cudaStream_t st) {
@@ -1481,14 +1492,12 @@ int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batc
         w.count = reinterpret_cast<unsigned*>(base) + 2 * segs;
         w.cand_x = reinterpret_cast<float*>(base + head_bytes);
         w.cand_pair = reinterpret_cast<int*>(base + head_bytes) + static_cast<size_t>(segs) * w.cap;
-        PreselChunks ct;
-        memset(&ct, 0, sizeof(ct));
+        long long items[DH_MAX_LEVELS];
         for (int l = 0; l < n_levels; ++l) {
             const bool vec = (reinterpret_cast<uintptr_t>(a.head[l]) & 15u) == 0 && (values[l] & 3) == 0;  // fcos_source_vec()
-            const long long items = vec ? values[l] >> 2 : static_cast<long long>(a.hl[l]) * a.wl[l] * num_classes;
-            ct.per_seg[l] = static_cast<int>((items + kPreChunkItems - 1) / kPreChunkItems);
-            ct.first[l + 1] = ct.first[l] + ct.per_seg[l] * batch;
+            items[l] = vec ? values[l] >> 2 : static_cast<long long>(a.hl[l]) * a.wl[l] * num_classes;
         }
+        const PreselChunks ct = plan_presel_chunks(items, n_levels, batch);
         dim3 grid(batch, n_levels);
         fcos_presel_estimate_kernel<<<grid, kSelThreads, 0, st>>>(a, w);
         if (ct.first[n_levels] > 0) fcos_presel_collect_kernel<<<ct.first[n_levels], kPreThreads, 0, st>>>(a, ct, batch, w);
@@ -1527,6 +1536,26 @@ int launch_select_segs(dh_handle_s* h, const float* dets, int batch, long long n
 using namespace dh;
 
 extern "C" {
+
+int dh_plan_fcos_select(const long long* values, int n_levels, int batch, signed char* level, unsigned char* lead,
+                        unsigned char* members, int* chunk_first) {
+    DH_CHECK_ARG(values && n_levels >= 1 && n_levels <= DH_MAX_LEVELS && batch >= 0, "dh_plan_fcos_select: bad arguments");
+    for (int l = 0; l < n_levels; ++l) DH_CHECK_ARG(values[l] >= 0, "dh_plan_fcos_select: values[%d] is negative", l);
+    const FcosClusterPlan plan = plan_fcos_clusters(values, n_levels);
+    for (int t = 0; t < n_levels; ++t)
+        for (int r = 0; r < kSelCluster; ++r) {
+            if (level) level[t * kSelCluster + r] = t < plan.n_types ? plan.level[t][r] : static_cast<signed char>(-1);
+            if (lead) lead[t * kSelCluster + r] = t < plan.n_types ? plan.lead[t][r] : static_cast<unsigned char>(0);
+            if (members) members[t * kSelCluster + r] = t < plan.n_types ? plan.members[t][r] : static_cast<unsigned char>(0);
+        }
+    if (chunk_first) {
+        long long items[DH_MAX_LEVELS];
+        for (int l = 0; l < n_levels; ++l) items[l] = values[l] >> 2;
+        const PreselChunks ct = plan_presel_chunks(items, n_levels, batch);
+        for (int l = 0; l <= n_levels; ++l) chunk_first[l] = ct.first[l];
+    }
+    return plan.n_types;
+}
 
 int dh_prediction_to_corners(dh_handle_t h, const float* pred, int batch, int height, int width, int sub, int ch_in, int mode,
                              float stride, float d0, float d1, const float* scales, float* out, void* stream) {

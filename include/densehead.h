@@ -61,6 +61,15 @@ int dh_set_option(dh_handle_t h, int option, int value);
 int dh_read_phase_timing(dh_handle_t h, long long* out8 /*[host] [8]*/);
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 long long dh_launch_count(dh_handle_t h);
+/* Host-only (no device needed): the work split dh_fcos_detect's candidate selection would use for per-level head sizes
+ * `values[l]` = rows * (num_classes + 5) floats.  Thread-block-cluster selector: returns the number of clusters per
+ * image (<= n_levels); level[t*8 + r] is the level rank r of cluster t works on (-1: idle), lead[t*8 + r] the rank of
+ * that group's leader CTA, members[t*8 + r] the group's size.  Streaming pre-select: chunk_first[l] (n_levels + 1
+ * entries) is the first CTA of level l when `batch` images are processed with float4 loads (ids run level > image >
+ * chunk).  Any output may be NULL.  Returns < 0 on a bad argument. */
+int dh_plan_fcos_select(const long long* values, int n_levels, int batch, signed char* level /*[n_levels*8]*/,
+                        unsigned char* lead /*[n_levels*8]*/, unsigned char* members /*[n_levels*8]*/,
+                        int* chunk_first /*[n_levels+1]*/);
 
 /* ---- target encoders ---------------------------------------------------------------------- */
 

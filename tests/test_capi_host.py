@@ -78,3 +78,66 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libdensehead.so")
     with pytest.raises(_capi.DenseHeadError):
         _capi.lib()
+
+
+def _plan(lib, values, batch):
+    n = len(values)
+    v = (ctypes.c_longlong * n)(*values)
+    level = (ctypes.c_byte * (n * 8))()
+    lead = (ctypes.c_ubyte * (n * 8))()
+    members = (ctypes.c_ubyte * (n * 8))()
+    first = (ctypes.c_int * (n + 1))()
+    n_types = lib.dh_plan_fcos_select(v, n, batch, level, lead, members, first)
+    return n_types, np.array(level).reshape(n, 8), np.array(lead).reshape(n, 8), np.array(members).reshape(n, 8), list(first)
+
+
+@pytest.mark.parametrize("values", [
+    [80 * 80 * 85, 40 * 40 * 85, 20 * 20 * 85, 10 * 10 * 85, 5 * 5 * 85],      # C4: COCO-shaped FCOS head
+    [64 * 64 * 25, 32 * 32 * 25, 16 * 16 * 25, 8 * 8 * 25, 4 * 4 * 25],        # C1: VOC-shaped
+    [160 * 160 * 85],                                                            # one long level
+    [100, 100, 100, 100, 100, 100, 100, 100],                                    # eight tiny levels
+    [0, 4 * 85],                                                                 # an empty level
+    [3_000_000, 2_000_000, 1_500_000, 700_000],                                  # several levels that want a whole cluster
+])
+def test_fcos_select_work_split(lib, values):
+    """Host-side planning of dh_fcos_detect's candidate selection (no device needed): every level is worked on by exactly
+    one group of consecutive ranks of one cluster, the group's bookkeeping is consistent, long segments get more CTAs; the
+    streaming pre-select's chunk table covers every load item of every image once."""
+    n = len(values)
+    n_types, level, lead, members, first = _plan(lib, values, batch=3)
+    assert 1 <= n_types <= n
+    seen = {}
+    for t in range(n_types):
+        r = 0
+        while r < 8:
+            l = int(level[t, r])
+            if l < 0:
+                assert all(int(x) < 0 for x in level[t, r:]), "idle ranks only at the end of a cluster"
+                break
+            g = int(members[t, r])
+            assert 1 <= g <= 8 and r + g <= 8 and l not in seen
+            assert all(int(level[t, q]) == l and int(lead[t, q]) == r and int(members[t, q]) == g for q in range(r, r + g))
+            seen[l] = g
+            r += g
+    assert sorted(seen) == list(range(n)), "every level exactly once"
+    assert all(int(x) < 0 for x in level[n_types:].ravel())
+    longest = max(range(n), key=lambda l: values[l])
+    assert seen[longest] == max(seen.values())
+    if values[longest] > 8 * 65536:
+        assert seen[longest] == 8
+    assert all(seen[l] == 1 for l in range(n) if values[l] <= 16384)
+    # chunk table: level-major, cumulative, one 1024-item CTA per chunk and image
+    assert first[0] == 0
+    for l in range(n):
+        items = values[l] // 4
+        assert first[l + 1] - first[l] == 3 * ((items + 1023) // 1024)
+
+
+def test_fcos_select_work_split_rejects_bad_arguments(lib):
+    v = (ctypes.c_longlong * 2)(100, -1)
+    assert lib.dh_plan_fcos_select(v, 2, 1, None, None, None, None) == -1
+    assert lib.dh_plan_fcos_select(None, 2, 1, None, None, None, None) == -1
+    assert lib.dh_plan_fcos_select(v, 0, 1, None, None, None, None) == -1
+    assert lib.dh_plan_fcos_select(v, 9, 1, None, None, None, None) == -1
+    ok = (ctypes.c_longlong * 1)(4096)
+    assert lib.dh_plan_fcos_select(ok, 1, 0, None, None, None, None) == 1
