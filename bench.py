@@ -60,6 +60,12 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-config extra measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (global batch sharded over the ranks)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="which configuration `value` reports (both are always measured: see `weak` / `strong`)")
+    ap.add_argument("--transports", default="peer,nccl", help="loss-exchange transports to set up at N > 1")
+    ap.add_argument("--no-fuse", action="store_true", help="keep the loss exchange out of the loss kernel (separate launch)")
     return ap.parse_args()
 
 
@@ -234,91 +240,117 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import densehead as dh
-    from densehead import _capi, retinanet, fcos, centernet
+    from densehead import _capi, retinanet, fcos, centernet, distributed
     from oracle import synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    comm = {"world": 1, "rank": 0, "peer": False, "nccl": False, "fused": False, "errors": []}
     if world > 1:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
+        # torch.distributed is only the bootstrap channel and the barrier: the loss exchange runs in libdensehead.so
+        comm = distributed.init_comm(transports=tuple(args.transports.split(",")), fuse=not args.no_fuse)
 
     B = args.batch
-    boxes_h, nbox_h = synth.config_boxes("retina_coco", B, synth.seed_for(5, 100 + rank))
-    dims_h = np.tile(np.array([[SIDE, SIDE]], dtype=np.float32), (B, 1))
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1000 + rank)
-    pred = []
-    for h in LEVELS:  # random-init head outputs: regs ~ U(-1,2), class logits ~ N(-4.595, 1) (focal prior)
-        p = torch.empty((B, ANCHORS, h, h, CLASSES + 4), device=dev)
-        p[..., :4].uniform_(-1, 2, generator=gen)
-        p[..., 4:].normal_(-4.595, 1.0, generator=gen)
-        pred.append(p)
-    boxes_d = torch.from_numpy(boxes_h).to(dev)
-    nbox_d = torch.from_numpy(nbox_h).to(dev)
-    dims_d = torch.from_numpy(dims_h).to(dev)
-    pred_bytes = sum(p.numel() for p in pred) * 4
-    box_bytes = boxes_h.nbytes + nbox_h.nbytes + dims_h.nbytes
-    assert pred_bytes == B * PRED_BYTES_PER_IMAGE
+    dims_row = np.array([[SIDE, SIDE]], dtype=np.float32)
 
-    def step_device():
-        return retinanet.encode_loss_batch(boxes_d, nbox_d, dims_d, CLASSES, [SIDE, SIDE], pred)
+    def make_pred(batch, seed):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        out = []
+        for h in LEVELS:  # random-init head outputs: regs ~ U(-1,2), class logits ~ N(-4.595, 1) (focal prior)
+            p = torch.empty((batch, ANCHORS, h, h, CLASSES + 4), device=dev)
+            p[..., :4].uniform_(-1, 2, generator=gen)
+            p[..., 4:].normal_(-4.595, 1.0, generator=gen)
+            out.append(p)
+        return out
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also grows the library's scratch so nothing allocates inside the graph) ------------
-    for _ in range(max(args.warmup, 3)):
-        per_image, total, pairs = step_device()
-        if dist is not None:
-            dist.all_reduce(total)
-    torch.cuda.synchronize()
+    def exchange(total):
+        """The loss-scalar all-reduce of one step when the loss kernel has not already done it."""
+        if world > 1 and not comm["fused"]:
+            distributed.allreduce_losses(total)
 
-    # ---- capture one step's kernels in a CUDA graph: the device-resident measurement must not time the
-    #      Python/ctypes launch path (that is what `e2e` is for)
-    l0 = dh.launch_count(local_rank)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        per_image, total, pairs = step_device()
-    launches_per_step = dh.launch_count(local_rank) - l0
-    graph.replay()
-    torch.cuda.synchronize()
+    in_graph_exchange = world == 1 or comm["fused"] or comm["peer"] or comm["nccl"]
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
+    def timed_graph(boxes_d, nbox_d, dims_d, pred, steps, sampler=None):
+        """CUDA-event time of `steps` graph replays of one step (encode + loss + exchange); max over ranks."""
+        def step():
+            out = retinanet.encode_loss_batch(boxes_d, nbox_d, dims_d, CLASSES, [SIDE, SIDE], pred)
+            if in_graph_exchange:
+                exchange(out[1])
+            return out
+        for _ in range(max(args.warmup, 3)):  # warm-up (also grows the library's scratch: nothing allocates inside the graph)
+            out = step()
+            if not in_graph_exchange:
+                dist.all_reduce(out[1])
+        torch.cuda.synchronize()
+        barrier()
+        # one step's kernels in a CUDA graph: the device-resident measurement must not time the Python/ctypes launch
+        # path (that is what `e2e` is for)
+        l0 = dh.launch_count(local_rank)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = step()
+        launches = dh.launch_count(local_rank) - l0
         graph.replay()
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+            if not in_graph_exchange:
+                dist.all_reduce(out[1])
+        e1.record()
+        barrier()
+        local_ms = e0.elapsed_time(e1)
+        ms = local_ms
         if dist is not None:
-            dist.all_reduce(total)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    local_ms = ms
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms / steps, local_ms / steps, launches, out
+
+    # ---- weak scaling (the contract's default): B images per GPU, rank-specific data ----------------------------
+    boxes_h, nbox_h = synth.config_boxes("retina_coco", B, synth.seed_for(5, 100 + rank))
+    dims_h = np.tile(dims_row, (B, 1))
+    pred = make_pred(B, 1000 + rank)
+    boxes_d = torch.from_numpy(boxes_h).to(dev)
+    nbox_d = torch.from_numpy(nbox_h).to(dev)
+    dims_d = torch.from_numpy(dims_h).to(dev)
+    pred_bytes = sum(p.numel() for p in pred) * 4
+    box_bytes = boxes_h.nbytes + nbox_h.nbytes + dims_h.nbytes
+    assert pred_bytes == B * PRED_BYTES_PER_IMAGE
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_per_step, local_ms_per_step, launches_per_step, out_w = timed_graph(boxes_d, nbox_d, dims_d, pred, args.steps, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-    ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (fused encode+loss): its launches ARE the timed region (one per step, plus
-    #      two finalize kernels of a few microseconds each), so the timed region's own CUDA-event time is used (this
-    #      rank's, before the max over ranks)
+    # ---- parity of the timed configuration, outside the timed region: two images of this very batch against the
+    #      oracle (rank 0), per-image rows against the total
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = check_parity(out_w, boxes_h, nbox_h, pred, world, comm)
+
+    # ---- roofline of the dominant kernel (fused encode+loss): its launch IS the timed region (one per step; the
+    #      reduction of the partials and the exchange run in its last CTA), so the timed region's own CUDA-event time is
+    #      used (this rank's, before the max over ranks)
     peak, peak_src = measured_peak()
-    kern_s = local_ms / args.steps * 1e-3
+    kern_s = local_ms_per_step * 1e-3
     alg_bytes = pred_bytes + box_bytes
     achieved = alg_bytes / kern_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "fused_loss_kernel<RetinaPolicy> (+2 finalize kernels, <1% of the time; CUDA events over the timed region)",
+    roofline = {"bound": "hbm", "kernel": "fused_loss_kernel<RetinaPolicy> (one launch per step; CUDA events over the timed region)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_s * 1e3, "peak_source": peak_src}
     ncu = os.path.join(ROOT, "profiles", "traffic.json")
@@ -350,7 +382,9 @@ def run_ours(args, rank, world, local_rank):
             else:
                 x = pred
             _, tot, _ = retinanet.encode_loss_batch(b, n, d, CLASSES, [SIDE, SIDE], x)
-            if dist is not None:
+            if in_graph_exchange:
+                exchange(tot)
+            else:
                 dist.all_reduce(tot)
             out_host.copy_(tot, non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the caller reads the loss
@@ -383,11 +417,55 @@ def run_ours(args, rank, world, local_rank):
     except Exception as exc:  # e.g. not enough pinned host memory
         e2e = {"value": None, "unit": "images/s", "error": repr(exc)}
 
+    # ---- strong scaling, as BASELINE.json configs[4] states it: ONE global batch of B images sharded by image over the
+    #      ranks (B / N per GPU), the exchange inside the step.  Every rank builds the same global batch; rank 0 also
+    #      runs all of it alone and the all-reduced total must equal that single-GPU total.
+    strong = None
+    if not args.no_strong:
+        if world == 1:
+            strong = {"global_batch": B, "images_per_gpu": B, "value": value, "ms_per_step": ms_per_step,
+                      "frac_of_hbm_peak": achieved / peak, "note": "N = 1: the weak and the strong configuration coincide"}
+        else:
+            del pred
+            torch.cuda.empty_cache()
+            gboxes_h, gnbox_h = synth.config_boxes("retina_coco", B, synth.seed_for(5, 99))
+            gpred = make_pred(B, 999)
+            lo, hi = distributed.shard_range(B, rank, world)
+            sb = torch.from_numpy(gboxes_h[lo:hi]).to(dev)
+            sn = torch.from_numpy(gnbox_h[lo:hi]).to(dev)
+            sd = torch.from_numpy(np.tile(dims_row, (hi - lo, 1))).to(dev)
+            spred = [p[lo:hi] for p in gpred]
+            s_ms, s_local, s_launch, s_out = timed_graph(sb, sn, sd, spred, args.steps)
+            torch.cuda.synchronize()
+            total_all = s_out[1].clone()
+            if not in_graph_exchange:
+                dist.all_reduce(total_all)
+            strong = {"global_batch": B, "images_per_gpu": hi - lo, "value": B / (s_ms * 1e-3), "ms_per_step": s_ms,
+                      "frac_of_hbm_peak": (hi - lo) * PRED_BYTES_PER_IMAGE / (s_local * 1e-3) / 1e9 / peak,
+                      "launches_per_step": int(s_launch)}
+            barrier()
+            if rank == 0:
+                distributed.set_fused(False)  # rank 0 alone: no exchange
+                fb = torch.from_numpy(gboxes_h).to(dev)
+                fn_ = torch.from_numpy(gnbox_h).to(dev)
+                fd = torch.from_numpy(np.tile(dims_row, (B, 1))).to(dev)
+                _, ftot, _ = retinanet.encode_loss_batch(fb, fn_, fd, CLASSES, [SIDE, SIDE], gpred)
+                torch.cuda.synchronize()
+                a, b_ = total_all.double().cpu().numpy(), ftot.double().cpu().numpy()
+                rel = float(np.max(np.abs(a[:2] - b_[:2]) / np.maximum(1.0, np.abs(b_[:2]))))
+                strong["sum_parity"] = {"allreduced_total": a.tolist(), "single_gpu_total": b_.tolist(), "max_rel_diff": rel,
+                                        "n_pos_equal": bool(a[3] == b_[3]), "ok": bool(rel <= 1e-6 and a[3] == b_[3])}
+            barrier()
+            distributed.set_fused(comm["fused"])
+            pred = gpred
+            del spred
+
     # ---- extra: the other BASELINE configs, device-resident, graph-timed ------------------------------
     extra = {}
     if rank == 0 and not args.no_extra:
         del pred
         torch.cuda.empty_cache()
+        distributed.set_fused(False)
         extra = extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak)
 
     cpu = None
@@ -395,17 +473,65 @@ def run_ours(args, rank, world, local_rank):
         cpu = cpu_port_single_core()
 
     if rank == 0:
-        line = {"metric": "dense-head target+loss images/sec", "value": value, "unit": "images/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "images sharded, dp%d" % world,
+        if world == 1:
+            collective = "none"
+        elif comm["fused"]:
+            collective = "sum of the 4 loss scalars over NVLink peer mailboxes inside the loss kernel's last CTA (same launch, in the graph)"
+        elif comm["peer"]:
+            collective = "dh_allreduce_loss: one kernel over NVLink peer mailboxes, in the graph"
+        elif comm["nccl"]:
+            collective = "dh_allreduce_loss: ncclAllReduce of 4 float32 on the compute stream, in the graph"
+        else:
+            collective = "torch.distributed all_reduce of 4 float32 per step, outside the graph"
+        scaling = "strong" if args.scaling == "strong" and strong else "weak"
+        line = {"metric": "dense-head target+loss images/sec", "value": strong["value"] if scaling == "strong" else value,
+                "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": strong["ms_per_step"] if scaling == "strong" else ms_per_step, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": B if scaling == "strong" else world * B,
+                           "parallelism": "images sharded, dp%d" % world,
                            "l2": "inputs (%.1f GB of predictions per GPU) are far larger than the 126 MB L2" % (pred_bytes / 1e9),
-                           "collective": "NCCL all-reduce of 4 float32 loss scalars per step" if world > 1 else "none"},
+                           "collective": collective},
                 "clocks": clocks, "e2e": e2e, "e2e_resident_pred": e2e_res, "gpu_launches": int(launches_per_step * args.steps),
+                "launches_per_step": int(launches_per_step), "parity_checked": bool(parity and parity.get("ok")), "parity": parity,
+                "weak": {"global_batch": world * B, "images_per_gpu": B, "value": value, "ms_per_step": ms_per_step},
+                "strong": strong, "comm": {k: comm[k] for k in ("peer", "nccl", "fused", "errors")},
                 "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
         emit_json(json.dumps(line))
     if dist is not None:
+        try:
+            distributed.destroy_comm()
+        except Exception:
+            pass
         dist.destroy_process_group()
+
+
+def check_parity(out, boxes_h, nbox_h, pred, world, comm):
+    """The timed batch itself against the CPU oracle: images 0 and 1 (cls and reg sums at 1e-5 relative, the positive
+    count and the pair count exactly) and the per-image rows against the total."""
+    from oracle import dense_head_ref as O
+    per_image, total, pairs = out[0].cpu().numpy(), out[1].cpu().numpy(), out[2].cpu().numpy()
+    res = {"images": [], "ok": True, "tolerance": "1e-5 relative (floor 1) on cls/reg sums; n_pos and pair counts exact"}
+    for b in (0, 1):
+        if b >= len(nbox_h):
+            break
+        labels, n_pairs = O.retina_format_data(boxes_h[b, :nbox_h[b]], [SIDE, SIDE], CLASSES)
+        want = O.retina_train_loss(labels, [[p[b, a].cpu().numpy() for a in range(ANCHORS)] for p in pred])
+        n_pos = int(sum(int((np.max(m[..., 4:], axis=-1) > 0).sum()) for lv in labels for m in lv))
+        got = per_image[b]
+        rel = [abs(float(got[k]) - float(want[k])) / max(1.0, abs(float(want[k]))) for k in (0, 1)]
+        ok = max(rel) <= 1e-5 and int(got[3]) == n_pos and int(pairs[b]) == int(n_pairs)
+        res["images"].append({"image": b, "cls": float(got[0]), "reg": float(got[1]), "oracle_cls": float(want[0]),
+                              "oracle_reg": float(want[1]), "rel": rel, "n_pos": int(got[3]), "oracle_n_pos": n_pos,
+                              "pairs": int(pairs[b]), "oracle_pairs": int(n_pairs), "ok": bool(ok)})
+        res["ok"] = res["ok"] and bool(ok)
+    if world == 1 or not comm["fused"]:  # (with the in-kernel exchange the total already spans all ranks)
+        s = per_image.astype(np.float64).sum(axis=0)
+        rel = float(np.max(np.abs(s[:3] - total[:3]) / np.maximum(1.0, np.abs(s[:3]))))
+        res["rows_sum_to_total"] = {"max_rel_diff": rel, "ok": bool(rel <= 1e-6 and s[3] == total[3])}
+        res["ok"] = res["ok"] and res["rows_sum_to_total"]["ok"]
+    return res
 
 
 def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):

@@ -22,8 +22,6 @@ void* scratch(dh_handle_s* h, size_t bytes) {
         cudaFree(h->scratch);
         h->scratch = nullptr;
         h->scratch_bytes = 0;
-    h->scratch_b = nullptr;
-    h->scratch_b_bytes = 0;
     }
     size_t want = bytes + (bytes >> 1) + (1u << 20);
     cudaError_t e = cudaMalloc(&h->scratch, want);
@@ -70,6 +68,26 @@ unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st) {
     return h->sched + (h->sched_next++ % kSchedRing) * 32;
 }
 
+unsigned int* image_counters(dh_handle_s* h, int batch) {
+    if (batch <= h->img_cnt_cap) return h->img_cnt;
+    if (h->img_cnt) {
+        cudaDeviceSynchronize();  // a kernel in flight may still count on the old block
+        cudaFree(h->img_cnt);
+        h->img_cnt = nullptr;
+        h->img_cnt_cap = 0;
+    }
+    int cap = 1024;
+    while (cap < batch) cap *= 2;
+    cudaError_t e = cudaMalloc(&h->img_cnt, static_cast<size_t>(cap) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(h->img_cnt, 0, static_cast<size_t>(cap) * sizeof(unsigned int));
+    if (e != cudaSuccess) {
+        set_error(DH_ERR_CUDA, "allocating the per-image counters failed: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    h->img_cnt_cap = cap;
+    return h->img_cnt;
+}
+
 }  // namespace dh
 
 extern "C" {
@@ -100,6 +118,10 @@ int dh_create(dh_handle_t* out, int device) {
     h->encode_min_chunk = 2;
     h->fcos_select_mode = 0;
     h->nms_sort = 0;
+    h->loss_allreduce = 0;
+    h->allreduce_mode = 0;
+    h->fused_tail = 1;
+    h->encode_kernel = 0;
     h->launches = 0;
     h->scratch = nullptr;
     h->scratch_bytes = 0;
@@ -108,18 +130,36 @@ int dh_create(dh_handle_t* out, int device) {
     h->phase_cycles = nullptr;
     h->sched = nullptr;
     h->sched_next = 0;
+    h->comm = nullptr;
+    h->dev_status = nullptr;
+    h->trace = nullptr;
+    h->img_cnt = nullptr;
+    h->img_cnt_cap = 0;
+    h->trace_bytes = 0;
+    {
+        dh::DeviceGuard g(device);
+        cudaError_t e = cudaMalloc(&h->dev_status, 128);
+        if (e == cudaSuccess) e = cudaMemset(h->dev_status, 0, 128);
+        if (e != cudaSuccess) {
+            delete h;
+            return dh::set_error(DH_ERR_CUDA, "dh_create: allocating the status word failed: %s", cudaGetErrorString(e));
+        }
+    }
     *out = h;
     return DH_OK;
 }
 
 int dh_destroy(dh_handle_t h) {
     if (!h) return DH_OK;
+    dh_comm_destroy(h);
     {
         dh::DeviceGuard g(h->device);
         if (h->scratch) cudaFree(h->scratch);
         if (h->scratch_b) cudaFree(h->scratch_b);
         if (h->sched) cudaFree(h->sched);
         if (h->phase_cycles) cudaFree(h->phase_cycles);
+        if (h->dev_status) cudaFree(h->dev_status);
+        if (h->img_cnt) cudaFree(h->img_cnt);
     }
     delete h;
     return DH_OK;
@@ -155,6 +195,22 @@ int dh_set_option(dh_handle_t h, int option, int value) {
             DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_NMS_SORT must be 0 or 1");
             h->nms_sort = value;
             return DH_OK;
+        case DH_OPT_LOSS_ALLREDUCE:
+            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_LOSS_ALLREDUCE must be 0 or 1");
+            h->loss_allreduce = value;
+            return DH_OK;
+        case DH_OPT_ALLREDUCE:
+            DH_CHECK_ARG(value >= 0 && value <= 2, "DH_OPT_ALLREDUCE must be 0, 1 or 2");
+            h->allreduce_mode = value;
+            return DH_OK;
+        case DH_OPT_FUSED_TAIL:
+            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_FUSED_TAIL must be 0 or 1");
+            h->fused_tail = value;
+            return DH_OK;
+        case DH_OPT_ENCODE_KERNEL:
+            DH_CHECK_ARG(value >= 0 && value <= 2, "DH_OPT_ENCODE_KERNEL must be 0, 1 or 2");
+            h->encode_kernel = value;
+            return DH_OK;
         case DH_OPT_FUSED_CHUNKS_PER_CTA:
             DH_CHECK_ARG(value >= 1 && value <= 64, "DH_OPT_FUSED_CHUNKS_PER_CTA must be in [1, 64]");
             h->fused_chunks_per_cta = value;
@@ -181,6 +237,21 @@ int dh_set_option(dh_handle_t h, int option, int value) {
 }
 
 long long dh_launch_count(dh_handle_t h) { return h ? h->launches : 0; }
+
+int dh_set_trace(dh_handle_t h, long long* buf, long long bytes) {
+    DH_CHECK_ARG(h, "dh_set_trace: handle is NULL");
+    h->trace = buf;
+    h->trace_bytes = buf ? bytes : 0;
+    return DH_OK;
+}
+
+int dh_get_status(dh_handle_t h, int32_t* out, int reset) {
+    DH_CHECK_ARG(h && out, "dh_get_status: NULL argument");
+    dh::DeviceGuard g(h);
+    DH_CUDA(cudaMemcpy(out, h->dev_status, sizeof(int32_t), cudaMemcpyDeviceToHost));  // synchronises with the null stream
+    if (reset && *out) DH_CUDA(cudaMemset(h->dev_status, 0, sizeof(int32_t)));
+    return DH_OK;
+}
 
 int dh_read_phase_timing(dh_handle_t h, long long* out8) {
     DH_CHECK_ARG(h && out8, "dh_read_phase_timing: NULL argument");

@@ -1566,7 +1566,7 @@ int dh_prediction_to_corners(dh_handle_t h, const float* pred, int batch, int he
     DH_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "dh_prediction_to_corners: out must be 16-byte aligned");
     const long long rows = static_cast<long long>(batch) * height * width * sub;
     if (rows == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     CornerParams p;
     memset(&p, 0, sizeof(p));
     p.mode = mode, p.height = height, p.width = width, p.sub = sub, p.ch_in = ch_in, p.stride = stride, p.d0 = d0, p.d1 = d1;
@@ -1582,7 +1582,7 @@ int dh_fcos_decode(dh_handle_t h, const float* const* pred_levels, int batch, in
     DH_CHECK_ARG(h && pred_levels && strides && boxes && scores, "dh_fcos_decode: NULL argument");
     DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_LEVELS && num_classes >= 1, "dh_fcos_decode: bad configuration");
     DH_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15u) == 0, "dh_fcos_decode: boxes must be 16-byte aligned");
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     long long n_total = 0;
     for (int l = 0; l < n_levels; ++l)
         n_total += static_cast<long long>(static_cast<int>(static_cast<double>(pad_h) / strides[l])) *
@@ -1608,7 +1608,7 @@ int dh_retina_decode(dh_handle_t h, const float* const* pred_levels, int batch, 
                      void* stream) {
     DH_CHECK_ARG(h && pred_levels && strides && anchor_hw_dev && dets, "dh_retina_decode: NULL argument");
     DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_LEVELS && n_anchors >= 1 && num_classes >= 1, "dh_retina_decode: bad configuration");
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     long long n_total = 0;
     for (int l = 0; l < n_levels; ++l)
         n_total += static_cast<long long>(n_anchors) * static_cast<int>(static_cast<double>(pad_h) / strides[l]) *
@@ -1681,7 +1681,7 @@ int dh_select_topk(dh_handle_t h, const float* dets, int batch, long long n_tota
                      n_seg >= 1 && k >= 1 && k <= 65535,
                  "dh_select_topk: bad sizes");
     if (batch == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     dim3 grid(batch, n_seg);
     select_topk_kernel<<<grid, kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(dets, n_total, row_floats, score_col, seg_off_dev, k, min_score,
                                                                                    score_inclusive, out, out_src, n_seg * k);

@@ -58,7 +58,7 @@ int dh_fcos_detect(dh_handle_t h, const float* const* pred_levels, int batch, in
     DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_PYRAMID_LEVELS && num_classes >= 1, "dh_fcos_detect: bad configuration");
     DH_CHECK_ARG(batch >= 0 && max_total >= 1 && pre_nms_topk >= 1, "dh_fcos_detect: bad sizes");
     if (batch == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     long long longest = 1;
     for (int l = 0; l < n_levels; ++l) {
@@ -97,7 +97,7 @@ int dh_retina_detect(dh_handle_t h, const float* const* pred_levels, int batch, 
     DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_PYRAMID_LEVELS && n_anchors >= 1 && num_classes >= 1, "dh_retina_detect: bad configuration");
     DH_CHECK_ARG(batch >= 0 && max_out >= 1 && pre_nms_topk >= 0, "dh_retina_detect: bad sizes");
     if (batch == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int seg[DH_MAX_PYRAMID_LEVELS + 1];
     seg[0] = 0;

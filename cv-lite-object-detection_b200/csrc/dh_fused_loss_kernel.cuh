@@ -196,7 +196,7 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     l.raw_off = (static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127;
     l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
     l.misc_off = l.cand_off + (DH_THREADS / 32) * box_cap * 4;  // per warp: tile candidates + map candidates
-    l.args_off = l.misc_off + 256;
+    l.args_off = l.misc_off + 512;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
     return l;
 }
@@ -405,63 +405,87 @@ __device__ __forceinline__ const float* warp_tile(const LossArgs<P>& a, const Ti
 }
 
 // ---- correct: the rows of this warp's tiles that receive targets ------------------------------------------------
+// Nearly every 32-row warp tile has no target at all, so the tiles are culled per run of the chunk's tiles inside one map
+// ("segment", at most 32 tiles): on entering a segment the warp lists the boxes that can match the map at all
+// (P::map_hit), takes each one's conservative row interval (P::row_span) and ORs, with one REDUX, a bit mask of the
+// segment's tiles whose slice of this warp meets any interval.  Only those tiles run the exact narrowing (P::range_hit)
+// and the row matcher; an empty segment costs a few dozen instructions instead of a few dozen per tile.
 template <class P>
 __device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typename P::Rec* recs, int n_boxes,
                                              unsigned short* cand, int img, int t_begin, int t_end) {
     LossAcc acc = {0.f, 0.f, 0.f, 0};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned short* maplist = cand + a.box_cap;
-    int cur_m = -1, nmap = 0;
+    const int rpt = a.tt.rows_per_tile;
     TileCursor cur;
     cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
 #pragma unroll 1
-    for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, cur)) {
-        TileInfo ti;
-        float* gg = nullptr;
-        const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, &gg);
-        if (ti.nrows <= 0) continue;
-        const MapDesc& md = a.tt.maps[ti.m];
-        if (ti.m != cur_m) {  // entering another map: the boxes that can match it at all (tile-independent tests)
-            __syncwarp();
-            cur_m = ti.m, nmap = 0;
-#pragma unroll 1
-            for (int k0 = 0; k0 < n_boxes; k0 += 32) {
-                const int k = k0 + lane;
-                const bool hit = k < n_boxes && P::map_hit(a.pp, recs[k], ti.level, ti.anchor);
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) maplist[nmap + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
-                nmap += __popc(bal);
-            }
-            __syncwarp();
-        }
-        int ncand = 0;
-#pragma unroll 1
-        for (int q0 = 0; q0 < nmap; q0 += 32) {  // ... narrowed to this tile's rows (and columns)
-            const int q = q0 + lane;
-            const int k = q < nmap ? maplist[q] : 0;
-            const bool hit = q < nmap && P::range_hit(a.pp, recs[k], ti, md);
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (hit) cand[ncand + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
-            ncand += __popc(bal);
-        }
-        if (ncand == 0) continue;  // warp-uniform
+    for (int tile = t_begin; tile < t_end;) {
+        // ---- segment: tiles [cur.t, cur.t + nseg) of map cur.m ---------------------------------------------------
+        const MapDesc& md = a.tt.maps[cur.m];
+        const int nseg = min(min(md.n_tiles - cur.t, t_end - tile), 32);
+        const int seg_r0 = cur.t * rpt + 32 * warp;  // first row of this warp's slice of the segment's first tile
+        int nmap = 0;
+        unsigned mask = 0u;
         __syncwarp();
-        int pairs = 0;
-        if (lane < ti.nrows) {
-            CompactSink sink;
-            sink.clear();
-            const int row = ti.r0 + lane;
-            pairs = P::match_row(a.pp, ti, md, row, sink, recs, cand, ncand);
-            if (pairs > 0) {
-                const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
-                const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
-                const LossAcc d = correct_row(a.spec, gp + lane * a.tt.ch, gg ? gg + lane * a.tt.ch : nullptr, sink, static_cast<float>(i),
-                                              static_cast<float>(cell - i * md.width));
-                acc.cls += d.cls, acc.reg += d.reg, acc.cen += d.cen, acc.npos += d.npos;
+#pragma unroll 1
+        for (int k0 = 0; k0 < n_boxes; k0 += 32) {
+            const int k = k0 + lane;
+            bool hit = k < n_boxes && P::map_hit(a.pp, recs[k], md.level, md.anchor);
+            if (hit) {
+                int rlo, rhi;
+                P::row_span(a.pp, recs[k], md, md.level, md.anchor, rlo, rhi);
+                rhi = min(rhi, md.rows - 1);
+                unsigned m = 0u;
+                for (int t = 0; t < nseg; ++t) {
+                    const int lo = seg_r0 + t * rpt;
+                    if (rhi >= lo && rlo < lo + 32) m |= 1u << t;
+                }
+                hit = m != 0u;
+                mask |= m;
             }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (hit) maplist[nmap + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
+            nmap += __popc(bal);
         }
-        P::tile_epilogue(a.pp, ti, pairs);
-        __syncwarp();  // the candidate list is rebuilt for the next tile
+        mask = __reduce_or_sync(0xffffffffu, mask);
+        __syncwarp();
+#pragma unroll 1
+        for (int t = 0; t < nseg; ++t, ++tile, cursor_next(a.tt, cur)) {
+            if (!((mask >> t) & 1u)) continue;  // warp-uniform
+            TileInfo ti;
+            float* gg = nullptr;
+            const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, &gg);
+            if (ti.nrows <= 0) continue;
+            int ncand = 0;
+#pragma unroll 1
+            for (int q0 = 0; q0 < nmap; q0 += 32) {  // ... narrowed to this tile's rows (and columns)
+                const int q = q0 + lane;
+                const int k = q < nmap ? maplist[q] : 0;
+                const bool hit = q < nmap && P::range_hit(a.pp, recs[k], ti, md);
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) cand[ncand + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
+                ncand += __popc(bal);
+            }
+            if (ncand == 0) continue;  // warp-uniform
+            __syncwarp();
+            int pairs = 0;
+            if (lane < ti.nrows) {
+                CompactSink sink;
+                sink.clear();
+                const int row = ti.r0 + lane;
+                pairs = P::match_row(a.pp, ti, md, row, sink, recs, cand, ncand);
+                if (pairs > 0) {
+                    const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
+                    const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
+                    const LossAcc d = correct_row(a.spec, gp + lane * a.tt.ch, gg ? gg + lane * a.tt.ch : nullptr, sink, static_cast<float>(i),
+                                                  static_cast<float>(cell - i * md.width));
+                    acc.cls += d.cls, acc.reg += d.reg, acc.cen += d.cen, acc.npos += d.npos;
+                }
+            }
+            P::tile_epilogue(a.pp, ti, pairs);
+            __syncwarp();  // the candidate list is rebuilt for the next tile
+        }
     }
     return acc;
 }
@@ -526,6 +550,99 @@ __device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int i
     });
     return sa;
 }
+// The chunk -> (tier, image, first tile) map of the tiered scheduler (LossArgs::tiers).
+template <class P>
+__device__ __forceinline__ void chunk_span(const LossArgs<P>& a, long long chunk, int& img, int& sub, int& t_begin, int& t_end) {
+    int tk = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxChunkTiers; ++q)
+        if (q < a.n_tiers && chunk >= a.tiers[q].chunk0) tk = q;
+    const ChunkTier& T = a.tiers[tk];
+    const int c2 = static_cast<int>(chunk - T.chunk0);
+    const int di = c2 / T.cpi;
+    img = T.image0 + di;
+    sub = c2 - di * T.cpi;
+    t_begin = sub * T.chunk_tiles;
+    t_end = min(t_begin + T.chunk_tiles, a.tt.tiles_per_image);
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Reduction of the chunk partials without a second launch and off the kernel's tail:
+//   image_done   warp 0 of a CTA calls it after every chunk: the chunk is counted on its image's counter, and the warp
+//                that counts the image's last chunk adds up the image's partials (float64, fixed lane/shuffle order ->
+//                deterministic) into per_image[img] and puts the counter back to zero for the next launch;
+//   finalize_total  the last CTA of the launch sums the per-image rows in a fixed order into the total and, when the
+//                communicator is attached, exchanges the total with the peer ranks (dh_comm.cuh).
+template <class P>
+__device__ __forceinline__ void image_done(const LossArgs<P>& a, int img, int lane) {
+    int tk = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxChunkTiers; ++q)
+        if (q < a.n_tiers && img >= a.tiers[q].image0) tk = q;
+    const ChunkTier& T = a.tiers[tk];
+    int fin = 0;
+    if (lane == 0) {
+        __threadfence();  // this CTA's partial of the chunk is visible device-wide before the chunk is counted
+        fin = atomicAdd(a.img_cnt + img, 1u) == static_cast<unsigned>(T.cpi - 1);
+    }
+    fin = __shfl_sync(0xffffffffu, fin, 0);
+    if (!fin) return;
+    __threadfence();
+    const float4* p = reinterpret_cast<const float4*>(a.partials) + T.chunk0 + static_cast<long long>(img - T.image0) * T.cpi;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int t = lane; t < T.cpi; t += 32) {
+        const float4 v = __ldcg(p + t);
+        acc[0] += v.x, acc[1] += v.y, acc[2] += v.z, acc[3] += v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = warp_sum_d(acc[k]);
+    if (lane == 0) {
+        reinterpret_cast<float4*>(a.per_image)[img] = make_float4(static_cast<float>(acc[0]), static_cast<float>(acc[1]),
+                                                                  static_cast<float>(acc[2]), static_cast<float>(acc[3]));
+        a.img_cnt[img] = 0u;
+    }
+}
+
+// `red` is [8][4] doubles followed by 4 floats (dynamic shared memory)
+template <class P>
+__device__ __forceinline__ void finalize_total(const LossArgs<P>& a, double* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!a.out_total) return;
+    const float4* rows = reinterpret_cast<const float4*>(a.per_image);
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int b = tid; b < a.tt.batch; b += DH_THREADS) {  // the total is the sum of the float32 per-image values
+        const float4 v = __ldcg(rows + b);
+        tot[0] += v.x, tot[1] += v.y, tot[2] += v.z, tot[3] += v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tot[k] = warp_sum_d(tot[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[warp * 4 + k] = tot[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float* vals = reinterpret_cast<float*>(red + (DH_THREADS / 32) * 4);  // (a static __shared__ array would count
+        if (lane < 4) {                                                      // against the 227 KB dynamic opt-in)
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < DH_THREADS / 32; ++w) v += red[w * 4 + lane];
+            vals[lane] = static_cast<float>(v);
+        }
+        __syncwarp();
+        if (a.use_comm) peer_allreduce_warp(a.comm, vals, 4);
+        __syncwarp();
+        if (lane < 4) a.out_total[lane] = vals[lane];
+    }
+}
+
 template <class P, int kCls, bool kGrad>
 __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_constant__ LossArgs<P> ga) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -536,18 +653,14 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     float* raw = reinterpret_cast<float*>(smem + lay.raw_off);
     uint64_t* boxbar = reinterpret_cast<uint64_t*>(smem + lay.misc_off);
     long long* next_chunk = reinterpret_cast<long long*>(smem + lay.misc_off + 8);
-    float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 64);  // [8][4]
+    int* is_last = reinterpret_cast<int*>(smem + lay.misc_off + 16);
+    float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 64);  // [8][4] floats; [8][4] doubles in the finalize
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned short* cand = reinterpret_cast<unsigned short*>(smem + lay.cand_off) + warp * 2 * ga.box_cap;
     const bool vec = ga.allow_vec && (ga.tt.ch & 3) == 0 && ga.spec.cen_mode == 0 && ga.spec.reg_ch == 4;
-    const int tpi = ga.tt.tiles_per_image;
-    const long long n_chunks = static_cast<long long>(ga.tt.batch) * ga.chunks_per_image;
-    long long chunk = blockIdx.x;
-    if (chunk >= n_chunks) {  // (the launchers clamp the grid to the chunk count; kept for safety)
-        if (threadIdx.x == 0) sched_release(ga.sched);
-        return;
-    }
+    const long long n_chunks = ga.n_chunks;
+    long long chunk = blockIdx.x;  // (the launchers clamp the grid to the chunk count)
     if (tid == 0) {
         mbar_init(boxbar, 1);
         mbar_init_fence();
@@ -556,12 +669,13 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
 
     uint32_t box_parity = 0;
     int cur_img = -1, n_boxes = 0;
+    const bool trace = ga.trace != nullptr && tid == 0;
+    int n_done = 0;
+    if (trace) ga.trace[blockIdx.x * 4 + 0] = static_cast<long long>(global_ns());
 #pragma unroll 1
     for (; chunk < n_chunks;) {
-        const int img = static_cast<int>(chunk / ga.chunks_per_image);
-        const int sub = static_cast<int>(chunk - static_cast<long long>(img) * ga.chunks_per_image);
-        const int t_begin = sub * ga.chunk_tiles;  // tile ids within the image
-        const int t_end = min(t_begin + ga.chunk_tiles, tpi);
+        int img, sub, t_begin, t_end;
+        chunk_span(a, chunk, img, sub, t_begin, t_end);
         if (tid == 0) *next_chunk = static_cast<long long>(atomicAdd(ga.sched, 1u)) + gridDim.x;
         if (img != cur_img) {  // block-uniform; the barrier at the end of the previous chunk protects recs/raw
             n_boxes = stage_boxes(a.boxes, a.nbox, img, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
@@ -571,6 +685,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
             cur_img = img;
         }
         if (sub == 0) P::image_prologue(a.pp, recs, n_boxes, img);
+        if (trace && n_done++ == 0) ga.trace[blockIdx.x * 4 + 1] = static_cast<long long>(global_ns());
 
         const StreamAcc sa = vec ? stream_pass_vec<P, kCls, kGrad>(a, img, t_begin, t_end)
                                  : stream_pass_scalar<P, kCls, kGrad>(a, img, t_begin, t_end);
@@ -592,16 +707,43 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
             wred[warp * 4 + 3] = static_cast<float>(npos);
         }
         __syncthreads();  // also: every warp is done with recs; the prefetched chunk id is visible
-        if (tid < 4) {
+        if (warp == 0) {  // wred [8][4] -> one float4 per chunk, stored by lane 0 (the thread that later counts the chunk)
             float v = 0.f;
+            if (lane < 4) {
 #pragma unroll
-            for (int w = 0; w < DH_THREADS / 32; ++w) v += wred[w * 4 + tid];
-            a.partials[chunk * 4 + tid] = v;
+                for (int w = 0; w < DH_THREADS / 32; ++w) v += wred[w * 4 + lane];
+            }
+            const float4 o = make_float4(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 1), __shfl_sync(0xffffffffu, v, 2),
+                                         __shfl_sync(0xffffffffu, v, 3));
+            if (lane == 0) reinterpret_cast<float4*>(a.partials)[chunk] = o;
         }
         chunk = *next_chunk;
         __syncthreads();  // wred / next_chunk are free again
+        // warp 0 counts the chunk on its image (and reduces the image when it was the last one) while the other warps
+        // already stream the next chunk
+        if (ga.fold_finalize && warp == 0) image_done<P>(a, img, lane);
     }
-    if (tid == 0) sched_release(ga.sched);
+    if (trace) {
+        ga.trace[blockIdx.x * 4 + 2] = static_cast<long long>(global_ns());
+        ga.trace[blockIdx.x * 4 + 3] = n_done;
+    }
+    // ---- the last CTA to get here finalizes ------------------------------------------------------------------
+    if (tid == 0) {
+        __threadfence();  // this CTA's partials and per-image rows are visible device-wide before it counts itself done
+        const unsigned done = atomicAdd(ga.sched + 1, 1u);
+        const int last = done == gridDim.x - 1;
+        if (last) {
+            ga.sched[0] = 0u, ga.sched[1] = 0u;  // the scheduler line is ready for the next launch that gets it
+            __threadfence();
+        }
+        *is_last = last;
+    }
+    if (!ga.fold_finalize) return;
+    __syncthreads();
+    if (*is_last) {
+        finalize_total<P>(a, reinterpret_cast<double*>(wred));
+        if (trace) ga.trace[static_cast<long long>(gridDim.x) * 4] = static_cast<long long>(global_ns());
+    }
 }
 
 }  // namespace dh

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "../../include/densehead.h"
 
@@ -19,6 +20,10 @@ struct dh_handle_s {
     int encode_min_chunk;      // DH_OPT_ENCODE_MIN_CHUNK
     int fcos_select_mode;  // DH_OPT_FCOS_SELECT
     int nms_sort;          // DH_OPT_NMS_SORT
+    int loss_allreduce;    // DH_OPT_LOSS_ALLREDUCE
+    int allreduce_mode;    // DH_OPT_ALLREDUCE
+    int fused_tail;        // DH_OPT_FUSED_TAIL
+    int encode_kernel;     // DH_OPT_ENCODE_KERNEL
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
     size_t scratch_bytes;
@@ -27,6 +32,15 @@ struct dh_handle_s {
     long long* phase_cycles;  // DH_OPT_PHASE_TIMING: device [8] counters (profiling aid)
     unsigned int* sched;      // ring of tile-scheduler counters (one per launch in flight)
     int sched_next;
+    // Entry points hold this for the duration of the call (host side only): two threads sharing a handle cannot race
+    // on the scratch arenas or the scheduler ring.  Recursive because the pipelines call other entry points.
+    std::recursive_mutex mu;
+    long long* trace;  // dh_set_trace: caller-owned device buffer for the fused kernel's per-CTA time stamps
+    long long trace_bytes;
+    unsigned int* img_cnt;  // per-image chunk counters of the fused loss kernel (zero between launches)
+    int img_cnt_cap;
+    int* dev_status;  // device word: sticky input-validation bits (dh_get_status)
+    void* comm;  // dh::Comm* once dh_comm_* has been called (comm.cu)
 };
 
 namespace dh {
@@ -37,6 +51,8 @@ void* scratch(dh_handle_s* h, size_t bytes);
 void* scratch_b(dh_handle_s* h, size_t bytes);
 // A zeroed (stream-ordered) device counter for one kernel's dynamic tile scheduler; null on error.
 unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st);
+// Zeroed per-image counters for at least `batch` images (grown, with a device synchronisation, on demand); null on error.
+unsigned int* image_counters(dh_handle_s* h, int batch);
 
 #define DH_CHECK_ARG(cond, ...)                                      \
     do {                                                             \
@@ -60,12 +76,22 @@ unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st);
 struct DeviceGuard {
     int prev;
     bool ok;
-    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    std::recursive_mutex* mu;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false), mu(nullptr) { enter(dev); }
+    // the form the entry points use: also serialises the calling threads on the handle
+    explicit DeviceGuard(dh_handle_s* h) : prev(-1), ok(false), mu(&h->mu) {
+        mu->lock();
+        enter(h->device);
+    }
+    void enter(int dev) {
         if (cudaGetDevice(&prev) == cudaSuccess && (prev == dev || cudaSetDevice(dev) == cudaSuccess)) ok = true;
     }
     ~DeviceGuard() {
         if (ok && prev >= 0) cudaSetDevice(prev);
+        if (mu) mu->unlock();
     }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
 }  // namespace dh

@@ -16,6 +16,7 @@
 //
 // Reference formulas: FCOS/fcos.py:380-496 (identical copies in the other modules).
 #pragma once
+#include "dh_comm.cuh"
 #include "dh_encode_kernel.cuh"  // build_candidates / total_candidates
 
 namespace dh {
@@ -39,6 +40,15 @@ struct NoPolicy {
     };
 };
 
+constexpr int kMaxChunkTiers = 4;
+struct ChunkTier {
+    long long chunk0;  // id of the tier's first chunk
+    int image0;        // first image of the tier
+    int chunk_tiles;   // tiles per chunk
+    int cpi;           // chunks per image
+    int pad_;
+};
+
 template <class P>
 struct LossArgs {
     TileTable tt;  // maps[m].pred = predictions, maps[m].out = targets (unfused)
@@ -54,7 +64,20 @@ struct LossArgs {
     int chunks_per_image;
     int allow_vec;  // every map pointer is 16-byte aligned
     unsigned int* sched;
-    float* partials;  // [batch * chunks_per_image, 4]
+    float* partials;  // [n_chunks, 4]
+    // fused stream + correct kernel only: the batch is cut into up to four runs of images ("tiers") with ever finer
+    // chunks, so that the launch ends on short chunks (tail = one fine chunk, not one coarse one); the last CTA to
+    // finish reduces the partials (per image, then the total) and, when asked, exchanges the total with the peer ranks
+    int n_tiers;
+    ChunkTier tiers[kMaxChunkTiers];
+    long long n_chunks;
+    float* per_image;  // [batch, 4] (caller's buffer or scratch)
+    unsigned int* img_cnt;  // [batch] chunks finished per image; zero between launches (the reducing warp resets it)
+    float* out_total;  // [4] or null
+    int fold_finalize;  // 1: the last CTA finalizes (no finalize kernels follow)
+    int use_comm;       // 1: out_total is summed over the ranks of `comm` (peer mailboxes)
+    CommDev comm;
+    long long* trace;  // profiling aid (dh_set_trace): per CTA {start, first chunk ready, loop end (globaltimer ns), chunks}
     const float* mask_maps[DH_MAX_MAPS];
     float* grad_maps[DH_MAX_MAPS];  // null: forward only; else d loss / d pred, same layout as the predictions
 };

@@ -28,6 +28,13 @@ __device__ __forceinline__ Corners pixel_corners(const float* g, float hi, float
     c.x1 = fmul(fadd(g[1], hw), wi);
     return c;
 }
+// A GT class outside [0, num_classes) would index past the row's class channels (the reference raises IndexError,
+// FCOS/fcos.py:281-283): the box is dropped and bit 1 of the status word is set; the host wrappers raise.
+__device__ __forceinline__ bool bad_class(int cls, int num_classes, int* status) {
+    const bool bad = cls < 0 || cls >= num_classes;
+    if (bad && status) atomicOr(status, 2);
+    return bad;
+}
 // the reference's paint order is ascending area (stable): the later painter is the larger
 // (area, index) pair.
 __device__ __forceinline__ bool paints_later(float area, int k, float best_area, int best_k) {
@@ -81,6 +88,7 @@ struct FcosPolicy {
         float b_dim[DH_MAX_LEVELS];  // n_levels-1 thresholds
         int hl[DH_MAX_LEVELS], wl[DH_MAX_LEVELS];
         int* num_targets;  // [B, n_levels] or null
+        int* status;       // bit1: a GT class outside [0, num_classes) was dropped (the reference raises IndexError)
     };
     struct Rec {
         float y0s, x0s, y1s, x1s;  // corners / stride  (CENTER_V1: the four regression values)
@@ -106,6 +114,7 @@ struct FcosPolicy {
         r.level = l;
         r.area = fmul(gh, gw);  // fcos.py:202-204
         r.cls = trunc_i(g[4]);
+        const bool bad_cls = bad_class(r.cls, p.num_classes, p.status);
         const float s = p.stride_f[l];
         const int hl = p.hl[l], wl = p.wl[l];
         const Corners c = pixel_corners(g, hi, wi);
@@ -120,7 +129,7 @@ struct FcosPolicy {
             r.x1s = fdiv(gw, box_sc);
             r.ry0 = i, r.ry1 = i + 1, r.rx0 = j, r.rx1 = j + 1;
             r.ycen = i, r.xcen = j;
-            if (i < 0 || j < 0 || i >= hl || j >= wl) flags = 0;
+            if (i < 0 || j < 0 || i >= hl || j >= wl || bad_cls) flags = 0;
             r.flags = flags;
             return;
         }
@@ -154,7 +163,7 @@ struct FcosPolicy {
             r.ry0 = r.ycen - rad, r.ry1 = r.ycen + rad + 1;
             r.rx0 = r.xcen - rad, r.rx1 = r.xcen + rad + 1;
         }
-        r.flags = flags;
+        r.flags = bad_cls ? 0 : flags;
     }
 
     __device__ static void image_prologue(const Params& p, const Rec* recs, int n, int b) {
@@ -185,6 +194,12 @@ struct FcosPolicy {
         if (i0 != i1) return true;
         const int j0 = ti.r0 - i0 * md.width, j1 = last - i0 * md.width;
         return r.rx1 > j0 && r.rx0 <= j1;
+    }
+
+    // a contiguous row interval [rlo, rhi] of the map that holds every row this box can touch (rlo > rhi: none)
+    __device__ static void row_span(const Params&, const Rec& r, const MapDesc& md, int, int, int& rlo, int& rhi) {
+        rlo = r.ry0 * md.width + r.rx0;
+        rhi = (r.ry1 - 1) * md.width + r.rx1 - 1;
     }
 
     // returns the number of painters that touched the row (0 = row stays zero)
@@ -258,6 +273,7 @@ struct RetinaPolicy {
         float anchor_h[DH_MAX_LEVELS][12], anchor_w[DH_MAX_LEVELS][12];
         float thr;
         int* num_pairs;  // [B] (zeroed by the launcher) or null
+        int* status;     // see FcosPolicy::Params
     };
     struct Rec {
         float gy, gx, gh, gw;
@@ -274,6 +290,7 @@ struct RetinaPolicy {
         r.lo_y = fsub(r.gy, hh), r.lo_x = fsub(r.gx, hw), r.hi_y = fadd(r.gy, hh), r.hi_x = fadd(r.gx, hw);
         r.area = fmul(r.gh, r.gw);
         r.cls = trunc_i(g[4]);
+        if (bad_class(r.cls, p.num_classes, p.status)) r.cls = -1;  // never matches (tile_hit / map_hit)
     }
     __device__ static void image_prologue(const Params&, const Rec*, int, int) {}
     // positive (gt, anchor) pairs of the tile -> num_pairs[b] (integer atomics: order-independent)
@@ -287,6 +304,7 @@ struct RetinaPolicy {
     //   IoU <= min(area)/max(area),  IoU <= overlap_y / max(ah, gh),  IoU <= overlap_x / max(aw, gw)
     // (inter <= oy * min(aw, gw) and union >= max(ah, gh) * min(aw, gw)).  0.999 covers float rounding.
     __device__ static bool tile_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
+        if (r.cls < 0) return false;
         if (p.thr < 0.f) return true;
         const float ah = p.anchor_h[ti.level][ti.anchor], aw = p.anchor_w[ti.level][ti.anchor];
         const float s = static_cast<float>(p.stride[ti.level]);
@@ -304,6 +322,7 @@ struct RetinaPolicy {
     }
 
     __device__ static bool map_hit(const Params& p, const Rec& r, int level, int anchor) {
+        if (r.cls < 0) return false;
         if (!(p.thr > 0.f)) return true;
         const float ah = p.anchor_h[level][anchor], aw = p.anchor_w[level][anchor];
         const float aa = ah * aw, k = 0.999f * p.thr;
@@ -326,6 +345,31 @@ struct RetinaPolicy {
         const float j0 = static_cast<float>(ti.r0 - i0 * md.width), j1 = static_cast<float>(last - i0 * md.width);
         const float need_x = k * fmaxf(aw, r.gw);
         return j1 * s + 0.5f * aw > r.lo_x + need_x - 0.01f && j0 * s - 0.5f * aw < r.hi_x - need_x + 0.01f;
+    }
+
+    // a contiguous row interval [rlo, rhi] of the (level, anchor) map that holds every anchor this box can match: the
+    // inverse of range_hit's tests (anchor row i needs i*s + ah/2 > lo_y + need - 0.01 and i*s - ah/2 < hi_y - need + 0.01),
+    // widened by a cell on each side
+    __device__ static void row_span(const Params& p, const Rec& r, const MapDesc& md, int level, int anchor, int& rlo, int& rhi) {
+        if (p.thr < 0.f) {
+            rlo = 0, rhi = md.rows - 1;
+            return;
+        }
+        const float ah = p.anchor_h[level][anchor], aw = p.anchor_w[level][anchor];
+        const float inv_s = 1.0f / static_cast<float>(p.stride[level]);
+        const float k = p.thr > 0.f ? 0.999f * p.thr : 0.f;
+        const float need_y = k * fmaxf(ah, r.gh) - 0.01f, need_x = k * fmaxf(aw, r.gw) - 0.01f;
+        const float hmax = static_cast<float>(md.height), wmax = static_cast<float>(md.width);
+        const int ilo = static_cast<int>(fminf(fmaxf(floorf((r.lo_y + need_y - 0.5f * ah) * inv_s), 0.f), hmax));
+        const int ihi = static_cast<int>(fminf(fmaxf(ceilf((r.hi_y - need_y + 0.5f * ah) * inv_s), -1.f), hmax - 1.f));
+        const int jlo = static_cast<int>(fminf(fmaxf(floorf((r.lo_x + need_x - 0.5f * aw) * inv_s), 0.f), wmax));
+        const int jhi = static_cast<int>(fminf(fmaxf(ceilf((r.hi_x - need_x + 0.5f * aw) * inv_s), -1.f), wmax - 1.f));
+        if (ilo > ihi || jlo > jhi) {
+            rlo = 1, rhi = 0;
+            return;
+        }
+        rlo = ilo * md.width + jlo;
+        rhi = ihi * md.width + jhi;
     }
 
     // returns the number of (gt, anchor) pairs above the threshold at this row (:302-317)
@@ -385,7 +429,7 @@ struct CenterNetPolicy {
         float stride_f, sigma;
         float scales[8];
         int pad0, pad1;  // img_pad[0], img_pad[1]
-        int* status;     // bit0: a box was not below the largest scale (reference raises ValueError)
+        int* status;     // bit0: a box was not below the largest scale (reference raises ValueError); bit1: bad class
     };
     struct Rec {
         float r0, r1, r2, r3;  // ONEHOT/HOURGLASS: regression values; FALLOFF: y0s, x0s, y1s, x1s
@@ -409,6 +453,10 @@ struct CenterNetPolicy {
         r.cls = trunc_i(g[4]);
         r.flags = 4;
         r.row = -1;
+        if (bad_class(r.cls, p.num_classes, p.status)) {
+            r.flags = 0;
+            return;
+        }
         if (p.mode == CN_POWER_FALLOFF) {  // tf_centernet.py:165-223
             const float h_ratio = fdiv(hi, s), w_ratio = fdiv(wi, s);
             const int hl = static_cast<int>(static_cast<double>(p.pad0) / p.stride);
@@ -527,6 +575,15 @@ struct CenterNetPolicy {
         if (i0 != i1) return true;
         const int j0 = ti.r0 - i0 * md.width, j1 = last - i0 * md.width;
         return r.rx1 > j0 && r.rx0 <= j1;
+    }
+
+    __device__ static void row_span(const Params& p, const Rec& r, const MapDesc& md, int, int, int& rlo, int& rhi) {
+        if (p.mode != CN_POWER_FALLOFF) {
+            rlo = rhi = r.row;
+            return;
+        }
+        rlo = r.ry0 * md.width + r.rx0;
+        rhi = (r.ry1 - 1) * md.width + r.rx1 - 1;
     }
 
     // Scatter emission for the centre-cell modes: thread q owns candidate q, whose target is a single

@@ -218,7 +218,7 @@ int dh_fcos_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, const
     DH_CHECK_ARG(h && boxes && img_dim && strides && out_levels, "dh_fcos_encode: NULL argument");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_fcos_encode: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_fcos_encode: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     EncodeArgs<FcosPolicy> a;
     memset(&a, 0, sizeof(a));
     int rc = fill_fcos(a.pp, a.tt, pad_h, pad_w, n_levels, strides, b_dim, num_classes, mode, out_levels, nullptr,
@@ -226,6 +226,7 @@ int dh_fcos_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, const
     if (rc) return rc;
     a.tile_buf_bytes = finish_table(a.tt, num_classes + 5, batch, auto_tile_bytes(a.tt, num_classes + 5, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    a.pp.status = h->dev_status;
     return launch_encode<FcosPolicy>(h, a, static_cast<cudaStream_t>(stream), "dh_fcos_encode");
 }
 
@@ -236,7 +237,7 @@ int dh_retina_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, con
     DH_CHECK_ARG(h && boxes && img_dim && strides && anchor_hw && out_levels, "dh_retina_encode: NULL argument");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_retina_encode: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_retina_encode: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EncodeArgs<RetinaPolicy> a;
     memset(&a, 0, sizeof(a));
@@ -245,6 +246,7 @@ int dh_retina_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, con
     if (rc) return rc;
     a.tile_buf_bytes = finish_table(a.tt, num_classes + 4, batch, auto_tile_bytes(a.tt, num_classes + 4, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    a.pp.status = h->dev_status;
     if (num_pairs && batch > 0) DH_CUDA(cudaMemsetAsync(num_pairs, 0, sizeof(int32_t) * batch, st));
     return launch_encode<RetinaPolicy>(h, a, st, "dh_retina_encode");
 }
@@ -255,7 +257,7 @@ int dh_centernet_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, 
     DH_CHECK_ARG(h && boxes && img_dim && out, "dh_centernet_encode: NULL argument");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_centernet_encode: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_centernet_encode: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EncodeArgs<CenterNetPolicy> a;
     memset(&a, 0, sizeof(a));
@@ -266,6 +268,7 @@ int dh_centernet_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, 
     a.tile_buf_bytes = finish_table(a.tt, ch, batch, auto_tile_bytes(a.tt, ch, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    else a.pp.status = h->dev_status;
     return launch_encode<CenterNetPolicy>(h, a, st, "dh_centernet_encode");
 }
 

@@ -145,7 +145,7 @@ int dh_compute_iou(dh_handle_t h, const float* boxes1, int n, const float* boxes
     DH_CHECK_ARG(n >= 0 && m >= 0, "dh_compute_iou: bad sizes");
     const long long total = static_cast<long long>(n) * m;
     if (total == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     long long g = (total + 255) / 256;
     if (g > static_cast<long long>(h->sm_count) * 16) g = static_cast<long long>(h->sm_count) * 16;
     compute_iou_kernel<<<static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes1, n, boxes2, m, out);
@@ -159,7 +159,7 @@ int dh_bboxes_iou(dh_handle_t h, const double* boxes1, int n1, const double* box
     DH_CHECK_ARG(n1 >= 0 && n2 >= 0 && (n1 == n2 || n1 == 1 || n2 == 1), "dh_bboxes_iou: shapes %d and %d do not broadcast", n1, n2);
     const int n = (n1 == 0 || n2 == 0) ? 0 : (n1 > n2 ? n1 : n2);
     if (n == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     bboxes_iou_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes1, n1, boxes2, n2, out);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -170,7 +170,7 @@ int dh_centernet_nms(dh_handle_t h, const double* rows, int n, const double* cla
                      double sigma, int soft, double* out_rows, int32_t* out_src, int32_t* n_out, void* stream) {
     DH_CHECK_ARG(h && out_rows && out_src && n_out, "dh_centernet_nms: NULL argument");
     DH_CHECK_ARG(n >= 0 && n_classes >= 0 && (n == 0 || (rows && classes)), "dh_centernet_nms: bad arguments");
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n == 0 || n_classes == 0) {
         DH_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), st));

@@ -99,7 +99,7 @@ int dh_box_convert(dh_handle_t h, const float* boxes, long long n, int mode, flo
     DH_CHECK_ARG(h && boxes && out, "dh_box_convert: NULL argument");
     DH_CHECK_ARG(((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0, "dh_box_convert: buffers must be 16-byte aligned");
     if (n == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     box_convert_kernel<<<grid1d(n, 256, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(boxes), n, mode, reinterpret_cast<float4*>(out));
     DH_CUDA(cudaGetLastError());
@@ -113,7 +113,7 @@ int dh_prepare_labels(dh_handle_t h, const float* raw_boxes, const float* classe
     DH_CHECK_ARG(h && raw_boxes && classes && out_labels, "dh_prepare_labels: NULL argument");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 1 && (box_offsets || in_max_boxes >= 0), "dh_prepare_labels: bad sizes");
     if (batch == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     prepare_labels_kernel<<<grid1d(static_cast<long long>(batch) * max_boxes, 256, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         raw_boxes, classes, box_offsets, nbox, flip, batch, max_boxes, in_max_boxes, out_labels, out_nbox);
     DH_CUDA(cudaGetLastError());
@@ -127,7 +127,7 @@ int dh_format_detections(dh_handle_t h, const float* rows, const int32_t* n_keep
     DH_CHECK_ARG(batch >= 0 && n >= 0, "dh_format_detections: bad sizes");
     DH_CHECK_ARG((reinterpret_cast<uintptr_t>(out_boxes) & 15u) == 0, "dh_format_detections: out_boxes must be 16-byte aligned");
     if (batch == 0 || n == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     format_detections_kernel<<<grid1d(static_cast<long long>(batch) * n, 256, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         rows, n_keep, ratios, batch, n, out_boxes, out_scores, out_labels);
     DH_CUDA(cudaGetLastError());

@@ -7,6 +7,8 @@
 
 namespace dh {
 
+const CommDev* comm_dev_if_fused(dh_handle_s* h);  // comm.cu
+
 static int check_spec(const LossSpec& s, const char* who) {
     if (!(s.reg_ch == 0 || s.reg_ch == 4)) return set_error(DH_ERR_BAD_ARG, "%s: reg_ch must be 0 or 4", who);
     if (s.cen_mode < 0 || s.cen_mode > 3) return set_error(DH_ERR_BAD_ARG, "%s: cen_mode %d", who, s.cen_mode);
@@ -98,7 +100,55 @@ static int finalize_loss(dh_handle_s* h, const float* partials, int batch, int c
     return DH_OK;
 }
 
-// Fused encode+loss, stream + correct formulation (dh_fused_loss_kernel.cuh): 256-row tiles, 32 rows per warp.
+// The tiered chunk plan of the fused kernel (LossArgs::tiers): tier 0 holds most images in chunks of about `ct0` tiles;
+// with `tail` the last images are cut into chunks of ct0/2, ct0/4, ... 1 tiles.  A tier is sized so that its tiles
+// absorb the stagger of the tier before it (CTAs leave a tier spread over one of its chunk times: grid * ct / 2 tiles).
+template <class P>
+static void plan_tiers(LossArgs<P>& a, long long grid, int ct0, bool tail) {
+    const int tpi = a.tt.tiles_per_image, batch = a.tt.batch;
+    int cts[kMaxChunkTiers], imgs[kMaxChunkTiers], n = 0;
+    cts[n++] = ct0;
+    if (tail && tpi > 0)
+        for (int c = ct0 / 2; c >= 1 && n < kMaxChunkTiers; c /= 2) cts[n++] = c;
+    long long need[kMaxChunkTiers] = {0, 0, 0, 0}, need_total = 0;
+    for (int k = 1; k < n; ++k) {
+        need[k] = (grid * cts[k - 1] / 2 + tpi - 1) / tpi;
+        if (need[k] < 1) need[k] = 1;
+        need_total += need[k];
+    }
+    if (need_total > batch / 2) {  // a small batch: the fine tiers share half of it (or vanish)
+        for (int k = 1; k < n; ++k) need[k] = need_total > 0 ? need[k] * (batch / 2) / need_total : 0;
+    }
+    int left = batch;
+    for (int k = n - 1; k >= 1; --k) {
+        imgs[k] = static_cast<int>(need[k]);
+        left -= imgs[k];
+    }
+    imgs[0] = left;
+    a.n_tiers = 0;
+    long long chunk0 = 0;
+    int image0 = 0;
+    for (int k = 0; k < n; ++k) {
+        if (imgs[k] <= 0 && !(k == 0 && batch == 0)) continue;
+        ChunkTier& T = a.tiers[a.n_tiers++];
+        const int n_sub = tpi > 0 ? (tpi + cts[k] - 1) / cts[k] : 1;
+        T.chunk_tiles = tpi > 0 ? (tpi + n_sub - 1) / n_sub : 1;
+        T.cpi = tpi > 0 ? (tpi + T.chunk_tiles - 1) / T.chunk_tiles : 1;
+        T.chunk0 = chunk0, T.image0 = image0, T.pad_ = 0;
+        chunk0 += static_cast<long long>(imgs[k]) * T.cpi;
+        image0 += imgs[k];
+    }
+    if (a.n_tiers == 0) {
+        a.n_tiers = 1;
+        a.tiers[0] = ChunkTier{0, 0, 1, 1, 0};
+    }
+    a.n_chunks = chunk0;
+    a.chunk_tiles = a.tiers[0].chunk_tiles, a.chunks_per_image = a.tiers[0].cpi;
+}
+
+// Fused encode+loss, stream + correct formulation (dh_fused_loss_kernel.cuh): 256-row tiles, 32 rows per warp.  One
+// launch: the kernel's last CTA reduces the chunk partials to the per-image sums and the total (and exchanges the
+// total with the peer ranks when DH_OPT_LOSS_ALLREDUCE is on).
 template <class P, int kCls, bool kGrad>
 static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, float* out_total, cudaStream_t st,
                           const char* who) {
@@ -111,32 +161,44 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kCls, kGrad>, DH_THREADS, lay.total));
     if (per_sm < 1) per_sm = 1;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
-    // image-aligned chunks: aim at >= 8 chunks per CTA, 2..32 tiles (512..8192 rows) each
-    const int tpi = a.tt.tiles_per_image;
     // measured on B200 (tools/fused_loss_probe.py): chunks of 4..8 tiles (1-2 K rows) balance best -- smaller chunks pay
     // the chunk-end barrier too often, larger ones leave a tail
     long long want = total / (grid * h->fused_chunks_per_cta);
     want = want < 4 ? 4 : (want > 8 ? 8 : want);
-    const int n_sub = tpi > 0 ? static_cast<int>((tpi + want - 1) / want) : 1;
-    a.chunk_tiles = tpi > 0 ? (tpi + n_sub - 1) / n_sub : 1;
-    a.chunks_per_image = tpi > 0 ? (tpi + a.chunk_tiles - 1) / a.chunk_tiles : 1;
-    const long long n_chunks = static_cast<long long>(a.tt.batch) * a.chunks_per_image;
+    plan_tiers(a, grid, static_cast<int>(want), h->fused_tail != 0);
+    const long long n_chunks = a.n_chunks;
     if (grid > n_chunks) grid = n_chunks;
+    if (grid < 1) grid = 1;
     const size_t part_bytes = static_cast<size_t>(n_chunks) * 16;
     const size_t img_bytes = static_cast<size_t>(a.tt.batch) * 16;
     char* sc = static_cast<char*>(scratch(h, part_bytes + img_bytes + 512));
     if (!sc) return DH_ERR_CUDA;
     a.partials = reinterpret_cast<float*>(sc);
-    float* per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
-    if (total > 0) {
-        a.sched = next_sched_counter(h, st);
-        if (!a.sched) return DH_ERR_CUDA;
-        fused_loss_kernel<P, kCls, kGrad><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
-        DH_CUDA(cudaGetLastError());
-        h->launches += 1;
+    a.per_image = out_per_image ? out_per_image : reinterpret_cast<float*>(sc + ((part_bytes + 255) & ~size_t(255)));
+    a.out_total = out_total;
+    a.fold_finalize = (out_per_image || out_total) ? 1 : 0;
+    a.use_comm = 0;
+    if (out_total) {
+        if (const CommDev* cd = comm_dev_if_fused(h)) a.comm = *cd, a.use_comm = 1;
     }
+    if (total == 0) {  // no tiles at all (maps of zero cells): the sums are zero
+        if (a.fold_finalize) DH_CUDA(cudaMemsetAsync(a.per_image, 0, img_bytes, st));
+        if (out_total) {
+            DH_CUDA(cudaMemsetAsync(out_total, 0, 16, st));
+            if (a.use_comm) return dh_allreduce_loss(h, out_total, 4, st);
+        }
+        return DH_OK;
+    }
+    a.sched = next_sched_counter(h, st);
+    if (!a.sched) return DH_ERR_CUDA;
+    a.img_cnt = image_counters(h, a.tt.batch);
+    if (!a.img_cnt) return DH_ERR_CUDA;
+    a.trace = (h->trace && h->trace_bytes >= (grid * 4 + 1) * 8) ? h->trace : nullptr;
+    fused_loss_kernel<P, kCls, kGrad><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 1;
     (void)who;
-    return finalize_loss(h, a.partials, a.tt.batch, total > 0 ? a.chunks_per_image : 0, per_image, out_total, st);
+    return DH_OK;
 }
 
 // Picks the fused kernel: stream + correct when the class bitmask fits (<= 128 classes), else the shared-memory
@@ -264,7 +326,7 @@ static int dense_loss_impl(const GradOut* go, dh_handle_t h, int n_maps, const f
     if (rc) return rc;
     DH_CHECK_ARG(ch >= reg_ch + (cen_mode != 0 ? 1 : 0), "dh_dense_loss: ch %d too small for the channel layout", ch);
     DH_CHECK_ARG(pos_rule != 2 || mask_maps, "dh_dense_loss: pos_rule 2 needs mask_maps");
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     a.tt.n_maps = n_maps;
     for (int m = 0; m < n_maps; ++m) {
         DH_CHECK_ARG(target_maps[m] && pred_maps[m], "dh_dense_loss: map %d pointer is NULL", m);
@@ -299,7 +361,7 @@ static int fcos_encode_loss_impl(const GradOut* go, dh_handle_t h, const float* 
     DH_CHECK_ARG(go || out_per_image || out_total, "dh_fcos_encode_loss: no output requested");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_fcos_encode_loss: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_fcos_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     LossArgs<FcosPolicy> a;
     memset(&a, 0, sizeof(a));
     int rc = fill_fcos(a.pp, a.tt, pad_h, pad_w, n_levels, strides, b_dim, num_classes, mode, nullptr, pred_levels,
@@ -312,6 +374,7 @@ static int fcos_encode_loss_impl(const GradOut* go, dh_handle_t h, const float* 
     if (rc) return rc;
     a.tt.ch = num_classes + 5, a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    a.pp.status = h->dev_status;
     if (go) {
         a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
         for (int m = 0; m < a.tt.n_maps; ++m) {
@@ -332,7 +395,7 @@ static int retina_encode_loss_impl(const GradOut* go, dh_handle_t h, const float
     DH_CHECK_ARG(go || out_per_image || out_total, "dh_retina_encode_loss: no output requested");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_retina_encode_loss: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_retina_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossArgs<RetinaPolicy> a;
     memset(&a, 0, sizeof(a));
@@ -343,6 +406,7 @@ static int retina_encode_loss_impl(const GradOut* go, dh_handle_t h, const float
     a.spec.alpha = alpha, a.spec.gamma = gamma, a.spec.delta = delta;
     a.tt.ch = num_classes + 4, a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
+    a.pp.status = h->dev_status;
     if (num_pairs && batch > 0) DH_CUDA(cudaMemsetAsync(num_pairs, 0, sizeof(int32_t) * batch, st));
     if (go) {
         a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
@@ -364,7 +428,7 @@ static int centernet_encode_loss_impl(const GradOut* go, dh_handle_t h, const fl
     DH_CHECK_ARG(go || out_per_image || out_total, "dh_centernet_encode_loss: no output requested");
     DH_CHECK_ARG(batch >= 0 && max_boxes >= 0, "dh_centernet_encode_loss: bad sizes");
     if (max_boxes > DH_MAX_BOXES) return set_error(DH_ERR_CAPACITY, "dh_centernet_encode_loss: max_boxes %d > %d", max_boxes, DH_MAX_BOXES);
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LossArgs<CenterNetPolicy> a;
     memset(&a, 0, sizeof(a));
@@ -381,6 +445,7 @@ static int centernet_encode_loss_impl(const GradOut* go, dh_handle_t h, const fl
     a.tt.ch = num_classes + ((falloff || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4), a.tt.batch = batch;
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    else a.pp.status = h->dev_status;
     if (go) {
         a.spec.w_cls = go->w_cls, a.spec.w_reg = go->w_reg, a.spec.w_cen = go->w_cen;
         DH_CHECK_ARG(go->grad[0], "gradient pointer is NULL");

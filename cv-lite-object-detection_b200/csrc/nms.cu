@@ -471,7 +471,7 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     DH_CHECK_ARG(mode != DH_NMS_PER_CLASS || max_per_class <= 0 || (num_classes >= 1 && num_classes <= 8192),
                  "dh_nms: per-class caps need 1..8192 classes");
     if (batch == 0) return DH_OK;
-    DeviceGuard guard(h->device);
+    DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_max == 0) {
         DH_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int32_t) * batch, st));

@@ -10,9 +10,9 @@ keeps everything on the device.  All arithmetic runs in libdensehead.so (hand-wr
 """
 from . import _capi
 from ._capi import DenseHeadError, launch_count, set_option  # noqa: F401
-from . import fcos, retinanet, centernet, prep  # noqa: F401
+from . import fcos, retinanet, centernet, prep, distributed  # noqa: F401
 
-__all__ = ["fcos", "retinanet", "centernet", "prep", "DenseHeadError", "launch_count", "set_option", "version"]
+__all__ = ["fcos", "retinanet", "centernet", "prep", "distributed", "DenseHeadError", "launch_count", "set_option", "version"]
 
 
 def version():

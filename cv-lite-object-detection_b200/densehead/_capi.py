@@ -13,8 +13,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DENSEHEAD_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libdensehead.so"))
 
 DH_OK = 0
-DH_ERR_BAD_ARG, DH_ERR_SHAPE, DH_ERR_CUDA, DH_ERR_CAPACITY = -1, -2, -3, -4
+DH_ERR_BAD_ARG, DH_ERR_SHAPE, DH_ERR_CUDA, DH_ERR_CAPACITY, DH_ERR_NCCL = -1, -2, -3, -4, -5
 DH_OPT_TMA_STORE, DH_OPT_TILE_BYTES, DH_OPT_CTAS_PER_SM = 1, 2, 3
+DH_OPT_LOSS_ALLREDUCE, DH_OPT_ALLREDUCE, DH_OPT_FUSED_TAIL, DH_OPT_ENCODE_KERNEL = 11, 12, 13, 14
+DH_STATUS_BAD_SCALE, DH_STATUS_BAD_CLASS, DH_STATUS_COMM_TIMEOUT = 1, 2, 4
+DH_UNIQUE_ID_BYTES, DH_IPC_HANDLE_BYTES = 128, 64
 DH_MAX_BOXES_PER_IMAGE = 256
 
 c_fp = ctypes.POINTER(ctypes.c_float)
@@ -79,6 +82,16 @@ def lib():
         L.dh_compute_iou.argtypes = [P, P, I, P, I, P, P]
         L.dh_bboxes_iou.argtypes = [P, P, I, P, I, P, P]
         L.dh_centernet_nms.argtypes = [P, P, I, P, I, D, D, I, P, P, P, P]
+        L.dh_get_status.argtypes = [P, c_ip, I]
+        L.dh_set_trace.argtypes = [P, P, ctypes.c_longlong]
+        L.dh_comm_get_unique_id.argtypes = [P]
+        L.dh_comm_init_rank.argtypes = [P, I, I, P]
+        L.dh_comm_init_all.argtypes = [PP, I]
+        L.dh_comm_peer_export.argtypes = [P, P]
+        L.dh_comm_peer_import.argtypes = [P, I, I, P]
+        L.dh_comm_info.argtypes = [P, c_ip, c_ip, c_ip]
+        L.dh_allreduce_loss.argtypes = [P, P, I, P]
+        L.dh_comm_destroy.argtypes = [P]
         for name, proto in _OPTIONAL.items():
             if hasattr(L, name):
                 getattr(L, name).argtypes = proto
@@ -109,6 +122,25 @@ def handle(device_index):
                 check(lib().dh_create(ctypes.byref(out), int(device_index)), "dh_create")
                 h = _handles[device_index] = out
     return h
+
+
+def status(device_index=0, reset=True):
+    """Sticky validation bits of the device's handle (DH_STATUS_*); synchronises."""
+    out = ctypes.c_int32(0)
+    check(lib().dh_get_status(handle(device_index), ctypes.byref(out), 1 if reset else 0), "dh_get_status")
+    return int(out.value)
+
+
+def raise_for_status(device_index=0):
+    """Raise what the reference raises for the inputs the kernels flagged: IndexError for a GT class outside
+    [0, num_classes) (FCOS/fcos.py:281-283), ValueError for a CenterNet box not below the largest box scale."""
+    bits = status(device_index)
+    if bits & DH_STATUS_BAD_CLASS:
+        raise IndexError("a ground-truth class index is out of bounds for num_classes")
+    if bits & DH_STATUS_BAD_SCALE:
+        raise ValueError("min() arg is an empty sequence (a box is not below the largest box scale)")
+    if bits & DH_STATUS_COMM_TIMEOUT:
+        raise DenseHeadError("a peer rank did not arrive at the loss all-reduce")
 
 
 def set_option(device_index, option, value):

@@ -27,6 +27,43 @@ def _is_dlpack_capsule(x):
     return type(x).__name__ == "PyCapsule"
 
 
+_KDL_CUDA = (2, 13)  # DLDeviceType: kDLCUDA, kDLCUDAManaged
+
+
+def _on_cuda(x):
+    """True when `x` speaks DLPack and says it lives in CUDA memory."""
+    try:
+        return int(x.__dlpack_device__()[0]) in _KDL_CUDA
+    except Exception:
+        return False
+
+
+def _tf_gpu_capsule(x):
+    """TensorFlow eager tensors before `__dlpack__` existed: tf.experimental.dlpack.to_dlpack."""
+    if not type(x).__module__.startswith("tensorflow") or "GPU" not in str(getattr(x, "device", "")):
+        return None
+    try:
+        import tensorflow as tf
+        return tf.experimental.dlpack.to_dlpack(x)
+    except Exception:
+        return None
+
+
+def uses_stream(fn):
+    """Run a wrapper that takes `stream=` with that stream current: its staging copies and output allocations are then
+    ordered on (and owned by) the stream the kernels are launched on."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        stream = kwargs.get("stream")
+        if stream is None or stream == torch.cuda.current_stream():
+            return fn(*args, **kwargs)
+        with torch.cuda.stream(stream):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def as_host(x, dtype=np.float32):
     """Host NumPy view/copy of a small input (GT labels, image size)."""
     if isinstance(x, torch.Tensor):
@@ -66,8 +103,15 @@ def to_device(x, dtype, device=None):
     device = device or current_device()
     if _is_dlpack_capsule(x):
         x = torch.utils.dlpack.from_dlpack(x)
-    elif not isinstance(x, (torch.Tensor, np.ndarray)) and hasattr(x, "__dlpack__") and not hasattr(x, "numpy"):
-        x = torch.from_dlpack(x)
+    elif not isinstance(x, (torch.Tensor, np.ndarray)):
+        # device-resident objects cross zero-copy even when they also offer .numpy() (a TensorFlow EagerTensor on the
+        # GPU does): asking for .numpy() there would be a D2H + H2D round trip
+        if hasattr(x, "__dlpack__") and (_on_cuda(x) or not hasattr(x, "numpy")):
+            x = torch.from_dlpack(x)
+        else:
+            cap = _tf_gpu_capsule(x)
+            if cap is not None:
+                x = torch.utils.dlpack.from_dlpack(cap)
     if isinstance(x, torch.Tensor):
         if x.is_cuda:
             if x.device != device:

@@ -4,12 +4,13 @@ import numpy as np
 import torch
 
 from . import _capi, infer, losses
-from ._batch import image_dims, pack_labels
-from ._tensors import as_host, current_device, stream_ptr, to_device
+from ._batch import image_dims, pack_labels, check_classes
+from ._tensors import as_host, current_device, stream_ptr, to_device, uses_stream
 
 MODES = {"s8": 0, "hourglass": 1, "falloff": 2, "hourglass4": 3}
 
 
+@uses_stream
 def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, stride=8, mode="s8", box_scales=None, sigma=0.25,
                       out=None, status=None, stream=None):
     """Encode a padded batch.  Output shape: s8 [B, H, W, S, C+4]; hourglass [B, H, W, C+4];
@@ -17,6 +18,7 @@ def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, stride=8, mode
     the unpadded square side per image, `img_pad` the padded one).  `img_pad` is passed through with the reference's own
     indexing."""
     dev = current_device()
+    check_classes(boxes, nbox, num_classes)
     boxes_d = to_device(boxes, torch.float32, dev)
     if boxes_d.dim() != 3 or boxes_d.shape[2] != 5:
         raise ValueError("boxes must be [B, Nmax, 5]")
@@ -146,11 +148,13 @@ def model_loss(y_true, y_pred, reg_type="l1", cen_type="l1"):
     return tot[0], tot[1], tot[2]
 
 
+@uses_stream
 def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride=8, mode="s8", box_scales=None,
                       sigma=0.25, reg_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None, cls_type="focal"):
     """Fused CenterNet encode + loss.  Returns (per_image [B,4], total [4], status [1]); with `weights` = (w_cls,
     w_reg, w_cen) a fourth item, the gradient d(w . {cls, reg, cen}) / d y_pred (dh_centernet_encode_loss_grad)."""
     dev = current_device()
+    check_classes(boxes, nbox, num_classes)
     boxes_d = to_device(boxes, torch.float32, dev)
     batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
     nbox_d = to_device(nbox, torch.int32, dev)

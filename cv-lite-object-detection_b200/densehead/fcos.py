@@ -11,8 +11,8 @@ import numpy as np
 import torch
 
 from . import _capi, infer, losses
-from ._batch import image_dims, pack_labels
-from ._tensors import as_host, current_device, stream_ptr, to_device
+from ._batch import image_dims, pack_labels, check_classes
+from ._tensors import as_host, current_device, stream_ptr, to_device, uses_stream
 
 DEFAULT_STRIDES = [8, 16, 32, 64, 128]
 DEFAULT_B_DIM = [32, 64, 128, 256]
@@ -23,6 +23,7 @@ def level_shapes(img_pad, strides):
     return [(int(img_pad[0] / s), int(img_pad[1] / s)) for s in strides]
 
 
+@uses_stream
 def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, strides=None, b_dim=None, mode="fcos",
                       out=None, num_targets=None, stream=None):
     """Encode a padded batch on the device.
@@ -36,6 +37,7 @@ def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, strides=None, 
     if len(b_dim) != len(strides) - 1:
         raise ValueError("b_dim must have len(strides)-1 entries")
     dev = current_device()
+    check_classes(boxes, nbox, num_classes)
     boxes_d = to_device(boxes, torch.float32, dev)
     if boxes_d.dim() != 3 or boxes_d.shape[2] != 5:
         raise ValueError("boxes must be [B, Nmax, 5]")
@@ -104,6 +106,7 @@ def _as_batched(maps, dev):
     return out
 
 
+@uses_stream
 def model_loss_batch(y_true, y_pred, reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
     """Loss over materialised FCOS targets for a batch -> (per_image [B,4], total [4]) = {cls, reg, cen, n_pos}
     (+ per-level gradients when `weights` = (w_cls, w_reg, w_cen) is given)."""
@@ -136,6 +139,7 @@ def model_loss_center_v1(y_true, y_pred):
     return tot[0], tot[1], tot[2]
 
 
+@uses_stream
 def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, strides=None, b_dim=None, mode="fcos",
                       reg_type="l1", cen_type="l1", alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
     """Fused target encoding + loss: targets never reach HBM.  y_pred: per-level [B, Hl, Wl, C+5].
@@ -144,6 +148,7 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
     strides = list(DEFAULT_STRIDES if strides is None else strides)
     b_dim = list(DEFAULT_B_DIM if b_dim is None else b_dim)
     dev = current_device()
+    check_classes(boxes, nbox, num_classes)
     boxes_d = to_device(boxes, torch.float32, dev)
     batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
     nbox_d = to_device(nbox, torch.int32, dev)
@@ -194,6 +199,7 @@ def prediction_to_corners_center_v1(xy_pred, box_sc, stride):
     return infer.prediction_to_corners(xy_pred, 2, stride, d0=box_sc)
 
 
+@uses_stream
 def decode_batch(head_outputs, num_classes, img_pad, strides=None, center=False, stream=None):
     """FCOS/infer_fcos.py:35-57 for a batch: per-level heads [B, Hl, Wl, C+5] -> (boxes [B, N, 4], scores [B, N, C])."""
     strides = list(DEFAULT_STRIDES if strides is None else strides)
@@ -210,6 +216,7 @@ def decode_batch(head_outputs, num_classes, img_pad, strides=None, center=False,
     return boxes, scores
 
 
+@uses_stream
 def detect_batch(head_outputs, num_classes, img_pad, center=False, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,
                  max_total_size=100, pre_nms_topk=1000, strides=None, with_candidates=False, stream=None):
     """FCOS/infer_fcos.py:27-62 for a batch, one library call (dh_fcos_detect): decode -> per-level top-k of the

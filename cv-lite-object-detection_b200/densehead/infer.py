@@ -9,12 +9,13 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._tensors import current_device, stream_ptr, to_device
+from ._tensors import current_device, stream_ptr, to_device, uses_stream
 
 NMS_AGNOSTIC, NMS_PER_CLASS = 0, 1
 NMS_MAX_CANDIDATES = 16384
 
 
+@uses_stream
 def prediction_to_corners(xy_pred, mode, stride, d0=0.0, d1=0.0, scales=None, stream=None):
     """xy_pred: [..., H, W, >=4] (modes 0-2) or [..., H, W, S, >=4] (mode 3) -> same leading shape + [4]."""
     dev = current_device()
@@ -36,6 +37,7 @@ def prediction_to_corners(xy_pred, mode, stride, d0=0.0, d1=0.0, scales=None, st
     return out
 
 
+@uses_stream
 def nms(dets, iou_thr, mode=NMS_AGNOSTIC, min_score=-float("inf"), score_inclusive=True, n_valid=None, num_classes=0,
         max_per_class=0, max_total=0, max_out=None, stream=None):
     """dets [B, n, >=5(6)] float32 on the device -> (keep int32 [B, max_out], n_keep int32 [B])."""
@@ -57,6 +59,7 @@ def nms(dets, iou_thr, mode=NMS_AGNOSTIC, min_score=-float("inf"), score_inclusi
     return keep, n_keep
 
 
+@uses_stream
 def select_topk(dets, seg_offsets, k, min_score, score_inclusive=True, score_col=4, with_source=False, stream=None):
     """Per-segment threshold + exact top-k.  dets [B, n, row] -> [B, n_seg*k, row] (unused slots: score -inf)."""
     dev = current_device()

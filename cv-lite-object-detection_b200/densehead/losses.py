@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._tensors import current_device, stream_ptr, to_device
+from ._tensors import current_device, stream_ptr, to_device, uses_stream
 
 CEN_NONE, CEN_SMOOTH_L1, CEN_FOCAL, CEN_IGNORE = 0, 1, 2, 3
 REG_SMOOTH_L1, REG_IOU = 0, 1
@@ -17,6 +17,7 @@ POS_GE1, POS_GT0, POS_MASK = 0, 1, 2
 CLS_FOCAL, CLS_SIGMOID_BCE = 0, 1
 
 
+@uses_stream
 def dense_loss(targets, preds, shapes, batch, ch, reg_ch, cen_mode, reg_mode, pos_rule, alpha=0.25, gamma=2.0,
                delta=1.0, masks=None, per_image=True, stream=None, weights=None, cls_mode=CLS_FOCAL):
     """targets/preds: lists of contiguous float32 device tensors, map m holding [B, H*W*sub, ch] rows.

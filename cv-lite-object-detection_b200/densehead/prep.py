@@ -8,11 +8,12 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._tensors import current_device, stream_ptr, to_device
+from ._tensors import current_device, stream_ptr, to_device, uses_stream
 
 SWAP_XY, TO_XYWH, TO_CORNERS, FLIP_HORIZONTAL = 0, 1, 2, 3
 
 
+@uses_stream
 def _convert(boxes, mode, stream=None):
     dev = current_device()
     b = to_device(boxes, torch.float32, dev).contiguous()
@@ -44,6 +45,7 @@ def flip_boxes_horizontal(boxes):
     return _convert(boxes, FLIP_HORIZONTAL)
 
 
+@uses_stream
 def prepare_labels(bboxes, classes, flip=None, max_boxes=None, offsets=None, nbox=None, stream=None):
     """Dataset boxes -> (labels [B, max_boxes, 5] = (cy, cx, h, w, class), nbox [B]) on the device.
 
@@ -82,6 +84,7 @@ def prepare_labels(bboxes, classes, flip=None, max_boxes=None, offsets=None, nbo
     return out, out_n
 
 
+@uses_stream
 def format_detections(rows, n_keep, ratios, stream=None):
     """RetinaNet/retinanet_module.py:559-569 for a batch: kept rows [B, n, 6] (y1, x1, y2, x2, score, label) ->
     (boxes [B, n, 4] as (x1, y1, x2, y2) in source-image pixels, scores [B, n], labels int32 [B, n])."""

@@ -11,8 +11,8 @@ import numpy as np
 import torch
 
 from . import _capi, infer, losses
-from ._batch import image_dims, pack_labels
-from ._tensors import as_host, current_device, stream_ptr, to_device
+from ._batch import image_dims, pack_labels, check_classes
+from ._tensors import as_host, current_device, stream_ptr, to_device, uses_stream
 
 STRIDES = [8, 16, 32, 64, 128]
 
@@ -40,6 +40,7 @@ def anchor_table(anchor_sizes=None, aspect_ratios=None, anchor_scales=None):
     return table
 
 
+@uses_stream
 def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, anchor_hw=None, iou_thresh=0.5, strides=None,
                       out=None, num_pairs=None, stream=None):
     """Match + encode a padded batch.  Returns (list of 5 tensors [B, A, Hl, Wl, C+4], num_pairs int32 [B])."""
@@ -49,6 +50,7 @@ def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, anchor_hw=None
     if n_levels != len(strides):
         raise ValueError("anchor table has %d levels for %d strides" % (n_levels, len(strides)))
     dev = current_device()
+    check_classes(boxes, nbox, num_classes)
     boxes_d = to_device(boxes, torch.float32, dev)
     if boxes_d.dim() != 3 or boxes_d.shape[2] != 5:
         raise ValueError("boxes must be [B, Nmax, 5]")
@@ -87,16 +89,13 @@ def _pack_levels(x, n_anchors, dev):
     return out
 
 
+@uses_stream
 def loss_batch(x_label, x_pred, n_anchors=9, alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
     """Loss over materialised RetinaNet targets -> (per_image [B,4], total [4]) = {cls, reg, 0, n_pos}."""
     dev = current_device()
     yt, yp = _pack_levels(x_label, n_anchors, dev), _pack_levels(x_pred, n_anchors, dev)
     batch, ch = int(yp[0].shape[0]), int(yp[0].shape[-1])
     shapes = [(int(p.shape[2]), int(p.shape[3]), 1) for p in yp]
-    if batch == 1:  # [1, A, Hl, Wl, ch]: the anchor axis folds into rows
-        shapes = [(int(p.shape[1]) * int(p.shape[2]), int(p.shape[3]), 1) for p in yp]
-        return losses.dense_loss(yt, yp, shapes, 1, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_GT0,
-                                 alpha, gamma, delta, stream=stream)
     # batch-major packed layout: image stride covers all anchors, so fold anchors into rows as well
     shapes = [(int(p.shape[1]) * int(p.shape[2]), int(p.shape[3]), 1) for p in yp]
     return losses.dense_loss(yt, yp, shapes, batch, ch, 4, losses.CEN_NONE, losses.REG_SMOOTH_L1, losses.POS_GT0,
@@ -104,6 +103,7 @@ def loss_batch(x_label, x_pred, n_anchors=9, alpha=0.25, gamma=2.0, delta=1.0, s
                              weights=None if weights is None else (weights[0], weights[1], 0.0))
 
 
+@uses_stream
 def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, x_pred, anchor_hw=None, iou_thresh=0.5,
                       strides=None, alpha=0.25, gamma=2.0, delta=1.0, stream=None, weights=None):
     """Fused match + encode + loss (targets never reach HBM).  x_pred: per-level [B, A, Hl, Wl, C+4].
@@ -113,6 +113,7 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, x_pred, anchor
     table = anchor_table() if anchor_hw is None else np.ascontiguousarray(anchor_hw, dtype=np.float32)
     n_levels, n_anchors = table.shape[0], table.shape[1]
     dev = current_device()
+    check_classes(boxes, nbox, num_classes)
     boxes_d = to_device(boxes, torch.float32, dev)
     batch, nmax = int(boxes_d.shape[0]), int(boxes_d.shape[1])
     nbox_d = to_device(nbox, torch.int32, dev)
@@ -156,6 +157,7 @@ def compute_iou(boxes1, boxes2):
     return out
 
 
+@uses_stream
 def decode_batch(head_outputs, num_classes, img_pad, anchor_hw=None, strides=None, stream=None):
     """retinanet_module.py:487-520 for a batch: per-level heads [B, A, Hl, Wl, C+4] -> dets [B, N, 6]
     (y1, x1, y2, x2, max score, first-argmax label), order level > anchor > row-major cell."""
@@ -176,6 +178,7 @@ def decode_batch(head_outputs, num_classes, img_pad, anchor_hw=None, strides=Non
     return dets
 
 
+@uses_stream
 def detect_batch(head_outputs, num_classes, img_pad, iou_thresh=0.5, cls_thresh=0.05, anchor_hw=None, strides=None,
                  pre_nms_topk=None, with_rows=False, stream=None):
     """retinanet_module.py:483-530 for a batch, one library call (dh_retina_detect): decode -> `score >= cls_thresh`

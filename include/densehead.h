@@ -32,6 +32,7 @@ extern "C" {
 #define DH_ERR_SHAPE (-2)
 #define DH_ERR_CUDA (-3)
 #define DH_ERR_CAPACITY (-4)
+#define DH_ERR_NCCL (-5)
 
 #define DH_MAX_BOXES_PER_IMAGE 256
 #define DH_MAX_PYRAMID_LEVELS 8
@@ -55,10 +56,27 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_FUSED_CHUNKS_PER_CTA 8 /* fused loss scheduler: aim at this many image-aligned chunks per persistent CTA (default 12; a chunk is always 4..8 tiles of 256 rows) */
 #define DH_OPT_ENCODE_MIN_CHUNK 9 /* encoders: smallest scheduler chunk in tiles (default 2) */
 #define DH_OPT_NMS_SORT 10 /* score sort ahead of the NMS. 0 (default): bucket sort in shared memory, bitonic network when the scores pile onto few buckets; 1: always the bitonic network (A/B checks) */
+#define DH_OPT_LOSS_ALLREDUCE 11 /* 1: the out_total of every dh_*_encode_loss(_grad) call is summed over the ranks of the handle's communicator inside the same kernel (its last CTA exchanges the scalars through the NVLink peer mailboxes, see dh_comm_peer_import); 0 (default): out_total is this rank's sum */
+#define DH_OPT_ALLREDUCE 12 /* transport of dh_allreduce_loss. 0 (default): peer mailboxes when imported, else NCCL; 1: NCCL; 2: peer mailboxes */
+#define DH_OPT_FUSED_TAIL 13 /* fused loss scheduler: 1 (default) cuts the last images of a launch into finer chunks so that the tail is short; 0: uniform chunks */
+#define DH_OPT_ENCODE_KERNEL 14 /* target encoders. 0 (default): pick per problem -- direct-store kernel for small outputs, shared-memory tile streamer with TMA bulk stores for large ones; 1: always the tile streamer; 2: always the direct-store kernel */
 int dh_set_option(dh_handle_t h, int option, int value);
 /* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in
  * {stage GT + records, candidates + buffer recycle, emit rows, hand-off to TMA, drain}, out8[5] = tiles. */
 int dh_read_phase_timing(dh_handle_t h, long long* out8 /*[host] [8]*/);
+/* Sticky input-validation bits accumulated by the kernels launched through this handle (synchronous read; `reset`
+ * clears them).  DH_STATUS_BAD_SCALE: a CenterNet box was not below the largest box scale (the reference raises
+ * ValueError, CenterNet/tf_centernet_resnet_s8.py:306-307); DH_STATUS_BAD_CLASS: a GT class was outside
+ * [0, num_classes) -- the reference raises IndexError (FCOS/fcos.py:281-283), the kernels drop the box;
+ * DH_STATUS_COMM_TIMEOUT: a peer rank did not arrive at a loss all-reduce within 10 s (the sums are NaN). */
+#define DH_STATUS_BAD_SCALE 1
+#define DH_STATUS_BAD_CLASS 2
+#define DH_STATUS_COMM_TIMEOUT 4
+int dh_get_status(dh_handle_t h, int32_t* out /*[host] [1]*/, int reset);
+/* Profiling aid: while `buf` ([dev], `bytes` long; NULL switches it off) is set, every fused encode+loss launch whose
+ * grid fits writes per CTA b: buf[4b+0] = start, buf[4b+1] = first chunk staged, buf[4b+2] = chunk loop done (globaltimer
+ * nanoseconds), buf[4b+3] = chunks processed; buf[4*grid] = end of the in-kernel reduction. */
+int dh_set_trace(dh_handle_t h, long long* buf /*[dev]*/, long long bytes);
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 long long dh_launch_count(dh_handle_t h);
 /* Host-only (no device needed): the work split dh_fcos_detect's candidate selection would use for per-level head sizes
@@ -255,6 +273,35 @@ int dh_centernet_encode_loss_grad(dh_handle_t h, const float* boxes, const int32
                                   float sigma, int num_classes, int mode, const float* pred, int reg_mode, int cls_mode, float alpha,
                                   float gamma, float delta, float w_cls, float w_reg, float w_cen, float* grad /*[dev]*/,
                                   float* out_per_image, float* out_total, int32_t* status, void* stream);
+
+/* ---- multi-GPU: the loss-scalar exchange -----------------------------------------
+ * The reference has no distribution strategy at all; the batch is sharded by image, one rank
+ * per GPU, and the only collective of the path is the sum of {cls, reg, cen, n_pos} -- what the reference's training
+ * loop accumulates over the images of a batch (FCOS/train_fcos.py:167-194).  Two transports:
+ *   peer mailboxes  every rank's 2 KB mailbox is mapped into its peers (cudaIpc between processes, peer access
+ *                   inside one process); a rank stores its values into every peer's mailbox over NVLink and sums what
+ *                   arrives in its own, in rank order (bit-identical on all ranks, deterministic).  ~2 us; can run
+ *                   inside the fused loss kernel itself (DH_OPT_LOSS_ALLREDUCE).
+ *   NCCL            ncclAllReduce on the caller's stream (libnccl.so.2 is dlopen'ed on first use).
+ * Both are stream-ordered and capturable in a CUDA graph.  Setup, one process per GPU: rank 0 calls
+ * dh_comm_get_unique_id and every rank dh_comm_init_rank with those 128 bytes (NCCL); every rank calls
+ * dh_comm_peer_export, the 64-byte blobs are all-gathered out of band (MPI, a file, torch.distributed ...) and handed
+ * to dh_comm_peer_import (mailboxes).  One process driving several GPUs: dh_comm_init_all sets up both.
+ * Every rank must issue the same sequence of all-reduces.  dh_comm_destroy (also run by dh_destroy) must only be
+ * called once no peer can still be inside an exchange (barrier first). */
+#define DH_UNIQUE_ID_BYTES 128
+#define DH_IPC_HANDLE_BYTES 64
+#define DH_COMM_MAX_RANKS 16
+int dh_comm_get_unique_id(void* out128 /*[host] [DH_UNIQUE_ID_BYTES]*/);
+int dh_comm_init_rank(dh_handle_t h, int world, int rank, const void* unique_id128 /*[host]*/);
+int dh_comm_init_all(dh_handle_t* handles /*[host] [ndev]*/, int ndev);
+int dh_comm_peer_export(dh_handle_t h, void* out64 /*[host] [DH_IPC_HANDLE_BYTES]*/);
+int dh_comm_peer_import(dh_handle_t h, int world, int rank, const void* handles /*[host] [world][DH_IPC_HANDLE_BYTES], rank-major*/);
+/* world / rank of the handle's communicator (1 / 0 without one); transports: bit 0 NCCL, bit 1 peer mailboxes. */
+int dh_comm_info(dh_handle_t h, int* world, int* rank, int* transports);
+/* In-place sum of scalars[0..count) (count <= 12) over all ranks; no-op for a single rank. */
+int dh_allreduce_loss(dh_handle_t h, float* scalars /*[dev] [count]*/, int count, void* stream);
+int dh_comm_destroy(dh_handle_t h);
 
 /* ---- inference: decode, candidate selection, NMS ------------------------------------------------- */
 

@@ -215,6 +215,120 @@ def losses(tf):
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **d)
 
 
+GRAD_W = (1.0, 0.7, 1.3)  # weights of (cls, reg, cen) in the differentiated scalar
+
+
+def _fd_gradient(loss_fn, preds, picks, h=1e-6):
+    """Central differences of `loss_fn(preds) -> float` (float64) at the picked elements: picks[m] = flat indices
+    into preds[m].  Returns one float64 array per map."""
+    out = []
+    for m, idx in enumerate(picks):
+        flat = preds[m].reshape(-1)
+        g = np.zeros(len(idx), dtype=np.float64)
+        for n, e in enumerate(idx):
+            keep = flat[e]
+            flat[e] = keep + h
+            up = loss_fn(preds)
+            flat[e] = keep - h
+            dn = loss_fn(preds)
+            flat[e] = keep
+            g[n] = (up - dn) / (2 * h)
+        out.append(g)
+    return out
+
+
+def _grad_picks(targets, ch, cls0, rng, n_pos_rows=6, n_other=24):
+    """Per map: every channel of a few positive rows (they carry the regression / centerness / labelled-class
+    derivatives) plus random other elements (label-0 focal and all-location centerness terms)."""
+    picks = []
+    for t in targets:
+        rows = t.reshape(-1, ch)
+        pos = np.nonzero(rows[:, cls0:].max(axis=1) > 0)[0]
+        if len(pos) > n_pos_rows:
+            pos = rng.choice(pos, n_pos_rows, replace=False)
+        idx = [r * ch + c for r in pos for c in range(ch)]
+        idx += list(rng.integers(0, rows.size, size=min(n_other, rows.size)))
+        picks.append(np.unique(np.asarray(idx, dtype=np.int64)))
+    return picks
+
+
+def grad(tf):
+    """d(w . (cls, reg, cen)) / d pred by central differences THROUGH THE REFERENCE'S OWN LOSS FUNCTIONS
+    (fcos.model_loss FCOS/fcos.py:464-496 and its fcos_center / fcos_center_v1 copies, RetinaNet.train_loss
+    RetinaNet/retinanet_module.py:403-426, the CenterNet model_loss pair) -- the callers obtain this gradient from
+    tf.GradientTape (FCOS/train_fcos.py:152-176); TensorFlow's autodiff is not available here, finite differences of
+    the reference's code are.  The stub's `tf.float32` is switched to float64 for the duration, so the reference's
+    formulas are evaluated in double precision and a step of 1e-6 gives derivatives good to ~1e-9."""
+    fcos, fc, fv1 = R.load("FCOS", "fcos"), R.load("FCOS", "fcos_center"), R.load("FCOS", "fcos_center_v1")
+    s8, hg = R.load("CenterNet", "tf_centernet_resnet_s8"), R.load("CenterNet", "tf_centernet_hourglass")
+    rn = R.retinanet(20)
+    d = {"weights": np.array(GRAD_W)}
+    rng = np.random.default_rng(synth.seed_for(7, 0))
+    w = GRAD_W
+    img = tf.cast([256, 256], tf.float32)
+    seed = synth.seed_for(7, 1)
+    boxes, nbox = synth.make_boxes(1, 256, 12, 20, 8.0, 180.0, seed)
+    g = boxes[0, :nbox[0]]
+    d["fcos_g"], d["fcos_seed"] = g, np.int64(seed)
+    targets = {"fcos": fcos.format_data(tf.constant(g), img, 20)[0], "center": fc.format_data(tf.constant(g), img, 20)[0],
+               "v1": fv1.format_data(tf.constant(g), img, 20)[0]}
+    rseed = synth.seed_for(7, 2)
+    rboxes, rnbox = synth.make_boxes(1, 128, 8, 20, 8.0, 100.0, rseed)
+    rg = rboxes[0, :rnbox[0]]
+    rlab, _ = rn.format_data(tf.constant(rg), tf.cast([128, 128], tf.float32))
+    d["retina_g"], d["retina_seed"] = rg, np.int64(rseed)
+    cseed = synth.seed_for(7, 3)
+    cboxes, cnbox = synth.make_boxes(2, 256, 30, 3, 8.0, 200.0, cseed)
+    d["cn_boxes"], d["cn_nbox"], d["cn_seed"] = cboxes, cnbox, np.int64(cseed)
+    yt_s8 = np.stack([np.asarray(s8.format_data(tf.constant(cboxes[b, :cnbox[b]]), SCALES, [256, 256], 3)[0]) for b in range(2)])
+    yt_hg = np.stack([np.asarray(hg.format_data(tf.constant(cboxes[b, :cnbox[b]]), [256, 256], 3)[0]) for b in range(2)])
+    with R.float64_mode():
+        # ---- FCOS family: five model_loss variants on the same predictions ---------------------------------
+        base = [p.astype(np.float64) for p in synth.fcos_predictions(1, 256, 20, seed)]
+        for p in base:
+            p[..., :4] = np.abs(p[..., :4]) + 0.3  # tblr distances are positive in a trained head (IoU loss)
+        variants = (("fcos_l1", fcos.model_loss, targets["fcos"], (None,), {}),
+                    ("fcos_iou", fcos.model_loss, targets["fcos"], (None,), {"reg_type": "iou"}),
+                    ("center_focal", fc.model_loss, targets["center"], (), {"cen_type": "focal"}),
+                    ("center_l1", fc.model_loss, targets["center"], (), {}),
+                    ("v1", fv1.model_loss, targets["v1"], (), {}))
+        for name, fn, tg, args, kw in variants:
+            preds = [p.copy() for p in base]
+            tgt = [np.asarray(t, dtype=np.float64) for t in tg]
+
+            def loss(ps, fn=fn, tgt=tgt, args=args, kw=kw):
+                out = fn(tgt, [tf.constant(p) for p in ps], *args, **kw)
+                return sum(wk * float(np.asarray(v.numpy() if hasattr(v, "numpy") else v)) for wk, v in zip(w, out))
+            picks = _grad_picks(tgt, 25, 5, rng)
+            fd = _fd_gradient(loss, preds, picks)
+            for l in range(5):
+                d["%s_idx%d" % (name, l)], d["%s_fd%d" % (name, l)] = picks[l], fd[l]
+        # ---- RetinaNet.train_loss -----------------------------------------------------------------------------
+        rbase = [p.astype(np.float64) for p in synth.retina_predictions(1, 128, 20, rseed)]
+        rt = [[np.asarray(rlab[l][a], dtype=np.float64) for a in range(9)] for l in range(5)]
+
+        def rloss(ps):
+            rn.model = _FixedModel([[tf.constant(p[:, a]) for a in range(9)] for p in ps])
+            out = rn.train_loss(None, rt)
+            return sum(wk * float(np.asarray(v.numpy() if hasattr(v, "numpy") else v)) for wk, v in zip(w, out))
+        picks = _grad_picks([np.stack(rt[l]) for l in range(5)], 24, 4, rng, n_pos_rows=5, n_other=20)
+        fd = _fd_gradient(rloss, rbase, picks)
+        for l in range(5):
+            d["retina_idx%d" % l], d["retina_fd%d" % l] = picks[l], fd[l]
+        # ---- CenterNet s8 / hourglass model_loss (batched) -----------------------------------------------------
+        yp = synth.centernet_s8_predictions(2, 256, 8, 5, 3, cseed).astype(np.float64)
+        for name, fn, yt, pr in (("cn_s8", s8.model_loss, yt_s8, yp), ("cn_hg", hg.model_loss, yt_hg, np.ascontiguousarray(yp[:, :, :, 0, :]))):
+            tgt = yt.astype(np.float64)
+
+            def closs(ps, fn=fn, tgt=tgt):
+                out = fn(tf.constant(tgt), tf.constant(ps[0]))
+                return sum(wk * float(np.asarray(v.numpy() if hasattr(v, "numpy") else v)) for wk, v in zip(w, out))
+            picks = _grad_picks([tgt], 7, 4, rng, n_pos_rows=12, n_other=60)
+            fd = _fd_gradient(closs, [pr.copy()], picks)
+            d[name + "_idx"], d[name + "_fd"] = picks[0], fd[0]
+    np.savez_compressed(os.path.join(OUT, "grad.npz"), **d)
+
+
 def decode_nms(tf):
     fcos, fv1 = R.load("FCOS", "fcos"), R.load("FCOS", "fcos_center_v1")
     s8 = R.load("CenterNet", "tf_centernet_resnet_s8")
@@ -237,6 +351,7 @@ def decode_nms(tf):
             captured["boxes"], captured["scores"], captured["args"] = np.asarray(boxes), np.asarray(scores), (a, k)
             return None
     stub = R.tf()
+    saved_image = stub.image  # the stub's own tf.image (data_preprocess.random_flip_horizontal needs it in prep())
     stub.image = _Image
     ns = R.functions_only("FCOS", "infer_fcos", ("image_detections",))
     for center in (False, True):
@@ -245,7 +360,7 @@ def decode_nms(tf):
         d["fcos_dec_boxes_c%d" % center] = f32(captured["boxes"][0, :, 0, :])
         d["fcos_dec_scores_c%d" % center] = f32(captured["scores"][0])
     d["fcos_dec_seed"] = np.int64(seed + 1)
-    del stub.image
+    stub.image = saved_image
     # RetinaNet image_detections (decode + threshold + class-agnostic NMS); unique scores enforced
     t = 0
     for s in range(50):
@@ -315,12 +430,17 @@ def hourglass4(tf):
     np.savez_compressed(os.path.join(OUT, "hourglass4.npz"), **d)
 
 
-def main():
+def main(out_dir=None):
+    """Rewrite every fixture (into `out_dir` when given: tests/test_make_golden.py runs the whole recipe into a
+    temporary directory and compares the bytes of the arrays with the committed files)."""
+    global OUT
     if not R.available():
         raise SystemExit("reference tree not found at %s" % R.REF_ROOT)
+    if out_dir is not None:
+        OUT = out_dir
     os.makedirs(OUT, exist_ok=True)
     tf = R.tf()
-    for fn in (kat, fcos_family, retina, centernet, losses, decode_nms, prep, hourglass4):
+    for fn in (kat, fcos_family, retina, centernet, losses, grad, decode_nms, prep, hourglass4):
         fn(tf)
         print("wrote", fn.__name__)
     for f in sorted(os.listdir(OUT)):
@@ -328,4 +448,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -81,6 +81,27 @@ def tf():
     return _cache["tf"]
 
 
+class float64_mode:
+    """Evaluate the reference's formulas in double precision: inside the block the stub's `tf.float32` IS float64 and
+    Python floats become float64 tensors, so `tf.cast(x, tf.float32)` and literals such as `mask=1.0` no longer round
+    to single precision.  Used to take finite differences through the reference's loss functions (make_golden.grad)."""
+
+    def __enter__(self):
+        stub = tf()
+        self.stub, self.saved = stub, (stub.float32, stub._default_dtype)
+        inner = stub._default_dtype
+
+        def default_dtype(x):
+            dt = inner(x)
+            return np.dtype(np.float64) if dt == np.float32 and not isinstance(x, (np.ndarray, np.generic)) else dt
+        stub.float32, stub._default_dtype = np.float64, default_dtype
+        return self
+
+    def __exit__(self, *exc):
+        self.stub.float32, self.stub._default_dtype = self.saved
+        return False
+
+
 def retinanet(n_classes, **kwargs):
     """Instantiate the reference RetinaNet class with its Keras graph builder patched out
     (RetinaNet/retinanet_module.py:194-196 builds a backbone in __init__)."""

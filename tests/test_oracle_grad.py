@@ -58,3 +58,69 @@ def test_float64_loss_agrees_with_reference_order_float32_loss():
     for t, p in zip(tg, pred):
         got += O.dense_loss_f64(t, p[0], reg_ch=4, cen_mode=1, pos_rule="ge1")
     assert np.allclose(got, [float(v) for v in want], rtol=2e-6)
+
+
+# ---- pinned by the reference itself: central differences THROUGH the reference's own loss functions -----------------
+# tests/golden/grad.npz (oracle/make_golden.py: grad) holds d(w . (cls, reg, cen)) / d pred at sampled elements,
+# obtained by finite differences of fcos.model_loss (FCOS/fcos.py:464-496), its fcos_center / fcos_center_v1 copies,
+# RetinaNet.train_loss (RetinaNet/retinanet_module.py:403-426) and the CenterNet model_loss pair, the reference's code
+# evaluated in float64 under the stub.  The oracle's analytic gradient must reproduce them.
+import os  # noqa: E402
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grad.npz"))
+W_GOLD = tuple(float(v) for v in GOLD["weights"])
+
+
+def _fd_close(got, want, what):
+    err = np.abs(got - want)
+    assert np.all(err <= 2e-6 * np.maximum(1.0, np.abs(want))), "%s: max err %g (want %g)" % (what, err.max(), want[err.argmax()])
+
+
+def golden_fcos_case():
+    g, seed = GOLD["fcos_g"], int(GOLD["fcos_seed"])
+    pred = [p[0].astype(np.float64) for p in synth.fcos_predictions(1, 256, 20, seed)]
+    for p in pred:
+        p[..., :4] = np.abs(p[..., :4]) + 0.3
+    return g, pred
+
+
+FCOS_VARIANTS = {  # name -> (encoder, loss kwargs)
+    "fcos_l1": (lambda g: O.fcos_format_data(g, [256, 256], 20)[0], dict(cen_mode=1, reg_mode=0)),
+    "fcos_iou": (lambda g: O.fcos_format_data(g, [256, 256], 20)[0], dict(cen_mode=1, reg_mode=1)),
+    "center_focal": (lambda g: O.fcos_center_format_data(g, [256, 256], 20)[0], dict(cen_mode=2, reg_mode=0)),
+    "center_l1": (lambda g: O.fcos_center_format_data(g, [256, 256], 20)[0], dict(cen_mode=1, reg_mode=0)),
+    "v1": (lambda g: O.fcos_center_v1_format_data(g, [256, 256], 20)[0], dict(cen_mode=2, reg_mode=0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FCOS_VARIANTS))
+def test_fcos_gradients_match_differences_through_the_reference(name):
+    g, pred = golden_fcos_case()
+    enc, kw = FCOS_VARIANTS[name]
+    tg = enc(g)
+    for l in range(5):
+        grad = O.dense_loss_grad(tg[l], pred[l], weights=W_GOLD, reg_ch=4, pos_rule="ge1", **kw)
+        _fd_close(grad.reshape(-1)[GOLD["%s_idx%d" % (name, l)]], GOLD["%s_fd%d" % (name, l)], "%s level %d" % (name, l))
+
+
+def test_retina_gradients_match_differences_through_the_reference():
+    g, seed = GOLD["retina_g"], int(GOLD["retina_seed"])
+    lab, _ = O.retina_format_data(g, [128, 128], 20)
+    pred = synth.retina_predictions(1, 128, 20, seed)
+    for l in range(5):
+        grad = O.dense_loss_grad(np.stack(lab[l]), pred[l][0].astype(np.float64), weights=(W_GOLD[0], W_GOLD[1], 0.0), reg_ch=4,
+                                 cen_mode=0, pos_rule="gt0")
+        _fd_close(grad.reshape(-1)[GOLD["retina_idx%d" % l]], GOLD["retina_fd%d" % l], "retina level %d" % l)
+
+
+@pytest.mark.parametrize("name", ["cn_s8", "cn_hg"])
+def test_centernet_gradients_match_differences_through_the_reference(name):
+    boxes, nbox, seed = GOLD["cn_boxes"], GOLD["cn_nbox"], int(GOLD["cn_seed"])
+    yp = synth.centernet_s8_predictions(2, 256, 8, 5, 3, seed).astype(np.float64)
+    if name == "cn_s8":
+        yt = np.stack([O.centernet_s8_format_data(boxes[b, :nbox[b]], [32, 64, 128, 256, 512], [256, 256], 3)[0] for b in range(2)])
+    else:
+        yt = np.stack([O.centernet_hourglass_format_data(boxes[b, :nbox[b]], [256, 256], 3)[0] for b in range(2)])
+        yp = np.ascontiguousarray(yp[:, :, :, 0, :])
+    grad = O.dense_loss_grad(yt, yp, weights=W_GOLD, reg_ch=4, cen_mode=0, pos_rule="gt0")
+    _fd_close(grad.reshape(-1)[GOLD[name + "_idx"]], GOLD[name + "_fd"], name)

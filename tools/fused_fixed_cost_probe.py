@@ -1,0 +1,88 @@
+"""Fixed cost of the fused encode+loss kernel (development aid; bench.py is the contract): CUDA-graph-timed
+dh_retina_encode_loss on COCO-shaped batches of 8..256 images with the tiered tail on/off and several chunk
+targets, with and without GT boxes, and at three logit distributions.  One JSON line per case."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "cv-lite-object-detection_b200")]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import densehead as dh  # noqa: E402
+from densehead import _capi  # noqa: E402
+from oracle import synth  # noqa: E402
+
+PEAK = 6553.3
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def graph_time(fn, reps=30):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def make_pred(B, dist):
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    pred = []
+    for h in (80, 40, 20, 10, 5):
+        p = torch.empty((B, 9, h, h, 84), device="cuda")
+        p[..., :4].uniform_(-1, 2, generator=gen)
+        if dist == "prior":          # N(-4.595, 1): a freshly initialised head (focal prior)
+            p[..., 4:].normal_(-4.595, 1.0, generator=gen)
+        elif dist == "wide":         # N(-2, 3)
+            p[..., 4:].normal_(-2.0, 3.0, generator=gen)
+        else:                        # trained-head-like: 97 % background N(-6, 1.5), 3 % confident N(1.5, 2)
+            p[..., 4:].normal_(-6.0, 1.5, generator=gen)
+            m = torch.rand(p[..., 4:].shape, device="cuda", generator=gen) < 0.03
+            hot = torch.empty_like(p[..., 4:]).normal_(1.5, 2.0, generator=gen)
+            p[..., 4:] = torch.where(m, hot, p[..., 4:])
+            del m, hot
+        pred.append(p)
+    return pred
+
+
+def main():
+    batches = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "16,32,64,128,256".split(","))]
+    for B in batches:
+        boxes, nbox = synth.config_boxes("retina_coco", B, 3)
+        bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
+        zero = torch.zeros_like(nd)
+        dims = torch.tensor([[640., 640.]] * B, device="cuda")
+        for dist in ("prior", "wide", "trained"):
+            pred = make_pred(B, dist)
+            nbytes = sum(p.numel() for p in pred) * 4
+            cases = [("tail=1", 1, 12, nd), ("tail=0", 0, 12, nd)]
+            if dist == "prior":
+                cases += [("tail=1 cpc=6", 1, 6, nd), ("tail=1 cpc=24", 1, 24, nd), ("tail=1 no boxes", 1, 12, zero)]
+            for tag, tail, cpc, n in cases:
+                dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
+                dh.set_option(0, 8, cpc)
+                t = graph_time(lambda: dh.retinanet.encode_loss_batch(bd, n, dims, 80, [640, 640], pred))
+                print(json.dumps({"B": B, "logits": dist, "case": tag, "us": round(t * 1e6, 1), "GBps": round(nbytes / t / 1e9, 1),
+                                  "frac": round(nbytes / t / 1e9 / PEAK, 3), "ideal_us": round(nbytes / PEAK / 1e3, 1)}), flush=True)
+            dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, 1)
+            dh.set_option(0, 8, 12)
+            del pred
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
