@@ -68,26 +68,6 @@ unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st) {
     return h->sched + (h->sched_next++ % kSchedRing) * 32;
 }
 
-unsigned int* image_counters(dh_handle_s* h, int batch) {
-    if (batch <= h->img_cnt_cap) return h->img_cnt;
-    if (h->img_cnt) {
-        cudaDeviceSynchronize();  // a kernel in flight may still count on the old block
-        cudaFree(h->img_cnt);
-        h->img_cnt = nullptr;
-        h->img_cnt_cap = 0;
-    }
-    int cap = 1024;
-    while (cap < batch) cap *= 2;
-    cudaError_t e = cudaMalloc(&h->img_cnt, static_cast<size_t>(cap) * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(h->img_cnt, 0, static_cast<size_t>(cap) * sizeof(unsigned int));
-    if (e != cudaSuccess) {
-        set_error(DH_ERR_CUDA, "allocating the per-image counters failed: %s", cudaGetErrorString(e));
-        return nullptr;
-    }
-    h->img_cnt_cap = cap;
-    return h->img_cnt;
-}
-
 }  // namespace dh
 
 extern "C" {
@@ -118,9 +98,12 @@ int dh_create(dh_handle_t* out, int device) {
     h->encode_min_chunk = 2;
     h->fcos_select_mode = 0;
     h->nms_sort = 0;
+    h->nms_filter = 1;
+    h->nms_chain = 0;
     h->loss_allreduce = 0;
     h->allreduce_mode = 0;
     h->fused_tail = 1;
+    h->fused_max_chunk = 16;
     h->encode_kernel = 0;
     h->launches = 0;
     h->scratch = nullptr;
@@ -133,8 +116,6 @@ int dh_create(dh_handle_t* out, int device) {
     h->comm = nullptr;
     h->dev_status = nullptr;
     h->trace = nullptr;
-    h->img_cnt = nullptr;
-    h->img_cnt_cap = 0;
     h->trace_bytes = 0;
     {
         dh::DeviceGuard g(device);
@@ -159,7 +140,6 @@ int dh_destroy(dh_handle_t h) {
         if (h->sched) cudaFree(h->sched);
         if (h->phase_cycles) cudaFree(h->phase_cycles);
         if (h->dev_status) cudaFree(h->dev_status);
-        if (h->img_cnt) cudaFree(h->img_cnt);
     }
     delete h;
     return DH_OK;
@@ -206,6 +186,18 @@ int dh_set_option(dh_handle_t h, int option, int value) {
         case DH_OPT_FUSED_TAIL:
             DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_FUSED_TAIL must be 0 or 1");
             h->fused_tail = value;
+            return DH_OK;
+        case DH_OPT_FUSED_MAX_CHUNK:
+            DH_CHECK_ARG(value >= 4 && value <= 16, "DH_OPT_FUSED_MAX_CHUNK must be in [4, 16]");
+            h->fused_max_chunk = value;
+            return DH_OK;
+        case DH_OPT_NMS_FILTER:
+            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_NMS_FILTER must be 0 or 1");
+            h->nms_filter = value;
+            return DH_OK;
+        case DH_OPT_NMS_CHAIN:
+            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_NMS_CHAIN must be 0 or 1");
+            h->nms_chain = value;
             return DH_OK;
         case DH_OPT_ENCODE_KERNEL:
             DH_CHECK_ARG(value >= 0 && value <= 2, "DH_OPT_ENCODE_KERNEL must be 0, 1 or 2");

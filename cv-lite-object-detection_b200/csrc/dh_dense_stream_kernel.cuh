@@ -123,10 +123,10 @@ __device__ __noinline__ float dense_row_reg(const LossSpec& sp, const float* __r
             for (int k = 0; k < 4; ++k) grow[k] = m * sp.w_reg * smooth_l1_grad(y[k], x[k], sp.delta);
         }
     } else {
-        acc = iou_loss_term(y, x, gy, gx);
+        acc = iou_loss_term(y, x, gy, gx, sp.reg_mode);
         if (grow) {
             float g[4];
-            iou_loss_grad(y, x, gy, gx, g);
+            iou_loss_grad(y, x, gy, gx, g, sp.reg_mode);
 #pragma unroll
             for (int k = 0; k < 4; ++k) grow[k] = m * sp.w_reg * g[k];
         }

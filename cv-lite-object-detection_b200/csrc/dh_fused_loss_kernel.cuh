@@ -186,16 +186,37 @@ __device__ __forceinline__ float cen_l1_zero(float x, float delta) {
     return s < delta ? 0.5f * s * s : s;
 }
 
+constexpr int kTraceSlots = 12;  // dh_set_trace: longs per CTA
+constexpr int kMaxChunkTiles = 16;  // tiles (of 256 rows) per scheduler chunk at most (launch_fused_g)
+constexpr int kMaxSegments = kMaxChunkTiles;  // ... so a chunk meets at most as many maps
 struct FusedSmemLayout {
-    int rec_off, raw_off, cand_off, misc_off, args_off, total;
+    int rec_off, raw_off, cand_off, seg_off, run_off, misc_off, args_off, total;
 };
+// Candidate list of one segment (the run of a chunk's tiles inside one map), built once per chunk by one warp and read by
+// all eight: the boxes that can match the map at all, in ascending GT order, with the cell rectangle each can touch.
+constexpr int kRunCap = 8;      // boxes of one row a lane keeps privately (more: the segment's whole list is matched)
+constexpr int kMaxPairs = 1024;  // (row, box) candidates one chunk can hold before it falls back to visiting every row
+struct SegLists {
+    int* nmap;                // [kMaxSegments] boxes that can match the segment's map (zero between chunks)
+    int* npairs;              // [1] pairs appended (zero between chunks); > kMaxPairs: overflow
+    unsigned short* box;      // [kMaxSegments][box_cap] those boxes, in no particular order
+    uint32_t* pairs;          // [kMaxPairs] chunk row << 16 | box, in no particular order
+    unsigned short* next;     // [kMaxPairs] the pair appended before this one for the same row (kNoPair: none)
+    uint32_t* head;           // [kMaxChunkTiles * 256] per chunk row: the last pair appended for it (kNoPair between chunks)
+    uint32_t* rowbits;        // [kMaxChunkTiles * 8] one bit per chunk row: has a pair (zero between chunks)
+    unsigned short* rowlist;  // [kMaxPairs] the chunk rows that have pairs, ascending (scan_rows)
+    int* tile_tab;            // [kMaxChunkTiles][4] per tile of the chunk: map, first row, segment
+};
+constexpr uint32_t kNoPair = 0xffffu;
 template <class P>
 __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     FusedSmemLayout l;
     l.rec_off = 0;
     l.raw_off = (static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127;
     l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
-    l.misc_off = l.cand_off + (DH_THREADS / 32) * box_cap * 4;  // per warp: tile candidates + map candidates
+    l.seg_off = l.cand_off;
+    l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 4 + 32 + 16);  // SegLists
+    l.misc_off = l.run_off + DH_THREADS * kRunCap * 2;  // resolve_pass: the boxes of the row a lane resolves
     l.args_off = l.misc_off + 512;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
     return l;
@@ -359,10 +380,10 @@ __device__ __noinline__ LossAcc correct_row(const LossSpec& sp, const float* __r
             for (int k = 0; k < 4; ++k) grow[k] = sp.w_reg * smooth_l1_grad(sink.r[k], x[k], sp.delta);
         }
     } else {
-        acc.reg += iou_loss_term(sink.r, x, gy, gx);
+        acc.reg += iou_loss_term(sink.r, x, gy, gx, sp.reg_mode);
         if (grow) {
             float g[4];
-            iou_loss_grad(sink.r, x, gy, gx, g);
+            iou_loss_grad(sink.r, x, gy, gx, g, sp.reg_mode);
 #pragma unroll
             for (int k = 0; k < 4; ++k) grow[k] = sp.w_reg * g[k];
         }
@@ -404,88 +425,239 @@ __device__ __forceinline__ const float* warp_tile(const LossArgs<P>& a, const Ti
     return md.pred + off;
 }
 
-// ---- correct: the rows of this warp's tiles that receive targets ------------------------------------------------
-// Nearly every 32-row warp tile has no target at all, so the tiles are culled per run of the chunk's tiles inside one map
-// ("segment", at most 32 tiles): on entering a segment the warp lists the boxes that can match the map at all
-// (P::map_hit), takes each one's conservative row interval (P::row_span) and ORs, with one REDUX, a bit mask of the
-// segment's tiles whose slice of this warp meets any interval.  Only those tiles run the exact narrowing (P::range_hit)
-// and the row matcher; an empty segment costs a few dozen instructions instead of a few dozen per tile.
+// ---- correct: the rows of the chunk that receive targets --------------------------------------------------------
+// Nearly every row has no target at all and the SMs are busy issuing the streaming pass, so this part must cost
+// instructions in proportion to the rows that DO get one -- and keep its lanes full.  Per chunk (at most 8 tiles of 256
+// rows, walked as "segments" = runs of tiles inside one map):
+//   pair   (before the streaming pass) the (segment, 32-box group) pairs are dealt to the warps; a warp finds the boxes
+//          of its group that can match the segment's map at all (P::map_hit) and the cell rectangle each can touch
+//          (P::cell_bounds), then walks every such rectangle with its 32 lanes, one cell per lane, and appends
+//          (row, box) to the chunk's pair list where the box may paint the cell (P::pair_hit: a cheap superset test);
+//          and chains the pair to the row's earlier ones (an atomicExch on the row's slot of a shared-memory table);
+//          and sets the row's bit in the chunk's row map;
+//   resolve  (after the streaming pass) one warp lists the marked rows in ascending order; then 32 rows per warp pass: a
+//          lane walks its row's chain, runs the exact row matcher (P::match_row) over those boxes and adds the correction of the row
+//          (correct_row); the matcher does not depend on the order of the boxes, so neither does the result.
+// A chunk with more than kMaxPairs candidates (an IoU threshold near zero, say) visits every row instead (visit_dense).
+__device__ __forceinline__ SegLists seg_lists(unsigned char* base, int box_cap) {
+    SegLists L;
+    L.nmap = reinterpret_cast<int*>(base);
+    L.npairs = L.nmap + kMaxSegments;
+    L.head = reinterpret_cast<uint32_t*>(base + 128);
+    L.pairs = L.head + kMaxChunkTiles * DH_THREADS;
+    L.rowbits = L.pairs + kMaxPairs;
+    L.tile_tab = reinterpret_cast<int*>(L.rowbits + kMaxChunkTiles * 8);
+    L.next = reinterpret_cast<unsigned short*>(L.tile_tab + kMaxChunkTiles * 4);
+    L.rowlist = L.next + kMaxPairs;
+    L.box = L.rowlist + kMaxPairs;
+    return L;
+}
+
+// Tile `tile` of image `img` and the segment of the chunk it belongs to.
 template <class P>
-__device__ __noinline__ LossAcc correct_pass(const LossArgs<P>& a, const typename P::Rec* recs, int n_boxes,
-                                             unsigned short* cand, int img, int t_begin, int t_end) {
+__device__ __forceinline__ int locate_tile(const LossArgs<P>& a, int img, int t_begin, int tile, TileCursor& cur) {
+    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
+    int seg = 0;
+    for (int t = t_begin; t < tile; ++t) {
+        const int m = cur.m;
+        cursor_next(a.tt, cur);
+        seg += cur.m != m;
+    }
+    return seg;
+}
+
+template <class P>
+__device__ __forceinline__ void pair_pass(const LossArgs<P>& a, const typename P::Rec* recs, int n_boxes, const SegLists& L,
+                                          int img, int t_begin, int t_end) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rpt = a.tt.rows_per_tile;
+    const int n_groups = (n_boxes + 31) >> 5;
+    TileCursor cur;
+    if (static_cast<int>(threadIdx.x) < t_end - t_begin) {  // thread t: where tile t of the chunk lies (read by resolve_pass)
+        const int seg_t = locate_tile<P>(a, img, t_begin, t_begin + threadIdx.x, cur);
+        L.tile_tab[threadIdx.x * 4 + 0] = cur.m, L.tile_tab[threadIdx.x * 4 + 1] = cur.t * rpt, L.tile_tab[threadIdx.x * 4 + 2] = seg_t;
+    }
+    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
+    int seg = 0, item = 0;
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end; ++seg) {
+        const MapDesc& md = a.tt.maps[cur.m];
+        const int nseg = min(md.n_tiles - cur.t, t_end - tile);
+        const int row0 = cur.t * rpt;                                  // the segment's rows in the map: [row0, row1]
+        const int row1 = min(row0 + nseg * rpt, md.rows) - 1;
+        const int local0 = (tile - t_begin) * rpt - row0;              // map row -> row of the chunk
+        const int cell0 = static_cast<int>(fdiv_u32(static_cast<uint32_t>(row0), md.div_sub));
+        const int cell1 = static_cast<int>(fdiv_u32(static_cast<uint32_t>(row1), md.div_sub));
+        const int seg_i0 = static_cast<int>(fdiv_u32(static_cast<uint32_t>(cell0), md.div_width));
+        const int seg_i1 = static_cast<int>(fdiv_u32(static_cast<uint32_t>(cell1), md.div_width));
+#pragma unroll 1
+        for (int g = 0; g < n_groups; ++g, ++item) {
+            if ((item & (DH_THREADS / 32 - 1)) != warp) continue;      // (warp-uniform) this warp's items
+            const int k = g * 32 + lane;
+            int ilo = 0, ihi = -1, jlo = 0, jhi = -1;
+            bool hit = k < n_boxes && P::map_hit(a.pp, recs[k], md.level, md.anchor) &&
+                       P::cell_bounds(a.pp, recs[k], md, md.level, md.anchor, ilo, ihi, jlo, jhi);
+            ilo = max(ilo, seg_i0), ihi = min(ihi, seg_i1);           // the map rows the segment holds
+            hit = hit && ilo <= ihi;
+            unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(L.nmap + seg, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) L.box[seg * a.box_cap + base + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
+            }
+            // every rectangle in turn, one cell (its `sub` rows) per lane
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const int bk = g * 32 + src;
+                const int bi0 = __shfl_sync(0xffffffffu, ilo, src), bi1 = __shfl_sync(0xffffffffu, ihi, src);
+                const int bj0 = __shfl_sync(0xffffffffu, jlo, src), bj1 = __shfl_sync(0xffffffffu, jhi, src);
+                const int nw = bj1 - bj0 + 1, n = (bi1 - bi0 + 1) * nw * md.sub;
+                const float inv = 1.0f / static_cast<float>(nw * md.sub);
+                const typename P::Rec& r = recs[bk];
+#pragma unroll 1
+                for (int c0 = 0; c0 < n; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool ok = false;
+                    int row = 0;
+                    if (c < n) {
+                        const int di = __float2int_rz((static_cast<float>(c) + 0.5f) * inv);  // c / (nw * sub), exact for c < 2^20
+                        const int rem = c - di * nw * md.sub;
+                        const int i = bi0 + di, j = bj0 + static_cast<int>(fdiv_u32(static_cast<uint32_t>(rem), md.div_sub));
+                        row = (i * md.width + bj0) * md.sub + rem;
+                        ok = row >= row0 && row <= row1 && P::pair_hit(a.pp, r, md, md.level, md.anchor, row, i, j);
+                    }
+                    const unsigned okb = __ballot_sync(0xffffffffu, ok);
+                    if (okb) {
+                        int at = 0;
+                        if (lane == 0) at = atomicAdd(L.npairs, __popc(okb));
+                        at = __shfl_sync(0xffffffffu, at, 0) + __popc(okb & ((1u << lane) - 1u));
+                        if (ok && at < kMaxPairs) {  // append, and chain to the row's earlier pairs
+                            L.pairs[at] = (static_cast<uint32_t>(local0 + row) << 16) | static_cast<uint32_t>(bk);
+                            L.next[at] = static_cast<unsigned short>(atomicExch(L.head + local0 + row, static_cast<uint32_t>(at)));
+                            atomicOr(L.rowbits + ((local0 + row) >> 5), 1u << ((local0 + row) & 31));
+                        }
+                    }
+                }
+            }
+        }
+        tile += nseg;
+        cur.t += nseg;  // (cursor_next, nseg times)
+        if (cur.t == md.n_tiles) {
+            cur.t = 0;
+            if (++cur.m == a.tt.n_maps) cur.m = 0, ++cur.b;
+        }
+    }
+}
+
+// The chunk rows that have pairs, in ascending order (one warp; the row map goes back to zero).  Returns their number.
+__device__ __forceinline__ int scan_rows(const SegLists& L) {
+    const int lane = threadIdx.x & 31;
+    constexpr int kPer = kMaxChunkTiles * 8 / 32;  // words per lane
+    uint32_t w[kPer];
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        w[u] = L.rowbits[lane * kPer + u];
+        cnt += __popc(w[u]);
+        L.rowbits[lane * kPer + u] = 0u;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    int at = incl - cnt;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+        for (uint32_t m = w[u]; m; m &= m - 1) L.rowlist[at++] = static_cast<unsigned short>((lane * kPer + u) * 32 + __ffs(m) - 1);
+    return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// Rows are resolved in ascending order, 32 per warp pass (lane <-> row), so the order of the float sums does not depend on
+// the order in which the pairs were appended: results are run-to-run deterministic.
+template <class P>
+__device__ __noinline__ LossAcc resolve_pass(const LossArgs<P>& a, const typename P::Rec* recs, const SegLists& L, int n_rows, int img,
+                                             unsigned short* scratch) {
     LossAcc acc = {0.f, 0.f, 0.f, 0};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned short* maplist = cand + a.box_cap;
     const int rpt = a.tt.rows_per_tile;
-    TileCursor cur;
-    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
+    unsigned short* mine = scratch + threadIdx.x * kRunCap;  // this lane's boxes (a row seldom has more than two or three)
 #pragma unroll 1
-    for (int tile = t_begin; tile < t_end;) {
-        // ---- segment: tiles [cur.t, cur.t + nseg) of map cur.m ---------------------------------------------------
-        const MapDesc& md = a.tt.maps[cur.m];
-        const int nseg = min(min(md.n_tiles - cur.t, t_end - tile), 32);
-        const int seg_r0 = cur.t * rpt + 32 * warp;  // first row of this warp's slice of the segment's first tile
-        int nmap = 0;
-        unsigned mask = 0u;
-        __syncwarp();
-#pragma unroll 1
-        for (int k0 = 0; k0 < n_boxes; k0 += 32) {
-            const int k = k0 + lane;
-            bool hit = k < n_boxes && P::map_hit(a.pp, recs[k], md.level, md.anchor);
-            if (hit) {
-                int rlo, rhi;
-                P::row_span(a.pp, recs[k], md, md.level, md.anchor, rlo, rhi);
-                rhi = min(rhi, md.rows - 1);
-                unsigned m = 0u;
-                for (int t = 0; t < nseg; ++t) {
-                    const int lo = seg_r0 + t * rpt;
-                    if (rhi >= lo && rlo < lo + 32) m |= 1u << t;
-                }
-                hit = m != 0u;
-                mask |= m;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (hit) maplist[nmap + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
-            nmap += __popc(bal);
-        }
-        mask = __reduce_or_sync(0xffffffffu, mask);
-        __syncwarp();
-#pragma unroll 1
-        for (int t = 0; t < nseg; ++t, ++tile, cursor_next(a.tt, cur)) {
-            if (!((mask >> t) & 1u)) continue;  // warp-uniform
+    for (int p0 = warp * 32; p0 < n_rows; p0 += DH_THREADS) {  // warp-uniform trip count
+        const int p = p0 + lane;
+        int pairs = 0;
+        if (p < n_rows) {
+            const int crow = L.rowlist[p];
+            int len = 0;
+            for (uint32_t q = L.head[crow]; q != kNoPair; q = L.next[q], ++len)
+                if (len < kRunCap) mine[len] = static_cast<unsigned short>(L.pairs[q] & 0xffffu);
+            L.head[crow] = kNoPair;  // (this lane is the row's only reader)
+            const int tix = crow / rpt;
+            const int m = L.tile_tab[tix * 4 + 0], r0 = L.tile_tab[tix * 4 + 1], seg = L.tile_tab[tix * 4 + 2];
+            const MapDesc& md = a.tt.maps[m];
             TileInfo ti;
-            float* gg = nullptr;
-            const float* __restrict__ gp = warp_tile(a, cur, img, warp, ti, &gg);
-            if (ti.nrows <= 0) continue;
-            int ncand = 0;
-#pragma unroll 1
-            for (int q0 = 0; q0 < nmap; q0 += 32) {  // ... narrowed to this tile's rows (and columns)
-                const int q = q0 + lane;
-                const int k = q < nmap ? maplist[q] : 0;
-                const bool hit = q < nmap && P::range_hit(a.pp, recs[k], ti, md);
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) cand[ncand + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned short>(k);
-                ncand += __popc(bal);
+            ti.b = img, ti.m = m, ti.r0 = r0, ti.nrows = min(rpt, md.rows - r0);
+            ti.level = md.level, ti.anchor = md.anchor, ti.height = md.height, ti.width = md.width, ti.sub = md.sub;
+            const unsigned short* boxes = mine;
+            if (len > kRunCap) boxes = L.box + seg * a.box_cap, len = L.nmap[seg];  // (rare) every box that can match the map
+            const int row = r0 + (crow - tix * rpt);
+            const long long off = static_cast<long long>(img) * md.image_stride + static_cast<long long>(row) * a.tt.ch;
+            CompactSink sink;
+            sink.clear();
+            pairs = P::match_row(a.pp, ti, md, row, sink, recs, boxes, len);
+            if (pairs > 0) {
+                const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
+                const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
+                const LossAcc d = correct_row(a.spec, md.pred + off, a.grad_maps[m] ? a.grad_maps[m] + off : nullptr, sink,
+                                              static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                acc.cls += d.cls, acc.reg += d.reg, acc.cen += d.cen, acc.npos += d.npos;
             }
-            if (ncand == 0) continue;  // warp-uniform
-            __syncwarp();
-            int pairs = 0;
-            if (lane < ti.nrows) {
-                CompactSink sink;
-                sink.clear();
-                const int row = ti.r0 + lane;
-                pairs = P::match_row(a.pp, ti, md, row, sink, recs, cand, ncand);
-                if (pairs > 0) {
-                    const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
-                    const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
-                    const LossAcc d = correct_row(a.spec, gp + lane * a.tt.ch, gg ? gg + lane * a.tt.ch : nullptr, sink, static_cast<float>(i),
-                                                  static_cast<float>(cell - i * md.width));
-                    acc.cls += d.cls, acc.reg += d.reg, acc.cen += d.cen, acc.npos += d.npos;
-                }
-            }
-            P::tile_epilogue(a.pp, ti, pairs);
-            __syncwarp();  // the candidate list is rebuilt for the next tile
         }
+        TileInfo tb;
+        tb.b = img;
+        P::tile_epilogue(a.pp, tb, pairs);
+    }
+    return acc;
+}
+
+// Fallback for a chunk whose pair list overflowed: warp w visits every row of tile w with the segment's whole box list.
+template <class P>
+__device__ __noinline__ LossAcc visit_dense(const LossArgs<P>& a, const typename P::Rec* recs, const SegLists& L, int img, int t_begin,
+                                            int t_end) {
+    LossAcc acc = {0.f, 0.f, 0.f, 0};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int tile = t_begin + warp; tile < t_end; tile += DH_THREADS / 32) {
+    TileCursor cur;
+    const int seg = locate_tile<P>(a, img, t_begin, tile, cur);
+    const MapDesc& md = a.tt.maps[cur.m];
+    TileInfo ti;
+    cursor_info(a.tt, cur, ti);
+    const long long off = static_cast<long long>(img) * md.image_stride + static_cast<long long>(ti.r0) * a.tt.ch;
+    const float* __restrict__ gp = md.pred + off;
+    float* gg = a.grad_maps[ti.m] ? a.grad_maps[ti.m] + off : nullptr;
+    const unsigned short* cand = L.box + seg * a.box_cap;
+    const int ncand = L.nmap[seg];
+    int pairs = 0;
+#pragma unroll 1
+    for (int r = lane; r < ti.nrows; r += 32) {
+        CompactSink sink;
+        sink.clear();
+        const int row = ti.r0 + r;
+        const int n = P::match_row(a.pp, ti, md, row, sink, recs, cand, ncand);
+        if (n > 0) {
+            pairs += n;
+            const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
+            const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
+            const LossAcc d = correct_row(a.spec, gp + static_cast<long long>(r) * a.tt.ch, gg ? gg + static_cast<long long>(r) * a.tt.ch : nullptr,
+                                          sink, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+            acc.cls += d.cls, acc.reg += d.reg, acc.cen += d.cen, acc.npos += d.npos;
+        }
+    }
+    P::tile_epilogue(a.pp, ti, pairs);
     }
     return acc;
 }
@@ -572,55 +744,60 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// Reduction of the chunk partials without a second launch and off the kernel's tail:
-//   image_done   warp 0 of a CTA calls it after every chunk: the chunk is counted on its image's counter, and the warp
-//                that counts the image's last chunk adds up the image's partials (float64, fixed lane/shuffle order ->
-//                deterministic) into per_image[img] and puts the counter back to zero for the next launch;
-//   finalize_total  the last CTA of the launch sums the per-image rows in a fixed order into the total and, when the
-//                communicator is attached, exchanges the total with the peer ranks (dh_comm.cuh).
+// Reduction of the chunk partials without a second launch, by the last CTA of the launch:
+//   reduce_images   chunk partials -> per_image rows.  Tier by tier, L = 1..32 lanes share an image so that no lane has
+//                   more than 16 partials to add (a fine tail tier has 300 chunks per image, the coarse tier ~38) and the
+//                   loads of all images of a pass are in flight together; float64, fixed lane / shuffle order ->
+//                   deterministic.
+//   finalize_total  per_image rows -> total, and, when the communicator is attached, the exchange of the total with
+//                   the peer ranks (dh_comm.cuh).
 template <class P>
-__device__ __forceinline__ void image_done(const LossArgs<P>& a, int img, int lane) {
-    int tk = 0;
+__device__ __forceinline__ void reduce_images(const LossArgs<P>& a, double (&tot)[4]) {
+    constexpr int kInFlight = 16;  // partials one lane loads per image: all issued before the first add (one L2 round trip)
+    const int tid = threadIdx.x;
+    const float4* part = reinterpret_cast<const float4*>(a.partials);
+#pragma unroll 1
+    for (int tk = 0; tk < a.n_tiers; ++tk) {
+        const ChunkTier& T = a.tiers[tk];
+        const int img_end = tk + 1 < a.n_tiers ? a.tiers[tk + 1].image0 : a.tt.batch;
+        int L = 1;
+        while (L < 32 && L * kInFlight < T.cpi) L <<= 1;
+        const int G = DH_THREADS / L, sub = tid & (L - 1);
+#pragma unroll 1
+        for (int b0 = T.image0; b0 < img_end; b0 += G) {  // block-uniform trip count
+            const int b = b0 + tid / L;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            if (b < img_end) {
+                const float4* p = part + T.chunk0 + static_cast<long long>(b - T.image0) * T.cpi;
+#pragma unroll 1
+                for (int t0 = sub; t0 < T.cpi; t0 += L * kInFlight) {  // one trip unless an image has > 512 chunks
+                    float4 v[kInFlight];
 #pragma unroll
-    for (int q = 1; q < kMaxChunkTiers; ++q)
-        if (q < a.n_tiers && img >= a.tiers[q].image0) tk = q;
-    const ChunkTier& T = a.tiers[tk];
-    int fin = 0;
-    if (lane == 0) {
-        __threadfence();  // this CTA's partial of the chunk is visible device-wide before the chunk is counted
-        fin = atomicAdd(a.img_cnt + img, 1u) == static_cast<unsigned>(T.cpi - 1);
-    }
-    fin = __shfl_sync(0xffffffffu, fin, 0);
-    if (!fin) return;
-    __threadfence();
-    const float4* p = reinterpret_cast<const float4*>(a.partials) + T.chunk0 + static_cast<long long>(img - T.image0) * T.cpi;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-    for (int t = lane; t < T.cpi; t += 32) {
-        const float4 v = __ldcg(p + t);
-        acc[0] += v.x, acc[1] += v.y, acc[2] += v.z, acc[3] += v.w;
-    }
+                    for (int u = 0; u < kInFlight; ++u)
+                        v[u] = t0 + u * L < T.cpi ? __ldcg(p + t0 + u * L) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = warp_sum_d(acc[k]);
-    if (lane == 0) {
-        reinterpret_cast<float4*>(a.per_image)[img] = make_float4(static_cast<float>(acc[0]), static_cast<float>(acc[1]),
-                                                                  static_cast<float>(acc[2]), static_cast<float>(acc[3]));
-        a.img_cnt[img] = 0u;
+                    for (int u = 0; u < kInFlight; ++u) acc[0] += v[u].x, acc[1] += v[u].y, acc[2] += v[u].z, acc[3] += v[u].w;
+                }
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            }
+            if (b < img_end && sub == 0) {
+                const float4 o4 = make_float4(static_cast<float>(acc[0]), static_cast<float>(acc[1]), static_cast<float>(acc[2]),
+                                              static_cast<float>(acc[3]));
+                reinterpret_cast<float4*>(a.per_image)[b] = o4;
+                tot[0] += o4.x, tot[1] += o4.y, tot[2] += o4.z, tot[3] += o4.w;  // the total is the sum of the float32 per-image values
+            }
+        }
     }
 }
 
-// `red` is [8][4] doubles followed by 4 floats (dynamic shared memory)
+// `red` is [8][4] doubles followed by 4 floats (dynamic shared memory); tot = this thread's share of the total
 template <class P>
-__device__ __forceinline__ void finalize_total(const LossArgs<P>& a, double* red) {
+__device__ __forceinline__ void finalize_total(const LossArgs<P>& a, double (&tot)[4], double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.out_total) return;
-    const float4* rows = reinterpret_cast<const float4*>(a.per_image);
-    double tot[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-    for (int b = tid; b < a.tt.batch; b += DH_THREADS) {  // the total is the sum of the float32 per-image values
-        const float4 v = __ldcg(rows + b);
-        tot[0] += v.x, tot[1] += v.y, tot[2] += v.z, tot[3] += v.w;
-    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) tot[k] = warp_sum_d(tot[k]);
     if (lane == 0) {
@@ -657,7 +834,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 64);  // [8][4] floats; [8][4] doubles in the finalize
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned short* cand = reinterpret_cast<unsigned short*>(smem + lay.cand_off) + warp * 2 * ga.box_cap;
+    const SegLists segs = seg_lists(smem + lay.seg_off, ga.box_cap);
     const bool vec = ga.allow_vec && (ga.tt.ch & 3) == 0 && ga.spec.cen_mode == 0 && ga.spec.reg_ch == 4;
     const long long n_chunks = ga.n_chunks;
     long long chunk = blockIdx.x;  // (the launchers clamp the grid to the chunk count)
@@ -665,13 +842,23 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         mbar_init(boxbar, 1);
         mbar_init_fence();
     }
+    if (tid <= kMaxSegments) segs.nmap[tid] = 0;  // nmap[], npairs
+    for (int e = tid; e < kMaxChunkTiles * DH_THREADS; e += DH_THREADS) segs.head[e] = kNoPair;
+    if (tid < kMaxChunkTiles * 8) segs.rowbits[tid] = 0u;
     __syncthreads();
 
     uint32_t box_parity = 0;
     int cur_img = -1, n_boxes = 0;
     const bool trace = ga.trace != nullptr && tid == 0;
     int n_done = 0;
-    if (trace) ga.trace[blockIdx.x * 4 + 0] = static_cast<long long>(global_ns());
+    long long ph[6] = {0, 0, 0, 0, 0, 0}, pt = 0;  // trace: time thread 0 spends per phase of a chunk
+#define DH_TRACE_PHASE(i)                                    \
+    if (trace) {                                            \
+        const long long now = static_cast<long long>(global_ns()); \
+        ph[i] += now - pt;                                  \
+        pt = now;                                           \
+    }
+    if (trace) ga.trace[blockIdx.x * kTraceSlots + 0] = pt = static_cast<long long>(global_ns());
 #pragma unroll 1
     for (; chunk < n_chunks;) {
         int img, sub, t_begin, t_end;
@@ -685,13 +872,33 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
             cur_img = img;
         }
         if (sub == 0) P::image_prologue(a.pp, recs, n_boxes, img);
-        if (trace && n_done++ == 0) ga.trace[blockIdx.x * 4 + 1] = static_cast<long long>(global_ns());
+        DH_TRACE_PHASE(0)
+        if (n_boxes > 0) pair_pass<P>(a, recs, n_boxes, segs, img, t_begin, t_end);  // (read after the barrier behind the streaming pass)
+        DH_TRACE_PHASE(1)
+        if (trace && n_done++ == 0) ga.trace[blockIdx.x * kTraceSlots + 1] = static_cast<long long>(global_ns());
 
         const StreamAcc sa = vec ? stream_pass_vec<P, kCls, kGrad>(a, img, t_begin, t_end)
                                  : stream_pass_scalar<P, kCls, kGrad>(a, img, t_begin, t_end);
-        if (kGrad) __syncthreads();  // every zero-label gradient of the chunk is written before a matched row overwrites its own
+        DH_TRACE_PHASE(2)
         LossAcc acc = {0.f, 0.f, 0.f, 0};  // corrections + regression, natural units
-        if (n_boxes > 0) acc = correct_pass<P>(a, recs, n_boxes, cand, img, t_begin, t_end);
+        if (n_boxes > 0 || kGrad) __syncthreads();  // (block-uniform) the pair list is complete; every zero-label gradient of
+                                                   // the chunk is written before a matched row overwrites its own
+        DH_TRACE_PHASE(3)
+        int n_pairs = 0;
+        if (n_boxes > 0) {
+            n_pairs = *segs.npairs;  // block-uniform
+            if (n_pairs > kMaxPairs) {
+                acc = visit_dense<P>(a, recs, segs, img, t_begin, t_end);
+            } else if (n_pairs > 0) {
+                if (warp == 0) {
+                    const int n_rows = scan_rows(segs);
+                    if (lane == 0) segs.npairs[1] = n_rows;
+                }
+                __syncthreads();
+                acc = resolve_pass<P>(a, recs, segs, segs.npairs[1], img, reinterpret_cast<unsigned short*>(smem + lay.run_off));
+            }
+        }
+        DH_TRACE_PHASE(4)
 
         // ---- per-chunk reduction -> partials[chunk] -----------------------------------------------------------
         float q0, q1, q2, q3;
@@ -718,14 +925,21 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
             if (lane == 0) reinterpret_cast<float4*>(a.partials)[chunk] = o;
         }
         chunk = *next_chunk;
-        __syncthreads();  // wred / next_chunk are free again
-        // warp 0 counts the chunk on its image (and reduces the image when it was the last one) while the other warps
-        // already stream the next chunk
-        if (ga.fold_finalize && warp == 0) image_done<P>(a, img, lane);
+        if (n_boxes > 0) {  // (the correct pass is done with the lists) counters and row chains back to empty
+            if (tid <= kMaxSegments) segs.nmap[tid] = 0;
+            if (n_pairs > kMaxPairs) {  // (the resolve pass leaves both tables empty; the dense visit does not use them)
+                for (int e = tid; e < kMaxChunkTiles * DH_THREADS; e += DH_THREADS) segs.head[e] = kNoPair;
+                if (tid < kMaxChunkTiles * 8) segs.rowbits[tid] = 0u;
+            }
+        }
+        __syncthreads();  // wred / next_chunk are free again; the lists are empty
+        DH_TRACE_PHASE(5)
     }
+#undef DH_TRACE_PHASE
     if (trace) {
-        ga.trace[blockIdx.x * 4 + 2] = static_cast<long long>(global_ns());
-        ga.trace[blockIdx.x * 4 + 3] = n_done;
+        ga.trace[blockIdx.x * kTraceSlots + 2] = static_cast<long long>(global_ns());
+        ga.trace[blockIdx.x * kTraceSlots + 3] = n_done;
+        for (int k = 0; k < 6; ++k) ga.trace[blockIdx.x * kTraceSlots + 4 + k] = ph[k];
     }
     // ---- the last CTA to get here finalizes ------------------------------------------------------------------
     if (tid == 0) {
@@ -741,8 +955,10 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     if (!ga.fold_finalize) return;
     __syncthreads();
     if (*is_last) {
-        finalize_total<P>(a, reinterpret_cast<double*>(wred));
-        if (trace) ga.trace[static_cast<long long>(gridDim.x) * 4] = static_cast<long long>(global_ns());
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        reduce_images<P>(a, tot);
+        finalize_total<P>(a, tot, reinterpret_cast<double*>(wred));
+        if (trace) ga.trace[static_cast<long long>(gridDim.x) * kTraceSlots] = static_cast<long long>(global_ns());
     }
 }
 

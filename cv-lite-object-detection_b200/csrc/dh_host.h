@@ -20,9 +20,12 @@ struct dh_handle_s {
     int encode_min_chunk;      // DH_OPT_ENCODE_MIN_CHUNK
     int fcos_select_mode;  // DH_OPT_FCOS_SELECT
     int nms_sort;          // DH_OPT_NMS_SORT
+    int nms_filter;        // DH_OPT_NMS_FILTER
+    int nms_chain;         // DH_OPT_NMS_CHAIN
     int loss_allreduce;    // DH_OPT_LOSS_ALLREDUCE
     int allreduce_mode;    // DH_OPT_ALLREDUCE
     int fused_tail;        // DH_OPT_FUSED_TAIL
+    int fused_max_chunk;   // DH_OPT_FUSED_MAX_CHUNK
     int encode_kernel;     // DH_OPT_ENCODE_KERNEL
     long long launches;
     void* scratch;        // device scratch (loss partials, NMS masks), grown on demand
@@ -37,8 +40,6 @@ struct dh_handle_s {
     std::recursive_mutex mu;
     long long* trace;  // dh_set_trace: caller-owned device buffer for the fused kernel's per-CTA time stamps
     long long trace_bytes;
-    unsigned int* img_cnt;  // per-image chunk counters of the fused loss kernel (zero between launches)
-    int img_cnt_cap;
     int* dev_status;  // device word: sticky input-validation bits (dh_get_status)
     void* comm;  // dh::Comm* once dh_comm_* has been called (comm.cu)
 };
@@ -51,8 +52,6 @@ void* scratch(dh_handle_s* h, size_t bytes);
 void* scratch_b(dh_handle_s* h, size_t bytes);
 // A zeroed (stream-ordered) device counter for one kernel's dynamic tile scheduler; null on error.
 unsigned int* next_sched_counter(dh_handle_s* h, cudaStream_t st);
-// Zeroed per-image counters for at least `batch` images (grown, with a device synchronisation, on demand); null on error.
-unsigned int* image_counters(dh_handle_s* h, int batch);
 
 #define DH_CHECK_ARG(cond, ...)                                      \
     do {                                                             \

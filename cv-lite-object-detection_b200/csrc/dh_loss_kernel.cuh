@@ -24,7 +24,7 @@ namespace dh {
 struct LossSpec {
     int reg_ch;    // 0 or 4: channels [0, reg_ch) are box regression
     int cen_mode;  // 0 no centerness channel, 1 smooth-L1(sigmoid(pred)) over all rows, 2 focal, 3 present but unused
-    int reg_mode;  // 0 smooth-L1, 1 -log(IoU) on the integer grid
+    int reg_mode;  // 0 smooth-L1, 1 -log(IoU) on the integer grid, 2 1 - GIoU on the same boxes
     int pos_rule;  // 0 max(class) >= 1, 1 max(class) > 0, 2 external per-row mask
     int cls_mode;  // 0 focal, 1 sigmoid cross-entropy (alpha / gamma unused)
     float alpha, gamma, delta;
@@ -40,7 +40,7 @@ struct NoPolicy {
     };
 };
 
-constexpr int kMaxChunkTiers = 4;
+constexpr int kMaxChunkTiers = 5;
 struct ChunkTier {
     long long chunk0;  // id of the tier's first chunk
     int image0;        // first image of the tier
@@ -72,7 +72,6 @@ struct LossArgs {
     ChunkTier tiers[kMaxChunkTiers];
     long long n_chunks;
     float* per_image;  // [batch, 4] (caller's buffer or scratch)
-    unsigned int* img_cnt;  // [batch] chunks finished per image; zero between launches (the reducing warp resets it)
     float* out_total;  // [4] or null
     int fold_finalize;  // 1: the last CTA finalizes (no finalize kernels follow)
     int use_comm;       // 1: out_total is summed over the ranks of `comm` (peer mailboxes)
@@ -143,8 +142,10 @@ __device__ __forceinline__ float smooth_l1_term(float y, float x, float delta) {
     const float d = y - x, ad = fabsf(d);
     return ad < delta ? 0.5f * d * d : ad;  // no -delta/2 (FCOS/fcos.py:386-388)
 }
-// -log(IoU) of two tblr boxes anchored at the integer grid point (gx, gy) (FCOS/fcos.py:393-441)
-__device__ __forceinline__ float iou_loss_term(const float* t, const float* p, float gy, float gx) {
+// Box loss of two tblr boxes anchored at the integer grid point (gx, gy).  mode 1: -log(IoU), FCOS/fcos.py:393-441.
+// mode 2 (DH_REG_GIOU, an extension: BASELINE's north_star names it, the reference has no GIoU): 1 - GIoU on the same
+// box construction, GIoU = IoU - (C - union) / (C + 1e-12) with C the area of the smallest enclosing box.
+__device__ __forceinline__ float iou_loss_term(const float* t, const float* p, float gy, float gx, int mode = 1) {
     const float ty0 = gy - t[0], ty1 = gy + t[1], tx0 = gx - t[2], tx1 = gx + t[3];
     const float py0 = gy - p[0], py1 = gy + p[1], px0 = gx - p[2], px1 = gx + p[3];
     const float ih = fmaxf(0.f, fminf(ty1, py1) - fmaxf(ty0, py0));
@@ -152,6 +153,10 @@ __device__ __forceinline__ float iou_loss_term(const float* t, const float* p, f
     const float inter = iw * ih;
     const float uni = ((ty1 - ty0) * (tx1 - tx0) + (py1 - py0) * (px1 - px0)) - inter;
     const float iou = inter / (uni + 1.0e-12f);
+    if (mode == 2) {
+        const float ac = (fmaxf(ty1, py1) - fminf(ty0, py0)) * (fmaxf(tx1, px1) - fminf(tx0, px0));
+        return 1.0f - (iou - (ac - uni) / (ac + 1.0e-12f));
+    }
     return -logf(iou + 1.0e-12f);
 }
 
@@ -184,7 +189,7 @@ __device__ __forceinline__ float cen_l1_grad(float y, float x, float delta) {
     return smooth_l1_grad(y, s, delta) * s * (1.0f - s);
 }
 // gradient of iou_loss_term with respect to the four predicted distances (t, b, l, r)
-__device__ __forceinline__ void iou_loss_grad(const float* t, const float* p, float gy, float gx, float* g) {
+__device__ __forceinline__ void iou_loss_grad(const float* t, const float* p, float gy, float gx, float* g, int mode = 1) {
     const float ty0 = gy - t[0], ty1 = gy + t[1], tx0 = gx - t[2], tx1 = gx + t[3];
     const float py0 = gy - p[0], py1 = gy + p[1], px0 = gx - p[2], px1 = gx + p[3];
     const float ih_raw = fminf(ty1, py1) - fmaxf(ty0, py0), iw_raw = fminf(tx1, px1) - fmaxf(tx0, px0);
@@ -201,6 +206,23 @@ __device__ __forceinline__ void iou_loss_grad(const float* t, const float* p, fl
     di[2] = ih * live_w * (px0 > tx0 ? 1.0f : 0.f);
     di[3] = ih * live_w * (px1 < tx1 ? 1.0f : 0.f);
     da[0] = da[1] = pw, da[2] = da[3] = ph;
+    if (mode == 2) {  // d (1 - GIoU) = -(d IoU - d ((C - union) / (C + eps)))
+        const float eh = fmaxf(ty1, py1) - fminf(ty0, py0), ew = fmaxf(tx1, px1) - fminf(tx0, px0);
+        const float ac = eh * ew, dc = ac + 1.0e-12f;
+        float de[4];  // d C / d p_k: an edge of the enclosing box moves with the prediction where the prediction is the outer one
+        de[0] = ew * (py0 < ty0 ? 1.0f : 0.f);
+        de[1] = ew * (py1 > ty1 ? 1.0f : 0.f);
+        de[2] = eh * (px0 < tx0 ? 1.0f : 0.f);
+        de[3] = eh * (px1 > tx1 ? 1.0f : 0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float d_uni = da[q] - di[q];
+            const float d_iou = (di[q] * den - inter * d_uni) / (den * den);
+            const float d_gap = ((de[q] - d_uni) * dc - (ac - uni) * de[q]) / (dc * dc);
+            g[q] = -(d_iou - d_gap);
+        }
+        return;
+    }
     const float k = -1.0f / (iou + 1.0e-12f);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -416,10 +438,10 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                                     const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
                                     const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
                                     const float tv[4] = {y.x, y.y, y.z, y.w}, pv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-                                    acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                                    acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), sp.reg_mode);
                                     if (kGrad && gg) {
                                         float g4[4];
-                                        iou_loss_grad(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), g4);
+                                        iou_loss_grad(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), g4, sp.reg_mode);
                                         const float k = m * sp.w_reg;
                                         gv = make_float4(k * g4[0], k * g4[1], k * g4[2], k * g4[3]);
                                     }
@@ -455,7 +477,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                         const float m = sp.pos_rule == 2 ? __int_as_float(rowpos[r]) : (pos_row ? 1.0f : 0.0f);
                         if (c == 0 && sp.reg_ch > 0 && m != 0.f) {
                             if (!kFused) ++acc.npos;
-                            if (sp.reg_mode == 1) {
+                            if (sp.reg_mode != 0) {
                                 const int row = ti.r0 + r;
                                 const int cell = static_cast<int>(fdiv_u32(row, md.div_sub));
                                 const int i = static_cast<int>(fdiv_u32(cell, md.div_width));
@@ -465,7 +487,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                                     pv[k] = gp[e + k];
                                     tv[k] = kFused ? st[e + k] : gt[e + k];
                                 }
-                                acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width));
+                                acc.reg += m * iou_loss_term(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), sp.reg_mode);
                             }
                         }
                         accumulate_element(sp, cls0, c, x[u], y, m, acc);
@@ -484,7 +506,7 @@ __global__ void __launch_bounds__(DH_THREADS) loss_kernel(const __grid_constant_
                                         float tv[4], pv[4], g4[4];
 #pragma unroll
                                         for (int k = 0; k < 4; ++k) pv[k] = gp[e - c + k], tv[k] = gt[e - c + k];
-                                        iou_loss_grad(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), g4);
+                                        iou_loss_grad(tv, pv, static_cast<float>(i), static_cast<float>(cell - i * md.width), g4, sp.reg_mode);
                                         g = m * sp.w_reg * (c == 0 ? g4[0] : (c == 1 ? g4[1] : (c == 2 ? g4[2] : g4[3])));
                                     }
                                 }

@@ -12,8 +12,11 @@
 
 namespace dh {
 
-enum FcosMode { FCOS_FOOTPRINT = 0, FCOS_CENTER3X3 = 1, FCOS_CENTER_ONLY = 2, FCOS_CENTER_V1 = 3 };
-enum CenterNetMode { CN_ONEHOT_SCALES = 0, CN_HOURGLASS = 1, CN_POWER_FALLOFF = 2, CN_HOURGLASS4 = 3 };
+enum FcosMode { FCOS_FOOTPRINT = 0, FCOS_CENTER3X3 = 1, FCOS_CENTER_ONLY = 2, FCOS_CENTER_V1 = 3, FCOS_MIN_AREA = 4 };
+enum CenterNetMode { CN_ONEHOT_SCALES = 0, CN_HOURGLASS = 1, CN_POWER_FALLOFF = 2, CN_HOURGLASS4 = 3, CN_GAUSSIAN = 4 };
+// FCOS_MIN_AREA and CN_GAUSSIAN are the canonical variants BASELINE's north_star names and the reference does not have
+// (SURVEY.md section 0); their specifications are fcos_format_data(order="min_area") and
+// centernet_gaussian_format_data of the CPU oracle.
 
 struct Corners {
     float y0, x0, y1, x1;
@@ -50,12 +53,14 @@ __device__ __forceinline__ double ratio64(float a, float b) {
 // (encoders, and the shared-memory tile of the unfused-compatible loss kernel); CompactSink keeps the row in
 // registers as <= 5 regression values + a class bitmask (fused loss: targets never exist in memory at all).
 struct DenseSink {
+    static constexpr bool kExact = true;  // the targets themselves are the product: the reference's float64 arithmetic
     float* dst;
     __device__ __forceinline__ void cls(int first_class_ch, int c) { dst[first_class_ch + c] = 1.0f; }
     __device__ __forceinline__ void reg(int k, float v) { dst[k] = v; }
 };
 constexpr int kCompactClassWords = 4;  // fused loss fast path: up to 128 classes
 struct CompactSink {
+    static constexpr bool kExact = false;  // targets feed a loss with a 1e-5 bar: float32 arithmetic is enough
     float r[5];
     uint32_t m[kCompactClassWords];
     __device__ __forceinline__ void clear() {
@@ -135,7 +140,7 @@ struct FcosPolicy {
         }
         r.y0s = fdiv(c.y0, s), r.x0s = fdiv(c.x0, s), r.y1s = fdiv(c.y1, s), r.x1s = fdiv(c.x1, s);
         const float h_ratio = fdiv(hi, s), w_ratio = fdiv(wi, s);  // fcos.py:162-163
-        if (p.mode == FCOS_FOOTPRINT) {
+        if (p.mode == FCOS_FOOTPRINT || p.mode == FCOS_MIN_AREA) {
             const float half_h = fdiv(g[2], 2.0f), half_w = fdiv(g[3], 2.0f);
             const int y_low = max(0, trunc_i(fmul(fsub(g[0], half_h), h_ratio)) + 1);  // fcos.py:217-225
             const int x_low = max(0, trunc_i(fmul(fsub(g[1], half_w), w_ratio)) + 1);
@@ -196,11 +201,14 @@ struct FcosPolicy {
         return r.rx1 > j0 && r.rx0 <= j1;
     }
 
-    // a contiguous row interval [rlo, rhi] of the map that holds every row this box can touch (rlo > rhi: none)
-    __device__ static void row_span(const Params&, const Rec& r, const MapDesc& md, int, int, int& rlo, int& rhi) {
-        rlo = r.ry0 * md.width + r.rx0;
-        rhi = (r.ry1 - 1) * md.width + r.rx1 - 1;
+    // cells [ilo, ihi] x [jlo, jhi] of the map that hold every row this box can touch; false: none
+    __device__ static bool cell_bounds(const Params&, const Rec& r, const MapDesc& md, int, int, int& ilo, int& ihi, int& jlo, int& jhi) {
+        ilo = max(r.ry0, 0), ihi = min(r.ry1, md.height) - 1, jlo = max(r.rx0, 0), jhi = min(r.rx1, md.width) - 1;
+        return ilo <= ihi && jlo <= jhi;
     }
+
+    // may this box paint row `row` = cell (i, j)?  A superset is enough (match_row decides); here the rectangle is exact.
+    __device__ static bool pair_hit(const Params&, const Rec&, const MapDesc&, int, int, int, int, int) { return true; }
 
     // returns the number of painters that touched the row (0 = row stays zero)
     __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
@@ -226,7 +234,11 @@ struct FcosPolicy {
                 const float sc = (dy == 0 && dx == 0) ? 1.0f : ((dy != 0 && dx != 0) ? 0.25f : 0.5f);
                 best_score = fmaxf(best_score, sc);
             }
-            if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
+            // the reference paints in ascending-area order, so the largest covering box supplies channels 0..4
+            // (fcos.py:202-209); FCOS_MIN_AREA is what its comment (:185-188) and the FCOS paper ask for: the smallest
+            if (p.mode == FCOS_MIN_AREA ? (best < 0 || r.area < best_area || (r.area == best_area && k > best))
+                                        : paints_later(r.area, k, best_area, best))
+                best = k, best_area = r.area;
         }
         if (best < 0) return 0;
         const Rec& r = recs[best];
@@ -235,7 +247,7 @@ struct FcosPolicy {
             return hits;
         }
         const float fi = static_cast<float>(i) + 0.5f, fj = static_cast<float>(j) + 0.5f;
-        if (p.mode != FCOS_FOOTPRINT) {  // fcos_center.py:267-273 (unclipped)
+        if (p.mode != FCOS_FOOTPRINT && p.mode != FCOS_MIN_AREA) {  // fcos_center.py:267-273 (unclipped)
             dst.reg(0, fsub(fi, r.y0s));
             dst.reg(1, fsub(fsub(r.y1s, static_cast<float>(i)), 0.5f));
             dst.reg(2, fsub(fj, r.x0s));
@@ -347,29 +359,38 @@ struct RetinaPolicy {
         return j1 * s + 0.5f * aw > r.lo_x + need_x - 0.01f && j0 * s - 0.5f * aw < r.hi_x - need_x + 0.01f;
     }
 
-    // a contiguous row interval [rlo, rhi] of the (level, anchor) map that holds every anchor this box can match: the
-    // inverse of range_hit's tests (anchor row i needs i*s + ah/2 > lo_y + need - 0.01 and i*s - ah/2 < hi_y - need + 0.01),
-    // widened by a cell on each side
-    __device__ static void row_span(const Params& p, const Rec& r, const MapDesc& md, int level, int anchor, int& rlo, int& rhi) {
+    // cells [ilo, ihi] x [jlo, jhi] of the (level, anchor) map that hold every anchor this box can match: the inverse of
+    // range_hit's tests (anchor row i needs i*s + ah/2 > lo_y + need - 0.01 and i*s - ah/2 < hi_y - need + 0.01), widened
+    // by a cell on each side; false: none
+    __device__ static bool cell_bounds(const Params& p, const Rec& r, const MapDesc& md, int level, int anchor, int& ilo, int& ihi,
+                                       int& jlo, int& jhi) {
         if (p.thr < 0.f) {
-            rlo = 0, rhi = md.rows - 1;
-            return;
+            ilo = 0, ihi = md.height - 1, jlo = 0, jhi = md.width - 1;
+            return true;
         }
         const float ah = p.anchor_h[level][anchor], aw = p.anchor_w[level][anchor];
         const float inv_s = 1.0f / static_cast<float>(p.stride[level]);
         const float k = p.thr > 0.f ? 0.999f * p.thr : 0.f;
         const float need_y = k * fmaxf(ah, r.gh) - 0.01f, need_x = k * fmaxf(aw, r.gw) - 0.01f;
         const float hmax = static_cast<float>(md.height), wmax = static_cast<float>(md.width);
-        const int ilo = static_cast<int>(fminf(fmaxf(floorf((r.lo_y + need_y - 0.5f * ah) * inv_s), 0.f), hmax));
-        const int ihi = static_cast<int>(fminf(fmaxf(ceilf((r.hi_y - need_y + 0.5f * ah) * inv_s), -1.f), hmax - 1.f));
-        const int jlo = static_cast<int>(fminf(fmaxf(floorf((r.lo_x + need_x - 0.5f * aw) * inv_s), 0.f), wmax));
-        const int jhi = static_cast<int>(fminf(fmaxf(ceilf((r.hi_x - need_x + 0.5f * aw) * inv_s), -1.f), wmax - 1.f));
-        if (ilo > ihi || jlo > jhi) {
-            rlo = 1, rhi = 0;
-            return;
-        }
-        rlo = ilo * md.width + jlo;
-        rhi = ihi * md.width + jhi;
+        ilo = static_cast<int>(fminf(fmaxf(floorf((r.lo_y + need_y - 0.5f * ah) * inv_s), 0.f), hmax));
+        ihi = static_cast<int>(fminf(fmaxf(ceilf((r.hi_y - need_y + 0.5f * ah) * inv_s), -1.f), hmax - 1.f));
+        jlo = static_cast<int>(fminf(fmaxf(floorf((r.lo_x + need_x - 0.5f * aw) * inv_s), 0.f), wmax));
+        jhi = static_cast<int>(fminf(fmaxf(ceilf((r.hi_x - need_x + 0.5f * aw) * inv_s), -1.f), wmax - 1.f));
+        return ilo <= ihi && jlo <= jhi;
+    }
+
+    // may this box match the anchor at cell (i, j)?  A superset is enough (match_row decides exactly): the IoU test without
+    // the division and with a margin under the threshold
+    __device__ static bool pair_hit(const Params& p, const Rec& r, const MapDesc&, int level, int anchor, int, int i, int j) {
+        if (p.thr < 0.f) return true;
+        const float ah = p.anchor_h[level][anchor], aw = p.anchor_w[level][anchor];
+        const float s = static_cast<float>(p.stride[level]);
+        const float ay = static_cast<float>(i) * s, ax = static_cast<float>(j) * s;
+        const float dy = fmaxf(0.f, fminf(r.hi_y, ay + 0.5f * ah) - fmaxf(r.lo_y, ay - 0.5f * ah));
+        const float dx = fmaxf(0.f, fminf(r.hi_x, ax + 0.5f * aw) - fmaxf(r.lo_x, ax - 0.5f * aw));
+        const float inter = dy * dx;
+        return inter > (p.thr - 1.0e-3f) * (r.area + ah * aw - inter) - 1.0e-6f;
     }
 
     // returns the number of (gt, anchor) pairs above the threshold at this row (:302-317)
@@ -404,16 +425,21 @@ struct RetinaPolicy {
             if (iou > p.thr) {  // :302 strict
                 ++pairs;
                 dst.cls(kRegCh, r.cls);
-                best = k;  // highest GT index wins the regression (:357)
+                best = max(best, k);  // highest GT index wins the regression (:357), whatever the order of the list
             }
         }
         if (best >= 0) {  // :337-353, float64 like the reference's containers
             const Rec& r = recs[best];
-            const double dah = static_cast<double>(ah), daw = static_cast<double>(aw);
-            dst.reg(0, static_cast<float>(ddiv(dsub(static_cast<double>(i * s), static_cast<double>(r.gy)), dah)));
-            dst.reg(1, static_cast<float>(ddiv(dsub(static_cast<double>(j * s), static_cast<double>(r.gx)), daw)));
-            dst.reg(2, static_cast<float>(ddiv(static_cast<double>(r.gh), dah)));
-            dst.reg(3, static_cast<float>(ddiv(static_cast<double>(r.gw), daw)));
+            if constexpr (Sink::kExact) {
+                const double dah = static_cast<double>(ah), daw = static_cast<double>(aw);
+                dst.reg(0, static_cast<float>(ddiv(dsub(static_cast<double>(i * s), static_cast<double>(r.gy)), dah)));
+                dst.reg(1, static_cast<float>(ddiv(dsub(static_cast<double>(j * s), static_cast<double>(r.gx)), daw)));
+                dst.reg(2, static_cast<float>(ddiv(static_cast<double>(r.gh), dah)));
+                dst.reg(3, static_cast<float>(ddiv(static_cast<double>(r.gw), daw)));
+            } else {  // (four float64 divisions are ~250 instructions on the warp that holds up its CTA's chunk)
+                const float iah = 1.0f / ah, iaw = 1.0f / aw;
+                dst.reg(0, (ay - r.gy) * iah), dst.reg(1, (ax - r.gx) * iaw), dst.reg(2, r.gh * iah), dst.reg(3, r.gw * iaw);
+            }
         }
         return pairs;
     }
@@ -439,12 +465,14 @@ struct CenterNetPolicy {
         int muy, mux;
         int cls;
         int flags;  // bit0 live_y, bit1 live_x, bit2 valid
+        float gstd;  // CN_GAUSSIAN: max(1, sqrt(box area in cells)), tf_centernet.py:203-205
     };
     static constexpr int kRegChOnehot = 4;
     static constexpr bool kScatter = true;  // centre-cell modes: one thread per box writes its single row
-    __device__ static bool use_scatter(const Params& p) { return p.mode != CN_POWER_FALLOFF; }
+    __device__ static bool footprint(const Params& p) { return p.mode == CN_POWER_FALLOFF || p.mode == CN_GAUSSIAN; }
+    __device__ static bool use_scatter(const Params& p) { return !footprint(p); }
 
-    __device__ static int reg_ch(const Params& p) { return (p.mode == CN_POWER_FALLOFF || p.mode == CN_HOURGLASS4) ? 5 : 4; }
+    __device__ static int reg_ch(const Params& p) { return (footprint(p) || p.mode == CN_HOURGLASS4) ? 5 : 4; }
 
     __device__ static void make_record(const Params& p, const float* g, float hi, float wi, int k, Rec& r) {
         const Corners c = pixel_corners(g, hi, wi);
@@ -457,8 +485,9 @@ struct CenterNetPolicy {
             r.flags = 0;
             return;
         }
-        if (p.mode == CN_POWER_FALLOFF) {  // tf_centernet.py:165-223
+        if (footprint(p)) {  // tf_centernet.py:165-223
             const float h_ratio = fdiv(hi, s), w_ratio = fdiv(wi, s);
+            r.gstd = fmaxf(1.0f, __fsqrt_rn(fmul(fmul(fmul(g[2], g[3]), h_ratio), w_ratio)));  // :203-205 (before the 8.0 override)
             const int hl = static_cast<int>(static_cast<double>(p.pad0) / p.stride);
             const int wl = static_cast<int>(static_cast<double>(p.pad1) / p.stride);
             const int clip_h = trunc_i(fdiv(hi, s)), clip_w = trunc_i(fdiv(wi, s));  // clip by img_dim (:222-223)
@@ -560,14 +589,14 @@ struct CenterNetPolicy {
 
     __device__ static bool tile_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
         if (!(r.flags & 4)) return false;
-        if (p.mode != CN_POWER_FALLOFF) return r.row >= ti.r0 && r.row < ti.r0 + ti.nrows;
+        if (!footprint(p)) return r.row >= ti.r0 && r.row < ti.r0 + ti.nrows;
         const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
         const int i1 = static_cast<int>(fdiv_u32(ti.r0 + ti.nrows - 1, md.div_width));
         return r.ry1 > i0 && r.ry0 <= i1;
     }
     __device__ static bool map_hit(const Params&, const Rec& r, int, int) { return (r.flags & 4) != 0; }
     __device__ static bool range_hit(const Params& p, const Rec& r, const TileInfo& ti, const MapDesc& md) {
-        if (p.mode != CN_POWER_FALLOFF) return r.row >= ti.r0 && r.row < ti.r0 + ti.nrows;
+        if (!footprint(p)) return r.row >= ti.r0 && r.row < ti.r0 + ti.nrows;
         const int i0 = static_cast<int>(fdiv_u32(ti.r0, md.div_width));
         const int last = ti.r0 + ti.nrows - 1;
         const int i1 = static_cast<int>(fdiv_u32(last, md.div_width));
@@ -577,13 +606,19 @@ struct CenterNetPolicy {
         return r.rx1 > j0 && r.rx0 <= j1;
     }
 
-    __device__ static void row_span(const Params& p, const Rec& r, const MapDesc& md, int, int, int& rlo, int& rhi) {
-        if (p.mode != CN_POWER_FALLOFF) {
-            rlo = rhi = r.row;
-            return;
+    __device__ static bool cell_bounds(const Params& p, const Rec& r, const MapDesc& md, int, int, int& ilo, int& ihi, int& jlo, int& jhi) {
+        if (!footprint(p)) {  // one row: its cell
+            const int cell = static_cast<int>(fdiv_u32(static_cast<uint32_t>(r.row), md.div_sub));
+            ilo = ihi = static_cast<int>(fdiv_u32(static_cast<uint32_t>(cell), md.div_width));
+            jlo = jhi = cell - ilo * md.width;
+            return r.row >= 0;
         }
-        rlo = r.ry0 * md.width + r.rx0;
-        rhi = (r.ry1 - 1) * md.width + r.rx1 - 1;
+        ilo = max(r.ry0, 0), ihi = min(r.ry1, md.height) - 1, jlo = max(r.rx0, 0), jhi = min(r.rx1, md.width) - 1;
+        return ilo <= ihi && jlo <= jhi;
+    }
+
+    __device__ static bool pair_hit(const Params& p, const Rec& r, const MapDesc&, int, int, int row, int, int) {
+        return footprint(p) || r.row == row;
     }
 
     // Scatter emission for the centre-cell modes: thread q owns candidate q, whose target is a single
@@ -608,6 +643,25 @@ struct CenterNetPolicy {
         }
     }
 
+    // gaussian_dist_2d of tf_centernet.py:30-40 on the footprint grid (cells at z + 0.5, integer mean): exp(-d^2 / (2 std^2))
+    // over the live axes, divided by its maximum over the footprint (reached 0.5 cells from the mean on every live axis);
+    // the centre cell is forced to 1 like the reference does for its fall-off (:261-262).  float64 like the reference's NumPy.
+    __device__ static float gauss_heat(const Rec& c, int i, int j) {
+        const bool live_y = c.flags & 1, live_x = c.flags & 2;
+        if ((i == c.muy && j == c.mux) || !(live_y || live_x)) return 1.0f;
+        double d2 = 0.0;
+        if (live_y) {
+            const double dy = (static_cast<double>(i) + 0.5) - static_cast<double>(c.muy);
+            d2 += dy * dy - 0.25;
+        }
+        if (live_x) {
+            const double dx = (static_cast<double>(j) + 0.5) - static_cast<double>(c.mux);
+            d2 += dx * dx - 0.25;
+        }
+        const double sd = static_cast<double>(c.gstd);
+        return static_cast<float>(exp(-d2 / (2.0 * sd * sd)));
+    }
+
     __device__ static double inv_pow8(double d) {  // 1/(d^8): tf_centernet.py:6-19 with spread forced to 8 (:207)
         const double d2 = dmul(d, d), d4 = dmul(d2, d2);
         return ddiv(1.0, dmul(d4, d4));
@@ -623,7 +677,7 @@ struct CenterNetPolicy {
                                     const Rec* recs, const unsigned short* cand, int ncand) {
         int best = -1, hits = 0;
         float best_area = 0.f;
-        if (p.mode != CN_POWER_FALLOFF) {
+        if (!footprint(p)) {
             for (int q = 0; q < ncand; ++q) {
                 const int k = cand[q];
                 const Rec& r = recs[k];
@@ -657,7 +711,16 @@ struct CenterNetPolicy {
         dst.reg(2, fmaxf(0.f, fsub(fj, r.r1)));
         dst.reg(3, live_x ? fmaxf(0.f, fsub(r.r3, fj)) : fmaxf(0.f, fsub(fsub(r.r3, static_cast<float>(j)), 0.5f)));
         float heat = 1.0f;
-        if (!(i == r.muy && j == r.mux) && (live_y || live_x)) {
+        if (p.mode == CN_GAUSSIAN) {
+            // canonical CenterNet splat: the heat of a cell is the MAXIMUM over the boxes whose footprint covers it of
+            // gaussian_dist_2d (the reference's commented-out code, tf_centernet.py:30-40) -- order-free, no atomics
+            heat = 0.f;
+            for (int q = 0; q < ncand; ++q) {
+                const Rec& c = recs[cand[q]];
+                if (i < c.ry0 || i >= c.ry1 || j < c.rx0 || j >= c.rx1) continue;
+                heat = fmaxf(heat, gauss_heat(c, i, j));
+            }
+        } else if (!(i == r.muy && j == r.mux) && (live_y || live_x)) {
             // max over the footprint is reached at the centre cell: 1/0.5^8 = 256 per live axis
             double v = 1.0;
             if (live_y) v = dmul(v, inv_pow8(static_cast<double>(fi) - static_cast<double>(r.muy)) * (1.0 / 256.0));

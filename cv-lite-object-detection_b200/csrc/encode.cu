@@ -1,7 +1,7 @@
 // C-ABI launchers for the target encoders (see include/densehead.h).
 #include <cstring>
 
-#include "dh_encode_kernel.cuh"
+#include "dh_encode_direct_kernel.cuh"
 #include "dh_host.h"
 #include "dh_launch.h"
 
@@ -39,8 +39,66 @@ int finish_table(TileTable& tt, int ch, int batch, int tile_bytes) {
     return ((rpt * ch * 4 + 16) + 127) & ~127;  // shared-memory bytes per stage
 }
 
+// Output bytes up to which DH_OPT_ENCODE_KERNEL = 0 picks the direct-store kernel (measured on B200)
+constexpr long long kDirectMaxBytes = 192ll << 20;
+
+static long long map_bytes(const TileTable& tt, int ch, int batch) {
+    long long bytes = 0;
+    for (int m = 0; m < tt.n_maps; ++m) bytes += static_cast<long long>(tt.maps[m].rows) * ch * 4;
+    return bytes * batch;
+}
+
+// The direct-store kernel (dh_encode_direct_kernel.cuh): one CTA per image-aligned chunk, cut statically.
+template <class P>
+static int launch_encode_direct(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, const char* who) {
+    const int ch = a.tt.ch, batch = a.tt.batch;
+    const long long bytes = map_bytes(a.tt, ch, batch);
+    // the unit ("tile") is ~4 KB of rows; a chunk is a run of tiles of one image sized so that the problem makes about
+    // 8 CTAs per SM, at least 8 KB and at most 128 KB each (small images: several whole images per chunk)
+    a.tile_buf_bytes = finish_table(a.tt, ch, batch, 4096);
+    const long long total = static_cast<long long>(batch) * a.tt.tiles_per_image;
+    if (total == 0) return DH_OK;
+    a.box_cap = ((a.max_boxes > 0 ? a.max_boxes : 1) + 31) & ~31;
+    const DirectSmemLayout lay = direct_smem_layout<P>(a.box_cap);
+    if (lay.total > 227 * 1024) return set_error(DH_ERR_CAPACITY, "%s: needs %d bytes of shared memory", who, lay.total);
+    DH_ONCE_PER_DEVICE(h) {
+        DH_CUDA(cudaFuncSetAttribute(encode_direct_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    int per_sm = 1;
+    DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_direct_kernel<P>, DH_THREADS, lay.total));
+    if (per_sm < 1) per_sm = 1;
+    // one wave of resident CTAs when the chunks then hold 8..128 KB each
+    long long want_bytes = bytes / (static_cast<long long>(h->sm_count) * per_sm) + 1;
+    const long long tile_b = static_cast<long long>(a.tt.rows_per_tile) * ch * 4;
+    long long want = (want_bytes + tile_b - 1) / tile_b;
+    if (want < 1) want = 1;
+    const int tpi = a.tt.tiles_per_image;
+    if (tpi <= want) {
+        a.chunks_per_image = 1;
+        a.images_per_chunk = static_cast<int>(want / tpi);
+        if (a.images_per_chunk < 1) a.images_per_chunk = 1;
+        a.chunk_tiles = a.images_per_chunk * tpi;
+        a.n_chunks = (batch + a.images_per_chunk - 1) / a.images_per_chunk;
+    } else {
+        const int n_sub = static_cast<int>((tpi + want - 1) / want);
+        a.chunk_tiles = (tpi + n_sub - 1) / n_sub;
+        a.chunks_per_image = (tpi + a.chunk_tiles - 1) / a.chunk_tiles;
+        a.images_per_chunk = 1;
+        a.n_chunks = static_cast<long long>(batch) * a.chunks_per_image;
+    }
+    a.sched = nullptr;
+    a.use_tma_store = 0;
+    a.phase_cycles = nullptr;
+    encode_direct_kernel<P><<<static_cast<unsigned>(a.n_chunks), DH_THREADS, lay.total, st>>>(a);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return DH_OK;
+}
+
 template <class P>
 static int launch_encode(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t st, const char* who) {
+    if (h->encode_kernel == 2 || (h->encode_kernel == 0 && map_bytes(a.tt, a.tt.ch, a.tt.batch) <= kDirectMaxBytes))
+        return launch_encode_direct<P>(h, a, st, who);
     const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
     if (total == 0) return DH_OK;
     a.box_cap = ((a.max_boxes > 0 ? a.max_boxes : 1) + 31) & ~31;
@@ -117,7 +175,7 @@ int fill_fcos(FcosPolicy::Params& p, TileTable& tt, int pad_h, int pad_w, int n_
     DH_FILL_CHECK(n_levels == 1 || b_dim, "%s: b_dim is NULL", who);
     DH_FILL_CHECK(pad_h > 0 && pad_w > 0, "%s: bad padded size", who);
     DH_FILL_CHECK(num_classes >= 1 && num_classes <= 4096, "%s: num_classes %d", who, num_classes);
-    DH_FILL_CHECK(mode >= 0 && mode <= 3, "%s: mode %d", who, mode);
+    DH_FILL_CHECK(mode >= 0 && mode <= 4, "%s: mode %d", who, mode);
     p.n_levels = n_levels, p.num_classes = num_classes, p.mode = mode, p.num_targets = num_targets;
     tt.n_maps = n_levels;
     for (int l = 0; l < n_levels; ++l) {
@@ -176,7 +234,7 @@ int fill_retina(RetinaPolicy::Params& p, TileTable& tt, int pad_h, int pad_w, in
 int fill_centernet(CenterNetPolicy::Params& p, TileTable& tt, int pad0, int pad1, int stride, int n_scales,
                    const float* box_scales, float sigma, int num_classes, int mode, float* out, const float* pred,
                    int32_t* status, const char* who) {
-    DH_FILL_CHECK(mode >= 0 && mode <= 3, "%s: mode %d", who, mode);
+    DH_FILL_CHECK(mode >= 0 && mode <= 4, "%s: mode %d", who, mode);
     DH_FILL_CHECK(mode != DH_CENTERNET_ONEHOT_SCALES || (box_scales && n_scales >= 1 && n_scales <= 8),
                   "%s: mode 0 needs 1..8 box_scales", who);
     DH_FILL_CHECK(pad0 > 0 && pad1 > 0 && stride > 0, "%s: bad sizes", who);
@@ -190,14 +248,14 @@ int fill_centernet(CenterNetPolicy::Params& p, TileTable& tt, int pad0, int pad1
     MapDesc& md = tt.maps[0];
     tt.n_maps = 1;
     int hh, ww;
-    if (mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_HOURGLASS4) {
+    if (mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_GAUSSIAN || mode == DH_CENTERNET_HOURGLASS4) {
         hh = static_cast<int>(static_cast<double>(pad0) / stride);
         ww = static_cast<int>(static_cast<double>(pad1) / stride);
     } else {  // the reference swaps the indices (tf_centernet_resnet_s8.py:259-260)
         hh = static_cast<int>(static_cast<double>(pad1) / stride);
         ww = static_cast<int>(static_cast<double>(pad0) / stride);
     }
-    const int ch = num_classes + ((mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4);
+    const int ch = num_classes + ((mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_GAUSSIAN || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4);
     md.out = out;
     md.pred = pred;
     md.height = hh, md.width = ww, md.sub = p.n_scales, md.level = 0, md.anchor = 0;
@@ -264,7 +322,7 @@ int dh_centernet_encode(dh_handle_t h, const float* boxes, const int32_t* nbox, 
     int rc = fill_centernet(a.pp, a.tt, pad0, pad1, stride, n_scales, box_scales, sigma, num_classes, mode, out, nullptr,
                             status, "dh_centernet_encode");
     if (rc) return rc;
-    const int ch = num_classes + ((mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4);
+    const int ch = num_classes + ((mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_GAUSSIAN || mode == DH_CENTERNET_HOURGLASS4) ? 5 : 4);
     a.tile_buf_bytes = finish_table(a.tt, ch, batch, auto_tile_bytes(a.tt, ch, batch, h->tile_bytes, h->sm_count));
     a.boxes = boxes, a.nbox = nbox, a.img_dim = img_dim, a.max_boxes = max_boxes;
     if (status) DH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));

@@ -12,7 +12,7 @@ const CommDev* comm_dev_if_fused(dh_handle_s* h);  // comm.cu
 static int check_spec(const LossSpec& s, const char* who) {
     if (!(s.reg_ch == 0 || s.reg_ch == 4)) return set_error(DH_ERR_BAD_ARG, "%s: reg_ch must be 0 or 4", who);
     if (s.cen_mode < 0 || s.cen_mode > 3) return set_error(DH_ERR_BAD_ARG, "%s: cen_mode %d", who, s.cen_mode);
-    if (s.reg_mode < 0 || s.reg_mode > 1) return set_error(DH_ERR_BAD_ARG, "%s: reg_mode %d", who, s.reg_mode);
+    if (s.reg_mode < 0 || s.reg_mode > 2) return set_error(DH_ERR_BAD_ARG, "%s: reg_mode %d", who, s.reg_mode);
     if (s.pos_rule < 0 || s.pos_rule > 2) return set_error(DH_ERR_BAD_ARG, "%s: pos_rule %d", who, s.pos_rule);
     if (s.cls_mode < 0 || s.cls_mode > 1) return set_error(DH_ERR_BAD_ARG, "%s: cls_mode %d", who, s.cls_mode);
     return DH_OK;
@@ -110,7 +110,7 @@ static void plan_tiers(LossArgs<P>& a, long long grid, int ct0, bool tail) {
     cts[n++] = ct0;
     if (tail && tpi > 0)
         for (int c = ct0 / 2; c >= 1 && n < kMaxChunkTiers; c /= 2) cts[n++] = c;
-    long long need[kMaxChunkTiers] = {0, 0, 0, 0}, need_total = 0;
+    long long need[kMaxChunkTiers] = {}, need_total = 0;
     for (int k = 1; k < n; ++k) {
         need[k] = (grid * cts[k - 1] / 2 + tpi - 1) / tpi;
         if (need[k] < 1) need[k] = 1;
@@ -161,10 +161,19 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kCls, kGrad>, DH_THREADS, lay.total));
     if (per_sm < 1) per_sm = 1;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
-    // measured on B200 (tools/fused_loss_probe.py): chunks of 4..8 tiles (1-2 K rows) balance best -- smaller chunks pay
-    // the chunk-end barrier too often, larger ones leave a tail
-    long long want = total / (grid * h->fused_chunks_per_cta);
-    want = want < 4 ? 4 : (want > 8 ? 8 : want);
+    // Chunk size.  Uniform chunks (DH_OPT_FUSED_TAIL = 0): aim at DH_OPT_FUSED_CHUNKS_PER_CTA chunks per CTA, 4..8 tiles each
+    // (smaller chunks pay the chunk-end barriers too often, larger ones leave a tail).  Tiered (default): the tail is
+    // taken care of by the finer tiers, so the first tier can be coarse -- about half of a CTA's share of the tiles,
+    // 4..16 tiles -- which matters for small batches, where a chunk's fixed cost (GT staging, barriers) is not hidden
+    // behind other CTAs' streaming.
+    long long want;
+    if (h->fused_tail) {
+        want = (total / grid) * 55 / 100;
+        want = want < 4 ? 4 : (want > h->fused_max_chunk ? h->fused_max_chunk : want);
+    } else {
+        want = total / (grid * h->fused_chunks_per_cta);
+        want = want < 4 ? 4 : (want > 8 ? 8 : want);
+    }
     plan_tiers(a, grid, static_cast<int>(want), h->fused_tail != 0);
     const long long n_chunks = a.n_chunks;
     if (grid > n_chunks) grid = n_chunks;
@@ -191,9 +200,7 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     }
     a.sched = next_sched_counter(h, st);
     if (!a.sched) return DH_ERR_CUDA;
-    a.img_cnt = image_counters(h, a.tt.batch);
-    if (!a.img_cnt) return DH_ERR_CUDA;
-    a.trace = (h->trace && h->trace_bytes >= (grid * 4 + 1) * 8) ? h->trace : nullptr;
+    a.trace = (h->trace && h->trace_bytes >= (grid * kTraceSlots + 1) * 8) ? h->trace : nullptr;
     fused_loss_kernel<P, kCls, kGrad><<<static_cast<unsigned>(grid), DH_THREADS, lay.total, st>>>(a);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -435,7 +442,7 @@ static int centernet_encode_loss_impl(const GradOut* go, dh_handle_t h, const fl
     int rc = fill_centernet(a.pp, a.tt, pad0, pad1, stride, n_scales, box_scales, sigma, num_classes, mode, nullptr,
                                pred, status, "dh_centernet_encode_loss");
     if (rc) return rc;
-    const bool falloff = mode == DH_CENTERNET_POWER_FALLOFF;
+    const bool falloff = mode == DH_CENTERNET_POWER_FALLOFF || mode == DH_CENTERNET_GAUSSIAN;  // the [H,W,C+5] footprint layouts
     a.spec.reg_ch = 4, a.spec.cen_mode = falloff ? 1 : 0, a.spec.reg_mode = falloff ? reg_mode : 0;
     a.spec.pos_rule = falloff ? 0 : 1;  // tf_centernet.py:435 (>= 1) vs tf_centernet_resnet_s8.py:376 (> 0)
     a.spec.cls_mode = cls_mode;

@@ -58,14 +58,30 @@ __device__ __forceinline__ unsigned long long nms_sort_key(const float* d, int r
     return k == 0ull ? 1ull : k;
 }
 
+// ---- slab masks: a conservative "can these two boxes overlap at all" test in three instructions -------------------
+// Each axis of an image's candidates is cut into 32 slabs over the candidates' own coordinate range; a box carries, per
+// axis, the bit mask of the slabs it touches.  The slab index is a monotone function of the coordinate, so two boxes that
+// overlap on an axis share a slab there: (mask_a & mask_c) == 0 on either axis proves an empty intersection.  Boxes
+// without a positive finite area get all-ones masks (they always take the exact predicate).
+__device__ __forceinline__ unsigned ordered_bits(float v) {  // monotone float -> uint
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_float(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+__device__ __forceinline__ unsigned slab_range_mask(float lo_v, float hi_v, float lo, float scale) {
+    const int s0 = min(max(__float2int_rd((lo_v - lo) * scale), 0), 31), s1 = min(max(__float2int_rd((hi_v - lo) * scale), 0), 31);
+    return (s1 >= 31 ? 0xffffffffu : ((1u << (s1 + 1)) - 1u)) & ~((1u << s0) - 1u);
+}
+
 __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __restrict__ dets, const int* __restrict__ n_valid,
                                                                 NmsParams p, int n_pow2, int force_bitonic, float4* __restrict__ sorted_boxes,
                                                                 int* __restrict__ sorted_cls, int* __restrict__ order,
-                                                                int* __restrict__ n_cand) {
+                                                                int* __restrict__ n_cand, uint2* __restrict__ sorted_slabs) {
     extern __shared__ unsigned long long keys[];  // [n_pow2]
     __shared__ unsigned bucket_start[kSortBuckets], bucket_fill[kSortBuckets];
     __shared__ unsigned warp_tot[kSortThreads / 32];
     __shared__ unsigned key_min, key_max, biggest;
+    __shared__ unsigned rng[4];  // ordered bits of {min, max} of axis 0 and of axis 1 over the valid candidates
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = n_valid ? min(n_valid[b], p.n_max) : p.n_max;
     const float* d = dets + static_cast<long long>(b) * p.n_max * p.row_floats;
@@ -75,19 +91,46 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
         sorted_boxes[static_cast<long long>(b) * p.n_max + pos] = make_float4(r[0], r[1], r[2], r[3]);
         sorted_cls[static_cast<long long>(b) * p.n_max + pos] = p.per_class ? __float2int_rz(r[5]) : 0;
         order[static_cast<long long>(b) * p.n_max + pos] = src;
+        if (sorted_slabs) {
+            const float a0 = fminf(r[0], r[2]), a1 = fmaxf(r[0], r[2]), b0 = fminf(r[1], r[3]), b1 = fmaxf(r[1], r[3]);
+            const float area = (a1 - a0) * (b1 - b0);
+            uint2 m = make_uint2(0xffffffffu, 0xffffffffu);
+            if (area > 0.f && area < 3.0e38f) {  // (a NaN fails both)
+                const float lo0 = ordered_float(rng[0]), hi0 = ordered_float(rng[1]), lo1 = ordered_float(rng[2]), hi1 = ordered_float(rng[3]);
+                const float sc0 = hi0 > lo0 ? 32.0f / (hi0 - lo0) : 0.f, sc1 = hi1 > lo1 ? 32.0f / (hi1 - lo1) : 0.f;
+                if (sc0 < 3.0e38f && sc1 < 3.0e38f) m = make_uint2(slab_range_mask(a0, a1, lo0, sc0), slab_range_mask(b0, b1, lo1, sc1));
+            }
+            sorted_slabs[static_cast<long long>(b) * p.n_max + pos] = m;
+        }
     };
     // span of the score keys
-    if (tid == 0) key_min = 0xFFFFFFFFu, key_max = 0u, biggest = 0u;
+    if (tid == 0) key_min = 0xFFFFFFFFu, key_max = 0u, biggest = 0u, rng[0] = rng[2] = 0xFFFFFFFFu, rng[1] = rng[3] = 0u;
     for (int i = tid; i < kSortBuckets; i += kSortThreads) bucket_fill[i] = 0u;
     __syncthreads();
     unsigned lo = 0xFFFFFFFFu, hi = 0u;
+    unsigned r0 = 0xFFFFFFFFu, r1 = 0u, r2 = 0xFFFFFFFFu, r3 = 0u;
     for (int i = tid; i < n; i += kSortThreads) {
         const unsigned long long k = nms_sort_key(d, p.row_floats, i, p.inclusive, p.min_score);
-        if (k) lo = min(lo, static_cast<unsigned>(k >> 32)), hi = max(hi, static_cast<unsigned>(k >> 32));
+        if (k) {
+            lo = min(lo, static_cast<unsigned>(k >> 32)), hi = max(hi, static_cast<unsigned>(k >> 32));
+            if (sorted_slabs) {
+                const float* r = d + static_cast<long long>(i) * p.row_floats;
+                const float c0 = r[0], c1 = r[1], c2 = r[2], c3 = r[3];
+                if (c0 == c0 && c1 == c1 && c2 == c2 && c3 == c3 && fabsf(c0) < 3.0e38f && fabsf(c1) < 3.0e38f && fabsf(c2) < 3.0e38f && fabsf(c3) < 3.0e38f) {
+                    r0 = min(r0, ordered_bits(fminf(c0, c2))), r1 = max(r1, ordered_bits(fmaxf(c0, c2)));
+                    r2 = min(r2, ordered_bits(fminf(c1, c3))), r3 = max(r3, ordered_bits(fmaxf(c1, c3)));
+                }
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)), hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     if (lane == 0 && lo <= hi) atomicMin(&key_min, lo), atomicMax(&key_max, hi);
+    if (sorted_slabs) {
+        r0 = __reduce_min_sync(0xffffffffu, r0), r1 = __reduce_max_sync(0xffffffffu, r1);
+        r2 = __reduce_min_sync(0xffffffffu, r2), r3 = __reduce_max_sync(0xffffffffu, r3);
+        if (lane == 0) atomicMin(&rng[0], r0), atomicMax(&rng[1], r1), atomicMin(&rng[2], r2), atomicMax(&rng[3], r3);
+    }
     __syncthreads();
     const unsigned kmin = key_min, span = key_max >= kmin ? key_max - kmin : 0u;
     const int shift = max(0, (32 - __clz(span)) - 12);  // (u - kmin) >> shift < 4096
@@ -204,45 +247,80 @@ __device__ __forceinline__ bool suppress_iou(const float4& a0, const float4& c0,
 }
 
 // ---- kernel 2 -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sorted_boxes, const int* __restrict__ sorted_cls,
-                                                      const int* __restrict__ n_cand, NmsParams p, int words,
-                                                      unsigned long long* __restrict__ mask) {
-    const int b = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+// One CTA takes the 64 boxes of column block cb against four row blocks (256 threads, one row each).  Nearly all of the
+// 400 M pairs of a 64 x 5 000-candidate batch do not overlap at all, so the exact predicate must not run for them: the
+// column block's slab masks are turned into "which of my 64 boxes touch slab s" words (64 ballots per axis), a row ORs
+// the words of the slabs it touches on each axis and ANDs the two -- the 64-bit set of columns that can overlap it, for
+// ~30 instructions -- and only those take the exact predicate (identical arithmetic, identical bits).  A pair that is
+// filtered out has two boxes of positive finite area and an empty intersection, for which both predicates answer
+// "not suppressed" whenever the threshold is not negative (a negative threshold switches the filter off).
+constexpr int kMaskRowBlocks = 4;
+__global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(const float4* __restrict__ sorted_boxes, const int* __restrict__ sorted_cls,
+                                                                       const uint2* __restrict__ sorted_slabs, const int* __restrict__ n_cand,
+                                                                       NmsParams p, int words, unsigned long long* __restrict__ mask) {
+    const int b = blockIdx.z, cb = blockIdx.x, rb = blockIdx.y * kMaskRowBlocks + (threadIdx.x >> 6);
     const int m = n_cand[b];
-    if (rb * 64 >= m || cb * 64 >= m || cb < rb) return;  // only later boxes (j > i) can be suppressed
+    if (cb * 64 >= m || blockIdx.y * kMaskRowBlocks > cb) return;  // only later boxes (j > i) can be suppressed
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
     __shared__ int ccls[64];
-    const int tid = threadIdx.x;
+    __shared__ unsigned slab_cols[2][32][2];  // [axis][slab][column half]: columns of the block that touch the slab
+    const int tid = threadIdx.x, t = tid & 63, lane = tid & 31;
     const long long base = static_cast<long long>(b) * p.n_max;
-    const int j = cb * 64 + tid;
-    if (j < m) {
-        const float4 c = sorted_boxes[base + j];
-        cbox[tid] = c, carea[tid] = box_area(c), ccls[tid] = sorted_cls[base + j];
+    const bool filter = sorted_slabs != nullptr && !(p.iou_thr < 0.f);
+    if (tid < 64) {
+        const int j = cb * 64 + t;
+        uint2 sm = make_uint2(0u, 0u);
+        if (j < m) {
+            const float4 c = sorted_boxes[base + j];
+            cbox[t] = c, carea[t] = box_area(c), ccls[t] = sorted_cls[base + j];
+            if (filter) sm = sorted_slabs[base + j];
+        }
+        if (filter) {
+#pragma unroll
+            for (int s = 0; s < 32; ++s) {
+                const unsigned b0 = __ballot_sync(0xffffffffu, (sm.x >> s) & 1u), b1 = __ballot_sync(0xffffffffu, (sm.y >> s) & 1u);
+                if (lane == 0) slab_cols[0][s][tid >> 5] = b0, slab_cols[1][s][tid >> 5] = b1;
+            }
+        }
     }
     __syncthreads();
-    const int i = rb * 64 + tid;
-    if (i >= m) return;
+    const int i = rb * 64 + t;
+    if (rb > cb || i >= m) return;
     const float4 a = sorted_boxes[base + i];
     const float area_a = box_area(a);
     const int ac = sorted_cls[base + i];
-    unsigned long long bits = 0ull;
     const int jn = min(64, m - cb * 64);
+    unsigned long long todo = jn >= 64 ? ~0ull : ((1ull << jn) - 1ull);
+    if (rb == cb) todo &= t >= 63 ? 0ull : (~0ull << (t + 1));
+    if (filter) {
+        const uint2 sm = sorted_slabs[base + i];
+        unsigned x0 = 0u, x1 = 0u, y0 = 0u, y1 = 0u;
+        for (unsigned r = sm.x; r; r &= r - 1) {
+            const int s = __ffs(r) - 1;
+            x0 |= slab_cols[0][s][0], x1 |= slab_cols[0][s][1];
+        }
+        for (unsigned r = sm.y; r; r &= r - 1) {
+            const int s = __ffs(r) - 1;
+            y0 |= slab_cols[1][s][0], y1 |= slab_cols[1][s][1];
+        }
+        todo &= (static_cast<unsigned long long>(x1 & y1) << 32) | (x0 & y0);
+    }
+    unsigned long long bits = 0ull;
     if (p.per_class) {
-        for (int t = (rb == cb) ? tid + 1 : 0; t < jn; ++t)
-            if (ccls[t] == ac && suppress_iou(a, cbox[t], p.iou_thr)) bits |= (1ull << t);
+        for (; todo; todo &= todo - 1) {
+            const int c = __ffsll(static_cast<long long>(todo)) - 1;
+            if (ccls[c] == ac && suppress_iou(a, cbox[c], p.iou_thr)) bits |= 1ull << c;
+        }
     } else {
-        unsigned lo = 0u, hi = 0u;  // two 32-bit halves: no 64-bit shifts in the loop
-        const int t0 = (rb == cb) ? tid + 1 : 0;
-        for (int t = t0; t < min(jn, 32); ++t)
-            if (suppress_agnostic(a, area_a, cbox[t], carea[t], p.iou_thr)) lo |= 1u << t;
-        for (int t = max(t0, 32); t < jn; ++t)
-            if (suppress_agnostic(a, area_a, cbox[t], carea[t], p.iou_thr)) hi |= 1u << (t - 32);
-        bits = (static_cast<unsigned long long>(hi) << 32) | lo;
+        for (; todo; todo &= todo - 1) {
+            const int c = __ffsll(static_cast<long long>(todo)) - 1;
+            if (suppress_agnostic(a, area_a, cbox[c], carea[c], p.iou_thr)) bits |= 1ull << c;
+        }
     }
     // block-major layout [image][row block][column block][row in block]: a row block's words right of the diagonal are
     // one contiguous range (a single bulk copy for the sweep) and this store is coalesced
-    mask[(((static_cast<long long>(b) * words + rb) * words + cb) << 6) + tid] = bits;
+    mask[(((static_cast<long long>(b) * words + rb) * words + cb) << 6) + t] = bits;
 }
 
 // ---- kernel 3 -----------------------------------------------------------------------------------------
@@ -255,7 +333,8 @@ constexpr int kSweepStageWords = 96;  // a row block's mask words are staged in 
 constexpr int kSweepDepth = 3;        // stage buffers: blocks w + 1 and w + 2 are in flight while block w is swept
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ sorted_cls,
                                                                   const int* __restrict__ order, const int* __restrict__ n_cand, NmsParams p,
-                                                                  int words, int staged, int* __restrict__ keep, int* __restrict__ n_keep) {
+                                                                  int words, int staged, int serial_chain, int* __restrict__ keep,
+                                                                  int* __restrict__ n_keep) {
     // dynamic shared memory: [kSweepDepth][words][64] staged mask words (when `staged`), then class_count (caps)
     extern __shared__ __align__(128) unsigned char sweep_smem[];
     __shared__ unsigned long long removed[kNmsMaxN / 64];
@@ -300,7 +379,39 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const unsigned
         const int my_order = tid < nb ? __ldg(order + base + first + tid) : 0;  // issued early: its latency hides behind the chain walk
         if (staged) mbar_wait(&bars[buf], static_cast<uint32_t>((w / kSweepDepth) & 1));  // requested two blocks ago
         const unsigned long long* src = staged ? stage + buf * buf_words : block_words(w);
-        if (tid == 0) {
+        if (tid < 32 && !caps && !serial_chain) {
+            // The greedy chain of the block, resolved in parallel rounds by one warp (lane l holds diagonal rows l and l + 32).
+            // K = kept for sure, U = undecided.  A box of U no box of K | U suppresses is kept; one a box of K suppresses is
+            // gone.  The lowest box of U has only decided boxes before it, so every round decides at least that one; with
+            // the few suppressions a 64-block holds, two or three rounds settle it (the serial walk takes 64 dependent steps).
+            const unsigned long long d_lo = src[lane], d_hi = src[lane + 32];
+            const unsigned long long valid = nb >= 64 ? ~0ull : ((1ull << nb) - 1ull);
+            unsigned long long K = 0ull, U = valid & ~removed[w];
+            while (U) {
+                const unsigned long long maybe = K | U;
+                const unsigned long long vm = (((maybe >> lane) & 1ull) ? d_lo : 0ull) | (((maybe >> (lane + 32)) & 1ull) ? d_hi : 0ull);
+                const unsigned long long vk = (((K >> lane) & 1ull) ? d_lo : 0ull) | (((K >> (lane + 32)) & 1ull) ? d_hi : 0ull);
+                const unsigned long long s_maybe = (static_cast<unsigned long long>(__reduce_or_sync(0xffffffffu, static_cast<unsigned>(vm >> 32))) << 32) |
+                                                   __reduce_or_sync(0xffffffffu, static_cast<unsigned>(vm));
+                const unsigned long long s_kept = (static_cast<unsigned long long>(__reduce_or_sync(0xffffffffu, static_cast<unsigned>(vk >> 32))) << 32) |
+                                                  __reduce_or_sync(0xffffffffu, static_cast<unsigned>(vk));
+                const unsigned long long new_k = U & ~s_maybe, new_r = U & s_kept;
+                K |= new_k;
+                U &= ~(new_k | new_r);
+            }
+            int kept = kept_before + __popcll(K);
+            bool live = true;
+            if (kept >= max_total) {  // the output is full inside this block: keep its first boxes only
+                int room = max_total - kept_before;
+                unsigned long long kk = 0ull;
+                for (unsigned long long r = K; r && room > 0; r &= r - 1, --room) kk |= r & (~r + 1ull);
+                K = kk, kept = max_total, live = false;
+            }
+            if (tid == 0) {
+                s_km = K, s_kept = kept;
+                if (!live) s_stop = 1;
+            }
+        } else if (tid == 0 && (caps || serial_chain)) {
             // one thread walks the greedy chain with the 64 diagonal words in registers: each step is a bit test and a
             // predicated OR, no memory access on the dependent path
             unsigned long long d[64];
@@ -489,32 +600,36 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     size_t off_cls = static_cast<size_t>(batch) * per_img * 16;
     size_t off_ord = off_cls + static_cast<size_t>(batch) * per_img * 4;
     size_t off_cnt = off_ord + static_cast<size_t>(batch) * per_img * 4;
-    size_t off_mask = (off_cnt + static_cast<size_t>(batch) * 4 + 255) & ~size_t(255);
-    size_t total = off_mask + static_cast<size_t>(batch) * words * words * 64 * 8;
+    size_t off_slab = (off_cnt + static_cast<size_t>(batch) * 4 + 255) & ~size_t(255);
+    size_t off_mask = (off_slab + static_cast<size_t>(batch) * per_img * 8 + 255) & ~size_t(255);
+    // a small output cap ends the sweep after a few blocks: suppression is evaluated lazily, one CTA per image, and the
+    // words^2 mask matrix (3 MB per image at 5 000 candidates) is never formed -- nor allocated
+    const int eff_total = max_total > 0 ? (max_total < max_out ? max_total : max_out) : max_out;
+    const bool lazy = eff_total <= kLazyMaxKept && (h->nms_kernel == 1 || (h->nms_kernel == 0 && eff_total <= 512));
+    size_t total = lazy ? off_mask : off_mask + static_cast<size_t>(batch) * words * words * 64 * 8;
     char* sc = static_cast<char*>(scratch(h, total));
     if (!sc) return DH_ERR_CUDA;
     float4* sboxes = reinterpret_cast<float4*>(sc);
     int* scls = reinterpret_cast<int*>(sc + off_cls);
     int* order = reinterpret_cast<int*>(sc + off_ord);
     int* ncand = reinterpret_cast<int*>(sc + off_cnt);
+    uint2* slabs = lazy ? nullptr : reinterpret_cast<uint2*>(sc + off_slab);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(sc + off_mask);
     DH_ONCE_PER_DEVICE(h) {
         DH_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsMaxN * 8));
     }
     nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, h->nms_sort == 1 ? 1 : 0, sboxes, scls, order,
-                                                                                    ncand);
+                                                                                    ncand, slabs);
     DH_CUDA(cudaGetLastError());
     const size_t cap_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
-    // a small output cap ends the sweep after a few blocks: evaluate suppression lazily, one CTA per image
-    const int eff_total = max_total > 0 ? (max_total < max_out ? max_total : max_out) : max_out;
-    if (eff_total <= kLazyMaxKept && (h->nms_kernel == 1 || (h->nms_kernel == 0 && eff_total <= 512))) {
+    if (lazy) {
         nms_lazy_kernel<<<batch, kLazyThreads, cap_smem, st>>>(sboxes, scls, order, ncand, p, keep, n_keep);
         DH_CUDA(cudaGetLastError());
         h->launches += 2;
         return DH_OK;
     }
-    dim3 grid(words, words, batch);
-    nms_mask_kernel<<<grid, 64, 0, st>>>(sboxes, scls, ncand, p, words, mask);
+    dim3 grid(words, (words + kMaskRowBlocks - 1) / kMaskRowBlocks, batch);
+    nms_mask_kernel<<<grid, 64 * kMaskRowBlocks, 0, st>>>(sboxes, scls, h->nms_filter ? slabs : nullptr, ncand, p, words, mask);
     DH_CUDA(cudaGetLastError());
     const int staged = words <= kSweepStageWords ? 1 : 0;
     const size_t stage_bytes = staged ? static_cast<size_t>(kSweepDepth) * 64 * words * 8 : 0;  // [depth][words][64] words
@@ -522,7 +637,7 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     DH_ONCE_PER_DEVICE(h) {
         DH_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    nms_sweep_kernel<<<batch, kSweepThreads, sweep_smem, st>>>(mask, scls, order, ncand, p, words, staged, keep, n_keep);
+    nms_sweep_kernel<<<batch, kSweepThreads, sweep_smem, st>>>(mask, scls, order, ncand, p, words, staged, h->nms_chain, keep, n_keep);
     DH_CUDA(cudaGetLastError());
     h->launches += 3;
     return DH_OK;

@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("DENSEHEAD_LIB", os.path.join(os.path.dirname(_HERE), 
 DH_OK = 0
 DH_ERR_BAD_ARG, DH_ERR_SHAPE, DH_ERR_CUDA, DH_ERR_CAPACITY, DH_ERR_NCCL = -1, -2, -3, -4, -5
 DH_OPT_TMA_STORE, DH_OPT_TILE_BYTES, DH_OPT_CTAS_PER_SM = 1, 2, 3
-DH_OPT_LOSS_ALLREDUCE, DH_OPT_ALLREDUCE, DH_OPT_FUSED_TAIL, DH_OPT_ENCODE_KERNEL = 11, 12, 13, 14
+DH_OPT_LOSS_ALLREDUCE, DH_OPT_ALLREDUCE, DH_OPT_FUSED_TAIL, DH_OPT_ENCODE_KERNEL, DH_OPT_FUSED_MAX_CHUNK = 11, 12, 13, 14, 15
+DH_OPT_NMS_FILTER, DH_OPT_NMS_CHAIN = 16, 17
 DH_STATUS_BAD_SCALE, DH_STATUS_BAD_CLASS, DH_STATUS_COMM_TIMEOUT = 1, 2, 4
 DH_UNIQUE_ID_BYTES, DH_IPC_HANDLE_BYTES = 128, 64
 DH_MAX_BOXES_PER_IMAGE = 256

@@ -7,14 +7,14 @@ from . import _capi, infer, losses
 from ._batch import image_dims, pack_labels, check_classes
 from ._tensors import as_host, current_device, stream_ptr, to_device, uses_stream
 
-MODES = {"s8": 0, "hourglass": 1, "falloff": 2, "hourglass4": 3}
+MODES = {"s8": 0, "hourglass": 1, "falloff": 2, "hourglass4": 3, "gaussian": 4}  # "gaussian": extension (DH_CENTERNET_GAUSSIAN)
 
 
 @uses_stream
 def format_data_batch(boxes, nbox, img_dim, num_classes, img_pad, stride=8, mode="s8", box_scales=None, sigma=0.25,
                       out=None, status=None, stream=None):
     """Encode a padded batch.  Output shape: s8 [B, H, W, S, C+4]; hourglass [B, H, W, C+4];
-    falloff [B, H, W, C+5]; hourglass4 [B, H, W, 4, C+5] (the inline encoder of train_hourglass_voc.py:99-153: `img_dim` is
+    falloff and gaussian (extension: DH_CENTERNET_GAUSSIAN) [B, H, W, C+5]; hourglass4 [B, H, W, 4, C+5] (the inline encoder of train_hourglass_voc.py:99-153: `img_dim` is
     the unpadded square side per image, `img_pad` the padded one).  `img_pad` is passed through with the reference's own
     indexing."""
     dev = current_device()
@@ -143,7 +143,7 @@ def model_loss(y_true, y_pred, reg_type="l1", cen_type="l1"):
         yp = yp.unsqueeze(0)
     b, h, w, ch = (int(v) for v in yp.shape)
     cen = losses.CEN_SMOOTH_L1 if cen_type.lower() == "l1" else losses.CEN_IGNORE
-    reg = losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1
+    reg = losses.reg_mode(reg_type)
     _, tot = losses.dense_loss([yt.contiguous()], [yp.contiguous()], [(h, w, 1)], b, ch, 4, cen, reg, losses.POS_GE1)
     return tot[0], tot[1], tot[2]
 
@@ -171,7 +171,7 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
             _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
             int(img_pad[0]), int(img_pad[1]), int(stride), len(scales), _capi.float_array(scales) if scales else None,
             float(sigma), int(num_classes), MODES[mode], yp.data_ptr(),
-            losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1,
+            losses.reg_mode(reg_type),
             losses.CLS_SIGMOID_BCE if cls_type == "sigmoid" else losses.CLS_FOCAL, float(alpha), float(gamma), float(delta),
             float(weights[0]), float(weights[1]), float(weights[2]), grad.data_ptr(), out_pi.data_ptr(), out_tot.data_ptr(),
             status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode_loss_grad")
@@ -180,7 +180,7 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
         _capi.handle(dev.index), boxes_d.data_ptr(), nbox_d.data_ptr(), dims_d.data_ptr(), batch, nmax,
         int(img_pad[0]), int(img_pad[1]), int(stride), len(scales), _capi.float_array(scales) if scales else None,
         float(sigma), int(num_classes), MODES[mode], yp.data_ptr(),
-        losses.REG_IOU if reg_type.lower() == "iou" else losses.REG_SMOOTH_L1,
+        losses.reg_mode(reg_type),
         losses.CLS_SIGMOID_BCE if cls_type == "sigmoid" else losses.CLS_FOCAL, float(alpha), float(gamma), float(delta),
         out_pi.data_ptr(), out_tot.data_ptr(), status.data_ptr(), stream_ptr(stream)), "dh_centernet_encode_loss")
     return out_pi, out_tot, status

@@ -16,7 +16,7 @@ from ._tensors import as_host, current_device, stream_ptr, to_device, uses_strea
 
 DEFAULT_STRIDES = [8, 16, 32, 64, 128]
 DEFAULT_B_DIM = [32, 64, 128, 256]
-MODES = {"fcos": 0, "center": 1, "center_only": 2, "center_v1": 3}
+MODES = {"fcos": 0, "center": 1, "center_only": 2, "center_v1": 3, "min_area": 4}  # "min_area": extension (DH_FCOS_MIN_AREA)
 
 
 def level_shapes(img_pad, strides):
@@ -115,7 +115,7 @@ def model_loss_batch(y_true, y_pred, reg_type="l1", cen_type="l1", alpha=0.25, g
     batch, ch = int(yp[0].shape[0]), int(yp[0].shape[-1])
     shapes = [(int(p.shape[1]), int(p.shape[2]), 1) for p in yp]
     cen = {"l1": losses.CEN_SMOOTH_L1, "focal": losses.CEN_FOCAL}.get(cen_type.lower(), losses.CEN_IGNORE)
-    reg = losses.REG_IOU if reg_type == "iou" else losses.REG_SMOOTH_L1
+    reg = losses.reg_mode(reg_type)
     return losses.dense_loss(yt, yp, shapes, batch, ch, 4, cen, reg, losses.POS_GE1, alpha, gamma, delta, stream=stream, weights=weights)
 
 
@@ -163,7 +163,7 @@ def encode_loss_batch(boxes, nbox, img_dim, num_classes, img_pad, y_pred, stride
     out_tot = torch.empty((4,), dtype=torch.float32, device=dev)
     cnt = torch.empty((batch, len(strides)), dtype=torch.int32, device=dev)
     cen = {"l1": losses.CEN_SMOOTH_L1, "focal": losses.CEN_FOCAL}.get(cen_type.lower(), losses.CEN_IGNORE)
-    reg = losses.REG_IOU if reg_type == "iou" else losses.REG_SMOOTH_L1
+    reg = losses.reg_mode(reg_type)
     if weights is not None:
         grads = [torch.empty_like(p) for p in yp]
         _capi.check(_capi.lib().dh_fcos_encode_loss_grad(

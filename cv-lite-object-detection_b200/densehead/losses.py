@@ -12,7 +12,12 @@ from . import _capi
 from ._tensors import current_device, stream_ptr, to_device, uses_stream
 
 CEN_NONE, CEN_SMOOTH_L1, CEN_FOCAL, CEN_IGNORE = 0, 1, 2, 3
-REG_SMOOTH_L1, REG_IOU = 0, 1
+REG_SMOOTH_L1, REG_IOU, REG_GIOU = 0, 1, 2
+
+
+def reg_mode(reg_type):
+    """`reg_type` of the reference's model_loss ("l1" / "iou", FCOS/fcos.py:464) plus the "giou" extension."""
+    return {"iou": REG_IOU, "giou": REG_GIOU}.get(str(reg_type).lower(), REG_SMOOTH_L1)
 POS_GE1, POS_GT0, POS_MASK = 0, 1, 2
 CLS_FOCAL, CLS_SIGMOID_BCE = 0, 1
 
@@ -111,7 +116,13 @@ def smooth_l1_loss(xy_true, xy_pred, mask=1.0, delta=1.0):
     return tot[1]
 
 
-def iou_loss(xy_true, xy_pred, mask):
+def giou_loss(xy_true, xy_pred, mask):
+    """EXTENSION (the reference has no GIoU loss): `sum((1 - GIoU) * mask)` on the box construction of `iou_loss`
+    (DH_REG_GIOU; its specification is giou_loss of the CPU oracle)."""
+    return iou_loss(xy_true, xy_pred, mask, _reg=REG_GIOU)
+
+
+def iou_loss(xy_true, xy_pred, mask, _reg=REG_IOU):
     """FCOS/fcos.py:393 -- `sum(-log(IoU + 1e-12) * mask)` for [H, W, 4] tblr maps on the integer grid.
     Rows whose mask is 0 contribute exactly 0 (the reference would propagate a NaN from them)."""
     dev = current_device()
@@ -121,6 +132,6 @@ def iou_loss(xy_true, xy_pred, mask):
     if t.dim() != 3 or t.shape[-1] != 4 or t.shape != p.shape or tuple(m.shape) != tuple(t.shape[:2]):
         raise ValueError("expected [H, W, 4] maps and an [H, W] mask")
     h, w = int(t.shape[0]), int(t.shape[1])
-    _, tot = dense_loss([t.reshape(-1)], [p.reshape(-1)], [(h, w, 1)], 1, 4, 4, CEN_NONE, REG_IOU, POS_MASK,
+    _, tot = dense_loss([t.reshape(-1)], [p.reshape(-1)], [(h, w, 1)], 1, 4, 4, CEN_NONE, _reg, POS_MASK,
                         masks=[m.reshape(-1).contiguous()], per_image=False)
     return tot[1]

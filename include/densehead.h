@@ -60,6 +60,9 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_ALLREDUCE 12 /* transport of dh_allreduce_loss. 0 (default): peer mailboxes when imported, else NCCL; 1: NCCL; 2: peer mailboxes */
 #define DH_OPT_FUSED_TAIL 13 /* fused loss scheduler: 1 (default) cuts the last images of a launch into finer chunks so that the tail is short; 0: uniform chunks */
 #define DH_OPT_ENCODE_KERNEL 14 /* target encoders. 0 (default): pick per problem -- direct-store kernel for small outputs, shared-memory tile streamer with TMA bulk stores for large ones; 1: always the tile streamer; 2: always the direct-store kernel */
+#define DH_OPT_FUSED_MAX_CHUNK 15 /* fused loss scheduler with the tiered tail: upper bound on the coarse tier's chunk in tiles of 256 rows (default 16; the coarse chunk is about half of a CTA's share of the work) */
+#define DH_OPT_NMS_FILTER 16 /* mask-matrix NMS: 1 (default) pairs that provably do not overlap (disjoint slab masks) skip the exact predicate; 0: every pair takes it (A/B checks; the bits are identical) */
+#define DH_OPT_NMS_CHAIN 17 /* block sweep of the mask-matrix NMS: 0 (default) the greedy chain of a 64-box block is resolved in parallel rounds when there are no per-class caps; 1: always the serial walk (A/B checks; identical keeps) */
 int dh_set_option(dh_handle_t h, int option, int value);
 /* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in
  * {stage GT + records, candidates + buffer recycle, emit rows, hand-off to TMA, drain}, out8[5] = tiles. */
@@ -74,8 +77,10 @@ int dh_read_phase_timing(dh_handle_t h, long long* out8 /*[host] [8]*/);
 #define DH_STATUS_COMM_TIMEOUT 4
 int dh_get_status(dh_handle_t h, int32_t* out /*[host] [1]*/, int reset);
 /* Profiling aid: while `buf` ([dev], `bytes` long; NULL switches it off) is set, every fused encode+loss launch whose
- * grid fits writes per CTA b: buf[4b+0] = start, buf[4b+1] = first chunk staged, buf[4b+2] = chunk loop done (globaltimer
- * nanoseconds), buf[4b+3] = chunks processed; buf[4*grid] = end of the in-kernel reduction. */
+ * grid fits writes 12 values per CTA b: buf[12b+0] = start, [1] = first chunk staged, [2] = chunk loop done (globaltimer
+ * nanoseconds), [3] = chunks processed, [4..9] = time thread 0 spent in {staging GT rows, marking candidate rows, the
+ * streaming pass, the barrier behind it, visiting marked rows, the chunk-end reduction}; buf[12*grid] = end of the
+ * in-kernel reduction. */
 int dh_set_trace(dh_handle_t h, long long* buf /*[dev]*/, long long bytes);
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 long long dh_launch_count(dh_handle_t h);
@@ -99,6 +104,7 @@ int dh_plan_fcos_select(const long long* values, int n_levels, int batch, signed
 #define DH_FCOS_CENTER3X3 1
 #define DH_FCOS_CENTER_ONLY 2
 #define DH_FCOS_CENTER_V1 3
+#define DH_FCOS_MIN_AREA 4 /* extension: mode 0 with the tie-break the FCOS paper and the reference's own comment (FCOS/fcos.py:185-188) ask for -- where footprints overlap the SMALLEST box supplies channels 0..4 (the reference's ascending-area paint order lets the largest win, :202-209); equal areas: the higher index.  Specified by oracle.fcos_format_data(order="min_area") */
 int dh_fcos_encode(dh_handle_t h,
                    const float* boxes /*[dev] [B,max_boxes,5]*/, const int32_t* nbox /*[dev] [B]*/,
                    const float* img_dim /*[dev] [B,2]*/,
@@ -137,6 +143,7 @@ int dh_retina_encode(dh_handle_t h,
 #define DH_CENTERNET_HOURGLASS 1
 #define DH_CENTERNET_POWER_FALLOFF 2
 #define DH_CENTERNET_HOURGLASS4 3
+#define DH_CENTERNET_GAUSSIAN 4 /* extension: mode 2 with a Gaussian heat channel -- the reference's commented-out gaussian_dist_2d (CenterNet/tf_centernet.py:30-40) with std = max(1, sqrt(box area in cells)) (:203-205, before its override to 8.0), normalised by its maximum over the footprint, centre cell 1; where footprints overlap the heat is the MAXIMUM over the boxes (canonical CenterNet splat, order-free), channels 0..3 and the classes as in mode 2.  Specified by oracle.centernet_gaussian_format_data */
 int dh_centernet_encode(dh_handle_t h,
                         const float* boxes, const int32_t* nbox, const float* img_dim,
                         int batch, int max_boxes, int pad0, int pad1, int stride,
@@ -184,6 +191,8 @@ int dh_format_detections(dh_handle_t h, const float* rows /*[dev] [B,n,6]*/, con
  *             DH_CEN_IGNORE    channel present, contributes 0 (fcos.py model_loss with cen_type != "l1")
  *   reg_mode  DH_REG_SMOOTH_L1 where(|d| < delta, d^2/2, |d|) over positive rows (FCOS/fcos.py:380-391)
  *             DH_REG_IOU       -log(IoU + 1e-12) on the integer grid over positive rows (FCOS/fcos.py:393-441)
+ *             DH_REG_GIOU      1 - GIoU on the same box construction (extension: the reference has no GIoU, SURVEY.md
+ *                              section 0; oracle.giou_loss states it), GIoU = IoU - (C - union) / (C + 1e-12)
  *   cls_mode  DH_CLS_FOCAL (alpha, gamma) or DH_CLS_SIGMOID_BCE (CenterNet/tf_hourglass_net.py:347-349, :381-382)
  *   pos_rule  DH_POS_GE1 max(class) >= 1 (fcos.py:475-477), DH_POS_GT0 max(class) > 0
  *             (retinanet_module.py:416-418), DH_POS_MASK caller-supplied per-row float mask.
@@ -197,6 +206,7 @@ int dh_format_detections(dh_handle_t h, const float* rows /*[dev] [B,n,6]*/, con
 #define DH_CEN_IGNORE 3
 #define DH_REG_SMOOTH_L1 0
 #define DH_REG_IOU 1
+#define DH_REG_GIOU 2
 #define DH_POS_GE1 0
 #define DH_POS_GT0 1
 #define DH_POS_MASK 2

@@ -73,9 +73,14 @@ def _ratio64(a, b):
 # --------------------------------------------------------------------------------------
 # a1  FCOS/fcos.py:136-378
 # --------------------------------------------------------------------------------------
-def fcos_format_data(gt_labels, img_dim, num_classes, img_pad=None, strides=None, b_dim=None):
+def fcos_format_data(gt_labels, img_dim, num_classes, img_pad=None, strides=None, b_dim=None, order="reference"):
     """Per-level FCOS targets `[Hl, Wl, C+5]` (t, b, l, r, centerness, multi-hot classes)
     and the per-level GT counts.  Follows FCOS/fcos.py:136-378 (Appendix A.1 of SURVEY.md).
+
+    `order="min_area"` is an EXTENSION and the specification of DH_FCOS_MIN_AREA: the reference paints the boxes of a level
+    in ASCENDING area order, so where footprints overlap the largest box supplies channels 0..4 (:202-209) although its
+    own comment (:185-188) -- and the FCOS paper -- want the smallest; this mode paints in DESCENDING area order (stable:
+    of two equal areas the higher index is painted later), everything else unchanged.
     """
     strides = list(DEFAULT_STRIDES if strides is None else strides)
     b_dim = list(DEFAULT_B_DIM if b_dim is None else b_dim)
@@ -92,7 +97,10 @@ def fcos_format_data(gt_labels, img_dim, num_classes, img_pad=None, strides=None
         idx = np.nonzero(lvl == n)[0]
         counts.append(int(idx.size))
         if idx.size:
-            idx = idx[np.argsort(area[idx], kind="stable")]     # ascending: largest painted last
+            if order == "min_area":
+                idx = idx[np.argsort(-area[idx], kind="stable")]    # descending: smallest painted last (extension)
+            else:
+                idx = idx[np.argsort(area[idx], kind="stable")]     # ascending: largest painted last
         sf = F(s)
         h_ratio, w_ratio = hi / sf, wi / sf                     # :162-163
         for k in idx:
@@ -382,9 +390,21 @@ def _falloff64(coords, mu, spread=8.0):
     return 1.0 / np.power(np.asarray(coords, dtype=np.float64) - float(mu), spread)
 
 
-def centernet_format_data(gt_labels, img_dim, num_classes, img_pad=None, stride=8, sigma=0.25):
+def centernet_gaussian_format_data(gt_labels, img_dim, num_classes, img_pad=None, stride=8, sigma=0.25):
+    """EXTENSION and the specification of DH_CENTERNET_GAUSSIAN (BASELINE's north_star asks for "Gaussian heatmap
+    rendering"; the reference renders none).  `centernet_format_data` with channel 4 rendered by the
+    reference's commented-out `gaussian_dist_2d` (CenterNet/tf_centernet.py:30-40): exp(-d^2 / (2 std^2)) per live axis on
+    the footprint grid (cells at z + 0.5, integer mean), divided by its maximum over the footprint, with
+    std = max(1, sqrt(h * w * h_ratio * w_ratio)) as :203-205 compute it before the override to 8.0 (float32), the
+    exponent in float64, the centre cell forced to 1 (:261-262).  Where footprints overlap the heat is the MAXIMUM over
+    the boxes (the canonical CenterNet splat -- order-free); channels 0..3 and the classes as in `centernet_format_data`."""
+    return centernet_format_data(gt_labels, img_dim, num_classes, img_pad, stride, sigma, heat="gaussian")
+
+
+def centernet_format_data(gt_labels, img_dim, num_classes, img_pad=None, stride=8, sigma=0.25, heat="falloff"):
     """Single-level `[H, W, C+5]` map: sigma-shrunk footprint, tblr of the full box, inverse-power
     fall-off heat (`tmp_std` forced to 8.0) -- CenterNet/tf_centernet.py:152-342."""
+    heat_mode = heat
     g = _labels(gt_labels)
     hi, wi = F(img_dim[0]), F(img_dim[1])
     pad = (img_dim[0], img_dim[1]) if img_pad is None else img_pad
@@ -433,6 +453,19 @@ def centernet_format_data(gt_labels, img_dim, num_classes, img_pad=None, stride=
         out[ys, xs, 1] = np.broadcast_to(b[:, None], (ny, nx))
         out[ys, xs, 2] = np.broadcast_to(l[None, :], (ny, nx))
         out[ys, xs, 3] = np.broadcast_to(r[None, :], (ny, nx))
+        if heat_mode == "gaussian":
+            std = np.maximum(F(1), np.sqrt(((row[2] * row[3]) * h_ratio) * w_ratio, dtype=np.float32))   # :203-205
+            d2 = np.zeros((ny, nx), dtype=np.float64)
+            if live_y:
+                d2 = d2 + ((gy.astype(np.float64) - mu_y) ** 2 - 0.25)[:, None]
+            if live_x:
+                d2 = d2 + ((gx.astype(np.float64) - mu_x) ** 2 - 0.25)[None, :]
+            heat = np.exp(-d2 / (2.0 * float(std) * float(std)))
+            if 0 <= mu_y - ys.start < ny and 0 <= mu_x - xs.start < nx:
+                heat[mu_y - ys.start, mu_x - xs.start] = 1.0
+            out[ys, xs, 4] = np.maximum(out[ys, xs, 4], heat.astype(np.float32))
+            out[ys, xs, 5 + int(row[4])] = 1.0
+            continue
         if live_y or live_x:
             heat = fy[:, None] * fx[None, :]
             heat = heat / heat.max()                                                    # :9, :18
@@ -491,6 +524,28 @@ def iou_loss(xy_true, xy_pred, mask):
         return F(np.sum(F(-1) * np.log(iou + F(1e-12)) * m, dtype=np.float32))
 
 
+def giou_loss(xy_true, xy_pred, mask):
+    """EXTENSION -- the reference has no GIoU loss (BASELINE's north_star names "IoU/GIoU losses").
+    `sum((1 - GIoU) * mask)` on exactly the box construction of `iou_loss` (FCOS/fcos.py:393-441: tblr distances around
+    the integer grid point, `iou = inter / (union + 1e-12)`), with GIoU = IoU - (C - union) / (C + 1e-12), C the area of
+    the smallest box enclosing both (Rezatofighi et al. 2019).  float32 in the written order; this function IS the
+    specification of DH_REG_GIOU."""
+    yt, yp, m = _f32(xy_true), _f32(xy_pred), _f32(mask)
+    hh, ww = yp.shape[0], yp.shape[1]
+    gx, gy = np.meshgrid(np.arange(ww, dtype=np.float32), np.arange(hh, dtype=np.float32))
+    tb = (gy - yt[..., 0], gx - yt[..., 2], gy + yt[..., 1], gx + yt[..., 3])
+    pb = (gy - yp[..., 0], gx - yp[..., 2], gy + yp[..., 1], gx + yp[..., 3])
+    ih = np.maximum(F(0), np.minimum(tb[2], pb[2]) - np.maximum(tb[0], pb[0]))
+    iw = np.maximum(F(0), np.minimum(tb[3], pb[3]) - np.maximum(tb[1], pb[1]))
+    inter = iw * ih
+    union = ((tb[2] - tb[0]) * (tb[3] - tb[1]) + (pb[2] - pb[0]) * (pb[3] - pb[1])) - inter
+    ac = (np.maximum(tb[2], pb[2]) - np.minimum(tb[0], pb[0])) * (np.maximum(tb[3], pb[3]) - np.minimum(tb[1], pb[1]))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        giou = inter / (union + F(1e-12)) - (ac - union) / (ac + F(1e-12))
+        per = np.where(m != 0, (F(1) - giou) * m, F(0))
+        return F(np.sum(per, dtype=np.float32))
+
+
 def fcos_model_loss(y_true, y_pred, reg_type="l1", cen_type="l1", pos_rule="ge1"):
     """(cls, reg, cen) summed over levels -- FCOS/fcos.py:464-496; `cen_type="focal"` is the
     fcos_center / fcos_center_v1 variant (fcos_center.py:365-399, fcos_center_v1.py:294-317).
@@ -507,6 +562,8 @@ def fcos_model_loss(y_true, y_pred, reg_type="l1", cen_type="l1", pos_rule="ge1"
             cen = cen + focal_loss(yt[..., 4], yp[..., 4])
         if reg_type == "iou":
             reg = reg + iou_loss(yt[..., :4], yp[..., :4], mask)
+        elif reg_type == "giou":  # extension
+            reg = reg + giou_loss(yt[..., :4], yp[..., :4], mask)
         else:
             reg = reg + smooth_l1_loss(yt[..., :4], yp[..., :4], mask=mask)
     return F(cls), F(reg), F(cen)
@@ -679,7 +736,11 @@ def dense_loss_f64(target, pred, reg_ch=4, cen_mode=0, reg_mode=0, pos_rule="gt0
             inter = iw * ih
             union = (tb[2] - tb[0]) * (tb[3] - tb[1]) + (pb[2] - pb[0]) * (pb[3] - pb[1]) - inter
             with np.errstate(divide="ignore", invalid="ignore"):
-                per = -np.log(inter / (union + 1e-12) + 1e-12)
+                if reg_mode == 2:  # 1 - GIoU (extension, see giou_loss)
+                    ac = (np.maximum(tb[2], pb[2]) - np.minimum(tb[0], pb[0])) * (np.maximum(tb[3], pb[3]) - np.minimum(tb[1], pb[1]))
+                    per = 1.0 - (inter / (union + 1e-12) - (ac - union) / (ac + 1e-12))
+                else:
+                    per = -np.log(inter / (union + 1e-12) + 1e-12)
             reg = np.sum(np.where(m > 0, per, 0.0) * m)
     cen = 0.0
     if cen_mode == 1:
@@ -737,8 +798,19 @@ def dense_loss_grad(target, pred, weights=(1.0, 1.0, 1.0), reg_ch=4, cen_mode=0,
                 di = [iw * (ih_raw > 0) * (py0 > ty0), iw * (ih_raw > 0) * (py1 < ty1),
                       ih * (iw_raw > 0) * (px0 > tx0), ih * (iw_raw > 0) * (px1 < tx1)]
                 da = [pw, pw, ph, ph]
+                if reg_mode == 2:  # 1 - GIoU: the enclosing box moves with the prediction where the prediction is the outer edge
+                    eh, ew = np.maximum(ty1, py1) - np.minimum(ty0, py0), np.maximum(tx1, px1) - np.minimum(tx0, px0)
+                    ac = eh * ew
+                    dc = ac + 1e-12
+                    uni = den - 1e-12
+                    de = [ew * (py0 < ty0), ew * (py1 > ty1), eh * (px0 < tx0), eh * (px1 > tx1)]
                 for q in range(4):
-                    gq = k * (di[q] * den - inter * (da[q] - di[q])) / (den * den)
+                    d_uni = da[q] - di[q]
+                    d_iou = (di[q] * den - inter * d_uni) / (den * den)
+                    if reg_mode == 2:
+                        gq = -(d_iou - ((de[q] - d_uni) * dc - (ac - uni) * de[q]) / (dc * dc))
+                    else:
+                        gq = k * d_iou
                     g[..., q] = w_reg * np.where(m > 0, gq, 0.0) * m
     if cen_mode == 1:
         sc = 1.0 / (1.0 + np.exp(-p[..., reg_ch]))

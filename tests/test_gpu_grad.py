@@ -115,3 +115,65 @@ def test_autograd_wrapper_and_grad_only_call():
     assert abs(lv - float((tot[:3].cpu() * torch.tensor(W)).sum())) <= 1e-5 * abs(lv)
     for p, g in zip(pred, grads):
         assert torch.allclose(p.grad, 0.5 * g)
+
+
+# ---- against the gradients pinned by the reference itself (tests/golden/grad.npz: central differences through the
+#      reference's own model_loss / train_loss in float64, oracle/make_golden.py: grad) ----------------------------------
+import os  # noqa: E402
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grad.npz"))
+W_GOLD = tuple(float(v) for v in GOLD["weights"])
+
+
+def _fd_close(got, want, what):
+    err = np.abs(np.asarray(got, np.float64) - want)
+    assert np.all(err <= 2e-5 * np.maximum(1.0, np.abs(want))), "%s: max err %g (want %g)" % (what, err.max(), want[err.argmax()])
+
+
+@pytest.mark.parametrize("name,mode,reg,cen", [("fcos_l1", "fcos", "l1", "l1"), ("fcos_iou", "fcos", "iou", "l1"),
+                                               ("center_focal", "center", "l1", "focal"), ("center_l1", "center", "l1", "l1"),
+                                               ("v1", "center_v1", "l1", "focal")])
+def test_fcos_gradients_against_the_reference_pinned_golden(name, mode, reg, cen):
+    dh = _dh()
+    g, seed = GOLD["fcos_g"], int(GOLD["fcos_seed"])
+    pred = synth.fcos_predictions(1, 256, 20, seed)
+    for p in pred:
+        p[..., :4] = np.abs(p[..., :4]) + np.float32(0.3)
+    boxes = np.zeros((1, (len(g) + 3) & ~3, 5), np.float32)
+    boxes[0, :len(g)] = g
+    nbox = np.array([len(g)], np.int32)
+    _, _, _, grads = dh.fcos.encode_loss_batch(boxes, nbox, [256, 256], 20, [256, 256], pred, mode=mode, reg_type=reg, cen_type=cen,
+                                              weights=W_GOLD)
+    tg, _ = dh.fcos.format_data_batch(boxes, nbox, [256, 256], 20, [256, 256], mode=mode)
+    _, _, ugrads = dh.fcos.model_loss_batch(tg, pred, reg, cen, weights=W_GOLD)
+    for l in range(5):
+        idx, want = GOLD["%s_idx%d" % (name, l)], GOLD["%s_fd%d" % (name, l)]
+        _fd_close(grads[l].cpu().numpy().reshape(-1)[idx], want, "fused %s level %d" % (name, l))
+        _fd_close(ugrads[l].cpu().numpy().reshape(-1)[idx], want, "unfused %s level %d" % (name, l))
+
+
+def test_retina_gradients_against_the_reference_pinned_golden():
+    dh = _dh()
+    g, seed = GOLD["retina_g"], int(GOLD["retina_seed"])
+    pred = synth.retina_predictions(1, 128, 20, seed)
+    boxes = np.zeros((1, (len(g) + 3) & ~3, 5), np.float32)
+    boxes[0, :len(g)] = g
+    nbox = np.array([len(g)], np.int32)
+    _, _, _, grads = dh.retinanet.encode_loss_batch(boxes, nbox, [128, 128], 20, [128, 128], pred, weights=(W_GOLD[0], W_GOLD[1]))
+    for l in range(5):
+        _fd_close(grads[l].cpu().numpy().reshape(-1)[GOLD["retina_idx%d" % l]], GOLD["retina_fd%d" % l], "retina level %d" % l)
+
+
+@pytest.mark.parametrize("name,mode", [("cn_s8", "s8"), ("cn_hg", "hourglass")])
+def test_centernet_gradients_against_the_reference_pinned_golden(name, mode):
+    dh = _dh()
+    boxes, nbox, seed = GOLD["cn_boxes"], GOLD["cn_nbox"], int(GOLD["cn_seed"])
+    yp = synth.centernet_s8_predictions(2, 256, 8, 5, 3, seed)
+    kw = dict(stride=8, mode="s8", box_scales=SCALES)
+    if mode == "hourglass":
+        yp = np.ascontiguousarray(yp[:, :, :, 0, :])
+        kw = dict(stride=8, mode="hourglass")
+    b4 = np.zeros((2, (boxes.shape[1] + 3) & ~3, 5), np.float32)
+    b4[:, :boxes.shape[1]] = boxes
+    _, _, _, grad = dh.centernet.encode_loss_batch(b4, nbox, [256, 256], 3, [256, 256], yp, weights=W_GOLD, **kw)
+    _fd_close(grad.cpu().numpy().reshape(-1)[GOLD[name + "_idx"]], GOLD[name + "_fd"], name)

@@ -124,3 +124,63 @@ def test_centernet_gradients_match_differences_through_the_reference(name):
         yp = np.ascontiguousarray(yp[:, :, :, 0, :])
     grad = O.dense_loss_grad(yt, yp, weights=W_GOLD, reg_ch=4, cen_mode=0, pos_rule="gt0")
     _fd_close(grad.reshape(-1)[GOLD[name + "_idx"]], GOLD[name + "_fd"], name)
+
+
+# ---- a second, independent check: torch autograd over a torch restatement of the reference's loss formulas -----------
+def _torch_losses(t, p, reg_ch, cen_mode, reg_mode, pos_rule, alpha=0.25, gamma=2.0, delta=1.0):
+    """FCOS/fcos.py:380-462 written with torch ops in float64 (focal in the reference's stable form, smooth-L1 without
+    the -delta/2 term, -log IoU on the integer grid); returns (cls, reg, cen)."""
+    import torch
+    cls0 = reg_ch + (1 if cen_mode else 0)
+
+    def focal(y, x):
+        s = torch.sigmoid(x)
+        ce = torch.log1p(torch.exp(-x.abs()))
+        return (y * alpha * ce * (1 - s) ** gamma + s ** gamma * (1 - y) * (1 - alpha) * ce
+                + (1 - y) * (1 - alpha) * torch.clamp(x, min=0) * s ** gamma - y * alpha * torch.clamp(x, max=0) * (1 - s) ** gamma).sum()
+
+    def sl1(a, b, m):
+        d = (a - b).abs()
+        return (torch.where(d < delta, 0.5 * d * d, d) * m).sum()
+    obj = t[..., cls0:].max(dim=-1).values
+    m = (obj >= 1).double() if pos_rule == "ge1" else (obj > 0).double()
+    cls = focal(t[..., cls0:], p[..., cls0:])
+    reg = torch.zeros((), dtype=torch.float64)
+    if reg_ch:
+        if reg_mode == 0:
+            reg = sl1(t[..., :4], p[..., :4], m[..., None])
+        else:
+            hh, ww = p.shape[-3], p.shape[-2]
+            gy, gx = torch.meshgrid(torch.arange(hh, dtype=torch.float64), torch.arange(ww, dtype=torch.float64), indexing="ij")
+            tb = (gy - t[..., 0], gx - t[..., 2], gy + t[..., 1], gx + t[..., 3])
+            pb = (gy - p[..., 0], gx - p[..., 2], gy + p[..., 1], gx + p[..., 3])
+            ih = torch.clamp(torch.minimum(tb[2], pb[2]) - torch.maximum(tb[0], pb[0]), min=0)
+            iw = torch.clamp(torch.minimum(tb[3], pb[3]) - torch.maximum(tb[1], pb[1]), min=0)
+            inter = ih * iw
+            union = (tb[2] - tb[0]) * (tb[3] - tb[1]) + (pb[2] - pb[0]) * (pb[3] - pb[1]) - inter
+            reg = (-torch.log(inter / (union + 1e-12) + 1e-12) * m).sum()
+    cen = torch.zeros((), dtype=torch.float64)
+    if cen_mode == 1:
+        cen = sl1(t[..., reg_ch], torch.sigmoid(p[..., reg_ch]), 1.0)
+    elif cen_mode == 2:
+        cen = focal(t[..., reg_ch], p[..., reg_ch])
+    return cls, reg, cen
+
+
+@pytest.mark.parametrize("cfg", [dict(ch=9, reg_ch=4, cen_mode=1, reg_mode=0, pos_rule="ge1"),
+                                 dict(ch=9, reg_ch=4, cen_mode=2, reg_mode=0, pos_rule="ge1"),
+                                 dict(ch=9, reg_ch=4, cen_mode=1, reg_mode=1, pos_rule="ge1"),
+                                 dict(ch=8, reg_ch=4, cen_mode=0, reg_mode=0, pos_rule="gt0")])
+def test_analytic_gradient_matches_torch_autograd(cfg):
+    torch = pytest.importorskip("torch")
+    t, p = _case(31 + cfg["ch"], cfg["ch"], cfg["reg_ch"], cfg["cen_mode"], hw=(9, 11))
+    w = (1.3, 0.7, 2.1)
+    tt, pp = torch.from_numpy(t), torch.from_numpy(p).requires_grad_(True)
+    kw = {k: v for k, v in cfg.items() if k != "ch"}
+    c, r, e = _torch_losses(tt, pp, **kw)
+    (w[0] * c + w[1] * r + w[2] * e).backward()
+    g = O.dense_loss_grad(t, p, weights=w, **kw)
+    want = pp.grad.numpy()
+    assert np.all(np.abs(g - want) <= 1e-9 * np.maximum(1.0, np.abs(want)))
+    # and the restated loss values are the oracle's float64 loss
+    assert np.allclose([float(c.detach()), float(r.detach()), float(e.detach())], O.dense_loss_f64(t, p, **kw), rtol=1e-12)

@@ -69,17 +69,17 @@ def main():
         for dist in ("prior", "wide", "trained"):
             pred = make_pred(B, dist)
             nbytes = sum(p.numel() for p in pred) * 4
-            cases = [("tail=1", 1, 12, nd), ("tail=0", 0, 12, nd)]
+            cases = [("tail=1", 1, 16, nd), ("tail=0", 0, 16, nd)]
             if dist == "prior":
-                cases += [("tail=1 cpc=6", 1, 6, nd), ("tail=1 cpc=24", 1, 24, nd), ("tail=1 no boxes", 1, 12, zero)]
-            for tag, tail, cpc, n in cases:
+                cases += [("tail=1 max=8", 1, 8, nd), ("tail=1 max=12", 1, 12, nd), ("tail=1 no boxes", 1, 16, zero)]
+            for tag, tail, mx, n in cases:
                 dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
-                dh.set_option(0, 8, cpc)
+                dh.set_option(0, _capi.DH_OPT_FUSED_MAX_CHUNK, mx)
                 t = graph_time(lambda: dh.retinanet.encode_loss_batch(bd, n, dims, 80, [640, 640], pred))
                 print(json.dumps({"B": B, "logits": dist, "case": tag, "us": round(t * 1e6, 1), "GBps": round(nbytes / t / 1e9, 1),
                                   "frac": round(nbytes / t / 1e9 / PEAK, 3), "ideal_us": round(nbytes / PEAK / 1e3, 1)}), flush=True)
             dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, 1)
-            dh.set_option(0, 8, 12)
+            dh.set_option(0, _capi.DH_OPT_FUSED_MAX_CHUNK, 16)
             del pred
             torch.cuda.empty_cache()
 

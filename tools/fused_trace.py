@@ -18,7 +18,7 @@ from oracle import synth  # noqa: E402
 
 def main():
     batches = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "16,32,64,256").split(",")]
-    buf = torch.zeros(4 * 2048 + 8, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(12 * 2048 + 8, dtype=torch.int64, device="cuda")
     h = _capi.handle(0)
     for B in batches:
         boxes, nbox = synth.config_boxes("retina_coco", B, 3)
@@ -46,11 +46,12 @@ def main():
             torch.cuda.synchronize()
             _capi.check(_capi.lib().dh_set_trace(h, None, 0), "dh_set_trace")
             t = buf.cpu().numpy()
-            grid = int(np.count_nonzero(t[0:4 * 2048:4])) - 1  # (the stamp of the in-kernel reduction sits right behind the last CTA row)
-            rows = t[:4 * grid].reshape(grid, 4)
+            grid = int(np.count_nonzero(t[0:12 * 2048:12])) - 1  # (the stamp of the in-kernel reduction sits right behind the last CTA row)
+            rows = t[:12 * grid].reshape(grid, 12)
             t0 = rows[:, 0].min()
             start, ready, end, chunks = rows[:, 0] - t0, rows[:, 1] - t0, rows[:, 2] - t0, rows[:, 3]
-            fin = t[4 * grid] - t0
+            fin = t[12 * grid] - t0
+            phases = rows[:, 4:10].mean(axis=0) / 1e3
             q = lambda v, p_: float(np.percentile(v, p_)) / 1e3  # noqa: E731
             print(json.dumps({
                 "B": B, "case": tag, "grid": grid, "event_us": round(e0.elapsed_time(e1) * 1e3, 1),
@@ -58,7 +59,8 @@ def main():
                 "prologue_us p50/max": [round(q(ready - start, 50), 1), round(q(ready - start, 100), 1)],
                 "end_us p1/p10/p50/p90/max": [round(q(end, x), 1) for x in (1, 10, 50, 90, 100)],
                 "finalize_done_us": round(float(fin) / 1e3, 1), "chunks min/mean/max": [int(chunks.min()), round(float(chunks.mean()), 2), int(chunks.max())],
-                "busy_frac (mean end / max end)": round(float(end.mean() / end.max()), 3)}), flush=True)
+                "busy_frac (mean end / max end)": round(float(end.mean() / end.max()), 3),
+                "mean us per CTA in {stage, mark, stream, barrier, visit, chunk end}": [round(float(v), 1) for v in phases]}), flush=True)
         dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, 1)
         del pred
         torch.cuda.empty_cache()

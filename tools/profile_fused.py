@@ -5,7 +5,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "cv-lite-object-detection_b200")]
 import torch
 import densehead as dh
 from oracle import synth
-B = 64
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 boxes, nbox = synth.config_boxes("retina_coco", B, 3)
 bd, nd = torch.from_numpy(boxes).cuda(), torch.from_numpy(nbox).cuda()
 dims = torch.tensor([[640., 640.]] * B, device="cuda")
