@@ -253,7 +253,7 @@ def run_ours(args, rank, world, local_rank):
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
         # torch.distributed is only the bootstrap channel and the barrier: the loss exchange runs in libdensehead.so
-        comm = distributed.init_comm(transports=tuple(args.transports.split(",")), fuse=not args.no_fuse)
+        comm = dict(distributed.init_comm(transports=tuple(args.transports.split(",")), fuse=not args.no_fuse))  # (a copy: set_fused edits the library's record)
 
     B = args.batch
     dims_row = np.array([[SIDE, SIDE]], dtype=np.float32)
@@ -586,6 +586,29 @@ def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
         entry("c2_centernet_s8_encode_b%d" % batch, batch, o.numel() * 4, secs,
               "[B,128,128,5,5] one-hot-centre targets, <=150 boxes; 10 launches per graph replay")
         del o
+    # the extension modes BASELINE's north_star names (the reference has none of them; each is specified by the oracle):
+    # min-area FCOS tie-break, Gaussian CenterNet heat map, GIoU box loss -- one line each, same shapes as C1 / C2 at 256
+    batch = 256
+    b, n, d = dev_boxes("fcos_voc", batch, synth.seed_for(1, 200), 512)
+    outs, cnt = fcos.format_data_batch(b, n, d, 20, [512, 512], mode="min_area")
+    secs = graph_time(lambda: fcos.format_data_batch(b, n, d, 20, [512, 512], mode="min_area", out=outs, num_targets=cnt), per_graph=10)
+    entry("ext_fcos_min_area_encode_b256", batch, sum(o.numel() for o in outs) * 4, secs, "DH_FCOS_MIN_AREA: the smallest covering box wins channels 0..4")
+    gen0 = torch.Generator(device=dev)
+    gen0.manual_seed(4)
+    fpred = []
+    for o in outs:
+        p = torch.randn(o.shape, device=dev, generator=gen0) - 4.0
+        p[..., :4] = p[..., :4].abs() + 0.3
+        fpred.append(p)
+    secs = graph_time(lambda: fcos.encode_loss_batch(b, n, d, 20, [512, 512], fpred, reg_type="giou"), per_graph=10)
+    entry("ext_fcos_fused_loss_giou_b256", batch, sum(o.numel() for o in outs) * 4, secs, "DH_REG_GIOU in the fused encode + loss step (C1 shapes)")
+    del outs, fpred
+    b, n, d = dev_boxes("centernet_crowdhuman", batch, synth.seed_for(2, 200), 512)
+    o, st = centernet.format_data_batch(b, n, d, 1, [512, 512], stride=4, mode="gaussian")
+    secs = graph_time(lambda: centernet.format_data_batch(b, n, d, 1, [512, 512], stride=4, mode="gaussian", out=o, status=st), per_graph=4)
+    entry("ext_centernet_gaussian_encode_b256", batch, o.numel() * 4, secs,
+          "DH_CENTERNET_GAUSSIAN: [B,128,128,6] maps, Gaussian heat (max over overlapping boxes) + tblr, <=150 boxes")
+    del o
     # C3: RetinaNet COCO-shaped encode (targets materialised), batch 64
     batch = 64
     b, n, d = dev_boxes("retina_coco", batch, synth.seed_for(3, 200), 640)
@@ -670,16 +693,22 @@ def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
     entry("c4_fcos_decode_topk_nms_b64", batch, nbytes, secs, "decode + sigmoid + top-1000/level + per-class NMS (100/class, 100 total); "
           "bytes = one read of the head outputs; NMS itself is latency-bound")
     del heads
-    heads = []
-    for h in LEVELS:
-        p = torch.empty((batch, ANCHORS, h, h, 84), device=dev)
-        p[..., :4].uniform_(-0.5, 1.5, generator=gen)
-        p[..., 4:].normal_(-4.595, 2.5, generator=gen)
-        heads.append(p)
-    nbytes = sum(p.numel() for p in heads) * 4
-    secs = eager_time(lambda: retinanet.detect_batch(heads, 80, [640, 640], pre_nms_topk=1000))
-    entry("c4_retina_decode_topk_nms_b64", batch, nbytes, secs, "decode + max/argmax + top-1000/level + class-agnostic NMS; "
-          "bytes = one read of the head outputs")
+    for tag, size_lo, note in (("", 0.5, "centre offsets ~ U(-0.5, 0.5) anchors, sizes ~ U(0.5, 1.5) anchors"),
+                               ("_r01_heads", -0.5, "round-1 head distribution: all four regressions ~ U(-0.5, 1.5), i.e. a quarter of the "
+                                "decoded sizes negative (inverted boxes, which no trained head emits)")):
+        heads = []
+        for h in LEVELS:
+            p = torch.empty((batch, ANCHORS, h, h, 84), device=dev)
+            p[..., :2].uniform_(-0.5, 0.5 if size_lo > 0 else 1.5, generator=gen)
+            p[..., 2:4].uniform_(size_lo, 1.5, generator=gen)
+            p[..., 4:].normal_(-4.595, 2.5, generator=gen)
+            heads.append(p)
+        nbytes = sum(p.numel() for p in heads) * 4
+        secs = eager_time(lambda: retinanet.detect_batch(heads, 80, [640, 640], pre_nms_topk=1000))
+        _, _, n_keep = retinanet.detect_batch(heads, 80, [640, 640], pre_nms_topk=1000)
+        entry("c4_retina_decode_topk_nms_b64" + tag, batch, nbytes, secs, "decode + max/argmax + top-1000/level + class-agnostic NMS; "
+              "bytes = one read of the head outputs; %s; %.0f of 5000 candidates kept per image" % (note, float(n_keep.float().mean())))
+        del heads
     return out
 
 

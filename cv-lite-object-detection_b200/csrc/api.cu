@@ -192,7 +192,7 @@ int dh_set_option(dh_handle_t h, int option, int value) {
             h->fused_max_chunk = value;
             return DH_OK;
         case DH_OPT_NMS_FILTER:
-            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_NMS_FILTER must be 0 or 1");
+            DH_CHECK_ARG(value >= 0 && value <= 64, "DH_OPT_NMS_FILTER must be in [0, 64]");
             h->nms_filter = value;
             return DH_OK;
         case DH_OPT_NMS_CHAIN:

@@ -205,8 +205,11 @@ struct SegLists {
     uint32_t* head;           // [kMaxChunkTiles * 256] per chunk row: the last pair appended for it (kNoPair between chunks)
     uint32_t* rowbits;        // [kMaxChunkTiles * 8] one bit per chunk row: has a pair (zero between chunks)
     unsigned short* rowlist;  // [kMaxPairs] the chunk rows that have pairs, ascending (scan_rows)
-    int* tile_tab;            // [kMaxChunkTiles][4] per tile of the chunk: map, first row, segment
+    int* tile_tab;            // [kMaxChunkTiles][4] per tile of the chunk: map, first row, segment, rows
+    float* span_sum;          // [kMaxSpans][2] the label-free sums {class, centerness} of each span of the chunk
+    int* span_ctr;            // [1] next span to hand out (zero between chunks)
 };
+constexpr int kMaxSpans = kMaxChunkTiles * 4;  // a tile (256 rows) is streamed as 2 spans of 128 rows or 4 of 64
 constexpr uint32_t kNoPair = 0xffffu;
 template <class P>
 __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
@@ -215,7 +218,7 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     l.raw_off = (static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127;
     l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
     l.seg_off = l.cand_off;
-    l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 4 + 32 + 16);  // SegLists
+    l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 4 + 32 + 16 + 32) + 16;  // SegLists
     l.misc_off = l.run_off + DH_THREADS * kRunCap * 2;  // resolve_pass: the boxes of the row a lane resolves
     l.args_off = l.misc_off + 512;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
@@ -249,18 +252,35 @@ __device__ __forceinline__ void stream_vec_item(const float4& x, bool is_reg, fl
 }
 // `c4` = position of this lane's next item inside its row (in float4s), advanced by 32 mod vpr per item: no division
 // in the loop, and correct for every row length (a lane may meet several regression float4s per tile, or none)
-template <int kCls, bool kGrad, int U>
+// the elements of a float4 whose channel is below n_skip (box regression, centerness) become -inf: they add exactly 0 to
+// the label-free class sum and get a zero gradient.  c0 = channel of the float4's first element.
+__device__ __forceinline__ void mask_skip(float4& x, int c0, int ch, int n_skip) {
+    int c = c0;
+    if (c < n_skip) x.x = -INFINITY;
+    c = c + 1 == ch ? 0 : c + 1;
+    if (c < n_skip) x.y = -INFINITY;
+    c = c + 1 == ch ? 0 : c + 1;
+    if (c < n_skip) x.z = -INFINITY;
+    c = c + 1 == ch ? 0 : c + 1;
+    if (c < n_skip) x.w = -INFINITY;
+}
+// kAny = false: rows are whole float4s (ch % 4 == 0) and start with exactly the 4 regression channels -- `vpr` float4s per
+// row, c4 = the item's position in its row.  kAny = true: any row length and channel layout over a 16-byte-aligned flat
+// range -- `vpr` is then the row length in floats, c4 the channel of the item's first element, `n_skip` the channels
+// that are not class logits (the centerness channel is added by a separate pass over the rows, stream_cen).
+template <int kCls, bool kGrad, int U, bool kAny = false>
 __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int c4, int step,
-                                           int lane, float gamma, float gscale, StreamAcc& a) {
+                                           int lane, float gamma, float gscale, StreamAcc& a, int n_skip = 4) {
     const float4* __restrict__ ptr = reinterpret_cast<const float4*>(p) + lane;
     float4* __restrict__ gptr = reinterpret_cast<float4*>(gout) + lane;
-    const int n_mine = (nrows * vpr - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
+    const int n_items = kAny ? (nrows * vpr) >> 2 : nrows * vpr;
+    const int n_mine = (n_items - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
     int k = 0;
     if constexpr (kCls == 1) {
         // gamma == 2: when every class logit of the warp's batch is <= kSmallLogit (one vote per 128 U elements; 96 % of the
         // batches at logits ~ N(-4.6, 1)) the batch takes the polynomial form of the term (and of its derivative)
         const unsigned small_bits = __float_as_uint(kSmallLogit);
-        const int n_all = (nrows * vpr) >> 5;  // items EVERY lane has: the vote below needs a warp-uniform trip count
+        const int n_all = n_items >> 5;  // items EVERY lane has: the vote below needs a warp-uniform trip count
 #pragma unroll 1
         for (; k + U <= n_all; k += U, ptr += 32 * U, gptr += 32 * U) {
             float4 x[U];
@@ -271,7 +291,8 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
             for (int u = 0; u < U; ++u) {
                 // float4 0 of a row = the 4 regression channels: as -inf they add exactly 0 in either form (e = 0), which
                 // is cheaper than branching around them
-                if (c4 == 0) x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                if constexpr (kAny) mask_skip(x[u], c4, vpr, n_skip);
+                else if (c4 == 0) x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
                 lowest = min(lowest, min_bits4(x[u]));
                 c4 += step;
                 if (c4 >= vpr) c4 -= vpr;
@@ -302,7 +323,12 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
             for (int u = 0; u < U; ++u) x[u] = __ldcs(ptr + 32 * u);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                stream_vec_item<kCls, kGrad>(x[u], c4 == 0, gamma, gscale, a, gptr + 32 * u);
+                if constexpr (kAny) {
+                    mask_skip(x[u], c4, vpr, n_skip);
+                    stream_vec_item<kCls, kGrad>(x[u], false, gamma, gscale, a, gptr + 32 * u);
+                } else {
+                    stream_vec_item<kCls, kGrad>(x[u], c4 == 0, gamma, gscale, a, gptr + 32 * u);
+                }
                 c4 += step;
                 if (c4 >= vpr) c4 -= vpr;
             }
@@ -310,10 +336,43 @@ __device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* _
     }
 #pragma unroll 1
     for (; k < n_mine; ++k, ptr += 32, gptr += 32) {
-        const float4 x = __ldcs(ptr);
-        stream_vec_item<kCls, kGrad>(x, c4 == 0, gamma, gscale, a, gptr);
+        float4 x = __ldcs(ptr);
+        if constexpr (kAny) {
+            mask_skip(x, c4, vpr, n_skip);
+            stream_vec_item<kCls, kGrad>(x, false, gamma, gscale, a, gptr);
+        } else {
+            stream_vec_item<kCls, kGrad>(x, c4 == 0, gamma, gscale, a, gptr);
+        }
         c4 += step;
         if (c4 >= vpr) c4 -= vpr;
+    }
+}
+// kAny companion: the centerness channel of rows [0, nrows) as if its label were zero (one element per row, lane <-> row;
+// the sectors were just streamed by this warp), and the up to three floats a flat range leaves behind its last float4.
+template <int kCls, bool kGrad>
+__device__ __forceinline__ void stream_cen_and_tail(const float* __restrict__ p, float* __restrict__ gout, int nrows, int ch, int lane,
+                                                    const LossSpec& sp, StreamAcc& a) {
+    if (kGrad) __syncwarp();  // the float4 stores above wrote a zero where the centerness gradient goes now
+    if (sp.cen_mode == 1 || sp.cen_mode == 2) {
+#pragma unroll 1
+        for (int r = lane; r < nrows; r += 32) {
+            const float x = p[static_cast<long long>(r) * ch + sp.reg_ch];
+            if (sp.cen_mode == 1) {
+                a.cen += cen_l1_zero(x, sp.delta);
+                if (kGrad) gout[static_cast<long long>(r) * ch + sp.reg_ch] = sp.w_cen * cen_l1_grad(0.f, x, sp.delta);
+            } else {
+                a.cen += focal_term(0.f, x, sp.alpha, sp.gamma);
+                if (kGrad) gout[static_cast<long long>(r) * ch + sp.reg_ch] = sp.w_cen * focal_grad(0.f, x, sp.alpha, sp.gamma);
+            }
+        }
+    }
+    const int n = nrows * ch, done = n & ~3;
+    if (lane < n - done) {
+        const int e = done + lane, c = e % ch;
+        const int n_skip = sp.reg_ch + (sp.cen_mode != 0 ? 1 : 0);
+        float d = 0.f;
+        if (c >= n_skip) d = stream_term<kCls, false, kGrad>(p[e], sp.gamma, a.c3) * ((kCls == 2 ? 1.0f : 1.0f - sp.alpha) * sp.w_cls);
+        if (kGrad && !(c == sp.reg_ch && (sp.cen_mode == 1 || sp.cen_mode == 2))) gout[e] = d;  // (the loop above wrote a centerness element)
     }
 }
 
@@ -447,7 +506,9 @@ __device__ __forceinline__ SegLists seg_lists(unsigned char* base, int box_cap) 
     L.pairs = L.head + kMaxChunkTiles * DH_THREADS;
     L.rowbits = L.pairs + kMaxPairs;
     L.tile_tab = reinterpret_cast<int*>(L.rowbits + kMaxChunkTiles * 8);
-    L.next = reinterpret_cast<unsigned short*>(L.tile_tab + kMaxChunkTiles * 4);
+    L.span_sum = reinterpret_cast<float*>(L.tile_tab + kMaxChunkTiles * 4);
+    L.span_ctr = reinterpret_cast<int*>(L.span_sum + kMaxSpans * 2);
+    L.next = reinterpret_cast<unsigned short*>(L.span_ctr + 4);
     L.rowlist = L.next + kMaxPairs;
     L.box = L.rowlist + kMaxPairs;
     return L;
@@ -466,17 +527,25 @@ __device__ __forceinline__ int locate_tile(const LossArgs<P>& a, int img, int t_
     return seg;
 }
 
+// tile t of the chunk: where it lies (every chunk; read by the streaming pass and by resolve_pass)
+template <class P>
+__device__ __forceinline__ void build_tile_tab(const LossArgs<P>& a, const SegLists& L, int img, int t_begin, int t_end) {
+    if (static_cast<int>(threadIdx.x) < t_end - t_begin) {
+        TileCursor cur;
+        const int seg_t = locate_tile<P>(a, img, t_begin, t_begin + threadIdx.x, cur);
+        const int r0 = cur.t * a.tt.rows_per_tile;
+        L.tile_tab[threadIdx.x * 4 + 0] = cur.m, L.tile_tab[threadIdx.x * 4 + 1] = r0, L.tile_tab[threadIdx.x * 4 + 2] = seg_t;
+        L.tile_tab[threadIdx.x * 4 + 3] = min(a.tt.rows_per_tile, a.tt.maps[cur.m].rows - r0);
+    }
+}
+
 template <class P>
 __device__ __forceinline__ void pair_pass(const LossArgs<P>& a, const typename P::Rec* recs, int n_boxes, const SegLists& L,
-                                          int img, int t_begin, int t_end) {
+                                          int img, int t_begin, int t_end, int n_workers) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rpt = a.tt.rows_per_tile;
     const int n_groups = (n_boxes + 31) >> 5;
     TileCursor cur;
-    if (static_cast<int>(threadIdx.x) < t_end - t_begin) {  // thread t: where tile t of the chunk lies (read by resolve_pass)
-        const int seg_t = locate_tile<P>(a, img, t_begin, t_begin + threadIdx.x, cur);
-        L.tile_tab[threadIdx.x * 4 + 0] = cur.m, L.tile_tab[threadIdx.x * 4 + 1] = cur.t * rpt, L.tile_tab[threadIdx.x * 4 + 2] = seg_t;
-    }
     cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
     int seg = 0, item = 0;
 #pragma unroll 1
@@ -492,7 +561,7 @@ __device__ __forceinline__ void pair_pass(const LossArgs<P>& a, const typename P
         const int seg_i1 = static_cast<int>(fdiv_u32(static_cast<uint32_t>(cell1), md.div_width));
 #pragma unroll 1
         for (int g = 0; g < n_groups; ++g, ++item) {
-            if ((item & (DH_THREADS / 32 - 1)) != warp) continue;      // (warp-uniform) this warp's items
+            if (item % n_workers != warp) continue;                    // (warp-uniform) this warp's items
             const int k = g * 32 + lane;
             int ilo = 0, ihi = -1, jlo = 0, jhi = -1;
             bool hit = k < n_boxes && P::map_hit(a.pp, recs[k], md.level, md.anchor) &&
@@ -580,13 +649,13 @@ __device__ __forceinline__ int scan_rows(const SegLists& L) {
 // the order in which the pairs were appended: results are run-to-run deterministic.
 template <class P>
 __device__ __noinline__ LossAcc resolve_pass(const LossArgs<P>& a, const typename P::Rec* recs, const SegLists& L, int n_rows, int img,
-                                             unsigned short* scratch) {
+                                             unsigned short* scratch, int n_workers) {
     LossAcc acc = {0.f, 0.f, 0.f, 0};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rpt = a.tt.rows_per_tile;
     unsigned short* mine = scratch + threadIdx.x * kRunCap;  // this lane's boxes (a row seldom has more than two or three)
 #pragma unroll 1
-    for (int p0 = warp * 32; p0 < n_rows; p0 += DH_THREADS) {  // warp-uniform trip count
+    for (int p0 = warp * 32; p0 < n_rows; p0 += 32 * n_workers) {  // warp-uniform trip count
         const int p = p0 + lane;
         int pairs = 0;
         if (p < n_rows) {
@@ -599,7 +668,7 @@ __device__ __noinline__ LossAcc resolve_pass(const LossArgs<P>& a, const typenam
             const int m = L.tile_tab[tix * 4 + 0], r0 = L.tile_tab[tix * 4 + 1], seg = L.tile_tab[tix * 4 + 2];
             const MapDesc& md = a.tt.maps[m];
             TileInfo ti;
-            ti.b = img, ti.m = m, ti.r0 = r0, ti.nrows = min(rpt, md.rows - r0);
+            ti.b = img, ti.m = m, ti.r0 = r0, ti.nrows = L.tile_tab[tix * 4 + 3];
             ti.level = md.level, ti.anchor = md.anchor, ti.height = md.height, ti.width = md.width, ti.sub = md.sub;
             const unsigned short* boxes = mine;
             if (len > kRunCap) boxes = L.box + seg * a.box_cap, len = L.nmap[seg];  // (rare) every box that can match the map
@@ -626,11 +695,11 @@ __device__ __noinline__ LossAcc resolve_pass(const LossArgs<P>& a, const typenam
 // Fallback for a chunk whose pair list overflowed: warp w visits every row of tile w with the segment's whole box list.
 template <class P>
 __device__ __noinline__ LossAcc visit_dense(const LossArgs<P>& a, const typename P::Rec* recs, const SegLists& L, int img, int t_begin,
-                                            int t_end) {
+                                            int t_end, int n_workers) {
     LossAcc acc = {0.f, 0.f, 0.f, 0};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1
-    for (int tile = t_begin + warp; tile < t_end; tile += DH_THREADS / 32) {
+    for (int tile = t_begin + warp; tile < t_end; tile += n_workers) {
     TileCursor cur;
     const int seg = locate_tile<P>(a, img, t_begin, tile, cur);
     const MapDesc& md = a.tt.maps[cur.m];
@@ -662,66 +731,57 @@ __device__ __noinline__ LossAcc visit_dense(const LossArgs<P>& a, const typename
     return acc;
 }
 
-// ---- stream: every element of this warp's tiles as if its label were zero -----------------------------------------
-// The chunk's rows (its tiles laid end to end) are split into eight equal contiguous spans, one per warp: a warp
-// streams a few long contiguous runs (one per tile it touches) instead of one 32-row slice of every tile, which
-// amortises the per-run setup and balances ragged tiles.  `run(ptr, grad_ptr, nrows)` is called per run.
-template <class P, class Run>
-__device__ __forceinline__ void for_warp_span(const LossArgs<P>& a, int img, int t_begin, int t_end, bool want_grad, Run run) {
-    const int warp = threadIdx.x >> 5;
+// ---- stream: every element of the chunk as if its label were zero --------------------------------------------------
+// The chunk's tiles are cut into spans of 64 or 128 rows which the warps TAKE from a shared-memory counter: a warp that
+// was busy with something else (the helper warps pair boxes with rows and resolve the target rows first) simply takes
+// fewer, and the warps reach the chunk-end barrier together.  A span's sums are reduced over the warp and stored per
+// span; the chunk's sum is formed from them in span order afterwards, so it does not depend on which warp took which
+// span: results stay run-to-run deterministic.
+template <class P, int kCls, bool kGrad, int kMode /*0 scalar, 1 whole-float4 rows, 2 any layout over an aligned flat range*/>
+__device__ __noinline__ void stream_spans(const LossArgs<P>& a, const SegLists& L, int img, int n_tiles, int span_rows) {
+    const int lane = threadIdx.x & 31;
     const int ch = a.tt.ch;
-    TileCursor cur;
-    cursor_init(a.tt, static_cast<long long>(img) * a.tt.tiles_per_image + t_begin, cur);
-    int total = 0;
-    {
-        TileCursor c = cur;
-        for (int tile = t_begin; tile < t_end; ++tile, cursor_next(a.tt, c)) {
-            TileInfo ti;
-            cursor_info(a.tt, c, ti);
-            total += ti.nrows;
-        }
-    }
-    const int lo = static_cast<int>(static_cast<long long>(total) * warp / (DH_THREADS / 32));
-    const int hi = static_cast<int>(static_cast<long long>(total) * (warp + 1) / (DH_THREADS / 32));
-    int off = 0;
+    const int spt = a.tt.rows_per_tile / span_rows, n_spans = n_tiles * spt;
+    const int vpr = ch >> 2;
+    const int step = kMode == 1 ? 32 % vpr : (kMode == 2 ? 128 % ch : 32 % ch);
+    const int c_lane = kMode == 1 ? lane % vpr : (kMode == 2 ? (4 * lane) % ch : lane % ch);
+    const int n_skip = a.spec.reg_ch + (a.spec.cen_mode != 0 ? 1 : 0);
+    const float gamma = a.spec.gamma, gscale = (kCls == 2 ? 1.0f : 1.0f - a.spec.alpha) * a.spec.w_cls;
+    const LossSpec sp = a.spec;
 #pragma unroll 1
-    for (int tile = t_begin; tile < t_end && off < hi; ++tile, cursor_next(a.tt, cur)) {
-        TileInfo ti;
-        cursor_info(a.tt, cur, ti);
-        const int b0 = max(lo, off), b1 = min(hi, off + ti.nrows);
-        if (b1 > b0) {
-            const MapDesc& md = a.tt.maps[ti.m];
-            const long long e = static_cast<long long>(img) * md.image_stride + static_cast<long long>(ti.r0 + (b0 - off)) * ch;
-            run(md.pred + e, (want_grad && a.grad_maps[ti.m]) ? a.grad_maps[ti.m] + e : nullptr, b1 - b0);
+    for (;;) {
+        int s = 0;
+        if (lane == 0) s = atomicAdd(L.span_ctr, 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s >= n_spans) break;
+        const int tix = s / spt, q = s - tix * spt;
+        const int m = L.tile_tab[tix * 4 + 0], r0 = L.tile_tab[tix * 4 + 1] + q * span_rows;
+        const int nrows = min(span_rows, L.tile_tab[tix * 4 + 3] - q * span_rows);
+        StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
+        if (nrows > 0) {
+            const MapDesc& md = a.tt.maps[m];
+            const long long e = static_cast<long long>(img) * md.image_stride + static_cast<long long>(r0) * ch;
+            float* gg = (kGrad && a.grad_maps[m]) ? a.grad_maps[m] + e : nullptr;
+            if constexpr (kMode == 1) {
+                stream_vec<kCls, kGrad, kGrad ? 5 : 7>(md.pred + e, gg, nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
+            } else if constexpr (kMode == 2) {
+                stream_vec<kCls, kGrad, kGrad ? 5 : 7, true>(md.pred + e, gg, nrows, ch, c_lane, step, lane, gamma, gscale, sa, n_skip);
+                stream_cen_and_tail<kCls, kGrad>(md.pred + e, gg, nrows, ch, lane, sp, sa);
+            } else {
+                stream_scalar<kCls, kGrad, 4>(md.pred + e, gg, nrows, ch, c_lane, step, lane, sp, sa);
+            }
         }
-        off += ti.nrows;
+        float q0, q1, q2, q3;
+        unpack2(sa.p0, q0, q1);
+        unpack2(sa.p1, q2, q3);
+        const float cls = warp_sum(((sa.c0 + sa.c1) + (sa.c2 + sa.c3)) + ((q0 + q1) + (q2 + q3)));
+        const float cen = warp_sum(sa.cen);
+        if (lane == 0) L.span_sum[2 * s] = cls, L.span_sum[2 * s + 1] = cen;
     }
 }
 
-template <class P, int kCls, bool kGrad>
-__device__ __noinline__ StreamAcc stream_pass_vec(const LossArgs<P>& a, int img, int t_begin, int t_end) {
-    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
-    const int lane = threadIdx.x & 31;
-    const int vpr = a.tt.ch >> 2;
-    const int step = 32 % vpr, c_lane = lane % vpr;
-    const float gamma = a.spec.gamma, gscale = (kCls == 2 ? 1.0f : 1.0f - a.spec.alpha) * a.spec.w_cls;
-    for_warp_span(a, img, t_begin, t_end, kGrad, [&](const float* gp, float* gg, int nrows) {
-        stream_vec<kCls, kGrad, kGrad ? 5 : 7>(gp, gg, nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
-    });
-    return sa;
-}
-template <class P, int kCls, bool kGrad>
-__device__ __noinline__ StreamAcc stream_pass_scalar(const LossArgs<P>& a, int img, int t_begin, int t_end) {
-    StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
-    const int lane = threadIdx.x & 31;
-    const int ch = a.tt.ch;
-    const int step = 32 % ch, c_lane = lane % ch;
-    const LossSpec sp = a.spec;
-    for_warp_span(a, img, t_begin, t_end, kGrad, [&](const float* gp, float* gg, int nrows) {
-        stream_scalar<kCls, kGrad, 4>(gp, gg, nrows, ch, c_lane, step, lane, sp, sa);
-    });
-    return sa;
-}
+__device__ __forceinline__ void helper_barrier(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+
 // The chunk -> (tier, image, first tile) map of the tiered scheduler (LossArgs::tiers).
 template <class P>
 __device__ __forceinline__ void chunk_span(const LossArgs<P>& a, long long chunk, int& img, int& sub, int& t_begin, int& t_end) {
@@ -845,8 +905,18 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     if (tid <= kMaxSegments) segs.nmap[tid] = 0;  // nmap[], npairs
     for (int e = tid; e < kMaxChunkTiles * DH_THREADS; e += DH_THREADS) segs.head[e] = kNoPair;
     if (tid < kMaxChunkTiles * 8) segs.rowbits[tid] = 0u;
+    if (tid == 0) *segs.span_ctr = 0;
+    if (chunk < n_chunks) {
+        int img, sub, t_begin, t_end;
+        chunk_span(ga, chunk, img, sub, t_begin, t_end);
+        build_tile_tab<P>(ga, segs, img, t_begin, t_end);
+    }
     __syncthreads();
 
+    // Warps 0..kHelpers-1 pair boxes with rows and resolve the target rows of a chunk while the others already stream it;
+    // they join the streaming afterwards (the span counter gives them what is left).  With the gradient a matched row
+    // overwrites the zero-label gradient the streaming pass wrote for it, so there the rows are resolved after a barrier.
+    constexpr int kHelpers = 4;
     uint32_t box_parity = 0;
     int cur_img = -1, n_boxes = 0;
     const bool trace = ga.trace != nullptr && tid == 0;
@@ -863,6 +933,8 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     for (; chunk < n_chunks;) {
         int img, sub, t_begin, t_end;
         chunk_span(a, chunk, img, sub, t_begin, t_end);
+        const int n_tiles = t_end - t_begin;
+        const int span_rows = n_tiles >= 8 ? 128 : 64;
         if (tid == 0) *next_chunk = static_cast<long long>(atomicAdd(ga.sched, 1u)) + gridDim.x;
         if (img != cur_img) {  // block-uniform; the barrier at the end of the previous chunk protects recs/raw
             n_boxes = stage_boxes(a.boxes, a.nbox, img, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
@@ -873,66 +945,78 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         }
         if (sub == 0) P::image_prologue(a.pp, recs, n_boxes, img);
         DH_TRACE_PHASE(0)
-        if (n_boxes > 0) pair_pass<P>(a, recs, n_boxes, segs, img, t_begin, t_end);  // (read after the barrier behind the streaming pass)
-        DH_TRACE_PHASE(1)
         if (trace && n_done++ == 0) ga.trace[blockIdx.x * kTraceSlots + 1] = static_cast<long long>(global_ns());
 
-        const StreamAcc sa = vec ? stream_pass_vec<P, kCls, kGrad>(a, img, t_begin, t_end)
-                                 : stream_pass_scalar<P, kCls, kGrad>(a, img, t_begin, t_end);
-        DH_TRACE_PHASE(2)
         LossAcc acc = {0.f, 0.f, 0.f, 0};  // corrections + regression, natural units
-        if (n_boxes > 0 || kGrad) __syncthreads();  // (block-uniform) the pair list is complete; every zero-label gradient of
-                                                   // the chunk is written before a matched row overwrites its own
-        DH_TRACE_PHASE(3)
         int n_pairs = 0;
-        if (n_boxes > 0) {
-            n_pairs = *segs.npairs;  // block-uniform
+        auto resolve = [&]() {  // helper warps, after their barrier: the pair list is complete
+            n_pairs = *segs.npairs;
+            if (tid == 0) segs.npairs[2] = n_pairs > kMaxPairs;  // (read at the chunk end, where npairs itself is being zeroed)
             if (n_pairs > kMaxPairs) {
-                acc = visit_dense<P>(a, recs, segs, img, t_begin, t_end);
+                acc = visit_dense<P>(a, recs, segs, img, t_begin, t_end, kHelpers);
             } else if (n_pairs > 0) {
                 if (warp == 0) {
                     const int n_rows = scan_rows(segs);
                     if (lane == 0) segs.npairs[1] = n_rows;
                 }
-                __syncthreads();
-                acc = resolve_pass<P>(a, recs, segs, segs.npairs[1], img, reinterpret_cast<unsigned short*>(smem + lay.run_off));
+                helper_barrier(32 * kHelpers);
+                acc = resolve_pass<P>(a, recs, segs, segs.npairs[1], img, reinterpret_cast<unsigned short*>(smem + lay.run_off), kHelpers);
             }
+        };
+        if (n_boxes > 0 && warp < kHelpers) {
+            pair_pass<P>(a, recs, n_boxes, segs, img, t_begin, t_end, kHelpers);
+            helper_barrier(32 * kHelpers);
+            DH_TRACE_PHASE(1)
+            if (!kGrad) resolve();
+            DH_TRACE_PHASE(4)
         }
-        DH_TRACE_PHASE(4)
+        if (vec) stream_spans<P, kCls, kGrad, 1>(a, segs, img, n_tiles, span_rows);
+        else if (ga.allow_vec) stream_spans<P, kCls, kGrad, 2>(a, segs, img, n_tiles, span_rows);
+        else stream_spans<P, kCls, kGrad, 0>(a, segs, img, n_tiles, span_rows);
+        DH_TRACE_PHASE(2)
+        if (kGrad) {
+            __syncthreads();  // every zero-label gradient of the chunk is written before a matched row overwrites its own
+            if (n_boxes > 0 && warp < kHelpers) resolve();
+        }
+        DH_TRACE_PHASE(3)
 
         // ---- per-chunk reduction -> partials[chunk] -----------------------------------------------------------
-        float q0, q1, q2, q3;
-        unpack2(sa.p0, q0, q1);
-        unpack2(sa.p1, q2, q3);
-        float cls = (((sa.c0 + sa.c1) + (sa.c2 + sa.c3)) + ((q0 + q1) + (q2 + q3))) * ((kCls == 2 ? 1.0f : 1.0f - ga.spec.alpha) * kLn2) + acc.cls;
-        float cen = sa.cen + acc.cen;
-        cls = warp_sum(cls), cen = warp_sum(cen);
-        const float reg = warp_sum(acc.reg);
+        const float reg = warp_sum(acc.reg), ccls = warp_sum(acc.cls), ccen = warp_sum(acc.cen);
         const int npos = warp_sum_i(acc.npos);
         if (lane == 0) {
-            wred[warp * 4 + 0] = cls, wred[warp * 4 + 1] = reg, wred[warp * 4 + 2] = cen;
+            wred[warp * 4 + 0] = ccls, wred[warp * 4 + 1] = reg, wred[warp * 4 + 2] = ccen;
             wred[warp * 4 + 3] = static_cast<float>(npos);
         }
-        __syncthreads();  // also: every warp is done with recs; the prefetched chunk id is visible
-        if (warp == 0) {  // wred [8][4] -> one float4 per chunk, stored by lane 0 (the thread that later counts the chunk)
+        __syncthreads();  // also: every warp is done with recs and with the spans; the prefetched chunk id is visible
+        if (warp == 0) {  // span sums (in span order) + wred [8][4] -> one float4 per chunk
+            const int n_spans = n_tiles * (a.tt.rows_per_tile / span_rows);
+            float scls = 0.f, scen = 0.f;
+            for (int q = lane; q < n_spans; q += 32) scls += segs.span_sum[2 * q], scen += segs.span_sum[2 * q + 1];
+            scls = warp_sum(scls) * ((kCls == 2 ? 1.0f : 1.0f - ga.spec.alpha) * kLn2), scen = warp_sum(scen);
             float v = 0.f;
             if (lane < 4) {
 #pragma unroll
                 for (int w = 0; w < DH_THREADS / 32; ++w) v += wred[w * 4 + lane];
             }
-            const float4 o = make_float4(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 1), __shfl_sync(0xffffffffu, v, 2),
+            const float4 o = make_float4(__shfl_sync(0xffffffffu, v, 0) + scls, __shfl_sync(0xffffffffu, v, 1), __shfl_sync(0xffffffffu, v, 2) + scen,
                                          __shfl_sync(0xffffffffu, v, 3));
             if (lane == 0) reinterpret_cast<float4*>(a.partials)[chunk] = o;
         }
         chunk = *next_chunk;
         if (n_boxes > 0) {  // (the correct pass is done with the lists) counters and row chains back to empty
             if (tid <= kMaxSegments) segs.nmap[tid] = 0;
-            if (n_pairs > kMaxPairs) {  // (the resolve pass leaves both tables empty; the dense visit does not use them)
+            if (segs.npairs[2]) {  // the pair list overflowed (resolve_pass leaves both tables empty; the dense visit does not use them)
                 for (int e = tid; e < kMaxChunkTiles * DH_THREADS; e += DH_THREADS) segs.head[e] = kNoPair;
                 if (tid < kMaxChunkTiles * 8) segs.rowbits[tid] = 0u;
             }
         }
-        __syncthreads();  // wred / next_chunk are free again; the lists are empty
+        if (tid == DH_THREADS - 1) *segs.span_ctr = 0;
+        if (chunk < n_chunks) {  // the next chunk's tile table, published by the barrier below
+            int img2, sub2, tb2, te2;
+            chunk_span(a, chunk, img2, sub2, tb2, te2);
+            build_tile_tab<P>(a, segs, img2, tb2, te2);
+        }
+        __syncthreads();  // wred / next_chunk are free again; the lists are empty; the tile table is the next chunk's
         DH_TRACE_PHASE(5)
     }
 #undef DH_TRACE_PHASE

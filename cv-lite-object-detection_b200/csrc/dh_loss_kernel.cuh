@@ -40,7 +40,7 @@ struct NoPolicy {
     };
 };
 
-constexpr int kMaxChunkTiers = 5;
+constexpr int kMaxChunkTiers = 8;
 struct ChunkTier {
     long long chunk0;  // id of the tier's first chunk
     int image0;        // first image of the tier

@@ -62,7 +62,7 @@ __device__ __forceinline__ unsigned long long nms_sort_key(const float* d, int r
 // Each axis of an image's candidates is cut into 32 slabs over the candidates' own coordinate range; a box carries, per
 // axis, the bit mask of the slabs it touches.  The slab index is a monotone function of the coordinate, so two boxes that
 // overlap on an axis share a slab there: (mask_a & mask_c) == 0 on either axis proves an empty intersection.  Boxes
-// without a positive finite area get all-ones masks (they always take the exact predicate).
+// that are not proper (inverted corners, zero extent, NaN) get all-ones masks: they always take the exact predicate.
 __device__ __forceinline__ unsigned ordered_bits(float v) {  // monotone float -> uint
     const unsigned u = __float_as_uint(v);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -76,12 +76,14 @@ __device__ __forceinline__ unsigned slab_range_mask(float lo_v, float hi_v, floa
 __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __restrict__ dets, const int* __restrict__ n_valid,
                                                                 NmsParams p, int n_pow2, int force_bitonic, float4* __restrict__ sorted_boxes,
                                                                 int* __restrict__ sorted_cls, int* __restrict__ order,
-                                                                int* __restrict__ n_cand, uint2* __restrict__ sorted_slabs) {
+                                                                int* __restrict__ n_cand, uint2* __restrict__ sorted_slabs,
+                                                                int* __restrict__ filter_ok) {
     extern __shared__ unsigned long long keys[];  // [n_pow2]
     __shared__ unsigned bucket_start[kSortBuckets], bucket_fill[kSortBuckets];
     __shared__ unsigned warp_tot[kSortThreads / 32];
     __shared__ unsigned key_min, key_max, biggest;
     __shared__ unsigned rng[4];  // ordered bits of {min, max} of axis 0 and of axis 1 over the valid candidates
+    __shared__ unsigned n_improper;  // valid candidates that are not proper boxes (they defeat the slab filter)
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = n_valid ? min(n_valid[b], p.n_max) : p.n_max;
     const float* d = dets + static_cast<long long>(b) * p.n_max * p.row_floats;
@@ -92,23 +94,24 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
         sorted_cls[static_cast<long long>(b) * p.n_max + pos] = p.per_class ? __float2int_rz(r[5]) : 0;
         order[static_cast<long long>(b) * p.n_max + pos] = src;
         if (sorted_slabs) {
-            const float a0 = fminf(r[0], r[2]), a1 = fmaxf(r[0], r[2]), b0 = fminf(r[1], r[3]), b1 = fmaxf(r[1], r[3]);
-            const float area = (a1 - a0) * (b1 - b0);
+            // only a proper box (c2 > c0, c3 > c1, finite) gets tight masks: for two such boxes with an empty intersection both
+            // suppression predicates answer "no" (positive areas, positive denominator); anything else -- inverted corners,
+            // zero extent, NaN -- keeps all-ones masks and always takes the exact predicate
             uint2 m = make_uint2(0xffffffffu, 0xffffffffu);
-            if (area > 0.f && area < 3.0e38f) {  // (a NaN fails both)
+            if (r[2] > r[0] && r[3] > r[1] && fabsf(r[0]) < 3.0e38f && fabsf(r[1]) < 3.0e38f && fabsf(r[2]) < 3.0e38f && fabsf(r[3]) < 3.0e38f) {
                 const float lo0 = ordered_float(rng[0]), hi0 = ordered_float(rng[1]), lo1 = ordered_float(rng[2]), hi1 = ordered_float(rng[3]);
                 const float sc0 = hi0 > lo0 ? 32.0f / (hi0 - lo0) : 0.f, sc1 = hi1 > lo1 ? 32.0f / (hi1 - lo1) : 0.f;
-                if (sc0 < 3.0e38f && sc1 < 3.0e38f) m = make_uint2(slab_range_mask(a0, a1, lo0, sc0), slab_range_mask(b0, b1, lo1, sc1));
+                if (sc0 < 3.0e38f && sc1 < 3.0e38f) m = make_uint2(slab_range_mask(r[0], r[2], lo0, sc0), slab_range_mask(r[1], r[3], lo1, sc1));
             }
             sorted_slabs[static_cast<long long>(b) * p.n_max + pos] = m;
         }
     };
     // span of the score keys
-    if (tid == 0) key_min = 0xFFFFFFFFu, key_max = 0u, biggest = 0u, rng[0] = rng[2] = 0xFFFFFFFFu, rng[1] = rng[3] = 0u;
+    if (tid == 0) key_min = 0xFFFFFFFFu, key_max = 0u, biggest = 0u, rng[0] = rng[2] = 0xFFFFFFFFu, rng[1] = rng[3] = 0u, n_improper = 0u;
     for (int i = tid; i < kSortBuckets; i += kSortThreads) bucket_fill[i] = 0u;
     __syncthreads();
     unsigned lo = 0xFFFFFFFFu, hi = 0u;
-    unsigned r0 = 0xFFFFFFFFu, r1 = 0u, r2 = 0xFFFFFFFFu, r3 = 0u;
+    unsigned r0 = 0xFFFFFFFFu, r1 = 0u, r2 = 0xFFFFFFFFu, r3 = 0u, bad = 0u;
     for (int i = tid; i < n; i += kSortThreads) {
         const unsigned long long k = nms_sort_key(d, p.row_floats, i, p.inclusive, p.min_score);
         if (k) {
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
                     r0 = min(r0, ordered_bits(fminf(c0, c2))), r1 = max(r1, ordered_bits(fmaxf(c0, c2)));
                     r2 = min(r2, ordered_bits(fminf(c1, c3))), r3 = max(r3, ordered_bits(fmaxf(c1, c3)));
                 }
+                bad += !(c2 > c0 && c3 > c1 && fabsf(c0) < 3.0e38f && fabsf(c1) < 3.0e38f && fabsf(c2) < 3.0e38f && fabsf(c3) < 3.0e38f);
             }
         }
     }
@@ -129,7 +133,8 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
     if (sorted_slabs) {
         r0 = __reduce_min_sync(0xffffffffu, r0), r1 = __reduce_max_sync(0xffffffffu, r1);
         r2 = __reduce_min_sync(0xffffffffu, r2), r3 = __reduce_max_sync(0xffffffffu, r3);
-        if (lane == 0) atomicMin(&rng[0], r0), atomicMax(&rng[1], r1), atomicMin(&rng[2], r2), atomicMax(&rng[3], r3);
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (lane == 0) atomicMin(&rng[0], r0), atomicMax(&rng[1], r1), atomicMin(&rng[2], r2), atomicMax(&rng[3], r3), atomicAdd(&n_improper, bad);
     }
     __syncthreads();
     const unsigned kmin = key_min, span = key_max >= kmin ? key_max - kmin : 0u;
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
         }
         __syncthreads();
         if (tid == 0) n_cand[b] = m;
+        if (tid == 0 && filter_ok) filter_ok[b] = n_improper * 8u <= static_cast<unsigned>(m);  // improper boxes take every pair: beyond 1 in 8 the filter costs more than it saves
         for (int q = tid; q < m; q += kSortThreads) {
             const unsigned long long k = keys[q];
             const int bk = bucket_of(k);
@@ -204,6 +210,7 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
     }
     // valid keys are a prefix (m of them); gather boxes in score order
     if (tid == 0) n_cand[b] = m;
+    if (tid == 0 && filter_ok) filter_ok[b] = n_improper * 8u <= static_cast<unsigned>(m);
     for (int i = tid; i < m; i += kSortThreads) emit(i, keys[i]);
 }
 
@@ -256,8 +263,9 @@ __device__ __forceinline__ bool suppress_iou(const float4& a0, const float4& c0,
 // "not suppressed" whenever the threshold is not negative (a negative threshold switches the filter off).
 constexpr int kMaskRowBlocks = 4;
 __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(const float4* __restrict__ sorted_boxes, const int* __restrict__ sorted_cls,
-                                                                       const uint2* __restrict__ sorted_slabs, const int* __restrict__ n_cand,
-                                                                       NmsParams p, int words, unsigned long long* __restrict__ mask) {
+                                                                       const uint2* __restrict__ sorted_slabs, const int* __restrict__ filter_ok,
+                                                                       const int* __restrict__ n_cand, NmsParams p, int words, int dense_at,
+                                                                       unsigned long long* __restrict__ mask) {
     const int b = blockIdx.z, cb = blockIdx.x, rb = blockIdx.y * kMaskRowBlocks + (threadIdx.x >> 6);
     const int m = n_cand[b];
     if (cb * 64 >= m || blockIdx.y * kMaskRowBlocks > cb) return;  // only later boxes (j > i) can be suppressed
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(const flo
     __shared__ unsigned slab_cols[2][32][2];  // [axis][slab][column half]: columns of the block that touch the slab
     const int tid = threadIdx.x, t = tid & 63, lane = tid & 31;
     const long long base = static_cast<long long>(b) * p.n_max;
-    const bool filter = sorted_slabs != nullptr && !(p.iou_thr < 0.f);
+    const bool filter = sorted_slabs != nullptr && !(p.iou_thr < 0.f) && filter_ok[b] != 0;
     if (tid < 64) {
         const int j = cb * 64 + t;
         uint2 sm = make_uint2(0u, 0u);
@@ -306,18 +314,42 @@ __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(const flo
         }
         todo &= (static_cast<unsigned long long>(x1 & y1) << 32) | (x0 & y0);
     }
-    unsigned long long bits = 0ull;
-    if (p.per_class) {
-        for (; todo; todo &= todo - 1) {
-            const int c = __ffsll(static_cast<long long>(todo)) - 1;
-            if (ccls[c] == ac && suppress_iou(a, cbox[c], p.iou_thr)) bits |= 1ull << c;
+    // the columns left take the exact predicate, after one more cheap and safe reject for two proper boxes: IoU cannot
+    // exceed min(area) / max(area), so a pair whose areas differ by more than the threshold allows is never suppressed
+    // (0.999 covers the rounding of either side).  Two 32-bit halves: no 64-bit shifts in the loops.
+    const bool a_proper = a.z > a.x && a.w > a.y;
+    const float k_area = (filter && p.iou_thr > 0.f) ? 0.999f * p.iou_thr : -1.0f;  // < 0: reject off
+    unsigned half[2] = {static_cast<unsigned>(todo), static_cast<unsigned>(todo >> 32)}, out[2] = {0u, 0u};
+    // A warp whose rows keep most of their columns (no filter, or boxes that are not proper) walks the columns in step --
+    // every lane reads the same column box, a broadcast -- and each lane skips what it does not need; otherwise every
+    // lane walks its own few columns.
+    const int most = __reduce_max_sync(__activemask(), __popc(half[0]) + __popc(half[1]));
+    if (!filter || most > dense_at) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int t_end = min(32, jn - 32 * hh);
+            for (int tt = 0; tt < t_end; ++tt) {
+                if (!((half[hh] >> tt) & 1u)) continue;
+                const int c = 32 * hh + tt;
+                if (a_proper && k_area > 0.f && cbox[c].z > cbox[c].x && cbox[c].w > cbox[c].y && fminf(area_a, carea[c]) < k_area * fmaxf(area_a, carea[c])) continue;
+                const bool sup = p.per_class ? (ccls[c] == ac && suppress_iou(a, cbox[c], p.iou_thr)) : suppress_agnostic(a, area_a, cbox[c], carea[c], p.iou_thr);
+                if (sup) out[hh] |= 1u << tt;
+            }
         }
     } else {
-        for (; todo; todo &= todo - 1) {
-            const int c = __ffsll(static_cast<long long>(todo)) - 1;
-            if (suppress_agnostic(a, area_a, cbox[c], carea[c], p.iou_thr)) bits |= 1ull << c;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            for (unsigned r = half[hh]; r; r &= r - 1) {
+                const int c = 32 * hh + __ffs(r) - 1;
+                const float4 cbx = cbox[c];
+                const float ca = carea[c];
+                if (a_proper && k_area > 0.f && cbx.z > cbx.x && cbx.w > cbx.y && fminf(area_a, ca) < k_area * fmaxf(area_a, ca)) continue;
+                const bool sup = p.per_class ? (ccls[c] == ac && suppress_iou(a, cbx, p.iou_thr)) : suppress_agnostic(a, area_a, cbx, ca, p.iou_thr);
+                if (sup) out[hh] |= 1u << (c & 31);
+            }
         }
     }
+    const unsigned long long bits = (static_cast<unsigned long long>(out[1]) << 32) | out[0];
     // block-major layout [image][row block][column block][row in block]: a row block's words right of the diagonal are
     // one contiguous range (a single bulk copy for the sweep) and this store is coalesced
     mask[(((static_cast<long long>(b) * words + rb) * words + cb) << 6) + t] = bits;
@@ -600,7 +632,8 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     size_t off_cls = static_cast<size_t>(batch) * per_img * 16;
     size_t off_ord = off_cls + static_cast<size_t>(batch) * per_img * 4;
     size_t off_cnt = off_ord + static_cast<size_t>(batch) * per_img * 4;
-    size_t off_slab = (off_cnt + static_cast<size_t>(batch) * 4 + 255) & ~size_t(255);
+    size_t off_flag = off_cnt + static_cast<size_t>(batch) * 4;
+    size_t off_slab = (off_flag + static_cast<size_t>(batch) * 4 + 255) & ~size_t(255);
     size_t off_mask = (off_slab + static_cast<size_t>(batch) * per_img * 8 + 255) & ~size_t(255);
     // a small output cap ends the sweep after a few blocks: suppression is evaluated lazily, one CTA per image, and the
     // words^2 mask matrix (3 MB per image at 5 000 candidates) is never formed -- nor allocated
@@ -613,13 +646,14 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
     int* scls = reinterpret_cast<int*>(sc + off_cls);
     int* order = reinterpret_cast<int*>(sc + off_ord);
     int* ncand = reinterpret_cast<int*>(sc + off_cnt);
-    uint2* slabs = lazy ? nullptr : reinterpret_cast<uint2*>(sc + off_slab);
+    uint2* slabs = (lazy || !h->nms_filter) ? nullptr : reinterpret_cast<uint2*>(sc + off_slab);
+    int* filter_ok = reinterpret_cast<int*>(sc + off_flag);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(sc + off_mask);
     DH_ONCE_PER_DEVICE(h) {
         DH_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsMaxN * 8));
     }
     nms_sort_kernel<<<batch, kSortThreads, static_cast<size_t>(n_pow2) * 8, st>>>(dets, n_valid, p, n_pow2, h->nms_sort == 1 ? 1 : 0, sboxes, scls, order,
-                                                                                    ncand, slabs);
+                                                                                    ncand, slabs, slabs ? filter_ok : nullptr);
     DH_CUDA(cudaGetLastError());
     const size_t cap_smem = (p.per_class && max_per_class > 0) ? static_cast<size_t>(num_classes) * 4 : 0;
     if (lazy) {
@@ -629,7 +663,8 @@ extern "C" int dh_nms(dh_handle_t h, const float* dets, const int32_t* n_valid, 
         return DH_OK;
     }
     dim3 grid(words, (words + kMaskRowBlocks - 1) / kMaskRowBlocks, batch);
-    nms_mask_kernel<<<grid, 64 * kMaskRowBlocks, 0, st>>>(sboxes, scls, h->nms_filter ? slabs : nullptr, ncand, p, words, mask);
+    nms_mask_kernel<<<grid, 64 * kMaskRowBlocks, 0, st>>>(sboxes, scls, slabs, filter_ok, ncand, p, words, h->nms_filter > 1 ? h->nms_filter : 64,
+                                                          mask);
     DH_CUDA(cudaGetLastError());
     const int staged = words <= kSweepStageWords ? 1 : 0;
     const size_t stage_bytes = staged ? static_cast<size_t>(kSweepDepth) * 64 * words * 8 : 0;  // [depth][words][64] words

@@ -61,7 +61,7 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_FUSED_TAIL 13 /* fused loss scheduler: 1 (default) cuts the last images of a launch into finer chunks so that the tail is short; 0: uniform chunks */
 #define DH_OPT_ENCODE_KERNEL 14 /* target encoders. 0 (default): pick per problem -- direct-store kernel for small outputs, shared-memory tile streamer with TMA bulk stores for large ones; 1: always the tile streamer; 2: always the direct-store kernel */
 #define DH_OPT_FUSED_MAX_CHUNK 15 /* fused loss scheduler with the tiered tail: upper bound on the coarse tier's chunk in tiles of 256 rows (default 16; the coarse chunk is about half of a CTA's share of the work) */
-#define DH_OPT_NMS_FILTER 16 /* mask-matrix NMS: 1 (default) pairs that provably do not overlap (disjoint slab masks) skip the exact predicate; 0: every pair takes it (A/B checks; the bits are identical) */
+#define DH_OPT_NMS_FILTER 16 /* mask-matrix NMS: 1 (default) pairs that provably do not overlap (disjoint slab masks) skip the exact predicate; 0: every pair takes it (A/B checks; the bits are identical); 2..64: on, and a warp whose rows keep more than this many of a block's 64 columns walks the columns in step (tuning aid; default 64 = never).  Images where more than 1 candidate in 8 is not a proper box (inverted corners, NaN) skip the filter by themselves */
 #define DH_OPT_NMS_CHAIN 17 /* block sweep of the mask-matrix NMS: 0 (default) the greedy chain of a 64-box block is resolved in parallel rounds when there are no per-class caps; 1: always the serial walk (A/B checks; identical keeps) */
 int dh_set_option(dh_handle_t h, int option, int value);
 /* Synchronous read of the DH_OPT_PHASE_TIMING counters: out8[0..4] = cycles CTA 0 spent in

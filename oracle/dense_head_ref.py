@@ -986,6 +986,22 @@ def combined_nms(boxes, scores, max_output_size_per_class, max_total_size,
 # --------------------------------------------------------------------------------------
 # a12 / a14  image_detections (head outputs -> detections; model forward removed)
 # --------------------------------------------------------------------------------------
+def retina_decode_dets(head_outputs, anchor_dims=None, strides=None):
+    """The decode front end of RetinaNet/retinanet_module.py:487-520: `head_outputs[level][anchor]` `[Hl, Wl, C+4]` ->
+    `[N, 6]` (y1, x1, y2, x2, max score, first-argmax label), order level > anchor > row-major cell, before any threshold."""
+    strides = list(DEFAULT_STRIDES if strides is None else strides)
+    dims = retina_anchor_dims() if anchor_dims is None else _f32(anchor_dims)
+    flat = []
+    for n, level in enumerate(head_outputs):
+        for a, m in enumerate(level):
+            m = _f32(m)
+            box = retina_prediction_to_corners(m[..., :4], dims[n, a], strides[n])
+            flat.append(np.concatenate([box, _sigmoid32(m[..., 4:])], axis=-1).reshape(-1, m.shape[-1]))
+    flat = np.concatenate(flat, axis=0)
+    return np.concatenate([flat[:, :4], flat[:, 4:].max(axis=1)[:, None], flat[:, 4:].argmax(axis=1).astype(np.float32)[:, None]],
+                          axis=1).astype(np.float32)
+
+
 def retina_image_detections(head_outputs, anchor_dims=None, strides=None, iou_thresh=0.5, cls_thresh=0.05):
     """`head_outputs[level][anchor]` `[Hl, Wl, C+4]` -> `[k, 6]` (y1, x1, y2, x2, score, label) in
     kept order -- RetinaNet/retinanet_module.py:483-530."""

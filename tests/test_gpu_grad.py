@@ -39,7 +39,9 @@ def test_fcos_gradients_fused_and_unfused(mode, reg, cen):
     pi, tot, cnt, grads = dh.fcos.encode_loss_batch(boxes, nbox, [512, 512], C, [512, 512], pred, mode=mode, reg_type=reg,
                                                    cen_type=cen, weights=W)
     pi0, tot0, _ = dh.fcos.encode_loss_batch(boxes, nbox, [512, 512], C, [512, 512], pred, mode=mode, reg_type=reg, cen_type=cen)
-    assert torch.equal(pi, pi0) and torch.equal(tot, tot0)
+    # (the forward and the gradient kernel batch 7 and 5 float4s per lane, so a few small logits take the polynomial form of
+    # the label-0 term in one and the general form in the other: a few 1e-7, not bit for bit; counts are exact)
+    assert torch.allclose(pi, pi0, rtol=2e-6, atol=0) and torch.allclose(tot, tot0, rtol=2e-6, atol=0) and torch.equal(pi[:, 3], pi0[:, 3])
     upi, utot, ugrads = dh.fcos.model_loss_batch(tg, pred, reg, cen, weights=W)
     cen_mode = 1 if cen == "l1" else 2
     for l in range(5):
@@ -90,7 +92,7 @@ def test_centernet_gradients(mode):
     yt, _ = dh.centernet.format_data_batch(boxes, nbox, [512, 512], C, [512, 512], **kw)
     pi, tot, st, grad = dh.centernet.encode_loss_batch(boxes, nbox, [512, 512], C, [512, 512], yp, weights=W, **kw)
     pi0, tot0, _ = dh.centernet.encode_loss_batch(boxes, nbox, [512, 512], C, [512, 512], yp, **kw)
-    assert torch.equal(pi, pi0) and torch.equal(tot, tot0)
+    assert torch.allclose(pi, pi0, rtol=2e-6, atol=0) and torch.allclose(tot, tot0, rtol=2e-6, atol=0) and torch.equal(pi[:, 3], pi0[:, 3])
     if mode == "falloff":
         want = O.dense_loss_grad(yt.cpu().numpy(), yp, weights=W, reg_ch=4, cen_mode=1, pos_rule="ge1")
     else:

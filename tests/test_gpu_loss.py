@@ -260,3 +260,52 @@ def test_retina_fused_forward_small_logit_form(logits, classes):
         yl = y[..., 4:]
         want[0] += float(np.sum(yl * 0.25 * (1 - s) ** 2 * sp_pos + (1 - yl) * 0.75 * s ** 2 * sp_neg))
     assert_close(ftot[:1].cpu().numpy(), want[:1], RTOL, what=logits + " vs float64")
+
+
+def test_bench_configuration_parity():
+    """The configuration bench.py times (BASELINE configs[4] on RetinaNet-COCO shapes: 256 images of 640 x 640, 80 classes,
+    <= 100 boxes, 9 anchors x 5 levels; the same generators): three sampled images of dh_retina_encode_loss against the oracle
+    (1e-5 relative on the sums, positive and pair counts exact), the per-image rows against the total, the gradient
+    variant's sums against the forward ones and its level-0 gradient of one image against the oracle's analytic gradient."""
+    dh = _dh()
+    B, side, C = 256, 640, 80
+    boxes, nbox = synth.config_boxes("retina_coco", B, synth.seed_for(5, 100))
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1000)
+    pred = []
+    for h in (80, 40, 20, 10, 5):
+        p = torch.empty((B, 9, h, h, C + 4), device="cuda")
+        p[..., :4].uniform_(-1, 2, generator=gen)
+        p[..., 4:].normal_(-4.595, 1.0, generator=gen)
+        pred.append(p)
+    pi, tot, pairs = dh.retinanet.encode_loss_batch(boxes, nbox, [side, side], C, [side, side], pred)
+    pi_h, tot_h, pairs_h = pi.cpu().numpy(), tot.cpu().numpy(), pairs.cpu().numpy()
+    for b in (0, 97, 255):
+        lab, n_pairs = O.retina_format_data(boxes[b, :nbox[b]], [side, side], C)
+        want = O.retina_train_loss(lab, [[p[b, a].cpu().numpy() for a in range(9)] for p in pred])
+        n_pos = sum(int((m[..., 4:].max(-1) > 0).sum()) for lv in lab for m in lv)
+        assert_close(pi_h[b, :2], _f(*want), RTOL, what="bench shape, image %d" % b)
+        assert int(pi_h[b, 3]) == n_pos and int(pairs_h[b]) == n_pairs
+    s = pi_h.astype(np.float64).sum(axis=0)
+    assert np.all(np.abs(s[:2] - tot_h[:2]) <= 1e-6 * np.abs(s[:2])) and s[3] == tot_h[3]
+    gpi, gtot, gpairs, grads = dh.retinanet.encode_loss_batch(boxes, nbox, [side, side], C, [side, side], pred, weights=(1.0, 1.0))
+    assert torch.allclose(gpi, pi, rtol=2e-6, atol=0) and torch.equal(gpairs, pairs) and torch.equal(gpi[:, 3], pi[:, 3])
+    b = 97
+    lab, _ = O.retina_format_data(boxes[b, :nbox[b]], [side, side], C)
+    want = O.dense_loss_grad(np.stack(lab[0]), pred[0][b].cpu().numpy(), weights=(1.0, 1.0, 0.0), reg_ch=4, cen_mode=0, pos_rule="gt0")
+    err = np.abs(grads[0][b].cpu().numpy() - want)
+    assert np.all(err <= 2e-5 * np.maximum(1.0, np.abs(want))), err.max()
+
+
+def test_retina_loss_batch_of_one_returns_gradients_too():
+    """`loss_batch(..., weights=)` used to drop the gradients for a one-image batch."""
+    dh = _dh()
+    boxes, nbox = synth.make_boxes(1, 256, 12, 20, 8.0, 150.0, synth.seed_for(5, 95))
+    pred = synth.retina_predictions(1, 256, 20, 9)
+    lab, _ = dh.retinanet.format_data_batch(boxes, nbox, [256, 256], 20, [256, 256])
+    out = dh.retinanet.loss_batch(lab, pred, weights=(1.0, 0.5))
+    assert len(out) == 3 and len(out[2]) == 5
+    pi, tot = dh.retinanet.loss_batch(lab, pred)
+    assert torch.equal(out[0], pi) and torch.equal(out[1], tot)
+    want = O.dense_loss_grad(lab[2][0].cpu().numpy(), pred[2][0], weights=(1.0, 0.5, 0.0), reg_ch=4, cen_mode=0, pos_rule="gt0")
+    assert np.all(np.abs(out[2][2][0].cpu().numpy() - want) <= 2e-5 * np.maximum(1.0, np.abs(want)))

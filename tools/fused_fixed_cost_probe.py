@@ -71,7 +71,7 @@ def main():
             nbytes = sum(p.numel() for p in pred) * 4
             cases = [("tail=1", 1, 16, nd), ("tail=0", 0, 16, nd)]
             if dist == "prior":
-                cases += [("tail=1 max=8", 1, 8, nd), ("tail=1 max=12", 1, 12, nd), ("tail=1 no boxes", 1, 16, zero)]
+                cases += [("tail=1 max=8", 1, 8, nd), ("tail=1 no boxes", 1, 16, zero)]
             for tag, tail, mx, n in cases:
                 dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
                 dh.set_option(0, _capi.DH_OPT_FUSED_MAX_CHUNK, mx)

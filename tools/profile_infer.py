@@ -22,7 +22,9 @@ for _ in range(2):
     r = fcos.detect_batch(hf, 80, [640, 640], pre_nms_topk=1000)
 torch.cuda.synchronize(); print("fcos valid", r[3][:8].tolist())
 del hf
-hr = heads(lambda h: (B, 9, h, h, 84), -0.5, 1.5)
+hr = heads(lambda h: (B, 9, h, h, 84), -0.5, 0.5)   # centre offsets; sizes below: proper boxes, as a trained head emits
+for p in hr:
+    p[..., 2:4].uniform_(0.5, 1.5, generator=gen)
 for _ in range(2):
     c, k, n = retinanet.detect_batch(hr, 80, [640, 640], pre_nms_topk=1000)
 torch.cuda.synchronize(); print("retina kept", n[:8].tolist())
