@@ -559,6 +559,18 @@ def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / (reps * per_graph) * 1e-3
 
+    def eager_time(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / reps * 1e-3
+
     def entry(name, batch, nbytes, secs, note=""):
         out[name] = {"images_per_s": batch / secs, "us": secs * 1e6, "GBps": nbytes / secs / 1e9,
                      "frac_of_hbm_peak": nbytes / secs / 1e9 / peak, "algorithmic_bytes": int(nbytes), "note": note}
@@ -609,6 +621,32 @@ def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
     entry("ext_centernet_gaussian_encode_b256", batch, o.numel() * 4, secs,
           "DH_CENTERNET_GAUSSIAN: [B,128,128,6] maps, Gaussian heat (max over overlapping boxes) + tblr, <=150 boxes")
     del o
+    # f-4: target maps sent back through the detector (show_heatmap's computation) and the offline sparse formatter
+    batch = 256
+    b, n, d = dev_boxes("fcos_voc", batch, synth.seed_for(1, 200), 512)
+    outs, _ = fcos.format_data_batch(b, n, d, 20, [512, 512], mode="center")
+    shapes = [(512, 512)] * batch
+    secs = eager_time(lambda: fcos.ground_truth_detections(outs, 20, shapes, 512, 512, center=True))
+    entry("f4_ground_truth_round_trip_b256", batch, sum(o.numel() for o in outs) * 4, secs,
+          "fcos_center target maps -> boxes, sqrt(class * centerness) scores, combined NMS 0.75 / 0.75 -> rectangles; bytes = one read of the maps")
+    del outs
+    rng = np.random.default_rng(9)
+    obj = np.zeros((batch, 8, 5))
+    obj[..., 0:2] = rng.uniform(0, 400, (batch, 8, 2))
+    obj[..., 2:4] = rng.uniform(8, 120, (batch, 8, 2))
+    obj[..., 4] = rng.integers(1, 81, (batch, 8))
+    objd = torch.from_numpy(obj).to(dev)
+    srcd = torch.tensor([[640.0, 480.0]] * batch, dtype=torch.float64, device=dev)
+    nb8 = torch.full((batch,), 8, dtype=torch.int32, device=dev)
+    idx, val, off = fcos.sparse_format_batch(objd, nb8, srcd)
+    nnz = int(off[-1])
+    from densehead import _capi as capi0
+    secs = graph_time(lambda: capi0.check(capi0.lib().dh_fcos_sparse_encode(
+        capi0.handle(dev.index), objd.data_ptr(), nb8.data_ptr(), srcd.data_ptr(), batch, 8, 448, 448, 5, nnz, idx.data_ptr(),
+        val.data_ptr(), off.data_ptr(), torch.cuda.current_stream().cuda_stream), "dh_fcos_sparse_encode"), per_graph=4)
+    entry("f4_sparse_fcos_format_b256", batch, nnz * 20, secs,
+          "offline COCO -> sparse FCOS targets: %d COO entries (16-byte index + float32 value each), 8 objects per image" % nnz)
+    del idx, val
     # C3: RetinaNet COCO-shaped encode (targets materialised), batch 64
     batch = 64
     b, n, d = dev_boxes("retina_coco", batch, synth.seed_for(3, 200), 640)
@@ -670,17 +708,6 @@ def extra_configs(torch, dh, fcos, retinanet, centernet, synth, dev, peak):
     batch = 64
     # C4: inference decode + per-level top-k (1000) + NMS, batch 64, COCO-shaped heads (eager timing: the pipeline
     # sizes one intermediate from a device-side count)
-    def eager_time(fn, reps=10):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b_.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b_) / reps * 1e-3
     gen.manual_seed(6)
     heads = []
     for h in LEVELS:  # logits ~ N(-4.595, 2.5): >= 1000 candidates per level pass cls_thresh on P3

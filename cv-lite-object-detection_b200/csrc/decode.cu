@@ -26,6 +26,16 @@
 namespace dh {
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return fdiv(1.0f, fadd(1.0f, expf(-x))); }
+// Score of one (location, class) pair from the class and centerness channels of its head row.  `center` is the
+// DH_FCOS_SCORE_* mode: 0 sigmoid(class), 1 sigmoid(centerness) * sigmoid(class) (FCOS/infer_fcos.py:44-51); 2 / 3 take
+// the channels as probabilities -- a TARGET map fed back through the detector (show_heatmap,
+// FCOS/train_fcos_center_voc.py:54-66): 2 the class value, 3 sqrt(class * centerness) in float64 like numpy.
+__device__ __forceinline__ float fcos_pair_score(int center, float cls, float cen) {
+    if (center == 2) return cls;
+    if (center == 3) return static_cast<float>(sqrt(static_cast<double>(cls) * static_cast<double>(cen)));
+    const float s = sigmoid_acc(cls);
+    return center ? fmul(sigmoid_acc(cen), s) : s;
+}
 
 struct CornerParams {
     int mode, height, width, sub, ch_in;  // rows = height*width*sub, input row stride ch_in (first 4 used)
@@ -96,11 +106,8 @@ __global__ void fcos_decode_kernel(const float* __restrict__ pred, int batch, in
             const float4 o = corners_of(cp, loc / wl, loc % wl, 0, q[0], q[1], q[2], q[3]);
             reinterpret_cast<float4*>(boxes)[orow] = o;
         }
-        const float cen = center ? sigmoid_acc(q[4]) : 1.0f;
-        for (int c = lane; c < num_classes; c += 32) {
-            const float s = sigmoid_acc(q[5 + c]);
-            scores[orow * num_classes + c] = center ? fmul(cen, s) : s;
-        }
+        const float cen = center ? q[4] : 0.0f;
+        for (int c = lane; c < num_classes; c += 32) scores[orow * num_classes + c] = fcos_pair_score(center, q[5 + c], cen);
     }
 }
 
@@ -610,8 +617,7 @@ struct FcosSource {
         const int loc = static_cast<int>(fdiv_u32(static_cast<uint32_t>(i), div_c));
         const int c = i - loc * num_classes;
         const float* q = head + static_cast<long long>(loc) * ch;
-        const float s = sigmoid_acc(__ldg(q + 5 + c));
-        return center ? fmul(sigmoid_acc(__ldg(q + 4)), s) : s;
+        return fcos_pair_score(center, __ldg(q + 5 + c), center ? __ldg(q + 4) : 0.0f);
     }
     __device__ __forceinline__ float logit(int i) const {
         const int loc = static_cast<int>(fdiv_u32(static_cast<uint32_t>(i), div_c));

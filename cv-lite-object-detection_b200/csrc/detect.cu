@@ -57,6 +57,7 @@ int dh_fcos_detect(dh_handle_t h, const float* const* pred_levels, int batch, in
     DH_CHECK_ARG(h && pred_levels && strides && out_boxes && out_scores && out_classes && out_valid, "dh_fcos_detect: NULL argument");
     DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_PYRAMID_LEVELS && num_classes >= 1, "dh_fcos_detect: bad configuration");
     DH_CHECK_ARG(batch >= 0 && max_total >= 1 && pre_nms_topk >= 1, "dh_fcos_detect: bad sizes");
+    DH_CHECK_ARG(center >= DH_FCOS_SCORE_CLS && center <= DH_FCOS_SCORE_MAP_CEN, "dh_fcos_detect: score mode %d", center);
     if (batch == 0) return DH_OK;
     DeviceGuard guard(h);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

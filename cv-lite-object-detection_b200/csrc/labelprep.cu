@@ -81,6 +81,26 @@ __global__ void format_detections_kernel(const float* __restrict__ rows, const i
     }
 }
 
+// show_heatmap's rectangles (FCOS/train_fcos_center_voc.py:92-121): float32 throughout (a TF tensor times a ratio array)
+__global__ void fcos_rectangles_kernel(const float4* __restrict__ boxes, const int* __restrict__ valid, const float* __restrict__ ratios,
+                                       int batch, int t, float4* __restrict__ rect) {
+    const int total = batch * t;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int b = e / t, r = e - b * t;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < valid[b]) {
+            const float4 q = boxes[e];  // (y1, x1, y2, x2)
+            const float wr = ratios[2 * b], hr = ratios[2 * b + 1];
+            float x1 = fmul(q.y, hr), y1 = fmul(q.x, wr);
+            const float x2 = fmul(q.w, hr), y2 = fmul(q.z, wr);
+            if (x1 <= 0.f) x1 = 0.f;
+            if (y1 <= 0.f) y1 = 0.f;
+            o = make_float4(x1, y1, fsub(x2, x1), fsub(y2, y1));
+        }
+        rect[e] = o;
+    }
+}
+
 static int grid1d(long long n, int block, int sm_count) {
     long long g = (n + block - 1) / block;
     const long long cap = static_cast<long long>(sm_count) * 8;
@@ -130,6 +150,21 @@ int dh_format_detections(dh_handle_t h, const float* rows, const int32_t* n_keep
     DeviceGuard guard(h);
     format_detections_kernel<<<grid1d(static_cast<long long>(batch) * n, 256, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         rows, n_keep, ratios, batch, n, out_boxes, out_scores, out_labels);
+    DH_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return DH_OK;
+}
+
+int dh_fcos_rectangles(dh_handle_t h, const float* boxes, const int32_t* valid, const float* ratios, int batch, int t, float* out_rect,
+                       void* stream) {
+    DH_CHECK_ARG(h && boxes && valid && ratios && out_rect, "dh_fcos_rectangles: NULL argument");
+    DH_CHECK_ARG(batch >= 0 && t >= 0, "dh_fcos_rectangles: bad sizes");
+    DH_CHECK_ARG(((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(out_rect)) & 15u) == 0,
+                 "dh_fcos_rectangles: boxes and out_rect must be 16-byte aligned");
+    if (batch == 0 || t == 0) return DH_OK;
+    DeviceGuard guard(h);
+    fcos_rectangles_kernel<<<grid1d(static_cast<long long>(batch) * t, 256, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(boxes), valid, ratios, batch, t, reinterpret_cast<float4*>(out_rect));
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
     return DH_OK;

@@ -200,6 +200,54 @@ def prediction_to_corners_center_v1(xy_pred, box_sc, stride):
 
 
 @uses_stream
+def sparse_format_batch(objects, nbox, src_dims, img_dims=(448, 448), num_scale=5, stream=None):
+    """/format_COCO_annotations_fcos.py:66-183 (the offline COCO -> sparse FCOS targets script) for a batch of images.
+
+    `objects` `[B, n, 5]` float64 rows (x_lower, y_lower, box_width, box_height, label) in source-image pixels -- `label` is
+    the script's 1-based class index -- `nbox` `[B]` (or None: every row counts), `src_dims` `[B, 2]` the source images'
+    (img_width, img_height).  Returns (indices `[nnz, 4]` int32 = (y, x, scale, channel), values `[nnz]` float32,
+    offsets `[B+1]` int64: image b owns entries offsets[b]:offsets[b+1]) on the device, entries in the script's order;
+    one host synchronisation (the entry count sizes the outputs)."""
+    dev = current_device()
+    obj = to_device(objects, torch.float64, dev).contiguous()
+    if obj.dim() != 3 or obj.shape[-1] != 5:
+        raise ValueError("objects must be [B, n, 5]")
+    batch, n = int(obj.shape[0]), int(obj.shape[1])
+    nb = to_device(nbox, torch.int32, dev) if nbox is not None else None
+    sd = to_device(np.asarray(src_dims, np.float64).reshape(batch, 2) if not isinstance(src_dims, torch.Tensor) else src_dims,
+                   torch.float64, dev).contiguous()
+    offsets = torch.empty((batch + 1,), dtype=torch.int64, device=dev)
+
+    def call(capacity, idx, val):
+        _capi.check(_capi.lib().dh_fcos_sparse_encode(
+            _capi.handle(dev.index), obj.data_ptr(), nb.data_ptr() if nb is not None else None, sd.data_ptr(), batch, max(n, 1),
+            int(img_dims[0]), int(img_dims[1]), int(num_scale), capacity, idx.data_ptr() if idx is not None else None,
+            val.data_ptr() if val is not None else None, offsets.data_ptr(), stream_ptr(stream)), "dh_fcos_sparse_encode")
+    if batch == 0 or n == 0:
+        return (torch.empty((0, 4), dtype=torch.int32, device=dev), torch.empty((0,), dtype=torch.float32, device=dev),
+                torch.zeros((batch + 1,), dtype=torch.int64, device=dev))
+    call(0, None, None)
+    nnz = int(offsets[-1].item())
+    indices = torch.empty((nnz, 4), dtype=torch.int32, device=dev)
+    values = torch.empty((nnz,), dtype=torch.float32, device=dev)
+    if nnz:
+        call(nnz, indices, values)
+    return indices, values, offsets
+
+
+SCORE_MODES = {"cls": 0, "cls_cen": 1, "map": 2, "map_cen": 3}  # DH_FCOS_SCORE_*
+
+
+def score_mode(center):
+    """The reference's `center` flag (False / True) or one of SCORE_MODES ("map", "map_cen": the input is a target map)."""
+    if isinstance(center, str):
+        if center not in SCORE_MODES:
+            raise ValueError("score mode must be one of %s" % sorted(SCORE_MODES))
+        return SCORE_MODES[center]
+    return 1 if center else 0
+
+
+@uses_stream
 def decode_batch(head_outputs, num_classes, img_pad, strides=None, center=False, stream=None):
     """FCOS/infer_fcos.py:35-57 for a batch: per-level heads [B, Hl, Wl, C+5] -> (boxes [B, N, 4], scores [B, N, C])."""
     strides = list(DEFAULT_STRIDES if strides is None else strides)
@@ -211,7 +259,7 @@ def decode_batch(head_outputs, num_classes, img_pad, strides=None, center=False,
     scores = torch.empty((batch, n, num_classes), dtype=torch.float32, device=dev)
     _capi.check(_capi.lib().dh_fcos_decode(
         _capi.handle(dev.index), _capi.ptr_array([h.data_ptr() for h in heads]), batch, int(img_pad[0]), int(img_pad[1]),
-        len(strides), _capi.int_array(strides), int(num_classes), 1 if center else 0, boxes.data_ptr(), scores.data_ptr(),
+        len(strides), _capi.int_array(strides), int(num_classes), score_mode(center), boxes.data_ptr(), scores.data_ptr(),
         stream_ptr(stream)), "dh_fcos_decode")
     return boxes, scores
 
@@ -237,10 +285,34 @@ def detect_batch(head_outputs, num_classes, img_pad, center=False, iou_thresh=0.
     cand = torch.empty((batch, len(strides) * k, 6), dtype=torch.float32, device=dev) if with_candidates else None
     _capi.check(_capi.lib().dh_fcos_detect(
         _capi.handle(dev.index), _capi.ptr_array([h.data_ptr() for h in heads]), batch, int(img_pad[0]), int(img_pad[1]),
-        len(strides), _capi.int_array(strides), int(num_classes), 1 if center else 0, float(iou_thresh), float(cls_thresh),
+        len(strides), _capi.int_array(strides), int(num_classes), score_mode(center), float(iou_thresh), float(cls_thresh),
         int(max_detections), t, int(pre_nms_topk), boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(), valid.data_ptr(),
         cand.data_ptr() if cand is not None else None, stream_ptr(stream)), "dh_fcos_detect")
     return (boxes, scores, classes, valid, cand) if with_candidates else (boxes, scores, classes, valid)
+
+
+@uses_stream
+def ground_truth_detections(img_labels, num_classes, image_shapes, img_rows=384, img_cols=384, center=True, iou_thresh=0.75,
+                            cls_thresh=0.75, strides=None, stream=None):
+    """The computation inside `show_heatmap` (FCOS/train_fcos_center_voc.py:13-121, the copies in the other FCOS training
+    scripts) for a batch: target maps `img_labels` (per level [B, Hl, Wl, C+5], what `format_data` returns) are sent back
+    through the detector -- boxes from channels 0..3, score sqrt(class * centerness) (`center=True`) or the class channel,
+    combined NMS at 0.75 / 0.75 with 100 / 100 caps -- and come out as the rectangles the reference draws: `(x1, y1, w, h)`
+    in source-image pixels `[B, 100, 4]`, scores `[B, 100]`, valid `[B]`.  `image_shapes` `[B, 2]` are the source images'
+    `.shape[:2]`.  Up to 16384 / n_levels entries per level pass the score threshold into the NMS (a target map has a few
+    per box).  Heat-map rendering (tf.image.resize + matplotlib) stays with the caller."""
+    strides = list(DEFAULT_STRIDES if strides is None else strides)
+    dev = current_device()
+    maps = _as_batched(img_labels, dev)
+    batch = int(maps[0].shape[0])
+    boxes, scores, _, valid = detect_batch(maps, num_classes, (img_rows, img_cols), "map_cen" if center else "map", iou_thresh,
+                                           cls_thresh, 100, 100, pre_nms_topk=16384 // len(strides), strides=strides)
+    shp = np.asarray(image_shapes, np.float64).reshape(batch, 2)
+    ratios = to_device(np.stack([shp[:, 0] / img_rows, shp[:, 1] / img_cols], axis=1).astype(np.float32), torch.float32, dev)
+    rect = torch.empty_like(boxes)
+    _capi.check(_capi.lib().dh_fcos_rectangles(_capi.handle(dev.index), boxes.data_ptr(), valid.data_ptr(), ratios.data_ptr(), batch,
+                                               int(boxes.shape[1]), rect.data_ptr(), stream_ptr(stream)), "dh_fcos_rectangles")
+    return rect, scores, valid
 
 
 def image_detections(image, model, num_classes, center=False, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,

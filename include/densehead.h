@@ -181,6 +181,31 @@ int dh_format_detections(dh_handle_t h, const float* rows /*[dev] [B,n,6]*/, con
                          const float* ratios /*[dev] [B,2]*/, int batch, int n, float* out_boxes /*[dev] [B,n,4]*/,
                          float* out_scores /*[dev] [B,n]*/, int32_t* out_labels /*[dev] [B,n]*/, void* stream);
 
+/* The offline COCO -> sparse FCOS target formatter, /format_COCO_annotations_fcos.py:66-183 (one call = a batch of
+ * images of the script's per-image loop).  boxes rows are (x_lower, y_lower, box_width, box_height, label) in SOURCE
+ * pixels, float64 like the script's table (the truncations decide indices), label = the script's 1-based class index;
+ * src_dims[b] = the source image's (img_width, img_height); (img_width, img_height) = the canvas (the script: 448, 448),
+ * scale limits int(min(canvas) / 2^x) (:49-56).  Per object, per footprint cell (objects in input order, cells x-major
+ * as np.nonzero walks them) seven COO entries: indices [y, x, scale, k] with values (b, t, l, r, centerness, 1) for
+ * k = 0..5 and [y, x, scale, label + 4] = 1 (the script writes this one five long, :171 -- the duplicated scale is
+ * dropped).  Values are float32 (centerness computed in float64, :8-11).  Overlapping objects all emit (`tmp_mask` is
+ * never written, :91).
+ * out_offsets [B+1] (int64): entries of image b are [out_offsets[b], out_offsets[b+1]).  With out_indices ==
+ * out_values == NULL only the offsets are computed (size the buffers from out_offsets[B], then call again); entries
+ * at or beyond `capacity` are not written. */
+int dh_fcos_sparse_encode(dh_handle_t h, const double* boxes /*[dev] [B,max_boxes,5]*/, const int32_t* nbox /*[dev] [B] or NULL*/,
+                          const double* src_dims /*[dev] [B,2]*/, int batch, int max_boxes, int img_width, int img_height,
+                          int num_scale, long long capacity, int32_t* out_indices /*[dev] [capacity,4] or NULL*/,
+                          float* out_values /*[dev] [capacity] or NULL*/, long long* out_offsets /*[dev] [B+1]*/, void* stream);
+
+/* The tail of show_heatmap (FCOS/train_fcos_center_voc.py:92-121): combined-NMS boxes [B,T,4] (y1, x1, y2, x2) of
+ * target maps decoded by dh_fcos_detect(center = DH_FCOS_SCORE_MAP[_CEN]) -> the rectangles it draws, (x1, y1, w, h):
+ * the columns are multiplied by ratios[b] = (w_ratio, h_ratio) in the reference's order (0 and 2 by w_ratio, 1 and 3
+ * by h_ratio, float32 like the TF multiply), swapped to (x1, y1, x2, y2), x1 / y1 <= 0 become 0, w = x2 - x1,
+ * h = y2 - y1.  Slots >= valid[b] are zero. */
+int dh_fcos_rectangles(dh_handle_t h, const float* boxes /*[dev] [B,T,4]*/, const int32_t* valid /*[dev] [B]*/,
+                       const float* ratios /*[dev] [B,2]*/, int batch, int t, float* out_rect /*[dev] [B,T,4]*/, void* stream);
+
 /* ---- losses --------------------------------------------------------------------------------- */
 
 /* Channel layout of a row: [0, reg_ch) box regression, then one centerness channel if cen_mode != 0,
@@ -327,8 +352,21 @@ int dh_prediction_to_corners(dh_handle_t h, const float* pred /*[dev]*/, int bat
                              int ch_in, int mode, float stride, float d0, float d1,
                              const float* scales /*[host] [sub], mode 3*/, float* out /*[dev]*/, void* stream);
 
+/* How dh_fcos_decode / dh_fcos_detect score a (location, class) pair (their `center` argument).
+ *   DH_FCOS_SCORE_CLS      sigmoid(class logit)                                      FCOS/infer_fcos.py:50-51
+ *   DH_FCOS_SCORE_CLS_CEN  sigmoid(centerness logit) * sigmoid(class logit)          FCOS/infer_fcos.py:44-48
+ *   DH_FCOS_SCORE_MAP      the class channel as it is: the input is a TARGET map ([B,Hl,Wl,C+5] as dh_fcos_encode writes
+ *                          it) sent back through the detector -- show_heatmap(center=False),
+ *                          FCOS/train_fcos_center_voc.py:63-66
+ *   DH_FCOS_SCORE_MAP_CEN  sqrt(class channel * centerness channel), product and root in float64 like NumPy, rounded to
+ *                          float32 where combined NMS takes it -- show_heatmap(center=True), :58-62 */
+#define DH_FCOS_SCORE_CLS 0
+#define DH_FCOS_SCORE_CLS_CEN 1
+#define DH_FCOS_SCORE_MAP 2
+#define DH_FCOS_SCORE_MAP_CEN 3
+
 /* FCOS decode front end (FCOS/infer_fcos.py:35-57): per-level heads [B,Hl,Wl,C+5] -> boxes [B,N,4] and
- * scores [B,N,C] = sigmoid(class) (times sigmoid(centerness) when center != 0), levels concatenated. */
+ * scores [B,N,C] (DH_FCOS_SCORE_* mode `center`), levels concatenated. */
 int dh_fcos_decode(dh_handle_t h, const float* const* pred_levels /*[host] n_levels [dev] ptrs*/, int batch,
                    int pad_h, int pad_w, int n_levels, const int32_t* strides /*[host]*/, int num_classes, int center,
                    float* boxes /*[dev] [B,N,4]*/, float* scores /*[dev] [B,N,C]*/, void* stream);
@@ -369,8 +407,9 @@ int dh_nms(dh_handle_t h, const float* dets /*[dev]*/, const int32_t* n_valid /*
 /* Whole-image pipelines: head outputs in, final detections out, in one call (all intermediates live in the handle's
  * scratch; nothing synchronises with the host).
  *
- * dh_fcos_detect = image_detections of FCOS/infer_fcos.py:27-62.  Scores are sigmoid(class) (times
- * sigmoid(centerness) when center != 0); per level the pre_nms_topk best (location, class) pairs with score > cls_thr
+ * dh_fcos_detect = image_detections of FCOS/infer_fcos.py:27-62.  Scores follow the DH_FCOS_SCORE_* mode `center`
+ * (with DH_FCOS_SCORE_MAP[_CEN], iou_thr = cls_thr = 0.75 and target maps as input it is the round trip of show_heatmap,
+ * FCOS/train_fcos_center_voc.py:54-90); per level the pre_nms_topk best (location, class) pairs with score > cls_thr
  * go to the per-class NMS with caps (see DH_NMS_PER_CLASS).  Outputs have the layout of
  * tf.image.combined_non_max_suppression: boxes [B,T,4], scores [B,T], classes [B,T] zero padded, valid [B], with
  * T = max_total.  pre_nms_topk >= the number of passing pairs reproduces the reference (which has no top-k).

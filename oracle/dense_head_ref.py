@@ -945,7 +945,8 @@ def combined_nms(boxes, scores, max_output_size_per_class, max_total_size,
     `pad_per_class=False`).  boxes `[N, 4]` (y1, x1, y2, x2), scores `[N, C]`.
     Per class: candidates with `score > score_threshold`, score-descending (ties: lower index
     first), greedy suppress `IoU > iou_threshold`, at most `max_output_size_per_class`; then the
-    union over classes is sorted by score (ties: lower class, then earlier pick) and truncated to
+    union over classes is sorted by score (ties: lower box index, then lower class -- TensorFlow's own order among
+    equal scores is unspecified; target maps sent back through the detector produce nothing but ties) and truncated to
     `max_total_size`.  Returns zero-padded (boxes `[T,4]`, scores `[T]`, classes `[T]`, valid)
     and the flat candidate index (box*C + class) of every kept detection."""
     b, s = _f32(boxes), _f32(scores)
@@ -972,13 +973,13 @@ def combined_nms(boxes, scores, max_output_size_per_class, max_total_size,
                     break
             if ok:
                 kept.append(int(i))
-        picked += [(-float(s[i, k]), k, r, i) for r, i in enumerate(kept)]
+        picked += [(-float(s[i, k]), i, k) for i in kept]
     picked.sort()
     picked = picked[:max_total_size]
     t = max_total_size
     ob, os_, oc = np.zeros((t, 4), np.float32), np.zeros(t, np.float32), np.zeros(t, np.float32)
     flat = np.full(t, -1, dtype=np.int64)
-    for r, (negs, k, _, i) in enumerate(picked):
+    for r, (negs, i, k) in enumerate(picked):
         ob[r], os_[r], oc[r], flat[r] = b[i], -negs, k, i * c + k
     return ob, os_, oc, len(picked), flat
 
@@ -1045,6 +1046,91 @@ def fcos_image_detections(head_outputs, num_classes, center=False, iou_thresh=0.
     """FCOS/infer_fcos.py:27-62 with the third-party NMS replaced by `combined_nms`."""
     boxes, scores = fcos_decode_scores(head_outputs, num_classes, strides, center)
     return combined_nms(boxes, scores, max_detections, max_total_size, iou_thresh, cls_thresh)
+
+
+def fcos_ground_truth_detections(img_labels, num_classes, image_shape, img_rows=384, img_cols=384, center=True,
+                                 strides=None):
+    """The computation inside `show_heatmap`, FCOS/train_fcos_center_voc.py:13-121 (heat-map rendering left out): the
+    target maps of ONE image, `img_labels[level]` `[Hl, Wl, C+5]`, decoded like predictions -- boxes
+    `prediction_to_corners(map[..., :4], stride)` (:54-55), scores `sqrt(class * centerness)` in the maps' float64
+    (:58-63) or the class channel (:64-66), combined NMS with 100 / 100 caps at IoU 0.75 / score 0.75 (:86-88, float32 from
+    there on), boxes times `[w_ratio, h_ratio, w_ratio, h_ratio]` (:91-94, a float32 TF multiply), `swap_xy`, then
+    per box x1 / y1 <= 0 -> 0, `w = x2 - x1`, `h = y2 - y1` (:103-116).  Returns (rectangles `[k, 4]` (x1, y1, w, h),
+    scores `[k]`), float32.  PARITY UNPINNED where `combined_nms` is."""
+    strides = list(DEFAULT_STRIDES if strides is None else strides)
+    w_ratio, h_ratio = image_shape[0] / img_rows, image_shape[1] / img_cols
+    bl, sl = [], []
+    for n, m in enumerate(img_labels):
+        m = np.asarray(m, dtype=np.float64)
+        bl.append(fcos_prediction_to_corners(_f32(m[..., :4]), strides[n]).reshape(-1, 4))
+        flat = m.reshape(-1, num_classes + 5)
+        sl.append(np.sqrt(flat[:, 5:] * flat[:, 4:5]) if center else flat[:, 5:])
+    ob, os_, _, valid, _ = combined_nms(np.concatenate(bl), np.concatenate(sl), 100, 100, 0.75, 0.75)
+    det = _f32(ob[:valid]) * np.array([w_ratio, h_ratio, w_ratio, h_ratio], dtype=np.float32)
+    x1, y1, x2, y2 = det[:, 1].copy(), det[:, 0].copy(), det[:, 3], det[:, 2]
+    x1[x1 <= 0] = 0
+    y1[y1 <= 0] = 0
+    return np.stack([x1, y1, x2 - x1, y2 - y1], axis=1).astype(np.float32).reshape(-1, 4), _f32(os_[:valid])
+
+
+# --------------------------------------------------------------------------------------
+# f-4  the offline COCO -> sparse FCOS target formatter (/format_COCO_annotations_fcos.py:66-183)
+# --------------------------------------------------------------------------------------
+def fcos_sparse_scales(img_dims, num_scale=5):
+    """`tmp_scale` of the script (:49-56): `int(min(img_dims) / 2**x)`, ascending."""
+    return [int(min(img_dims) / (2 ** x)) for x in range(num_scale)][::-1]
+
+
+def fcos_sparse_format(objects, src_dims, img_dims=(448, 448), num_scale=5):
+    """One image of /format_COCO_annotations_fcos.py:66-183.  `objects` `[n, 5]` float64 rows (x_lower, y_lower,
+    box_width, box_height, label) in SOURCE-image pixels (`label` is what the script looks up through its label tables,
+    1-based: index 0 is "objectness"), `src_dims` = the source image's (img_width, img_height).
+    Per object: the box is brought to the `img_dims` canvas by float64 division with the ratios (:86-87, :98-99), the scale
+    slot is the first one both sides are strictly below (:101-123), the footprint is the integer rectangle
+    `[int(x_lower / w_ratio), int(x_low + width)) x [int(y_lower / h_ratio), int(y_low + height))` (:126-131) cut by
+    NumPy's slice rules against an `[img_width, img_height]` array (:147-149), walked x-major (`np.nonzero`, :151).
+    `tmp_mask` is never written (:91, :151), so overlapping objects all emit.  Each cell emits, in this order, the six
+    entries `[y, x, scale, k]` = (b, t, l, r, centerness, 1) for k = 0..5 with `b = y - y_low`, `t = y_upp - y`,
+    `l = x - x_low`, `r = x_upp - x`, `centerness = sqrt(min(l,r)/max(l,r)) * sqrt(min(b,t)/max(b,t))` in float64 (:8-11,
+    :158-168), then the class entry, value 1, at `[y, x, scale, label + 4]` -- the script writes that index five long,
+    `[y, x, scale, scale, label + 4]` (:171), which `tf.sparse.SparseTensor` cannot take; the duplicate is dropped here
+    (documented deviation).  Returns (indices `[nnz, 4]` int32, values `[nnz]` float32 -- the script's mixed int / float64
+    list rounded once) and the `dense_shape` the script states (:76-78: `[img_h / 8, img_w / 8, num_scale, n_classes + 4]`
+    is the caller's business: it needs the label table)."""
+    img_w, img_h = int(img_dims[0]), int(img_dims[1])
+    scales = fcos_sparse_scales(img_dims, num_scale)
+    w_ratio, h_ratio = np.float64(src_dims[0]) / img_w, np.float64(src_dims[1]) / img_h
+    idx, val = [np.zeros((0, 4), np.int32)], [np.zeros(0, np.float32)]
+    for o in np.asarray(objects, dtype=np.float64).reshape(-1, 5):
+        width, height = o[2] / w_ratio, o[3] / h_ratio
+        if width < 0 or height < 0:
+            continue
+        sc = num_scale - 1
+        for k in range(num_scale - 1):
+            if width < scales[k] and height < scales[k]:
+                sc = k
+                break
+        x_low = int(o[0] / w_ratio)
+        x_upp = int(x_low + width)
+        y_low = int(o[1] / h_ratio)
+        y_upp = int(y_low + height)
+        xs = np.arange(img_w)[x_low:x_upp]
+        ys = np.arange(img_h)[y_low:y_upp]
+        if len(xs) == 0 or len(ys) == 0:
+            continue
+        x, y = [a.reshape(-1) for a in np.meshgrid(xs, ys, indexing="ij")]  # x-major
+        l, r, b, t = x - x_low, x_upp - x, y - y_low, y_upp - y
+        with np.errstate(invalid="ignore", divide="ignore"):
+            c = np.sqrt(np.minimum(l, r) / np.maximum(l, r)) * np.sqrt(np.minimum(b, t) / np.maximum(b, t))
+        n = len(x)
+        entry = np.zeros((n, 7, 4), np.int64)
+        entry[:, :, 0], entry[:, :, 1], entry[:, :, 2] = y[:, None], x[:, None], sc
+        entry[:, :6, 3] = np.arange(6)
+        entry[:, 6, 3] = int(o[4]) + 4
+        v = np.stack([b, t, l, r, c, np.ones(n), np.ones(n)], axis=1)
+        idx.append(entry.reshape(-1, 4).astype(np.int32))
+        val.append(v.reshape(-1).astype(np.float32))
+    return np.concatenate(idx), np.concatenate(val)
 
 
 # --------------------------------------------------------------------------------------

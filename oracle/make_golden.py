@@ -430,6 +430,52 @@ def hourglass4(tf):
     np.savez_compressed(os.path.join(OUT, "hourglass4.npz"), **d)
 
 
+SPARSE_LABELS = [(1, "person"), (2, "bicycle"), (3, "car"), (7, "zebra"), (9, "apple")]
+SPARSE_OBJECTS = [  # filename, img_width, img_height, category id, x_lower, y_lower, box_width, box_height
+    ("a.jpg", 640, 480, 3, 100.25, 50.5, 30.0, 45.75), ("a.jpg", 640, 480, 1, 300.0, 200.0, 120.0, 100.0),
+    ("a.jpg", 640, 480, 7, 301.5, 201.25, 40.0, 30.0),                       # overlaps the previous one: both emit
+    ("a.jpg", 640, 480, 9, 600.0, 440.0, 90.0, 90.0),                        # runs off the canvas: cut by the slice
+    ("b.jpg", 500, 375, 7, 10.2, 20.7, 30.3, 15.1), ("b.jpg", 500, 375, 2, 480.2, 360.7, 30.3, 35.1),
+    ("b.jpg", 500, 375, 1, 100.0, 100.0, 31.25, 23.4375),                    # exactly 28 wide on the canvas: NOT < 28, slot 1
+    ("b.jpg", 500, 375, 3, 50.0, 50.0, -4.0, 10.0),                          # negative width: skipped
+    ("b.jpg", 500, 375, 9, 200.0, 200.0, 0.5, 0.5),                          # empty footprint
+    ("c.jpg", 448, 448, 2, -6.0, 10.0, 3.0, 20.0),                           # negative corner: NumPy slices wrap around
+    ("c.jpg", 448, 448, 3, -30.0, -40.0, 60.0, 70.0), ("c.jpg", 448, 448, 1, 20.0, 30.0, 230.0, 60.0),
+    ("d.jpg", 896, 224, 9, 100.0, 20.0, 500.0, 150.0),                       # slot 4 (the last, unconditional)
+]
+
+
+def sparse_fcos(tf):
+    """The offline formatter /format_COCO_annotations_fcos.py run unmodified on a small annotation table
+    (oracle/ref_loader.offline_fcos_formatter).  Per image: the kernel-side inputs (rows (x_lower, y_lower, box_width,
+    box_height, label) with the label the script's tables produce, source dims), the number of entries, and either the
+    entries themselves or -- for the image with a slot-4 box -- their SHA-256."""
+    import hashlib
+    import pandas as pd
+    labels = pd.DataFrame(SPARSE_LABELS, columns=["id", "name"])
+    objects = pd.DataFrame(SPARSE_OBJECTS, columns=["filename", "img_width", "img_height", "id", "x_lower", "y_lower",
+                                                    "box_width", "box_height"])
+    out = R.offline_fcos_formatter(objects, labels)
+    names = ["objectness"] + sorted(labels["name"])
+    d = {"files": np.array([f for f, _, _ in out])}
+    for f, dims, sp in out:
+        key = f.split(".")[0]
+        sub = objects[objects.filename == f]
+        lab = [names.index(labels[labels.id == i].iloc[0]["name"]) for i in sub.id]
+        d[key + "_objects"] = np.column_stack([sub.x_lower, sub.y_lower, sub.box_width, sub.box_height, lab]).astype(np.float64)
+        d[key + "_src_dims"] = np.array([sub.img_width.iloc[0], sub.img_height.iloc[0]], np.float64)
+        d[key + "_img_dims"] = np.array(dims)
+        d[key + "_dense_shape"] = np.array(sp.dense_shape)
+        assert all(len(i) == 4 or (len(i) == 5 and i[2] == i[3]) for i in sp.indices)
+        idx = np.array([i if len(i) == 4 else [i[0], i[1], i[2], i[4]] for i in sp.indices], np.int32)  # (:171: one index too many)
+        val = np.array([float(v) for v in sp.values], np.float32)
+        d[key + "_nnz"] = np.array(len(val))
+        if len(val) <= 200000:
+            d[key + "_indices"], d[key + "_values"] = idx, val
+        d[key + "_sha"] = np.array(hashlib.sha256(idx.tobytes() + val.tobytes()).hexdigest())
+    np.savez_compressed(os.path.join(OUT, "sparse_fcos.npz"), **d)
+
+
 def main(out_dir=None):
     """Rewrite every fixture (into `out_dir` when given: tests/test_make_golden.py runs the whole recipe into a
     temporary directory and compares the bytes of the arrays with the committed files)."""
@@ -440,7 +486,7 @@ def main(out_dir=None):
         OUT = out_dir
     os.makedirs(OUT, exist_ok=True)
     tf = R.tf()
-    for fn in (kat, fcos_family, retina, centernet, losses, grad, decode_nms, prep, hourglass4):
+    for fn in (kat, fcos_family, retina, centernet, losses, grad, decode_nms, prep, hourglass4, sparse_fcos):
         fn(tf)
         print("wrote", fn.__name__)
     for f in sorted(os.listdir(OUT)):

@@ -148,3 +148,50 @@ def hourglass_inline_encoder(samples, n_classes, raw_dims, img_dims, pad_dims):
     finally:
         _leave(state)
     return ns["img_boxes"]
+
+
+def offline_fcos_formatter(objects, labels):
+    """Run the reference's offline COCO -> sparse FCOS target script, `/format_COCO_annotations_fcos.py`, UNMODIFIED from
+    where it lies.  It is a top-level script that reads two CSV files from a Windows path: `pandas.read_csv` is patched
+    for the duration to hand it `objects` (columns filename, img_width, img_height, id, x_lower, y_lower, box_width,
+    box_height) and `labels` (columns id, name); `tf.sparse.SparseTensor` is a recorder (the script appends one 5-long
+    index per cell among the 4-long ones, :166, so the real constructor would reject its input); `print` is silenced and
+    `open` refuses to write.  The script's last statements index `train_objects[1]` with one image scale configured
+    (:192) -- an IndexError after all the work is done, caught here.  Returns `train_objects[0]`: a list of
+    (filename, (img_width, img_height), recorder) with `.indices`, `.values`, `.dense_shape` as the script built them."""
+    import pandas as pd
+
+    class SparseRecorder:
+        def __init__(self, indices, values, dense_shape):
+            self.indices, self.values, self.dense_shape = indices, values, dense_shape
+
+    def read_csv(path, *a, **k):
+        return (labels if str(path).endswith("labels.csv") else objects).copy()
+
+    def no_open(*a, **k):
+        raise PermissionError("the offline formatter must not touch the file system here")
+
+    path = os.path.join(REF_ROOT, "format_COCO_annotations_fcos.py")
+    with open(path) as f:
+        code = compile(f.read(), path, "exec")
+    stub = tf()
+    saved_read, had_sparse = pd.read_csv, getattr(stub, "sparse", None)
+    state = _enter("FCOS")
+    ns = {"__name__": "_ref_offline_fcos", "print": lambda *a, **k: None, "open": no_open}
+    try:
+        import types
+        pd.read_csv = read_csv
+        stub.sparse = types.SimpleNamespace(SparseTensor=SparseRecorder)
+        try:
+            exec(code, ns)
+        except IndexError:
+            pass
+    finally:
+        pd.read_csv = saved_read
+        if had_sparse is None:
+            del stub.sparse
+        else:
+            stub.sparse = had_sparse
+        _leave(state)
+    return ns["train_objects"][0]
+

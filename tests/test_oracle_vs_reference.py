@@ -115,3 +115,28 @@ def test_label_prep_against_reference_utils():
     assert _eq(O.convert_to_corners(raw), utils.convert_to_corners(tf.constant(raw)))
     _, fl = dp.random_flip_horizontal(tf.constant(np.zeros((2, 2, 3), np.float32)), tf.constant(raw), p_flip=1.0)
     assert _eq(O.flip_boxes_horizontal(raw), fl)
+
+
+def test_offline_sparse_formatter_random():
+    """/format_COCO_annotations_fcos.py run unmodified on a random annotation table (oracle/ref_loader.offline_fcos_formatter)."""
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(11)
+    labels = pd.DataFrame([(3, "cat"), (5, "bus"), (8, "kite"), (13, "oven")], columns=["id", "name"])
+    names = ["objectness"] + sorted(labels["name"])
+    rows = []
+    for f, (w, h) in (("p.jpg", (640, 427)), ("q.jpg", (333, 500)), ("r.jpg", (448, 448))):
+        for _ in range(5):
+            rows.append((f, w, h, int(rng.choice(labels["id"])), round(float(rng.uniform(-5, w * 0.9)), 2), round(float(rng.uniform(-5, h * 0.9)), 2),
+                         round(float(rng.uniform(1, 90)), 2), round(float(rng.uniform(1, 90)), 2)))
+    objects = pd.DataFrame(rows, columns=["filename", "img_width", "img_height", "id", "x_lower", "y_lower", "box_width", "box_height"])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out = R.offline_fcos_formatter(objects, labels)
+    assert len(out) == 3
+    for f, dims, sp in out:
+        sub = objects[objects.filename == f]
+        lab = [names.index(labels[labels.id == i].iloc[0]["name"]) for i in sub.id]
+        idx, val = O.fcos_sparse_format(np.column_stack([sub.x_lower, sub.y_lower, sub.box_width, sub.box_height, lab]),
+                                        (sub.img_width.iloc[0], sub.img_height.iloc[0]), dims)
+        ref_idx = np.array([i if len(i) == 4 else [i[0], i[1], i[2], i[4]] for i in sp.indices], np.int32).reshape(-1, 4)
+        ref_val = np.array([float(v) for v in sp.values], np.float32)
+        assert np.array_equal(idx, ref_idx) and np.array_equal(val, ref_val, equal_nan=True)
