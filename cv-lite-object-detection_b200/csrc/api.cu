@@ -184,7 +184,7 @@ int dh_set_option(dh_handle_t h, int option, int value) {
             h->allreduce_mode = value;
             return DH_OK;
         case DH_OPT_FUSED_TAIL:
-            DH_CHECK_ARG(value == 0 || value == 1, "DH_OPT_FUSED_TAIL must be 0 or 1");
+            DH_CHECK_ARG(value >= 0 && (value >> 1) <= 5, "DH_OPT_FUSED_TAIL must be 0 or 1 (+ 2 * log2 of the spans of a chunk's last tile, 1..5)");
             h->fused_tail = value;
             return DH_OK;
         case DH_OPT_FUSED_MAX_CHUNK:

@@ -189,6 +189,8 @@ __device__ __forceinline__ float cen_l1_zero(float x, float delta) {
 constexpr int kTraceSlots = 12;  // dh_set_trace: longs per CTA
 constexpr int kMaxChunkTiles = 16;  // tiles (of 256 rows) per scheduler chunk at most (launch_fused_g)
 constexpr int kMaxSegments = kMaxChunkTiles;  // ... so a chunk meets at most as many maps
+// A tile (256 rows) is streamed as 2 spans; the chunk's last tiles as 4, 4, 8 and up to 32 (see span_plan)
+constexpr int kMaxSpans = (kMaxChunkTiles - 4) * 2 + 4 + 4 + 8 + 32;
 struct FusedSmemLayout {
     int rec_off, raw_off, cand_off, seg_off, run_off, misc_off, args_off, total;
 };
@@ -207,9 +209,9 @@ struct SegLists {
     unsigned short* rowlist;  // [kMaxPairs] the chunk rows that have pairs, ascending (scan_rows)
     int* tile_tab;            // [kMaxChunkTiles][4] per tile of the chunk: map, first row, segment, rows
     float* span_sum;          // [kMaxSpans][2] the label-free sums {class, centerness} of each span of the chunk
-    int* span_ctr;            // [1] next span to hand out (zero between chunks)
+    int2* span_tab;           // [kMaxSpans] the chunk's spans: {tile of the chunk, first unit | units << 16} (build_tile_tab)
+    int* span_ctr;            // [4] [0] next span to hand out (zero between chunks), [1] spans of the chunk
 };
-constexpr int kMaxSpans = kMaxChunkTiles * 4;  // a tile (256 rows) is streamed as 2 spans of 128 rows or 4 of 64
 constexpr uint32_t kNoPair = 0xffffu;
 template <class P>
 __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
@@ -218,7 +220,7 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     l.raw_off = (static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127;
     l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
     l.seg_off = l.cand_off;
-    l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 4 + 32 + 16 + 32) + 16;  // SegLists
+    l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 4 + 32 + 16) + kMaxSpans * 16 + 16;  // SegLists
     l.misc_off = l.run_off + DH_THREADS * kRunCap * 2;  // resolve_pass: the boxes of the row a lane resolves
     l.args_off = l.misc_off + 512;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
@@ -269,11 +271,10 @@ __device__ __forceinline__ void mask_skip(float4& x, int c0, int ch, int n_skip)
 // range -- `vpr` is then the row length in floats, c4 the channel of the item's first element, `n_skip` the channels
 // that are not class logits (the centerness channel is added by a separate pass over the rows, stream_cen).
 template <int kCls, bool kGrad, int U, bool kAny = false>
-__device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int nrows, int vpr, int c4, int step,
+__device__ __forceinline__ void stream_vec(const float* __restrict__ p, float* __restrict__ gout, int n_items, int vpr, int c4, int step,
                                            int lane, float gamma, float gscale, StreamAcc& a, int n_skip = 4) {
     const float4* __restrict__ ptr = reinterpret_cast<const float4*>(p) + lane;
     float4* __restrict__ gptr = reinterpret_cast<float4*>(gout) + lane;
-    const int n_items = kAny ? (nrows * vpr) >> 2 : nrows * vpr;
     const int n_mine = (n_items - lane + 31) >> 5;  // items of this lane (may be <= 0 in a ragged tile)
     int k = 0;
     if constexpr (kCls == 1) {
@@ -507,7 +508,8 @@ __device__ __forceinline__ SegLists seg_lists(unsigned char* base, int box_cap) 
     L.rowbits = L.pairs + kMaxPairs;
     L.tile_tab = reinterpret_cast<int*>(L.rowbits + kMaxChunkTiles * 8);
     L.span_sum = reinterpret_cast<float*>(L.tile_tab + kMaxChunkTiles * 4);
-    L.span_ctr = reinterpret_cast<int*>(L.span_sum + kMaxSpans * 2);
+    L.span_tab = reinterpret_cast<int2*>(L.span_sum + kMaxSpans * 2);
+    L.span_ctr = reinterpret_cast<int*>(L.span_tab + kMaxSpans);
     L.next = reinterpret_cast<unsigned short*>(L.span_ctr + 4);
     L.rowlist = L.next + kMaxPairs;
     L.box = L.rowlist + kMaxPairs;
@@ -537,6 +539,48 @@ __device__ __forceinline__ void build_tile_tab(const LossArgs<P>& a, const SegLi
         L.tile_tab[threadIdx.x * 4 + 0] = cur.m, L.tile_tab[threadIdx.x * 4 + 1] = r0, L.tile_tab[threadIdx.x * 4 + 2] = seg_t;
         L.tile_tab[threadIdx.x * 4 + 3] = min(a.tt.rows_per_tile, a.tt.maps[cur.m].rows - r0);
     }
+}
+
+// The spans the warps take from the chunk's counter, coarse first and ever finer towards the chunk's end: a warp streams
+// at an eighth of the CTA's share of the HBM rate, so when the counter runs dry the warps wait for the one that took the
+// last span for about half a span's time -- 15 us per chunk with 128-row spans, which the few chunks per CTA of a small
+// batch cannot hide.  Tile e (counted from the chunk's END) is cut into 2 spans for e >= 4 and into 2^min(fine, ...) spans
+// nearer the end: 4 for e = 2, 3, 8 for e = 1, 32 for the last tile.  Measured (B200, 32 / 64 COCO images): fine = 2 -- the
+// last four tiles in 64-row spans -- 178 / 302 us; every tile in 2 spans 185 / 308; down to single load batches (fine = 5)
+// 185 / 309: a span's fixed cost (the counter, two warp reductions, an empty load pipeline) eats what the shorter wait
+// gives.  A chunk of one to four tiles (the fine tiers that end a launch) is cut into at least 24 spans whatever `fine`
+// says: with four 64-row spans to a tile half of the warps of a one-tile chunk had nothing to take.
+// A span is measured in `unit`s: 128-bit items of the tile when
+// the rows are whole float4s (then every span but a tile's last is a whole number of load batches of `batch` items: no
+// ragged round trip), else rows (multiples of 32).  Thread t writes the spans of tile t; returns nothing -- span_ctr[1].
+__device__ __forceinline__ int spans_of_tile(int e, int n_tiles, int units, int batch, int fine, int& per_span) {
+    int shift = min(fine, e >= 4 ? 1 : (e >= 2 ? 2 : (e == 1 ? 3 : 5)));  // 2, 4, 8, 32 spans wanted
+    while (shift < 5 && (n_tiles << shift) < 24) ++shift;                // a short chunk: three spans per warp all the same
+    const unsigned share = (static_cast<unsigned>(units) + (1u << shift) - 1u) >> shift;
+    per_span = static_cast<int>((share + batch - 1u) / static_cast<unsigned>(batch)) * batch;
+    return per_span > 0 ? static_cast<int>((static_cast<unsigned>(units) + per_span - 1u) / static_cast<unsigned>(per_span)) : 0;
+}
+// (called by every thread of warp 0, between the chunk-end barriers: it is on every warp's critical path -- one thread per
+// tile, two divisions each, a shuffle scan for the first span of each tile)
+template <class P>
+__device__ __forceinline__ void build_span_tab(const LossArgs<P>& a, const SegLists& L, int n_tiles, bool items, int batch) {
+    const int t = threadIdx.x;
+    if (t >= 32) return;
+    int per = 0, mine = 0, units = 0;
+    if (t < n_tiles) {
+        const int rows = L.tile_tab[t * 4 + 3];
+        units = items ? rows * (a.tt.ch >> 2) : rows;
+        mine = spans_of_tile(n_tiles - 1 - t, n_tiles, units, items ? batch : 32, a.span_fine, per);
+    }
+    int first = mine;
+#pragma unroll
+    for (int d = 1; d < kMaxChunkTiles; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, first, d);
+        if (t >= d) first += u;
+    }
+    first -= mine;
+    for (int q = 0; q < mine; ++q) L.span_tab[first + q] = make_int2(t, (q * per) | (min(per, units - q * per) << 16));
+    if (t == n_tiles - 1) L.span_ctr[1] = first + mine;
 }
 
 template <class P>
@@ -738,13 +782,12 @@ __device__ __noinline__ LossAcc visit_dense(const LossArgs<P>& a, const typename
 // span; the chunk's sum is formed from them in span order afterwards, so it does not depend on which warp took which
 // span: results stay run-to-run deterministic.
 template <class P, int kCls, bool kGrad, int kMode /*0 scalar, 1 whole-float4 rows, 2 any layout over an aligned flat range*/>
-__device__ __noinline__ void stream_spans(const LossArgs<P>& a, const SegLists& L, int img, int n_tiles, int span_rows) {
+__device__ __noinline__ void stream_spans(const LossArgs<P>& a, const SegLists& L, int img) {
     const int lane = threadIdx.x & 31;
     const int ch = a.tt.ch;
-    const int spt = a.tt.rows_per_tile / span_rows, n_spans = n_tiles * spt;
+    const int n_spans = L.span_ctr[1];
     const int vpr = ch >> 2;
     const int step = kMode == 1 ? 32 % vpr : (kMode == 2 ? 128 % ch : 32 % ch);
-    const int c_lane = kMode == 1 ? lane % vpr : (kMode == 2 ? (4 * lane) % ch : lane % ch);
     const int n_skip = a.spec.reg_ch + (a.spec.cen_mode != 0 ? 1 : 0);
     const float gamma = a.spec.gamma, gscale = (kCls == 2 ? 1.0f : 1.0f - a.spec.alpha) * a.spec.w_cls;
     const LossSpec sp = a.spec;
@@ -754,21 +797,22 @@ __device__ __noinline__ void stream_spans(const LossArgs<P>& a, const SegLists& 
         if (lane == 0) s = atomicAdd(L.span_ctr, 1);
         s = __shfl_sync(0xffffffffu, s, 0);
         if (s >= n_spans) break;
-        const int tix = s / spt, q = s - tix * spt;
-        const int m = L.tile_tab[tix * 4 + 0], r0 = L.tile_tab[tix * 4 + 1] + q * span_rows;
-        const int nrows = min(span_rows, L.tile_tab[tix * 4 + 3] - q * span_rows);
+        const int2 span = L.span_tab[s];
+        const int tix = span.x, first = span.y & 0xffff, count = span.y >> 16;  // units: items (kMode 1) or rows
+        const int m = L.tile_tab[tix * 4 + 0], r0 = L.tile_tab[tix * 4 + 1];
         StreamAcc sa = {0.f, 0.f, 0.f, 0.f, 0.f, 0ull, 0ull};
-        if (nrows > 0) {
+        if (count > 0) {
             const MapDesc& md = a.tt.maps[m];
-            const long long e = static_cast<long long>(img) * md.image_stride + static_cast<long long>(r0) * ch;
+            const long long e = static_cast<long long>(img) * md.image_stride + static_cast<long long>(r0) * ch +
+                                static_cast<long long>(first) * (kMode == 1 ? 4 : ch);
             float* gg = (kGrad && a.grad_maps[m]) ? a.grad_maps[m] + e : nullptr;
             if constexpr (kMode == 1) {
-                stream_vec<kCls, kGrad, kGrad ? 5 : 7>(md.pred + e, gg, nrows, vpr, c_lane, step, lane, gamma, gscale, sa);
+                stream_vec<kCls, kGrad, kGrad ? 5 : 7>(md.pred + e, gg, count, vpr, (first + lane) % vpr, step, lane, gamma, gscale, sa);
             } else if constexpr (kMode == 2) {
-                stream_vec<kCls, kGrad, kGrad ? 5 : 7, true>(md.pred + e, gg, nrows, ch, c_lane, step, lane, gamma, gscale, sa, n_skip);
-                stream_cen_and_tail<kCls, kGrad>(md.pred + e, gg, nrows, ch, lane, sp, sa);
+                stream_vec<kCls, kGrad, kGrad ? 5 : 7, true>(md.pred + e, gg, (count * ch) >> 2, ch, (4 * lane) % ch, step, lane, gamma, gscale, sa, n_skip);
+                stream_cen_and_tail<kCls, kGrad>(md.pred + e, gg, count, ch, lane, sp, sa);
             } else {
-                stream_scalar<kCls, kGrad, 4>(md.pred + e, gg, nrows, ch, c_lane, step, lane, sp, sa);
+                stream_scalar<kCls, kGrad, 4>(md.pred + e, gg, count, ch, lane % ch, step, lane, sp, sa);
             }
         }
         float q0, q1, q2, q3;
@@ -805,27 +849,29 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // Reduction of the chunk partials without a second launch, by the last CTA of the launch:
-//   reduce_images   chunk partials -> per_image rows.  Tier by tier, L = 1..32 lanes share an image so that no lane has
-//                   more than 16 partials to add (a fine tail tier has 300 chunks per image, the coarse tier ~38) and the
-//                   loads of all images of a pass are in flight together; float64, fixed lane / shuffle order ->
-//                   deterministic.
+//   reduce_images   chunk partials -> per_image rows.  L = 1..32 lanes share an image so that no lane has more than 16
+//                   partials to add (a fine tail tier has 300 chunks per image, the coarse tier ~38); the (tier, group
+//                   of images) items are dealt to the eight warps, so the tiers' L2 round trips overlap instead of
+//                   following each other; float64, fixed lane / shuffle order -> deterministic.
 //   finalize_total  per_image rows -> total, and, when the communicator is attached, the exchange of the total with
 //                   the peer ranks (dh_comm.cuh).
 template <class P>
 __device__ __forceinline__ void reduce_images(const LossArgs<P>& a, double (&tot)[4]) {
     constexpr int kInFlight = 16;  // partials one lane loads per image: all issued before the first add (one L2 round trip)
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4* part = reinterpret_cast<const float4*>(a.partials);
+    int item = 0;  // (tier, group of 32 / L images) items are dealt to the warps: the tiers' round trips overlap
 #pragma unroll 1
     for (int tk = 0; tk < a.n_tiers; ++tk) {
         const ChunkTier& T = a.tiers[tk];
         const int img_end = tk + 1 < a.n_tiers ? a.tiers[tk + 1].image0 : a.tt.batch;
         int L = 1;
         while (L < 32 && L * kInFlight < T.cpi) L <<= 1;
-        const int G = DH_THREADS / L, sub = tid & (L - 1);
+        const int G = 32 / L, sub = lane & (L - 1);
 #pragma unroll 1
-        for (int b0 = T.image0; b0 < img_end; b0 += G) {  // block-uniform trip count
-            const int b = b0 + tid / L;
+        for (int b0 = T.image0; b0 < img_end; b0 += G, ++item) {
+            if ((item & (DH_THREADS / 32 - 1)) != warp) continue;  // warp-uniform
+            const int b = b0 + lane / L;
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             if (b < img_end) {
                 const float4* p = part + T.chunk0 + static_cast<long long>(b - T.image0) * T.cpi;
@@ -891,6 +937,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     uint64_t* boxbar = reinterpret_cast<uint64_t*>(smem + lay.misc_off);
     long long* next_chunk = reinterpret_cast<long long*>(smem + lay.misc_off + 8);
     int* is_last = reinterpret_cast<int*>(smem + lay.misc_off + 16);
+    int* next_img = reinterpret_cast<int*>(smem + lay.misc_off + 24);  // [0] image whose GT rows are on their way into `raw` (-1: none), [1] its box count
     float* wred = reinterpret_cast<float*>(smem + lay.misc_off + 64);  // [8][4] floats; [8][4] doubles in the finalize
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -905,11 +952,14 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     if (tid <= kMaxSegments) segs.nmap[tid] = 0;  // nmap[], npairs
     for (int e = tid; e < kMaxChunkTiles * DH_THREADS; e += DH_THREADS) segs.head[e] = kNoPair;
     if (tid < kMaxChunkTiles * 8) segs.rowbits[tid] = 0u;
-    if (tid == 0) *segs.span_ctr = 0;
+    if (tid == 0) *segs.span_ctr = 0, next_img[0] = -1;
+    const int span_batch = 32 * (kGrad ? 5 : 7);  // items of one load batch of stream_vec
     if (chunk < n_chunks) {
         int img, sub, t_begin, t_end;
         chunk_span(ga, chunk, img, sub, t_begin, t_end);
         build_tile_tab<P>(ga, segs, img, t_begin, t_end);
+        __syncwarp();
+        build_span_tab<P>(ga, segs, t_end - t_begin, vec, span_batch);
     }
     __syncthreads();
 
@@ -933,15 +983,41 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
     for (; chunk < n_chunks;) {
         int img, sub, t_begin, t_end;
         chunk_span(a, chunk, img, sub, t_begin, t_end);
-        const int n_tiles = t_end - t_begin;
-        const int span_rows = n_tiles >= 8 ? 128 : 64;
-        if (tid == 0) *next_chunk = static_cast<long long>(atomicAdd(ga.sched, 1u)) + gridDim.x;
         if (img != cur_img) {  // block-uniform; the barrier at the end of the previous chunk protects recs/raw
-            n_boxes = stage_boxes(a.boxes, a.nbox, img, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
+            if (next_img[0] == img) {  // the previous chunk asked for these rows: they have long arrived
+                mbar_wait(boxbar, box_parity);
+                box_parity ^= 1u;
+                n_boxes = next_img[1];
+            } else {
+                n_boxes = stage_boxes(a.boxes, a.nbox, img, a.max_boxes, a.box_cap, raw, boxbar, box_parity);
+            }
             const float hi = a.img_dim[2 * img], wi = a.img_dim[2 * img + 1];
             if (tid < n_boxes) P::make_record(a.pp, raw + 5 * tid, hi, wi, tid, recs[tid]);
             __syncthreads();
             cur_img = img;
+        }
+        // One thread of a streaming warp takes the next chunk from the scheduler and, when that chunk belongs to another
+        // image, starts the bulk copy of its GT rows into `raw` (free from here on: the records are built) -- the counter's
+        // and the copy's round trips pass under the streaming of this chunk instead of opening the next one.  All
+        // max_boxes rows are copied (the count is read meanwhile), which needs 16-byte-sized and -aligned images.
+        if (tid == DH_THREADS - 1) {
+            const long long nc = static_cast<long long>(atomicAdd(ga.sched, 1u)) + gridDim.x;
+            int pre = -1;
+            if (nc < n_chunks) {
+                int img2, sub2, tb2, te2;
+                chunk_span(a, nc, img2, sub2, tb2, te2);
+                const int rows = min(a.max_boxes, a.box_cap);
+                const float* src = a.boxes + static_cast<long long>(img2) * a.max_boxes * 5;
+                if (img2 != img && (rows & 3) == 0 && (a.max_boxes & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+                    mbar_expect_tx(boxbar, static_cast<uint32_t>(rows) * 20u);
+                    bulk_g2s(raw, src, static_cast<uint32_t>(rows) * 20u, boxbar);
+                    const int n2 = a.nbox ? a.nbox[img2] : a.max_boxes;
+                    next_img[1] = max(0, min(n2, rows));
+                    pre = img2;
+                }
+            }
+            next_img[0] = pre;
+            *next_chunk = nc;
         }
         if (sub == 0) P::image_prologue(a.pp, recs, n_boxes, img);
         DH_TRACE_PHASE(0)
@@ -970,9 +1046,9 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
             if (!kGrad) resolve();
             DH_TRACE_PHASE(4)
         }
-        if (vec) stream_spans<P, kCls, kGrad, 1>(a, segs, img, n_tiles, span_rows);
-        else if (ga.allow_vec) stream_spans<P, kCls, kGrad, 2>(a, segs, img, n_tiles, span_rows);
-        else stream_spans<P, kCls, kGrad, 0>(a, segs, img, n_tiles, span_rows);
+        if (vec) stream_spans<P, kCls, kGrad, 1>(a, segs, img);
+        else if (ga.allow_vec) stream_spans<P, kCls, kGrad, 2>(a, segs, img);
+        else stream_spans<P, kCls, kGrad, 0>(a, segs, img);
         DH_TRACE_PHASE(2)
         if (kGrad) {
             __syncthreads();  // every zero-label gradient of the chunk is written before a matched row overwrites its own
@@ -989,7 +1065,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         }
         __syncthreads();  // also: every warp is done with recs and with the spans; the prefetched chunk id is visible
         if (warp == 0) {  // span sums (in span order) + wred [8][4] -> one float4 per chunk
-            const int n_spans = n_tiles * (a.tt.rows_per_tile / span_rows);
+            const int n_spans = segs.span_ctr[1];
             float scls = 0.f, scen = 0.f;
             for (int q = lane; q < n_spans; q += 32) scls += segs.span_sum[2 * q], scen += segs.span_sum[2 * q + 1];
             scls = warp_sum(scls) * ((kCls == 2 ? 1.0f : 1.0f - ga.spec.alpha) * kLn2), scen = warp_sum(scen);
@@ -1011,10 +1087,12 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
             }
         }
         if (tid == DH_THREADS - 1) *segs.span_ctr = 0;
-        if (chunk < n_chunks) {  // the next chunk's tile table, published by the barrier below
+        if (chunk < n_chunks) {  // the next chunk's tile and span tables, published by the barrier below
             int img2, sub2, tb2, te2;
             chunk_span(a, chunk, img2, sub2, tb2, te2);
             build_tile_tab<P>(a, segs, img2, tb2, te2);
+            __syncwarp();
+            build_span_tab<P>(a, segs, te2 - tb2, vec, span_batch);
         }
         __syncthreads();  // wred / next_chunk are free again; the lists are empty; the tile table is the next chunk's
         DH_TRACE_PHASE(5)
@@ -1030,11 +1108,8 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         __threadfence();  // this CTA's partials and per-image rows are visible device-wide before it counts itself done
         const unsigned done = atomicAdd(ga.sched + 1, 1u);
         const int last = done == gridDim.x - 1;
-        if (last) {
-            ga.sched[0] = 0u, ga.sched[1] = 0u;  // the scheduler line is ready for the next launch that gets it
-            __threadfence();
-        }
-        *is_last = last;
+        if (last) ga.sched[0] = 0u, ga.sched[1] = 0u;  // the scheduler line is ready for the next launch that gets it (kernel
+        *is_last = last;                               // completion publishes the stores: nothing waits for them here)
     }
     if (!ga.fold_finalize) return;
     __syncthreads();

@@ -74,6 +74,7 @@ struct LossArgs {
     float* per_image;  // [batch, 4] (caller's buffer or scratch)
     float* out_total;  // [4] or null
     int fold_finalize;  // 1: the last CTA finalizes (no finalize kernels follow)
+    int span_fine;      // log2 of the spans the LAST tile of a chunk is cut into (fused kernel, see spans_of_tile)
     int use_comm;       // 1: out_total is summed over the ranks of `comm` (peer mailboxes)
     CommDev comm;
     long long* trace;  // profiling aid (dh_set_trace): per CTA {start, first chunk ready, loop end (globaltimer ns), chunks}

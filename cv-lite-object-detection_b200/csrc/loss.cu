@@ -182,14 +182,15 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     // 4..16 tiles -- which matters for small batches, where a chunk's fixed cost (GT staging, barriers) is not hidden
     // behind other CTAs' streaming.
     long long want;
-    if (h->fused_tail) {
+    a.span_fine = (h->fused_tail >> 1) ? (h->fused_tail >> 1) : 2;
+    if (h->fused_tail & 1) {
         want = (total / grid) * 55 / 100;
         want = want < 4 ? 4 : (want > h->fused_max_chunk ? h->fused_max_chunk : want);
     } else {
         want = total / (grid * h->fused_chunks_per_cta);
         want = want < 4 ? 4 : (want > 8 ? 8 : want);
     }
-    plan_tiers(a, grid, static_cast<int>(want), h->fused_tail != 0);
+    plan_tiers(a, grid, static_cast<int>(want), (h->fused_tail & 1) != 0);
     const long long n_chunks = a.n_chunks;
     if (grid > n_chunks) grid = n_chunks;
     if (grid < 1) grid = 1;

@@ -58,7 +58,7 @@ int dh_destroy(dh_handle_t h);
 #define DH_OPT_NMS_SORT 10 /* score sort ahead of the NMS. 0 (default): bucket sort in shared memory, bitonic network when the scores pile onto few buckets; 1: always the bitonic network (A/B checks) */
 #define DH_OPT_LOSS_ALLREDUCE 11 /* 1: the out_total of every dh_*_encode_loss(_grad) call is summed over the ranks of the handle's communicator inside the same kernel (its last CTA exchanges the scalars through the NVLink peer mailboxes, see dh_comm_peer_import); 0 (default): out_total is this rank's sum */
 #define DH_OPT_ALLREDUCE 12 /* transport of dh_allreduce_loss. 0 (default): peer mailboxes when imported, else NCCL; 1: NCCL; 2: peer mailboxes */
-#define DH_OPT_FUSED_TAIL 13 /* fused loss scheduler: 1 (default) cuts the last images of a launch into finer chunks so that the tail is short; 0: uniform chunks */
+#define DH_OPT_FUSED_TAIL 13 /* fused loss scheduler: 1 (default) cuts the last images of a launch into finer chunks so that the tail is short; 0: uniform chunks.  Tuning aid: + 2 * f, f = 1..5, cuts a chunk's last tile into up to 2^f spans for the warps to take (default f = 2) */
 #define DH_OPT_ENCODE_KERNEL 14 /* target encoders. 0 (default): pick per problem -- direct-store kernel for small outputs, shared-memory tile streamer with TMA bulk stores for large ones; 1: always the tile streamer; 2: always the direct-store kernel */
 #define DH_OPT_FUSED_MAX_CHUNK 15 /* fused loss scheduler with the tiered tail: upper bound on the coarse tier's chunk in tiles of 256 rows (default 16; the coarse chunk is about half of a CTA's share of the work) */
 #define DH_OPT_NMS_FILTER 16 /* mask-matrix NMS: 1 (default) pairs that provably do not overlap (disjoint slab masks) skip the exact predicate; 0: every pair takes it (A/B checks; the bits are identical); 2..64: on, and a warp whose rows keep more than this many of a block's 64 columns walks the columns in step (tuning aid; default 64 = never).  Images where more than 1 candidate in 8 is not a proper box (inverted corners, NaN) skip the filter by themselves */

@@ -70,10 +70,14 @@ def main():
             pred = make_pred(B, dist)
             nbytes = sum(p.numel() for p in pred) * 4
             cases = [("tail=1", 1, 16, nd), ("tail=0", 0, 16, nd)]
-            if dist == "prior":
-                cases += [("tail=1 max=8", 1, 8, nd), ("tail=1 no boxes", 1, 16, zero)]
+            if dist == "prior":  # (tail >> 1 = log2 of the spans of a chunk's last tile: 1 = every tile in 2 spans)
+                cases += [("tail=1 max=8", 1, 8, nd), ("tail=1 no boxes", 1, 16, zero), ("tail=1 fine=3", 1 | (3 << 1), 16, nd),
+                          ("tail=1 fine=2", 1 | (2 << 1), 16, nd), ("tail=1 fine=1", 1 | (1 << 1), 16, nd)]
             for tag, tail, mx, n in cases:
-                dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
+                try:
+                    dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
+                except ValueError:
+                    continue
                 dh.set_option(0, _capi.DH_OPT_FUSED_MAX_CHUNK, mx)
                 t = graph_time(lambda: dh.retinanet.encode_loss_batch(bd, n, dims, 80, [640, 640], pred))
                 print(json.dumps({"B": B, "logits": dist, "case": tag, "us": round(t * 1e6, 1), "GBps": round(nbytes / t / 1e9, 1),
