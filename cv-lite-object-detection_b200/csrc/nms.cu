@@ -58,11 +58,17 @@ __device__ __forceinline__ unsigned long long nms_sort_key(const float* d, int r
     return k == 0ull ? 1ull : k;
 }
 
-// ---- slab masks: a conservative "can these two boxes overlap at all" test in three instructions -------------------
+// ---- slab masks: a conservative "can this pair be suppressed at all" test in three instructions -------------------
 // Each axis of an image's candidates is cut into 32 slabs over the candidates' own coordinate range; a box carries, per
-// axis, the bit mask of the slabs it touches.  The slab index is a monotone function of the coordinate, so two boxes that
-// overlap on an axis share a slab there: (mask_a & mask_c) == 0 on either axis proves an empty intersection.  Boxes
-// that are not proper (inverted corners, zero extent, NaN) get all-ones masks: they always take the exact predicate.
+// axis, the bit mask of the slabs its CORE touches -- the box shrunk about its centre by the factor (1 - thr).  Why
+// cores: for two proper boxes, inter / union > thr needs inter > thr * max(area_a, area_c); inter = ix * iy with
+// iy <= min(h_a, h_c), so the overlap on the x axis must exceed thr * max(w_a, w_c) (same on y), and ix is at most
+// (w_a + w_c) / 2 - |centre distance|: the centres are closer than (1 - thr) (w_a + w_c) / 2, i.e. the cores intersect.
+// The slab index is a monotone function of the coordinate, so two intervals that intersect share a slab:
+// (mask_a & mask_c) == 0 on either axis proves that neither predicate suppresses the pair (both compute
+// inter / (union [+ 1e-8]); thr = 0 gives the plain "do they overlap" test).  With thr = 0.5 a core has a quarter of the
+// box's area: where boxes are large against the image (coarse pyramid levels) nearly every pair overlaps, few cores do.
+// Boxes that are not proper (inverted corners, zero extent, NaN) get all-ones masks: they always take the exact predicate.
 __device__ __forceinline__ unsigned ordered_bits(float v) {  // monotone float -> uint
     const unsigned u = __float_as_uint(v);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -101,7 +107,15 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const float* __r
             if (r[2] > r[0] && r[3] > r[1] && fabsf(r[0]) < 3.0e38f && fabsf(r[1]) < 3.0e38f && fabsf(r[2]) < 3.0e38f && fabsf(r[3]) < 3.0e38f) {
                 const float lo0 = ordered_float(rng[0]), hi0 = ordered_float(rng[1]), lo1 = ordered_float(rng[2]), hi1 = ordered_float(rng[3]);
                 const float sc0 = hi0 > lo0 ? 32.0f / (hi0 - lo0) : 0.f, sc1 = hi1 > lo1 ? 32.0f / (hi1 - lo1) : 0.f;
-                if (sc0 < 3.0e38f && sc1 < 3.0e38f) m = make_uint2(slab_range_mask(r[0], r[2], lo0, sc0), slab_range_mask(r[1], r[3], lo1, sc1));
+                if (sc0 < 3.0e38f && sc1 < 3.0e38f) {
+                    // the box shrunk about its centre by (1 - thr): see "cores" above.  thr is taken 1e-4 low (the rounding
+                    // of the exact predicate) and the core a little wide (the rounding of these few operations)
+                    const float keep = 1.0f - fminf(fmaxf(p.iou_thr * (1.0f - 1.0e-4f), 0.0f), 1.0f);
+                    const float h0 = 0.5f * keep * (r[2] - r[0]) * (1.0f + 1.0e-5f) + 1.0e-5f * (hi0 - lo0);
+                    const float h1 = 0.5f * keep * (r[3] - r[1]) * (1.0f + 1.0e-5f) + 1.0e-5f * (hi1 - lo1);
+                    const float m0 = 0.5f * (r[0] + r[2]), m1 = 0.5f * (r[1] + r[3]);
+                    m = make_uint2(slab_range_mask(m0 - h0, m0 + h0, lo0, sc0), slab_range_mask(m1 - h1, m1 + h1, lo1, sc1));
+                }
             }
             sorted_slabs[static_cast<long long>(b) * p.n_max + pos] = m;
         }
@@ -255,12 +269,12 @@ __device__ __forceinline__ bool suppress_iou(const float4& a0, const float4& c0,
 
 // ---- kernel 2 -----------------------------------------------------------------------------------------
 // One CTA takes the 64 boxes of column block cb against four row blocks (256 threads, one row each).  Nearly all of the
-// 400 M pairs of a 64 x 5 000-candidate batch do not overlap at all, so the exact predicate must not run for them: the
-// column block's slab masks are turned into "which of my 64 boxes touch slab s" words (64 ballots per axis), a row ORs
-// the words of the slabs it touches on each axis and ANDs the two -- the 64-bit set of columns that can overlap it, for
-// ~30 instructions -- and only those take the exact predicate (identical arithmetic, identical bits).  A pair that is
-// filtered out has two boxes of positive finite area and an empty intersection, for which both predicates answer
-// "not suppressed" whenever the threshold is not negative (a negative threshold switches the filter off).
+// 400 M pairs of a 64 x 5 000-candidate batch cannot reach the threshold, so the exact predicate must not run for them:
+// the column block's slab masks are turned into "which of my 64 boxes touch slab s" words (64 ballots per axis), a row
+// ORs the words of the slabs it touches on each axis and ANDs the two -- the 64-bit set of columns whose cores meet its
+// own, for ~30 instructions -- and only those take the exact predicate (identical arithmetic, identical bits).  A pair
+// that is filtered out has two boxes of positive finite area whose IoU is provably below the threshold, for which both
+// predicates answer "not suppressed" (a negative threshold switches the filter off).
 constexpr int kMaskRowBlocks = 4;
 __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(const float4* __restrict__ sorted_boxes, const int* __restrict__ sorted_cls,
                                                                        const uint2* __restrict__ sorted_slabs, const int* __restrict__ filter_ok,
@@ -276,6 +290,13 @@ __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(const flo
     const int tid = threadIdx.x, t = tid & 63, lane = tid & 31;
     const long long base = static_cast<long long>(b) * p.n_max;
     const bool filter = sorted_slabs != nullptr && !(p.iou_thr < 0.f) && filter_ok[b] != 0;
+    __shared__ uint2 cslab[64];
+    // this thread's row: asked for ahead of the barriers below
+    const int i = rb * 64 + t;
+    const bool row_ok = rb <= cb && i < m;
+    const float4 a = row_ok ? sorted_boxes[base + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ac = row_ok ? sorted_cls[base + i] : 0;
+    const uint2 row_sm = (row_ok && filter) ? sorted_slabs[base + i] : make_uint2(0u, 0u);
     if (tid < 64) {
         const int j = cb * 64 + t;
         uint2 sm = make_uint2(0u, 0u);
@@ -284,25 +305,28 @@ __global__ void __launch_bounds__(64 * kMaskRowBlocks) nms_mask_kernel(const flo
             cbox[t] = c, carea[t] = box_area(c), ccls[t] = sorted_cls[base + j];
             if (filter) sm = sorted_slabs[base + j];
         }
-        if (filter) {
-#pragma unroll
-            for (int s = 0; s < 32; ++s) {
-                const unsigned b0 = __ballot_sync(0xffffffffu, (sm.x >> s) & 1u), b1 = __ballot_sync(0xffffffffu, (sm.y >> s) & 1u);
-                if (lane == 0) slab_cols[0][s][tid >> 5] = b0, slab_cols[1][s][tid >> 5] = b1;
-            }
-        }
+        cslab[t] = sm;
     }
     __syncthreads();
-    const int i = rb * 64 + t;
-    if (rb > cb || i >= m) return;
-    const float4 a = sorted_boxes[base + i];
+    if (filter) {  // 128 ballots, dealt to the warps: warp w takes slabs 4w .. 4w + 3 of both axes for both column halves
+        const int w = tid >> 5;
+        for (int s = w; s < 32; s += (64 * kMaskRowBlocks) >> 5) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const uint2 sm = cslab[32 * hf + lane];
+                const unsigned b0 = __ballot_sync(0xffffffffu, (sm.x >> s) & 1u), b1 = __ballot_sync(0xffffffffu, (sm.y >> s) & 1u);
+                if (lane == 0) slab_cols[0][s][hf] = b0, slab_cols[1][s][hf] = b1;
+            }
+        }
+        __syncthreads();
+    }
+    if (!row_ok) return;
     const float area_a = box_area(a);
-    const int ac = sorted_cls[base + i];
     const int jn = min(64, m - cb * 64);
     unsigned long long todo = jn >= 64 ? ~0ull : ((1ull << jn) - 1ull);
     if (rb == cb) todo &= t >= 63 ? 0ull : (~0ull << (t + 1));
     if (filter) {
-        const uint2 sm = sorted_slabs[base + i];
+        const uint2 sm = row_sm;
         unsigned x0 = 0u, x1 = 0u, y0 = 0u, y1 = 0u;
         for (unsigned r = sm.x; r; r &= r - 1) {
             const int s = __ffs(r) - 1;
