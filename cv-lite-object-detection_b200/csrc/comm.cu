@@ -107,7 +107,7 @@ static int ensure_box(dh_handle_s* h, Comm* c) {
 }
 
 __global__ void peer_allreduce_kernel(const __grid_constant__ CommDev c, float* vals, int count) {
-    peer_allreduce_warp(c, vals, count);
+    peer_allreduce_warp(c, vals, count, peer_allreduce_seq(c));
 }
 
 // used by loss.cu: the device view of the communicator when the in-kernel exchange is on, else null

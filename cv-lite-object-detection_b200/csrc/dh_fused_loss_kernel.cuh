@@ -904,6 +904,7 @@ template <class P>
 __device__ __forceinline__ void finalize_total(const LossArgs<P>& a, double (&tot)[4], double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.out_total) return;
+    const unsigned int prev_seq = (a.use_comm && warp == 0) ? peer_allreduce_seq(a.comm) : 0u;
 #pragma unroll
     for (int k = 0; k < 4; ++k) tot[k] = warp_sum_d(tot[k]);
     if (lane == 0) {
@@ -920,7 +921,7 @@ __device__ __forceinline__ void finalize_total(const LossArgs<P>& a, double (&to
             vals[lane] = static_cast<float>(v);
         }
         __syncwarp();
-        if (a.use_comm) peer_allreduce_warp(a.comm, vals, 4);
+        if (a.use_comm) peer_allreduce_warp(a.comm, vals, 4, prev_seq);
         __syncwarp();
         if (lane < 4) a.out_total[lane] = vals[lane];
     }

@@ -51,7 +51,9 @@ def main():
                 dist.all_gather(parts, v)
                 want = sum(p_.double() for p_ in parts).float().cpu().numpy()
             distributed.allreduce_losses(v)
-            if check and not np.array_equal(v.cpu().numpy(), want):
+            # (the mailboxes add in float64 in rank order: exact; NCCL adds float32 in its own order: one rounding per rank)
+            got = v.cpu().numpy()
+            if check and not (np.array_equal(got, want) if name != "nccl" else np.allclose(got, want, rtol=1e-6 * world, atol=0)):
                 bad += 1
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
