@@ -168,6 +168,7 @@ struct RetinaDecodeArgs {
     const float* anchor_hw;             // device [n_levels, A, 2]
     int n_levels, n_anchors, num_classes, ch, use_tma;
     long long n_total;
+    float* scores;                      // optional [B, n_total]: the score column alone, for the selector that follows (dh_retina_detect)
 };
 
 // lower bound t such that x < t implies sigmoid_acc(x) < sigmoid_acc(m) strictly (conservative; see above)
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) retina_decode_stream_kernel(co
             const float4 o = corners_of(cp, static_cast<int>(i), static_cast<int>(loc - i * a.wl[l]), 0, q[0], q[1], q[2], q[3]);
             o6[0] = o.x, o6[1] = o.y, o6[2] = o.z, o6[3] = o.w, o6[4] = best, o6[5] = static_cast<float>(label);
             orow = static_cast<long long>(b) * a.n_total + a.level_off[l] + local;
+            if (a.scores) a.scores[orow] = best;
         }
         // hand the 6-float rows to the stage buffer and write them out coalesced (the tile's output rows are
         // contiguous unless it straddles an image boundary)
@@ -551,10 +553,13 @@ __device__ __forceinline__ void select_core(SelShared& sh, const Src& src, int k
 // generic source: rows of `row_floats` floats, the score in column `score_col`; selected rows are copied whole
 struct RowSource {
     const float* rows;  // first row of the segment
+    const float* scores;  // or null: the score column on its own (the three passes then read 4 bytes per row, not a 32-byte sector)
     float* out;         // first output slot of the segment
     int* out_src;       // or null
     int row_floats, score_col, n, first_index;
-    __device__ __forceinline__ float score(int i) const { return __ldg(rows + static_cast<long long>(i) * row_floats + score_col); }
+    __device__ __forceinline__ float score(int i) const {
+        return scores ? __ldg(scores + i) : __ldg(rows + static_cast<long long>(i) * row_floats + score_col);
+    }
     __device__ __forceinline__ void emit(int i, float, int rank) const {
         const float* src = rows + static_cast<long long>(i) * row_floats;
         float* dst = out + static_cast<long long>(rank) * row_floats;
@@ -574,12 +579,14 @@ struct SelSegs {
 };
 __global__ void __launch_bounds__(kSelThreads) select_topk_segs_kernel(const float* __restrict__ dets, long long n_total, int row_floats,
                                                                        int score_col, SelSegs segs, int k_slots, float min_score, int inclusive,
-                                                                       float* __restrict__ out, int out_rows, int* __restrict__ overflow) {
+                                                                       float* __restrict__ out, int out_rows, int* __restrict__ overflow,
+                                                                       const float* __restrict__ scores) {
     __shared__ SelShared sh;
     const int b = blockIdx.x, seg = blockIdx.y;  // level-major dispatch: the long (fine-level) segments of every image start first
     const int lo = segs.off[seg], hi = segs.off[seg + 1];
     RowSource src;
     src.rows = dets + (static_cast<long long>(b) * n_total + lo) * row_floats;
+    src.scores = scores ? scores + static_cast<long long>(b) * n_total + lo : nullptr;
     src.out = out + (static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots) * row_floats;
     src.out_src = nullptr;
     src.row_floats = row_floats, src.score_col = score_col, src.n = hi - lo, src.first_index = lo;
@@ -596,6 +603,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
     const int lo = seg_off[seg], hi = seg_off[seg + 1];
     RowSource src;
     src.rows = dets + (static_cast<long long>(b) * n_total + lo) * row_floats;
+    src.scores = nullptr;
     src.out = out + (static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots) * row_floats;
     src.out_src = out_src ? out_src + static_cast<long long>(b) * out_rows + static_cast<long long>(seg) * k_slots : nullptr;
     src.row_floats = row_floats, src.score_col = score_col, src.n = hi - lo, src.first_index = lo;
@@ -1525,13 +1533,13 @@ int launch_fcos_select(dh_handle_s* h, const float* const* pred_levels, int batc
 }
 
 int launch_select_segs(dh_handle_s* h, const float* dets, int batch, long long n_total, int row_floats, int score_col, const int* seg_off_host,
-                       int n_seg, int k, float min_score, int inclusive, float* out, int* overflow, cudaStream_t st) {
+                       int n_seg, int k, float min_score, int inclusive, float* out, int* overflow, cudaStream_t st, const float* scores) {
     SelSegs segs;
     memset(&segs, 0, sizeof(segs));
     for (int s = 0; s <= n_seg; ++s) segs.off[s] = seg_off_host[s];
     dim3 grid(batch, n_seg);
     select_topk_segs_kernel<<<grid, kSelThreads, 0, st>>>(dets, n_total, row_floats, score_col, segs, k, min_score, inclusive, out, n_seg * k,
-                                                          overflow);
+                                                          overflow, scores);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
     return DH_OK;
@@ -1612,6 +1620,18 @@ int dh_fcos_decode(dh_handle_t h, const float* const* pred_levels, int batch, in
 int dh_retina_decode(dh_handle_t h, const float* const* pred_levels, int batch, int pad_h, int pad_w, int n_levels,
                      const int32_t* strides, int n_anchors, const float* anchor_hw_dev, int num_classes, float* dets,
                      void* stream) {
+    return dh::retina_decode_scores(h, pred_levels, batch, pad_h, pad_w, n_levels, strides, n_anchors, anchor_hw_dev, num_classes, dets, nullptr,
+                                    nullptr, stream);
+}
+
+}  // extern "C"
+
+// dh_retina_decode; `scores` (optional, [B, N]) also receives the score column on its own when the streaming kernel runs
+// (*wrote_scores says whether it did).
+int dh::retina_decode_scores(dh_handle_s* h, const float* const* pred_levels, int batch, int pad_h, int pad_w, int n_levels,
+                             const int32_t* strides, int n_anchors, const float* anchor_hw_dev, int num_classes, float* dets, float* scores,
+                             int* wrote_scores, void* stream) {
+    if (wrote_scores) *wrote_scores = 0;
     DH_CHECK_ARG(h && pred_levels && strides && anchor_hw_dev && dets, "dh_retina_decode: NULL argument");
     DH_CHECK_ARG(n_levels >= 1 && n_levels <= DH_MAX_LEVELS && n_anchors >= 1 && num_classes >= 1, "dh_retina_decode: bad configuration");
     DeviceGuard guard(h);
@@ -1627,6 +1647,7 @@ int dh_retina_decode(dh_handle_t h, const float* const* pred_levels, int batch, 
         memset(&a, 0, sizeof(a));
         a.n_levels = n_levels, a.n_anchors = n_anchors, a.num_classes = num_classes, a.ch = ch, a.n_total = n_total;
         a.anchor_hw = anchor_hw_dev;
+        a.scores = scores;
         a.use_tma = (ch * 4) % 16 == 0 ? 1 : 0;
         long long off = 0, tiles = 0;
         for (int l = 0; l < n_levels; ++l) {
@@ -1660,6 +1681,7 @@ int dh_retina_decode(dh_handle_t h, const float* const* pred_levels, int batch, 
         retina_decode_stream_kernel<<<static_cast<unsigned>(grid), kDecWarps * 32, stream_smem, st>>>(a, dets);
         DH_CUDA(cudaGetLastError());
         h->launches += 1;
+        if (wrote_scores) *wrote_scores = scores != nullptr;
         return DH_OK;
     }
     long long off = 0;
@@ -1678,6 +1700,8 @@ int dh_retina_decode(dh_handle_t h, const float* const* pred_levels, int batch, 
     }
     return DH_OK;
 }
+
+extern "C" {
 
 int dh_select_topk(dh_handle_t h, const float* dets, int batch, long long n_total, int row_floats, int score_col,
                    const int32_t* seg_off_dev, int n_seg, int k, float min_score, int score_inclusive, float* out,
