@@ -466,6 +466,7 @@ struct CenterNetPolicy {
         int cls;
         int flags;  // bit0 live_y, bit1 live_x, bit2 valid
         float gstd;  // CN_GAUSSIAN: max(1, sqrt(box area in cells)), tf_centernet.py:203-205
+        float ginv_hi, ginv_lo;  // 1 / (2 gstd^2), a float64 value split into two floats (gauss_heat)
     };
     static constexpr int kRegChOnehot = 4;
     static constexpr bool kScatter = true;  // centre-cell modes: one thread per box writes its single row
@@ -488,6 +489,8 @@ struct CenterNetPolicy {
         if (footprint(p)) {  // tf_centernet.py:165-223
             const float h_ratio = fdiv(hi, s), w_ratio = fdiv(wi, s);
             r.gstd = fmaxf(1.0f, __fsqrt_rn(fmul(fmul(fmul(g[2], g[3]), h_ratio), w_ratio)));  // :203-205 (before the 8.0 override)
+            const double sd = static_cast<double>(r.gstd), ginv = 1.0 / (2.0 * sd * sd);
+            r.ginv_hi = static_cast<float>(ginv), r.ginv_lo = static_cast<float>(ginv - static_cast<double>(r.ginv_hi));
             const int hl = static_cast<int>(static_cast<double>(p.pad0) / p.stride);
             const int wl = static_cast<int>(static_cast<double>(p.pad1) / p.stride);
             const int clip_h = trunc_i(fdiv(hi, s)), clip_w = trunc_i(fdiv(wi, s));  // clip by img_dim (:222-223)
@@ -645,21 +648,27 @@ struct CenterNetPolicy {
 
     // gaussian_dist_2d of tf_centernet.py:30-40 on the footprint grid (cells at z + 0.5, integer mean): exp(-d^2 / (2 std^2))
     // over the live axes, divided by its maximum over the footprint (reached 0.5 cells from the mean on every live axis);
-    // the centre cell is forced to 1 like the reference does for its fall-off (:261-262).  float64 like the reference's NumPy.
+    // the centre cell is forced to 1 like the reference does for its fall-off (:261-262).  The specification
+    // (oracle.centernet_gaussian_format_data) evaluates the exponent and exp in float64 and rounds once; here the exponent
+    // is carried as an unevaluated sum of two floats -- d^2 is exact in float32, 1 / (2 std^2) is a float64 split in two,
+    // the product's rounding error comes out of an fma -- and exp(hi + lo) = expf(hi) * (1 + lo): within 2 ulp of float32
+    // of the specified value (the parity tests allow 2e-6 relative), for a dozen float32 instructions instead of a
+    // float64 division and a float64 exp per covering box per cell.
     __device__ static float gauss_heat(const Rec& c, int i, int j) {
         const bool live_y = c.flags & 1, live_x = c.flags & 2;
         if ((i == c.muy && j == c.mux) || !(live_y || live_x)) return 1.0f;
-        double d2 = 0.0;
+        float d2 = 0.0f;  // (integers and halves below 2^11: every operation is exact)
         if (live_y) {
-            const double dy = (static_cast<double>(i) + 0.5) - static_cast<double>(c.muy);
-            d2 += dy * dy - 0.25;
+            const float dy = (static_cast<float>(i) + 0.5f) - static_cast<float>(c.muy);
+            d2 += dy * dy - 0.25f;
         }
         if (live_x) {
-            const double dx = (static_cast<double>(j) + 0.5) - static_cast<double>(c.mux);
-            d2 += dx * dx - 0.25;
+            const float dx = (static_cast<float>(j) + 0.5f) - static_cast<float>(c.mux);
+            d2 += dx * dx - 0.25f;
         }
-        const double sd = static_cast<double>(c.gstd);
-        return static_cast<float>(exp(-d2 / (2.0 * sd * sd)));
+        const float hi = fmul(-d2, c.ginv_hi);
+        const float lo = fmaf(-d2, c.ginv_hi, -hi) - d2 * c.ginv_lo;
+        return expf(hi) * (1.0f + lo);
     }
 
     __device__ static double inv_pow8(double d) {  // 1/(d^8): tf_centernet.py:6-19 with spread forced to 8 (:207)
@@ -667,14 +676,35 @@ struct CenterNetPolicy {
         return ddiv(1.0, dmul(d4, d4));
     }
 
+    // Encoders: the 32 rows of a warp are neighbouring cells, so the warp first ballots which candidates' footprints meet
+    // the rectangle its cells span (one candidate per lane and round) and each lane then walks only those -- a tile's
+    // candidate list holds every box that touches its two image rows, a cell is covered by a handful of them.
+    static constexpr int kCandWords = (DH_MAX_BOXES + 31) / 32;
     __device__ static int emit_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, float* dst,
                                    const Rec* recs, const unsigned short* cand, int ncand) {
         DenseSink sink{dst};
+        if (footprint(p) && __activemask() == 0xffffffffu && ncand <= 32 * kCandWords) {
+            const int lane = threadIdx.x & 31;
+            const int i = static_cast<int>(fdiv_u32(row, md.div_width)), j = row - i * ti.width;
+            const int i0 = __reduce_min_sync(0xffffffffu, i), i1 = __reduce_max_sync(0xffffffffu, i);
+            const int j0 = __reduce_min_sync(0xffffffffu, j), j1 = __reduce_max_sync(0xffffffffu, j);
+            unsigned near[kCandWords];
+#pragma unroll
+            for (int w = 0; w < kCandWords; ++w) {
+                bool hit = false;
+                if (32 * w + lane < ncand) {
+                    const Rec& r = recs[cand[32 * w + lane]];
+                    hit = i1 >= r.ry0 && i0 < r.ry1 && j1 >= r.rx0 && j0 < r.rx1;
+                }
+                near[w] = 32 * w < ncand ? __ballot_sync(0xffffffffu, hit) : 0u;
+            }
+            return match_row<DenseSink, true>(p, ti, md, row, sink, recs, cand, ncand, near);
+        }
         return match_row(p, ti, md, row, sink, recs, cand, ncand);
     }
-    template <class Sink>
+    template <class Sink, bool kNear = false>
     __device__ static int match_row(const Params& p, const TileInfo& ti, const MapDesc& md, int row, Sink& dst,
-                                    const Rec* recs, const unsigned short* cand, int ncand) {
+                                    const Rec* recs, const unsigned short* cand, int ncand, const unsigned* near = nullptr) {
         int best = -1, hits = 0;
         float best_area = 0.f;
         if (!footprint(p)) {
@@ -694,13 +724,21 @@ struct CenterNetPolicy {
         }
         const int i = static_cast<int>(fdiv_u32(row, md.div_width));
         const int j = row - i * ti.width;
-        for (int q = 0; q < ncand; ++q) {
-            const int k = cand[q];
+        float heat = 0.f;  // CN_GAUSSIAN: the maximum over the covering boxes (see below), gathered in the same walk
+        auto visit = [&](int k) {
             const Rec& r = recs[k];
-            if (i < r.ry0 || i >= r.ry1 || j < r.rx0 || j >= r.rx1) continue;
+            if (i < r.ry0 || i >= r.ry1 || j < r.rx0 || j >= r.rx1) return;
             ++hits;
             dst.cls(5, r.cls);
             if (paints_later(r.area, k, best_area, best)) best = k, best_area = r.area;
+            if (p.mode == CN_GAUSSIAN) heat = fmaxf(heat, gauss_heat(r, i, j));
+        };
+        if constexpr (kNear) {
+#pragma unroll
+            for (int w = 0; w < kCandWords; ++w)
+                for (unsigned m = near[w]; m; m &= m - 1) visit(cand[32 * w + __ffs(m) - 1]);
+        } else {
+            for (int q = 0; q < ncand; ++q) visit(cand[q]);
         }
         if (best < 0) return 0;
         const Rec& r = recs[best];
@@ -710,22 +748,17 @@ struct CenterNetPolicy {
         dst.reg(1, live_y ? fmaxf(0.f, fsub(r.r2, fi)) : fmaxf(0.f, fsub(fsub(r.r2, static_cast<float>(i)), 0.5f)));
         dst.reg(2, fmaxf(0.f, fsub(fj, r.r1)));
         dst.reg(3, live_x ? fmaxf(0.f, fsub(r.r3, fj)) : fmaxf(0.f, fsub(fsub(r.r3, static_cast<float>(j)), 0.5f)));
-        float heat = 1.0f;
-        if (p.mode == CN_GAUSSIAN) {
-            // canonical CenterNet splat: the heat of a cell is the MAXIMUM over the boxes whose footprint covers it of
-            // gaussian_dist_2d (the reference's commented-out code, tf_centernet.py:30-40) -- order-free, no atomics
-            heat = 0.f;
-            for (int q = 0; q < ncand; ++q) {
-                const Rec& c = recs[cand[q]];
-                if (i < c.ry0 || i >= c.ry1 || j < c.rx0 || j >= c.rx1) continue;
-                heat = fmaxf(heat, gauss_heat(c, i, j));
+        // CN_GAUSSIAN, the canonical CenterNet splat: the heat of a cell is the MAXIMUM over the boxes whose footprint covers it
+        // of gaussian_dist_2d (the reference's commented-out code, tf_centernet.py:30-40) -- order-free, no atomics; gathered above
+        if (p.mode != CN_GAUSSIAN) {
+            heat = 1.0f;
+            if (!(i == r.muy && j == r.mux) && (live_y || live_x)) {
+                // max over the footprint is reached at the centre cell: 1/0.5^8 = 256 per live axis
+                double v = 1.0;
+                if (live_y) v = dmul(v, inv_pow8(static_cast<double>(fi) - static_cast<double>(r.muy)) * (1.0 / 256.0));
+                if (live_x) v = dmul(v, inv_pow8(static_cast<double>(fj) - static_cast<double>(r.mux)) * (1.0 / 256.0));
+                heat = static_cast<float>(v);
             }
-        } else if (!(i == r.muy && j == r.mux) && (live_y || live_x)) {
-            // max over the footprint is reached at the centre cell: 1/0.5^8 = 256 per live axis
-            double v = 1.0;
-            if (live_y) v = dmul(v, inv_pow8(static_cast<double>(fi) - static_cast<double>(r.muy)) * (1.0 / 256.0));
-            if (live_x) v = dmul(v, inv_pow8(static_cast<double>(fj) - static_cast<double>(r.mux)) * (1.0 / 256.0));
-            heat = static_cast<float>(v);
         }
         dst.reg(4, heat);
         return hits;
