@@ -40,7 +40,7 @@ __global__ void box_convert_kernel(const float4* __restrict__ in, long long n, i
 
 __global__ void prepare_labels_kernel(const float* __restrict__ raw, const float* __restrict__ classes, const int* __restrict__ offsets,
                                       const int* __restrict__ nbox, const int* __restrict__ flip, int batch, int max_boxes, int in_stride,
-                                      float* __restrict__ out, int* __restrict__ out_nbox) {
+                                      float* __restrict__ out, int* __restrict__ out_nbox, int* __restrict__ status) {
     const int total = batch * max_boxes;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int b = e / max_boxes, k = e - b * max_boxes;
@@ -48,6 +48,7 @@ __global__ void prepare_labels_kernel(const float* __restrict__ raw, const float
         const int n = max(0, min(n_in, max_boxes));
         float* o = out + static_cast<long long>(e) * 5;
         if (k == 0 && out_nbox) out_nbox[b] = n;
+        if (k == 0 && n_in > max_boxes && status) atomicOr(status, DH_STATUS_TRUNCATED);
         if (k >= n) {
             o[0] = o[1] = o[2] = o[3] = o[4] = 0.f;
             continue;
@@ -135,7 +136,7 @@ int dh_prepare_labels(dh_handle_t h, const float* raw_boxes, const float* classe
     if (batch == 0) return DH_OK;
     DeviceGuard guard(h);
     prepare_labels_kernel<<<grid1d(static_cast<long long>(batch) * max_boxes, 256, h->sm_count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        raw_boxes, classes, box_offsets, nbox, flip, batch, max_boxes, in_max_boxes, out_labels, out_nbox);
+        raw_boxes, classes, box_offsets, nbox, flip, batch, max_boxes, in_max_boxes, out_labels, out_nbox, h->dev_status);
     DH_CUDA(cudaGetLastError());
     h->launches += 1;
     return DH_OK;

@@ -9,7 +9,7 @@ keeps everything on the device.  All arithmetic runs in libdensehead.so (hand-wr
 `include/densehead.h`); there is no CPU fallback.
 """
 from . import _capi
-from ._capi import DenseHeadError, launch_count, set_option  # noqa: F401
+from ._capi import DenseHeadError, launch_count, raise_for_status, set_option, status  # noqa: F401
 from . import fcos, retinanet, centernet, prep, distributed  # noqa: F401
 
 __all__ = ["fcos", "retinanet", "centernet", "prep", "distributed", "DenseHeadError", "launch_count", "set_option", "version"]

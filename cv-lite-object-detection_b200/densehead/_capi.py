@@ -17,7 +17,7 @@ DH_ERR_BAD_ARG, DH_ERR_SHAPE, DH_ERR_CUDA, DH_ERR_CAPACITY, DH_ERR_NCCL = -1, -2
 DH_OPT_TMA_STORE, DH_OPT_TILE_BYTES, DH_OPT_CTAS_PER_SM = 1, 2, 3
 DH_OPT_LOSS_ALLREDUCE, DH_OPT_ALLREDUCE, DH_OPT_FUSED_TAIL, DH_OPT_ENCODE_KERNEL, DH_OPT_FUSED_MAX_CHUNK = 11, 12, 13, 14, 15
 DH_OPT_NMS_FILTER, DH_OPT_NMS_CHAIN = 16, 17
-DH_STATUS_BAD_SCALE, DH_STATUS_BAD_CLASS, DH_STATUS_COMM_TIMEOUT = 1, 2, 4
+DH_STATUS_BAD_SCALE, DH_STATUS_BAD_CLASS, DH_STATUS_COMM_TIMEOUT, DH_STATUS_TRUNCATED = 1, 2, 4, 8
 DH_UNIQUE_ID_BYTES, DH_IPC_HANDLE_BYTES = 128, 64
 DH_MAX_BOXES_PER_IMAGE = 256
 
@@ -144,6 +144,8 @@ def raise_for_status(device_index=0):
         raise ValueError("min() arg is an empty sequence (a box is not below the largest box scale)")
     if bits & DH_STATUS_COMM_TIMEOUT:
         raise DenseHeadError("a peer rank did not arrive at the loss all-reduce")
+    if bits & DH_STATUS_TRUNCATED:
+        raise ValueError("prepare_labels dropped boxes: an image has more boxes than max_boxes")
 
 
 def set_option(device_index, option, value):

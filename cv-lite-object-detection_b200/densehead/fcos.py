@@ -270,13 +270,19 @@ def detect_batch(head_outputs, num_classes, img_pad, center=False, iou_thresh=0.
     """FCOS/infer_fcos.py:27-62 for a batch, one library call (dh_fcos_detect): decode -> per-level top-k of the
     (location, class) scores above cls_thresh -> per-class greedy NMS with the combined-NMS caps.  Returns zero-padded
     (boxes [B, T, 4], scores [B, T], classes [B, T], valid [B]) with T = max_total_size, like
-    tf.image.combined_non_max_suppression.  `pre_nms_topk` bounds the candidates per level (the reference has none;
-    a value >= the number of scores above the threshold reproduces it)."""
+    tf.image.combined_non_max_suppression.
+
+    DEVIATION from the reference, which hands EVERY (location, class) score above `cls_thresh` to the NMS: at most
+    `pre_nms_topk` pairs per level go in (the best ones; exact, ties by index), and levels * pre_nms_topk <= 16384.  The
+    result equals the reference's whenever no level has more passing scores than that; `pre_nms_topk=None` takes the
+    largest value the NMS holds (16384 // levels = 3276 per level for five levels), the closest to the reference."""
     strides = list(DEFAULT_STRIDES if strides is None else strides)
     dev = current_device()
     heads = _as_batched(head_outputs, dev)
     batch, t = int(heads[0].shape[0]), int(max_total_size)
     longest = max([h * w * int(num_classes) for h, w in level_shapes(img_pad, strides)] + [1])
+    if pre_nms_topk is None:
+        pre_nms_topk = 16384 // len(strides)
     k = int(min(pre_nms_topk, longest))
     boxes = torch.empty((batch, t, 4), dtype=torch.float32, device=dev)
     scores = torch.empty((batch, t), dtype=torch.float32, device=dev)
@@ -316,9 +322,10 @@ def ground_truth_detections(img_labels, num_classes, image_shapes, img_rows=384,
 
 
 def image_detections(image, model, num_classes, center=False, iou_thresh=0.5, cls_thresh=0.05, max_detections=100,
-                     max_total_size=100, head_outputs=None, pre_nms_topk=1000):
+                     max_total_size=100, head_outputs=None, pre_nms_topk=None):
     """FCOS/infer_fcos.py:27 `image_detections`.  `model(image, training=False)` must return the per-level head
-    outputs [1, Hl, Wl, C+5] (or pass them as `head_outputs`)."""
+    outputs [1, Hl, Wl, C+5] (or pass them as `head_outputs`).  `pre_nms_topk=None` (default): as many candidates per
+    level as the NMS holds -- see `detect_batch` for the one deviation from the reference (a cap it does not have)."""
     heads = head_outputs if head_outputs is not None else model(image, training=False)
     dev = current_device()
     hb = _as_batched(heads, dev)

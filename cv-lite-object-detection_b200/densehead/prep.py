@@ -51,10 +51,17 @@ def prepare_labels(bboxes, classes, flip=None, max_boxes=None, offsets=None, nbo
 
     Either a list of per-image `[n_i, 4]` (xmin, ymin, xmax, ymax) arrays with a matching list of class-id arrays (packed
     ragged on the host, one copy), or ragged device tensors `bboxes [total, 4]`, `classes [total]` with `offsets [B+1]`, or
-    padded `[B, n, 4]` / `[B, n]` tensors with `nbox`."""
+    padded `[B, n, 4]` / `[B, n]` tensors with `nbox`.
+
+    `max_boxes` defaults to the longest image, so nothing is dropped.  An explicit `max_boxes` smaller than an image's box
+    count keeps that image's first `max_boxes` boxes (the reference keeps all of them, FCOS/train_fcos.py:131-135): with
+    host lists this raises ValueError here; with device inputs the kernel sets DH_STATUS_TRUNCATED, which
+    `densehead.raise_for_status()` turns into the same ValueError (a synchronising read)."""
     dev = current_device()
     if isinstance(bboxes, (list, tuple)):
         counts = [len(b) for b in bboxes]
+        if max_boxes is not None and counts and max(counts) > int(max_boxes):
+            raise ValueError("prepare_labels: an image has %d boxes, max_boxes is %d" % (max(counts), int(max_boxes)))
         offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
         bboxes = np.concatenate([np.asarray(b, np.float32).reshape(-1, 4) for b in bboxes] + [np.zeros((0, 4), np.float32)])
         classes = np.concatenate([np.asarray(c, np.float32).reshape(-1) for c in classes] + [np.zeros((0,), np.float32)])

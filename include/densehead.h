@@ -75,6 +75,7 @@ int dh_read_phase_timing(dh_handle_t h, long long* out8 /*[host] [8]*/);
 #define DH_STATUS_BAD_SCALE 1
 #define DH_STATUS_BAD_CLASS 2
 #define DH_STATUS_COMM_TIMEOUT 4
+#define DH_STATUS_TRUNCATED 8 /* dh_prepare_labels met an image with more boxes than max_boxes and kept the first max_boxes (the reference keeps all: FCOS/train_fcos.py:131-135) */
 int dh_get_status(dh_handle_t h, int32_t* out /*[host] [1]*/, int reset);
 /* Profiling aid: while `buf` ([dev], `bytes` long; NULL switches it off) is set, every fused encode+loss launch whose
  * grid fits writes 12 values per CTA b: buf[12b+0] = start, [1] = first chunk staged, [2] = chunk loop done (globaltimer
@@ -167,7 +168,8 @@ int dh_box_convert(dh_handle_t h, const float* boxes /*[dev] [n,4]*/, long long 
  * [B, max_boxes, 5] (cy, cx, h, w, class) + nbox layout the encoders take: per-image optional horizontal flip,
  * swap_xy, convert_to_xywh, concat with the class (FCOS/data_preprocess.py:121-131, FCOS/train_fcos.py:131-135).
  * Input is ragged when box_offsets ([B+1], rows of image b are [off[b], off[b+1])) is given, else padded
- * [B, in_max_boxes, 4] with optional nbox.  Images with more than max_boxes rows are truncated (out_nbox says so). */
+ * [B, in_max_boxes, 4] with optional nbox.  Images with more than max_boxes rows are truncated to the first max_boxes:
+ * out_nbox holds the kept count and DH_STATUS_TRUNCATED is set (dh_get_status). */
 int dh_prepare_labels(dh_handle_t h, const float* raw_boxes /*[dev]*/, const float* classes /*[dev] float32, indexed like raw_boxes*/,
                       const int32_t* box_offsets /*[dev] [B+1] or NULL*/, const int32_t* nbox /*[dev] [B] or NULL*/,
                       const int32_t* flip /*[dev] [B] or NULL*/, int batch, int in_max_boxes, int max_boxes,

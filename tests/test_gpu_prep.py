@@ -45,6 +45,11 @@ def test_prepare_labels_ragged_padded_and_flip(golden):
         pad[i, :counts[i]], pc[i, :counts[i]] = boxes[i], classes[i]
     lab2, nb2 = dh.prep.prepare_labels(pad, pc, flip=flip, nbox=counts, max_boxes=8)
     assert nb2.cpu().numpy().tolist() == [7, 0, 8, 8]
+    from densehead import _capi
+    assert _capi.status(0) & _capi.DH_STATUS_TRUNCATED  # the kernel says that it dropped boxes (and the read clears the bit)
+    assert not _capi.status(0) & _capi.DH_STATUS_TRUNCATED
+    with pytest.raises(ValueError):  # host lists: the wrapper knows the counts
+        dh.prep.prepare_labels(boxes, classes, max_boxes=8)
     assert np.array_equal(lab2.cpu().numpy()[2], lab[2, :8])
     # feeds the encoders directly
     outs, cnt = dh.fcos.format_data_batch(lab2, nb2, [512, 512], 20, [512, 512])
