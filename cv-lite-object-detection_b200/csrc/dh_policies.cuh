@@ -649,7 +649,7 @@ struct CenterNetPolicy {
     // gaussian_dist_2d of tf_centernet.py:30-40 on the footprint grid (cells at z + 0.5, integer mean): exp(-d^2 / (2 std^2))
     // over the live axes, divided by its maximum over the footprint (reached 0.5 cells from the mean on every live axis);
     // the centre cell is forced to 1 like the reference does for its fall-off (:261-262).  The specification
-    // (oracle.centernet_gaussian_format_data) evaluates the exponent and exp in float64 and rounds once; here the exponent
+    // (centernet_gaussian_format_data of the CPU oracle) evaluates the exponent and exp in float64 and rounds once; here the exponent
     // is carried as an unevaluated sum of two floats -- d^2 is exact in float32, 1 / (2 std^2) is a float64 split in two,
     // the product's rounding error comes out of an fma -- and exp(hi + lo) = expf(hi) * (1 + lo): within 2 ulp of float32
     // of the specified value (the parity tests allow 2e-6 relative), for a dozen float32 instructions instead of a
