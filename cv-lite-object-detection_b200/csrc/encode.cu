@@ -40,7 +40,7 @@ int finish_table(TileTable& tt, int ch, int batch, int tile_bytes) {
 }
 
 // Output bytes up to which DH_OPT_ENCODE_KERNEL = 0 picks the direct-store kernel (measured on B200)
-constexpr long long kDirectMaxBytes = 192ll << 20;
+constexpr long long kDirectMaxBytes = 512ll << 20;
 
 static long long map_bytes(const TileTable& tt, int ch, int batch) {
     long long bytes = 0;
@@ -68,6 +68,16 @@ static int launch_encode_direct(dh_handle_s* h, EncodeArgs<P>& a, cudaStream_t s
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_direct_kernel<P>, DH_THREADS, lay.total));
     if (per_sm < 1) per_sm = 1;
     // one wave of resident CTAs when the chunks then hold 8..128 KB each
+    // Chunks per SM the problem is cut into (measured, tools/encode_ab.py with this value swept 2..16 on FCOS-VOC and
+    // CenterNet-s8 shapes from 0.5 to 420 MB): a large output wants many medium chunks -- 14 per SM from 128 MB on: 140 MB in
+    // 34.7 us against 38.4 with 4 per SM, 419 MB in 78.4 us against 93.8 (and 86.5 for the tile streamer) --, a small one few
+    // CTAs (4 per SM below 24 MB: 8 images of 4.4 MB in 6.3 us against 8.8 with 8 per SM); images with many boxes want
+    // large chunks whatever the size, because every chunk rebuilds the image's records (3 per SM: CenterNet, 150 boxes,
+    // 52 MB in 16.4 us against 17.7).
+    if (bytes >= (128ll << 20)) per_sm = 14;
+    else if (a.max_boxes > 64) per_sm = 3;
+    else if (bytes < (24ll << 20)) per_sm = per_sm < 4 ? per_sm : 4;
+    else per_sm = 8;
     long long want_bytes = bytes / (static_cast<long long>(h->sm_count) * per_sm) + 1;
     const long long tile_b = static_cast<long long>(a.tt.rows_per_tile) * ch * 4;
     long long want = (want_bytes + tile_b - 1) / tile_b;
