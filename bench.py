@@ -8,9 +8,14 @@
 Workload (BASELINE.json configs[4], "full dense-head target+loss step"): RetinaNet COCO-shaped
 batches -- 640x640, 5 levels x 9 anchors, 80 classes, <= 100 GT boxes per image, 256 images per GPU.
 One step = anchor matching + box encoding + focal / smooth-L1 loss for every image of the batch
-(fused: targets are produced in shared memory and consumed there), followed at N > 1 by one NCCL
-all-reduce of the 4 loss scalars.  Images are sharded across ranks; per-GPU work is fixed, so scaling
-is "weak" and `value` counts the images all ranks processed.
+(fused: ONE kernel launch; the targets never reach HBM), including at N > 1 the sum of the 4 loss
+scalars over the ranks, which the kernel's last CTA exchanges over NVLink peer mailboxes (dh_comm_*;
+NCCL or a separate launch with --transports / --no-fuse).  Images are sharded across ranks.  `value`
+is the WEAK configuration (256 images per GPU: per-GPU work fixed, all ranks' images counted); the
+`strong` object holds BASELINE's "batch 256 sharded over 1/2/4/8 GPUs" (256 / N images per GPU) with
+`sum_parity`: the all-reduced total against rank 0 running the whole batch alone.  Before anything is
+timed, `parity` compares the step's per-image losses with the CPU oracle (`parity_checked`); a
+mismatch exits 1.  The timed region replays CUDA graphs of up to five steps each (see timed_graph).
 
   value   images/s with boxes and predictions already resident in HBM (CUDA-event timed graph replays).
   e2e     images/s through the public Python API (`densehead.retinanet.encode_loss_batch`) with HOST
