@@ -99,6 +99,24 @@ def test_gpu_random_batch_matches_the_oracle(canvas):
 
 
 @pytest.mark.gpu
+def test_gpu_full_batch_matches_the_oracle():
+    """256 images x up to 30 objects on the script's 448 x 448 canvas (about 10 M entries): every image against the oracle."""
+    torch = pytest.importorskip("torch")
+    import densehead as dh
+    rng = np.random.default_rng(78)
+    B = 256
+    obj, n = _random_objects(rng, B, 30, 640, 480)
+    src = np.stack([rng.choice([640.0, 500.0, 448.0, 1024.0], B), rng.choice([480.0, 375.0, 448.0, 333.0], B)], axis=1)
+    idx, val, off = dh.fcos.sparse_format_batch(obj, n, src)
+    idx, val, off = idx.cpu().numpy(), val.cpu().numpy(), off.cpu().numpy()
+    assert off[0] == 0 and off[-1] == len(val) and np.all(np.diff(off) >= 0)
+    for b in range(B):
+        wi, wv = O.fcos_sparse_format(obj[b, :n[b]], src[b])
+        assert off[b + 1] - off[b] == len(wv), b
+        assert _same(idx[off[b]:off[b + 1]], wi) and _same(val[off[b]:off[b + 1]], wv), b
+
+
+@pytest.mark.gpu
 def test_gpu_capacity_is_respected():
     torch = pytest.importorskip("torch")
     import densehead as dh
