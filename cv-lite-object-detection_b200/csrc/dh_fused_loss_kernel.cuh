@@ -204,7 +204,8 @@ struct SegLists {
     unsigned short* box;      // [kMaxSegments][box_cap] those boxes, in no particular order
     uint32_t* pairs;          // [kMaxPairs] chunk row << 16 | box, in no particular order
     unsigned short* next;     // [kMaxPairs] the pair appended before this one for the same row (kNoPair: none)
-    uint32_t* head;           // [kMaxChunkTiles * 256] per chunk row: the last pair appended for it (kNoPair between chunks)
+    uint32_t* head;           // [kMaxChunkTiles * 256 / 2] per chunk row, 16 bits each: the last pair appended for it (kNoPair between
+                              // chunks); two rows share a word (head_exchange), which keeps the kernel under the 48 KB carve-out step
     uint32_t* rowbits;        // [kMaxChunkTiles * 8] one bit per chunk row: has a pair (zero between chunks)
     unsigned short* rowlist;  // [kMaxPairs] the chunk rows that have pairs, ascending (scan_rows)
     int* tile_tab;            // [kMaxChunkTiles][4] per tile of the chunk: map, first row, segment, rows
@@ -213,6 +214,19 @@ struct SegLists {
     int* span_ctr;            // [4] [0] next span to hand out (zero between chunks), [1] spans of the chunk
 };
 constexpr uint32_t kNoPair = 0xffffu;
+// the row's 16-bit slot of the head table: swap in `val`, return what was there (shared-memory atomics are 32 bits wide:
+// a compare-and-swap on the word the row shares with its neighbour; rows of a chunk rarely collide)
+__device__ __forceinline__ uint32_t head_exchange(uint32_t* head, int row, uint32_t val) {
+    uint32_t* w = head + (row >> 1);
+    const int sh = (row & 1) * 16;
+    uint32_t old = *w, assumed;
+    do {
+        assumed = old;
+        old = atomicCAS(w, assumed, (assumed & ~(0xffffu << sh)) | (val << sh));
+    } while (old != assumed);
+    return (old >> sh) & 0xffffu;
+}
+__device__ __forceinline__ uint32_t head_take(uint32_t* head, int row) { return head_exchange(head, row, kNoPair); }
 template <class P>
 __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     FusedSmemLayout l;
@@ -220,15 +234,15 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     l.raw_off = (static_cast<int>(sizeof(typename P::Rec)) * box_cap + 127) & ~127;
     l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
     l.seg_off = l.cand_off;
-    l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 4 + 32 + 16) + kMaxSpans * 16 + 16;  // SegLists
+    l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 2 + 32 + 16) + kMaxSpans * 16 + 16;  // SegLists
     l.misc_off = l.run_off + DH_THREADS * kRunCap * 2;  // resolve_pass: the boxes of the row a lane resolves
     l.args_off = l.misc_off + 512;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
-    // Mind the total: it decides the shared-memory carve-out of the SM.  RetinaNet-COCO (box_cap 128) comes to 49 040 bytes;
-    // four CTAs of <= 48 KB (+ 1 KB each that the system keeps) fit the 196 KB carve-out and leave 60 KB of L1 for the
-    // loads in flight.  At 53 KB per CTA the SM takes the 228 KB carve-out, 28 KB of L1 remain, and the streaming pass
-    // loses a fifth of its rate (measured: 1 218 us against 1 021 us for 256 COCO images; 92 KB of L1 -- 38 KB per CTA with
-    // 8-tile chunks -- buy nothing further).
+    // Mind the total: it decides the shared-memory carve-out of the SM.  Four CTAs of <= 48 KB (+ 1 KB each that the system
+    // keeps) fit the 196 KB carve-out and leave 60 KB of L1 for the loads in flight; at 53 KB per CTA the SM takes the 228 KB
+    // carve-out, 28 KB of L1 remain, and the streaming pass loses a fifth of its rate (measured: 1 218 us against 1 021 us
+    // for 256 COCO images; 92 KB of L1 buy nothing further).  With the 16-bit head table RetinaNet-COCO (box_cap 128) comes
+    // to 40 848 bytes, FCOS and CenterNet with up to 160 boxes per image stay under 48 KB too (47 504).
     return l;
 }
 
@@ -509,7 +523,7 @@ __device__ __forceinline__ SegLists seg_lists(unsigned char* base, int box_cap) 
     L.nmap = reinterpret_cast<int*>(base);
     L.npairs = L.nmap + kMaxSegments;
     L.head = reinterpret_cast<uint32_t*>(base + 128);
-    L.pairs = L.head + kMaxChunkTiles * DH_THREADS;
+    L.pairs = L.head + kMaxChunkTiles * DH_THREADS / 2;
     L.rowbits = L.pairs + kMaxPairs;
     L.tile_tab = reinterpret_cast<int*>(L.rowbits + kMaxChunkTiles * 8);
     L.span_sum = reinterpret_cast<float*>(L.tile_tab + kMaxChunkTiles * 4);
@@ -653,7 +667,7 @@ __device__ __forceinline__ void pair_pass(const LossArgs<P>& a, const typename P
                         at = __shfl_sync(0xffffffffu, at, 0) + __popc(okb & ((1u << lane) - 1u));
                         if (ok && at < kMaxPairs) {  // append, and chain to the row's earlier pairs
                             L.pairs[at] = (static_cast<uint32_t>(local0 + row) << 16) | static_cast<uint32_t>(bk);
-                            L.next[at] = static_cast<unsigned short>(atomicExch(L.head + local0 + row, static_cast<uint32_t>(at)));
+                            L.next[at] = static_cast<unsigned short>(head_exchange(L.head, local0 + row, static_cast<uint32_t>(at)));
                             atomicOr(L.rowbits + ((local0 + row) >> 5), 1u << ((local0 + row) & 31));
                         }
                     }
@@ -710,9 +724,8 @@ __device__ __noinline__ LossAcc resolve_pass(const LossArgs<P>& a, const typenam
         if (p < n_rows) {
             const int crow = L.rowlist[p];
             int len = 0;
-            for (uint32_t q = L.head[crow]; q != kNoPair; q = L.next[q], ++len)
+            for (uint32_t q = head_take(L.head, crow); q != kNoPair; q = L.next[q], ++len)
                 if (len < kRunCap) mine[len] = static_cast<unsigned short>(L.pairs[q] & 0xffffu);
-            L.head[crow] = kNoPair;  // (this lane is the row's only reader)
             const int tix = crow / rpt;
             const int m = L.tile_tab[tix * 4 + 0], r0 = L.tile_tab[tix * 4 + 1], seg = L.tile_tab[tix * 4 + 2];
             const MapDesc& md = a.tt.maps[m];
@@ -956,7 +969,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         mbar_init_fence();
     }
     if (tid <= kMaxSegments) segs.nmap[tid] = 0;  // nmap[], npairs
-    for (int e = tid; e < kMaxChunkTiles * DH_THREADS; e += DH_THREADS) segs.head[e] = kNoPair;
+    for (int e = tid; e < kMaxChunkTiles * DH_THREADS / 2; e += DH_THREADS) segs.head[e] = 0xffffffffu;
     if (tid < kMaxChunkTiles * 8) segs.rowbits[tid] = 0u;
     if (tid == 0) *segs.span_ctr = 0, next_img[0] = -1;
     const int span_batch = 32 * (kGrad ? 5 : 7);  // items of one load batch of stream_vec
@@ -1088,7 +1101,7 @@ __global__ void __launch_bounds__(DH_THREADS, 4) fused_loss_kernel(const __grid_
         if (n_boxes > 0) {  // (the correct pass is done with the lists) counters and row chains back to empty
             if (tid <= kMaxSegments) segs.nmap[tid] = 0;
             if (segs.npairs[2]) {  // the pair list overflowed (resolve_pass leaves both tables empty; the dense visit does not use them)
-                for (int e = tid; e < kMaxChunkTiles * DH_THREADS; e += DH_THREADS) segs.head[e] = kNoPair;
+                for (int e = tid; e < kMaxChunkTiles * DH_THREADS / 2; e += DH_THREADS) segs.head[e] = 0xffffffffu;
                 if (tid < kMaxChunkTiles * 8) segs.rowbits[tid] = 0u;
             }
         }
