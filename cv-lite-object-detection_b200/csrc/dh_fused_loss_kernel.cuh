@@ -187,7 +187,8 @@ __device__ __forceinline__ float cen_l1_zero(float x, float delta) {
 }
 
 constexpr int kTraceSlots = 12;  // dh_set_trace: longs per CTA
-constexpr int kMaxChunkTiles = 16;  // tiles (of 256 rows) per scheduler chunk at most (launch_fused_g)
+constexpr int kMaxChunkTiles = 18;  // tiles (of 256 rows) per scheduler chunk at most (launch_fused_g: 16 in the tiered plans, up to 18
+                                    // when equal chunks of that size give every CTA exactly one -- 32 COCO images: 576 chunks of 18 tiles)
 constexpr int kMaxSegments = kMaxChunkTiles;  // ... so a chunk meets at most as many maps
 // A tile (256 rows) is streamed as 2 spans; the chunk's last tiles as 4, 4, 8 and up to 32 (see span_plan)
 constexpr int kMaxSpans = (kMaxChunkTiles - 4) * 2 + 4 + 4 + 8 + 32;
@@ -235,14 +236,15 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int box_cap) {
     l.cand_off = l.raw_off + ((box_cap * 20 + 127) & ~127);
     l.seg_off = l.cand_off;
     l.run_off = l.seg_off + 128 + kMaxSegments * box_cap * 2 + kMaxPairs * 8 + kMaxChunkTiles * (DH_THREADS * 2 + 32 + 16) + kMaxSpans * 16 + 16;  // SegLists
-    l.misc_off = l.run_off + DH_THREADS * kRunCap * 2;  // resolve_pass: the boxes of the row a lane resolves
+    l.misc_off = l.run_off + (DH_THREADS / 2) * kRunCap * 2;  // resolve_pass (run by the four helper warps): the boxes of the row a lane resolves
     l.args_off = l.misc_off + 512;
     l.total = l.args_off + ((static_cast<int>(sizeof(LossArgs<P>)) + 127) & ~127);
-    // Mind the total: it decides the shared-memory carve-out of the SM.  Four CTAs of <= 48 KB (+ 1 KB each that the system
-    // keeps) fit the 196 KB carve-out and leave 60 KB of L1 for the loads in flight; at 53 KB per CTA the SM takes the 228 KB
-    // carve-out, 28 KB of L1 remain, and the streaming pass loses a fifth of its rate (measured: 1 218 us against 1 021 us
-    // for 256 COCO images; 92 KB of L1 buy nothing further).  With the 16-bit head table RetinaNet-COCO (box_cap 128) comes
-    // to 40 848 bytes, FCOS and CenterNet with up to 160 boxes per image stay under 48 KB too (47 504).
+    // Mind the total: it decides the shared-memory carve-out of the SM, and what the carve-out leaves is the L1 that the
+    // loads in flight land in.  Four CTAs of <= 40 KB (+ 1 KB each that the system keeps) fit the 164 KB carve-out (92 KB of
+    // L1); up to 48 KB the 196 KB one (60 KB of L1: 2-5 % slower from 48 COCO images up -- 565 us against 537 at 128, 1 038
+    // against 1 020 at 256); at 53 KB per CTA the SM takes the 228 KB carve-out, 28 KB of L1 remain, and the streaming pass
+    // loses a fifth of its rate (1 218 us at 256 images).  RetinaNet-COCO (box_cap 128) comes to 39 984 bytes: the 16-bit
+    // head table, the run lists sized for the four helper warps and kMaxChunkTiles = 18 are chosen against that step.
     return l;
 }
 

@@ -198,7 +198,7 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
         want = total / (grid * h->fused_chunks_per_cta);
         want = want < 4 ? 4 : (want > 8 ? 8 : want);
     }
-    // A small launch -- at most four chunks per CTA -- is better off with equal chunks when their number fills whole waves of the
+    // A small launch -- at most three chunks per CTA (four waves of 18-tile chunks at 128 COCO images: 555 us against 537 us with tiers) -- is better off with equal chunks when their number fills whole waves of the
     // grid: every CTA then does the same k chunks and nothing is left to balance (32 COCO images: 1 152 chunks of 9 tiles
     // for 592 CTAs, 166 us against 175-182 us with tiers of 9, 4, 2 tiles).  The largest chunk whose last wave is at least
     // 85 % full wins (the fill of the last wave IS the efficiency of such a plan); without one (128 images: 5.19 waves of 14-tile chunks) the tiers take care of the tail.
@@ -206,10 +206,10 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     if ((h->fused_tail & 1) && a.tt.tiles_per_image > 0 && static_cast<int>(static_cast<unsigned>(h->fused_tail) >> 8) == 0) {
         double best = 0.0;
         const int tpi = a.tt.tiles_per_image;
-        for (int c = h->fused_max_chunk; c >= (min_tiles > 4 ? min_tiles : 4); --c) {
+        for (int c = (h->fused_max_chunk == 16 ? kMaxChunkTiles : h->fused_max_chunk); c >= (min_tiles > 4 ? min_tiles : 4); --c) {
             const int cpi = (tpi + c - 1) / c;
             const long long n = static_cast<long long>(cpi) * a.tt.batch, waves = (n + grid - 1) / grid;
-            if (waves > 4) break;
+            if (waves > 3) break;
             const double fill = static_cast<double>(n) / static_cast<double>(waves * grid);
             if (fill > best + 0.02) best = fill, uniform = (tpi + cpi - 1) / cpi;
         }
