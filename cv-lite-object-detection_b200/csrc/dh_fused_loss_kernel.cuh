@@ -688,14 +688,15 @@ __device__ __forceinline__ void pair_pass(const LossArgs<P>& a, const typename P
 // The chunk rows that have pairs, in ascending order (one warp; the row map goes back to zero).  Returns their number.
 __device__ __forceinline__ int scan_rows(const SegLists& L) {
     const int lane = threadIdx.x & 31;
-    constexpr int kPer = kMaxChunkTiles * 8 / 32;  // words per lane
+    constexpr int kWords = kMaxChunkTiles * 8, kPer = (kWords + 31) / 32;  // words per lane (rounded UP: 144 words are 4.5 per lane)
     uint32_t w[kPer];
     int cnt = 0;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
-        w[u] = L.rowbits[lane * kPer + u];
+        const int i = lane * kPer + u;
+        w[u] = i < kWords ? L.rowbits[i] : 0u;
         cnt += __popc(w[u]);
-        L.rowbits[lane * kPer + u] = 0u;
+        if (i < kWords) L.rowbits[i] = 0u;
     }
     int incl = cnt;
 #pragma unroll

@@ -309,3 +309,42 @@ def test_retina_loss_batch_of_one_returns_gradients_too():
     assert torch.equal(out[0], pi) and torch.equal(out[1], tot)
     want = O.dense_loss_grad(lab[2][0].cpu().numpy(), pred[2][0], weights=(1.0, 0.5, 0.0), reg_ch=4, cen_mode=0, pos_rule="gt0")
     assert np.all(np.abs(out[2][2][0].cpu().numpy() - want) <= 2e-5 * np.maximum(1.0, np.abs(want)))
+
+
+@pytest.mark.parametrize("batch", [16, 32, 40, 64, 96])
+def test_chunk_plans_agree_at_the_bench_shapes(batch):
+    """The host plans the fused kernel's chunks differently per batch size (equal chunks of up to 18 tiles for small
+    launches, tiers of 16 / 8 / 4 / 2 tiles otherwise); whatever the plan, the per-image sums are those of the uniform
+    8-tile plan (DH_OPT_FUSED_TAIL = 0) to float32 summation order, and the positive counts are the same integers.  (A
+    plan-specific bug -- rows of a chunk's 17th and 18th tile never resolved -- once passed every test that only ran the
+    tiered plans.)"""
+    dh = _dh()
+    from densehead import _capi
+    boxes, nbox = synth.config_boxes("retina_coco", batch, synth.seed_for(5, 400 + batch))
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(batch)
+    pred = []
+    for h in (80, 40, 20, 10, 5):
+        p = torch.empty((batch, 9, h, h, 84), device="cuda")
+        p[..., :4].uniform_(-1, 2, generator=gen)
+        p[..., 4:].normal_(-4.595, 1.0, generator=gen)
+        pred.append(p)
+    res = {}
+    for tail in (1, 0):
+        dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
+        try:
+            pi, tot, pairs = dh.retinanet.encode_loss_batch(boxes, nbox, [640, 640], 80, [640, 640], pred)
+        finally:
+            dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, 1)
+        res[tail] = (pi.cpu().numpy(), tot.cpu().numpy(), pairs.cpu().numpy())
+    assert np.array_equal(res[1][0][:, 3], res[0][0][:, 3]) and np.array_equal(res[1][2], res[0][2])
+    assert np.allclose(res[1][0][:, :3], res[0][0][:, :3], rtol=2e-6, atol=1e-4)
+    assert np.allclose(res[1][1][:3], res[0][1][:3], rtol=2e-6)
+    # and one image of the batch against the oracle
+    b = batch // 2
+    lab, n_pairs = O.retina_format_data(boxes[b, :nbox[b]], [640, 640], 80)
+    want = O.retina_train_loss(lab, [[p[b, a].cpu().numpy() for a in range(9)] for p in pred])
+    got = res[1][0][b]
+    assert int(res[1][2][b]) == n_pairs
+    assert_close(got[:2], np.array([float(want[0]), float(want[1])]), 1e-5, what="image %d of %d" % (b, batch))
+
