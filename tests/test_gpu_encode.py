@@ -191,3 +191,30 @@ def test_full_size_properties():
         assert cnt[bi].tolist() == wc
         for l in range(5):
             _same(outs[l][bi].cpu().numpy(), want[l], "c5 b%d L%d" % (bi, l), soft_channels=(4,))
+
+
+@pytest.mark.parametrize("family,batch", [("fcos", 256), ("centernet", 80), ("centernet", 256), ("retina", 16), ("retina", 3)])
+def test_both_encoder_kernels_agree_at_every_chunking_rule(family, batch):
+    """The direct-store kernel cuts its chunks by output size and boxes per image (14 chunks per SM from 128 MB on, 3 for
+    images with more than 64 boxes, 4 below 24 MB, 8 otherwise); whatever the rule, it writes the bytes the tile streamer
+    writes (which the golden and oracle tests above pin)."""
+    dh = _dh()
+    from densehead import _capi
+    if family == "fcos":
+        boxes, nbox = synth.config_boxes("fcos_voc", batch, synth.seed_for(1, 500 + batch))
+        call = lambda: dh.fcos.format_data_batch(boxes, nbox, [512, 512], 20, [512, 512])[0]
+    elif family == "centernet":
+        boxes, nbox = synth.config_boxes("centernet_crowdhuman", batch, synth.seed_for(2, 500 + batch))
+        call = lambda: [dh.centernet.format_data_batch(boxes, nbox, [512, 512], 1, [512, 512], stride=4, mode="s8", box_scales=SCALES)[0]]
+    else:
+        boxes, nbox = synth.config_boxes("retina_coco", batch, synth.seed_for(3, 500 + batch))
+        call = lambda: dh.retinanet.format_data_batch(boxes, nbox, [640, 640], 80, [640, 640])[0]
+    outs = {}
+    for kern in (1, 2):
+        dh.set_option(0, _capi.DH_OPT_ENCODE_KERNEL, kern)
+        try:
+            outs[kern] = [o.clone() for o in call()]
+        finally:
+            dh.set_option(0, _capi.DH_OPT_ENCODE_KERNEL, 0)
+    assert all(torch.equal(a, b) for a, b in zip(outs[1], outs[2]))
+    assert all(torch.equal(a, b) for a, b in zip(outs[1], call()))  # and the default choice
