@@ -348,3 +348,33 @@ def test_chunk_plans_agree_at_the_bench_shapes(batch):
     assert int(res[1][2][b]) == n_pairs
     assert_close(got[:2], np.array([float(want[0]), float(want[1])]), 1e-5, what="image %d of %d" % (b, batch))
 
+
+
+@pytest.mark.parametrize("family,batch", [("fcos", 256), ("centernet", 64), ("centernet", 32)])
+def test_chunk_plans_agree_for_the_other_policies(family, batch):
+    """Same check as above for the FCOS and CenterNet policies at batch sizes where the planner picks equal chunks (FCOS-VOC
+    at 256 images: 512 chunks of 12 tiles; CenterNet-s8 stride 4 at 64 / 32 images: 18-tile chunks)."""
+    dh = _dh()
+    from densehead import _capi
+    rng = np.random.default_rng(batch)
+    if family == "fcos":
+        boxes, nbox = synth.config_boxes("fcos_voc", batch, synth.seed_for(1, 600))
+        pred = [rng.normal(-3.0, 1.0, size=(batch, 512 // s, 512 // s, 25)).astype(np.float32) for s in (8, 16, 32, 64, 128)]
+        pred = [torch.from_numpy(p).cuda() for p in pred]
+        call = lambda: dh.fcos.encode_loss_batch(boxes, nbox, [512, 512], 20, [512, 512], pred)
+    else:
+        boxes, nbox = synth.config_boxes("centernet_crowdhuman", batch, synth.seed_for(2, 600))
+        pred = torch.from_numpy(rng.normal(-3.0, 1.0, size=(batch, 128, 128, 5, 5)).astype(np.float32)).cuda()
+        call = lambda: dh.centernet.encode_loss_batch(boxes, nbox, [512, 512], 1, [512, 512], pred, stride=4, mode="s8",
+                                                      box_scales=[32, 64, 128, 256, 512])
+    res = {}
+    for tail in (1, 0):
+        dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
+        try:
+            out = call()
+        finally:
+            dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, 1)
+        res[tail] = (out[0].cpu().numpy(), out[1].cpu().numpy())
+    assert np.array_equal(res[1][0][:, 3], res[0][0][:, 3])
+    assert np.allclose(res[1][0][:, :3], res[0][0][:, :3], rtol=2e-6, atol=1e-4)
+    assert np.allclose(res[1][1][:3], res[0][1][:3], rtol=2e-6)
