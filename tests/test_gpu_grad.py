@@ -179,3 +179,31 @@ def test_centernet_gradients_against_the_reference_pinned_golden(name, mode):
     b4[:, :boxes.shape[1]] = boxes
     _, _, _, grad = dh.centernet.encode_loss_batch(b4, nbox, [256, 256], 3, [256, 256], yp, weights=W_GOLD, **kw)
     _fd_close(grad.cpu().numpy().reshape(-1)[GOLD[name + "_idx"]], GOLD[name + "_fd"], name)
+
+
+def test_gradient_does_not_depend_on_the_chunk_plan():
+    """32 COCO-shaped images: the planner picks one 18-tile chunk per CTA (DH_OPT_FUSED_TAIL = 1) or uniform 8-tile chunks
+    (= 0); the gradient of every element is the same bits either way, and so are the positive counts."""
+    import densehead as dh
+    from densehead import _capi
+    B = 32
+    boxes, nbox = synth.config_boxes("retina_coco", B, synth.seed_for(5, 700))
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7)
+    pred = []
+    for h in (80, 40, 20, 10, 5):
+        p = torch.empty((B, 9, h, h, 84), device="cuda")
+        p[..., :4].uniform_(-1, 2, generator=gen)
+        p[..., 4:].normal_(-4.595, 1.0, generator=gen)
+        pred.append(p)
+    res = {}
+    for tail in (1, 0):
+        dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, tail)
+        try:
+            pi, tot, pairs, grads = dh.retinanet.encode_loss_batch(boxes, nbox, [640, 640], 80, [640, 640], pred, weights=(1.0, 1.0))
+        finally:
+            dh.set_option(0, _capi.DH_OPT_FUSED_TAIL, 1)
+        res[tail] = (pi.clone(), pairs.clone(), [g.clone() for g in grads])
+    assert torch.equal(res[1][0][:, 3], res[0][0][:, 3]) and torch.equal(res[1][1], res[0][1])
+    assert all(torch.equal(a, b) for a, b in zip(res[1][2], res[0][2]))
+    assert torch.allclose(res[1][0][:, :3], res[0][0][:, :3], rtol=2e-6, atol=1e-4)
