@@ -203,7 +203,9 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     // for 592 CTAs, 166 us against 175-182 us with tiers of 9, 4, 2 tiles).  The largest chunk whose last wave is at least
     // 85 % full wins (the fill of the last wave IS the efficiency of such a plan); without one (128 images: 5.19 waves of 14-tile chunks) the tiers take care of the tail.
     int uniform = 0;
-    if ((h->fused_tail & 1) && a.tt.tiles_per_image > 0 && static_cast<int>(static_cast<unsigned>(h->fused_tail) >> 8) == 0) {
+    // (Not with the gradient: twice the traffic per tile halves the weight of a chunk's fixed cost, and its resolve pass sits
+    // behind a block barrier -- 64 COCO images: 643 us with two 18-tile chunks per CTA against 612-622 us with tiers.)
+    if (!kGrad && (h->fused_tail & 1) && a.tt.tiles_per_image > 0) {
         double best = 0.0;
         const int tpi = a.tt.tiles_per_image;
         for (int c = (h->fused_max_chunk == 16 ? kMaxChunkTiles : h->fused_max_chunk); c >= (min_tiles > 4 ? min_tiles : 4); --c) {
