@@ -161,6 +161,61 @@ static void plan_tiers(LossArgs<P>& a, long long grid, int ct0, bool tail, int m
     emit_tiers(a, spec, n);
 }
 
+struct PlanOpts {
+    int tail, max_chunk, chunks_per_cta;  // DH_OPT_FUSED_TAIL, DH_OPT_FUSED_MAX_CHUNK, DH_OPT_FUSED_CHUNKS_PER_CTA
+};
+// The chunk plan of one fused launch (host only; also behind dh_plan_fused_chunks for the CPU tests): fills a.tiers,
+// a.n_chunks, a.span_fine from the tile table in a.tt and the grid.
+template <class P>
+static void plan_fused(const PlanOpts& o, LossArgs<P>& a, long long grid, bool grad) {
+    const long long total = static_cast<long long>(a.tt.batch) * a.tt.tiles_per_image;
+    // Chunk size.  Uniform chunks (DH_OPT_FUSED_TAIL = 0): aim at DH_OPT_FUSED_CHUNKS_PER_CTA chunks per CTA, 4..8 tiles each
+    // (smaller chunks pay the chunk-end barriers too often, larger ones leave a tail).  Tiered (default): the tail is
+    // taken care of by the finer tiers, so the first tier can be coarse -- about half of a CTA's share of the tiles,
+    // 4..16 tiles -- which matters for small batches, where a chunk's fixed cost (GT staging, barriers) is not hidden
+    // behind other CTAs' streaming.
+    long long want;
+    a.span_fine = (o.tail >> 1) ? (o.tail >> 1) : 2;
+    // A chunk costs about 7 us whatever it holds (GT staging, pairing, resolving, the barriers) and a CTA streams at about
+    // 11 GB/s, so a chunk under ~150 KB spends more time on that than on its bytes: that is 2 tiles of RetinaNet-COCO
+    // rows (336 B), 6 of FCOS-VOC rows (100 B), all 16 of CenterNet-s8 rows (20 B) -- no tier goes below it.
+    const long long tile_bytes = static_cast<long long>(a.tt.rows_per_tile) * a.tt.ch * 4;
+    long long min_tiles = (150 * 1024 + tile_bytes - 1) / tile_bytes;
+    min_tiles = min_tiles < 1 ? 1 : (min_tiles > o.max_chunk ? o.max_chunk : min_tiles);
+    if (o.tail & 1) {
+        want = (total / grid) * 55 / 100;
+        want = want < 4 ? 4 : want;
+        want = want < min_tiles ? min_tiles : want;
+        want = want > o.max_chunk ? o.max_chunk : want;
+    } else {
+        want = total / (grid * o.chunks_per_cta);
+        want = want < 4 ? 4 : (want > 8 ? 8 : want);
+    }
+    // A small launch -- at most three chunks per CTA -- is better off with EQUAL chunks (of up to kMaxChunkTiles = 18 tiles) when
+    // their number fills whole waves of the grid: every CTA then does the same k chunks and nothing is left to balance.
+    // 32 COCO images: 576 chunks of 18 tiles for 592 CTAs, 154 us against 175-182 us with tiers of 9, 4, 2 tiles; 64 images:
+    // 1 152 chunks, 292 us against 306.  The largest chunk whose last wave is at least 85 % full wins (the fill of the last
+    // wave IS the efficiency of such a plan); four waves measured slower than tiers (128 images: 555 us against 537), and
+    // without a fitting chunk size the tiers take care of the tail.
+    int uniform = 0;
+    // (Not with the gradient: twice the traffic per tile halves the weight of a chunk's fixed cost, and its resolve pass sits
+    // behind a block barrier -- 64 COCO images: 643 us with two 18-tile chunks per CTA against 612-622 us with tiers.)
+    if (!grad && (o.tail & 1) && a.tt.tiles_per_image > 0) {
+        double best = 0.0;
+        const int tpi = a.tt.tiles_per_image;
+        for (int c = (o.max_chunk == 16 ? kMaxChunkTiles : o.max_chunk); c >= (min_tiles > 4 ? min_tiles : 4); --c) {
+            const int cpi = (tpi + c - 1) / c;
+            const long long n = static_cast<long long>(cpi) * a.tt.batch, waves = (n + grid - 1) / grid;
+            if (waves > 3) break;
+            const double fill = static_cast<double>(n) / static_cast<double>(waves * grid);
+            if (fill > best + 0.02) best = fill, uniform = (tpi + cpi - 1) / cpi;
+        }
+        if (best < 0.85) uniform = 0;
+    }
+    if (uniform) plan_tiers(a, grid, uniform, false, 1);
+    else plan_tiers(a, grid, static_cast<int>(want), (o.tail & 1) != 0, static_cast<int>(min_tiles));
+}
+
 // Fused encode+loss, stream + correct formulation (dh_fused_loss_kernel.cuh): 256-row tiles, 32 rows per warp.  One
 // launch: the kernel's last CTA reduces the chunk partials to the per-image sums and the total (and exchanges the
 // total with the peer ranks when DH_OPT_LOSS_ALLREDUCE is on).
@@ -176,49 +231,8 @@ static int launch_fused_g(dh_handle_s* h, LossArgs<P>& a, float* out_per_image, 
     DH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_loss_kernel<P, kCls, kGrad>, DH_THREADS, lay.total));
     if (per_sm < 1) per_sm = 1;
     long long grid = static_cast<long long>(h->sm_count) * per_sm;
-    // Chunk size.  Uniform chunks (DH_OPT_FUSED_TAIL = 0): aim at DH_OPT_FUSED_CHUNKS_PER_CTA chunks per CTA, 4..8 tiles each
-    // (smaller chunks pay the chunk-end barriers too often, larger ones leave a tail).  Tiered (default): the tail is
-    // taken care of by the finer tiers, so the first tier can be coarse -- about half of a CTA's share of the tiles,
-    // 4..16 tiles -- which matters for small batches, where a chunk's fixed cost (GT staging, barriers) is not hidden
-    // behind other CTAs' streaming.
-    long long want;
-    a.span_fine = (h->fused_tail >> 1) ? (h->fused_tail >> 1) : 2;
-    // A chunk costs about 7 us whatever it holds (GT staging, pairing, resolving, the barriers) and a CTA streams at about
-    // 11 GB/s, so a chunk under ~150 KB spends more time on that than on its bytes: that is 2 tiles of RetinaNet-COCO
-    // rows (336 B), 6 of FCOS-VOC rows (100 B), all 16 of CenterNet-s8 rows (20 B) -- no tier goes below it.
-    const long long tile_bytes = static_cast<long long>(a.tt.rows_per_tile) * a.tt.ch * 4;
-    long long min_tiles = (150 * 1024 + tile_bytes - 1) / tile_bytes;
-    min_tiles = min_tiles < 1 ? 1 : (min_tiles > h->fused_max_chunk ? h->fused_max_chunk : min_tiles);
-    if (h->fused_tail & 1) {
-        want = (total / grid) * 55 / 100;
-        want = want < 4 ? 4 : want;
-        want = want < min_tiles ? min_tiles : want;
-        want = want > h->fused_max_chunk ? h->fused_max_chunk : want;
-    } else {
-        want = total / (grid * h->fused_chunks_per_cta);
-        want = want < 4 ? 4 : (want > 8 ? 8 : want);
-    }
-    // A small launch -- at most three chunks per CTA (four waves of 18-tile chunks at 128 COCO images: 555 us against 537 us with tiers) -- is better off with equal chunks when their number fills whole waves of the
-    // grid: every CTA then does the same k chunks and nothing is left to balance (32 COCO images: 1 152 chunks of 9 tiles
-    // for 592 CTAs, 166 us against 175-182 us with tiers of 9, 4, 2 tiles).  The largest chunk whose last wave is at least
-    // 85 % full wins (the fill of the last wave IS the efficiency of such a plan); without one (128 images: 5.19 waves of 14-tile chunks) the tiers take care of the tail.
-    int uniform = 0;
-    // (Not with the gradient: twice the traffic per tile halves the weight of a chunk's fixed cost, and its resolve pass sits
-    // behind a block barrier -- 64 COCO images: 643 us with two 18-tile chunks per CTA against 612-622 us with tiers.)
-    if (!kGrad && (h->fused_tail & 1) && a.tt.tiles_per_image > 0) {
-        double best = 0.0;
-        const int tpi = a.tt.tiles_per_image;
-        for (int c = (h->fused_max_chunk == 16 ? kMaxChunkTiles : h->fused_max_chunk); c >= (min_tiles > 4 ? min_tiles : 4); --c) {
-            const int cpi = (tpi + c - 1) / c;
-            const long long n = static_cast<long long>(cpi) * a.tt.batch, waves = (n + grid - 1) / grid;
-            if (waves > 3) break;
-            const double fill = static_cast<double>(n) / static_cast<double>(waves * grid);
-            if (fill > best + 0.02) best = fill, uniform = (tpi + cpi - 1) / cpi;
-        }
-        if (best < 0.85) uniform = 0;
-    }
-    if (uniform) plan_tiers(a, grid, uniform, false, 1);
-    else plan_tiers(a, grid, static_cast<int>(want), (h->fused_tail & 1) != 0, static_cast<int>(min_tiles));
+    const PlanOpts po{h->fused_tail, h->fused_max_chunk, h->fused_chunks_per_cta};
+    plan_fused(po, a, grid, kGrad);
     const long long n_chunks = a.n_chunks;
     if (grid > n_chunks) grid = n_chunks;
     if (grid < 1) grid = 1;
@@ -582,6 +596,26 @@ int dh_centernet_encode_loss_grad(dh_handle_t h, const float* boxes, const int32
     const GradOut go = {w_cls, w_reg, w_cen, levels};
     return centernet_encode_loss_impl(&go, h, boxes, nbox, img_dim, batch, max_boxes, pad0, pad1, stride, n_scales, box_scales, sigma,
                                       num_classes, mode, pred, reg_mode, cls_mode, alpha, gamma, delta, out_per_image, out_total, status, stream);
+}
+
+int dh_plan_fused_chunks(int batch, int tiles_per_image, int rows_per_tile, int ch, int grid, int with_grad, int tail, int max_chunk,
+                         int32_t* out) {
+    if (batch < 0 || tiles_per_image < 0 || rows_per_tile < 1 || ch < 1 || grid < 1 || !out || max_chunk < 4 || max_chunk > 16)
+        return set_error(DH_ERR_BAD_ARG, "dh_plan_fused_chunks: bad argument");
+    LossArgs<RetinaPolicy>* a = new LossArgs<RetinaPolicy>();  // (only the tile table's sizes and the plan fields are touched)
+    memset(a, 0, sizeof(*a));
+    a->tt.batch = batch, a->tt.tiles_per_image = tiles_per_image, a->tt.rows_per_tile = rows_per_tile, a->tt.ch = ch;
+    const PlanOpts po{tail, max_chunk, 12};
+    plan_fused(po, *a, grid, with_grad != 0);
+    out[0] = a->n_tiers, out[1] = static_cast<int32_t>(a->n_chunks);
+    for (int k = 0; k < 8; ++k) {
+        const bool live = k < a->n_tiers;
+        out[2 + 4 * k + 0] = live ? a->tiers[k].image0 : 0, out[2 + 4 * k + 1] = live ? a->tiers[k].chunk_tiles : 0;
+        out[2 + 4 * k + 2] = live ? a->tiers[k].cpi : 0, out[2 + 4 * k + 3] = live ? static_cast<int32_t>(a->tiers[k].chunk0) : 0;
+    }
+    const int n = a->n_tiers;
+    delete a;
+    return n;
 }
 
 }  // extern "C"

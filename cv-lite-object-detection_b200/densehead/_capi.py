@@ -80,6 +80,7 @@ def lib():
         L.dh_box_convert.argtypes = [P, P, ctypes.c_longlong, I, P, P]
         L.dh_prepare_labels.argtypes = [P, P, P, P, P, P, I, I, I, P, P, P]
         L.dh_format_detections.argtypes = [P, P, P, P, I, I, P, P, P, P]
+        L.dh_plan_fused_chunks.argtypes = [I, I, I, I, I, I, I, I, P]
         L.dh_fcos_rectangles.argtypes = [P, P, P, P, I, I, P, P]
         L.dh_fcos_sparse_encode.argtypes = [P, P, P, P, I, I, I, I, I, ctypes.c_longlong, P, P, P, P]
         L.dh_compute_iou.argtypes = [P, P, I, P, I, P, P]

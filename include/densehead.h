@@ -95,6 +95,14 @@ int dh_plan_fcos_select(const long long* values, int n_levels, int batch, signed
                         unsigned char* lead /*[n_levels*8]*/, unsigned char* members /*[n_levels*8]*/,
                         int* chunk_first /*[n_levels+1]*/);
 
+/* Host-only (no device needed): the chunk plan dh_*_encode_loss(_grad) would use for `batch` images of
+ * `tiles_per_image` tiles (256-row tiles of `ch` floats per row) on `grid` resident CTAs, with DH_OPT_FUSED_TAIL = tail and
+ * DH_OPT_FUSED_MAX_CHUNK = max_chunk.  out[0] = tiers, out[1] = chunks in total, then per tier k (at most 8)
+ * out[2 + 4k ..] = {first image, tiles per chunk, chunks per image, id of the tier's first chunk}.  A tier ends where the
+ * next begins (the last at `batch`).  Returns the number of tiers, < 0 on a bad argument. */
+int dh_plan_fused_chunks(int batch, int tiles_per_image, int rows_per_tile, int ch, int grid, int with_grad, int tail, int max_chunk,
+                         int32_t* out /*[host] [34]*/);
+
 /* ---- target encoders ---------------------------------------------------------------------- */
 
 /* FCOS family.  Replaces format_data in FCOS/fcos.py:136-378 (mode 0), FCOS/fcos_center.py:149-279
